@@ -1,0 +1,387 @@
+"""Benchmark of the IBC EBM hot path on B200 (contract in the task statement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE.json configs[1]): block-pushing-states MLP EBM
+(pushing_states/mlp_ebm.gin: obs 2x10, act 2, width 128, depth 16, batch 512,
+256 uniform counter-examples, InfoNCE, no gradient penalty).  A step is one
+`ImplicitBCAgent.train` on one synthetic batch: negatives -> B*(N+1)-row
+energy forward -> InfoNCE -> backward -> (NCCL all-reduce) -> Adam.
+metric = energy evaluations per second over all ranks.
+
+Extra blocks in the JSON line: `roofline` (dominant kernel of the step),
+`roofline_energy_fwd` (the tcgen05 fused forward kernel timed alone),
+`dfo_inference` (IbcPolicy actions/s at N=16384, DFO 3 iterations),
+`cpu_baseline` (the oracle = CPU restatement of the reference, timed on this
+box's host cores; the TF reference itself cannot be installed offline).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+CFG = dict(name='pushing_states/mlp_ebm.gin (C2)', obs_dim=20, seq=2, act_dim=2, width=128,
+           depth=16, batch=512, num_counter_examples=256, lr=1e-3, decay_steps=100,
+           dfo_samples=16384, dfo_iterations=3)
+
+
+def fwd_flops_per_row(c=CFG):
+  d_in = c['obs_dim'] + c['act_dim']
+  return 2 * (d_in * c['width'] + c['depth'] * c['width'] ** 2 + c['width'])
+
+
+def measured_peaks():
+  p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(p):
+    try:
+      d = json.load(open(p))
+      return dict(hbm=d['hbm_gbs'], bf16=d['bf16_tflops'], bf16_sustained=d.get(
+          'bf16_tflops_sustained', d['bf16_tflops']), source='measured')
+    except Exception:
+      pass
+  return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source='fallback')
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+  Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+       'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+       'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index):
+    self.index, self.rows, self.proc = index, [], None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+          ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+           '--format=csv,noheader,nounits', '-lms', '100'],
+          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.t = threading.Thread(target=self._read, daemon=True)
+      self.t.start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([x.strip() for x in line.split(',')])
+
+  def stop(self):
+    if not self.proc:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    time.sleep(0.15)
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except Exception:
+      self.proc.kill()
+    sm, mx, reasons = [], [], set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for r in self.rows:
+      try:
+        sm.append(float(r[0])); mx.append(float(r[1]))
+        for nm, v in zip(names, r[2:6]):
+          if v.lower().startswith('active'):
+            reasons.add(nm)
+      except Exception:
+        continue
+    return {'sm_mhz': float(np.median(sm)) if sm else None,
+            'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
+            'samples': len(sm)}
+
+
+def synthetic_batch(c, batch, seed, device=None, pinned=False):
+  """obs ~ N(0,1) (z-scored), true actions ~ U[-1,1] (min-max normalised)."""
+  g = torch.Generator().manual_seed(seed)
+  half = c['obs_dim'] // c['seq'] // 2
+  obs = {'block_translation': torch.randn(batch, c['seq'], half, generator=g),
+         'effector_translation': torch.randn(batch, c['seq'], c['obs_dim'] // c['seq'] - half,
+                                             generator=g)}
+  act = torch.rand(batch, c['act_dim'], generator=g) * 2 - 1
+  if pinned:
+    obs = {k: v.pin_memory() for k, v in obs.items()}
+    act = act.pin_memory()
+  if device is not None:
+    obs = {k: v.to(device) for k, v in obs.items()}
+    act = act.to(device)
+  return obs, act
+
+
+def build_agent(c, device, seed=1):
+  from ibc_b200.ibc import specs
+  from ibc_b200.ibc.agents import ibc_agent
+  from ibc_b200.ibc.train import get_agent
+  from ibc_b200.networks.mlp_ebm import MLPEBM
+  half = c['obs_dim'] // c['seq'] // 2
+  obs_spec = {'block_translation': specs.TensorSpec((c['seq'], half)),
+              'effector_translation': specs.TensorSpec((c['seq'], c['obs_dim'] // c['seq'] - half))}
+  act_spec = specs.BoundedTensorSpec((c['act_dim'],), minimum=-1.0, maximum=1.0)
+  sampling_spec = specs.BoundedTensorSpec((c['act_dim'],), minimum=-1.1, maximum=1.1)
+  net = MLPEBM((obs_spec, act_spec), specs.TensorSpec((1,)), width=c['width'], depth=c['depth'],
+               rate=0.0, layers='ResNetPreActivation', device=device, seed=seed)
+  opt = get_agent.Adam(get_agent.ExponentialDecay(c['lr'], c['decay_steps'], 0.99))
+  agent = ibc_agent.ImplicitBCAgent(
+      time_step_spec=obs_spec, action_spec=act_spec, action_sampling_spec=sampling_spec,
+      cloning_network=net, optimizer=opt, num_counter_examples=c['num_counter_examples'],
+      fraction_langevin_samples=0.0, add_grad_penalty=False, compute_mse=True,
+      return_full_chain=True)
+  policy = None
+  from ibc_b200.ibc.agents import ibc_policy
+  policy = ibc_policy.GreedyPolicy(ibc_policy.IbcPolicy(
+      obs_spec, act_spec, sampling_spec, net, num_action_samples=c['dfo_samples'], use_dfo=True,
+      use_langevin=False))
+  return net, agent, policy
+
+
+def timed(fn, steps, barrier):
+  """CUDA-event time of `steps` calls on the current stream, barrier + sync on both sides."""
+  barrier()
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for i in range(steps):
+    fn(i)
+  e1.record()
+  torch.cuda.synchronize()
+  barrier()
+  return e0.elapsed_time(e1) / 1e3
+
+
+def run_b200(args):
+  import torch.distributed as dist
+  from ibc_b200 import _lib
+  from ibc_b200 import engine as eng
+  from ibc_b200.ibc import specs
+  c = CFG
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local)
+  device = torch.device('cuda', local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=device)
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+
+  def max_over_ranks(x):
+    if world == 1:
+      return x
+    t = torch.tensor([x], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+  net, agent, policy = build_agent(c, device)
+  # weak scaling: every rank trains on its own batch of 512 (per-replica batch fixed)
+  b, n = c['batch'], c['num_counter_examples']
+  rows = b * (n + 1)
+  nb = 4
+  dev_batches = [synthetic_batch(c, b, 100 + rank * 17 + i, device=device) for i in range(nb)]
+  host_batches = [synthetic_batch(c, b, 100 + rank * 17 + i, pinned=True) for i in range(nb)]
+  total = args.steps + args.warmup
+
+  def step_dev(i):
+    agent.train((dev_batches[i % nb], ()))
+
+  for i in range(args.warmup):
+    step_dev(i)
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  _lib.reset_launch_count()
+  t_dev = max_over_ranks(timed(step_dev, args.steps, barrier))
+  launches = _lib.launch_count()
+  clocks = sampler.stop() if rank == 0 else None
+
+  # end to end: pinned host buffers -> H2D -> step -> loss back on the host
+  losses = []
+
+  def step_e2e(i):
+    info = agent.train((host_batches[i % nb], ()))
+    losses.append(float(info.loss))          # D2H read of the step's result
+
+  for i in range(min(3, args.warmup)):
+    step_e2e(i)
+  barrier()
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  for i in range(args.steps):
+    step_e2e(i)
+  torch.cuda.synchronize()
+  t_e2e = max_over_ranks(time.perf_counter() - t0)
+  h2d = sum(v.numel() * 4 for v in host_batches[0][0].values()) + host_batches[0][1].numel() * 4
+
+  # the fused tcgen05 energy forward timed alone on the step's rows
+  obs_flat = net._flat_obs(dev_batches[0][0])
+  acts = torch.rand(rows, c['act_dim'], device=device) * 2.2 - 1.1
+  peaks = measured_peaks()
+  tf32_peak = peaks['bf16'] / 2.0
+  fwd = {}
+  for prec, label in ((_lib.PRECISION_TF32, 'tf32'), (_lib.PRECISION_FP32, 'fp32')):
+    try:
+      net.engine.set_precision(prec)
+      for _ in range(3):
+        net.engine.energy(obs_flat, acts, n + 1)
+      reps = 20 if prec == _lib.PRECISION_TF32 else 5
+      t = timed(lambda i: net.engine.energy(obs_flat, acts, n + 1), reps, lambda: None) / reps
+      fwd[label] = t
+    except Exception as ex:   # noqa: BLE001
+      fwd[label] = None
+      fwd[label + '_error'] = str(ex)[:200]
+  net.engine.set_precision(_lib.PRECISION_TF32)
+  status = net.engine.kernel_status()
+
+  # DFO policy inference (B=1, N=16384, 3 iterations), actions/s
+  ts_obs = {k: v[:1] for k, v in dev_batches[0][0].items()}
+  time_step = specs.restart(ts_obs)
+  for _ in range(3):
+    policy.action(time_step)
+  reps = 20
+  t_act = timed(lambda i: policy.action(time_step), reps, lambda: None) / reps
+
+  result = None
+  if rank == 0:
+    evals = rows * world * args.steps
+    step_flops = 3.0 * rows * fwd_flops_per_row()
+    ms = t_dev / args.steps * 1e3
+    achieved = step_flops / (t_dev / args.steps) / 1e12
+    result = {
+        'metric': 'ebm_train_energy_evals_per_s', 'value': evals / t_dev, 'unit': 'energy evals/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32 (fp32 FMA backward, tf32 tcgen05 energy forward)', 'data': 'synthetic',
+        'config': {'workload': c['name'], 'batch_per_gpu': b,
+                   'num_counter_examples': n, 'rows_per_step_per_gpu': rows, 'width': c['width'],
+                   'depth': c['depth'], 'l2': 'per-step activations (%.2f GB) exceed the 126 MB L2'
+                   % ((2 * c['depth'] // 2 + 1) * rows * c['width'] * 4 / 1e9)},
+        'train_steps_per_s': args.steps / t_dev,
+        'e2e': {'value': evals / t_e2e, 'unit': 'energy evals/s', 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': 4, 'ms_per_step': t_e2e / args.steps * 1e3,
+                'final_loss': losses[-1] if losses else None},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'roofline': {'kernel': 'train step: per-layer fp32 FMA gemm_kernel launches (fwd+bwd)',
+                     'bound': 'tensor', 'achieved': achieved, 'peak': tf32_peak,
+                     'unit': 'TFLOP/s', 'frac': achieved / tf32_peak, 'traffic': None,
+                     'peak_source': '%s bf16 burst / 2 (tf32 nominal ratio)' % peaks['source'],
+                     'flops_per_step': step_flops},
+        'roofline_energy_fwd': None,
+        'dfo_inference': {'actions_per_s': 1.0 / t_act, 'ms_per_action': t_act * 1e3,
+                          'num_action_samples': c['dfo_samples'],
+                          'iterations': c['dfo_iterations']},
+        'kernel_status': status,
+    }
+    if fwd.get('tf32'):
+      fl = rows * fwd_flops_per_row()
+      a = fl / fwd['tf32'] / 1e12
+      result['roofline_energy_fwd'] = {
+          'kernel': 'mlp_fwd_umma_kernel<128,2> (tcgen05 kind::tf32)', 'bound': 'tensor',
+          'achieved': a, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': a / tf32_peak,
+          'traffic': None, 'ms_per_launch': fwd['tf32'] * 1e3, 'rows': rows,
+          'fp32_path_ms': fwd['fp32'] * 1e3 if fwd.get('fp32') else None}
+    else:
+      result['roofline_energy_fwd'] = {k: v for k, v in fwd.items()}
+    result['cpu_baseline'] = cpu_baseline(steps=2, warmup=1)
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+  return result
+
+
+def cpu_baseline(steps, warmup, batch=512):
+  """Oracle (CPU restatement of the reference, PyTorch-CPU) train step on a
+  bounded sample of the same workload: batch `batch` of 512, everything else
+  identical.  kind = 'port' (the TF reference cannot be installed offline)."""
+  from oracle import agent as oagent
+  from oracle import mlp_ebm as omlp
+  c = CFG
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  spec = omlp.MLPSpec(c['obs_dim'], c['act_dim'], c['width'], c['depth'])
+  flat = omlp.init_params(spec, seed=1)
+  state = oagent.adam_init(flat)
+  cfg = oagent.AgentConfig(num_counter_examples=c['num_counter_examples'],
+                           fraction_langevin_samples=0.0, add_grad_penalty=False)
+  mn, mx = torch.full((c['act_dim'],), -1.1), torch.full((c['act_dim'],), 1.1)
+  g = torch.Generator().manual_seed(0)
+  n = c['num_counter_examples']
+
+  def make_energy_fn(theta):
+    def fn(obs_t, a):
+      return omlp.energy(theta, spec, obs_t, a)
+    return fn
+
+  times = []
+  for i in range(warmup + steps):
+    obs = torch.randn(batch, c['obs_dim'], generator=g)
+    act = torch.rand(batch, c['act_dim'], generator=g) * 2 - 1
+    u = torch.rand(batch, n, c['act_dim'], generator=g)
+    t0 = time.perf_counter()
+    flat, loss, _, _ = oagent.train_step(make_energy_fn, flat, state, cfg, obs, act, mn, mx, u,
+                                         c['lr'])
+    times.append(time.perf_counter() - t0)
+  t = float(np.mean(times[warmup:]))
+  rows = batch * (n + 1)
+  return {'value': rows / t, 'unit': 'energy evals/s', 'cores': cores, 'kind': 'port',
+          'sample': 'oracle train step on batch %d of %d (N=%d, W=%d, D=%d), %d timed steps, '
+                    '%.2f s/step' % (batch, c['batch'], n, c['width'], c['depth'], steps, t),
+          'seconds_per_step': t}
+
+
+def run_reference(args):
+  """--impl reference: the reference's CPU implementation of the path.  The TF
+  reference cannot be installed offline (no tensorflow / tf-agents wheels), so
+  this times the oracle port on all host cores, on rank 0 only."""
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return None
+  c = CFG
+  base = cpu_baseline(steps=max(1, min(args.steps, 5)), warmup=max(1, min(args.warmup, 2)))
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  return {
+      'impl': 'reference', 'metric': 'ebm_train_energy_evals_per_s', 'value': base['value'],
+      'unit': 'energy evals/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+      'ms_per_step': base['seconds_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': c['name'], 'batch_per_gpu': c['batch'],
+                 'num_counter_examples': c['num_counter_examples'], 'width': c['width'],
+                 'depth': c['depth']},
+      'cpu_baseline': base,
+      'e2e': {'value': base['value'], 'unit': 'energy evals/s', 'h2d_bytes_per_step': 0,
+              'd2h_bytes_per_step': 0},
+      'gpu_launches': 0,
+  }
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--warmup', type=int, default=5)
+  ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  args = ap.parse_args()
+  if args.warmup < 3 and args.impl == 'b200':
+    args.warmup = 3
+  if args.impl == 'reference':
+    res = run_reference(args)
+  else:
+    res = run_b200(args)
+  if res is not None:
+    print(json.dumps(res))
+
+
+if __name__ == '__main__':
+  main()

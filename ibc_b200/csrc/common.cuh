@@ -1,0 +1,125 @@
+// Shared host/device helpers for the ibc_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/ibc_b200.h"
+
+namespace ibc {
+
+extern std::atomic<long long> g_launch_count;
+extern thread_local char g_create_error[512];
+
+inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
+// Parameter offsets in the flat vector (see include/ibc_b200.h).
+struct Layout {
+  int O, A, W, D, nb;
+  int64_t wp, bp, we, be, count;
+  __host__ __device__ int64_t w1(int j) const { return blk(j); }
+  __host__ __device__ int64_t b1(int j) const { return blk(j) + (int64_t)W * W; }
+  __host__ __device__ int64_t w2(int j) const { return blk(j) + (int64_t)W * W + W; }
+  __host__ __device__ int64_t b2(int j) const { return blk(j) + 2 * (int64_t)W * W + W; }
+  __host__ __device__ int64_t blk(int j) const {
+    return bp + W + (int64_t)j * (2 * (int64_t)W * W + 2 * W);
+  }
+};
+
+inline Layout make_layout(const ibc_mlp_arch& a) {
+  Layout L;
+  L.O = a.obs_dim; L.A = a.act_dim; L.W = a.width; L.D = a.depth; L.nb = a.depth / 2;
+  L.wp = 0;
+  L.bp = (int64_t)(L.O + L.A) * L.W;
+  L.we = L.blk(L.nb);
+  L.be = L.we + L.W;
+  L.count = L.be + 1;
+  return L;
+}
+
+// Growable device scratch owned by a handle.  Pointers stay valid until the
+// next grow; callers carve it per call.
+struct Workspace {
+  char* base = nullptr;
+  size_t cap = 0;
+  size_t used = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (base) {
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) return e;
+      cudaFree(base);
+      base = nullptr; cap = 0;
+    }
+    size_t want = bytes + (bytes >> 3) + (1 << 20);
+    cudaError_t e = cudaMalloc((void**)&base, want);
+    if (e != cudaSuccess) return e;
+    cap = want;
+    return cudaSuccess;
+  }
+  void reset() { used = 0; }
+  template <typename T>
+  T* take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+    T* p = (T*)(base + used);
+    used += bytes;
+    return p;
+  }
+  static size_t rounded(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+};
+
+}  // namespace ibc
+
+struct ibc_handle {
+  ibc_mlp_arch arch;
+  ibc::Layout L;
+  int device = 0;
+  int precision = IBC_PRECISION_FP32;
+  int sm_count = 148;
+  const float* params = nullptr;
+  bool packed_stale = true;
+  float* packed = nullptr;        // tcgen05 operand copies of the weights
+  size_t packed_bytes = 0;
+  int* dev_status = nullptr;      // kernel-side barrier-timeout flag
+  ibc::Workspace ws;        // dense-stack passes (reset by each pass)
+  ibc::Workspace ws_outer;  // sampler / trainer scratch that outlives a pass
+  std::string err;
+};
+
+#define IBC_FAIL(h, code, ...)                                  \
+  do {                                                          \
+    char _buf[512];                                             \
+    snprintf(_buf, sizeof(_buf), __VA_ARGS__);                  \
+    if (h) (h)->err = _buf;                                     \
+    else strncpy(ibc::g_create_error, _buf, 511);               \
+    return (code);                                              \
+  } while (0)
+
+#define IBC_CUDA(h, expr)                                                     \
+  do {                                                                        \
+    cudaError_t _e = (expr);                                                  \
+    if (_e != cudaSuccess)                                                    \
+      IBC_FAIL(h, IBC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,               \
+               cudaGetErrorString(_e), __FILE__, __LINE__);                   \
+  } while (0)
+
+#define IBC_LAUNCH_CHECK(h)                                                   \
+  do {                                                                        \
+    ibc::count_launch();                                                      \
+    cudaError_t _e = cudaGetLastError();                                      \
+    if (_e != cudaSuccess)                                                    \
+      IBC_FAIL(h, IBC_ERR_CUDA, "kernel launch failed: %s (%s:%d)",           \
+               cudaGetErrorString(_e), __FILE__, __LINE__);                   \
+  } while (0)
+
+#define IBC_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != IBC_OK) return _rc; \
+  } while (0)

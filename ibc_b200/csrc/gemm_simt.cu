@@ -1,0 +1,237 @@
+// fp32 FMA GEMM + small reductions (IBC_PRECISION_FP32 path of the dense
+// layers: networks/layers/resnet.py:135-153 forward, its reverse chain and
+// weight gradients).
+#include "gemm_simt.cuh"
+
+namespace ibc {
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, LDS = 68;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
+  __shared__ __align__(16) float As[BK][LDS];
+  __shared__ __align__(16) float Bs[BK][LDS];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kc = p.k_chunk > 0 ? p.k_chunk : p.K;
+  const int kbeg = blockIdx.z * kc;
+  const int kend = min(p.K, kbeg + kc);
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;
+      int m, k;
+      if (TA) { m = e & 63; k = e >> 6; } else { k = e & 15; m = e >> 4; }
+      float v = 0.f;
+      if (m0 + m < p.M && k0 + k < kend) {
+        const int64_t idx = TA ? (int64_t)(k0 + k) * p.lda + (m0 + m)
+                               : (int64_t)(m0 + m) * p.lda + (k0 + k);
+        v = p.A[idx];
+        if (p.aop == AOP_RELU) v = fmaxf(v, 0.f);
+        else if (p.aop == AOP_GATE) v = (p.gateA[idx] > 0.f) ? v : 0.f;
+      }
+      As[k][m] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;
+      int n, k;
+      if (TB) { k = e & 15; n = e >> 4; } else { n = e & 63; k = e >> 6; }
+      float v = 0.f;
+      if (n0 + n < p.N && k0 + k < kend) {
+        const int64_t idx = TB ? (int64_t)(n0 + n) * p.ldb + (k0 + k)
+                               : (int64_t)(k0 + k) * p.ldb + (n0 + n);
+        v = p.B[idx];
+      }
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  const bool first = (blockIdx.z == 0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      float v = acc[i][j] * p.alpha;
+      if (first) {
+        if (p.bias) v += p.bias[n];
+        if (p.rowbias) v += p.rowbias[(int64_t)(m / p.rows_per_group) * p.ldrb + n];
+      }
+      if (p.gateC) v = (p.gateC[(int64_t)m * p.ldgc + n] > 0.f) ? v : 0.f;
+      if (first && p.res) v += p.res[(int64_t)m * p.ldres + n];
+      float* c = p.C + (int64_t)m * p.ldc + n;
+      if (p.atomic) atomicAdd(c, v); else *c = v;
+    }
+  }
+}
+
+__global__ void rowdot_kernel(const float* __restrict__ X, int64_t ldx,
+                              const float* __restrict__ v, const float* __restrict__ b,
+                              int64_t R, int W, float* __restrict__ E) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  float s = 0.f;
+  for (int w = lane; w < W; w += 32) s = fmaf(X[r * ldx + w], v[w], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) E[r] = s + (b ? b[0] : 0.f);
+}
+
+__global__ void rowfill_kernel(const float* __restrict__ v, const float* __restrict__ scale,
+                               int64_t R, int W, float* __restrict__ G) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * W) return;
+  const int64_t r = i / W;
+  const int w = (int)(i - r * W);
+  G[i] = (scale ? scale[r] : 1.f) * v[w];
+}
+
+// grid (ceil(N/32), row_slices); block (32, 8)
+__global__ void colsum_kernel(const float* __restrict__ X, int64_t ldx, int64_t M, int N,
+                              const float* __restrict__ d, float* __restrict__ out) {
+  __shared__ float part[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const int64_t rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per;
+  const int64_t r1 = min(M, r0 + rows_per);
+  float s = 0.f;
+  if (n < N)
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8)
+      s = fmaf(X[r * ldx + n], d ? d[r] : 1.f, s);
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+    atomicAdd(out + n, t);
+  }
+}
+
+__global__ void groupsum_kernel(const float* __restrict__ X, int64_t B, int64_t n, int W,
+                                float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * W) return;
+  const int64_t b = i / W;
+  const int w = (int)(i - b * W);
+  const float* x = X + b * n * W + w;
+  float s = 0.f;
+  for (int64_t k = 0; k < n; ++k) s += x[k * W];
+  out[i] = s;
+}
+
+__global__ void sum_kernel(const float* __restrict__ d, int64_t R, float* __restrict__ out) {
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < R;
+       i += (int64_t)gridDim.x * blockDim.x)
+    s += d[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+}  // namespace
+
+int gemm(ibc_handle* h, const GemmP& p, bool ta, bool tb, cudaStream_t s) {
+  if (p.M <= 0 || p.N <= 0) return IBC_OK;
+  const int kc = p.k_chunk > 0 ? p.k_chunk : p.K;
+  const int splits = p.K > 0 ? (p.K + kc - 1) / kc : 1;
+  if (splits > 1 && !p.atomic)
+    IBC_FAIL(h, IBC_ERR_INVALID, "gemm: split-K requires atomic accumulation");
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, splits);
+  if (grid.y > 65535u) IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "gemm: M=%d too large", p.M);
+  if (ta && tb) gemm_kernel<true, true><<<grid, 256, 0, s>>>(p);
+  else if (ta) gemm_kernel<true, false><<<grid, 256, 0, s>>>(p);
+  else if (tb) gemm_kernel<false, true><<<grid, 256, 0, s>>>(p);
+  else gemm_kernel<false, false><<<grid, 256, 0, s>>>(p);
+  IBC_LAUNCH_CHECK(h);
+  return IBC_OK;
+}
+
+int rowdot(ibc_handle* h, const float* X, int64_t ldx, const float* v, const float* b,
+           int64_t R, int W, float* E, cudaStream_t s) {
+  if (R <= 0) return IBC_OK;
+  const int wpb = 8;
+  rowdot_kernel<<<(unsigned)((R + wpb - 1) / wpb), wpb * 32, 0, s>>>(X, ldx, v, b, R, W, E);
+  IBC_LAUNCH_CHECK(h);
+  return IBC_OK;
+}
+
+int rowfill(ibc_handle* h, const float* v, const float* scale, int64_t R, int W, float* G,
+            cudaStream_t s) {
+  if (R <= 0) return IBC_OK;
+  const int64_t tot = R * W;
+  rowfill_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(v, scale, R, W, G);
+  IBC_LAUNCH_CHECK(h);
+  return IBC_OK;
+}
+
+static int colsum_launch(ibc_handle* h, const float* X, int64_t ldx, int64_t M, int N,
+                         const float* d, float* out, cudaStream_t s) {
+  if (M <= 0 || N <= 0) return IBC_OK;
+  int slices = (int)((M + 511) / 512);
+  if (slices < 1) slices = 1;
+  if (slices > 1024) slices = 1024;
+  dim3 grid((N + 31) / 32, slices), block(32, 8);
+  colsum_kernel<<<grid, block, 0, s>>>(X, ldx, M, N, d, out);
+  IBC_LAUNCH_CHECK(h);
+  return IBC_OK;
+}
+
+int colsum_add(ibc_handle* h, const float* X, int64_t ldx, int64_t M, int N, float* out,
+               cudaStream_t s) {
+  return colsum_launch(h, X, ldx, M, N, nullptr, out, s);
+}
+
+int wcolsum_add(ibc_handle* h, const float* X, int64_t ldx, const float* d, int64_t R, int W,
+                float* out, cudaStream_t s) {
+  return colsum_launch(h, X, ldx, R, W, d, out, s);
+}
+
+int groupsum(ibc_handle* h, const float* X, int64_t B, int64_t n, int W, float* out,
+             cudaStream_t s) {
+  if (B <= 0) return IBC_OK;
+  const int64_t tot = B * W;
+  groupsum_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(X, B, n, W, out);
+  IBC_LAUNCH_CHECK(h);
+  return IBC_OK;
+}
+
+int sum_add(ibc_handle* h, const float* d, int64_t R, float* out, cudaStream_t s) {
+  if (R <= 0) return IBC_OK;
+  int blocks = (int)((R + 255) / 256);
+  if (blocks > 256) blocks = 256;
+  sum_kernel<<<blocks, 256, 0, s>>>(d, R, out);
+  IBC_LAUNCH_CHECK(h);
+  return IBC_OK;
+}
+
+}  // namespace ibc

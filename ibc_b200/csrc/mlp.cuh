@@ -1,0 +1,59 @@
+// Dense-stack passes of the MLPEBM (networks/mlp_ebm.py:72-96,
+// networks/layers/resnet.py:135-153), composed per layer for the fp32 path and
+// dispatched to the fused tcgen05 kernels for IBC_PRECISION_TF32.
+#pragma once
+
+#include "common.cuh"
+
+namespace ibc {
+
+// Saved state of one forward over R rows (all device pointers into the
+// handle's workspace): H[j] (j <= nb) is the residual stream entering block j
+// (H[nb] feeds Dense(1)); V[j] is block j's hidden pre-activation.
+struct FwdSave {
+  float* hp = nullptr;   // [B, W]  obs . Wp[:O] + bp (hoisted per observation)
+  float* H = nullptr;    // [(nb+1), R, W]
+  float* V = nullptr;    // [nb, R, W]
+  int64_t R = 0;
+  float* Hj(int j, int W) const { return H + (int64_t)j * R * W; }
+  float* Vj(int j, int W) const { return V + (int64_t)j * R * W; }
+};
+
+// Reverse-chain state: G[j] = dE/dH[j] (j <= nb), U[j] = masked dE/dV[j].
+struct RevSave {
+  float* G = nullptr;    // [(nb+1), R, W]
+  float* U = nullptr;    // [nb, R, W]
+  int64_t R = 0;
+  float* Gj(int j, int W) const { return G + (int64_t)j * R * W; }
+  float* Uj(int j, int W) const { return U + (int64_t)j * R * W; }
+};
+
+size_t fwd_save_bytes(const Layout& L, int64_t B, int64_t R);
+void carve_fwd_save(ibc_handle* h, int64_t B, int64_t R, FwdSave* out);
+
+// fp32 path --------------------------------------------------------------
+// E[R]; when `save` is non-null its buffers are filled, otherwise scratch
+// buffers are carved from the workspace (which the caller must have reserved).
+int mlp_forward_fp32(ibc_handle* h, const float* obs, int64_t B, const float* act,
+                     int64_t n, float* E, FwdSave* save, cudaStream_t s);
+// dE/dact [R, A] from a saved forward; row_scale (nullable) multiplies the
+// output cotangent per row (apply_exp).  rev (nullable) keeps G/U.
+int mlp_reverse_fp32(ibc_handle* h, const FwdSave& f, const float* row_scale,
+                     float* dEda, RevSave* rev, cudaStream_t s);
+// E and dE/dact in one call (workspace reserved and carved inside).
+int mlp_energy_dact_fp32(ibc_handle* h, const float* obs, int64_t B, const float* act,
+                         int64_t n, float* E, float* dEda, bool apply_exp, cudaStream_t s);
+
+// Dispatchers honouring h->precision ---------------------------------------
+int mlp_energy(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
+               float* E, cudaStream_t s);
+int mlp_energy_dact(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
+                    float* E, float* dEda, bool apply_exp, cudaStream_t s);
+
+// tcgen05 path (mlp_umma.cu) ---------------------------------------------
+bool umma_supported(const Layout& L);
+int umma_pack_params(ibc_handle* h, cudaStream_t s);
+int mlp_energy_umma(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
+                    float* E, float* dEda, bool apply_exp, cudaStream_t s);
+
+}  // namespace ibc

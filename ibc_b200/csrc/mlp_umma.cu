@@ -1,0 +1,540 @@
+// Layer-fused MLPEBM energy kernels on tcgen05 (kind::tf32, fp32 accumulate in
+// tensor memory) -- the IBC_PRECISION_TF32 path of
+//   networks/mlp_ebm.py:72-96 + networks/layers/resnet.py:135-153 (forward)
+//   ibc/agents/mcmc.py:161-191 (dE/dact, reverse chain)
+//
+// One persistent CTA per SM walks groups of NT row tiles (128 rows each).  The
+// residual stream h of a tile never leaves tensor memory: the second Dense of
+// every block accumulates straight onto it (D_h += relu(v) . W2), and the
+// biases are applied when the epilogue reads it (cumulative-bias vectors
+// precomputed at pack time).  Weights are pre-packed into the UMMA operand
+// layout (umma.cuh) and streamed from L2 in 16 KB K-slices through a
+// shared-memory ring by the TMA engine (cp.async.bulk + mbarrier tx-count).
+//
+// Warp roles: 4*NT epilogue warps (warpgroup t owns tile t: TMEM -> registers
+// -> bias/ReLU -> next A operand in shared memory), 1 producer warp (bulk
+// copies), 1 MMA warp (single elected thread issues tcgen05.mma / commit).
+// With NT = 2 the MMA of one tile overlaps the epilogue of the other and each
+// weight slice is read once per 256 rows.
+#include "gemm_simt.cuh"
+#include "mlp.cuh"
+#include "ops.cuh"
+#include "umma.cuh"
+
+namespace ibc {
+
+using namespace umma;
+
+namespace {
+
+constexpr int kSlots = 5;
+constexpr int kSliceBytes = 16384;
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Offsets (in floats) inside the packed operand buffer.
+struct PackedLayout {
+  int W, nb, KP, AP;
+  int64_t fwd_p;     // [KP/4][W][4]           act rows of Wp (B operand of step 0)
+  int64_t fwd_l;     // 2*nb matrices [W/4][W][4]: W1_0, W2_0, W1_1, ...
+  int64_t rev_l;     // 2*nb matrices: W2_{nb-1}^T, W1_{nb-1}^T, ..., W2_0^T, W1_0^T
+  int64_t rev_p;     // [W/4][AP][4]           Wp act rows, B operand of dE/dact
+  int64_t vecs;      // [(2nb+1)][W] epilogue bias vectors, then we[W], be, pad
+  int64_t total;
+};
+
+inline PackedLayout make_packed_layout(const Layout& L) {
+  PackedLayout p;
+  p.W = L.W; p.nb = L.nb;
+  p.KP = round_up(L.A, 8);
+  p.AP = round_up(L.A, 16);
+  const int64_t WW = (int64_t)L.W * L.W;
+  p.fwd_p = 0;
+  p.fwd_l = p.fwd_p + (int64_t)L.W * p.KP;
+  p.rev_l = p.fwd_l + 2 * L.nb * WW;
+  p.rev_p = p.rev_l + 2 * L.nb * WW;
+  p.vecs = p.rev_p + (int64_t)L.W * p.AP;
+  p.total = p.vecs + (int64_t)(2 * L.nb + 2) * L.W + 4;
+  return p;
+}
+
+__global__ void pack_kernel(const float* __restrict__ P, Layout L, PackedLayout pl,
+                            float* __restrict__ out) {
+  const int W = L.W;
+  const int64_t WW = (int64_t)W * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pl.total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (i < pl.fwd_l) {                    // step-0 operand: [KP/4][W][4]
+      const int64_t e = i - pl.fwd_p;
+      const int kq = (int)(e & 3), n = (int)((e >> 2) % W), kc = (int)((e >> 2) / W);
+      const int k = kc * 4 + kq;
+      v = (k < L.A) ? P[L.wp + (int64_t)(L.O + k) * W + n] : 0.f;
+    } else if (i < pl.rev_l) {             // forward W x W operands
+      const int64_t e = i - pl.fwd_l;
+      const int m = (int)(e / WW);         // 0: W1_0, 1: W2_0, ...
+      const int64_t r = e - (int64_t)m * WW;
+      const int kq = (int)(r & 3), n = (int)((r >> 2) % W), kc = (int)((r >> 2) / W);
+      const int k = kc * 4 + kq;
+      const int j = m >> 1;
+      const int64_t base = (m & 1) ? L.w2(j) : L.w1(j);
+      v = P[base + (int64_t)k * W + n];
+    } else if (i < pl.rev_p) {             // reverse operands (transposed use)
+      const int64_t e = i - pl.rev_l;
+      const int m = (int)(e / WW);         // 0: W2_{nb-1}, 1: W1_{nb-1}, 2: W2_{nb-2}, ...
+      const int64_t r = e - (int64_t)m * WW;
+      const int oq = (int)(r & 3), irow = (int)((r >> 2) % W), oc = (int)((r >> 2) / W);
+      const int o = oc * 4 + oq;
+      const int j = L.nb - 1 - (m >> 1);
+      const int64_t base = (m & 1) ? L.w1(j) : L.w2(j);
+      v = P[base + (int64_t)irow * W + o];
+    } else if (i < pl.vecs) {              // dE/dact operand: [W/4][AP][4]
+      const int64_t e = i - pl.rev_p;
+      const int wq = (int)(e & 3), a = (int)((e >> 2) % pl.AP), wc = (int)((e >> 2) / pl.AP);
+      const int w = wc * 4 + wq;
+      v = (a < L.A) ? P[L.wp + (int64_t)(L.O + a) * W + w] : 0.f;
+    } else {
+      const int64_t e = i - pl.vecs;
+      const int s = (int)(e / W), w = (int)(e % W);
+      if (s == 0) {
+        v = 0.f;                            // bp is folded into the hoisted obs projection
+      } else if (s <= 2 * L.nb) {
+        if (s & 1) {
+          v = P[L.b1((s - 1) >> 1) + w];
+        } else {                            // cumulative b2 of blocks 0 .. s/2-1
+          float c = 0.f;
+          for (int j = 0; j < (s >> 1); ++j) c += P[L.b2(j) + w];
+          v = c;
+        }
+      } else if (s == 2 * L.nb + 1) {
+        v = P[L.we + w];
+      } else {
+        v = (w == 0) ? P[L.be] : 0.f;
+      }
+    }
+    out[i] = v;
+  }
+}
+
+struct FwdParams {
+  const float* act;      // [R, A]
+  const float* hp;       // [B, W]
+  const float* packed;
+  float* E;              // [R]
+  int64_t R, n_per_obs;
+  int nb, A, KP;
+  int64_t off_fwd_p, off_fwd_l, off_vecs;
+  int* status;
+  int num_groups;
+};
+
+template <int W, int NT>
+struct FwdSmem {
+  static constexpr int kABytes = 128 * W * 4;
+  static constexpr int kSliceK = kSliceBytes / (W * 4);      // K elements per ring slot
+  static constexpr int kSlicesPerLayer = W / kSliceK;
+  static constexpr int kStepsPerSlice = kSliceK / 8;
+  static constexpr int kThreads = (4 * NT + 2) * 32;
+  static size_t bytes(int nb) {
+    return (size_t)NT * kABytes + (size_t)kSlots * kSliceBytes + (size_t)(2 * nb + 2) * W * 4 +
+           16 + 256;
+  }
+};
+
+// 32 accumulator columns of one row: + bias, ReLU, write the 8 operand chunks.
+template <bool kRelu>
+__device__ __forceinline__ void emit_chunks(const uint32_t (&v)[32], const float* __restrict__ bias,
+                                            float4* __restrict__ a_tile, int c32, int row) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + c32 * 32 + q * 4);
+    float4 o;
+    o.x = __uint_as_float(v[q * 4 + 0]) + b.x;
+    o.y = __uint_as_float(v[q * 4 + 1]) + b.y;
+    o.z = __uint_as_float(v[q * 4 + 2]) + b.z;
+    o.w = __uint_as_float(v[q * 4 + 3]) + b.w;
+    if (kRelu) {
+      o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+    }
+    a_tile[(c32 * 8 + q) * 128 + row] = o;
+  }
+}
+
+template <int W, int NT>
+__global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdParams p) {
+  using S = FwdSmem<W, NT>;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* a_base = smem;
+  unsigned char* ring = smem + NT * S::kABytes;
+  float* vecs = reinterpret_cast<float*>(ring + kSlots * kSliceBytes);
+  const int nvec = 2 * p.nb + 2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(vecs + (size_t)nvec * W + 4);
+  uint64_t* a_ready = bars;                 // [NT]
+  uint64_t* d_ready = bars + NT;            // [NT]
+  uint64_t* w_full = bars + 2 * NT;         // [kSlots]
+  uint64_t* w_empty = bars + 2 * NT + kSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NT + 2 * kSlots);
+  __shared__ int s_abort;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int nsteps = 2 * p.nb + 1;
+
+  if (tid == 0) {
+    s_abort = 0;
+    for (int t = 0; t < NT; ++t) { mbar_init(&a_ready[t], 128); mbar_init(&d_ready[t], 1); }
+    for (int s = 0; s < kSlots; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    fence_mbar_init();
+  }
+  for (int i = tid; i < nvec * W + 4; i += S::kThreads) vecs[i] = p.packed[p.off_vecs + i];
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  volatile int* abort_flag = &s_abort;
+  const float* we = vecs + (size_t)(2 * p.nb + 1) * W;
+  const float be = vecs[(size_t)nvec * W];
+
+  if (warp < 4 * NT) {
+    // ===================== epilogue warpgroup t ==============================
+    const int t = warp >> 2;
+    const int row = tid & 127;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t col_h = (uint32_t)(t * 2 * W), col_v = (uint32_t)(t * 2 * W + W);
+    float4* a_tile = reinterpret_cast<float4*>(a_base + t * S::kABytes);
+    uint32_t ph_d = 0;
+    for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+      const int64_t r = ((int64_t)g * NT + t) * 128 + row;
+      const bool valid = r < p.R;
+      // step-0 A operand: this row's action, zero padded to KP
+      for (int c = 0; c < p.KP / 4; ++c) {
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+          const float* a = p.act + r * p.A;
+          const int k = c * 4;
+          if (k + 0 < p.A) o.x = a[k + 0];
+          if (k + 1 < p.A) o.y = a[k + 1];
+          if (k + 2 < p.A) o.z = a[k + 2];
+          if (k + 3 < p.A) o.w = a[k + 3];
+        }
+        a_tile[c * 128 + row] = o;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&a_ready[t]);
+      const float* hp_row = p.hp + (valid ? (r / p.n_per_obs) : 0) * W;
+      for (int i = 0; i < nsteps; ++i) {
+        mbar_wait(&d_ready[t], ph_d, abort_flag, p.status, 100 + i);
+        ph_d ^= 1;
+        tc_fence_after();
+        const bool is_h = (i & 1) == 0;
+        const uint32_t taddr = tmem_base + lane_off + (is_h ? col_h : col_v);
+        const float* bias = vecs + (size_t)i * W;
+        if (i == nsteps - 1) {
+          // Dense(1): E = (h + cb) . we + be   (mlp_ebm.py:91-94)
+          float e = 0.f;
+#pragma unroll 1
+          for (int c32 = 0; c32 < W / 32; ++c32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c32 * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              float x = __uint_as_float(v[q]) + bias[c32 * 32 + q];
+              if (i == 0) x += hp_row[c32 * 32 + q];
+              e = fmaf(x, we[c32 * 32 + q], e);
+            }
+          }
+          if (valid) p.E[r] = e + be;
+          tc_fence_before();
+        } else {
+#pragma unroll 1
+          for (int c32 = 0; c32 < W / 32; ++c32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c32 * 32, v);
+            tmem_ld_wait();
+            if (i == 0) {
+              // h0 = act . Wp[O:] + (obs . Wp[:O] + bp); keep it in tensor memory
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 hv = *reinterpret_cast<const float4*>(hp_row + c32 * 32 + q * 4);
+                v[q * 4 + 0] = __float_as_uint(__uint_as_float(v[q * 4 + 0]) + hv.x);
+                v[q * 4 + 1] = __float_as_uint(__uint_as_float(v[q * 4 + 1]) + hv.y);
+                v[q * 4 + 2] = __float_as_uint(__uint_as_float(v[q * 4 + 2]) + hv.z);
+                v[q * 4 + 3] = __float_as_uint(__uint_as_float(v[q * 4 + 3]) + hv.w);
+              }
+              tmem_st32(taddr + c32 * 32, v);
+            }
+            emit_chunks<true>(v, bias, a_tile, c32, row);
+          }
+          if (i == 0) tmem_st_wait();
+          tc_fence_before();
+          fence_proxy_async_smem();
+          mbar_arrive(&a_ready[t]);
+        }
+      }
+    }
+  } else if (warp == 4 * NT) {
+    // ===================== producer: weight slices via bulk copy ==============
+    if (lane == 0) {
+      uint32_t q = 0;
+      for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+        for (int i = 0; i < nsteps; ++i) {
+          const int nsl = (i == 0) ? (p.KP + S::kSliceK - 1) / S::kSliceK : S::kSlicesPerLayer;
+          const float* src =
+              (i == 0) ? p.packed + p.off_fwd_p : p.packed + p.off_fwd_l + (int64_t)(i - 1) * W * W;
+          for (int s = 0; s < nsl; ++s, ++q) {
+            const int ke = (i == 0) ? min(S::kSliceK, p.KP - s * S::kSliceK) : S::kSliceK;
+            const uint32_t bytes = (uint32_t)(W * ke * 4);
+            const int slot = q % kSlots;
+            const uint32_t ph = (q / kSlots) & 1;
+            mbar_wait(&w_empty[slot], ph ^ 1, abort_flag, p.status, 200 + i);
+            mbar_arrive_expect_tx(&w_full[slot], bytes);
+            bulk_g2s(ring + slot * kSliceBytes, src + (int64_t)s * (kSliceBytes / 4), bytes,
+                     &w_full[slot]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== MMA issuer ==========================================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(128, W);
+      const uint32_t a_lbo = 128 * 16, b_lbo = W * 16, sbo = 128;
+      uint32_t q = 0;
+      uint32_t ph_a[NT];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) ph_a[t] = 0;
+      for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+        for (int i = 0; i < nsteps; ++i) {
+          const int nsl = (i == 0) ? (p.KP + S::kSliceK - 1) / S::kSliceK : S::kSlicesPerLayer;
+          const bool to_h = (i & 1) == 0;
+          const uint32_t acc0 = (to_h && i > 0) ? 1u : 0u;
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            mbar_wait(&a_ready[t], ph_a[t], abort_flag, p.status, 300 + i);
+            ph_a[t] ^= 1;
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(t * 2 * W + (to_h ? 0 : W));
+            const uint32_t a_addr = smem_u32(a_base + t * S::kABytes);
+            for (int s = 0; s < nsl; ++s) {
+              const uint32_t qq = q + s;
+              const int slot = qq % kSlots;
+              mbar_wait(&w_full[slot], (qq / kSlots) & 1, abort_flag, p.status, 400 + i);
+              const uint32_t b_addr = smem_u32(ring + slot * kSliceBytes);
+              const int ke = (i == 0) ? min(S::kSliceK, p.KP - s * S::kSliceK) : S::kSliceK;
+              const int kps = ke / 8;
+              for (int ks = 0; ks < kps; ++ks) {
+                // k-step (8 elements = 2 chunks) within the layer
+                const int kk = s * S::kStepsPerSlice + ks;
+                const uint64_t ad = smem_desc(a_addr + (uint32_t)kk * 2 * a_lbo, a_lbo, sbo);
+                const uint64_t bd = smem_desc(b_addr + (uint32_t)ks * 2 * b_lbo, b_lbo, sbo);
+                mma_tf32_ss(d_tmem, ad, bd, idesc, (acc0 | (uint32_t)(kk > 0)));
+              }
+              if (t == NT - 1) mma_commit(&w_empty[slot]);
+            }
+            mma_commit(&d_ready[t]);
+          }
+          q += nsl;
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------
+// Self test: one 128 x N x K tile through the same operand layout.
+// ---------------------------------------------------------------------------
+__global__ void pack_rows_kernel(const float* __restrict__ X, int rows, int K,
+                                 float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * K) return;
+  const int kq = i & 3, r = (i >> 2) % rows, kc = (i >> 2) / rows;
+  out[i] = X[(int64_t)r * K + kc * 4 + kq];
+}
+
+__global__ void __launch_bounds__(160, 1)
+umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bpacked, int N, int K,
+                     int mode, float* __restrict__ D, int* status) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  float4* a_tile = reinterpret_cast<float4*>(smem);                       // [K/4][128]
+  unsigned char* b_tile = smem + 128 * K * 4;                             // [K/4][N][16B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_tile + (size_t)N * K * 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  __shared__ int s_abort;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    s_abort = 0;
+    mbar_init(&bars[0], 1);   // B landed
+    mbar_init(&bars[1], 1);   // MMA done
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  volatile int* abort_flag = &s_abort;
+  const uint32_t a_col = 256;   // tensor-memory copy of A for mode 1
+
+  if (warp < 4) {
+    const int row = tid;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    if (mode == 0) {
+      for (int c = 0; c < K / 4; ++c)
+        a_tile[c * 128 + row] = *reinterpret_cast<const float4*>(A + (int64_t)row * K + c * 4);
+      fence_proxy_async_smem();
+    } else {
+      for (int c32 = 0; c32 < K / 32; ++c32) {
+        uint32_t v[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(A[(int64_t)row * K + c32 * 32 + q]);
+        tmem_st32(tmem_base + lane_off + a_col + c32 * 32, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+    }
+  } else if (lane == 0) {
+    mbar_arrive_expect_tx(&bars[0], (uint32_t)(N * K * 4));
+    bulk_g2s(b_tile, Bpacked, (uint32_t)(N * K * 4), &bars[0]);
+  }
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 4 && lane == 0) {
+    mbar_wait(&bars[0], 0, abort_flag, status, 1);
+    const uint32_t idesc = idesc_tf32(128, N);
+    const uint32_t a_lbo = 128 * 16, b_lbo = (uint32_t)N * 16, sbo = 128;
+    for (int ks = 0; ks < K / 8; ++ks) {
+      const uint64_t bd = smem_desc(smem_u32(b_tile) + (uint32_t)ks * 2 * b_lbo, b_lbo, sbo);
+      if (mode == 0) {
+        const uint64_t ad = smem_desc(smem_u32(a_tile) + (uint32_t)ks * 2 * a_lbo, a_lbo, sbo);
+        mma_tf32_ss(tmem_base, ad, bd, idesc, ks > 0);
+      } else {
+        mma_tf32_ts(tmem_base, tmem_base + a_col + ks * 8, bd, idesc, ks > 0);
+      }
+    }
+    mma_commit(&bars[1]);
+  }
+  __syncwarp();
+  if (warp < 4) {
+    mbar_wait(&bars[1], 0, abort_flag, status, 2);
+    tc_fence_after();
+    const int row = tid;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    for (int c16 = 0; c16 < N / 16; ++c16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + lane_off + c16 * 16, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 16; ++q) D[(int64_t)row * N + c16 * 16 + q] = __uint_as_float(v[q]);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+template <int W, int NT>
+int launch_fwd(ibc_handle* h, const FwdParams& p, cudaStream_t s) {
+  using S = FwdSmem<W, NT>;
+  const size_t smem = S::bytes(p.nb);
+  if (smem > 227 * 1024)
+    IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "tcgen05 forward: depth %d needs %zu B of shared memory",
+             2 * p.nb, smem);
+  IBC_CUDA(h, cudaFuncSetAttribute(mlp_fwd_umma_kernel<W, NT>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = p.num_groups < h->sm_count ? p.num_groups : h->sm_count;
+  mlp_fwd_umma_kernel<W, NT><<<grid, S::kThreads, smem, s>>>(p);
+  IBC_LAUNCH_CHECK(h);
+  return IBC_OK;
+}
+
+}  // namespace
+
+bool umma_supported(const Layout& L) {
+  return (L.W == 128 || L.W == 256) && L.nb >= 1 && L.A >= 1 && L.A <= 32 && L.O >= 1;
+}
+
+int umma_pack_params(ibc_handle* h, cudaStream_t s) {
+  const PackedLayout pl = make_packed_layout(h->L);
+  if (!h->packed) {
+    IBC_CUDA(h, cudaMalloc((void**)&h->packed, (size_t)pl.total * 4));
+    h->packed_bytes = (size_t)pl.total * 4;
+  }
+  pack_kernel<<<296, 256, 0, s>>>(h->params, h->L, pl, h->packed);
+  IBC_LAUNCH_CHECK(h);
+  h->packed_stale = false;
+  return IBC_OK;
+}
+
+int mlp_energy_umma(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
+                    float* E, float* dEda, bool apply_exp, cudaStream_t s) {
+  const Layout& L = h->L;
+  if (!umma_supported(L))
+    IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "tcgen05 path supports width 128/256, act_dim <= 32");
+  if (dEda) {
+    // The fused reverse chain is not built yet: dE/dact runs on the fp32 path.
+    return mlp_energy_dact_fp32(h, obs, B, act, n, E, dEda, apply_exp, s);
+  }
+  if (h->packed_stale) IBC_TRY(umma_pack_params(h, s));
+  const PackedLayout pl = make_packed_layout(L);
+  const int64_t R = B * n;
+  IBC_CUDA(h, h->ws.reserve(Workspace::rounded((size_t)B * L.W * 4)));
+  h->ws.reset();
+  float* hp = h->ws.take<float>((size_t)B * L.W);
+  {  // hoisted observation projection (fp32): hp = obs . Wp[:O] + bp
+    GemmP g;
+    g.A = obs; g.lda = L.O; g.B = h->params + L.wp; g.ldb = L.W; g.C = hp; g.ldc = L.W;
+    g.bias = h->params + L.bp; g.M = (int)B; g.N = L.W; g.K = L.O;
+    IBC_TRY(gemm(h, g, false, false, s));
+  }
+  FwdParams p;
+  p.act = act; p.hp = hp; p.packed = h->packed; p.E = E; p.R = R; p.n_per_obs = n;
+  p.nb = L.nb; p.A = L.A; p.KP = pl.KP;
+  p.off_fwd_p = pl.fwd_p; p.off_fwd_l = pl.fwd_l; p.off_vecs = pl.vecs;
+  p.status = h->dev_status;
+  if (L.W == 128) {
+    p.num_groups = (int)((R + 255) / 256);
+    IBC_TRY((launch_fwd<128, 2>(h, p, s)));
+  } else {
+    p.num_groups = (int)((R + 127) / 128);
+    IBC_TRY((launch_fwd<256, 1>(h, p, s)));
+  }
+  return IBC_OK;
+}
+
+int umma_selftest(const float* A, const float* Bt, int N, int K, int mode, float* D,
+                  int* status_host, cudaStream_t s) {
+  ibc_handle* h = nullptr;
+  if (N < 16 || N > 256 || (N % 16) || K < 8 || K > 128 || (K % 8) || (mode == 1 && (K % 32)))
+    IBC_FAIL(h, IBC_ERR_INVALID, "umma_selftest: need 16<=N<=256 (x16), 8<=K<=128 (x8; x32 for mode 1)");
+  float* bp = nullptr;
+  int* st = nullptr;
+  IBC_CUDA(h, cudaMalloc((void**)&bp, (size_t)N * K * 4));
+  IBC_CUDA(h, cudaMalloc((void**)&st, sizeof(int)));
+  IBC_CUDA(h, cudaMemsetAsync(st, 0, sizeof(int), s));
+  pack_rows_kernel<<<(N * K + 255) / 256, 256, 0, s>>>(Bt, N, K, bp);
+  count_launch();
+  const size_t smem = (size_t)128 * K * 4 + (size_t)N * K * 4 + 64;
+  IBC_CUDA(h, cudaFuncSetAttribute(umma_selftest_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  umma_selftest_kernel<<<1, 160, smem, s>>>(A, bp, N, K, mode, D, st);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  int st_host = -1;
+  if (e == cudaSuccess) e = cudaMemcpy(&st_host, st, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(bp);
+  cudaFree(st);
+  if (status_host) *status_host = st_host;
+  if (e != cudaSuccess) IBC_FAIL(h, IBC_ERR_CUDA, "umma_selftest: %s", cudaGetErrorString(e));
+  return IBC_OK;
+}
+
+}  // namespace ibc

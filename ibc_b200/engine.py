@@ -1,0 +1,328 @@
+"""Torch-facing wrapper of one `ibc_handle` (include/ibc_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every number is
+produced by the CUDA library.  All tensors must be CUDA, contiguous, fp32
+(fp64 for DFO uniforms).  Nothing falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from ibc_b200 import _lib
+from ibc_b200._lib import LangevinCfg, LossCfg, MlpArch
+
+
+def _ptr(t: Optional[torch.Tensor]):
+  return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _check_f32(t: torch.Tensor, name: str):
+  if not t.is_cuda:
+    raise ValueError('%s must be a CUDA tensor (no CPU fallback)' % name)
+  if t.dtype != torch.float32:
+    raise ValueError('%s must be float32, got %s' % (name, t.dtype))
+  if not t.is_contiguous():
+    raise ValueError('%s must be contiguous' % name)
+
+
+def _stream():
+  return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def langevin_cfg(num_iterations=25, sampler_stepsize_init=1e-1,
+                 sampler_stepsize_decay=0.8, noise_scale=1.0, grad_clip=None,
+                 delta_action_clip=0.1, use_polynomial_rate=True,
+                 sampler_stepsize_final=1e-5, sampler_stepsize_power=2.0,
+                 grad_norm_type='inf', apply_exp=False) -> LangevinCfg:
+  if grad_norm_type not in _lib.NORM_BY_NAME:
+    raise KeyError(grad_norm_type)   # same failure mode as mcmc.py:197-200
+  return LangevinCfg(int(num_iterations), float(sampler_stepsize_init),
+                     float(sampler_stepsize_decay), float(noise_scale),
+                     -1.0 if grad_clip is None else float(grad_clip),
+                     float(delta_action_clip), int(bool(use_polynomial_rate)),
+                     float(sampler_stepsize_final),
+                     float(sampler_stepsize_power),
+                     _lib.NORM_BY_NAME[grad_norm_type], int(bool(apply_exp)))
+
+
+def loss_cfg(softmax_temperature=1.0, add_grad_penalty=True,
+             grad_norm_type='inf', grad_margin=1.0, square_grad_penalty=True,
+             grad_loss_weight=1.0) -> LossCfg:
+  return LossCfg(float(softmax_temperature), int(bool(add_grad_penalty)),
+                 _lib.NORM_BY_NAME[grad_norm_type],
+                 -1.0 if grad_margin is None else float(grad_margin),
+                 int(bool(square_grad_penalty)), float(grad_loss_weight))
+
+
+def param_count(obs_dim: int, act_dim: int, width: int, depth: int) -> int:
+  """Pure arithmetic; usable without a GPU."""
+  d_in = obs_dim + act_dim
+  return d_in * width + width + (depth // 2) * (2 * width * width + 2 * width) + width + 1
+
+
+class EBMEngine:
+  """Owns an ibc_handle for one MLPEBM architecture on one GPU."""
+
+  def __init__(self, obs_dim: int, act_dim: int, width: int, depth: int,
+               device: Optional[torch.device] = None):
+    if depth % 2 != 0:
+      raise AssertionError('ResNet wants layers to be even numbers')  # resnet.py:42
+    if not torch.cuda.is_available():
+      raise _lib.IbcError('ibc_b200 needs a CUDA device (B200); there is no CPU path')
+    self.lib = _lib.load()
+    self.device = torch.device('cuda', torch.cuda.current_device()) if device is None \
+        else torch.device(device)
+    self.arch = MlpArch(obs_dim, act_dim, width, depth)
+    self.obs_dim, self.act_dim, self.width, self.depth = obs_dim, act_dim, width, depth
+    self.param_count = int(self.lib.ibc_param_count(ctypes.byref(self.arch)))
+    h = ctypes.c_void_p()
+    _lib.check(self.lib.ibc_create(ctypes.byref(self.arch), self.device.index or 0,
+                                   ctypes.byref(h)))
+    self._h = h
+    self._params = None
+
+  def __del__(self):
+    h = getattr(self, '_h', None)
+    if h is not None and h.value:
+      try:
+        self.lib.ibc_destroy(h)
+      except Exception:  # interpreter shutdown
+        pass
+      self._h = None
+
+  # -- configuration ---------------------------------------------------------
+  @property
+  def precision(self) -> int:
+    return int(self.lib.ibc_get_precision(self._h))
+
+  def set_precision(self, precision: int):
+    _lib.check(self.lib.ibc_set_precision(self._h, int(precision)), self._h)
+
+  def bind_params(self, params: torch.Tensor):
+    _check_f32(params, 'params')
+    if params.numel() != self.param_count:
+      raise ValueError('params has %d elements, expected %d' % (params.numel(), self.param_count))
+    self._params = params
+    _lib.check(self.lib.ibc_bind_params(self._h, _ptr(params), _stream()), self._h)
+
+  def params_changed(self):
+    _lib.check(self.lib.ibc_params_changed(self._h), self._h)
+
+  def kernel_status(self) -> int:
+    st = ctypes.c_int32(0)
+    _lib.check(self.lib.ibc_kernel_status(self._h, ctypes.byref(st)), self._h)
+    return int(st.value)
+
+  # -- energy ------------------------------------------------------------------
+  def _check_obs_act(self, obs, act, n):
+    _check_f32(obs, 'obs')
+    _check_f32(act, 'act')
+    if obs.dim() != 2 or obs.shape[1] != self.obs_dim:
+      raise ValueError('obs must be [B, %d], got %s' % (self.obs_dim, tuple(obs.shape)))
+    b = obs.shape[0]
+    if act.dim() != 2 or act.shape[1] != self.act_dim or act.shape[0] != b * n:
+      raise ValueError('act must be [%d, %d], got %s' % (b * n, self.act_dim, tuple(act.shape)))
+    return b
+
+  def energy(self, obs: torch.Tensor, act: torch.Tensor, n: int) -> torch.Tensor:
+    b = self._check_obs_act(obs, act, n)
+    e = torch.empty(b * n, device=obs.device, dtype=torch.float32)
+    _lib.check(self.lib.ibc_mlp_energy(self._h, _ptr(obs), b, _ptr(act), n, _ptr(e), _stream()),
+               self._h)
+    return e
+
+  def energy_dact(self, obs, act, n):
+    b = self._check_obs_act(obs, act, n)
+    e = torch.empty(b * n, device=obs.device, dtype=torch.float32)
+    g = torch.empty(b * n, self.act_dim, device=obs.device, dtype=torch.float32)
+    _lib.check(self.lib.ibc_mlp_energy_dact(self._h, _ptr(obs), b, _ptr(act), n, _ptr(e),
+                                            _ptr(g), _stream()), self._h)
+    return e, g
+
+  # -- samplers ------------------------------------------------------------------
+  def dfo(self, obs, actions, n, min_actions, max_actions, temperature=1.0,
+          num_iterations=3, iteration_std=0.33, uniforms=None, normals=None, seed=0):
+    """In-place on `actions`; returns probs [B*n]."""
+    b = self._check_obs_act(obs, actions, n)
+    _check_f32(min_actions, 'min_actions')
+    _check_f32(max_actions, 'max_actions')
+    if uniforms is not None:
+      if uniforms.dtype != torch.float64 or not uniforms.is_cuda or not uniforms.is_contiguous():
+        raise ValueError('uniforms must be a contiguous CUDA float64 tensor')
+      if uniforms.numel() != num_iterations * b * n:
+        raise ValueError('uniforms must have num_iterations*B*n elements')
+    if normals is not None:
+      _check_f32(normals, 'normals')
+      if normals.numel() != (num_iterations - 1) * b * n * self.act_dim:
+        raise ValueError('normals must have (num_iterations-1)*B*n*A elements')
+    probs = torch.empty(b * n, device=obs.device, dtype=torch.float32)
+    _lib.check(self.lib.ibc_dfo(self._h, _ptr(obs), b, _ptr(actions), n, _ptr(min_actions),
+                                _ptr(max_actions), float(temperature), int(num_iterations),
+                                float(iteration_std), _ptr(uniforms), _ptr(normals), int(seed),
+                                _ptr(probs), _stream()), self._h)
+    return probs
+
+  def langevin(self, obs, actions, n, min_actions, max_actions, cfg: LangevinCfg,
+               normals=None, seed=0, return_chain=False):
+    """In-place on `actions`; returns (chain_actions, energies, grad_norms) or None."""
+    b = self._check_obs_act(obs, actions, n)
+    _check_f32(min_actions, 'min_actions')
+    _check_f32(max_actions, 'max_actions')
+    r, k = b * n, cfg.num_iterations
+    if normals is not None:
+      _check_f32(normals, 'normals')
+      if normals.numel() != k * r * self.act_dim:
+        raise ValueError('normals must have K*B*n*A elements')
+    ca = ce = cg = None
+    if return_chain:
+      ca = torch.empty(k, r, self.act_dim, device=obs.device, dtype=torch.float32)
+      ce = torch.empty(k, r, device=obs.device, dtype=torch.float32)
+      cg = torch.empty(k, r, device=obs.device, dtype=torch.float32)
+    _lib.check(self.lib.ibc_langevin(self._h, _ptr(obs), b, _ptr(actions), n, _ptr(min_actions),
+                                     _ptr(max_actions), ctypes.byref(cfg), _ptr(normals),
+                                     int(seed), _ptr(ca), _ptr(ce), _ptr(cg), _stream()),
+               self._h)
+    return (ca, ce, cg) if return_chain else None
+
+  # -- training --------------------------------------------------------------------
+  def train_grads(self, obs, actions, num_counter_examples, cfg: LossCfg, global_batch,
+                  grads: Optional[torch.Tensor] = None, want_energies=False):
+    """Returns (per_example_loss [B], grad_loss [B], energies or None, grads)."""
+    n1 = num_counter_examples + 1
+    b = self._check_obs_act(obs, actions, n1)
+    if grads is None:
+      grads = torch.empty(self.param_count, device=obs.device, dtype=torch.float32)
+    _check_f32(grads, 'grads')
+    per_example = torch.empty(b, device=obs.device, dtype=torch.float32)
+    grad_loss = torch.empty(b, device=obs.device, dtype=torch.float32)
+    energies = torch.empty(b * n1, device=obs.device, dtype=torch.float32) if want_energies else None
+    _lib.check(self.lib.ibc_train_grads(self._h, _ptr(obs), b, _ptr(actions),
+                                        int(num_counter_examples), ctypes.byref(cfg),
+                                        int(global_batch), _ptr(per_example), _ptr(grad_loss),
+                                        _ptr(energies), _ptr(grads), _stream()), self._h)
+    return per_example, grad_loss, energies, grads
+
+
+# -- handle-free ops -----------------------------------------------------------------
+def resample(logits: torch.Tensor, uniforms: torch.Tensor, want_draws=False, want_counts=False):
+  """categorical_bincount + tf.repeat (mcmc.py:32-55,136-137).  Returns
+  (rows [B*count] int64, draws or None, counts or None)."""
+  _check_f32(logits, 'logits')
+  if uniforms.dtype != torch.float64 or not uniforms.is_cuda or not uniforms.is_contiguous():
+    raise ValueError('uniforms must be a contiguous CUDA float64 tensor')
+  b, n = logits.shape
+  count = uniforms.shape[1]
+  if uniforms.shape[0] != b:
+    raise ValueError('uniforms must be [B, count]')
+  rows = torch.empty(b * count, device=logits.device, dtype=torch.int64)
+  draws = torch.empty(b, count, device=logits.device, dtype=torch.int32) if want_draws else None
+  counts = torch.empty(b, n, device=logits.device, dtype=torch.int32) if want_counts else None
+  _lib.check(_lib.load().ibc_resample(_ptr(logits), _ptr(uniforms), b, n, count, _ptr(draws),
+                                      _ptr(counts), _ptr(rows), _stream()))
+  return rows, draws, counts
+
+
+def softmax_rows(logits: torch.Tensor, temperature: float = 1.0) -> torch.Tensor:
+  _check_f32(logits, 'logits')
+  b, n = logits.shape
+  probs = torch.empty_like(logits)
+  _lib.check(_lib.load().ibc_softmax_rows(_ptr(logits), b, n, float(temperature), _ptr(probs),
+                                          _stream()))
+  return probs
+
+
+def uniform_actions(rows: int, min_actions, max_actions, u=None, seed=0) -> torch.Tensor:
+  _check_f32(min_actions, 'min_actions')
+  _check_f32(max_actions, 'max_actions')
+  a = min_actions.numel()
+  if u is not None:
+    _check_f32(u, 'u')
+    if u.numel() != rows * a:
+      raise ValueError('u must have rows*A elements')
+  out = torch.empty(rows, a, device=min_actions.device, dtype=torch.float32)
+  _lib.check(_lib.load().ibc_uniform_actions(_ptr(u), rows, a, _ptr(min_actions),
+                                             _ptr(max_actions), int(seed), _ptr(out), _stream()))
+  return out
+
+
+def gather_perturb(src, rows, std, min_actions, max_actions, normals=None, seed=0):
+  _check_f32(src, 'src')
+  r, a = rows.numel(), src.shape[1]
+  if rows.dtype != torch.int64 or not rows.is_cuda:
+    raise ValueError('rows must be CUDA int64')
+  if normals is not None:
+    _check_f32(normals, 'normals')
+  out = torch.empty(r, a, device=src.device, dtype=torch.float32)
+  _lib.check(_lib.load().ibc_dfo_gather_perturb(_ptr(src), _ptr(rows), r, a, _ptr(normals),
+                                                int(seed), float(std), _ptr(min_actions),
+                                                _ptr(max_actions), _ptr(out), _stream()))
+  return out
+
+
+def langevin_update(actions, de_dact_pos, stepsize, min_actions, max_actions, noise_scale=1.0,
+                    grad_clip=None, delta_action_clip=0.1, grad_norm_type='inf', normals=None,
+                    seed=0):
+  """One langevin_step update in place given +dE/dact; returns grad_norms [R]."""
+  _check_f32(actions, 'actions')
+  _check_f32(de_dact_pos, 'dE_dact')
+  r, a = actions.shape
+  if normals is not None:
+    _check_f32(normals, 'normals')
+  norms = torch.empty(r, device=actions.device, dtype=torch.float32)
+  _lib.check(_lib.load().ibc_langevin_update(
+      _ptr(actions), _ptr(de_dact_pos), r, a, _ptr(normals), int(seed), float(noise_scale),
+      -1.0 if grad_clip is None else float(grad_clip), float(delta_action_clip), float(stepsize),
+      _ptr(min_actions), _ptr(max_actions), _lib.NORM_BY_NAME[grad_norm_type], _ptr(norms),
+      _stream()))
+  return norms
+
+
+def info_nce(predictions: torch.Tensor, temperature=1.0, grad_scale=1.0, want_grad=False):
+  _check_f32(predictions, 'predictions')
+  b, n1 = predictions.shape
+  loss = torch.empty(b, device=predictions.device, dtype=torch.float32)
+  dpred = torch.empty_like(predictions) if want_grad else None
+  _lib.check(_lib.load().ibc_info_nce(_ptr(predictions), b, n1, float(temperature),
+                                      float(grad_scale), _ptr(loss), _ptr(dpred), _stream()))
+  return (loss, dpred) if want_grad else loss
+
+
+def grad_penalty_from_dact(de_dact, batch_size, cfg: LossCfg, grad_scale=1.0, want_cotangent=False):
+  _check_f32(de_dact, 'dE_dact')
+  r, a = de_dact.shape
+  n1 = r // batch_size
+  gl = torch.empty(batch_size, device=de_dact.device, dtype=torch.float32)
+  cot = torch.empty_like(de_dact) if want_cotangent else None
+  _lib.check(_lib.load().ibc_grad_penalty_from_dact(_ptr(de_dact), batch_size, n1, a,
+                                                    ctypes.byref(cfg), float(grad_scale),
+                                                    _ptr(gl), _ptr(cot), _stream()))
+  return (gl, cot) if want_cotangent else gl
+
+
+def adam_step(params, grads, m, v, lr_t, beta1=0.9, beta2=0.999, epsilon=1e-7):
+  for t, name in ((params, 'params'), (grads, 'grads'), (m, 'm'), (v, 'v')):
+    _check_f32(t, name)
+  _lib.check(_lib.load().ibc_adam_step(_ptr(params), _ptr(grads), _ptr(m), _ptr(v),
+                                       params.numel(), float(lr_t), float(beta1), float(beta2),
+                                       float(epsilon), _stream()))
+
+
+def langevin_stepsizes(cfg: LangevinCfg):
+  out = (ctypes.c_float * max(cfg.num_iterations, 1))()
+  _lib.check(_lib.load().ibc_langevin_stepsizes(ctypes.byref(cfg), out))
+  return [float(out[i]) for i in range(cfg.num_iterations)]
+
+
+def umma_selftest(a: torch.Tensor, bt: torch.Tensor, mode: int = 0):
+  """D = A[128,K] . Bt[N,K]^T through tcgen05; returns (D, status)."""
+  _check_f32(a, 'A')
+  _check_f32(bt, 'Bt')
+  n, k = bt.shape
+  d = torch.zeros(128, n, device=a.device, dtype=torch.float32)
+  st = ctypes.c_int32(-1)
+  _lib.check(_lib.load().ibc_umma_selftest(_ptr(a), _ptr(bt), n, k, int(mode), _ptr(d),
+                                           ctypes.byref(st), _stream()))
+  return d, int(st.value)

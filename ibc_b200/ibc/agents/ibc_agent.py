@@ -1,0 +1,268 @@
+"""ImplicitBCAgent on the B200 engine -- the reference's
+`ibc/agents/ibc_agent.py:39-475` + `ibc/agents/base_agent.py:36-66` re-hosted.
+
+`agent.train(experience)` runs: counter-example generation (uniform / DFO /
+Langevin, `_make_counter_example_actions`), the B*(N+1)-row forward, InfoNCE
+(+ gradient penalty), the backward pass, the data-parallel gradient all-reduce
+(torch.distributed, NCCL on GPUs) and Adam -- all tensor math inside
+libibc_b200.so.  experience = ((obs_dict [B, T, .], action [B, A]), ()).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ibc_b200 import engine as eng
+from ibc_b200 import gin_lite as gin
+from ibc_b200.ibc import specs
+from ibc_b200.ibc.agents import ibc_policy
+from ibc_b200.ibc.agents import mcmc
+from ibc_b200.ibc.losses import ebm_loss
+from ibc_b200.ibc.losses import gradient_loss
+from ibc_b200.networks.mlp_ebm import MLPEBM
+
+
+class BehavioralCloningAgent:
+  """base_agent.py:29-66: loss -> gradients -> (all-reduce) -> optimizer."""
+
+  def __init__(self, time_step_spec, action_spec, policy, collect_policy,
+               train_step_counter=None):
+    self.time_step_spec = time_step_spec
+    self.action_spec = action_spec
+    self.policy = policy
+    self.collect_policy = collect_policy
+    self.train_step_counter = 0 if train_step_counter is None else train_step_counter
+
+  def train(self, experience, weights=None):
+    return self._train(experience, weights)
+
+  def get_eval_loss(self, experience):
+    loss_dict = self._loss(experience, training=False)
+    return loss_dict
+
+
+@gin.configurable
+class ImplicitBCAgent(BehavioralCloningAgent):
+  """TFAgent look-alike implementing implicit behavioral cloning."""
+
+  def __init__(self,
+               time_step_spec,
+               action_spec,
+               action_sampling_spec,
+               cloning_network,
+               optimizer,
+               obs_norm_layer=None,
+               act_norm_layer=None,
+               act_denorm_layer=None,
+               num_counter_examples=256,
+               debug_summaries=False,
+               summarize_grads_and_vars=False,
+               train_step_counter=None,
+               name=None,
+               fraction_dfo_samples=0.,
+               fraction_langevin_samples=1.0,
+               ebm_loss_type='info_nce',
+               late_fusion=False,
+               compute_mse=False,
+               run_full_chain_under_gradient=False,
+               return_full_chain=True,
+               add_grad_penalty=True,
+               grad_norm_type='inf',
+               softmax_temperature=1.0):
+    del debug_summaries, summarize_grads_and_vars
+    self.name = name
+    self._action_sampling_spec = action_sampling_spec
+    self._obs_norm_layer = obs_norm_layer
+    self._act_norm_layer = act_norm_layer
+    self._act_denorm_layer = act_denorm_layer
+    self.cloning_network = cloning_network
+    self.cloning_network.create_variables(training=False)
+    self._optimizer = optimizer
+    self._num_counter_examples = int(num_counter_examples)
+    self._fraction_dfo_samples = fraction_dfo_samples
+    self._fraction_langevin_samples = fraction_langevin_samples
+    assert self._fraction_dfo_samples + self._fraction_langevin_samples <= 1.0
+    assert self._fraction_dfo_samples >= 0.
+    assert self._fraction_langevin_samples >= 0.
+    self.ebm_loss_type = ebm_loss_type
+    if ebm_loss_type != 'info_nce':
+      if ebm_loss_type in ('cd', 'cd_kl', 'clipped_cd'):
+        raise NotImplementedError('ebm_loss_type %r is out of scope (no shipped gin selects it)'
+                                  % ebm_loss_type)
+      raise ValueError('Unsupported EBM loss type.')                 # ibc_agent.py:336
+    if late_fusion:
+      raise NotImplementedError('late_fusion (PixelEBM) training is not built yet')
+    self._run_full_chain_under_gradient = run_full_chain_under_gradient
+    self._return_full_chain = return_full_chain
+    self._add_grad_penalty = add_grad_penalty
+    self._grad_norm_type = grad_norm_type
+    self._softmax_temperature = softmax_temperature
+    self._late_fusion = late_fusion
+    self._compute_mse = compute_mse
+    self._kl = None
+    device = cloning_network.device
+    self._min = torch.as_tensor(np.asarray(action_sampling_spec.minimum, np.float32)).to(device)
+    self._max = torch.as_tensor(np.asarray(action_sampling_spec.maximum, np.float32)).to(device)
+    collect_policy = ibc_policy.IbcPolicy(
+        time_step_spec=time_step_spec,
+        action_spec=action_spec,
+        action_sampling_spec=action_sampling_spec,
+        actor_network=cloning_network,
+        late_fusion=late_fusion,
+        obs_norm_layer=self._obs_norm_layer,
+        act_denorm_layer=self._act_denorm_layer)
+    policy = ibc_policy.GreedyPolicy(collect_policy)
+    super().__init__(time_step_spec, action_spec, policy, collect_policy, train_step_counter)
+    self._grads = torch.zeros_like(cloning_network.params)
+    self.last_losses_dict = {}
+
+  # -- helpers -----------------------------------------------------------------
+  def _num_replicas(self) -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+  def _loss_cfg(self):
+    # grad_penalty's own gin bindings (gradient_loss.py:24-34)
+    b = gin._BINDINGS.get('grad_penalty', {})
+    if not b.get('only_apply_final_grad_penalty', True):
+      raise NotImplementedError('only_apply_final_grad_penalty=False is not built for training')
+    return eng.loss_cfg(self._softmax_temperature, self._add_grad_penalty, self._grad_norm_type,
+                        b.get('grad_margin', 1.0), b.get('square_grad_penalty', True),
+                        b.get('grad_loss_weight', 1.0))
+
+  def _to_device(self, experience):
+    (observations, actions), _ = experience if len(experience) == 2 and isinstance(
+        experience[0], tuple) else (experience, ())
+    net = self.cloning_network
+    obs = specs.map_structure(lambda t: t.to(net.device, torch.float32, non_blocking=True),
+                              observations)
+    act = actions.to(net.device, torch.float32, non_blocking=True)
+    return obs, act
+
+  # -- loss (ibc_agent.py:132-300) -------------------------------------------------
+  def _loss(self, experience, variables_to_train=None, weights=None, training=False,
+            draws: Optional[dict] = None):
+    del variables_to_train
+    if weights is not None:
+      raise NotImplementedError('sample weights are not supported')
+    net = self.cloning_network
+    observations, actions = self._to_device(experience)
+    obs_flat = net._flat_obs(observations)                       # [B, O]
+    batch_size = obs_flat.shape[0]
+    n = self._num_counter_examples
+    expanded_actions = actions[:, None, :]
+    counter_example_actions, combined, chain_data = self._make_counter_example_actions(
+        obs_flat, expanded_actions, batch_size, training, draws or {})
+    losses_dict = {}
+    global_batch = batch_size * self._num_replicas()            # aggregate_losses
+
+    raw = eff = None
+    if training and isinstance(net, MLPEBM):
+      raw, eff = net.effective_params_for_training()             # spectral norm, training=True
+    per_example, grad_loss, _, grads = net.engine.train_grads(
+        obs_flat, combined, n, self._loss_cfg(), global_batch, self._grads)
+    total_loss = per_example.sum() / float(global_batch)
+    losses_dict['ebm_total_loss'] = total_loss
+    if self._add_grad_penalty:
+      losses_dict['grad_loss'] = grad_loss.mean()
+    if self._compute_mse:
+      # Keras MSE(NONE) -> [B, N]; aggregate_losses averages the extra axis then
+      # sums / global batch (ibc_agent.py:182-189)
+      mse = ((counter_example_actions - expanded_actions) ** 2).mean(dim=-1).mean(dim=1)
+      losses_dict['mse_counter_examples'] = mse.sum() / float(global_batch)
+    if chain_data is not None and chain_data.energies is not None:
+      e = chain_data.energies
+      losses_dict['overall_energies_avg'] = e.mean()
+      losses_dict['first_energies_avg'] = e[0].mean()
+      losses_dict['final_energies_avg'] = e[-1].mean()
+    if chain_data is not None and chain_data.grad_norms is not None:
+      g = chain_data.grad_norms
+      losses_dict['overall_grad_norms_avg'] = g.mean()
+      losses_dict['first_grad_norms_avg'] = g[0].mean()
+      losses_dict['final_grad_norms_avg'] = g[-1].mean()
+    self.last_losses_dict = losses_dict
+    if training:
+      if raw is not None:   # chain dL/dW_bar through the spectral normalisation
+        (graw,) = torch.autograd.grad(eff, raw, grad_outputs=grads)
+        grads.copy_(graw)
+      return specs.LossInfo(total_loss, ()), grads
+    return losses_dict
+
+  def _compute_ebm_loss(self, batch_size, predictions, counter_example_actions,
+                        expanded_actions, grad_flow_network_inputs=None):
+    """ibc_agent.py:302-338 (forward value only)."""
+    del counter_example_actions, expanded_actions, grad_flow_network_inputs
+    if self.ebm_loss_type == 'info_nce':
+      return ebm_loss.info_nce(predictions, batch_size, self._num_counter_examples,
+                               self._softmax_temperature, self._kl)
+    raise ValueError('Unsupported EBM loss type.')
+
+  # -- negatives (ibc_agent.py:340-475) -----------------------------------------------
+  def _make_counter_example_actions(self, obs_flat, expanded_actions, batch_size,
+                                    training=False, draws=None):
+    """obs_flat [B, O] (un-tiled), expanded_actions [B, 1, A].  Returns
+    (counter_example_actions [B, N, A], combined [B*(N+1), A], chain_data)."""
+    del training   # sampler network calls always use training=False (:388, :403)
+    draws = draws or {}
+    net = self.cloning_network
+    n = self._num_counter_examples
+    a_dim = expanded_actions.shape[-1]
+    u = draws.get('uniform_u')
+    random_uniform = eng.uniform_actions(batch_size * n, self._min, self._max,
+                                         None if u is None else u.reshape(batch_size * n, a_dim)
+                                         .contiguous(), mcmc._next_seed())
+    chain_data = None
+    if self._fraction_dfo_samples == 0.0 and self._fraction_langevin_samples == 0.0:
+      counter = random_uniform.view(batch_size, n, a_dim)
+    else:
+      dfo_actions = lang_actions = None
+      if self._fraction_dfo_samples > 0.:
+        if self._return_full_chain:
+          raise NotImplementedError('Not implemented to return dfo chain.')   # :374-375
+        dfo_actions = random_uniform.clone()
+        net.engine.dfo(obs_flat, dfo_actions, n, self._min, self._max, 1.0, 3, 0.33,
+                       draws.get('dfo_uniforms'), draws.get('dfo_normals'), mcmc._next_seed())
+      if self._fraction_langevin_samples > 0.:
+        tiled = torch.repeat_interleave(obs_flat, n, dim=0)
+        out = mcmc.langevin_actions_given_obs(
+            net, tiled, random_uniform, policy_state=(), min_actions=self._min,
+            max_actions=self._max, num_action_samples=n, training=False,
+            return_chain=self._return_full_chain, grad_norm_type=self._grad_norm_type,
+            normal_draws=draws.get('langevin_normals'))
+        if self._return_full_chain:
+          lang_actions, chain_data = out
+        else:
+          lang_actions = out
+      frac_init = 1.0 - self._fraction_dfo_samples - self._fraction_langevin_samples
+      n_init = int(frac_init * n)
+      n_dfo = int(self._fraction_dfo_samples * n)
+      n_lang = int(self._fraction_langevin_samples * n)
+      n_init += n - n_init - n_dfo - n_lang                    # residual -> init (:416-430)
+      pieces, used = [], 0
+      if n_init > 0:
+        pieces.append(random_uniform.view(batch_size, n, a_dim)[:, :n_init])
+        used += n_init
+      if n_dfo > 0:
+        pieces.append(dfo_actions.view(batch_size, n, a_dim)[:, used:used + n_dfo])
+        used += n_dfo
+      if n_lang > 0:
+        pieces.append(lang_actions.view(batch_size, n, a_dim)[:, used:used + n_lang])
+        used += n_lang
+      counter = torch.cat(pieces, dim=1)
+    combined = torch.cat([counter, expanded_actions], dim=1)    # true action LAST (:461-473)
+    combined = combined.reshape(batch_size * (n + 1), a_dim).contiguous()
+    return counter, combined, chain_data
+
+  # -- train (base_agent.py:36-62) ------------------------------------------------------
+  def _train(self, experience, weights=None, draws=None):
+    loss_info, grads = self._loss(experience, weights=weights, training=True, draws=draws)
+    if not bool(torch.isfinite(loss_info.loss)):                # check_numerics (:46)
+      raise FloatingPointError('Loss is inf or nan')
+    if self._num_replicas() > 1:
+      dist.all_reduce(grads, op=dist.ReduceOp.SUM)              # MirroredStrategy all-reduce
+    self._optimizer.apply_gradients(self.cloning_network, grads)
+    self.train_step_counter += 1
+    return loss_info

@@ -1,0 +1,257 @@
+/* ibc_b200 -- C-ABI of the B200-native IBC energy-based-policy hot path.
+ *
+ * The reference (google-research/ibc) is pure Python on TensorFlow and has no
+ * FFI layer; its "operator API" for this path is the Python call protocol of
+ *   ibc/agents/mcmc.py, ibc/losses/ebm_loss.py, ibc/losses/gradient_loss.py,
+ *   networks/mlp_ebm.py, networks/pixel_ebm.py, ibc/agents/base_agent.py.
+ * Each entry point below names the reference function (file:line) whose tensor
+ * arithmetic it replaces.  The Python package `ibc_b200.ibc` re-hosts those
+ * signatures on top of this library through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *     the library borrows caller memory and never frees it;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     no call synchronises the host unless documented;
+ *   - all functions return 0 on success or a negative IBC_ERR_* code; the
+ *     message is available from ibc_last_error();
+ *   - float = IEEE fp32, double = fp64, row-major dense tensors;
+ *   - B observations are tiled against n candidate actions per observation the
+ *     way tf-agents nest_utils.tile_batch does: row r of an [R = B*n, .] tensor
+ *     belongs to observation r / n.  Observations are passed
+ *     UN-tiled ([B, O]); the tiling is implicit.
+ *
+ * Flat parameter vector of an MLPEBM (ResNetPreActivation body, relu, no
+ * normaliser, dropout 0; networks/mlp_ebm.py:29-96, layers/resnet.py:32-153),
+ * Keras kernels are [in, out] row-major:
+ *   Wp [O + A, W] (observation rows first), bp [W],
+ *   for each of depth/2 blocks: W1 [W, W], b1 [W], W2 [W, W], b2 [W],
+ *   we [W] (Dense(1) kernel), be [1].
+ */
+#ifndef IBC_B200_H_
+#define IBC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IBC_OK 0
+#define IBC_ERR_INVALID (-1)     /* bad argument (ValueError / assert upstream) */
+#define IBC_ERR_UNSUPPORTED (-2) /* shape or option this build has no kernel for */
+#define IBC_ERR_CUDA (-3)        /* CUDA runtime error, message has the detail */
+#define IBC_ERR_NOT_FINITE (-4)  /* loss is inf/nan (base_agent.py:46)         */
+
+/* Arithmetic used by the dense layers. */
+#define IBC_PRECISION_FP32 0 /* fp32 FMA kernels (exact-order-independent)     */
+#define IBC_PRECISION_TF32 1 /* tcgen05 kind::tf32 MMA, fp32 accumulate in TMEM */
+
+#define IBC_NORM_NONE 0 /* grad_norm_type=None -> zeros (mcmc.py:203-206) */
+#define IBC_NORM_L1 1
+#define IBC_NORM_L2 2
+#define IBC_NORM_INF 3
+
+typedef struct ibc_handle ibc_handle;
+
+typedef struct {
+  int32_t obs_dim; /* O = T * sum of observation feature dims, flattened       */
+  int32_t act_dim; /* A                                                        */
+  int32_t width;   /* W, MLPEBM.width                                          */
+  int32_t depth;   /* D, MLPEBM.depth (even; resnet.py:42)                     */
+} ibc_mlp_arch;
+
+/* langevin_actions_given_obs keyword arguments (mcmc.py:332-355). */
+typedef struct {
+  int32_t num_iterations;        /* default 25                                 */
+  float sampler_stepsize_init;   /* 1e-1                                       */
+  float sampler_stepsize_decay;  /* 0.8 (ExponentialSchedule, mcmc.py:267-278) */
+  float noise_scale;             /* 1.0                                        */
+  float grad_clip;               /* <= 0 means None                            */
+  float delta_action_clip;       /* 0.1                                        */
+  int32_t use_polynomial_rate;   /* 1                                          */
+  float sampler_stepsize_final;  /* 1e-5                                       */
+  float sampler_stepsize_power;  /* 2.0                                        */
+  int32_t grad_norm_type;        /* IBC_NORM_*, default INF                    */
+  int32_t apply_exp;             /* 0; 1 differentiates exp(E) (mcmc.py:186)   */
+} ibc_langevin_cfg;
+
+/* ImplicitBCAgent._loss options (ibc_agent.py:43-66, gradient_loss.py:24-34). */
+typedef struct {
+  float softmax_temperature;   /* 1.0                                          */
+  int32_t add_grad_penalty;    /* 1                                            */
+  int32_t grad_norm_type;      /* IBC_NORM_INF                                 */
+  float grad_margin;           /* 1.0; < 0 means None                          */
+  int32_t square_grad_penalty; /* 1                                            */
+  float grad_loss_weight;      /* 1.0                                          */
+} ibc_loss_cfg;
+
+/* ---- lifetime ---------------------------------------------------------- */
+
+/* Creates the per-GPU state that owns workspaces and packed weight copies for
+ * one MLPEBM (networks/mlp_ebm.py:29-70).  depth must be even. */
+int ibc_create(const ibc_mlp_arch* arch, int device, ibc_handle** out);
+int ibc_destroy(ibc_handle* h);
+/* Last error message of `h` (or of the last failed ibc_create when h==NULL). */
+const char* ibc_last_error(const ibc_handle* h);
+/* Number of fp32 parameters in the flat vector described above. */
+int64_t ibc_param_count(const ibc_mlp_arch* arch);
+/* Library build tag, e.g. "ibc_b200 0.1 sm_100a". */
+const char* ibc_version(void);
+
+/* IBC_PRECISION_*; TF32 is refused (IBC_ERR_UNSUPPORTED) for widths the
+ * tcgen05 kernels do not cover. */
+int ibc_set_precision(ibc_handle* h, int precision);
+int ibc_get_precision(const ibc_handle* h);
+
+/* Borrow the caller's flat parameter vector (device, fp32).  Must be called
+ * again (or ibc_params_changed) whenever the values change so packed copies
+ * are refreshed.  Replaces the Keras variable ownership of
+ * networks/mlp_ebm.py:41-70. */
+int ibc_bind_params(ibc_handle* h, const float* params, void* stream);
+int ibc_params_changed(ibc_handle* h);
+
+/* ---- energy network ---------------------------------------------------- */
+
+/* MLPEBM.call (networks/mlp_ebm.py:72-96 + layers/resnet.py:135-153):
+ * energy[r] = E(obs[r / n], act[r]) for r in [0, B*n). */
+int ibc_mlp_energy(ibc_handle* h, const float* obs, int64_t B,
+                   const float* act, int64_t n, float* energy, void* stream);
+
+/* mcmc.gradient_wrt_act (ibc/agents/mcmc.py:161-191) without the sign flip:
+ * energy[r] and dE_dact[r, :] = +dE/dact (the reference returns -dE/dact). */
+int ibc_mlp_energy_dact(ibc_handle* h, const float* obs, int64_t B,
+                        const float* act, int64_t n, float* energy,
+                        float* dE_dact, void* stream);
+
+/* ---- samplers ---------------------------------------------------------- */
+
+/* categorical_bincount + tf.repeat (mcmc.py:32-55, 136-137), bit-exact with
+ * TF's CPU multinomial given the same uniforms: sequential fp64 CDF of
+ * exp(logit - max), to_find = u * total, upper_bound.
+ *   logits [B, n] f32; uniforms [B, count] f64 in [0, 1);
+ *   draws  [B, count] i32 raw class ids        (nullable)
+ *   counts [B, n] i32                          (nullable)
+ *   rows   [B * count] i64 global row ids b*n + class, ascending (nullable) */
+int ibc_resample(const float* logits, const double* uniforms, int64_t B,
+                 int64_t n, int64_t count, int32_t* draws, int32_t* counts,
+                 int64_t* rows, void* stream);
+
+/* mcmc.iterative_dfo (mcmc.py:58-158).  actions [B*n, A] is updated in place;
+ * probs [B*n] receives softmax(last logits) (NOT aligned with the resampled
+ * actions, as upstream).  uniforms [num_iterations, B, n] f64 and normals
+ * [num_iterations-1, B*n, A] f32 are the explicit draws; when NULL they are
+ * generated on device from `seed` (Philox4x32-10). */
+int ibc_dfo(ibc_handle* h, const float* obs, int64_t B, float* actions,
+            int64_t n, const float* min_actions, const float* max_actions,
+            float temperature, int32_t num_iterations, float iteration_std,
+            const double* uniforms, const float* normals, uint64_t seed,
+            float* probs, void* stream);
+
+/* mcmc.langevin_actions_given_obs (mcmc.py:330-425) with stop_chain_grad.
+ * actions [B*n, A] updated in place.  normals [K, B*n, A] or NULL (-> seed).
+ * Optional chain outputs (update_chain_data, mcmc.py:297-327):
+ *   chain_actions [K, R, A] post-step, chain_energies [K, R] and
+ *   chain_grad_norms [K, R] pre-step. */
+int ibc_langevin(ibc_handle* h, const float* obs, int64_t B, float* actions,
+                 int64_t n, const float* min_actions, const float* max_actions,
+                 const ibc_langevin_cfg* cfg, const float* normals,
+                 uint64_t seed, float* chain_actions, float* chain_energies,
+                 float* chain_grad_norms, void* stream);
+
+/* Pieces of the two samplers for energy functions that are not an MLPEBM owned
+ * by a handle (e.g. the mock network of ibc/agents/mcmc_test.py:67-81), so the
+ * host can interleave its own energy evaluation:
+ *   out[r, :] = clip(src[rows[r], :] + normal * std, min, max)   (std == 0:
+ *   plain gather)                                   mcmc.py:139-150
+ *   one langevin_step update after dE/dact is known mcmc.py:238-262
+ * normals NULL -> generated from seed. */
+int ibc_dfo_gather_perturb(const float* src, const int64_t* rows, int64_t R,
+                           int32_t A, const float* normals, uint64_t seed,
+                           float std, const float* min_actions,
+                           const float* max_actions, float* out, void* stream);
+int ibc_langevin_update(float* actions, const float* dE_dact, int64_t R,
+                        int32_t A, const float* normals, uint64_t seed,
+                        float noise_scale, float grad_clip,
+                        float delta_action_clip, float stepsize,
+                        const float* min_actions, const float* max_actions,
+                        int32_t grad_norm_type, float* grad_norms, void* stream);
+
+/* PolynomialSchedule / ExponentialSchedule (mcmc.py:267-294): step size used
+ * AT each of the K steps, written to out_host[K] (host memory). */
+int ibc_langevin_stepsizes(const ibc_langevin_cfg* cfg, float* out_host);
+
+/* mcmc.get_probabilities (mcmc.py:428-441) given the logits: row softmax of
+ * logits / temperature over n, flattened. */
+int ibc_softmax_rows(const float* logits, int64_t B, int64_t n,
+                     float temperature, float* probs, void* stream);
+
+/* tensor_spec.sample_spec_nest on a bounded float spec (ibc_agent.py:350-352,
+ * ibc_policy.py:263-265): out = u * (max - min) + min with u [rows, A] given
+ * or (NULL) generated from seed. */
+int ibc_uniform_actions(const float* u, int64_t rows, int32_t A,
+                        const float* min_actions, const float* max_actions,
+                        uint64_t seed, float* out, void* stream);
+
+/* ---- losses and training ---------------------------------------------- */
+
+/* ebm_loss.info_nce (ibc/losses/ebm_loss.py:21-48) in the Keras KLDivergence
+ * epsilon-clipped form.  predictions [B, n1] with the true action in the LAST
+ * column.  loss [B]; dpred [B, n1] (nullable) = grad_scale * dloss/dpred. */
+int ibc_info_nce(const float* predictions, int64_t B, int64_t n1,
+                 float temperature, float grad_scale, float* loss,
+                 float* dpred, void* stream);
+
+/* gradient_loss.grad_penalty given dE/dact (gradient_loss.py:49-72):
+ * grad_loss [B]; cotangent [B*n1, A] (nullable) = grad_scale * d(sum_b
+ * grad_loss[b]) / d(dE_dact). */
+int ibc_grad_penalty_from_dact(const float* dE_dact, int64_t B, int64_t n1,
+                               int32_t A, const ibc_loss_cfg* cfg,
+                               float grad_scale, float* grad_loss,
+                               float* cotangent, void* stream);
+
+/* ImplicitBCAgent._loss + tape.gradient (ibc_agent.py:132-300,
+ * base_agent.py:43-48) for given combined actions [B*(N+1), A] (true action
+ * last per observation):
+ *   per_example_loss [B]  = info_nce (+ grad_penalty)
+ *   grad_loss        [B]  (nullable; zeros when the penalty is off)
+ *   energies   [B*(N+1)]  (nullable)
+ *   grads [param_count]   = d( sum_b per_example_loss[b] / global_batch )/dtheta
+ * (common.aggregate_losses scaling, ibc_agent.py:246-250).  grads is
+ * overwritten. */
+int ibc_train_grads(ibc_handle* h, const float* obs, int64_t B,
+                    const float* actions, int64_t N, const ibc_loss_cfg* cfg,
+                    int64_t global_batch, float* per_example_loss,
+                    float* grad_loss, float* energies, float* grads,
+                    void* stream);
+
+/* Keras-2.6 Adam (get_agent.py:64-68): m, v, params updated in place with the
+ * bias-corrected step size lr_t computed by the caller. */
+int ibc_adam_step(float* params, const float* grads, float* m, float* v,
+                  int64_t count, float lr_t, float beta1, float beta2,
+                  float epsilon, void* stream);
+
+/* ---- diagnostics ------------------------------------------------------- */
+
+/* Number of kernels this library has launched since the handle was created
+ * (bench.py's gpu_launches) and a reset. */
+int64_t ibc_launch_count(void);
+void ibc_reset_launch_count(void);
+
+/* Synchronises the device and returns (then clears) the sticky status word the
+ * fused kernels write when one of their internal barriers timed out (0 = ok;
+ * otherwise the code of the first wait that gave up -- results are invalid). */
+int ibc_kernel_status(ibc_handle* h, int32_t* status_host);
+
+/* tcgen05 self test: D[128, N] = A[128, K] * Bt[N, K]^T through the same
+ * shared-memory operand layout, descriptors and TMEM epilogue the fused
+ * kernels use.  mode 0 = A from shared memory, 1 = A from tensor memory.
+ * status_host[0] receives 0, or a non-zero stage code if a barrier timed out. */
+int ibc_umma_selftest(const float* A, const float* Bt, int32_t N, int32_t K,
+                      int32_t mode, float* D, int32_t* status_host,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IBC_B200_H_ */

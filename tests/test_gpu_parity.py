@@ -1,0 +1,346 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via ibc_b200.engine)
+against the CPU oracle on identical seeded inputs.
+
+Tolerances (stated per test):
+  * integer / index work (resample): bit-exact;
+  * fp32 FMA kernels vs the fp32/fp64 oracle: |d| <= 2e-5 * (|x| + rms(x));
+  * tcgen05 kind::tf32 energies (10-bit mantissa operands, fp32 accumulate,
+    up to 18 chained layers): |d| <= 2e-3 * (|x| + rms(x))   (SURVEY.md 8d).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import agent as oagent
+from oracle import losses as olosses
+from oracle import mcmc as omcmc
+from oracle import mlp_ebm as omlp
+from oracle import resample_c
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 2e-5
+TF32_TOL = 2e-3
+
+
+def _close(got, want, tol, name=''):
+  got = got.detach().double().cpu()
+  want = want.detach().double().cpu()
+  assert got.shape == want.shape, (name, got.shape, want.shape)
+  rms = float(want.pow(2).mean().sqrt())
+  bound = tol * (want.abs() + rms) + 1e-30
+  err = (got - want).abs()
+  worst = float((err / bound).max())
+  assert worst <= 1.0, '%s: max err/bound = %.3g (max abs err %.3g, rms %.3g)' % (
+      name, worst, float(err.max()), rms)
+
+
+def _engine(spec, seed=1, precision=None):
+  from ibc_b200 import engine as eng
+  e = eng.EBMEngine(spec.obs_dim, spec.act_dim, spec.width, spec.depth)
+  flat = omlp.init_params(spec, seed=seed)
+  # larger weights than the 0.05 init so that energies are not near-constant
+  flat = flat * 2.0
+  dev = flat.cuda().contiguous()
+  e.bind_params(dev)
+  if precision is not None:
+    e.set_precision(precision)
+  e._keep = dev
+  return e, flat
+
+
+def _data(spec, b, n, seed=0):
+  g = torch.Generator().manual_seed(seed)
+  obs = torch.randn(b, spec.obs_dim, generator=g)
+  act = torch.rand(b * n, spec.act_dim, generator=g) * 2 - 1
+  return obs, act
+
+
+SPECS_FP32 = [
+    omlp.MLPSpec(16, 2, 256, 2),     # C1 particle-2D
+    omlp.MLPSpec(20, 2, 128, 16),    # C2 pushing states
+    omlp.MLPSpec(39, 28, 64, 4),     # odd width, D4RL-like dims
+    omlp.MLPSpec(7, 3, 40, 2),       # ragged everything
+]
+SPECS_TF32 = [
+    omlp.MLPSpec(16, 2, 256, 2),
+    omlp.MLPSpec(20, 2, 128, 16),
+    omlp.MLPSpec(256, 32, 256, 2),   # C3 particle-32D
+    omlp.MLPSpec(20, 2, 128, 2),
+]
+
+
+# ------------------------------ tcgen05 self test ---------------------------
+@pytest.mark.parametrize('mode', [0, 1])
+@pytest.mark.parametrize('n,k', [(128, 32), (128, 128), (256, 64), (16, 32), (32, 128)])
+def test_umma_selftest(mode, n, k):
+  from ibc_b200 import engine as eng
+  g = torch.Generator().manual_seed(n * 1000 + k)
+  a = torch.randn(128, k, generator=g)
+  bt = torch.randn(n, k, generator=g)
+  d, status = eng.umma_selftest(a.cuda(), bt.cuda(), mode)
+  assert status == 0, 'barrier timeout code %d' % status
+  want = a.double() @ bt.double().t()
+  _close(d, want.float(), 2e-3, 'umma mode %d N=%d K=%d' % (mode, n, k))
+
+
+# ------------------------------ energy --------------------------------------
+@pytest.mark.parametrize('spec', SPECS_FP32, ids=str)
+@pytest.mark.parametrize('b,n', [(3, 5), (2, 256), (1, 1)])
+def test_energy_fp32(spec, b, n):
+  from ibc_b200 import _lib
+  e, flat = _engine(spec, precision=_lib.PRECISION_FP32)
+  obs, act = _data(spec, b, n)
+  got = e.energy(obs.cuda(), act.cuda(), n)
+  want = omlp.energy(flat.double(), spec, torch.repeat_interleave(obs, n, 0).double(),
+                     act.double())
+  _close(got, want, FP32_TOL, 'energy fp32')
+
+
+@pytest.mark.parametrize('spec', SPECS_TF32, ids=str)
+@pytest.mark.parametrize('b,n', [(3, 5), (2, 256), (5, 300), (1, 2048)])
+def test_energy_tf32(spec, b, n):
+  from ibc_b200 import _lib
+  e, flat = _engine(spec, precision=_lib.PRECISION_TF32)
+  obs, act = _data(spec, b, n)
+  got = e.energy(obs.cuda(), act.cuda(), n)
+  assert e.kernel_status() == 0
+  want = omlp.energy(flat.double(), spec, torch.repeat_interleave(obs, n, 0).double(),
+                     act.double())
+  _close(got, want, TF32_TOL, 'energy tf32')
+
+
+@pytest.mark.parametrize('spec', SPECS_FP32, ids=str)
+def test_energy_dact_fp32(spec):
+  from ibc_b200 import _lib
+  e, flat = _engine(spec, precision=_lib.PRECISION_FP32)
+  b, n = 4, 9
+  obs, act = _data(spec, b, n)
+  got_e, got_g = e.energy_dact(obs.cuda(), act.cuda(), n)
+  obs_t = torch.repeat_interleave(obs, n, 0).double()
+  want_e, want_g = omlp.energy_and_dact_manual(flat.double(), spec, obs_t, act.double())
+  _close(got_e, want_e, FP32_TOL, 'E')
+  _close(got_g, want_g, 1e-4, 'dE/dact')
+
+
+# ------------------------------ resample ---------------------------------------
+@pytest.mark.parametrize('b,n,count,scale', [(3, 257, 257, 1.0), (2, 2048, 2048, 30.0),
+                                             (1, 16384, 16384, 5.0), (4, 3, 5, 10.0),
+                                             (512, 256, 256, 3.0)])
+def test_resample_bit_exact(b, n, count, scale):
+  from ibc_b200 import engine as eng
+  rs = np.random.RandomState(n + count)
+  logits = (rs.randn(b, n) * scale).astype(np.float32)
+  logits[0, min(3, n - 1)] = -np.inf
+  if b > 1:
+    logits[1, 0] = np.inf            # non-finite logits are skipped
+  u = rs.rand(b, count)
+  u[0, 0] = 0.0
+  want_draws, want_counts, want_rows = resample_c.resample(logits, u)
+  rows, draws, counts = eng.resample(torch.from_numpy(logits).cuda(),
+                                     torch.from_numpy(u).cuda(), True, True)
+  assert np.array_equal(draws.cpu().numpy(), want_draws)
+  assert np.array_equal(counts.cpu().numpy(), want_counts)
+  assert np.array_equal(rows.cpu().numpy(), want_rows)
+
+
+def test_resample_known_answer():
+  from ibc_b200 import engine as eng
+  logits = torch.tensor([[0.0, math.log(3.0)]], dtype=torch.float32)
+  u = torch.tensor([[0.10, 0.20, 0.30, 0.90]], dtype=torch.float64)
+  rows, draws, counts = eng.resample(logits.cuda(), u.cuda(), True, True)
+  assert draws.cpu().tolist() == [[0, 0, 1, 1]]
+  assert counts.cpu().tolist() == [[2, 2]]
+  assert rows.cpu().tolist() == [0, 0, 1, 1]
+
+
+# ------------------------------ losses -------------------------------------------
+@pytest.mark.parametrize('b,n1,temp,scale', [(512, 257, 1.0, 1.0), (16, 9, 0.5, 20.0),
+                                             (3, 2, 1.0, 50.0)])
+def test_info_nce(b, n1, temp, scale):
+  from ibc_b200 import engine as eng
+  g = torch.Generator().manual_seed(b)
+  pred = (torch.randn(b, n1, generator=g) * scale).requires_grad_(True)
+  want = olosses.info_nce(pred, b, n1 - 1, temp)
+  (want_grad,) = torch.autograd.grad(want.sum() / b, pred)
+  loss, dpred = eng.info_nce(pred.detach().cuda(), temp, 1.0 / b, want_grad=True)
+  _close(loss, want, 1e-5, 'info_nce')
+  _close(dpred, want_grad, 1e-4, 'd info_nce')
+
+
+def test_info_nce_known_answer():
+  from ibc_b200 import engine as eng
+  loss = eng.info_nce(torch.zeros(1, 9).cuda(), 1.0)
+  assert abs(float(loss[0]) - 2.19721344) < 2e-6
+
+
+@pytest.mark.parametrize('norm', ['inf', '1', '2'])
+def test_grad_penalty_from_dact(norm):
+  from ibc_b200 import engine as eng
+  b, n1, a = 6, 9, 5
+  g = torch.Generator().manual_seed(3)
+  d = (torch.randn(b * n1, a, generator=g) * 1.5)
+  d[0] = torch.tensor([2.0, -2.0, 0.5, 2.0, 0.0])        # exact ties for the inf norm
+  d = d.requires_grad_(True)
+  norms = omcmc.compute_grad_norm(norm, d).reshape(b, n1)
+  pen = torch.clamp(norms - 1.0, 0.0, 1e10) ** 2
+  want = pen.mean(dim=1) * 0.7
+  (want_cot,) = torch.autograd.grad(want.sum() / b, d)
+  cfg = eng.loss_cfg(1.0, True, norm, 1.0, True, 0.7)
+  gl, cot = eng.grad_penalty_from_dact(d.detach().cuda(), b, cfg, 1.0 / b, want_cotangent=True)
+  _close(gl, want, 1e-5, 'grad_loss')
+  _close(cot, want_cot, 1e-5, 'cotangent')
+
+
+# ------------------------------ DFO / Langevin -----------------------------------------
+@pytest.mark.parametrize('precision', [0, 1])
+def test_dfo_pipeline_bit_exact_given_gpu_energies(precision):
+  """The whole iterative_dfo pipeline (resample indices, gather, perturb, clip,
+  softmax) is reproduced exactly by the oracle when the oracle is fed the GPU's
+  own energies; energy parity itself is tested above."""
+  spec = omlp.MLPSpec(20, 2, 128, 4)
+  e, _ = _engine(spec, precision=precision)
+  b, n, iters = 3, 512, 3
+  obs, act0 = _data(spec, b, n, seed=5)
+  mn, mx = torch.full((2,), -1.1), torch.full((2,), 1.1)
+  rs = np.random.RandomState(0)
+  uniforms = rs.rand(iters, b, n)
+  normals = torch.from_numpy(rs.randn(iters - 1, b * n, 2).astype(np.float32))
+  obs_d = obs.cuda()
+
+  def gpu_energy(_obs, actions):
+    return e.energy(obs_d, actions.float().cuda().contiguous(), n).cpu()
+
+  want_probs, want_actions = omcmc.iterative_dfo(
+      gpu_energy, b, None, act0, n, mn, mx, uniforms, normals)
+  actions = act0.cuda().clone()
+  probs = e.dfo(obs_d, actions, n, mn.cuda(), mx.cuda(), 1.0, iters, 0.33,
+                torch.from_numpy(uniforms).cuda(), normals.cuda())
+  assert torch.equal(actions.cpu(), want_actions)
+  _close(probs, want_probs, 1e-5, 'dfo probs')
+
+
+def test_dfo_device_rng_behaviour():
+  """mcmc_test.py:117-144 style check with draws generated on device."""
+  spec = omlp.MLPSpec(20, 2, 128, 4)
+  e, _ = _engine(spec)
+  b, n = 2, 2048
+  obs, act0 = _data(spec, b, n, seed=7)
+  mn, mx = torch.full((2,), -1.1).cuda(), torch.full((2,), 1.1).cuda()
+  actions = act0.cuda().clone()
+  e0 = e.energy(obs.cuda(), actions, n).reshape(b, n)
+  probs = e.dfo(obs.cuda(), actions, n, mn, mx, 1.0, 3, 0.33, None, None, seed=123)
+  e1 = e.energy(obs.cuda(), actions, n).reshape(b, n)
+  assert probs.shape == (b * n,)
+  assert torch.allclose(probs.reshape(b, n).sum(1), torch.ones(b).cuda(), atol=1e-4)
+  assert bool((actions >= -1.1).all()) and bool((actions <= 1.1).all())
+  # resampling proportional to exp(E) must raise the mean energy
+  assert bool((e1.mean(1) > e0.mean(1)).all())
+  actions2 = act0.cuda().clone()
+  e.dfo(obs.cuda(), actions2, n, mn, mx, 1.0, 3, 0.33, None, None, seed=123)
+  assert torch.equal(actions, actions2)          # same seed -> same draws
+
+
+@pytest.mark.parametrize('spec', [omlp.MLPSpec(16, 2, 256, 2), omlp.MLPSpec(39, 28, 64, 4)],
+                         ids=str)
+def test_langevin_matches_oracle(spec):
+  from ibc_b200 import _lib
+  from ibc_b200 import engine as eng
+  e, flat = _engine(spec, precision=_lib.PRECISION_FP32)
+  b, n, k = 4, 8, 12
+  a_dim = spec.act_dim
+  obs, act0 = _data(spec, b, n, seed=11)
+  mn, mx = torch.full((a_dim,), -1.1), torch.full((a_dim,), 1.1)
+  normals = torch.randn(k, b * n, a_dim, generator=torch.Generator().manual_seed(2))
+  obs_t = torch.repeat_interleave(obs, n, 0)
+
+  def energy_fn(_o, a):
+    return omlp.energy(flat, spec, obs_t, a)
+
+  want, chain = omcmc.langevin_actions_given_obs(
+      energy_fn, None, act0, mn, mx, normals, num_iterations=k, noise_scale=0.5,
+      delta_action_clip=0.5, sampler_stepsize_init=0.5, return_chain=True)
+  cfg = eng.langevin_cfg(num_iterations=k, noise_scale=0.5, delta_action_clip=0.5,
+                         sampler_stepsize_init=0.5)
+  actions = act0.cuda().clone()
+  ca, ce, cg = e.langevin(obs.cuda(), actions, n, mn.cuda(), mx.cuda(), cfg, normals.cuda(),
+                          return_chain=True)
+  # |da| <= 5e-3 * (max - min) after K steps
+  assert float((actions.cpu() - want).abs().max()) <= 5e-3 * 2.2
+  _close(ce[0], chain.energies[0], FP32_TOL, 'chain energies[0]')
+  _close(cg[0], chain.grad_norms[0], 1e-4, 'chain grad norms[0]')
+  assert float((ca[-1].cpu() - chain.actions[-1]).abs().max()) <= 5e-3 * 2.2
+
+
+def test_langevin_stepsizes_match_oracle():
+  from ibc_b200 import engine as eng
+  for k, init, final in [(100, 0.1, 1e-5), (100, 0.5, 1e-5), (25, 1e-5, 1e-5)]:
+    cfg = eng.langevin_cfg(num_iterations=k, sampler_stepsize_init=init,
+                           sampler_stepsize_final=final)
+    got = eng.langevin_stepsizes(cfg)
+    want = omcmc.stepsize_table(k, init=init, final=final)
+    assert np.allclose(got, want, rtol=1e-6, atol=0)
+
+
+# ------------------------------ training -----------------------------------------------
+@pytest.mark.parametrize('spec,gp', [(omlp.MLPSpec(16, 2, 64, 4), False),
+                                     (omlp.MLPSpec(16, 2, 64, 4), True),
+                                     (omlp.MLPSpec(20, 2, 128, 2), True),
+                                     (omlp.MLPSpec(39, 28, 48, 2), True)], ids=str)
+def test_train_grads_match_oracle_autograd(spec, gp):
+  from ibc_b200 import _lib
+  from ibc_b200 import engine as eng
+  e, flat = _engine(spec, precision=_lib.PRECISION_FP32)
+  flat = flat * 1.5     # make the gradient penalty active (|dE/da| > margin somewhere)
+  dev = flat.cuda().contiguous()
+  e.bind_params(dev)
+  b, n = 8, 7
+  obs, act = _data(spec, b, n + 1, seed=21)
+  theta = flat.double().clone().requires_grad_(True)
+  obs_t = torch.repeat_interleave(obs, n + 1, 0).double()
+
+  def energy_fn(_o, a):
+    return omlp.energy(theta, spec, obs_t, a)
+
+  pred = energy_fn(None, act.double()).reshape(b, n + 1)
+  per = olosses.info_nce(pred, b, n, 1.0)
+  gl = torch.zeros(b, dtype=torch.float64)
+  if gp:
+    gl = olosses.grad_penalty(energy_fn, 'inf', b, None, act.double())
+    per = per + gl
+  gb = 16        # global batch > local batch (2 replicas)
+  total = per.sum() / gb
+  (want_grad,) = torch.autograd.grad(total, theta)
+  cfg = eng.loss_cfg(1.0, gp, 'inf', 1.0, True, 1.0)
+  per_g, gl_g, en_g, grads = e.train_grads(obs.cuda(), act.cuda(), n, cfg, gb, want_energies=True)
+  _close(en_g, pred.reshape(-1), FP32_TOL, 'energies')
+  _close(per_g, per, 1e-4, 'per-example loss')
+  _close(gl_g, gl, 1e-4, 'grad loss')
+  if gp:
+    assert float(gl.max()) > 0, 'test is vacuous: penalty inactive'
+  # per parameter tensor: relative Frobenius error
+  for name, off, shape in omlp.param_layout(spec):
+    cnt = math.prod(shape)
+    w = want_grad[off:off + cnt]
+    g = grads[off:off + cnt].double().cpu()
+    denom = float(w.norm()) + 1e-12 * math.sqrt(cnt)
+    rel = float((g - w).norm()) / max(denom, 1e-30)
+    assert rel < 1e-4 or float((g - w).abs().max()) < 1e-9, (name, rel)
+
+
+def test_adam_step_matches_oracle():
+  from ibc_b200 import engine as eng
+  g = torch.Generator().manual_seed(0)
+  p = torch.randn(1000, generator=g)
+  st = oagent.adam_init(p)
+  pg = p.cuda().clone()
+  m, v = torch.zeros_like(pg), torch.zeros_like(pg)
+  want = p.clone()
+  for it in range(5):
+    grad = torch.randn(1000, generator=g) * 0.1
+    lr_t = oagent.adam_step_scalars(1e-3, st.iterations)
+    want = oagent.adam_update(want, grad, st, 1e-3)
+    eng.adam_step(pg, grad.cuda(), m, v, lr_t)
+  _close(pg, want, 1e-5, 'adam')
