@@ -32,6 +32,17 @@ constexpr int kSliceBytes = 16384;
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// tcgen05 kind::tf32 reads the top 19 bits of each fp32 operand (truncation);
+// rounding to nearest-even on the way in halves the error and removes the bias.
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 tf32_rn4(float4 v) {
+  return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+}
+
 // Offsets (in floats) inside the packed operand buffer.
 struct PackedLayout {
   int W, nb, KP, AP;
@@ -112,7 +123,7 @@ __global__ void pack_kernel(const float* __restrict__ P, Layout L, PackedLayout 
         v = (w == 0) ? P[L.be] : 0.f;
       }
     }
-    out[i] = v;
+    out[i] = (i < pl.vecs) ? tf32_rn(v) : v;   // MMA operands rounded to nearest tf32
   }
 }
 
@@ -156,7 +167,7 @@ __device__ __forceinline__ void emit_chunks(const uint32_t (&v)[32], const float
     if (kRelu) {
       o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
     }
-    a_tile[(c32 * 8 + q) * 128 + row] = o;
+    a_tile[(c32 * 8 + q) * 128 + row] = tf32_rn4(o);
   }
 }
 
@@ -218,7 +229,7 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
           if (k + 2 < p.A) o.z = a[k + 2];
           if (k + 3 < p.A) o.w = a[k + 3];
         }
-        a_tile[c * 128 + row] = o;
+        a_tile[c * 128 + row] = tf32_rn4(o);
       }
       fence_proxy_async_smem();
       mbar_arrive(&a_ready[t]);

@@ -75,8 +75,20 @@ resample_kernel(const float* __restrict__ logits, const double* __restrict__ uni
   }
   __syncthreads();
   if (tid == 0) {
+    // same left-to-right order as the CPU loop; loads are batched ahead of the
+    // dependent add chain so only the fp64 add latency is serial
     double total = 0.0;
-    for (int j = 0; j < n; ++j) {
+    int j = 0;
+    for (; j + 16 <= n; j += 16) {
+      double w[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) w[q] = cdf[j + q];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { total = __dadd_rn(total, w[q]); w[q] = total; }
+#pragma unroll
+      for (int q = 0; q < 16; ++q) cdf[j + q] = w[q];
+    }
+    for (; j < n; ++j) {
       total = __dadd_rn(total, cdf[j]);
       cdf[j] = total;
     }
