@@ -248,6 +248,11 @@ int ibc_train_grads(ibc_handle* h, const float* obs, int64_t B, const float* act
   if (!h->params) IBC_FAIL(h, IBC_ERR_INVALID, "no parameters bound (ibc_bind_params)");
   if (cfg->softmax_temperature <= 0.f)
     IBC_FAIL(h, IBC_ERR_INVALID, "ibc_train_grads: softmax_temperature must be > 0");
+  const bool gp = cfg->add_grad_penalty != 0 && cfg->grad_norm_type != IBC_NORM_NONE;
+  if (h->precision == IBC_PRECISION_TF32 && umma_train_supported(h->L) && !gp)
+    return train_grads_umma(h, obs, B, actions, N, *cfg, global_batch, per_example_loss,
+                            grad_loss, energies, grads, (cudaStream_t)stream);
+  // gradient penalty (second order) and other widths: fp32 path
   return train_grads_fp32(h, obs, B, actions, N, *cfg, global_batch, per_example_loss, grad_loss,
                           energies, grads, (cudaStream_t)stream);
 }

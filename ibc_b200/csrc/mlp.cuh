@@ -53,6 +53,13 @@ int mlp_energy_dact(ibc_handle* h, const float* obs, int64_t B, const float* act
 // tcgen05 path (mlp_umma.cu) ---------------------------------------------
 bool umma_supported(const Layout& L);
 int umma_pack_params(ibc_handle* h, cudaStream_t s);
+int umma_forward(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
+                 float* hp, float* E, float* xa_save, cudaStream_t s);
+// tcgen05 training path (mlp_umma_train.cu): W == 128, no gradient penalty.
+bool umma_train_supported(const Layout& L);
+int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* actions, int64_t N,
+                     const ibc_loss_cfg& c, int64_t global_batch, float* per_example,
+                     float* grad_loss_out, float* energies_out, float* grads, cudaStream_t s);
 int mlp_energy_umma(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
                     float* E, float* dEda, bool apply_exp, cudaStream_t s);
 

@@ -20,6 +20,7 @@
 #include "mlp.cuh"
 #include "ops.cuh"
 #include "umma.cuh"
+#include "umma_pack.cuh"
 
 namespace ibc {
 
@@ -29,45 +30,6 @@ namespace {
 
 constexpr int kSlots = 5;
 constexpr int kSliceBytes = 16384;
-
-__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
-
-// tcgen05 kind::tf32 reads the top 19 bits of each fp32 operand (truncation);
-// rounding to nearest-even on the way in halves the error and removes the bias.
-__device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-__device__ __forceinline__ float4 tf32_rn4(float4 v) {
-  return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-}
-
-// Offsets (in floats) inside the packed operand buffer.
-struct PackedLayout {
-  int W, nb, KP, AP;
-  int64_t fwd_p;     // [KP/4][W][4]           act rows of Wp (B operand of step 0)
-  int64_t fwd_l;     // 2*nb matrices [W/4][W][4]: W1_0, W2_0, W1_1, ...
-  int64_t rev_l;     // 2*nb matrices: W2_{nb-1}^T, W1_{nb-1}^T, ..., W2_0^T, W1_0^T
-  int64_t rev_p;     // [W/4][AP][4]           Wp act rows, B operand of dE/dact
-  int64_t vecs;      // [(2nb+1)][W] epilogue bias vectors, then we[W], be, pad
-  int64_t total;
-};
-
-inline PackedLayout make_packed_layout(const Layout& L) {
-  PackedLayout p;
-  p.W = L.W; p.nb = L.nb;
-  p.KP = round_up(L.A, 8);
-  p.AP = round_up(L.A, 16);
-  const int64_t WW = (int64_t)L.W * L.W;
-  p.fwd_p = 0;
-  p.fwd_l = p.fwd_p + (int64_t)L.W * p.KP;
-  p.rev_l = p.fwd_l + 2 * L.nb * WW;
-  p.rev_p = p.rev_l + 2 * L.nb * WW;
-  p.vecs = p.rev_p + (int64_t)L.W * p.AP;
-  p.total = p.vecs + (int64_t)(2 * L.nb + 2) * L.W + 4;
-  return p;
-}
 
 __global__ void pack_kernel(const float* __restrict__ P, Layout L, PackedLayout pl,
                             float* __restrict__ out) {
@@ -137,6 +99,11 @@ struct FwdParams {
   int64_t off_fwd_p, off_fwd_l, off_vecs;
   int* status;
   int num_groups;
+  // Training: when non-null the A operand of every W x W layer (slots
+  // 0..2nb-1, tf32-rounded) and the final residual stream h_nb (slot 2nb,
+  // fp32) are also written to global memory in the tile layout of
+  // train_tile_offset() for the backward kernels.
+  float* xa_save;
 };
 
 template <int W, int NT>
@@ -153,9 +120,10 @@ struct FwdSmem {
 };
 
 // 32 accumulator columns of one row: + bias, ReLU, write the 8 operand chunks.
-template <bool kRelu>
+template <bool kRelu, int W>
 __device__ __forceinline__ void emit_chunks(const uint32_t (&v)[32], const float* __restrict__ bias,
-                                            float4* __restrict__ a_tile, int c32, int row) {
+                                            float4* __restrict__ a_tile, int c32, int row,
+                                            float4* __restrict__ g_slot) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(bias + c32 * 32 + q * 4);
@@ -167,7 +135,9 @@ __device__ __forceinline__ void emit_chunks(const uint32_t (&v)[32], const float
     if (kRelu) {
       o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
     }
-    a_tile[(c32 * 8 + q) * 128 + row] = tf32_rn4(o);
+    const float4 r4 = tf32_rn4(o);
+    a_tile[(c32 * 8 + q) * 128 + row] = r4;
+    if (g_slot) g_slot[TrainTile<W>::chunk_f4(row, c32 * 8 + q)] = r4;
   }
 }
 
@@ -234,7 +204,10 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
       fence_proxy_async_smem();
       mbar_arrive(&a_ready[t]);
       const float* hp_row = p.hp + (valid ? (r / p.n_per_obs) : 0) * W;
+      const int64_t tile_id = (int64_t)g * NT + t;
       for (int i = 0; i < nsteps; ++i) {
+        float4* g_slot = p.xa_save ? reinterpret_cast<float4*>(
+            p.xa_save + TrainTile<W>::slot_base(tile_id, nsteps, i)) : nullptr;
         mbar_wait(&d_ready[t], ph_d, abort_flag, p.status, 100 + i);
         ph_d ^= 1;
         tc_fence_after();
@@ -254,6 +227,14 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
               float x = __uint_as_float(v[q]) + bias[c32 * 32 + q];
               if (i == 0) x += hp_row[c32 * 32 + q];
               e = fmaf(x, we[c32 * 32 + q], e);
+              v[q] = __float_as_uint(x);
+            }
+            if (g_slot) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                g_slot[TrainTile<W>::chunk_f4(row, c32 * 8 + q)] =
+                    make_float4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]),
+                                __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
             }
           }
           if (valid) p.E[r] = e + be;
@@ -276,7 +257,7 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
               }
               tmem_st32(taddr + c32 * 32, v);
             }
-            emit_chunks<true>(v, bias, a_tile, c32, row);
+            emit_chunks<true, W>(v, bias, a_tile, c32, row, g_slot);
           }
           if (i == 0) tmem_st_wait();
           tc_fence_before();
@@ -362,12 +343,20 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
 // ---------------------------------------------------------------------------
 // Self test: one 128 x N x K tile through the same operand layout.
 // ---------------------------------------------------------------------------
-__global__ void pack_rows_kernel(const float* __restrict__ X, int rows, int K,
+__global__ void pack_rows_kernel(const float* __restrict__ X, int rows, int K, int mn_major,
                                  float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * K) return;
-  const int kq = i & 3, r = (i >> 2) % rows, kc = (i >> 2) / rows;
-  out[i] = X[(int64_t)r * K + kc * 4 + kq];
+  if (!mn_major) {   // [K/4][rows][4]
+    const int kq = i & 3, r = (i >> 2) % rows, kc = (i >> 2) / rows;
+    out[i] = X[(int64_t)r * K + kc * 4 + kq];
+  } else if (mn_major == 1) {   // [rows/4][K][4]
+    const int rq = i & 3, k = (i >> 2) % K, rc = (i >> 2) / K;
+    out[i] = X[(int64_t)(rc * 4 + rq) * K + k];
+  } else {           // MN-major 128B/32B-base swizzle atoms
+    const int r = i / K, k = i % K;
+    out[mn32_offset(r, k, (uint32_t)(K / 4) * 512u, 512u) / 4] = X[i];
+  }
 }
 
 __global__ void __launch_bounds__(160, 1)
@@ -401,6 +390,15 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bpac
       for (int c = 0; c < K / 4; ++c)
         a_tile[c * 128 + row] = *reinterpret_cast<const float4*>(A + (int64_t)row * K + c * 4);
       fence_proxy_async_smem();
+    } else if (mode == 3) {   // MN-major, SWIZZLE_128B_BASE32B atoms
+      float* af = reinterpret_cast<float*>(smem);
+      for (int k = 0; k < K; ++k)
+        af[mn32_offset(row, k, (uint32_t)(K / 4) * 512u, 512u) / 4] = A[(int64_t)row * K + k];
+      fence_proxy_async_smem();
+    } else if (mode == 2) {   // MN-major staging: [row/4][K][4]
+      float* af = reinterpret_cast<float*>(smem);
+      for (int k = 0; k < K; ++k) af[((row >> 2) * K + k) * 4 + (row & 3)] = A[(int64_t)row * K + k];
+      fence_proxy_async_smem();
     } else {
       for (int c32 = 0; c32 < K / 32; ++c32) {
         uint32_t v[32];
@@ -422,6 +420,24 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bpac
     const uint32_t idesc = idesc_tf32(128, N);
     const uint32_t a_lbo = 128 * 16, b_lbo = (uint32_t)N * 16, sbo = 128;
     for (int ks = 0; ks < K / 8; ++ks) {
+      if (mode == 3) {
+        // both operands MN-major in the 128B / 32-byte-base swizzled layout:
+        // LBO = stride between 32-element MN atoms, SBO = between 4-row K atoms
+        const uint32_t lbo = (uint32_t)(K / 4) * 512u;
+        const uint64_t ad = smem_desc_lt(smem_u32(a_tile) + (uint32_t)ks * 1024, lbo, 512, 1);
+        const uint64_t bd = smem_desc_lt(smem_u32(b_tile) + (uint32_t)ks * 1024, lbo, 512, 1);
+        mma_tf32_ss(tmem_base, ad, bd, idesc | kIdescAMajorMN | kIdescBMajorMN, ks > 0);
+        continue;
+      }
+      if (mode == 2) {
+        // both operands MN-major: 8 K-rows per step are 128 contiguous bytes per
+        // 4-element MN chunk; SBO = stride between MN chunks, LBO = between 8-row groups
+        const uint32_t mn_sbo = (uint32_t)K * 16;
+        const uint64_t ad = smem_desc(smem_u32(a_tile) + (uint32_t)ks * 128, 128, mn_sbo);
+        const uint64_t bd = smem_desc(smem_u32(b_tile) + (uint32_t)ks * 128, 128, mn_sbo);
+        mma_tf32_ss(tmem_base, ad, bd, idesc | kIdescAMajorMN | kIdescBMajorMN, ks > 0);
+        continue;
+      }
       const uint64_t bd = smem_desc(smem_u32(b_tile) + (uint32_t)ks * 2 * b_lbo, b_lbo, sbo);
       if (mode == 0) {
         const uint64_t ad = smem_desc(smem_u32(a_tile) + (uint32_t)ks * 2 * a_lbo, a_lbo, sbo);
@@ -493,13 +509,21 @@ int mlp_energy_umma(ibc_handle* h, const float* obs, int64_t B, const float* act
     // The fused reverse chain is not built yet: dE/dact runs on the fp32 path.
     return mlp_energy_dact_fp32(h, obs, B, act, n, E, dEda, apply_exp, s);
   }
-  if (h->packed_stale) IBC_TRY(umma_pack_params(h, s));
-  const PackedLayout pl = make_packed_layout(L);
-  const int64_t R = B * n;
   IBC_CUDA(h, h->ws.reserve(Workspace::rounded((size_t)B * L.W * 4)));
   h->ws.reset();
   float* hp = h->ws.take<float>((size_t)B * L.W);
-  {  // hoisted observation projection (fp32): hp = obs . Wp[:O] + bp
+  return umma_forward(h, obs, B, act, n, hp, E, nullptr, s);
+}
+
+// Hoisted observation projection + fused forward.  hp [B, W] is caller scratch;
+// xa_save (nullable) receives the saved operand tiles for the backward pass.
+int umma_forward(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
+                 float* hp, float* E, float* xa_save, cudaStream_t s) {
+  const Layout& L = h->L;
+  if (h->packed_stale) IBC_TRY(umma_pack_params(h, s));
+  const PackedLayout pl = make_packed_layout(L);
+  const int64_t R = B * n;
+  {  // hp = obs . Wp[:O] + bp   (fp32)
     GemmP g;
     g.A = obs; g.lda = L.O; g.B = h->params + L.wp; g.ldb = L.W; g.C = hp; g.ldc = L.W;
     g.bias = h->params + L.bp; g.M = (int)B; g.N = L.W; g.K = L.O;
@@ -510,6 +534,7 @@ int mlp_energy_umma(ibc_handle* h, const float* obs, int64_t B, const float* act
   p.nb = L.nb; p.A = L.A; p.KP = pl.KP;
   p.off_fwd_p = pl.fwd_p; p.off_fwd_l = pl.fwd_l; p.off_vecs = pl.vecs;
   p.status = h->dev_status;
+  p.xa_save = xa_save;
   if (L.W == 128) {
     p.num_groups = (int)((R + 255) / 256);
     IBC_TRY((launch_fwd<128, 2>(h, p, s)));
@@ -530,7 +555,7 @@ int umma_selftest(const float* A, const float* Bt, int N, int K, int mode, float
   IBC_CUDA(h, cudaMalloc((void**)&bp, (size_t)N * K * 4));
   IBC_CUDA(h, cudaMalloc((void**)&st, sizeof(int)));
   IBC_CUDA(h, cudaMemsetAsync(st, 0, sizeof(int), s));
-  pack_rows_kernel<<<(N * K + 255) / 256, 256, 0, s>>>(Bt, N, K, bp);
+  pack_rows_kernel<<<(N * K + 255) / 256, 256, 0, s>>>(Bt, N, K, mode == 2 ? 1 : (mode == 3 ? 2 : 0), bp);
   count_launch();
   const size_t smem = (size_t)128 * K * 4 + (size_t)N * K * 4 + 64;
   IBC_CUDA(h, cudaFuncSetAttribute(umma_selftest_kernel,

@@ -1,0 +1,495 @@
+// Training backward of the MLPEBM on tcgen05 (kind::tf32) for width 128:
+//   tape.gradient(loss, variables)       ibc/agents/base_agent.py:43-48
+//   of the InfoNCE loss                  ibc/losses/ebm_loss.py:21-48
+//   through the ResNetPreActivation body networks/layers/resnet.py:135-153
+//
+// Three fused kernels after the forward (mlp_umma.cu, which saves the A
+// operand of every W x W layer per 128-row tile):
+//   mlp_bwd_umma_kernel   reverse chain per tile.  The gradient of the
+//       residual stream g stays in tensor memory; every layer's output
+//       gradient GY is written once (tf32, tile layout) for the weight
+//       gradient, ReLU masks come from the saved operands (x > 0).
+//   mlp_wgrad_umma_kernel dW_i = XA_i^T . GY_i as one tcgen05 GEMM per layer
+//       with K = all rows: both saved tiles are consumed as MN-major operands
+//       straight from their bulk-copied (TMA engine) shared-memory image,
+//       accumulating in tensor memory across all tiles of the CTA; the bias
+//       gradient (fp32 column sums of GY) is taken by the otherwise idle
+//       epilogue warps while the tiles sit in shared memory.
+//   first / last layer pieces (K = act_dim, obs_dim; Dense(1)) reuse the fp32
+//       kernels: they are O(R * W) work.
+#include "gemm_simt.cuh"
+#include "mlp.cuh"
+#include "ops.cuh"
+#include "umma.cuh"
+#include "umma_pack.cuh"
+
+namespace ibc {
+
+using namespace umma;
+
+namespace {
+
+constexpr int kSlots = 5;
+constexpr int kSliceBytes = 16384;
+constexpr int kW = 128;          // the only width this path is instantiated for
+constexpr int kNT = 2;
+
+// ---------------------------------------------------------------------------
+// reverse chain
+// ---------------------------------------------------------------------------
+struct BwdParams {
+  const float* dE;        // [R]   d(sum loss / global_batch) / dE
+  const float* xa_save;   // forward operand tiles, 2nb+1 slots
+  float* gy_save;         // output-gradient tiles, 2nb slots (slot i-1 = GY of layer i)
+  float* g0;              // [R, W] row-major gradient of the first Dense output
+  const float* packed;
+  int64_t off_rev_l, off_we;
+  float* dwe;             // [W] accumulated with atomics
+  int64_t R;
+  int nb, num_groups;
+  int* status;
+};
+
+struct BwdSmem {
+  static constexpr int kABytes = 128 * kW * 4;
+  static constexpr int kSliceK = kSliceBytes / (kW * 4);
+  static constexpr int kSlicesPerLayer = kW / kSliceK;
+  static constexpr int kStepsPerSlice = kSliceK / 8;
+  static constexpr int kThreads = (4 * kNT + 2) * 32;
+  static constexpr size_t kBytes = (size_t)kNT * kABytes + (size_t)kSlots * kSliceBytes +
+                                   2 * kW * 4 + 256;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(BwdSmem::kThreads, 1) mlp_bwd_umma_kernel(BwdParams p) {
+  using S = BwdSmem;
+  using TT = TrainTile<kW>;
+  constexpr int W = kW, NT = kNT;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* a_base = smem;
+  unsigned char* ring = smem + NT * S::kABytes;
+  float* we = reinterpret_cast<float*>(ring + kSlots * kSliceBytes);
+  float* dwe_acc = we + W;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dwe_acc + W);
+  uint64_t* a_ready = bars;
+  uint64_t* d_ready = bars + NT;
+  uint64_t* w_full = bars + 2 * NT;
+  uint64_t* w_empty = bars + 2 * NT + kSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NT + 2 * kSlots);
+  __shared__ int s_abort;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int nsteps = 2 * p.nb;
+  const int xa_slots = 2 * p.nb + 1, gy_slots = 2 * p.nb;
+
+  if (tid == 0) {
+    s_abort = 0;
+    for (int t = 0; t < NT; ++t) { mbar_init(&a_ready[t], 128); mbar_init(&d_ready[t], 1); }
+    for (int s = 0; s < kSlots; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    fence_mbar_init();
+  }
+  for (int i = tid; i < W; i += S::kThreads) { we[i] = p.packed[p.off_we + i]; dwe_acc[i] = 0.f; }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  volatile int* abort_flag = &s_abort;
+
+  if (warp < 4 * NT) {
+    // ===================== epilogue warpgroup t ==============================
+    const int t = warp >> 2;
+    const int row = tid & 127;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t col_g = (uint32_t)(t * 2 * W), col_d = (uint32_t)(t * 2 * W + W);
+    float4* a_tile = reinterpret_cast<float4*>(a_base + t * S::kABytes);
+    uint32_t ph_d = 0;
+    for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+      const int64_t tile_id = (int64_t)g * NT + t;
+      const int64_t r = tile_id * 128 + row;
+      const bool valid = r < p.R;
+      const float de = valid ? p.dE[r] : 0.f;
+      {
+        // g_top = dE (x) we   (gradient of the residual stream entering Dense(1));
+        // dwe += h_nb^T dE with h_nb from the forward's last slot
+        const float4* hn = reinterpret_cast<const float4*>(
+            p.xa_save + TT::slot_base(tile_id, xa_slots, 2 * p.nb));
+        float4* gy_top = reinterpret_cast<float4*>(
+            p.gy_save + TT::slot_base(tile_id, gy_slots, 2 * p.nb - 1));
+#pragma unroll 1
+        for (int c32 = 0; c32 < W / 32; ++c32) {
+          uint32_t v[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int c = c32 * 8 + q;
+            const float4 w4 = *reinterpret_cast<const float4*>(we + c * 4);
+            const float4 g4 = make_float4(de * w4.x, de * w4.y, de * w4.z, de * w4.w);
+            v[q * 4 + 0] = __float_as_uint(g4.x); v[q * 4 + 1] = __float_as_uint(g4.y);
+            v[q * 4 + 2] = __float_as_uint(g4.z); v[q * 4 + 3] = __float_as_uint(g4.w);
+            a_tile[c * 128 + row] = tf32_rn4(g4);
+            gy_top[TT::chunk_f4(row, c)] = g4;     // fp32: exact bias sums, MMA truncates
+            const float4 h4 = hn[TT::chunk_f4(row, c)];
+            const float s0 = warp_sum(de * h4.x), s1 = warp_sum(de * h4.y);
+            const float s2 = warp_sum(de * h4.z), s3 = warp_sum(de * h4.w);
+            if (lane == 0) {
+              atomicAdd(&dwe_acc[c * 4 + 0], s0); atomicAdd(&dwe_acc[c * 4 + 1], s1);
+              atomicAdd(&dwe_acc[c * 4 + 2], s2); atomicAdd(&dwe_acc[c * 4 + 3], s3);
+            }
+          }
+          tmem_st32(tmem_base + lane_off + col_g + c32 * 32, v);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(&a_ready[t]);
+      }
+      for (int s = 0; s < nsteps; ++s) {
+        const int i = nsteps - s;                     // forward layer index 2nb .. 1
+        mbar_wait(&d_ready[t], ph_d, abort_flag, p.status, 500 + s);
+        ph_d ^= 1;
+        tc_fence_after();
+        const bool odd = (i & 1) != 0;                // W1 layer: result adds onto g
+        const bool last = (i == 1);
+        const float4* xm = reinterpret_cast<const float4*>(
+            p.xa_save + TT::slot_base(tile_id, xa_slots, i - 1));
+        float4* gy_out = last ? nullptr : reinterpret_cast<float4*>(
+            p.gy_save + TT::slot_base(tile_id, gy_slots, i - 2));
+#pragma unroll 1
+        for (int c32 = 0; c32 < W / 32; ++c32) {
+          uint32_t v[32], gp[32];
+          tmem_ld32(tmem_base + lane_off + col_d + c32 * 32, v);
+          if (odd) tmem_ld32(tmem_base + lane_off + col_g + c32 * 32, gp);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int c = c32 * 8 + q;
+            const float4 m = xm[TT::chunk_f4(row, c)];
+            float4 o;
+            o.x = m.x > 0.f ? __uint_as_float(v[q * 4 + 0]) : 0.f;
+            o.y = m.y > 0.f ? __uint_as_float(v[q * 4 + 1]) : 0.f;
+            o.z = m.z > 0.f ? __uint_as_float(v[q * 4 + 2]) : 0.f;
+            o.w = m.w > 0.f ? __uint_as_float(v[q * 4 + 3]) : 0.f;
+            if (odd) {
+              o.x += __uint_as_float(gp[q * 4 + 0]); o.y += __uint_as_float(gp[q * 4 + 1]);
+              o.z += __uint_as_float(gp[q * 4 + 2]); o.w += __uint_as_float(gp[q * 4 + 3]);
+              gp[q * 4 + 0] = __float_as_uint(o.x); gp[q * 4 + 1] = __float_as_uint(o.y);
+              gp[q * 4 + 2] = __float_as_uint(o.z); gp[q * 4 + 3] = __float_as_uint(o.w);
+            }
+            if (!last) {
+              a_tile[c * 128 + row] = tf32_rn4(o);
+              gy_out[TT::chunk_f4(row, c)] = o;
+            } else if (valid) {
+              *reinterpret_cast<float4*>(p.g0 + r * W + c * 4) = o;
+            }
+          }
+          if (odd && !last) tmem_st32(tmem_base + lane_off + col_g + c32 * 32, gp);
+        }
+        if (odd && !last) tmem_st_wait();
+        tc_fence_before();
+        if (!last) {
+          fence_proxy_async_smem();
+          mbar_arrive(&a_ready[t]);
+        }
+      }
+    }
+  } else if (warp == 4 * NT) {
+    // ===================== producer ===========================================
+    if (lane == 0) {
+      uint32_t q = 0;
+      for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+        for (int s = 0; s < nsteps; ++s) {
+          const float* src = p.packed + p.off_rev_l + (int64_t)s * W * W;
+          for (int sl = 0; sl < S::kSlicesPerLayer; ++sl, ++q) {
+            const int slot = q % kSlots;
+            const uint32_t ph = (q / kSlots) & 1;
+            mbar_wait(&w_empty[slot], ph ^ 1, abort_flag, p.status, 600 + s);
+            mbar_arrive_expect_tx(&w_full[slot], (uint32_t)kSliceBytes);
+            bulk_g2s(ring + slot * kSliceBytes, src + (int64_t)sl * (kSliceBytes / 4),
+                     (uint32_t)kSliceBytes, &w_full[slot]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== MMA issuer ==========================================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(128, W);
+      const uint32_t a_lbo = 128 * 16, b_lbo = W * 16, sbo = 128;
+      uint32_t q = 0;
+      uint32_t ph_a[NT];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) ph_a[t] = 0;
+      for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+        for (int s = 0; s < nsteps; ++s) {
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            mbar_wait(&a_ready[t], ph_a[t], abort_flag, p.status, 700 + s);
+            ph_a[t] ^= 1;
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(t * 2 * W + W);
+            const uint32_t a_addr = smem_u32(a_base + t * S::kABytes);
+            for (int sl = 0; sl < S::kSlicesPerLayer; ++sl) {
+              const uint32_t qq = q + sl;
+              const int slot = qq % kSlots;
+              mbar_wait(&w_full[slot], (qq / kSlots) & 1, abort_flag, p.status, 800 + s);
+              const uint32_t b_addr = smem_u32(ring + slot * kSliceBytes);
+              for (int ks = 0; ks < S::kStepsPerSlice; ++ks) {
+                const int kk = sl * S::kStepsPerSlice + ks;
+                const uint64_t ad = smem_desc(a_addr + (uint32_t)kk * 2 * a_lbo, a_lbo, sbo);
+                const uint64_t bd = smem_desc(b_addr + (uint32_t)ks * 2 * b_lbo, b_lbo, sbo);
+                mma_tf32_ss(d_tmem, ad, bd, idesc, (uint32_t)(kk > 0));
+              }
+              if (t == NT - 1) mma_commit(&w_empty[slot]);
+            }
+            mma_commit(&d_ready[t]);
+          }
+          q += S::kSlicesPerLayer;
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  for (int i = tid; i < W; i += S::kThreads) atomicAdd(p.dwe + i, dwe_acc[i]);
+}
+
+// ---------------------------------------------------------------------------
+// weight gradient
+// ---------------------------------------------------------------------------
+struct WgradParams {
+  const float* xa_save;   // 2nb+1 slots
+  const float* gy_save;   // 2nb slots
+  float* grads;           // flat gradient vector (atomic accumulate)
+  Layout L;
+  int nb, num_tiles, splits;
+  int* status;
+};
+
+struct WgradSmem {
+  static constexpr int kStages = 3;
+  static constexpr int kSubBytes = 32768;                     // one operand sub-tile
+  static constexpr int kThreads = 6 * 32;
+  static constexpr size_t kBytes = (size_t)kStages * 2 * kSubBytes + 256;
+};
+
+__global__ void __launch_bounds__(WgradSmem::kThreads, 1) mlp_wgrad_umma_kernel(WgradParams p) {
+  using S = WgradSmem;
+  using TT = TrainTile<kW>;
+  constexpr int W = kW;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* stage_base = smem;                            // [stage][xa | gy]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S::kStages * 2 * S::kSubBytes);
+  uint64_t* full = bars;                 // [kStages]
+  uint64_t* empty = bars + S::kStages;   // [kStages]
+  uint64_t* done = bars + 2 * S::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 1);
+  __shared__ int s_abort;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int layer = blockIdx.x + 1;                            // forward layer index 1 .. 2nb
+  const int per = (p.num_tiles + p.splits - 1) / p.splits;
+  const int t0 = blockIdx.y * per;
+  const int t1 = min(p.num_tiles, t0 + per);
+  const int ntiles = max(0, t1 - t0);
+  const int xa_slots = 2 * p.nb + 1, gy_slots = 2 * p.nb;
+
+  if (tid == 0) {
+    s_abort = 0;
+    // a stage is free again when its MMAs retired (1 commit) and the four
+    // column-sum warps have read it (4 arrivals)
+    for (int s = 0; s < S::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 5); }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  volatile int* abort_flag = &s_abort;
+  const int nsub = ntiles * TT::kSubTiles;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int u = 0; u < nsub; ++u) {
+        const int stage = u % S::kStages;
+        const uint32_t ph = (u / S::kStages) & 1;
+        const int64_t tile = t0 + u / TT::kSubTiles;
+        const int sub = u % TT::kSubTiles;
+        mbar_wait(&empty[stage], ph ^ 1, abort_flag, p.status, 900);
+        mbar_arrive_expect_tx(&full[stage], 2u * S::kSubBytes);
+        unsigned char* dst = stage_base + (size_t)stage * 2 * S::kSubBytes;
+        bulk_g2s(dst, p.xa_save + TT::slot_base(tile, xa_slots, layer - 1) +
+                          (int64_t)sub * (S::kSubBytes / 4),
+                 S::kSubBytes, &full[stage]);
+        bulk_g2s(dst + S::kSubBytes, p.gy_save + TT::slot_base(tile, gy_slots, layer - 1) +
+                                         (int64_t)sub * (S::kSubBytes / 4),
+                 S::kSubBytes, &full[stage]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (lane == 0 && nsub > 0) {
+      // both operands MN-major (SWIZZLE_128B_BASE32B atoms, see umma_pack.cuh):
+      // one K step = 8 rows = two 512-byte K atoms
+      const uint32_t idesc = idesc_tf32(128, W) | kIdescAMajorMN | kIdescBMajorMN;
+      for (int u = 0; u < nsub; ++u) {
+        const int stage = u % S::kStages;
+        mbar_wait(&full[stage], (u / S::kStages) & 1, abort_flag, p.status, 901);
+        const uint32_t xa_addr = smem_u32(stage_base + (size_t)stage * 2 * S::kSubBytes);
+        const uint32_t gy_addr = xa_addr + S::kSubBytes;
+        for (int ks = 0; ks < TT::kSubRows / 8; ++ks) {
+          const uint64_t ad = smem_desc_lt(xa_addr + (uint32_t)ks * 1024, TT::kLbo, TT::kSbo, 1);
+          const uint64_t bd = smem_desc_lt(gy_addr + (uint32_t)ks * 1024, TT::kLbo, TT::kSbo, 1);
+          mma_tf32_ss(tmem_base, ad, bd, idesc, (uint32_t)(u > 0 || ks > 0));   // dW += XA^T GY
+        }
+        mma_commit(&empty[stage]);
+      }
+      mma_commit(done);
+    }
+    __syncwarp();
+  } else if (nsub > 0) {
+    // warps 0-3: bias gradient = fp32 column sums of the (unrounded) output
+    // gradients while they sit in shared memory, then the dW flush
+    const int col = tid;                                         // output feature n
+    float bsum = 0.f;
+    for (int u = 0; u < nsub; ++u) {
+      const int stage = u % S::kStages;
+      mbar_wait(&full[stage], (u / S::kStages) & 1, abort_flag, p.status, 903);
+      const unsigned char* gy = stage_base + (size_t)stage * 2 * S::kSubBytes + S::kSubBytes;
+#pragma unroll 8
+      for (int k = 0; k < TT::kSubRows; ++k)
+        bsum += *reinterpret_cast<const float*>(gy + mn32_offset(col, k, TT::kLbo, TT::kSbo));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+    }
+    mbar_wait(done, 0, abort_flag, p.status, 902);
+    tc_fence_after();
+    const int row = tid;                                         // input feature k
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const int j = (layer - 1) >> 1;
+    const bool is_w2 = (layer & 1) == 0;
+    float* dw = p.grads + (is_w2 ? p.L.w2(j) : p.L.w1(j)) + (int64_t)row * W;
+    float* db = p.grads + (is_w2 ? p.L.b2(j) : p.L.b1(j));
+    atomicAdd(db + col, bsum);
+#pragma unroll 1
+    for (int c32 = 0; c32 < W / 32; ++c32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + lane_off + c32 * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 32; ++q) atomicAdd(dw + c32 * 32 + q, __uint_as_float(v[q]));
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace
+
+bool umma_train_supported(const Layout& L) {
+  return umma_supported(L) && L.W == kW;
+}
+
+// ImplicitBCAgent._loss + tape.gradient, tensor-core path (no gradient penalty).
+int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* actions, int64_t N,
+                     const ibc_loss_cfg& c, int64_t global_batch, float* per_example,
+                     float* grad_loss_out, float* energies_out, float* grads, cudaStream_t s) {
+  const Layout& L = h->L;
+  using TT = TrainTile<kW>;
+  const float* P = h->params;
+  const int W = L.W, A = L.A, nb = L.nb;
+  const int64_t n1 = N + 1, R = B * n1;
+  const float gscale = 1.0f / (float)global_batch;
+  const int num_groups = (int)((R + 255) / 256);
+  const int64_t num_tiles = (int64_t)num_groups * kNT;
+  const size_t xa_floats = (size_t)num_tiles * (2 * nb + 1) * TT::kTileFloats;
+  const size_t gy_floats = (size_t)num_tiles * (2 * nb) * TT::kTileFloats;
+  const size_t bytes = Workspace::rounded(xa_floats * 4) + Workspace::rounded(gy_floats * 4) +
+                       Workspace::rounded((size_t)R * W * 4) +
+                       2 * Workspace::rounded((size_t)B * W * 4) +
+                       2 * Workspace::rounded((size_t)R * 4) + 2 * Workspace::rounded((size_t)B * 4);
+  IBC_CUDA(h, h->ws.reserve(bytes));
+  h->ws.reset();
+  float* xa = h->ws.take<float>(xa_floats);
+  float* gy = h->ws.take<float>(gy_floats);
+  float* g0 = h->ws.take<float>((size_t)R * W);
+  float* hp = h->ws.take<float>((size_t)B * W);
+  float* gsum = h->ws.take<float>((size_t)B * W);
+  float* E = h->ws.take<float>(R);
+  float* dE = h->ws.take<float>(R);
+  float* gl = h->ws.take<float>(B);
+
+  IBC_CUDA(h, cudaMemsetAsync(grads, 0, (size_t)L.count * 4, s));
+  IBC_TRY(umma_forward(h, obs, B, actions, n1, hp, E, xa, s));
+  if (energies_out)
+    IBC_CUDA(h, cudaMemcpyAsync(energies_out, E, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
+  IBC_TRY(info_nce(h, E, B, n1, c.softmax_temperature, gscale, per_example, dE, s));
+  if (grad_loss_out) IBC_CUDA(h, cudaMemsetAsync(grad_loss_out, 0, (size_t)B * 4, s));
+  (void)gl;
+
+  const PackedLayout pl = make_packed_layout(L);
+  BwdParams bp;
+  bp.dE = dE; bp.xa_save = xa; bp.gy_save = gy; bp.g0 = g0; bp.packed = h->packed;
+  bp.off_rev_l = pl.rev_l; bp.off_we = pl.vecs + (int64_t)(2 * nb + 1) * W;
+  bp.dwe = grads + L.we; bp.R = R; bp.nb = nb; bp.num_groups = num_groups;
+  bp.status = h->dev_status;
+  static bool attr_done = false;
+  if (!attr_done) {
+    IBC_CUDA(h, cudaFuncSetAttribute(mlp_bwd_umma_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)BwdSmem::kBytes));
+    IBC_CUDA(h, cudaFuncSetAttribute(mlp_wgrad_umma_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)WgradSmem::kBytes));
+    attr_done = true;
+  }
+  {
+    const int grid = num_groups < h->sm_count ? num_groups : h->sm_count;
+    mlp_bwd_umma_kernel<<<grid, BwdSmem::kThreads, BwdSmem::kBytes, s>>>(bp);
+    IBC_LAUNCH_CHECK(h);
+  }
+  {
+    WgradParams wp;
+    wp.xa_save = xa; wp.gy_save = gy; wp.grads = grads; wp.L = L; wp.nb = nb;
+    wp.num_tiles = (int)num_tiles;
+    int splits = h->sm_count / (2 * nb);
+    if (splits < 1) splits = 1;
+    if (splits > num_tiles) splits = (int)num_tiles;
+    wp.splits = splits;
+    wp.status = h->dev_status;
+    dim3 grid(2 * nb, splits);
+    mlp_wgrad_umma_kernel<<<grid, WgradSmem::kThreads, WgradSmem::kBytes, s>>>(wp);
+    IBC_LAUNCH_CHECK(h);
+  }
+  // Dense(1) bias and the first Dense layer (x = [obs tiled, act]) in fp32
+  IBC_TRY(sum_add(h, dE, R, grads + L.be, s));
+  {
+    GemmP g;   // dWp[O:] = act^T . g0   (split-K over rows)
+    g.A = actions; g.lda = A; g.B = g0; g.ldb = W; g.C = grads + L.wp + (int64_t)L.O * W;
+    g.ldc = W; g.M = A; g.N = W; g.K = (int)R; g.k_chunk = 1024; g.atomic = 1;
+    IBC_TRY(gemm(h, g, true, false, s));
+  }
+  IBC_TRY(groupsum(h, g0, B, n1, W, gsum, s));
+  {
+    GemmP g;   // dWp[:O] = obs^T . sum_n g0
+    g.A = obs; g.lda = L.O; g.B = gsum; g.ldb = W; g.C = grads + L.wp; g.ldc = W;
+    g.M = L.O; g.N = W; g.K = (int)B; g.k_chunk = 1024; g.atomic = 1;
+    IBC_TRY(gemm(h, g, true, false, s));
+  }
+  IBC_TRY(colsum_add(h, gsum, W, B, W, grads + L.bp, s));
+  return IBC_OK;
+}
+
+}  // namespace ibc

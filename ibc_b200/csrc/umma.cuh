@@ -149,11 +149,21 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint
   d |= (uint64_t)1 << 46;
   return d;
 }
+// Same with an explicit layout type (bits 61-63): 0 none, 1 128B swizzle with a
+// 32-byte base (the only layout tcgen05 accepts for MN-major 32-bit operands),
+// 2 128B, 4 64B, 6 32B.
+__device__ __forceinline__ uint64_t smem_desc_lt(uint32_t saddr, uint32_t lbo, uint32_t sbo,
+                                                 uint32_t layout_type) {
+  return smem_desc(saddr, lbo, sbo) | ((uint64_t)layout_type << 61);
+}
 // kind::tf32, fp32 accumulate, both operands K-major, M x N.
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
+
+constexpr uint32_t kIdescAMajorMN = 1u << 15;   // A operand is M-major (transposed)
+constexpr uint32_t kIdescBMajorMN = 1u << 16;   // B operand is N-major (transposed)
 
 // D[tmem] (+)= A[smem] . B[smem]^T   (single elected thread)
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,

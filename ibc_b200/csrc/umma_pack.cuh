@@ -1,0 +1,86 @@
+// Packed tcgen05 operand buffer of one MLPEBM (built by pack_kernel in
+// mlp_umma.cu) and small helpers shared by the fused kernels.
+#pragma once
+
+#include "common.cuh"
+
+namespace ibc {
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// tcgen05 kind::tf32 reads the top 19 bits of each fp32 operand (truncation);
+// rounding to nearest-even on the way in halves the error and removes the bias.
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 tf32_rn4(float4 v) {
+  return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+}
+
+// Offsets (in floats) inside the packed operand buffer.
+struct PackedLayout {
+  int W, nb, KP, AP;
+  int64_t fwd_p;     // [KP/4][W][4]           act rows of Wp (B operand of step 0)
+  int64_t fwd_l;     // 2*nb matrices [W/4][W][4]: W1_0, W2_0, W1_1, ...
+  int64_t rev_l;     // 2*nb matrices: W2_{nb-1}^T, W1_{nb-1}^T, ..., W2_0^T, W1_0^T
+  int64_t rev_p;     // [W/4][AP][4]           Wp act rows, B operand of dE/dact
+  int64_t vecs;      // [(2nb+1)][W] epilogue bias vectors, then we[W], be, pad
+  int64_t total;
+};
+
+inline PackedLayout make_packed_layout(const Layout& L) {
+  PackedLayout p;
+  p.W = L.W; p.nb = L.nb;
+  p.KP = round_up(L.A, 8);
+  p.AP = round_up(L.A, 16);
+  const int64_t WW = (int64_t)L.W * L.W;
+  p.fwd_p = 0;
+  p.fwd_l = p.fwd_p + (int64_t)L.W * p.KP;
+  p.rev_l = p.fwd_l + 2 * L.nb * WW;
+  p.rev_p = p.rev_l + 2 * L.nb * WW;
+  p.vecs = p.rev_p + (int64_t)L.W * p.AP;
+  p.total = p.vecs + (int64_t)(2 * L.nb + 2) * L.W + 4;
+  return p;
+}
+
+
+// MN-major tf32 operand layout (UMMA SWIZZLE_128B_BASE32B, layout type 1; the
+// only shared-memory layout tcgen05 accepts for MN-major 32-bit operands).
+// Atoms of 32 MN-elements x 4 K-rows = 512 B: K-row kr is a 128-byte line made
+// of four 32-byte units (8 consecutive MN-elements each); the unit that holds
+// MN-octet o of line kr is (o ^ kr) (Swizzle<2,5,2> on byte addresses).
+// Decoded on hardware with one-hot probes (scripts/diag_mn.py).
+// Byte offset of element (mn, k) for atom strides lbo (MN) and sbo (K):
+__host__ __device__ inline uint32_t mn32_offset(int mn, int k, uint32_t lbo, uint32_t sbo) {
+  const int kr = k & 3, oct = (mn >> 3) & 3;
+  return (uint32_t)(mn >> 5) * lbo + (uint32_t)(k >> 2) * sbo + (uint32_t)kr * 128u +
+         (uint32_t)((oct ^ kr) << 5) + (uint32_t)(mn & 7) * 4u;
+}
+
+// Saved operand tiles of the training path: [tile][slot][sub-tile] where a
+// sub-tile is kSubRows rows x W features stored as the MN-major operand above
+// with MN = features and K = rows ([W/32 MN atoms][kSubRows/4 K atoms][512 B]),
+// so one sub-tile (32 KB) is a single contiguous bulk copy and is directly the
+// A (forward operand) or B (output gradient) operand of dW = XA^T . GY.
+template <int W>
+struct TrainTile {
+  static constexpr int kSubRows = 8192 / W;
+  static constexpr int kSubTiles = 128 / kSubRows;
+  static constexpr int kTileFloats = 128 * W;
+  static constexpr uint32_t kSbo = 512;                        // between 4-row K atoms
+  static constexpr uint32_t kLbo = (kSubRows / 4) * 512;       // between 32-feature MN atoms
+  __host__ __device__ static int64_t slot_base(int64_t tile, int slots, int slot) {
+    return (tile * slots + slot) * (int64_t)kTileFloats;
+  }
+  // float4 index inside a slot of chunk c (features 4c .. 4c+3) of row `row`
+  __host__ __device__ static int chunk_f4(int row, int c) {
+    const int sub = row / kSubRows, rs = row % kSubRows;
+    const int ka = rs >> 2, kr = rs & 3, ma = c >> 3, oct = (c >> 1) & 3, half = c & 1;
+    return sub * (kSubRows * W / 4) + (ma * (kSubRows / 4) + ka) * 32 + kr * 8 +
+           ((oct ^ kr) << 1) + half;
+  }
+};
+
+}  // namespace ibc
