@@ -224,6 +224,21 @@ def run_b200(args):
   t_e2e = max_over_ranks(time.perf_counter() - t0)
   h2d = sum(v.numel() * 4 for v in host_batches[0][0].values()) + host_batches[0][1].numel() * 4
 
+  # per-kernel CUDA-event timings of the tensor-core training step (same steps,
+  # profiling on: events recorded on the launching stream around each phase)
+  kt = None
+  try:
+    net.engine.set_profiling(True)
+    acc = np.zeros(5)
+    for i in range(args.steps):
+      step_dev(i)
+      acc += np.array(net.engine.train_timings())
+    kt = (acc / args.steps).tolist()
+  except Exception as ex:   # noqa: BLE001  (fp32 path has no phase events)
+    kt = None
+  finally:
+    net.engine.set_profiling(False)
+
   # the fused tcgen05 energy forward timed alone on the step's rows
   obs_flat = net._flat_obs(dev_batches[0][0])
   acts = torch.rand(rows, c['act_dim'], device=device) * 2.2 - 1.1
@@ -262,7 +277,7 @@ def run_b200(args):
         'metric': 'ebm_train_energy_evals_per_s', 'value': evals / t_dev, 'unit': 'energy evals/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32 (fp32 FMA backward, tf32 tcgen05 energy forward)', 'data': 'synthetic',
+        'dtype': 'tf32 (tcgen05 kind::tf32 operands, fp32 accumulate; first/last layer and loss in fp32)', 'data': 'synthetic',
         'config': {'workload': c['name'], 'batch_per_gpu': b,
                    'num_counter_examples': n, 'rows_per_step_per_gpu': rows, 'width': c['width'],
                    'depth': c['depth'], 'l2': 'per-step activations (%.2f GB) exceed the 126 MB L2'
@@ -273,11 +288,11 @@ def run_b200(args):
                 'final_loss': losses[-1] if losses else None},
         'gpu_launches': int(launches),
         'clocks': clocks,
-        'roofline': {'kernel': 'train step: per-layer fp32 FMA gemm_kernel launches (fwd+bwd)',
-                     'bound': 'tensor', 'achieved': achieved, 'peak': tf32_peak,
-                     'unit': 'TFLOP/s', 'frac': achieved / tf32_peak, 'traffic': None,
-                     'peak_source': '%s bf16 burst / 2 (tf32 nominal ratio)' % peaks['source'],
-                     'flops_per_step': step_flops},
+        'roofline': None,
+        'roofline_step': {'kernel': 'whole train step (all kernels)', 'bound': 'tensor',
+                          'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s',
+                          'frac': achieved / tf32_peak, 'flops_per_step': step_flops,
+                          'peak_source': '%s bf16 burst / 2 (tf32 nominal ratio)' % peaks['source']},
         'roofline_energy_fwd': None,
         'dfo_inference': {'actions_per_s': 1.0 / t_act, 'ms_per_action': t_act * 1e3,
                           'num_action_samples': c['dfo_samples'],
@@ -294,6 +309,34 @@ def run_b200(args):
           'fp32_path_ms': fwd['fp32'] * 1e3 if fwd.get('fp32') else None}
     else:
       result['roofline_energy_fwd'] = {k: v for k, v in fwd.items()}
+    if kt is not None:
+      # dominant kernel of the step = the one with the largest measured share
+      wflops = 2.0 * c['depth'] * c['width'] ** 2 * rows     # one pass over the W x W layers
+      names = ['mlp_fwd_umma_kernel<128,2> (fused forward + operand save)', 'info_nce_kernel',
+               'mlp_bwd_umma_kernel (fused reverse chain)', 'mlp_wgrad_umma_kernel (dW GEMM)',
+               'first/last-layer fp32 kernels']
+      flops = [rows * fwd_flops_per_row(), 0.0, wflops, wflops, 0.0]
+      # algorithmic HBM bytes: saved operand tiles written / read once
+      tile_bytes = rows * c['width'] * 4.0
+      hbm = [(c['depth'] + 1) * tile_bytes, 0.0, 2 * c['depth'] * tile_bytes + tile_bytes,
+             2 * c['depth'] * tile_bytes, 0.0]
+      top = int(np.argmax(kt))
+      result['kernel_ms'] = dict(zip(['forward', 'info_nce', 'reverse', 'wgrad', 'first_last'], kt))
+      a = flops[top] / (kt[top] * 1e-3) / 1e12 if flops[top] else 0.0
+      gbs = hbm[top] / (kt[top] * 1e-3) / 1e9
+      result['roofline'] = {
+          'kernel': names[top], 'bound': 'tensor', 'achieved': a, 'peak': tf32_peak,
+          'unit': 'TFLOP/s', 'frac': a / tf32_peak, 'traffic': None,
+          'ms_per_launch': kt[top], 'share_of_step': kt[top] / sum(kt),
+          'hbm_algorithmic_GBs': gbs, 'hbm_frac_of_measured': gbs / peaks['hbm'],
+          'peak_source': '%s bf16 burst / 2 (tf32 nominal ratio)' % peaks['source']}
+      result['roofline_kernels'] = [
+          {'kernel': names[i], 'ms': kt[i], 'tflops': flops[i] / (kt[i] * 1e-3) / 1e12 if flops[i] else None,
+           'hbm_GBs': hbm[i] / (kt[i] * 1e-3) / 1e9 if hbm[i] else None} for i in range(5)]
+    else:
+      result['roofline'] = dict(result['roofline_step'])
+      result['roofline']['kernel'] = 'train step: per-layer fp32 FMA gemm_kernel launches'
+      result['roofline']['traffic'] = None
     result['cpu_baseline'] = cpu_baseline(steps=2, warmup=1)
   if world > 1:
     dist.barrier()

@@ -98,6 +98,8 @@ SIGNATURES = {
     'ibc_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                               c_float, c_float, c_float, c_float, c_void_p]),
     'ibc_kernel_status': (c_int, [c_void_p, POINTER(c_int32)]),
+    'ibc_set_profiling': (c_int, [c_void_p, c_int32]),
+    'ibc_get_train_timings': (c_int, [c_void_p, POINTER(c_float)]),
     'ibc_launch_count': (c_int64, []),
     'ibc_reset_launch_count': (None, []),
     'ibc_umma_selftest': (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32,

@@ -80,6 +80,7 @@ int ibc_destroy(ibc_handle* h) {
     cudaDeviceSynchronize();
     if (h->packed) cudaFree(h->packed);
     if (h->dev_status) cudaFree(h->dev_status);
+    for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->ws.base) cudaFree(h->ws.base);
     if (h->ws_outer.base) cudaFree(h->ws_outer.base);
   }
@@ -274,6 +275,25 @@ int ibc_kernel_status(ibc_handle* h, int32_t* status_host) {
   IBC_CUDA(h, cudaMemcpy(&st, h->dev_status, sizeof(int), cudaMemcpyDeviceToHost));
   IBC_CUDA(h, cudaMemset(h->dev_status, 0, sizeof(int)));
   *status_host = st;
+  return IBC_OK;
+}
+
+int ibc_set_profiling(ibc_handle* h, int32_t on) {
+  IBC_ENTER(h);
+  if (on && !h->ev[0])
+    for (int i = 0; i < 6; ++i) IBC_CUDA(h, cudaEventCreate(&h->ev[i]));
+  h->profiling = on != 0;
+  h->ev_valid = false;
+  return IBC_OK;
+}
+
+int ibc_get_train_timings(ibc_handle* h, float* ms_host) {
+  IBC_ENTER(h);
+  if (!ms_host) IBC_FAIL(h, IBC_ERR_INVALID, "ibc_get_train_timings: null argument");
+  if (!h->profiling || !h->ev_valid)
+    IBC_FAIL(h, IBC_ERR_INVALID, "no profiled tensor-core training step has run");
+  IBC_CUDA(h, cudaEventSynchronize(h->ev[5]));
+  for (int i = 0; i < 5; ++i) IBC_CUDA(h, cudaEventElapsedTime(&ms_host[i], h->ev[i], h->ev[i + 1]));
   return IBC_OK;
 }
 

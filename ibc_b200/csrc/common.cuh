@@ -87,6 +87,9 @@ struct ibc_handle {
   float* packed = nullptr;        // tcgen05 operand copies of the weights
   size_t packed_bytes = 0;
   int* dev_status = nullptr;      // kernel-side barrier-timeout flag
+  bool profiling = false;         // record CUDA events around the training kernels
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ev_valid = false;          // a full set of events has been recorded
   ibc::Workspace ws;        // dense-stack passes (reset by each pass)
   ibc::Workspace ws_outer;  // sampler / trainer scratch that outlives a pass
   std::string err;

@@ -431,13 +431,17 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
   float* dE = h->ws.take<float>(R);
   float* gl = h->ws.take<float>(B);
 
+  auto mark = [&](int i) { if (h->profiling) cudaEventRecord(h->ev[i], s); };
   IBC_CUDA(h, cudaMemsetAsync(grads, 0, (size_t)L.count * 4, s));
+  mark(0);
   IBC_TRY(umma_forward(h, obs, B, actions, n1, hp, E, xa, s));
+  mark(1);
   if (energies_out)
     IBC_CUDA(h, cudaMemcpyAsync(energies_out, E, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
   IBC_TRY(info_nce(h, E, B, n1, c.softmax_temperature, gscale, per_example, dE, s));
   if (grad_loss_out) IBC_CUDA(h, cudaMemsetAsync(grad_loss_out, 0, (size_t)B * 4, s));
   (void)gl;
+  mark(2);
 
   const PackedLayout pl = make_packed_layout(L);
   BwdParams bp;
@@ -460,6 +464,7 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
     mlp_bwd_umma_kernel<<<grid, BwdSmem::kThreads, BwdSmem::kBytes, s>>>(bp);
     IBC_LAUNCH_CHECK(h);
   }
+  mark(3);
   {
     WgradParams wp;
     wp.xa_save = xa; wp.gy_save = gy; wp.grads = grads; wp.L = L; wp.nb = nb;
@@ -473,6 +478,7 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
     mlp_wgrad_umma_kernel<<<grid, WgradSmem::kThreads, WgradSmem::kBytes, s>>>(wp);
     IBC_LAUNCH_CHECK(h);
   }
+  mark(4);
   // Dense(1) bias and the first Dense layer (x = [obs tiled, act]) in fp32
   IBC_TRY(sum_add(h, dE, R, grads + L.be, s));
   {
@@ -489,6 +495,8 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
     IBC_TRY(gemm(h, g, true, false, s));
   }
   IBC_TRY(colsum_add(h, gsum, W, B, W, grads + L.bp, s));
+  mark(5);
+  if (h->profiling) h->ev_valid = true;
   return IBC_OK;
 }
 

@@ -116,6 +116,15 @@ class EBMEngine:
     _lib.check(self.lib.ibc_kernel_status(self._h, ctypes.byref(st)), self._h)
     return int(st.value)
 
+  def set_profiling(self, on: bool):
+    _lib.check(self.lib.ibc_set_profiling(self._h, int(bool(on))), self._h)
+
+  def train_timings(self):
+    """ms of {forward, info_nce, reverse chain, weight gradient, first/last layer}."""
+    out = (ctypes.c_float * 5)()
+    _lib.check(self.lib.ibc_get_train_timings(self._h, out), self._h)
+    return [float(x) for x in out]
+
   # -- energy ------------------------------------------------------------------
   def _check_obs_act(self, obs, act, n):
     _check_f32(obs, 'obs')

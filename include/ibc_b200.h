@@ -238,6 +238,14 @@ int ibc_adam_step(float* params, const float* grads, float* m, float* v,
 int64_t ibc_launch_count(void);
 void ibc_reset_launch_count(void);
 
+/* Per-kernel timing of the tensor-core training step (ibc_train_grads on the
+ * TF32 path): with profiling on, CUDA events are recorded on the call's stream
+ * around its phases; ibc_get_train_timings waits for the last step and writes
+ * ms_host[5] = {fused forward, InfoNCE, fused reverse chain, weight-gradient
+ * GEMM, first/last-layer fp32 pieces} in milliseconds. */
+int ibc_set_profiling(ibc_handle* h, int32_t on);
+int ibc_get_train_timings(ibc_handle* h, float* ms_host);
+
 /* Synchronises the device and returns (then clears) the sticky status word the
  * fused kernels write when one of their internal barriers timed out (0 = ok;
  * otherwise the code of the first wait that gave up -- results are invalid). */
