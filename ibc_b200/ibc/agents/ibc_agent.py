@@ -14,10 +14,10 @@ from typing import Optional
 
 import numpy as np
 import torch
-import torch.distributed as dist
 
 from ibc_b200 import engine as eng
 from ibc_b200 import gin_lite as gin
+from ibc_b200 import parallel
 from ibc_b200.ibc import specs
 from ibc_b200.ibc.agents import ibc_policy
 from ibc_b200.ibc.agents import mcmc
@@ -122,7 +122,7 @@ class ImplicitBCAgent(BehavioralCloningAgent):
 
   # -- helpers -----------------------------------------------------------------
   def _num_replicas(self) -> int:
-    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    return parallel.num_replicas()
 
   def _loss_cfg(self):
     # grad_penalty's own gin bindings (gradient_loss.py:24-34)
@@ -261,8 +261,7 @@ class ImplicitBCAgent(BehavioralCloningAgent):
     loss_info, grads = self._loss(experience, weights=weights, training=True, draws=draws)
     if not bool(torch.isfinite(loss_info.loss)):                # check_numerics (:46)
       raise FloatingPointError('Loss is inf or nan')
-    if self._num_replicas() > 1:
-      dist.all_reduce(grads, op=dist.ReduceOp.SUM)              # MirroredStrategy all-reduce
+    parallel.allreduce_gradients(grads)                         # MirroredStrategy all-reduce
     self._optimizer.apply_gradients(self.cloning_network, grads)
     self.train_step_counter += 1
     return loss_info

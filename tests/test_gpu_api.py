@@ -1,0 +1,271 @@
+"""GPU tests of the reference-facing Python surface (ibc_b200.ibc.*): the
+reference's own behavioural tests (ibc/agents/mcmc_test.py) on the mock energy
+network, and agent / policy steps against the oracle on identical draws."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import agent as oagent
+from oracle import mlp_ebm as omlp
+
+pytestmark = pytest.mark.gpu
+
+
+def _mock_energy_network(mean=(0.3, 0.4), scale=1e2):
+  """mcmc_test.py:67-81: E = -(scale * ||a - mean||)^2, any callable network."""
+  mean_t = torch.tensor(mean, dtype=torch.float32).cuda()
+
+  def net(inputs, training=False, step_type=(), network_state=()):
+    _, act = inputs
+    return -(torch.linalg.norm(act - mean_t, dim=1) * scale) ** 2, network_state
+  return net, mean_t
+
+
+def test_batched_categorical_bincount_shapes_and_correct():
+  from ibc_b200.ibc.agents import mcmc
+  # mcmc_test.py:30-43
+  for b in (1, 2):
+    probs = torch.rand(b, 256).cuda()
+    counts = mcmc.categorical_bincount(128, torch.log(probs), 256)
+    assert tuple(counts.shape) == (b, 256)
+    assert counts.sum(1).cpu().tolist() == [128] * b
+  # mcmc_test.py:45-57
+  eps = 1e-6
+  probs = torch.tensor([[eps, eps, 1. - eps], [eps, 1. - eps, eps]]).cuda()
+  counts = mcmc.categorical_bincount(5, torch.log(probs), 3).cpu()
+  assert counts.sum(1).tolist() == [5, 5]
+  assert int(counts[0].argmax()) == 2 and int(counts[1].argmax()) == 1
+
+
+def test_correct_iterative_dfo_on_mock_network():
+  """mcmc_test.py:117-144: B=2, N=2048, 10 iterations, std 0.1."""
+  from ibc_b200.ibc.agents import mcmc
+  torch.manual_seed(0)
+  net, mean = _mock_energy_network()
+  b, n = 2, 2048
+  obs = torch.zeros(b * n, 4).cuda()
+  init = torch.rand(b * n, 2).cuda()
+  probs, actions, _ = mcmc.iterative_dfo(net, b, obs, init, (), n, np.zeros(2, np.float32),
+                                         np.ones(2, np.float32), num_iterations=10,
+                                         iteration_std=0.1)
+  assert tuple(probs.shape) == (b * n,) and tuple(actions.shape) == (b * n, 2)
+  best = actions[int(torch.argmax(probs))]
+  assert float((best - mean).abs().max()) < 0.01
+
+
+def test_correct_langevin_on_mock_network():
+  """mcmc_test.py:146-170: N=128, 25 iterations -> actions[0] within 0.1."""
+  from ibc_b200.ibc.agents import mcmc
+  torch.manual_seed(1)
+  net, mean = _mock_energy_network()
+  b, n = 2, 128
+  obs = torch.zeros(b * n, 4).cuda()
+  init = torch.rand(b * n, 2).cuda()
+  actions, chain = mcmc.langevin_actions_given_obs(
+      net, obs, init, (), np.zeros(2, np.float32), np.ones(2, np.float32), n,
+      num_iterations=25, return_chain=True)
+  assert float((actions[0] - mean).abs().max()) < 0.1
+  assert tuple(chain.actions.shape) == (25, b * n, 2)
+  assert tuple(chain.energies.shape) == (25, b * n)
+  assert tuple(chain.grad_norms.shape) == (25, b * n)
+
+
+def test_langevin_single_step_known_answer():
+  """one noiseless step on the mock energy."""
+  from ibc_b200.ibc.agents import mcmc
+  net, _ = _mock_energy_network()
+  a = torch.tensor([[0.5, 0.5]]).cuda()
+  zeros = torch.zeros(1, 2).cuda()
+  new, e, nrm = mcmc.langevin_step(net, torch.zeros(1, 4).cuda(), a, False, (), (), 0.0, None,
+                                   0.1, 0.1, False, np.zeros(2, np.float32),
+                                   np.ones(2, np.float32), 'inf', None, normal_draws=zeros)
+  assert torch.allclose(new.cpu(), torch.tensor([[0.45, 0.45]]), atol=1e-6)
+  assert abs(float(nrm[0]) - 4000.0) < 1e-2
+
+
+def _build(spec, n_counter, precision, **agent_kw):
+  from ibc_b200.ibc import specs
+  from ibc_b200.ibc.agents import ibc_agent
+  from ibc_b200.ibc.train import get_agent
+  from ibc_b200.networks.mlp_ebm import MLPEBM
+  obs_spec = {'obs': specs.TensorSpec((1, spec.obs_dim))}
+  act_spec = specs.BoundedTensorSpec((spec.act_dim,), minimum=-1.0, maximum=1.0)
+  samp = specs.BoundedTensorSpec((spec.act_dim,), minimum=-1.1, maximum=1.1)
+  net = MLPEBM((obs_spec, act_spec), specs.TensorSpec((1,)), width=spec.width, depth=spec.depth,
+               rate=0.0, layers='ResNetPreActivation', seed=3)
+  net.engine.set_precision(precision)
+  opt = get_agent.Adam(get_agent.ExponentialDecay(1e-3, 100, 0.99))
+  agent = ibc_agent.ImplicitBCAgent(obs_spec, act_spec, samp, net, opt,
+                                    num_counter_examples=n_counter, **agent_kw)
+  return net, agent
+
+
+@pytest.mark.parametrize('langevin', [False, True])
+def test_agent_train_steps_match_oracle(langevin):
+  """ImplicitBCAgent.train (negatives -> loss -> gradients -> Adam) against
+  oracle.agent.train_step on identical uniform / normal draws (fp32 path)."""
+  from ibc_b200 import _lib
+  from ibc_b200 import gin_lite as gin
+  gin.clear_config()
+  spec = omlp.MLPSpec(12, 2, 64, 4)
+  b, n, k = 16, 8, 6
+  kw = dict(fraction_langevin_samples=1.0 if langevin else 0.0, add_grad_penalty=langevin,
+            compute_mse=True)
+  if langevin:
+    gin.parse_config('langevin_actions_given_obs.num_iterations = %d\n'
+                     'grad_penalty.grad_margin = 0.02' % k)
+  try:
+    net, agent = _build(spec, n, _lib.PRECISION_FP32, **kw)
+    flat = net.params.detach().cpu().clone()
+    state = oagent.adam_init(flat)
+    cfg = oagent.AgentConfig(num_counter_examples=n,
+                             fraction_langevin_samples=kw['fraction_langevin_samples'],
+                             add_grad_penalty=langevin, compute_mse=True,
+                             langevin_num_iterations=k, grad_margin=0.02)
+    mn, mx = torch.full((2,), -1.1), torch.full((2,), 1.1)
+    g = torch.Generator().manual_seed(5)
+    for step in range(3):
+      obs = torch.randn(b, 1, spec.obs_dim, generator=g)
+      act = torch.rand(b, 2, generator=g) * 2 - 1
+      u = torch.rand(b, n, 2, generator=g)
+      normals = torch.randn(k, b * n, 2, generator=g)
+      draws = {'uniform_u': u.cuda()}
+      odraws = {}
+      if langevin:
+        draws['langevin_normals'] = normals.cuda()
+        odraws['langevin_normals'] = normals
+
+      def make_energy_fn(theta):
+        return lambda o, a: omlp.energy(theta, spec, o, a)
+
+      flat, want_loss, _, want_metrics = oagent.train_step(
+          make_energy_fn, flat, state, cfg, obs.reshape(b, -1), act, mn, mx, u, 1e-3, **odraws)
+      info = agent._train((({'obs': obs}, act), ()), draws=draws)
+      assert abs(float(info.loss) - float(want_loss)) <= 2e-4 * abs(float(want_loss))
+      got = net.params.detach().cpu()
+      # Adam's first steps move every weight by ~lr: compare the update
+      assert float((got - flat).abs().max()) < 2e-5, step
+      ld = agent.last_losses_dict
+      assert abs(float(ld['mse_counter_examples']) - float(want_metrics['mse_counter_examples'])) < 1e-5
+      if langevin:
+        assert abs(float(ld['grad_loss']) - float(want_metrics['grad_loss'])) <= 1e-3 * abs(
+            float(want_metrics['grad_loss'])) + 1e-7
+        assert abs(float(ld['final_energies_avg']) - float(want_metrics['final_energies_avg'])) < 1e-3
+    assert agent.train_step_counter == 3
+  finally:
+    gin.clear_config()
+
+
+def test_agent_tf32_training_reduces_loss():
+  """The tensor-core training path trains: InfoNCE on a fixed batch decreases."""
+  from ibc_b200 import _lib
+  spec = omlp.MLPSpec(20, 2, 128, 4)
+  net, agent = _build(spec, 64, _lib.PRECISION_TF32, fraction_langevin_samples=0.0,
+                      add_grad_penalty=False)
+  agent._optimizer.learning_rate = 1e-3
+  g = torch.Generator().manual_seed(0)
+  obs = torch.randn(64, 1, spec.obs_dim, generator=g)
+  act = torch.tanh(obs[:, 0, :2])            # the action is a function of the observation
+  losses = [float(agent.train((({'obs': obs}, act), ())).loss) for _ in range(60)]
+  assert net.engine.kernel_status() == 0
+  assert losses[0] > math.log(65) - 0.3
+  assert losses[-1] < losses[0] - 0.5, (losses[0], losses[-1])
+  ev = agent.get_eval_loss((({'obs': obs}, act), ()))
+  assert 'ebm_total_loss' in ev and torch.isfinite(ev['ebm_total_loss'])
+
+
+def test_policy_dfo_action():
+  from ibc_b200 import _lib
+  from ibc_b200.ibc import specs
+  from ibc_b200.ibc.agents import ibc_policy
+  spec = omlp.MLPSpec(20, 2, 128, 4)
+  net, agent = _build(spec, 8, _lib.PRECISION_TF32, fraction_langevin_samples=0.0,
+                      add_grad_penalty=False)
+  pol = ibc_policy.IbcPolicy(agent.time_step_spec, agent.action_spec,
+                             agent._action_sampling_spec, net, num_action_samples=512,
+                             use_dfo=True, use_langevin=False)
+  ts = specs.restart({'obs': torch.randn(1, 1, spec.obs_dim)})
+  torch.manual_seed(3)
+  dist = pol.distribution(ts).action
+  assert tuple(dist.probs.shape) == (512,) and tuple(dist.mapped_values.shape) == (512, 2)
+  assert abs(float(dist.probs.sum()) - 1.0) < 1e-4
+  mode = dist.mode()                                           # flat arg max, [1, A]
+  assert tuple(mode.shape) == (1, 2)
+  torch.manual_seed(3)
+  greedy = ibc_policy.GreedyPolicy(pol).action(ts).action     # same draws -> same action
+  assert torch.allclose(greedy, torch.clamp(mode, -1.0, 1.0))
+  # batched observations: one action per observation
+  ts3 = specs.restart({'obs': torch.randn(3, 1, spec.obs_dim)})
+  a3 = ibc_policy.GreedyPolicy(pol).action(ts3).action
+  assert tuple(a3.shape) == (3, 2) and bool((a3.abs() <= 1.0).all())
+
+
+def test_policy_langevin_action_matches_oracle():
+  """IbcPolicy with Langevin + optimize_again + get_probabilities vs the oracle
+  on the same draws (fp32 path, D4RL-style settings)."""
+  from ibc_b200 import _lib
+  from ibc_b200 import gin_lite as gin
+  from ibc_b200.ibc import specs
+  from ibc_b200.ibc.agents import ibc_policy
+  gin.clear_config()
+  k = 8
+  gin.parse_config('langevin_actions_given_obs.num_iterations = %d\n'
+                   'langevin_actions_given_obs.sampler_stepsize_init = 0.5\n'
+                   'langevin_actions_given_obs.delta_action_clip = 0.5\n'
+                   'langevin_actions_given_obs.noise_scale = 0.5' % k)
+  try:
+    spec = omlp.MLPSpec(12, 3, 64, 2)
+    net, agent = _build(spec, 8, _lib.PRECISION_FP32, fraction_langevin_samples=0.0,
+                        add_grad_penalty=False)
+    n, b = 64, 2
+    pol = ibc_policy.IbcPolicy(agent.time_step_spec, agent.action_spec,
+                               agent._action_sampling_spec, net, num_action_samples=n,
+                               use_dfo=False, use_langevin=True, optimize_again=True,
+                               again_stepsize_init=1e-5, inference_langevin_noise_scale=0.5)
+    g = torch.Generator().manual_seed(9)
+    obs = torch.randn(b, 1, spec.obs_dim, generator=g)
+    u = torch.rand(b * n, 3, generator=g)
+    n1 = torch.randn(k, b * n, 3, generator=g)
+    n2 = torch.randn(k, b * n, 3, generator=g)
+    step = pol.distribution(specs.restart({'obs': obs}),
+                            draws={'uniform_u': u.cuda(), 'langevin_normals': n1.cuda(),
+                                   'again_normals': n2.cuda()})
+    flat = net.params.detach().cpu()
+    mn, mx = torch.full((3,), -1.1), torch.full((3,), 1.1)
+    energy_fn = lambda o, a: omlp.energy(flat, spec, o, a)
+    want_probs, want_actions = oagent.policy_distribution(
+        energy_fn, obs.reshape(b, -1), n, mn, mx, u, use_dfo=False, use_langevin=True,
+        langevin_normals=n1, optimize_again=True, again_normals=n2, again_stepsize_init=1e-5,
+        inference_langevin_noise_scale=0.5,
+        langevin_kwargs=dict(num_iterations=k, sampler_stepsize_init=0.5, delta_action_clip=0.5,
+                             noise_scale=0.5))
+    got_a = step.action.mapped_values.cpu()
+    assert float((got_a - want_actions).abs().max()) < 5e-3 * 2.2
+    assert float((step.action.probs.cpu() - want_probs).abs().max()) < 1e-3
+  finally:
+    gin.clear_config()
+
+
+def test_gin_configured_network_and_errors():
+  from ibc_b200 import gin_lite as gin
+  from ibc_b200.ibc import specs
+  from ibc_b200.networks.mlp_ebm import MLPEBM
+  gin.clear_config()
+  gin.parse_config("MLPEBM.layers = 'ResNetPreActivation'\nMLPEBM.width = 128\n"
+                   "MLPEBM.depth = 4\nMLPEBM.rate = 0.0\nResNetLayer.normalizer = None")
+  try:
+    obs_spec = {'a': specs.TensorSpec((2, 3)), 'b': specs.TensorSpec((2, 7))}
+    act_spec = specs.BoundedTensorSpec((2,), minimum=-1, maximum=1)
+    net = MLPEBM((obs_spec, act_spec), specs.TensorSpec((1,)))
+    assert (net.width, net.depth, net.obs_dim, net.act_dim) == (128, 4, 20, 2)
+    obs = {'a': torch.randn(6, 2, 3).cuda(), 'b': torch.randn(6, 2, 7).cuda()}
+    e, state = net((obs, torch.rand(6, 2).cuda()), training=False)
+    assert tuple(e.shape) == (6,) and state == ()
+    with pytest.raises(ValueError):
+      MLPEBM((obs_spec, act_spec), specs.TensorSpec((1,)), dense_layer_type='nope')
+    with pytest.raises(AssertionError):
+      MLPEBM((obs_spec, act_spec), specs.TensorSpec((1,)), depth=3)
+  finally:
+    gin.clear_config()
