@@ -55,6 +55,12 @@ bool umma_supported(const Layout& L);
 int umma_pack_params(ibc_handle* h, cudaStream_t s);
 int umma_forward(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
                  float* hp, float* E, float* xa_save, cudaStream_t s);
+// width-128 kernels with the activations in tensor memory (mlp_umma_ts.cu)
+int ts_tiles_per_cta(ibc_handle* h, int64_t R);
+int umma_forward_ts(ibc_handle* h, const float* act, int64_t R, int64_t n, const float* hp,
+                    float* E, float* xa_save, int nt, cudaStream_t s);
+int umma_backward_ts(ibc_handle* h, const float* dE, int64_t R, const float* xa_save,
+                     float* gy_save, float* g0, float* dwe, int nt, cudaStream_t s);
 // tcgen05 training path (mlp_umma_train.cu): W == 128, no gradient penalty.
 bool umma_train_supported(const Layout& L);
 int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* actions, int64_t N,

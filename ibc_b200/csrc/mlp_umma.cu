@@ -16,6 +16,8 @@
 // copies), 1 MMA warp (single elected thread issues tcgen05.mma / commit).
 // With NT = 2 the MMA of one tile overlaps the epilogue of the other and each
 // weight slice is read once per 256 rows.
+#include <stdlib.h>
+
 #include "gemm_simt.cuh"
 #include "mlp.cuh"
 #include "ops.cuh"
@@ -66,6 +68,12 @@ __global__ void pack_kernel(const float* __restrict__ P, Layout L, PackedLayout 
       const int wq = (int)(e & 3), a = (int)((e >> 2) % pl.AP), wc = (int)((e >> 2) / pl.AP);
       const int w = wc * 4 + wq;
       v = (a < L.A) ? P[L.wp + (int64_t)(L.O + a) * W + w] : 0.f;
+    } else if (i >= pl.raw) {              // raw per-step biases (residual kept in registers)
+      const int64_t e = i - pl.raw;
+      const int s = (int)(e / W), w = (int)(e % W);
+      if (s == 0) v = 0.f;
+      else if (s & 1) v = P[L.b1((s - 1) >> 1) + w];
+      else v = P[L.b2((s >> 1) - 1) + w];
     } else {
       const int64_t e = i - pl.vecs;
       const int s = (int)(e / W), w = (int)(e % W);
@@ -104,6 +112,7 @@ struct FwdParams {
   // fp32) are also written to global memory in the tile layout of
   // train_tile_offset() for the backward kernels.
   float* xa_save;
+  long long* dbg;   // optional timeline of CTA 0, group 0: [step][tile][5] clock64 stamps
 };
 
 template <int W, int NT>
@@ -211,6 +220,8 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
         mbar_wait(&d_ready[t], ph_d, abort_flag, p.status, 100 + i);
         ph_d ^= 1;
         tc_fence_after();
+        const bool stamp = p.dbg && blockIdx.x == 0 && g == (int)blockIdx.x && row == 0 && i < 64;
+        if (stamp) p.dbg[(i * NT + t) * 5 + 0] = clock64();
         const bool is_h = (i & 1) == 0;
         const uint32_t taddr = tmem_base + lane_off + (is_h ? col_h : col_v);
         const float* bias = vecs + (size_t)i * W;
@@ -260,9 +271,11 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
             emit_chunks<true, W>(v, bias, a_tile, c32, row, g_slot);
           }
           if (i == 0) tmem_st_wait();
+          if (stamp) p.dbg[(i * NT + t) * 5 + 1] = clock64();
           tc_fence_before();
           fence_proxy_async_smem();
           mbar_arrive(&a_ready[t]);
+          if (stamp) p.dbg[(i * NT + t) * 5 + 2] = clock64();
         }
       }
     }
@@ -308,6 +321,8 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
             mbar_wait(&a_ready[t], ph_a[t], abort_flag, p.status, 300 + i);
             ph_a[t] ^= 1;
             tc_fence_after();
+            const bool mstamp = p.dbg && blockIdx.x == 0 && g == (int)blockIdx.x && i < 64;
+            if (mstamp) p.dbg[(i * NT + t) * 5 + 3] = clock64();
             const uint32_t d_tmem = tmem_base + (uint32_t)(t * 2 * W + (to_h ? 0 : W));
             const uint32_t a_addr = smem_u32(a_base + t * S::kABytes);
             for (int s = 0; s < nsl; ++s) {
@@ -327,6 +342,7 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
               if (t == NT - 1) mma_commit(&w_empty[slot]);
             }
             mma_commit(&d_ready[t]);
+            if (mstamp) p.dbg[(i * NT + t) * 5 + 4] = clock64();
           }
           q += nsl;
         }
@@ -381,12 +397,13 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bpac
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   volatile int* abort_flag = &s_abort;
-  const uint32_t a_col = 256;   // tensor-memory copy of A for mode 1
+  // tensor-memory copy of A for the TS modes (23 / 24 probe other column offsets)
+  const uint32_t a_col = (mode == 23) ? 128 : ((mode == 24) ? 384 : 256);
 
   if (warp < 4) {
     const int row = tid;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    if (mode == 0) {
+    if (mode == 0 || mode == 20 || mode == 22) {
       for (int c = 0; c < K / 4; ++c)
         a_tile[c * 128 + row] = *reinterpret_cast<const float4*>(A + (int64_t)row * K + c * 4);
       fence_proxy_async_smem();
@@ -415,7 +432,36 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bpac
   }
   __syncthreads();
   tc_fence_after();
-  if (warp == 4 && lane == 0) {
+  if (warp == 4 && lane == 0 && mode >= 20) {
+    // MMA issue-rate microbenchmark: 16 passes over the K steps, results unused.
+    // 20: A,B from shared memory (no swizzle); 21: A from tensor memory;
+    // 22: A,B descriptors in the 128B-swizzle K-major form (timing only)
+    mbar_wait(&bars[0], 0, abort_flag, status, 1);
+    const uint32_t idesc = idesc_tf32(128, N);
+    const uint32_t a_lbo = 128 * 16, b_lbo = (uint32_t)N * 16, sbo = 128;
+    const int nk = K / 8;
+    const long long t0 = clock64();
+    for (int rep = 0; rep < 16; ++rep)
+      for (int ks = 0; ks < nk; ++ks) {
+        if (mode == 22) {
+          const uint32_t ao = (uint32_t)(ks & 3) * 32 + (uint32_t)(ks >> 2) * (128 * 128);
+          const uint32_t bo = (uint32_t)(ks & 3) * 32 + (uint32_t)(ks >> 2) * ((uint32_t)N * 128);
+          mma_tf32_ss(tmem_base, smem_desc_lt(smem_u32(a_tile) + ao, 16, 1024, 2),
+                      smem_desc_lt(smem_u32(b_tile) + bo, 16, 1024, 2), idesc, 1);
+        } else if (mode == 21 || mode == 23 || mode == 24) {
+          const uint64_t bd = smem_desc(smem_u32(b_tile) + (uint32_t)ks * 2 * b_lbo, b_lbo, sbo);
+          mma_tf32_ts(tmem_base, tmem_base + a_col + ks * 8, bd, idesc, 1);
+        } else {
+          const uint64_t bd = smem_desc(smem_u32(b_tile) + (uint32_t)ks * 2 * b_lbo, b_lbo, sbo);
+          const uint64_t ad = smem_desc(smem_u32(a_tile) + (uint32_t)ks * 2 * a_lbo, a_lbo, sbo);
+          mma_tf32_ss(tmem_base, ad, bd, idesc, 1);
+        }
+      }
+    mma_commit(&bars[1]);
+    mbar_wait(&bars[1], 0, abort_flag, status, 2);
+    const long long t1 = clock64();
+    atomicExch(status, (int)((t1 - t0) / (16 * nk)));      // cycles per MMA
+  } else if (warp == 4 && lane == 0) {
     mbar_wait(&bars[0], 0, abort_flag, status, 1);
     const uint32_t idesc = idesc_tf32(128, N);
     const uint32_t a_lbo = 128 * 16, b_lbo = (uint32_t)N * 16, sbo = 128;
@@ -529,12 +575,44 @@ int umma_forward(ibc_handle* h, const float* obs, int64_t B, const float* act, i
     g.bias = h->params + L.bp; g.M = (int)B; g.N = L.W; g.K = L.O;
     IBC_TRY(gemm(h, g, false, false, s));
   }
+  // Experimental variant with the activations in tensor memory (mlp_umma_ts.cu):
+  // correct, but measured slower on B200 (0.44 vs 0.30 ms on 131 584 rows), so
+  // it is opt-in for tuning only.
+  static const bool use_ts = getenv("IBC_TMEM_ACTIVATIONS") != nullptr;
+  if (L.W == 128 && use_ts) {
+    const int nt = xa_save ? 2 : ts_tiles_per_cta(h, R);
+    return umma_forward_ts(h, act, R, n, hp, E, xa_save, nt, s);
+  }
   FwdParams p;
   p.act = act; p.hp = hp; p.packed = h->packed; p.E = E; p.R = R; p.n_per_obs = n;
   p.nb = L.nb; p.A = L.A; p.KP = pl.KP;
   p.off_fwd_p = pl.fwd_p; p.off_fwd_l = pl.fwd_l; p.off_vecs = pl.vecs;
   p.status = h->dev_status;
   p.xa_save = xa_save;
+  p.dbg = nullptr;
+  static const bool want_dbg = getenv("IBC_DBG_TIMELINE") != nullptr;
+  if (want_dbg) {
+    IBC_CUDA(h, cudaMalloc((void**)&p.dbg, 64 * 2 * 5 * sizeof(long long)));
+    IBC_CUDA(h, cudaMemsetAsync(p.dbg, 0, 64 * 2 * 5 * sizeof(long long), s));
+  }
+  struct DbgDump {
+    long long* d; int nsteps, nt; cudaStream_t s;
+    ~DbgDump() {
+      if (!d) return;
+      cudaStreamSynchronize(s);
+      std::vector<long long> hbuf(64 * 2 * 5);
+      cudaMemcpy(hbuf.data(), d, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      cudaFree(d);
+      long long t0 = hbuf[3];
+      fprintf(stderr, "[ibc timeline] step tile | mma_start mma_issued | epi_start epi_done arrived (cycles from first MMA)\n");
+      for (int i = 0; i < nsteps && i < 64; ++i)
+        for (int t = 0; t < nt; ++t) {
+          const long long* e = &hbuf[(i * nt + t) * 5];
+          fprintf(stderr, "[ibc timeline] %3d %d | %8lld %8lld | %8lld %8lld %8lld\n", i, t,
+                  e[3] - t0, e[4] - t0, e[0] - t0, e[1] ? e[1] - t0 : 0, e[2] ? e[2] - t0 : 0);
+        }
+    }
+  } dump{p.dbg, 2 * L.nb + 1, L.W == 128 ? 2 : 1, s};
   if (L.W == 128) {
     p.num_groups = (int)((R + 255) / 256);
     IBC_TRY((launch_fwd<128, 2>(h, p, s)));
@@ -548,7 +626,8 @@ int umma_forward(ibc_handle* h, const float* obs, int64_t B, const float* act, i
 int umma_selftest(const float* A, const float* Bt, int N, int K, int mode, float* D,
                   int* status_host, cudaStream_t s) {
   ibc_handle* h = nullptr;
-  if (N < 16 || N > 256 || (N % 16) || K < 8 || K > 128 || (K % 8) || (mode == 1 && (K % 32)))
+  if (N < 16 || N > 256 || (N % 16) || K < 8 || K > 128 || (K % 8) ||
+      ((mode == 1 || mode == 21 || mode == 23 || mode == 24) && (K % 32)))
     IBC_FAIL(h, IBC_ERR_INVALID, "umma_selftest: need 16<=N<=256 (x16), 8<=K<=128 (x8; x32 for mode 1)");
   float* bp = nullptr;
   int* st = nullptr;

@@ -17,6 +17,8 @@
 //       epilogue warps while the tiles sit in shared memory.
 //   first / last layer pieces (K = act_dim, obs_dim; Dense(1)) reuse the fp32
 //       kernels: they are O(R * W) work.
+#include <stdlib.h>
+
 #include "gemm_simt.cuh"
 #include "mlp.cuh"
 #include "ops.cuh"
@@ -263,6 +265,39 @@ __global__ void __launch_bounds__(BwdSmem::kThreads, 1) mlp_bwd_umma_kernel(BwdP
   for (int i = tid; i < W; i += S::kThreads) atomicAdd(p.dwe + i, dwe_acc[i]);
 }
 
+// dWp_act[a, w] += sum_r act[r, a] * g0[r, w]: one thread per output feature w
+// streams 256 rows (coalesced g0 reads, broadcast action reads), A <= 32
+// accumulators in registers, one atomic per (a, w) per block.
+template <int AMAX>
+__global__ void __launch_bounds__(kW) act_wgrad_kernel(const float* __restrict__ act,
+                                                        const float* __restrict__ g0, int64_t R,
+                                                        int A, float* __restrict__ dw) {
+  __shared__ float s_act[64 * AMAX];
+  const int w = threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * 256;
+  const int64_t r1 = min(R, r0 + 256);
+  float acc[AMAX];
+#pragma unroll
+  for (int a = 0; a < AMAX; ++a) acc[a] = 0.f;
+  for (int64_t rb = r0; rb < r1; rb += 64) {
+    const int nr = (int)min((int64_t)64, r1 - rb);
+    __syncthreads();
+    for (int i = w; i < nr * AMAX; i += kW) {
+      const int k = i / AMAX, a = i % AMAX;
+      s_act[i] = (a < A) ? act[(rb + k) * A + a] : 0.f;
+    }
+    __syncthreads();
+    for (int k = 0; k < nr; ++k) {
+      const float g = g0[(rb + k) * kW + w];
+#pragma unroll
+      for (int a = 0; a < AMAX; ++a) acc[a] = fmaf(s_act[k * AMAX + a], g, acc[a]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < AMAX; ++a)
+    if (a < A) atomicAdd(dw + (int64_t)a * kW + w, acc[a]);
+}
+
 // ---------------------------------------------------------------------------
 // weight gradient
 // ---------------------------------------------------------------------------
@@ -443,23 +478,30 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
   (void)gl;
   mark(2);
 
-  const PackedLayout pl = make_packed_layout(L);
-  BwdParams bp;
-  bp.dE = dE; bp.xa_save = xa; bp.gy_save = gy; bp.g0 = g0; bp.packed = h->packed;
-  bp.off_rev_l = pl.rev_l; bp.off_we = pl.vecs + (int64_t)(2 * nb + 1) * W;
-  bp.dwe = grads + L.we; bp.R = R; bp.nb = nb; bp.num_groups = num_groups;
-  bp.status = h->dev_status;
   static bool attr_done = false;
   if (!attr_done) {
-    IBC_CUDA(h, cudaFuncSetAttribute(mlp_bwd_umma_kernel,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)BwdSmem::kBytes));
     IBC_CUDA(h, cudaFuncSetAttribute(mlp_wgrad_umma_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)WgradSmem::kBytes));
     attr_done = true;
   }
-  {
+  static const bool use_ts = getenv("IBC_TMEM_ACTIVATIONS") != nullptr;
+  if (use_ts) {
+    IBC_TRY(umma_backward_ts(h, dE, R, xa, gy, g0, grads + L.we, kNT, s));
+  } else {
+    const PackedLayout pl = make_packed_layout(L);
+    BwdParams bp;
+    bp.dE = dE; bp.xa_save = xa; bp.gy_save = gy; bp.g0 = g0; bp.packed = h->packed;
+    bp.off_rev_l = pl.rev_l; bp.off_we = pl.vecs + (int64_t)(2 * nb + 1) * W;
+    bp.dwe = grads + L.we; bp.R = R; bp.nb = nb; bp.num_groups = num_groups;
+    bp.status = h->dev_status;
+    static bool bwd_attr = false;
+    if (!bwd_attr) {
+      IBC_CUDA(h, cudaFuncSetAttribute(mlp_bwd_umma_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)BwdSmem::kBytes));
+      bwd_attr = true;
+    }
     const int grid = num_groups < h->sm_count ? num_groups : h->sm_count;
     mlp_bwd_umma_kernel<<<grid, BwdSmem::kThreads, BwdSmem::kBytes, s>>>(bp);
     IBC_LAUNCH_CHECK(h);
@@ -481,11 +523,13 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
   mark(4);
   // Dense(1) bias and the first Dense layer (x = [obs tiled, act]) in fp32
   IBC_TRY(sum_add(h, dE, R, grads + L.be, s));
-  {
-    GemmP g;   // dWp[O:] = act^T . g0   (split-K over rows)
-    g.A = actions; g.lda = A; g.B = g0; g.ldb = W; g.C = grads + L.wp + (int64_t)L.O * W;
-    g.ldc = W; g.M = A; g.N = W; g.K = (int)R; g.k_chunk = 1024; g.atomic = 1;
-    IBC_TRY(gemm(h, g, true, false, s));
+  {  // dWp[O:] = act^T . g0 : K = all rows, M = act_dim (tiny) -> row-streaming kernel
+    const int blocks = (int)((R + 255) / 256);
+    float* dwa = grads + L.wp + (int64_t)L.O * W;
+    if (A <= 2) act_wgrad_kernel<2><<<blocks, kW, 0, s>>>(actions, g0, R, A, dwa);
+    else if (A <= 8) act_wgrad_kernel<8><<<blocks, kW, 0, s>>>(actions, g0, R, A, dwa);
+    else act_wgrad_kernel<32><<<blocks, kW, 0, s>>>(actions, g0, R, A, dwa);
+    IBC_LAUNCH_CHECK(h);
   }
   IBC_TRY(groupsum(h, g0, B, n1, W, gsum, s));
   {

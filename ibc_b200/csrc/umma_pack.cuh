@@ -27,6 +27,7 @@ struct PackedLayout {
   int64_t rev_l;     // 2*nb matrices: W2_{nb-1}^T, W1_{nb-1}^T, ..., W2_0^T, W1_0^T
   int64_t rev_p;     // [W/4][AP][4]           Wp act rows, B operand of dE/dact
   int64_t vecs;      // [(2nb+1)][W] epilogue bias vectors, then we[W], be, pad
+  int64_t raw;       // [(2nb+1)][W] per-step raw biases: zeros, b1_0, b2_0, b1_1, ...
   int64_t total;
 };
 
@@ -41,7 +42,8 @@ inline PackedLayout make_packed_layout(const Layout& L) {
   p.rev_l = p.fwd_l + 2 * L.nb * WW;
   p.rev_p = p.rev_l + 2 * L.nb * WW;
   p.vecs = p.rev_p + (int64_t)L.W * p.AP;
-  p.total = p.vecs + (int64_t)(2 * L.nb + 2) * L.W + 4;
+  p.raw = p.vecs + (int64_t)(2 * L.nb + 2) * L.W + 4;
+  p.total = p.raw + (int64_t)(2 * L.nb + 1) * L.W;
   return p;
 }
 
