@@ -52,6 +52,13 @@ class LossCfg(Structure):
               ('square_grad_penalty', c_int32), ('grad_loss_weight', c_float)]
 
 
+class PixelArch(Structure):
+  _fields_ = [('seq_len', c_int32), ('height', c_int32), ('width', c_int32),
+              ('channels', c_int32), ('target_height', c_int32),
+              ('target_width', c_int32), ('act_dim', c_int32),
+              ('value_width', c_int32), ('value_blocks', c_int32)]
+
+
 # name -> (restype, argtypes); must list every symbol include/ibc_b200.h declares
 SIGNATURES = {
     'ibc_create': (c_int, [POINTER(MlpArch), c_int, POINTER(c_void_p)]),
@@ -97,6 +104,20 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p]),
     'ibc_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                               c_float, c_float, c_float, c_float, c_void_p]),
+    'ibc_pixel_create': (c_int, [POINTER(PixelArch), c_int, POINTER(c_void_p)]),
+    'ibc_pixel_destroy': (c_int, [c_void_p]),
+    'ibc_pixel_last_error': (c_char_p, [c_void_p]),
+    'ibc_pixel_param_count': (c_int64, [POINTER(PixelArch)]),
+    'ibc_pixel_bind_params': (c_int, [c_void_p, c_void_p]),
+    'ibc_pixel_encode': (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
+    'ibc_pixel_energy': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                 c_void_p]),
+    'ibc_pixel_dfo': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                              c_void_p, c_float, c_int32, c_float, c_void_p, c_void_p,
+                              c_uint64, c_void_p, c_void_p]),
+    'ibc_pixel_train_grads': (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_int64,
+                                      POINTER(LossCfg), c_int64, c_void_p, c_void_p, c_void_p,
+                                      c_void_p]),
     'ibc_kernel_status': (c_int, [c_void_p, POINTER(c_int32)]),
     'ibc_set_profiling': (c_int, [c_void_p, c_int32]),
     'ibc_get_train_timings': (c_int, [c_void_p, POINTER(c_float)]),
@@ -132,10 +153,10 @@ _EXC = {IBC_ERR_INVALID: ValueError, IBC_ERR_UNSUPPORTED: NotImplementedError,
         IBC_ERR_CUDA: IbcError, IBC_ERR_NOT_FINITE: FloatingPointError}
 
 
-def check(rc: int, handle=None):
+def check(rc: int, handle=None, pixel=False):
   if rc == IBC_OK:
     return
-  msg = load().ibc_last_error(handle)
+  msg = (load().ibc_pixel_last_error if pixel else load().ibc_last_error)(handle)
   msg = msg.decode('utf-8', 'replace') if msg else 'error %d' % rc
   raise _EXC.get(rc, IbcError)(msg)
 

@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
       }
       if (p.gateC) v = (p.gateC[(int64_t)m * p.ldgc + n] > 0.f) ? v : 0.f;
       if (first && p.res) v += p.res[(int64_t)m * p.ldres + n];
+      if (p.relu_out) v = fmaxf(v, 0.f);
       float* c = p.C + (int64_t)m * p.ldc + n;
       if (p.atomic) atomicAdd(c, v); else *c = v;
     }

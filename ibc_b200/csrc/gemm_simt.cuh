@@ -9,7 +9,8 @@ namespace ibc {
 
 enum { AOP_ID = 0, AOP_RELU = 1, AOP_GATE = 2 };
 
-// C[M,N] (+)= ((op(A) * B) * alpha + bias + rowbias) (.) (gateC > 0) + res
+// C[M,N] (+)= f(((op(A) * B) * alpha + bias + rowbias) (.) (gateC > 0) + res)
+//   f = identity, or max(., 0) when relu_out
 //   op(A)(m,k): A(m,k), relu(A(m,k)) or A(m,k) * (gateA(m,k) > 0)
 //   A(m,k) = TA ? A[k*lda + m] : A[m*lda + k]
 //   B(k,n) = TB ? B[n*ldb + k] : B[k*ldb + n]
@@ -26,6 +27,7 @@ struct GemmP {
   int aop = AOP_ID;
   int k_chunk = 0;   // K elements per grid.z slice (0 = all of K)
   int atomic = 0;    // accumulate into C with atomicAdd
+  int relu_out = 0;  // C = max(C, 0) (not with split-K)
   float alpha = 1.f;
 };
 

@@ -1,6 +1,8 @@
 // Internal C++ entry points behind the C-ABI (api.cu).
 #pragma once
 
+#include <functional>
+
 #include "common.cuh"
 
 namespace ibc {
@@ -16,6 +18,10 @@ int dfo(ibc_handle* h, const float* obs, int64_t B, float* actions, int64_t n, c
         const float* mx, float temperature, int num_iterations, float iteration_std,
         const double* uniforms, const float* normals, uint64_t seed, float* probs,
         cudaStream_t s);
+int dfo_generic(ibc_handle* h, int A, int64_t B, float* actions, int64_t n, const float* mn,
+                const float* mx, float temperature, int num_iterations, float iteration_std,
+                const double* uniforms, const float* normals, uint64_t seed, float* probs,
+                const std::function<int(const float*, float*)>& energy_fn, cudaStream_t s);
 int gather_perturb(ibc_handle* h, const float* src, const int64_t* rows, int64_t R, int A,
                    const float* normals, uint64_t seed, uint64_t rng_stream, float std,
                    const float* mn, const float* mx, float* out, cudaStream_t s);

@@ -1,0 +1,635 @@
+// Late-fusion PixelEBM (fp32 path): image preprocessing, ConvMaxpool encoder,
+// DenseResnetValue head, their backward passes and DFO inference.
+//
+//   networks/utils/image_prepro.py:20-43     u8 -> [0,1], RAW reshape, bilinear resize
+//   networks/layers/conv_maxpool.py:20-48    4 x (conv3x3 same + ReLU + maxpool2) + GAP
+//   networks/layers/dense_resnet_value.py:22-69
+//   networks/pixel_ebm.py:79-125             encode / call with observation_encoding
+//   ibc/agents/ibc_agent.py:191-213          late-fusion loss (encode once, tile N+1)
+//
+// Convolutions are im2col (per batch chunk) + the fp32 GEMM with fused
+// bias/ReLU; the tcgen05 implicit-GEMM version is future work.
+// Flat parameter layout: conv{1..4} kernel [3,3,cin,cout] + bias, value dense0
+// [256+A, Wv] + b, per block d0 [Wv,Wv/4], d1 [Wv/4,Wv/4], d2 [Wv/4,Wv] (+ biases),
+// dense1 [Wv] + b.
+#include <functional>
+
+#include "gemm_simt.cuh"
+#include "ops.cuh"
+
+struct ibc_pixel_handle {
+  ibc_handle core;          // workspaces, error string, launch accounting
+  ibc_pixel_arch arch;
+  const float* params = nullptr;
+};
+
+namespace ibc {
+namespace {
+
+constexpr int kConvCh[4] = {32, 64, 128, 256};
+constexpr int kEnc = 256;
+
+struct PixelLayout {
+  int CT, Wv, Wq, nblk, A;
+  int64_t conv_k[4], conv_b[4];
+  int64_t d0_w, d0_b, d1_w, d1_b, count;
+  int64_t blk(int j) const { return blk0 + (int64_t)j * blk_size; }
+  int64_t blk0, blk_size;
+  // inside a block: d0 W [Wv,Wq], b [Wq], d1 W [Wq,Wq], b [Wq], d2 W [Wq,Wv], b [Wv]
+  int64_t b_d0w(int j) const { return blk(j); }
+  int64_t b_d0b(int j) const { return blk(j) + (int64_t)Wv * Wq; }
+  int64_t b_d1w(int j) const { return b_d0b(j) + Wq; }
+  int64_t b_d1b(int j) const { return b_d1w(j) + (int64_t)Wq * Wq; }
+  int64_t b_d2w(int j) const { return b_d1b(j) + Wq; }
+  int64_t b_d2b(int j) const { return b_d2w(j) + (int64_t)Wq * Wv; }
+};
+
+PixelLayout make_pixel_layout(const ibc_pixel_arch& a) {
+  PixelLayout L;
+  L.CT = a.channels * a.seq_len; L.Wv = a.value_width; L.Wq = a.value_width / 4;
+  L.nblk = a.value_blocks; L.A = a.act_dim;
+  int64_t off = 0;
+  int cin = L.CT;
+  for (int i = 0; i < 4; ++i) {
+    L.conv_k[i] = off; off += (int64_t)9 * cin * kConvCh[i];
+    L.conv_b[i] = off; off += kConvCh[i];
+    cin = kConvCh[i];
+  }
+  L.d0_w = off; off += (int64_t)(kEnc + L.A) * L.Wv;
+  L.d0_b = off; off += L.Wv;
+  L.blk0 = off;
+  L.blk_size = (int64_t)L.Wv * L.Wq + L.Wq + (int64_t)L.Wq * L.Wq + L.Wq + (int64_t)L.Wq * L.Wv + L.Wv;
+  off += L.blk_size * L.nblk;
+  L.d1_w = off; off += L.Wv;
+  L.d1_b = off; off += 1;
+  L.count = off;
+  return L;
+}
+
+// ---- elementwise / data-movement kernels ----------------------------------------------
+// out[b, y, x, c] (NHWC, c < CT): bilinear sample (half-pixel centres, no
+// antialias) of the input viewed as [B, H, W, CT] -- the reference's raw
+// reshape of [B, T, H, W, C] (image_prepro.py:28).
+__global__ void preprocess_kernel(const void* __restrict__ img, int is_u8, int64_t B, int H, int W,
+                                  int CT, int th, int tw, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t tot = B * th * tw * CT;
+  if (i >= tot) return;
+  const int c = (int)(i % CT);
+  const int x = (int)((i / CT) % tw);
+  const int y = (int)((i / ((int64_t)CT * tw)) % th);
+  const int64_t b = i / ((int64_t)CT * tw * th);
+  const float sy = (float)H / (float)th, sx = (float)W / (float)tw;
+  float fy = sy * ((float)y + 0.5f) - 0.5f, fx = sx * ((float)x + 0.5f) - 0.5f;
+  fy = fmaxf(fy, 0.f); fx = fmaxf(fx, 0.f);
+  const int y0 = min((int)fy, H - 1), x0 = min((int)fx, W - 1);
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float ly = fy - (float)y0, lx = fx - (float)x0;
+  const int64_t base = b * H * W * CT;
+  auto at = [&](int yy, int xx) -> float {
+    const int64_t idx = base + ((int64_t)yy * W + xx) * CT + c;
+    return is_u8 ? (float)reinterpret_cast<const unsigned char*>(img)[idx] * (1.0f / 255.0f)
+                 : reinterpret_cast<const float*>(img)[idx];
+  };
+  const float top = at(y0, x0) + lx * (at(y0, x1) - at(y0, x0));
+  const float bot = at(y1, x0) + lx * (at(y1, x1) - at(y1, x0));
+  out[i] = top + ly * (bot - top);
+}
+
+// col[(b,y,x), (ky,kx,c)] = X[b, y+ky-1, x+kx-1, c] (zero padded), X is NHWC.
+__global__ void im2col3x3_kernel(const float* __restrict__ X, int64_t nb, int H, int W, int C,
+                                 float* __restrict__ col) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t K = 9 * C, tot = nb * H * W * K;
+  if (i >= tot) return;
+  const int j = (int)(i % K);
+  const int64_t m = i / K;
+  const int c = j % C, kk = j / C, ky = kk / 3, kx = kk % 3;
+  const int x = (int)(m % W), y = (int)((m / W) % H);
+  const int64_t b = m / ((int64_t)W * H);
+  const int yy = y + ky - 1, xx = x + kx - 1;
+  float v = 0.f;
+  if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = X[((b * H + yy) * W + xx) * C + c];
+  col[i] = v;
+}
+
+// dX[b, y, x, c] = sum_{ky,kx} dcol[(b, y-ky+1, x-kx+1), (ky,kx,c)]
+__global__ void col2im3x3_kernel(const float* __restrict__ dcol, int64_t nb, int H, int W, int C,
+                                 float* __restrict__ dX) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t tot = nb * H * W * C;
+  if (i >= tot) return;
+  const int c = (int)(i % C);
+  const int x = (int)((i / C) % W), y = (int)((i / ((int64_t)C * W)) % H);
+  const int64_t b = i / ((int64_t)C * W * H);
+  const int64_t K = 9 * C;
+  float s = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int yo = y - ky + 1, xo = x - kx + 1;
+      if (yo >= 0 && yo < H && xo >= 0 && xo < W)
+        s += dcol[((b * H + yo) * W + xo) * K + (ky * 3 + kx) * C + c];
+    }
+  dX[i] = s;
+}
+
+__global__ void maxpool2_fwd_kernel(const float* __restrict__ Y, int64_t n, int H, int W, int C,
+                                    float* __restrict__ P) {
+  const int Hp = H / 2, Wp = W / 2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * Hp * Wp * C) return;
+  const int c = (int)(i % C);
+  const int x = (int)((i / C) % Wp), y = (int)((i / ((int64_t)C * Wp)) % Hp);
+  const int64_t b = i / ((int64_t)C * Wp * Hp);
+  const float* p = Y + ((b * H + 2 * y) * W + 2 * x) * C + c;
+  P[i] = fmaxf(fmaxf(p[0], p[C]), fmaxf(p[(int64_t)W * C], p[(int64_t)W * C + C]));
+}
+
+// dY = (first maximum of its 2x2 window ? dP : 0) * (Y > 0)   (MaxPool + ReLU backward)
+__global__ void maxpool2_relu_bwd_kernel(const float* __restrict__ Y, const float* __restrict__ dP,
+                                         int64_t n, int H, int W, int C, float* __restrict__ dY) {
+  const int Hp = H / 2, Wp = W / 2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * H * W * C) return;
+  const int c = (int)(i % C);
+  const int x = (int)((i / C) % W), y = (int)((i / ((int64_t)C * W)) % H);
+  const int64_t b = i / ((int64_t)C * W * H);
+  const int yp = y >> 1, xp = x >> 1;
+  float g = 0.f;
+  const float v = Y[i];
+  if (yp < Hp && xp < Wp && v > 0.f) {
+    const float* p = Y + ((b * H + 2 * yp) * W + 2 * xp) * C + c;
+    const float w00 = p[0], w01 = p[C], w10 = p[(int64_t)W * C], w11 = p[(int64_t)W * C + C];
+    const int me = (y & 1) * 2 + (x & 1);
+    int arg = 0; float mx = w00;
+    if (w01 > mx) { mx = w01; arg = 1; }
+    if (w10 > mx) { mx = w10; arg = 2; }
+    if (w11 > mx) { mx = w11; arg = 3; }
+    if (arg == me) g = dP[((b * Hp + yp) * Wp + xp) * C + c];
+  }
+  dY[i] = g;
+}
+
+__global__ void gap_fwd_kernel(const float* __restrict__ P, int64_t B, int HW, int C,
+                               float* __restrict__ enc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int c = (int)(i % C);
+  const int64_t b = i / C;
+  float s = 0.f;
+  for (int k = 0; k < HW; ++k) s += P[(b * HW + k) * C + c];
+  enc[i] = s / (float)HW;
+}
+
+__global__ void gap_bwd_kernel(const float* __restrict__ dEnc, int64_t B, int HW, int C,
+                               float* __restrict__ dP) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * HW * C) return;
+  const int c = (int)(i % C);
+  const int64_t b = i / ((int64_t)C * HW);
+  dP[i] = dEnc[b * C + c] / (float)HW;
+}
+
+inline unsigned nblocks(int64_t n) { return (unsigned)((n + 255) / 256); }
+
+struct EncDims { int H[5], W[5], C[5]; };   // [0] = preprocessed input, [l] = conv l output (pre-pool)
+
+EncDims enc_dims(const ibc_pixel_arch& a) {
+  EncDims d;
+  d.H[0] = a.target_height; d.W[0] = a.target_width; d.C[0] = a.channels * a.seq_len;
+  int h = d.H[0], w = d.W[0];
+  for (int l = 1; l <= 4; ++l) {
+    d.H[l] = h; d.W[l] = w; d.C[l] = kConvCh[l - 1];
+    h /= 2; w /= 2;
+  }
+  return d;
+}
+
+struct EncSave {
+  float* X0 = nullptr;
+  float* Y[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // conv + relu outputs
+  float* P[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // pooled
+  float* col = nullptr;
+  int chunk = 1;
+};
+
+size_t enc_bytes(const ibc_pixel_arch& a, int64_t B, int* chunk_out) {
+  const EncDims d = enc_dims(a);
+  size_t bytes = Workspace::rounded((size_t)B * d.H[0] * d.W[0] * d.C[0] * 4);
+  size_t col_per_img = 0;
+  for (int l = 1; l <= 4; ++l) {
+    bytes += Workspace::rounded((size_t)B * d.H[l] * d.W[l] * d.C[l] * 4);
+    bytes += Workspace::rounded((size_t)B * (d.H[l] / 2) * (d.W[l] / 2) * d.C[l] * 4);
+    const size_t c = (size_t)d.H[l] * d.W[l] * 9 * d.C[l - 1] * 4;
+    if (c > col_per_img) col_per_img = c;
+  }
+  int chunk = (int)((size_t)(256u << 20) / col_per_img);
+  if (chunk < 1) chunk = 1;
+  if (chunk > B) chunk = (int)B;
+  // keep the GEMM's grid.y (M / 64) under 65535
+  while (chunk > 1 && (int64_t)chunk * d.H[1] * d.W[1] / 64 > 60000) --chunk;
+  *chunk_out = chunk;
+  bytes += Workspace::rounded((size_t)chunk * col_per_img);
+  return bytes;
+}
+
+void carve_enc(ibc_handle* h, const ibc_pixel_arch& a, int64_t B, int chunk, EncSave* s) {
+  const EncDims d = enc_dims(a);
+  s->chunk = chunk;
+  s->X0 = h->ws.take<float>((size_t)B * d.H[0] * d.W[0] * d.C[0]);
+  size_t col_per_img = 0;
+  for (int l = 1; l <= 4; ++l) {
+    s->Y[l] = h->ws.take<float>((size_t)B * d.H[l] * d.W[l] * d.C[l]);
+    s->P[l] = h->ws.take<float>((size_t)B * (d.H[l] / 2) * (d.W[l] / 2) * d.C[l]);
+    const size_t c = (size_t)d.H[l] * d.W[l] * 9 * d.C[l - 1];
+    if (c > col_per_img) col_per_img = c;
+  }
+  s->col = h->ws.take<float>((size_t)chunk * col_per_img);
+}
+
+int encode_fwd(ibc_pixel_handle* ph, const PixelLayout& L, const void* images, int is_u8,
+               int64_t B, const EncSave& sv, float* enc, cudaStream_t s) {
+  ibc_handle* h = &ph->core;
+  const ibc_pixel_arch& a = ph->arch;
+  const EncDims d = enc_dims(a);
+  const float* P = ph->params;
+  preprocess_kernel<<<nblocks((int64_t)B * d.H[0] * d.W[0] * d.C[0]), 256, 0, s>>>(
+      images, is_u8, B, a.height, a.width, d.C[0], d.H[0], d.W[0], sv.X0);
+  IBC_LAUNCH_CHECK(h);
+  const float* in = sv.X0;
+  for (int l = 1; l <= 4; ++l) {
+    const int H = d.H[l], W = d.W[l], Ci = d.C[l - 1], Co = d.C[l];
+    for (int64_t b0 = 0; b0 < B; b0 += sv.chunk) {
+      const int64_t nb = std::min<int64_t>(sv.chunk, B - b0);
+      const int64_t M = nb * H * W;
+      im2col3x3_kernel<<<nblocks(M * 9 * Ci), 256, 0, s>>>(in + b0 * H * W * Ci, nb, H, W, Ci, sv.col);
+      IBC_LAUNCH_CHECK(h);
+      GemmP g;   // Y = relu(col . K + b)
+      g.A = sv.col; g.lda = 9 * Ci; g.B = P + L.conv_k[l - 1]; g.ldb = Co;
+      g.C = sv.Y[l] + b0 * H * W * Co; g.ldc = Co; g.bias = P + L.conv_b[l - 1];
+      g.M = (int)M; g.N = Co; g.K = 9 * Ci; g.relu_out = 1;
+      IBC_TRY(gemm(h, g, false, false, s));
+    }
+    maxpool2_fwd_kernel<<<nblocks((int64_t)B * (H / 2) * (W / 2) * Co), 256, 0, s>>>(
+        sv.Y[l], B, H, W, Co, sv.P[l]);
+    IBC_LAUNCH_CHECK(h);
+    in = sv.P[l];
+  }
+  gap_fwd_kernel<<<nblocks(B * kEnc), 256, 0, s>>>(sv.P[4], B, (d.H[4] / 2) * (d.W[4] / 2), kEnc, enc);
+  IBC_LAUNCH_CHECK(h);
+  return IBC_OK;
+}
+
+// Encoder backward given dEnc [B, 256]; accumulates conv kernel / bias gradients.
+int encode_bwd(ibc_pixel_handle* ph, const PixelLayout& L, int64_t B, const EncSave& sv,
+               const float* dEnc, float* grads, float* dbufA, float* dbufB, cudaStream_t s) {
+  ibc_handle* h = &ph->core;
+  const EncDims d = enc_dims(ph->arch);
+  const float* P = ph->params;
+  // dP4
+  float* dP = dbufA;
+  gap_bwd_kernel<<<nblocks(B * (d.H[4] / 2) * (d.W[4] / 2) * kEnc), 256, 0, s>>>(
+      dEnc, B, (d.H[4] / 2) * (d.W[4] / 2), kEnc, dP);
+  IBC_LAUNCH_CHECK(h);
+  float* dY = dbufB;
+  for (int l = 4; l >= 1; --l) {
+    const int H = d.H[l], W = d.W[l], Ci = d.C[l - 1], Co = d.C[l];
+    maxpool2_relu_bwd_kernel<<<nblocks((int64_t)B * H * W * Co), 256, 0, s>>>(sv.Y[l], dP, B, H, W,
+                                                                            Co, dY);
+    IBC_LAUNCH_CHECK(h);
+    IBC_TRY(colsum_add(h, dY, Co, (int64_t)B * H * W, Co, grads + L.conv_b[l - 1], s));
+    const float* in = (l == 1) ? sv.X0 : sv.P[l - 1];
+    float* dIn = dP;   // overwritten with the gradient of this layer's input (l > 1)
+    for (int64_t b0 = 0; b0 < B; b0 += sv.chunk) {
+      const int64_t nb = std::min<int64_t>(sv.chunk, B - b0);
+      const int64_t M = nb * H * W;
+      im2col3x3_kernel<<<nblocks(M * 9 * Ci), 256, 0, s>>>(in + b0 * H * W * Ci, nb, H, W, Ci, sv.col);
+      IBC_LAUNCH_CHECK(h);
+      GemmP gk;   // dK += col^T . dY
+      gk.A = sv.col; gk.lda = 9 * Ci; gk.B = dY + b0 * H * W * Co; gk.ldb = Co;
+      gk.C = grads + L.conv_k[l - 1]; gk.ldc = Co; gk.M = 9 * Ci; gk.N = Co; gk.K = (int)M;
+      gk.k_chunk = 2048; gk.atomic = 1;
+      IBC_TRY(gemm(h, gk, true, false, s));
+      if (l > 1) {
+        GemmP gd;   // dcol = dY . K^T
+        gd.A = dY + b0 * H * W * Co; gd.lda = Co; gd.B = P + L.conv_k[l - 1]; gd.ldb = Co;
+        gd.C = sv.col; gd.ldc = 9 * Ci; gd.M = (int)M; gd.N = 9 * Ci; gd.K = Co;
+        IBC_TRY(gemm(h, gd, false, true, s));
+        col2im3x3_kernel<<<nblocks(M * Ci), 256, 0, s>>>(sv.col, nb, H, W, Ci,
+                                                          dIn + b0 * H * W * Ci);
+        IBC_LAUNCH_CHECK(h);
+      }
+    }
+  }
+  return IBC_OK;
+}
+
+// ---- value head --------------------------------------------------------------------------------
+struct ValSave {
+  float* encp = nullptr;   // [B, Wv]
+  float* X = nullptr;      // [(nblk+1), R, Wv]
+  float* Y0 = nullptr;     // [nblk, R, Wq]
+  float* Y1 = nullptr;     // [nblk, R, Wq]
+  int64_t R = 0;
+};
+
+size_t val_bytes(const PixelLayout& L, int64_t B, int64_t R) {
+  const int nb = L.nblk > 0 ? L.nblk : 1;
+  return Workspace::rounded((size_t)B * L.Wv * 4) +
+         Workspace::rounded((size_t)(L.nblk + 1) * R * L.Wv * 4) +
+         2 * Workspace::rounded((size_t)nb * R * L.Wq * 4);
+}
+
+void carve_val(ibc_handle* h, const PixelLayout& L, int64_t B, int64_t R, ValSave* v) {
+  const int nb = L.nblk > 0 ? L.nblk : 1;
+  v->R = R;
+  v->encp = h->ws.take<float>((size_t)B * L.Wv);
+  v->X = h->ws.take<float>((size_t)(L.nblk + 1) * R * L.Wv);
+  v->Y0 = h->ws.take<float>((size_t)nb * R * L.Wq);
+  v->Y1 = h->ws.take<float>((size_t)nb * R * L.Wq);
+}
+
+// E[r] for enc [B, 256] (un-tiled) and act [B*n, A]   (pixel_ebm.py:113-125)
+int value_fwd(ibc_pixel_handle* ph, const PixelLayout& L, const float* enc, int64_t B,
+              const float* act, int64_t n, const ValSave& v, float* E, cudaStream_t s) {
+  ibc_handle* h = &ph->core;
+  const float* P = ph->params;
+  const int Wv = L.Wv, Wq = L.Wq;
+  const int64_t R = B * n;
+  {  // encp = enc . W0[:256] + b0
+    GemmP g;
+    g.A = enc; g.lda = kEnc; g.B = P + L.d0_w; g.ldb = Wv; g.C = v.encp; g.ldc = Wv;
+    g.bias = P + L.d0_b; g.M = (int)B; g.N = Wv; g.K = kEnc;
+    IBC_TRY(gemm(h, g, false, false, s));
+  }
+  {  // x0 = act . W0[256:] + encp[row / n]
+    GemmP g;
+    g.A = act; g.lda = L.A; g.B = P + L.d0_w + (int64_t)kEnc * Wv; g.ldb = Wv;
+    g.C = v.X; g.ldc = Wv; g.rowbias = v.encp; g.ldrb = Wv; g.rows_per_group = n;
+    g.M = (int)R; g.N = Wv; g.K = L.A;
+    IBC_TRY(gemm(h, g, false, false, s));
+  }
+  for (int j = 0; j < L.nblk; ++j) {
+    const float* x = v.X + (int64_t)j * R * Wv;
+    float* xn = v.X + (int64_t)(j + 1) * R * Wv;
+    float* y0 = v.Y0 + (int64_t)j * R * Wq;
+    float* y1 = v.Y1 + (int64_t)j * R * Wq;
+    GemmP g0;  // y0 = relu(x) . D0 + b
+    g0.A = x; g0.lda = Wv; g0.aop = AOP_RELU; g0.B = P + L.b_d0w(j); g0.ldb = Wq;
+    g0.C = y0; g0.ldc = Wq; g0.bias = P + L.b_d0b(j); g0.M = (int)R; g0.N = Wq; g0.K = Wv;
+    IBC_TRY(gemm(h, g0, false, false, s));
+    GemmP g1;  // y1 = relu(y0) . D1 + b
+    g1.A = y0; g1.lda = Wq; g1.aop = AOP_RELU; g1.B = P + L.b_d1w(j); g1.ldb = Wq;
+    g1.C = y1; g1.ldc = Wq; g1.bias = P + L.b_d1b(j); g1.M = (int)R; g1.N = Wq; g1.K = Wq;
+    IBC_TRY(gemm(h, g1, false, false, s));
+    GemmP g2;  // x' = x + relu(y1) . D2 + b
+    g2.A = y1; g2.lda = Wq; g2.aop = AOP_RELU; g2.B = P + L.b_d2w(j); g2.ldb = Wv;
+    g2.C = xn; g2.ldc = Wv; g2.bias = P + L.b_d2b(j); g2.res = x; g2.ldres = Wv;
+    g2.M = (int)R; g2.N = Wv; g2.K = Wq;
+    IBC_TRY(gemm(h, g2, false, false, s));
+  }
+  IBC_TRY(rowdot(h, v.X + (int64_t)L.nblk * R * Wv, Wv, P + L.d1_w, P + L.d1_b, R, Wv, E, s));
+  return IBC_OK;
+}
+
+static int dwg(ibc_handle* h, const float* X, int64_t ldx, int aop, const float* Y, int64_t ldy,
+               int64_t R, int Kin, int Nout, float* dW, cudaStream_t s) {
+  GemmP g;
+  g.A = X; g.lda = ldx; g.aop = aop; g.B = Y; g.ldb = ldy; g.C = dW; g.ldc = Nout;
+  g.M = Kin; g.N = Nout; g.K = (int)R; g.k_chunk = 1024; g.atomic = 1;
+  return gemm(h, g, true, false, s);
+}
+
+// Value-head backward: parameter gradients (accumulated) and dEnc [B, 256].
+int value_bwd(ibc_pixel_handle* ph, const PixelLayout& L, const float* enc, int64_t B,
+              const float* act, int64_t n, const ValSave& v, const float* dE, float* grads,
+              float* dEnc, cudaStream_t s) {
+  ibc_handle* h = &ph->core;
+  const float* P = ph->params;
+  const int Wv = L.Wv, Wq = L.Wq;
+  const int64_t R = B * n;
+  float* Ga = h->ws.take<float>((size_t)R * Wv);
+  float* Gb = h->ws.take<float>((size_t)R * Wv);
+  float* g1b = h->ws.take<float>((size_t)R * Wq);
+  float* g0b = h->ws.take<float>((size_t)R * Wq);
+  float* gsum = h->ws.take<float>((size_t)B * Wv);
+  const float* xl = v.X + (int64_t)L.nblk * R * Wv;
+  IBC_TRY(wcolsum_add(h, xl, Wv, dE, R, Wv, grads + L.d1_w, s));
+  IBC_TRY(sum_add(h, dE, R, grads + L.d1_b, s));
+  IBC_TRY(rowfill(h, P + L.d1_w, dE, R, Wv, Ga, s));
+  float* G = Ga;
+  for (int j = L.nblk - 1; j >= 0; --j) {
+    float* Gn = (G == Ga) ? Gb : Ga;
+    const float* x = v.X + (int64_t)j * R * Wv;
+    const float* y0 = v.Y0 + (int64_t)j * R * Wq;
+    const float* y1 = v.Y1 + (int64_t)j * R * Wq;
+    IBC_TRY(dwg(h, y1, Wq, AOP_RELU, G, Wv, R, Wq, Wv, grads + L.b_d2w(j), s));
+    IBC_TRY(colsum_add(h, G, Wv, R, Wv, grads + L.b_d2b(j), s));
+    GemmP a1;  // g1 = (G . D2^T) (.) (y1 > 0)
+    a1.A = G; a1.lda = Wv; a1.B = P + L.b_d2w(j); a1.ldb = Wv; a1.C = g1b; a1.ldc = Wq;
+    a1.gateC = y1; a1.ldgc = Wq; a1.M = (int)R; a1.N = Wq; a1.K = Wv;
+    IBC_TRY(gemm(h, a1, false, true, s));
+    IBC_TRY(dwg(h, y0, Wq, AOP_RELU, g1b, Wq, R, Wq, Wq, grads + L.b_d1w(j), s));
+    IBC_TRY(colsum_add(h, g1b, Wq, R, Wq, grads + L.b_d1b(j), s));
+    GemmP a0;  // g0 = (g1 . D1^T) (.) (y0 > 0)
+    a0.A = g1b; a0.lda = Wq; a0.B = P + L.b_d1w(j); a0.ldb = Wq; a0.C = g0b; a0.ldc = Wq;
+    a0.gateC = y0; a0.ldgc = Wq; a0.M = (int)R; a0.N = Wq; a0.K = Wq;
+    IBC_TRY(gemm(h, a0, false, true, s));
+    IBC_TRY(dwg(h, x, Wv, AOP_RELU, g0b, Wq, R, Wv, Wq, grads + L.b_d0w(j), s));
+    IBC_TRY(colsum_add(h, g0b, Wq, R, Wq, grads + L.b_d0b(j), s));
+    GemmP ax;  // G' = G + (g0 . D0^T) (.) (x > 0)
+    ax.A = g0b; ax.lda = Wq; ax.B = P + L.b_d0w(j); ax.ldb = Wq; ax.C = Gn; ax.ldc = Wv;
+    ax.gateC = x; ax.ldgc = Wv; ax.res = G; ax.ldres = Wv; ax.M = (int)R; ax.N = Wv; ax.K = Wq;
+    IBC_TRY(gemm(h, ax, false, true, s));
+    G = Gn;
+  }
+  // dense0 on x = [enc tiled, act]
+  IBC_TRY(dwg(h, act, L.A, AOP_ID, G, Wv, R, L.A, Wv, grads + L.d0_w + (int64_t)kEnc * Wv, s));
+  IBC_TRY(groupsum(h, G, B, n, Wv, gsum, s));
+  IBC_TRY(dwg(h, enc, kEnc, AOP_ID, gsum, Wv, B, kEnc, Wv, grads + L.d0_w, s));
+  IBC_TRY(colsum_add(h, gsum, Wv, B, Wv, grads + L.d0_b, s));
+  if (dEnc) {  // dEnc = gsum . W0[:256]^T
+    GemmP g;
+    g.A = gsum; g.lda = Wv; g.B = P + L.d0_w; g.ldb = Wv; g.C = dEnc; g.ldc = kEnc;
+    g.M = (int)B; g.N = kEnc; g.K = Wv;
+    IBC_TRY(gemm(h, g, false, true, s));
+  }
+  return IBC_OK;
+}
+
+int check_arch(ibc_handle* h, const ibc_pixel_arch& a) {
+  if (a.seq_len < 1 || a.height < 1 || a.width < 1 || a.channels < 1 || a.act_dim < 1 ||
+      a.value_width < 4 || a.value_width % 4 || a.value_blocks < 0)
+    IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_create: bad architecture");
+  if (a.target_height < 16 || a.target_width < 16)
+    IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_create: target size must be >= 16 (four 2x2 pools)");
+  return IBC_OK;
+}
+
+}  // namespace
+}  // namespace ibc
+
+using namespace ibc;
+
+#define PIX_ENTER(ph)                                                                  \
+  if (!(ph)) { strncpy(ibc::g_create_error, "null handle", 511); return IBC_ERR_INVALID; } \
+  ibc_handle* h = &(ph)->core;                                                         \
+  int _prev = -1; cudaGetDevice(&_prev);                                               \
+  if (_prev != h->device) cudaSetDevice(h->device);                                    \
+  struct _Restore { int p, d; ~_Restore() { if (p >= 0 && p != d) cudaSetDevice(p); } } \
+      _restore{_prev, h->device}
+
+extern "C" {
+
+int64_t ibc_pixel_param_count(const ibc_pixel_arch* arch) {
+  if (!arch) return -1;
+  return make_pixel_layout(*arch).count;
+}
+
+int ibc_pixel_create(const ibc_pixel_arch* arch, int device, ibc_pixel_handle** out) {
+  ibc_handle* h = nullptr;
+  if (!arch || !out) IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_create: null argument");
+  IBC_TRY(check_arch(h, *arch));
+  int ndev = 0;
+  IBC_CUDA(h, cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev)
+    IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_create: device %d out of range (%d visible)", device, ndev);
+  cudaDeviceProp prop;
+  IBC_CUDA(h, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "ibc_b200 is built for sm_100a only; device %d is sm_%d%d",
+             device, prop.major, prop.minor);
+  ibc_pixel_handle* ph = new ibc_pixel_handle();
+  ph->arch = *arch;
+  ph->core.device = device;
+  ph->core.sm_count = prop.multiProcessorCount;
+  *out = ph;
+  return IBC_OK;
+}
+
+int ibc_pixel_destroy(ibc_pixel_handle* ph) {
+  if (!ph) return IBC_OK;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(ph->core.device);
+  cudaDeviceSynchronize();
+  if (ph->core.ws.base) cudaFree(ph->core.ws.base);
+  if (ph->core.ws_outer.base) cudaFree(ph->core.ws_outer.base);
+  if (prev >= 0) cudaSetDevice(prev);
+  delete ph;
+  return IBC_OK;
+}
+
+const char* ibc_pixel_last_error(const ibc_pixel_handle* ph) {
+  return ph ? ph->core.err.c_str() : ibc::g_create_error;
+}
+
+int ibc_pixel_bind_params(ibc_pixel_handle* ph, const float* params) {
+  PIX_ENTER(ph);
+  if (!params) IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_bind_params: null params");
+  ph->params = params;
+  return IBC_OK;
+}
+
+int ibc_pixel_encode(ibc_pixel_handle* ph, const void* images, int32_t is_uint8, int64_t B,
+                     float* enc, void* stream) {
+  PIX_ENTER(ph);
+  if (!images || !enc || B < 1) IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_encode: bad argument");
+  if (!ph->params) IBC_FAIL(h, IBC_ERR_INVALID, "no parameters bound (ibc_pixel_bind_params)");
+  const PixelLayout L = make_pixel_layout(ph->arch);
+  int chunk = 1;
+  const size_t bytes = enc_bytes(ph->arch, B, &chunk);
+  IBC_CUDA(h, h->ws.reserve(bytes));
+  h->ws.reset();
+  EncSave sv;
+  carve_enc(h, ph->arch, B, chunk, &sv);
+  return encode_fwd(ph, L, images, is_uint8, B, sv, enc, (cudaStream_t)stream);
+}
+
+int ibc_pixel_energy(ibc_pixel_handle* ph, const float* enc, int64_t B, const float* act, int64_t n,
+                     float* energy, void* stream) {
+  PIX_ENTER(ph);
+  if (!enc || !act || !energy || B < 1 || n < 1)
+    IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_energy: bad argument");
+  if (!ph->params) IBC_FAIL(h, IBC_ERR_INVALID, "no parameters bound (ibc_pixel_bind_params)");
+  const PixelLayout L = make_pixel_layout(ph->arch);
+  IBC_CUDA(h, h->ws.reserve(val_bytes(L, B, B * n)));
+  h->ws.reset();
+  ValSave v;
+  carve_val(h, L, B, B * n, &v);
+  return value_fwd(ph, L, enc, B, act, n, v, energy, (cudaStream_t)stream);
+}
+
+int ibc_pixel_dfo(ibc_pixel_handle* ph, const float* enc, int64_t B, float* actions, int64_t n,
+                  const float* min_actions, const float* max_actions, float temperature,
+                  int32_t num_iterations, float iteration_std, const double* uniforms,
+                  const float* normals, uint64_t seed, float* probs, void* stream) {
+  PIX_ENTER(ph);
+  if (!enc || !actions || !min_actions || !max_actions || B < 1 || n < 1)
+    IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_dfo: bad argument");
+  if (!ph->params) IBC_FAIL(h, IBC_ERR_INVALID, "no parameters bound (ibc_pixel_bind_params)");
+  const PixelLayout L = make_pixel_layout(ph->arch);
+  cudaStream_t s = (cudaStream_t)stream;
+  auto energy_fn = [&](const float* acts, float* E) -> int {
+    IBC_CUDA(h, h->ws.reserve(val_bytes(L, B, B * n)));
+    h->ws.reset();
+    ValSave v;
+    carve_val(h, L, B, B * n, &v);
+    return value_fwd(ph, L, enc, B, acts, n, v, E, s);
+  };
+  return dfo_generic(h, ph->arch.act_dim, B, actions, n, min_actions, max_actions, temperature,
+                     num_iterations, iteration_std, uniforms, normals, seed, probs, energy_fn, s);
+}
+
+int ibc_pixel_train_grads(ibc_pixel_handle* ph, const void* images, int32_t is_uint8, int64_t B,
+                          const float* actions, int64_t N, const ibc_loss_cfg* cfg,
+                          int64_t global_batch, float* per_example_loss, float* energies,
+                          float* grads, void* stream) {
+  PIX_ENTER(ph);
+  if (!images || !actions || !cfg || !per_example_loss || !grads || B < 1 || N < 0 ||
+      global_batch < 1)
+    IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_train_grads: bad argument");
+  if (!ph->params) IBC_FAIL(h, IBC_ERR_INVALID, "no parameters bound (ibc_pixel_bind_params)");
+  if (cfg->add_grad_penalty)
+    IBC_FAIL(h, IBC_ERR_UNSUPPORTED,
+             "gradient penalty for PixelEBM is not built (pixel_ebm_best.gin trains without it)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const PixelLayout L = make_pixel_layout(ph->arch);
+  const EncDims d = enc_dims(ph->arch);
+  const int64_t n1 = N + 1, R = B * n1;
+  int chunk = 1;
+  size_t dmax = 0;   // largest activation tensor (gradient ping-pong buffers)
+  for (int l = 1; l <= 4; ++l)
+    dmax = std::max(dmax, (size_t)B * d.H[l] * d.W[l] * d.C[l]);
+  size_t bytes = enc_bytes(ph->arch, B, &chunk) + val_bytes(L, B, R) +
+                 2 * Workspace::rounded(dmax * 4) + 2 * Workspace::rounded((size_t)R * L.Wv * 4) +
+                 2 * Workspace::rounded((size_t)R * L.Wq * 4) +
+                 Workspace::rounded((size_t)B * L.Wv * 4) + 2 * Workspace::rounded((size_t)B * kEnc * 4) +
+                 2 * Workspace::rounded((size_t)R * 4) + (1 << 16);
+  IBC_CUDA(h, h->ws.reserve(bytes));
+  h->ws.reset();
+  EncSave sv;
+  carve_enc(h, ph->arch, B, chunk, &sv);
+  ValSave v;
+  carve_val(h, L, B, R, &v);
+  float* dA = h->ws.take<float>(dmax);
+  float* dB = h->ws.take<float>(dmax);
+  float* enc = h->ws.take<float>((size_t)B * kEnc);
+  float* dEnc = h->ws.take<float>((size_t)B * kEnc);
+  float* E = h->ws.take<float>(R);
+  float* dE = h->ws.take<float>(R);
+  IBC_CUDA(h, cudaMemsetAsync(grads, 0, (size_t)L.count * 4, s));
+  IBC_TRY(encode_fwd(ph, L, images, is_uint8, B, sv, enc, s));
+  IBC_TRY(value_fwd(ph, L, enc, B, actions, n1, v, E, s));
+  if (energies)
+    IBC_CUDA(h, cudaMemcpyAsync(energies, E, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
+  IBC_TRY(info_nce(h, E, B, n1, cfg->softmax_temperature, 1.0f / (float)global_batch,
+                   per_example_loss, dE, s));
+  IBC_TRY(value_bwd(ph, L, enc, B, actions, n1, v, dE, grads, dEnc, s));
+  IBC_TRY(encode_bwd(ph, L, B, sv, dEnc, grads, dA, dB, s));
+  return IBC_OK;
+}
+
+}  // extern "C"

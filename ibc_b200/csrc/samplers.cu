@@ -3,8 +3,11 @@
 // update, row softmax and uniform action init.
 #include <math.h>
 
+#include <functional>
+
 #include "gemm_simt.cuh"
 #include "mlp.cuh"
+#include "ops.cuh"
 #include "philox.cuh"
 
 namespace ibc {
@@ -319,12 +322,13 @@ int langevin_update(ibc_handle* h, float* actions, const float* dEda, int64_t R,
   return IBC_OK;
 }
 
-// mcmc.iterative_dfo (ibc/agents/mcmc.py:58-158).
-int dfo(ibc_handle* h, const float* obs, int64_t B, float* actions, int64_t n, const float* mn,
-        const float* mx, float temperature, int num_iterations, float iteration_std,
-        const double* uniforms, const float* normals, uint64_t seed, float* probs,
-        cudaStream_t s) {
-  const int A = h->L.A;
+// mcmc.iterative_dfo (ibc/agents/mcmc.py:58-158) around any energy evaluator
+// energy_fn(actions [B*n, A]) -> E [B*n] (MLPEBM, or the PixelEBM value head on
+// a fixed observation encoding for late fusion, mcmc.py:98-110).
+int dfo_generic(ibc_handle* h, int A, int64_t B, float* actions, int64_t n, const float* mn,
+                const float* mx, float temperature, int num_iterations, float iteration_std,
+                const double* uniforms, const float* normals, uint64_t seed, float* probs,
+                const std::function<int(const float*, float*)>& energy_fn, cudaStream_t s) {
   const int64_t R = B * n;
   if (num_iterations < 1) IBC_FAIL(h, IBC_ERR_INVALID, "dfo: num_iterations must be >= 1");
   if (temperature <= 0.f) IBC_FAIL(h, IBC_ERR_INVALID, "dfo: temperature must be > 0");
@@ -339,7 +343,7 @@ int dfo(ibc_handle* h, const float* obs, int64_t B, float* actions, int64_t n, c
   float std = iteration_std;
   const float* logits = E;
   for (int it = 0; it < num_iterations; ++it) {
-    IBC_TRY(mlp_energy(h, obs, B, actions, n, E, s));
+    IBC_TRY(energy_fn(actions, E));
     if (temperature != 1.0f) {
       scale_div_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(E, temperature, R, logits_buf);
       IBC_LAUNCH_CHECK(h);
@@ -358,6 +362,17 @@ int dfo(ibc_handle* h, const float* obs, int64_t B, float* actions, int64_t n, c
   }
   if (probs) IBC_TRY(softmax_rows(h, logits, B, n, 1.0f, probs, s));
   return IBC_OK;
+}
+
+int dfo(ibc_handle* h, const float* obs, int64_t B, float* actions, int64_t n, const float* mn,
+        const float* mx, float temperature, int num_iterations, float iteration_std,
+        const double* uniforms, const float* normals, uint64_t seed, float* probs,
+        cudaStream_t s) {
+  auto energy_fn = [&](const float* acts, float* E) -> int {
+    return mlp_energy(h, obs, B, acts, n, E, s);
+  };
+  return dfo_generic(h, h->L.A, B, actions, n, mn, mx, temperature, num_iterations, iteration_std,
+                     uniforms, normals, seed, probs, energy_fn, s);
 }
 
 void langevin_stepsizes(const ibc_langevin_cfg& c, std::vector<float>* out) {

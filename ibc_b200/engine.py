@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from ibc_b200 import _lib
-from ibc_b200._lib import LangevinCfg, LossCfg, MlpArch
+from ibc_b200._lib import LangevinCfg, LossCfg, MlpArch, PixelArch
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -213,6 +213,110 @@ class EBMEngine:
                                         int(global_batch), _ptr(per_example), _ptr(grad_loss),
                                         _ptr(energies), _ptr(grads), _stream()), self._h)
     return per_example, grad_loss, energies, grads
+
+
+class PixelEngine:
+  """Owns an ibc_pixel_handle (late-fusion PixelEBM: ConvMaxpool encoder +
+  DenseResnetValue head) on one GPU."""
+
+  def __init__(self, seq_len, height, width, channels, target_height, target_width, act_dim,
+               value_width, value_blocks, device: Optional[torch.device] = None):
+    if not torch.cuda.is_available():
+      raise _lib.IbcError('ibc_b200 needs a CUDA device (B200); there is no CPU path')
+    self.lib = _lib.load()
+    self.device = torch.device('cuda', torch.cuda.current_device()) if device is None \
+        else torch.device(device)
+    self.arch = PixelArch(seq_len, height, width, channels, target_height, target_width, act_dim,
+                          value_width, value_blocks)
+    self.act_dim = act_dim
+    self.param_count = int(self.lib.ibc_pixel_param_count(ctypes.byref(self.arch)))
+    h = ctypes.c_void_p()
+    _lib.check(self.lib.ibc_pixel_create(ctypes.byref(self.arch), self.device.index or 0,
+                                         ctypes.byref(h)), None, pixel=True)
+    self._h = h
+    self._params = None
+
+  def __del__(self):
+    h = getattr(self, '_h', None)
+    if h is not None and h.value:
+      try:
+        self.lib.ibc_pixel_destroy(h)
+      except Exception:
+        pass
+      self._h = None
+
+  def bind_params(self, params: torch.Tensor):
+    _check_f32(params, 'params')
+    if params.numel() != self.param_count:
+      raise ValueError('params has %d elements, expected %d' % (params.numel(), self.param_count))
+    self._params = params
+    _lib.check(self.lib.ibc_pixel_bind_params(self._h, _ptr(params)), self._h, pixel=True)
+
+  def _check_images(self, images):
+    a = self.arch
+    if not images.is_cuda or not images.is_contiguous():
+      raise ValueError('images must be a contiguous CUDA tensor')
+    if images.dtype not in (torch.uint8, torch.float32):
+      raise ValueError('images must be uint8 or float32')
+    if tuple(images.shape[1:]) != (a.seq_len, a.height, a.width, a.channels):
+      raise ValueError('images must be [B, %d, %d, %d, %d], got %s'
+                       % (a.seq_len, a.height, a.width, a.channels, tuple(images.shape)))
+    return images.shape[0], int(images.dtype == torch.uint8)
+
+  def encode(self, images: torch.Tensor) -> torch.Tensor:
+    b, is_u8 = self._check_images(images)
+    enc = torch.empty(b, 256, device=images.device, dtype=torch.float32)
+    _lib.check(self.lib.ibc_pixel_encode(self._h, _ptr(images), is_u8, b, _ptr(enc), _stream()),
+               self._h, pixel=True)
+    return enc
+
+  def energy(self, enc: torch.Tensor, act: torch.Tensor, n: int) -> torch.Tensor:
+    _check_f32(enc, 'enc')
+    _check_f32(act, 'act')
+    b = enc.shape[0]
+    if enc.shape[1] != 256 or tuple(act.shape) != (b * n, self.act_dim):
+      raise ValueError('enc must be [B, 256] and act [B*n, A]')
+    e = torch.empty(b * n, device=enc.device, dtype=torch.float32)
+    _lib.check(self.lib.ibc_pixel_energy(self._h, _ptr(enc), b, _ptr(act), n, _ptr(e), _stream()),
+               self._h, pixel=True)
+    return e
+
+  def dfo(self, enc, actions, n, min_actions, max_actions, temperature=1.0, num_iterations=3,
+          iteration_std=0.33, uniforms=None, normals=None, seed=0):
+    _check_f32(enc, 'enc')
+    _check_f32(actions, 'actions')
+    b = enc.shape[0]
+    if tuple(actions.shape) != (b * n, self.act_dim):
+      raise ValueError('actions must be [B*n, A]')
+    if uniforms is not None and (uniforms.dtype != torch.float64 or not uniforms.is_cuda
+                                 or uniforms.numel() != num_iterations * b * n):
+      raise ValueError('uniforms must be CUDA float64 with num_iterations*B*n elements')
+    if normals is not None:
+      _check_f32(normals, 'normals')
+    probs = torch.empty(b * n, device=enc.device, dtype=torch.float32)
+    _lib.check(self.lib.ibc_pixel_dfo(self._h, _ptr(enc), b, _ptr(actions), n, _ptr(min_actions),
+                                      _ptr(max_actions), float(temperature), int(num_iterations),
+                                      float(iteration_std), _ptr(uniforms), _ptr(normals),
+                                      int(seed), _ptr(probs), _stream()), self._h, pixel=True)
+    return probs
+
+  def train_grads(self, images, actions, num_counter_examples, cfg: LossCfg, global_batch,
+                  grads: Optional[torch.Tensor] = None, want_energies=False):
+    b, is_u8 = self._check_images(images)
+    n1 = num_counter_examples + 1
+    _check_f32(actions, 'actions')
+    if tuple(actions.shape) != (b * n1, self.act_dim):
+      raise ValueError('actions must be [B*(N+1), A]')
+    if grads is None:
+      grads = torch.empty(self.param_count, device=images.device, dtype=torch.float32)
+    per_example = torch.empty(b, device=images.device, dtype=torch.float32)
+    energies = torch.empty(b * n1, device=images.device, dtype=torch.float32) if want_energies else None
+    _lib.check(self.lib.ibc_pixel_train_grads(self._h, _ptr(images), is_u8, b, _ptr(actions),
+                                              int(num_counter_examples), ctypes.byref(cfg),
+                                              int(global_batch), _ptr(per_example),
+                                              _ptr(energies), _ptr(grads), _stream()),
+               self._h, pixel=True)
+    return per_example, energies, grads
 
 
 # -- handle-free ops -----------------------------------------------------------------

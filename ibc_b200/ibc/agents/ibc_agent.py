@@ -24,6 +24,7 @@ from ibc_b200.ibc.agents import mcmc
 from ibc_b200.ibc.losses import ebm_loss
 from ibc_b200.ibc.losses import gradient_loss
 from ibc_b200.networks.mlp_ebm import MLPEBM
+from ibc_b200.networks.pixel_ebm import PixelEBM
 
 
 class BehavioralCloningAgent:
@@ -94,8 +95,13 @@ class ImplicitBCAgent(BehavioralCloningAgent):
         raise NotImplementedError('ebm_loss_type %r is out of scope (no shipped gin selects it)'
                                   % ebm_loss_type)
       raise ValueError('Unsupported EBM loss type.')                 # ibc_agent.py:336
-    if late_fusion:
-      raise NotImplementedError('late_fusion (PixelEBM) training is not built yet')
+    if late_fusion != isinstance(cloning_network, PixelEBM):
+      raise NotImplementedError('late_fusion must be used with (and only with) PixelEBM')
+    if late_fusion and (fraction_dfo_samples > 0. or fraction_langevin_samples > 0.
+                        or add_grad_penalty):
+      raise NotImplementedError(
+          'late-fusion training is built for uniform counter-examples without gradient '
+          'penalty (pushing_pixels/pixel_ebm_best.gin)')
     self._run_full_chain_under_gradient = run_full_chain_under_gradient
     self._return_full_chain = return_full_chain
     self._add_grad_penalty = add_grad_penalty
@@ -149,6 +155,8 @@ class ImplicitBCAgent(BehavioralCloningAgent):
     if weights is not None:
       raise NotImplementedError('sample weights are not supported')
     net = self.cloning_network
+    if self._late_fusion:
+      return self._loss_late_fusion(experience, training, draws or {})
     observations, actions = self._to_device(experience)
     obs_flat = net._flat_obs(observations)                       # [B, O]
     batch_size = obs_flat.shape[0]
@@ -188,6 +196,37 @@ class ImplicitBCAgent(BehavioralCloningAgent):
       if raw is not None:   # chain dL/dW_bar through the spectral normalisation
         (graw,) = torch.autograd.grad(eff, raw, grad_outputs=grads)
         grads.copy_(graw)
+      return specs.LossInfo(total_loss, ()), grads
+    return losses_dict
+
+  def _loss_late_fusion(self, experience, training, draws):
+    """ibc_agent.py:191-213: encode once (training=True), tile the encoding N+1
+    times, value head, InfoNCE; gradients flow into the conv encoder."""
+    net = self.cloning_network
+    (observations, actions), _ = experience if len(experience) == 2 and isinstance(
+        experience[0], tuple) else (experience, ())
+    images = net._images(observations)
+    actions = actions.to(net.device, torch.float32, non_blocking=True)
+    batch_size = images.shape[0]
+    n = self._num_counter_examples
+    expanded_actions = actions[:, None, :]
+    a_dim = actions.shape[-1]
+    u = draws.get('uniform_u')
+    counter = eng.uniform_actions(batch_size * n, self._min, self._max,
+                                  None if u is None else u.reshape(batch_size * n, a_dim)
+                                  .contiguous(), mcmc._next_seed()).view(batch_size, n, a_dim)
+    combined = torch.cat([counter, expanded_actions], dim=1).reshape(
+        batch_size * (n + 1), a_dim).contiguous()
+    global_batch = batch_size * self._num_replicas()
+    per_example, _, grads = net.engine.train_grads(images, combined, n, self._loss_cfg(),
+                                                   global_batch, self._grads)
+    total_loss = per_example.sum() / float(global_batch)
+    losses_dict = {'ebm_total_loss': total_loss}
+    if self._compute_mse:
+      mse = ((counter - expanded_actions) ** 2).mean(dim=-1).mean(dim=1)
+      losses_dict['mse_counter_examples'] = mse.sum() / float(global_batch)
+    self.last_losses_dict = losses_dict
+    if training:
       return specs.LossInfo(total_loss, ()), grads
     return losses_dict
 

@@ -23,6 +23,7 @@ from ibc_b200 import engine as eng
 from ibc_b200 import gin_lite as gin
 from ibc_b200.ibc import specs
 from ibc_b200.networks.mlp_ebm import MLPEBM
+from ibc_b200.networks.pixel_ebm import PixelEBM
 
 my_range = range
 
@@ -91,6 +92,14 @@ def iterative_dfo(network,
     obs = _untile(network._flat_obs(observations), batch_size, n)
     actions = action_samples.to(torch.float32).contiguous().clone()
     probs = network.engine.dfo(obs, actions, n, min_actions, max_actions, temperature,
+                               num_iterations, iteration_std, uniform_draws, normal_draws, seed)
+    return probs, actions, policy_state
+
+  if isinstance(network, PixelEBM) and late_fusion:
+    # embed observations once (:98-102), then the whole loop runs in the library
+    enc = network.encode(observations, training=training)
+    actions = action_samples.to(torch.float32).contiguous().clone()
+    probs = network.engine.dfo(enc, actions, n, min_actions, max_actions, temperature,
                                num_iterations, iteration_std, uniform_draws, normal_draws, seed)
     return probs, actions, policy_state
 

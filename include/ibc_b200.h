@@ -231,6 +231,64 @@ int ibc_adam_step(float* params, const float* grads, float* m, float* v,
                   int64_t count, float lr_t, float beta1, float beta2,
                   float epsilon, void* stream);
 
+/* ---- late-fusion PixelEBM ---------------------------------------------- */
+
+/* networks/pixel_ebm.py:46-125 with encoder_network='ConvMaxpoolEncoder'
+ * (networks/layers/conv_maxpool.py:20-48) and value_network='DenseResnetValue'
+ * (networks/layers/dense_resnet_value.py:22-69).  Flat parameter vector:
+ * conv{1..4}: kernel [3,3,cin,cout] (Keras layout) + bias [cout], channels
+ * C*T -> 32 -> 64 -> 128 -> 256; value dense0 [256 + A, Wv] + b [Wv]; per block
+ * d0 [Wv, Wv/4] + b, d1 [Wv/4, Wv/4] + b, d2 [Wv/4, Wv] + b; dense1 [Wv] + b [1]. */
+typedef struct ibc_pixel_handle ibc_pixel_handle;
+
+typedef struct {
+  int32_t seq_len;       /* T: stacked frames (obs_spec['rgb'].shape[0])           */
+  int32_t height, width; /* raw frame size (240 x 320)                             */
+  int32_t channels;      /* 3                                                      */
+  int32_t target_height; /* PixelEBM.target_height (180)                           */
+  int32_t target_width;  /* PixelEBM.target_width (240)                            */
+  int32_t act_dim;       /* A                                                      */
+  int32_t value_width;   /* DenseResnetValue.width (multiple of 4)                 */
+  int32_t value_blocks;  /* DenseResnetValue.num_blocks                            */
+} ibc_pixel_arch;
+
+int ibc_pixel_create(const ibc_pixel_arch* arch, int device, ibc_pixel_handle** out);
+int ibc_pixel_destroy(ibc_pixel_handle* h);
+const char* ibc_pixel_last_error(const ibc_pixel_handle* h);
+int64_t ibc_pixel_param_count(const ibc_pixel_arch* arch);
+int ibc_pixel_bind_params(ibc_pixel_handle* h, const float* params);
+
+/* PixelEBM.encode (pixel_ebm.py:79-96): images [B, T, H, W, C] uint8 (is_uint8)
+ * or float32 in [0,1] -> u8/255, RAW reshape to [B, H, W, C*T]
+ * (image_prepro.py:28), bilinear resize (half-pixel centres), 4 x (conv3x3 same
+ * + ReLU + maxpool2), global average pool -> enc [B, 256]. */
+int ibc_pixel_encode(ibc_pixel_handle* h, const void* images, int32_t is_uint8,
+                     int64_t B, float* enc, void* stream);
+
+/* PixelEBM.call with observation_encoding (pixel_ebm.py:113-125): energy[r] of
+ * concat(enc[r / n], act[r]) through DenseResnetValue; enc is un-tiled. */
+int ibc_pixel_energy(ibc_pixel_handle* h, const float* enc, int64_t B,
+                     const float* act, int64_t n, float* energy, void* stream);
+
+/* mcmc.iterative_dfo with late_fusion=True (mcmc.py:98-110): the observation
+ * is encoded once by the caller (ibc_pixel_encode); same draws contract as
+ * ibc_dfo. */
+int ibc_pixel_dfo(ibc_pixel_handle* h, const float* enc, int64_t B, float* actions,
+                  int64_t n, const float* min_actions, const float* max_actions,
+                  float temperature, int32_t num_iterations, float iteration_std,
+                  const double* uniforms, const float* normals, uint64_t seed,
+                  float* probs, void* stream);
+
+/* Late-fusion ImplicitBCAgent._loss + tape.gradient (ibc_agent.py:191-250):
+ * encode (training=True), tile the encoding N+1 times, value head, InfoNCE,
+ * backward through the value head and the conv encoder.  cfg->add_grad_penalty
+ * must be 0.  grads [param_count] is overwritten. */
+int ibc_pixel_train_grads(ibc_pixel_handle* h, const void* images, int32_t is_uint8,
+                          int64_t B, const float* actions, int64_t N,
+                          const ibc_loss_cfg* cfg, int64_t global_batch,
+                          float* per_example_loss, float* energies, float* grads,
+                          void* stream);
+
 /* ---- diagnostics ------------------------------------------------------- */
 
 /* Number of kernels this library has launched since the handle was created

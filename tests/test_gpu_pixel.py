@@ -1,0 +1,175 @@
+"""GPU parity tests of the late-fusion PixelEBM (fp32 path) against the oracle
+(oracle/pixel_ebm.py) on identical inputs.  Tolerance: fp32 kernels vs the fp64
+oracle, |d| <= 1e-4 * (|x| + rms(x)) for activations/energies, 2e-3 relative
+Frobenius error per parameter tensor for gradients (long fp32 reductions over
+B*H*W rows)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import losses as olosses
+from oracle import mcmc as omcmc
+from oracle import pixel_ebm as opix
+
+pytestmark = pytest.mark.gpu
+
+SMALL = opix.PixelSpec(seq_len=2, height=40, width=56, channels=3, target_height=32,
+                       target_width=48, act_dim=2, value_width=64, value_blocks=2)
+
+
+def _close(got, want, tol, name=''):
+  got, want = got.detach().double().cpu(), want.detach().double().cpu()
+  assert got.shape == want.shape, (name, got.shape, want.shape)
+  rms = float(want.pow(2).mean().sqrt())
+  worst = float(((got - want).abs() / (tol * (want.abs() + rms) + 1e-30)).max())
+  assert worst <= 1.0, '%s: err/bound %.3g (rms %.3g)' % (name, worst, rms)
+
+
+def _engine(spec, seed=1):
+  from ibc_b200 import engine as eng
+  e = eng.PixelEngine(spec.seq_len, spec.height, spec.width, spec.channels, spec.target_height,
+                      spec.target_width, spec.act_dim, spec.value_width, spec.value_blocks)
+  flat = opix.init_params(spec, seed=seed)
+  assert e.param_count == opix.param_count(spec)
+  dev = flat.cuda().contiguous()
+  e.bind_params(dev)
+  e._keep = dev
+  return e, flat
+
+
+def _images(spec, b, seed=0, u8=True):
+  g = torch.Generator().manual_seed(seed)
+  img = torch.randint(0, 256, (b, spec.seq_len, spec.height, spec.width, spec.channels),
+                      generator=g, dtype=torch.uint8)
+  return img if u8 else img.float() / 255.0
+
+
+@pytest.mark.parametrize('u8', [True, False])
+def test_encode_matches_oracle(u8):
+  e, flat = _engine(SMALL)
+  img = _images(SMALL, 3, u8=u8)
+  got = e.encode(img.cuda())
+  want = opix.encode(flat.double(), SMALL, img.double() / 255.0 if u8 else img.double())
+  _close(got, want, 1e-4, 'encode')
+
+
+def test_value_energy_matches_oracle():
+  e, flat = _engine(SMALL)
+  b, n = 3, 17
+  g = torch.Generator().manual_seed(2)
+  enc = torch.rand(b, 256, generator=g)
+  act = torch.rand(b * n, 2, generator=g) * 2 - 1
+  got = e.energy(enc.cuda(), act.cuda(), n)
+  want = opix.value(flat.double(), SMALL, torch.repeat_interleave(enc, n, 0).double(), act.double())
+  _close(got, want, 1e-4, 'value energy')
+
+
+def test_train_grads_match_oracle_autograd():
+  from ibc_b200 import engine as eng
+  e, flat = _engine(SMALL)
+  b, n = 4, 7
+  img = _images(SMALL, b, seed=3)
+  g = torch.Generator().manual_seed(4)
+  act = torch.rand(b * (n + 1), 2, generator=g) * 2 - 1
+  theta = flat.double().clone().requires_grad_(True)
+  pred = opix.energy(theta, SMALL, img.double() / 255.0, act.double()).reshape(b, n + 1)
+  per = olosses.info_nce(pred, b, n, 1.0)
+  gb = 2 * b
+  (want,) = torch.autograd.grad(per.sum() / gb, theta, retain_graph=True)
+  dpred_l1 = float(torch.autograd.grad(per.sum() / gb, pred)[0].abs().sum())
+  per_g, en_g, grads = e.train_grads(img.cuda(), act.cuda(), n, eng.loss_cfg(1.0, False), gb,
+                                     want_energies=True)
+  _close(en_g, pred.reshape(-1), 1e-4, 'energies')
+  _close(per_g, per, 1e-4, 'per-example loss')
+  grms = float(want.pow(2).mean().sqrt())
+  for name, off, shape in opix.param_layout(SMALL):
+    cnt = math.prod(shape)
+    w = want[off:off + cnt]
+    got = grads[off:off + cnt].double().cpu()
+    denom = float(w.norm()) + 1e-2 * grms * math.sqrt(cnt)
+    if name == 'v_dense1_b':
+      denom = dpred_l1     # sum of softmax gradients cancels to ~0: compare to the terms
+    rel = float((got - w).norm()) / denom
+    assert rel < 2e-3, (name, rel)
+
+
+def test_pixel_dfo_pipeline_bit_exact_given_gpu_energies():
+  e, _ = _engine(SMALL)
+  b, n, iters = 2, 256, 3
+  img = _images(SMALL, b, seed=5)
+  enc = e.encode(img.cuda())
+  rs = np.random.RandomState(1)
+  uniforms = rs.rand(iters, b, n)
+  normals = torch.from_numpy(rs.randn(iters - 1, b * n, 2).astype(np.float32))
+  act0 = torch.from_numpy(rs.rand(b * n, 2).astype(np.float32)) * 2 - 1
+  mn, mx = torch.full((2,), -1.1), torch.full((2,), 1.1)
+
+  def gpu_energy(_obs, actions):
+    return e.energy(enc, actions.float().cuda().contiguous(), n).cpu()
+
+  want_probs, want_actions = omcmc.iterative_dfo(gpu_energy, b, None, act0, n, mn, mx, uniforms,
+                                                 normals)
+  actions = act0.cuda().clone()
+  probs = e.dfo(enc, actions, n, mn.cuda(), mx.cuda(), 1.0, iters, 0.33,
+                torch.from_numpy(uniforms).cuda(), normals.cuda())
+  assert torch.equal(actions.cpu(), want_actions)
+  _close(probs, want_probs, 1e-5, 'dfo probs')
+
+
+def test_network_agent_and_policy_surface():
+  """PixelEBM / late-fusion ImplicitBCAgent / IbcPolicy with the reference's
+  call protocol: a few training steps reduce the loss; the DFO policy returns a
+  bounded action."""
+  from ibc_b200 import gin_lite as gin
+  from ibc_b200.ibc import specs
+  from ibc_b200.ibc.agents import ibc_agent, ibc_policy
+  from ibc_b200.ibc.train import get_agent
+  from ibc_b200.networks.pixel_ebm import PixelEBM
+  gin.clear_config()
+  gin.parse_config('DenseResnetValue.width = 64\nDenseResnetValue.num_blocks = 1')
+  try:
+    obs_spec = {'rgb': specs.TensorSpec((2, 40, 56, 3), dtype=torch.uint8)}
+    act_spec = specs.BoundedTensorSpec((2,), minimum=-1.0, maximum=1.0)
+    samp = specs.BoundedTensorSpec((2,), minimum=-1.1, maximum=1.1)
+    net = PixelEBM((obs_spec, act_spec), specs.TensorSpec((1,)), 'ConvMaxpoolEncoder',
+                   'DenseResnetValue', target_height=32, target_width=48, seed=0)
+    with pytest.raises(ValueError):
+      PixelEBM((obs_spec, act_spec), specs.TensorSpec((1,)), 'Nope', 'DenseResnetValue')
+    opt = get_agent.Adam(1e-3)
+    agent = ibc_agent.ImplicitBCAgent(obs_spec, act_spec, samp, net, opt, num_counter_examples=16,
+                                      fraction_langevin_samples=0.0, late_fusion=True,
+                                      add_grad_penalty=False, compute_mse=True)
+    g = torch.Generator().manual_seed(0)
+    # the action is readable from the mean brightness of two colour channels
+    level = torch.randint(0, 200, (8, 1, 1, 1, 3), generator=g)
+    img = (level + torch.randint(0, 56, (8, 2, 40, 56, 3), generator=g)).to(torch.uint8)
+    act = (level[:, 0, 0, 0, :2].float() / 200.0) * 2 - 1
+    losses = [float(agent.train((({'rgb': img}, act), ())).loss) for _ in range(80)]
+    assert losses[-1] < losses[0] - 0.3, (losses[0], losses[-1])
+    # network call protocol
+    enc = net.encode({'rgb': img.cuda()}, training=False)
+    assert tuple(enc.shape) == (8, 256)
+    acts = torch.rand(8 * 5, 2).cuda()
+    e1, _ = net(({'rgb': img.cuda()}, acts), training=False)
+    e2, _ = net(({'rgb': img.cuda()}, acts), training=False,
+                observation_encoding=specs.tile_batch(enc, 5))
+    assert torch.allclose(e1, e2, atol=1e-5)
+    pol = ibc_policy.GreedyPolicy(ibc_policy.IbcPolicy(
+        obs_spec, act_spec, samp, net, num_action_samples=256, use_dfo=True, use_langevin=False,
+        late_fusion=True))
+    a = pol.action(specs.restart({'rgb': img[:1]})).action
+    assert tuple(a.shape) == (1, 2) and bool((a.abs() <= 1.0).all())
+  finally:
+    gin.clear_config()
+
+
+def test_full_size_frames_run():
+  """pushing_pixels/pixel_ebm_best.gin shapes: 2 x 240x320x3 -> 180x240, Wv=1024, 1 block."""
+  spec = opix.PixelSpec()
+  e, flat = _engine(spec)
+  img = _images(spec, 2, seed=9)
+  enc = e.encode(img.cuda())
+  want = opix.encode(flat.double(), spec, img.double() / 255.0)
+  _close(enc, want, 2e-4, 'full-size encode')
