@@ -66,6 +66,10 @@ bool umma_train_supported(const Layout& L);
 int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* actions, int64_t N,
                      const ibc_loss_cfg& c, int64_t global_batch, float* per_example,
                      float* grad_loss_out, float* energies_out, float* grads, cudaStream_t s);
+int umma_reverse(ibc_handle* h, const float* dE, int64_t R, const float* xa_save, float* gy_save,
+                 float* g0, float* dwe, cudaStream_t s);
+int mlp_energy_dact_umma(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
+                         float* E, float* dEda, bool apply_exp, cudaStream_t s);
 int mlp_energy_umma(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
                     float* E, float* dEda, bool apply_exp, cudaStream_t s);
 

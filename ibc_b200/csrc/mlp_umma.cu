@@ -551,10 +551,7 @@ int mlp_energy_umma(ibc_handle* h, const float* obs, int64_t B, const float* act
   const Layout& L = h->L;
   if (!umma_supported(L))
     IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "tcgen05 path supports width 128/256, act_dim <= 32");
-  if (dEda) {
-    // The fused reverse chain is not built yet: dE/dact runs on the fp32 path.
-    return mlp_energy_dact_fp32(h, obs, B, act, n, E, dEda, apply_exp, s);
-  }
+  if (dEda) return mlp_energy_dact_umma(h, obs, B, act, n, E, dEda, apply_exp, s);
   IBC_CUDA(h, h->ws.reserve(Workspace::rounded((size_t)B * L.W * 4)));
   h->ws.reset();
   float* hp = h->ws.take<float>((size_t)B * L.W);

@@ -52,14 +52,15 @@ struct BwdParams {
   int* status;
 };
 
+template <int W_, int NT_>
 struct BwdSmem {
-  static constexpr int kABytes = 128 * kW * 4;
-  static constexpr int kSliceK = kSliceBytes / (kW * 4);
-  static constexpr int kSlicesPerLayer = kW / kSliceK;
+  static constexpr int kABytes = 128 * W_ * 4;
+  static constexpr int kSliceK = kSliceBytes / (W_ * 4);
+  static constexpr int kSlicesPerLayer = W_ / kSliceK;
   static constexpr int kStepsPerSlice = kSliceK / 8;
-  static constexpr int kThreads = (4 * kNT + 2) * 32;
-  static constexpr size_t kBytes = (size_t)kNT * kABytes + (size_t)kSlots * kSliceBytes +
-                                   2 * kW * 4 + 256;
+  static constexpr int kThreads = (4 * NT_ + 2) * 32;
+  static constexpr size_t kBytes = (size_t)NT_ * kABytes + (size_t)kSlots * kSliceBytes +
+                                   2 * W_ * 4 + 256;
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -68,10 +69,11 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-__global__ void __launch_bounds__(BwdSmem::kThreads, 1) mlp_bwd_umma_kernel(BwdParams p) {
-  using S = BwdSmem;
-  using TT = TrainTile<kW>;
-  constexpr int W = kW, NT = kNT;
+template <int W_, int NT_>
+__global__ void __launch_bounds__((4 * NT_ + 2) * 32, 1) mlp_bwd_umma_kernel(BwdParams p) {
+  using S = BwdSmem<W_, NT_>;
+  using TT = TrainTile<W_>;
+  constexpr int W = W_, NT = NT_;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* a_base = smem;
   unsigned char* ring = smem + NT * S::kABytes;
@@ -122,8 +124,8 @@ __global__ void __launch_bounds__(BwdSmem::kThreads, 1) mlp_bwd_umma_kernel(BwdP
         // dwe += h_nb^T dE with h_nb from the forward's last slot
         const float4* hn = reinterpret_cast<const float4*>(
             p.xa_save + TT::slot_base(tile_id, xa_slots, 2 * p.nb));
-        float4* gy_top = reinterpret_cast<float4*>(
-            p.gy_save + TT::slot_base(tile_id, gy_slots, 2 * p.nb - 1));
+        float4* gy_top = p.gy_save ? reinterpret_cast<float4*>(
+            p.gy_save + TT::slot_base(tile_id, gy_slots, 2 * p.nb - 1)) : nullptr;
 #pragma unroll 1
         for (int c32 = 0; c32 < W / 32; ++c32) {
           uint32_t v[32];
@@ -135,13 +137,15 @@ __global__ void __launch_bounds__(BwdSmem::kThreads, 1) mlp_bwd_umma_kernel(BwdP
             v[q * 4 + 0] = __float_as_uint(g4.x); v[q * 4 + 1] = __float_as_uint(g4.y);
             v[q * 4 + 2] = __float_as_uint(g4.z); v[q * 4 + 3] = __float_as_uint(g4.w);
             a_tile[c * 128 + row] = tf32_rn4(g4);
-            gy_top[TT::chunk_f4(row, c)] = g4;     // fp32: exact bias sums, MMA truncates
-            const float4 h4 = hn[TT::chunk_f4(row, c)];
-            const float s0 = warp_sum(de * h4.x), s1 = warp_sum(de * h4.y);
-            const float s2 = warp_sum(de * h4.z), s3 = warp_sum(de * h4.w);
-            if (lane == 0) {
-              atomicAdd(&dwe_acc[c * 4 + 0], s0); atomicAdd(&dwe_acc[c * 4 + 1], s1);
-              atomicAdd(&dwe_acc[c * 4 + 2], s2); atomicAdd(&dwe_acc[c * 4 + 3], s3);
+            if (gy_top) gy_top[TT::chunk_f4(row, c)] = g4;   // fp32: exact bias sums, MMA truncates
+            if (p.dwe) {
+              const float4 h4 = hn[TT::chunk_f4(row, c)];
+              const float s0 = warp_sum(de * h4.x), s1 = warp_sum(de * h4.y);
+              const float s2 = warp_sum(de * h4.z), s3 = warp_sum(de * h4.w);
+              if (lane == 0) {
+                atomicAdd(&dwe_acc[c * 4 + 0], s0); atomicAdd(&dwe_acc[c * 4 + 1], s1);
+                atomicAdd(&dwe_acc[c * 4 + 2], s2); atomicAdd(&dwe_acc[c * 4 + 3], s3);
+              }
             }
           }
           tmem_st32(tmem_base + lane_off + col_g + c32 * 32, v);
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(BwdSmem::kThreads, 1) mlp_bwd_umma_kernel(BwdP
         const bool last = (i == 1);
         const float4* xm = reinterpret_cast<const float4*>(
             p.xa_save + TT::slot_base(tile_id, xa_slots, i - 1));
-        float4* gy_out = last ? nullptr : reinterpret_cast<float4*>(
+        float4* gy_out = (last || !p.gy_save) ? nullptr : reinterpret_cast<float4*>(
             p.gy_save + TT::slot_base(tile_id, gy_slots, i - 2));
 #pragma unroll 1
         for (int c32 = 0; c32 < W / 32; ++c32) {
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(BwdSmem::kThreads, 1) mlp_bwd_umma_kernel(BwdP
             }
             if (!last) {
               a_tile[c * 128 + row] = tf32_rn4(o);
-              gy_out[TT::chunk_f4(row, c)] = o;
+              if (gy_out) gy_out[TT::chunk_f4(row, c)] = o;
             } else if (valid) {
               *reinterpret_cast<float4*>(p.g0 + r * W + c * 4) = o;
             }
@@ -262,7 +266,8 @@ __global__ void __launch_bounds__(BwdSmem::kThreads, 1) mlp_bwd_umma_kernel(BwdP
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
-  for (int i = tid; i < W; i += S::kThreads) atomicAdd(p.dwe + i, dwe_acc[i]);
+  if (p.dwe)
+    for (int i = tid; i < W; i += S::kThreads) atomicAdd(p.dwe + i, dwe_acc[i]);
 }
 
 // dWp_act[a, w] += sum_r act[r, a] * g0[r, w]: one thread per output feature w
@@ -433,6 +438,71 @@ __global__ void __launch_bounds__(WgradSmem::kThreads, 1) mlp_wgrad_umma_kernel(
 
 }  // namespace
 
+template <int W_, int NT_>
+static int launch_bwd(ibc_handle* h, const BwdParams& bp, cudaStream_t s) {
+  using S = BwdSmem<W_, NT_>;
+  IBC_CUDA(h, cudaFuncSetAttribute(mlp_bwd_umma_kernel<W_, NT_>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
+  const int grid = bp.num_groups < h->sm_count ? bp.num_groups : h->sm_count;
+  mlp_bwd_umma_kernel<W_, NT_><<<grid, S::kThreads, S::kBytes, s>>>(bp);
+  IBC_LAUNCH_CHECK(h);
+  return IBC_OK;
+}
+
+// Fused reverse chain over the tiles saved by umma_forward(..., xa_save): g0 [R, W]
+// = d(sum_r dE[r] * E[r]) / d(first Dense output).  gy_save / dwe are optional
+// (training only).
+int umma_reverse(ibc_handle* h, const float* dE, int64_t R, const float* xa_save, float* gy_save,
+                 float* g0, float* dwe, cudaStream_t s) {
+  const Layout& L = h->L;
+  const PackedLayout pl = make_packed_layout(L);
+  BwdParams bp;
+  bp.dE = dE; bp.xa_save = xa_save; bp.gy_save = gy_save; bp.g0 = g0; bp.packed = h->packed;
+  bp.off_rev_l = pl.rev_l; bp.off_we = pl.vecs + (int64_t)(2 * L.nb + 1) * L.W;
+  bp.dwe = dwe; bp.R = R; bp.nb = L.nb; bp.status = h->dev_status;
+  if (L.W == 128) {
+    bp.num_groups = (int)((R + 255) / 256);
+    return launch_bwd<128, 2>(h, bp, s);
+  }
+  bp.num_groups = (int)((R + 127) / 128);
+  return launch_bwd<256, 1>(h, bp, s);
+}
+
+__global__ void fill_or_exp_kernel(float* __restrict__ e, float* __restrict__ de, int64_t R,
+                                   int apply_exp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  if (apply_exp) { const float v = expf(e[i]); e[i] = v; de[i] = v; } else { de[i] = 1.0f; }
+}
+
+// mcmc.gradient_wrt_act (ibc/agents/mcmc.py:161-191) on tensor cores: fused
+// forward (operands saved per tile), fused reverse chain, then
+// dE/dact = g0 . Wp[O:]^T (K = W, N = act_dim: fp32 GEMM).
+int mlp_energy_dact_umma(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
+                         float* E, float* dEda, bool apply_exp, cudaStream_t s) {
+  const Layout& L = h->L;
+  const int64_t R = B * n;
+  const int nt = (L.W == 128) ? 2 : 1;
+  const int64_t tiles = ((R + 128 * nt - 1) / (128 * nt)) * nt;
+  const size_t xa_floats = (size_t)tiles * (2 * L.nb + 1) * 128 * L.W;
+  const size_t bytes = Workspace::rounded(xa_floats * 4) + Workspace::rounded((size_t)R * L.W * 4) +
+                       Workspace::rounded((size_t)B * L.W * 4) + Workspace::rounded((size_t)R * 4);
+  IBC_CUDA(h, h->ws.reserve(bytes));
+  h->ws.reset();
+  float* xa = h->ws.take<float>(xa_floats);
+  float* g0 = h->ws.take<float>((size_t)R * L.W);
+  float* hp = h->ws.take<float>((size_t)B * L.W);
+  float* dE = h->ws.take<float>(R);
+  IBC_TRY(umma_forward(h, obs, B, act, n, hp, E, xa, s));
+  fill_or_exp_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(E, dE, R, apply_exp ? 1 : 0);
+  IBC_LAUNCH_CHECK(h);
+  IBC_TRY(umma_reverse(h, dE, R, xa, nullptr, g0, nullptr, s));
+  GemmP g;
+  g.A = g0; g.lda = L.W; g.B = h->params + L.wp + (int64_t)L.O * L.W; g.ldb = L.W;
+  g.C = dEda; g.ldc = L.A; g.M = (int)R; g.N = L.A; g.K = L.W;
+  return gemm(h, g, false, true, s);
+}
+
 bool umma_train_supported(const Layout& L) {
   return umma_supported(L) && L.W == kW;
 }
@@ -489,22 +559,7 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
   if (use_ts) {
     IBC_TRY(umma_backward_ts(h, dE, R, xa, gy, g0, grads + L.we, kNT, s));
   } else {
-    const PackedLayout pl = make_packed_layout(L);
-    BwdParams bp;
-    bp.dE = dE; bp.xa_save = xa; bp.gy_save = gy; bp.g0 = g0; bp.packed = h->packed;
-    bp.off_rev_l = pl.rev_l; bp.off_we = pl.vecs + (int64_t)(2 * nb + 1) * W;
-    bp.dwe = grads + L.we; bp.R = R; bp.nb = nb; bp.num_groups = num_groups;
-    bp.status = h->dev_status;
-    static bool bwd_attr = false;
-    if (!bwd_attr) {
-      IBC_CUDA(h, cudaFuncSetAttribute(mlp_bwd_umma_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)BwdSmem::kBytes));
-      bwd_attr = true;
-    }
-    const int grid = num_groups < h->sm_count ? num_groups : h->sm_count;
-    mlp_bwd_umma_kernel<<<grid, BwdSmem::kThreads, BwdSmem::kBytes, s>>>(bp);
-    IBC_LAUNCH_CHECK(h);
+    IBC_TRY(umma_reverse(h, dE, R, xa, gy, g0, grads + L.we, s));
   }
   mark(3);
   {
