@@ -269,3 +269,57 @@ def test_gin_configured_network_and_errors():
       MLPEBM((obs_spec, act_spec), specs.TensorSpec((1,)), depth=3)
   finally:
     gin.clear_config()
+
+
+def test_spectral_norm_network_matches_oracle():
+  """MLPEBM(dense_layer_type='spectral_norm') (d4rl/mlp_ebm_langevin_best.gin:46,
+  networks/layers/spectral_norm.py:57-86): forward on W_bar = W / sigma, gradient
+  chained back through the power iteration, u updated only when training."""
+  from ibc_b200 import _lib
+  from ibc_b200 import gin_lite as gin
+  from ibc_b200.ibc import specs
+  from ibc_b200.ibc.agents import ibc_agent
+  from ibc_b200.ibc.train import get_agent
+  from ibc_b200.networks.mlp_ebm import MLPEBM
+  from oracle import losses as olosses
+  gin.clear_config()
+  spec = omlp.MLPSpec(10, 3, 64, 2)
+  obs_spec = {'obs': specs.TensorSpec((1, spec.obs_dim))}
+  act_spec = specs.BoundedTensorSpec((3,), minimum=-1.0, maximum=1.0)
+  samp = specs.BoundedTensorSpec((3,), minimum=-1.1, maximum=1.1)
+  net = MLPEBM((obs_spec, act_spec), specs.TensorSpec((1,)), width=64, depth=2, rate=0.0,
+               layers='ResNetPreActivation', dense_layer_type='spectral_norm', seed=4)
+  net.engine.set_precision(_lib.PRECISION_FP32)
+  us = omlp.init_sn_u(spec, seed=3)
+  net._sn_u = {k: v.cuda() for k, v in us.items()}
+  net._rebind()
+  flat = net.params.detach().cpu().clone()
+  b, n = 8, 5
+  g = torch.Generator().manual_seed(2)
+  obs = torch.randn(b, 1, spec.obs_dim, generator=g)
+  act = torch.rand(b, 3, generator=g) * 2 - 1
+  u = torch.rand(b, n, 3, generator=g)
+  # network forward on the normalised weights
+  acts = torch.rand(b, 3, generator=g) * 2 - 1
+  eff, _ = omlp.sn_effective_params(flat, us, spec)
+  want_e = omlp.energy(eff, spec, obs.reshape(b, -1), acts)
+  got_e, _ = net(({'obs': obs.cuda()}, acts.cuda()), training=False)
+  assert float((got_e.cpu() - want_e).abs().max()) < 1e-5
+  # training gradient w.r.t. the RAW weights
+  agent = ibc_agent.ImplicitBCAgent(obs_spec, act_spec, samp, net, get_agent.Adam(1e-3),
+                                    num_counter_examples=n, fraction_langevin_samples=0.0,
+                                    add_grad_penalty=False)
+  info, grads = agent._loss((({'obs': obs}, act), ()), training=True, draws={'uniform_u': u.cuda()})
+  theta = flat.clone().requires_grad_(True)
+  eff_t, new_us = omlp.sn_effective_params(theta, us, spec)
+  mn, mx = torch.full((3,), -1.1), torch.full((3,), 1.1)
+  cfg = oagent.AgentConfig(num_counter_examples=n, fraction_langevin_samples=0.0,
+                           add_grad_penalty=False)
+  total, _, _ = oagent.loss(lambda o, a: omlp.energy(eff_t, spec, o, a), cfg, obs.reshape(b, -1),
+                            act, mn, mx, u)
+  (want_grad,) = torch.autograd.grad(total, theta)
+  assert abs(float(info.loss) - float(total)) < 1e-5
+  rel = float((grads.cpu() - want_grad).norm() / want_grad.norm())
+  assert rel < 1e-4, rel
+  for k in new_us:                                   # u <- u' because training=True
+    assert torch.allclose(net._sn_u[k].cpu(), new_us[k], atol=1e-6)
