@@ -68,6 +68,18 @@ __global__ void pack_kernel(const float* __restrict__ P, Layout L, PackedLayout 
       const int wq = (int)(e & 3), a = (int)((e >> 2) % pl.AP), wc = (int)((e >> 2) / pl.AP);
       const int w = wc * 4 + wq;
       v = (a < L.A) ? P[L.wp + (int64_t)(L.O + a) * W + w] : 0.f;
+    } else if (i >= pl.fwd_bias) {
+      // bias of step s as a K = 8 operand slice [2 chunks][W][4]: row n of chunk 0 holds
+      // (hi, lo, 0, 0) with hi + lo = bias to ~2^-21; the matching A operand is a
+      // constant (1, 1, 0, 0 | 0) tile, so the MMA adds the bias in fp32
+      const int64_t e = i - pl.fwd_bias;
+      const int s = (int)(e / (8 * W));
+      const int r = (int)(e % (8 * W));
+      const int kc = r / (4 * W), n = (r / 4) % W, kq = r & 3;
+      float b = 0.f;
+      if (s > 0) b = (s & 1) ? P[L.b1((s - 1) >> 1) + n] : P[L.b2((s >> 1) - 1) + n];
+      const float hi = tf32_rn(b);
+      v = (kc == 0 && kq == 0) ? hi : ((kc == 0 && kq == 1) ? tf32_rn(b - hi) : 0.f);
     } else if (i >= pl.raw) {              // raw per-step biases (residual kept in registers)
       const int64_t e = i - pl.raw;
       const int s = (int)(e / W), w = (int)(e % W);
@@ -104,7 +116,7 @@ struct FwdParams {
   float* E;              // [R]
   int64_t R, n_per_obs;
   int nb, A, KP;
-  int64_t off_fwd_p, off_fwd_l, off_vecs;
+  int64_t off_fwd_p, off_fwd_l, off_vecs, off_fwd_bias;
   int* status;
   int num_groups;
   // Training: when non-null the A operand of every W x W layer (slots
@@ -123,24 +135,20 @@ struct FwdSmem {
   static constexpr int kStepsPerSlice = kSliceK / 8;
   static constexpr int kThreads = (4 * NT + 2) * 32;
   static size_t bytes(int nb) {
-    return (size_t)NT * kABytes + (size_t)kSlots * kSliceBytes + (size_t)(2 * nb + 2) * W * 4 +
-           16 + 256;
+    (void)nb;
+    return (size_t)NT * kABytes + (size_t)kSlots * kSliceBytes + 4096 + (size_t)W * 4 + 16 + 256;
   }
 };
 
-// 32 accumulator columns of one row: + bias, ReLU, write the 8 operand chunks.
+// 32 accumulator columns of one row (bias already added by the MMA): ReLU, round
+// to tf32, write the 8 operand chunks.
 template <bool kRelu, int W>
-__device__ __forceinline__ void emit_chunks(const uint32_t (&v)[32], const float* __restrict__ bias,
-                                            float4* __restrict__ a_tile, int c32, int row,
-                                            float4* __restrict__ g_slot) {
+__device__ __forceinline__ void emit_chunks(const uint32_t (&v)[32], float4* __restrict__ a_tile,
+                                            int c32, int row, float4* __restrict__ g_slot) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const float4 b = *reinterpret_cast<const float4*>(bias + c32 * 32 + q * 4);
-    float4 o;
-    o.x = __uint_as_float(v[q * 4 + 0]) + b.x;
-    o.y = __uint_as_float(v[q * 4 + 1]) + b.y;
-    o.z = __uint_as_float(v[q * 4 + 2]) + b.z;
-    o.w = __uint_as_float(v[q * 4 + 3]) + b.w;
+    float4 o = make_float4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]),
+                           __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
     if (kRelu) {
       o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
     }
@@ -156,9 +164,9 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* a_base = smem;
   unsigned char* ring = smem + NT * S::kABytes;
-  float* vecs = reinterpret_cast<float*>(ring + kSlots * kSliceBytes);
-  const int nvec = 2 * p.nb + 2;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(vecs + (size_t)nvec * W + 4);
+  float4* ones_tile = reinterpret_cast<float4*>(ring + kSlots * kSliceBytes);   // [2][128]
+  float* vecs = reinterpret_cast<float*>(ones_tile + 256);                        // we[W], be
+  uint64_t* bars = reinterpret_cast<uint64_t*>(vecs + W + 4);
   uint64_t* a_ready = bars;                 // [NT]
   uint64_t* d_ready = bars + NT;            // [NT]
   uint64_t* w_full = bars + 2 * NT;         // [kSlots]
@@ -176,15 +184,19 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
     for (int s = 0; s < kSlots; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     fence_mbar_init();
   }
-  for (int i = tid; i < nvec * W + 4; i += S::kThreads) vecs[i] = p.packed[p.off_vecs + i];
+  for (int i = tid; i < W + 4; i += S::kThreads)
+    vecs[i] = p.packed[p.off_vecs + (int64_t)(2 * p.nb + 1) * W + i];
+  for (int i = tid; i < 256; i += S::kThreads)
+    ones_tile[i] = (i < 128) ? make_float4(1.f, 1.f, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_proxy_async_smem();
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   volatile int* abort_flag = &s_abort;
-  const float* we = vecs + (size_t)(2 * p.nb + 1) * W;
-  const float be = vecs[(size_t)nvec * W];
+  const float* we = vecs;
+  const float be = vecs[W];
 
   if (warp < 4 * NT) {
     // ===================== epilogue warpgroup t ==============================
@@ -224,51 +236,62 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
         if (stamp) p.dbg[(i * NT + t) * 5 + 0] = clock64();
         const bool is_h = (i & 1) == 0;
         const uint32_t taddr = tmem_base + lane_off + (is_h ? col_h : col_v);
-        const float* bias = vecs + (size_t)i * W;
         if (i == nsteps - 1) {
           // Dense(1): E = (h + cb) . we + be   (mlp_ebm.py:91-94)
           float e = 0.f;
 #pragma unroll 1
-          for (int c32 = 0; c32 < W / 32; ++c32) {
-            uint32_t v[32];
-            tmem_ld32(taddr + c32 * 32, v);
+          for (int cb = 0; cb < W / 128; ++cb) {
+            // four 32-column loads in flight, one wait: the TMEM latency is paid once
+            uint32_t v[4][32];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tmem_ld32(taddr + cb * 128 + j * 32, v[j]);
             tmem_ld_wait();
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              float x = __uint_as_float(v[q]) + bias[c32 * 32 + q];
-              if (i == 0) x += hp_row[c32 * 32 + q];
-              e = fmaf(x, we[c32 * 32 + q], e);
-              v[q] = __float_as_uint(x);
-            }
-            if (g_slot) {
+            for (int j = 0; j < 4; ++j) {
+              const int c32 = cb * 4 + j;
 #pragma unroll
-              for (int q = 0; q < 8; ++q)
-                g_slot[TrainTile<W>::chunk_f4(row, c32 * 8 + q)] =
-                    make_float4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]),
-                                __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+              for (int q = 0; q < 32; ++q) {
+                float x = __uint_as_float(v[j][q]);
+                if (i == 0) x += hp_row[c32 * 32 + q];
+                e = fmaf(x, we[c32 * 32 + q], e);
+                v[j][q] = __float_as_uint(x);
+              }
+              if (g_slot) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  g_slot[TrainTile<W>::chunk_f4(row, c32 * 8 + q)] = make_float4(
+                      __uint_as_float(v[j][q * 4 + 0]), __uint_as_float(v[j][q * 4 + 1]),
+                      __uint_as_float(v[j][q * 4 + 2]), __uint_as_float(v[j][q * 4 + 3]));
+              }
             }
           }
           if (valid) p.E[r] = e + be;
           tc_fence_before();
         } else {
 #pragma unroll 1
-          for (int c32 = 0; c32 < W / 32; ++c32) {
-            uint32_t v[32];
-            tmem_ld32(taddr + c32 * 32, v);
-            tmem_ld_wait();
-            if (i == 0) {
-              // h0 = act . Wp[O:] + (obs . Wp[:O] + bp); keep it in tensor memory
+          for (int cb = 0; cb < W / 128; ++cb) {
+            uint32_t v[4][32];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 hv = *reinterpret_cast<const float4*>(hp_row + c32 * 32 + q * 4);
-                v[q * 4 + 0] = __float_as_uint(__uint_as_float(v[q * 4 + 0]) + hv.x);
-                v[q * 4 + 1] = __float_as_uint(__uint_as_float(v[q * 4 + 1]) + hv.y);
-                v[q * 4 + 2] = __float_as_uint(__uint_as_float(v[q * 4 + 2]) + hv.z);
-                v[q * 4 + 3] = __float_as_uint(__uint_as_float(v[q * 4 + 3]) + hv.w);
+            for (int j = 0; j < 4; ++j) tmem_ld32(taddr + cb * 128 + j * 32, v[j]);
+            tmem_ld_wait();
+            if (stamp && cb == 0) p.dbg[640 + i * NT + t] = clock64();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c32 = cb * 4 + j;
+              if (i == 0) {
+                // h0 = act . Wp[O:] + (obs . Wp[:O] + bp); keep it in tensor memory
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 hv = *reinterpret_cast<const float4*>(hp_row + c32 * 32 + q * 4);
+                  v[j][q * 4 + 0] = __float_as_uint(__uint_as_float(v[j][q * 4 + 0]) + hv.x);
+                  v[j][q * 4 + 1] = __float_as_uint(__uint_as_float(v[j][q * 4 + 1]) + hv.y);
+                  v[j][q * 4 + 2] = __float_as_uint(__uint_as_float(v[j][q * 4 + 2]) + hv.z);
+                  v[j][q * 4 + 3] = __float_as_uint(__uint_as_float(v[j][q * 4 + 3]) + hv.w);
+                }
+                tmem_st32(taddr + c32 * 32, v[j]);
               }
-              tmem_st32(taddr + c32 * 32, v);
+              emit_chunks<true, W>(v[j], a_tile, c32, row, g_slot);
             }
-            emit_chunks<true, W>(v, bias, a_tile, c32, row, g_slot);
           }
           if (i == 0) tmem_st_wait();
           if (stamp) p.dbg[(i * NT + t) * 5 + 1] = clock64();
@@ -298,6 +321,15 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
             bulk_g2s(ring + slot * kSliceBytes, src + (int64_t)s * (kSliceBytes / 4), bytes,
                      &w_full[slot]);
           }
+          if (i > 0) {   // this step's bias as one more K = 8 operand slice
+            const int slot = q % kSlots;
+            const uint32_t ph = (q / kSlots) & 1;
+            mbar_wait(&w_empty[slot], ph ^ 1, abort_flag, p.status, 250 + i);
+            mbar_arrive_expect_tx(&w_full[slot], (uint32_t)(8 * W * 4));
+            bulk_g2s(ring + slot * kSliceBytes, p.packed + p.off_fwd_bias + (int64_t)i * 8 * W,
+                     (uint32_t)(8 * W * 4), &w_full[slot]);
+            ++q;
+          }
         }
       }
     }
@@ -324,27 +356,48 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
             const bool mstamp = p.dbg && blockIdx.x == 0 && g == (int)blockIdx.x && i < 64;
             if (mstamp) p.dbg[(i * NT + t) * 5 + 3] = clock64();
             const uint32_t d_tmem = tmem_base + (uint32_t)(t * 2 * W + (to_h ? 0 : W));
-            const uint32_t a_addr = smem_u32(a_base + t * S::kABytes);
-            for (int s = 0; s < nsl; ++s) {
-              const uint32_t qq = q + s;
-              const int slot = qq % kSlots;
-              mbar_wait(&w_full[slot], (qq / kSlots) & 1, abort_flag, p.status, 400 + i);
-              const uint32_t b_addr = smem_u32(ring + slot * kSliceBytes);
-              const int ke = (i == 0) ? min(S::kSliceK, p.KP - s * S::kSliceK) : S::kSliceK;
-              const int kps = ke / 8;
-              for (int ks = 0; ks < kps; ++ks) {
-                // k-step (8 elements = 2 chunks) within the layer
-                const int kk = s * S::kStepsPerSlice + ks;
-                const uint64_t ad = smem_desc(a_addr + (uint32_t)kk * 2 * a_lbo, a_lbo, sbo);
-                const uint64_t bd = smem_desc(b_addr + (uint32_t)ks * 2 * b_lbo, b_lbo, sbo);
-                mma_tf32_ss(d_tmem, ad, bd, idesc, (acc0 | (uint32_t)(kk > 0)));
+            const uint64_t a_desc0 = smem_desc(smem_u32(a_base + t * S::kABytes), a_lbo, sbo);
+            constexpr uint32_t a_step16 = (2 * 128 * 16) >> 4, b_step16 = (2 * W * 16) >> 4;
+            if (i == 0) {
+              for (int s = 0; s < nsl; ++s) {
+                const uint32_t qq = q + s;
+                const int slot = qq % kSlots;
+                if (t == 0) mbar_wait(&w_full[slot], (qq / kSlots) & 1, abort_flag, p.status, 400);
+                const uint64_t b_desc0 = smem_desc(smem_u32(ring + slot * kSliceBytes), b_lbo, sbo);
+                const int kps = min(S::kSliceK, p.KP - s * S::kSliceK) / 8;
+                for (int ks = 0; ks < kps; ++ks) {
+                  const int kk = s * S::kStepsPerSlice + ks;
+                  mma_tf32_ss(d_tmem, a_desc0 + (uint64_t)(kk * a_step16),
+                              b_desc0 + (uint64_t)(ks * b_step16), idesc, (uint32_t)(kk > 0));
+                }
+                if (t == NT - 1) mma_commit(&w_empty[slot]);
               }
-              if (t == NT - 1) mma_commit(&w_empty[slot]);
+            } else {
+#pragma unroll
+              for (int s = 0; s < S::kSlicesPerLayer; ++s) {
+                const uint32_t qq = q + s;
+                const int slot = qq % kSlots;
+                // the second tile reuses slices the first tile already waited for
+                if (t == 0) mbar_wait(&w_full[slot], (qq / kSlots) & 1, abort_flag, p.status, 400 + i);
+                const uint64_t b_desc0 = smem_desc(smem_u32(ring + slot * kSliceBytes), b_lbo, sbo);
+                mma_tf32_ss_steps<S::kStepsPerSlice>(
+                    d_tmem, a_desc0 + (uint64_t)(s * S::kStepsPerSlice * a_step16), b_desc0,
+                    a_step16, b_step16, idesc, s == 0 ? acc0 : 1u);
+                if (t == NT - 1) mma_commit(&w_empty[slot]);
+              }
+              {   // + bias: (1, 1, 0, ...) . (hi, lo, 0, ...)^T
+                const uint32_t qq = q + S::kSlicesPerLayer;
+                const int slot = qq % kSlots;
+                if (t == 0) mbar_wait(&w_full[slot], (qq / kSlots) & 1, abort_flag, p.status, 450 + i);
+                mma_tf32_ss(d_tmem, smem_desc(smem_u32(ones_tile), a_lbo, sbo),
+                            smem_desc(smem_u32(ring + slot * kSliceBytes), b_lbo, sbo), idesc, 1u);
+                if (t == NT - 1) mma_commit(&w_empty[slot]);
+              }
             }
             mma_commit(&d_ready[t]);
             if (mstamp) p.dbg[(i * NT + t) * 5 + 4] = clock64();
           }
-          q += nsl;
+          q += nsl + (i > 0 ? 1 : 0);
         }
       }
     }
@@ -403,7 +456,7 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bpac
   if (warp < 4) {
     const int row = tid;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    if (mode == 0 || mode == 20 || mode == 22) {
+    if (mode == 0 || mode == 20 || mode == 22 || (mode >= 25 && mode <= 27)) {
       for (int c = 0; c < K / 4; ++c)
         a_tile[c * 128 + row] = *reinterpret_cast<const float4*>(A + (int64_t)row * K + c * 4);
       fence_proxy_async_smem();
@@ -433,7 +486,7 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bpac
   __syncthreads();
   tc_fence_after();
   if (warp == 4 && lane == 0 && mode >= 20) {
-    // MMA issue-rate microbenchmark: 16 passes over the K steps, results unused.
+    // MMA issue-rate microbenchmark: 256 passes over the K steps, results unused.
     // 20: A,B from shared memory (no swizzle); 21: A from tensor memory;
     // 22: A,B descriptors in the 128B-swizzle K-major form (timing only)
     mbar_wait(&bars[0], 0, abort_flag, status, 1);
@@ -441,9 +494,27 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bpac
     const uint32_t a_lbo = 128 * 16, b_lbo = (uint32_t)N * 16, sbo = 128;
     const int nk = K / 8;
     const long long t0 = clock64();
-    for (int rep = 0; rep < 16; ++rep)
+    for (int rep = 0; rep < 256; ++rep)
       for (int ks = 0; ks < nk; ++ks) {
-        if (mode == 22) {
+        if (mode >= 25 && mode <= 27) {
+          // accumulator-dependency probes: the same work as mode 20 split over several
+          // independent accumulators.  25: two N halves, 26: four N quarters,
+          // 27: two full-N accumulators alternating (N <= 128 so both fit)
+          const uint64_t ad = smem_desc(smem_u32(a_tile) + (uint32_t)ks * 2 * a_lbo, a_lbo, sbo);
+          if (mode == 27) {
+            const uint64_t bd = smem_desc(smem_u32(b_tile) + (uint32_t)ks * 2 * b_lbo, b_lbo, sbo);
+            mma_tf32_ss(tmem_base + ((rep & 1) ? 256u : 0u), ad, bd, idesc, 1);
+          } else {
+            const int parts = (mode == 25) ? 2 : 4;
+            const int np = N / parts;
+            const uint32_t idp = idesc_tf32(128, np);
+            for (int part = 0; part < parts; ++part) {
+              const uint64_t bd = smem_desc(smem_u32(b_tile) + (uint32_t)ks * 2 * b_lbo +
+                                                (uint32_t)(part * np) * 16, b_lbo, sbo);
+              mma_tf32_ss(tmem_base + (uint32_t)(part * np), ad, bd, idp, 1);
+            }
+          }
+        } else if (mode == 22) {
           const uint32_t ao = (uint32_t)(ks & 3) * 32 + (uint32_t)(ks >> 2) * (128 * 128);
           const uint32_t bo = (uint32_t)(ks & 3) * 32 + (uint32_t)(ks >> 2) * ((uint32_t)N * 128);
           mma_tf32_ss(tmem_base, smem_desc_lt(smem_u32(a_tile) + ao, 16, 1024, 2),
@@ -460,7 +531,7 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bpac
     mma_commit(&bars[1]);
     mbar_wait(&bars[1], 0, abort_flag, status, 2);
     const long long t1 = clock64();
-    atomicExch(status, (int)((t1 - t0) / (16 * nk)));      // cycles per MMA
+    atomicExch(status, (int)((t1 - t0) * 10 / (256 * nk)));      // 0.1 cycles per MMA
   } else if (warp == 4 && lane == 0) {
     mbar_wait(&bars[0], 0, abort_flag, status, 1);
     const uint32_t idesc = idesc_tf32(128, N);
@@ -584,20 +655,21 @@ int umma_forward(ibc_handle* h, const float* obs, int64_t B, const float* act, i
   p.act = act; p.hp = hp; p.packed = h->packed; p.E = E; p.R = R; p.n_per_obs = n;
   p.nb = L.nb; p.A = L.A; p.KP = pl.KP;
   p.off_fwd_p = pl.fwd_p; p.off_fwd_l = pl.fwd_l; p.off_vecs = pl.vecs;
+  p.off_fwd_bias = pl.fwd_bias;
   p.status = h->dev_status;
   p.xa_save = xa_save;
   p.dbg = nullptr;
   static const bool want_dbg = getenv("IBC_DBG_TIMELINE") != nullptr;
   if (want_dbg) {
-    IBC_CUDA(h, cudaMalloc((void**)&p.dbg, 64 * 2 * 5 * sizeof(long long)));
-    IBC_CUDA(h, cudaMemsetAsync(p.dbg, 0, 64 * 2 * 5 * sizeof(long long), s));
+    IBC_CUDA(h, cudaMalloc((void**)&p.dbg, (640 + 128) * sizeof(long long)));
+    IBC_CUDA(h, cudaMemsetAsync(p.dbg, 0, (640 + 128) * sizeof(long long), s));
   }
   struct DbgDump {
     long long* d; int nsteps, nt; cudaStream_t s;
     ~DbgDump() {
       if (!d) return;
       cudaStreamSynchronize(s);
-      std::vector<long long> hbuf(64 * 2 * 5);
+      std::vector<long long> hbuf(640 + 128);
       cudaMemcpy(hbuf.data(), d, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
       cudaFree(d);
       long long t0 = hbuf[3];
@@ -605,8 +677,9 @@ int umma_forward(ibc_handle* h, const float* obs, int64_t B, const float* act, i
       for (int i = 0; i < nsteps && i < 64; ++i)
         for (int t = 0; t < nt; ++t) {
           const long long* e = &hbuf[(i * nt + t) * 5];
-          fprintf(stderr, "[ibc timeline] %3d %d | %8lld %8lld | %8lld %8lld %8lld\n", i, t,
-                  e[3] - t0, e[4] - t0, e[0] - t0, e[1] ? e[1] - t0 : 0, e[2] ? e[2] - t0 : 0);
+          fprintf(stderr, "[ibc timeline] %3d %d | %8lld %8lld | %8lld (tmem loaded +%5lld) %8lld %8lld\n", i, t,
+                  e[3] - t0, e[4] - t0, e[0] - t0, hbuf[640 + i * nt + t] ? hbuf[640 + i * nt + t] - e[0] : 0,
+                  e[1] ? e[1] - t0 : 0, e[2] ? e[2] - t0 : 0);
         }
     }
   } dump{p.dbg, 2 * L.nb + 1, L.W == 128 ? 2 : 1, s};

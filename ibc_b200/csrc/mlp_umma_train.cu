@@ -157,44 +157,68 @@ __global__ void __launch_bounds__((4 * NT_ + 2) * 32, 1) mlp_bwd_umma_kernel(Bwd
       }
       for (int s = 0; s < nsteps; ++s) {
         const int i = nsteps - s;                     // forward layer index 2nb .. 1
-        mbar_wait(&d_ready[t], ph_d, abort_flag, p.status, 500 + s);
-        ph_d ^= 1;
-        tc_fence_after();
         const bool odd = (i & 1) != 0;                // W1 layer: result adds onto g
         const bool last = (i == 1);
         const float4* xm = reinterpret_cast<const float4*>(
             p.xa_save + TT::slot_base(tile_id, xa_slots, i - 1));
         float4* gy_out = (last || !p.gy_save) ? nullptr : reinterpret_cast<float4*>(
             p.gy_save + TT::slot_base(tile_id, gy_slots, i - 2));
-#pragma unroll 1
+        // ReLU masks of this layer (saved forward operand > 0) as bits, fetched
+        // while the tensor core is still working on this step's MMA
+        uint32_t mbits[W / 32];
+#pragma unroll
         for (int c32 = 0; c32 < W / 32; ++c32) {
-          uint32_t v[32], gp[32];
-          tmem_ld32(tmem_base + lane_off + col_d + c32 * 32, v);
-          if (odd) tmem_ld32(tmem_base + lane_off + col_g + c32 * 32, gp);
-          tmem_ld_wait();
+          uint32_t bits = 0;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const int c = c32 * 8 + q;
-            const float4 m = xm[TT::chunk_f4(row, c)];
-            float4 o;
-            o.x = m.x > 0.f ? __uint_as_float(v[q * 4 + 0]) : 0.f;
-            o.y = m.y > 0.f ? __uint_as_float(v[q * 4 + 1]) : 0.f;
-            o.z = m.z > 0.f ? __uint_as_float(v[q * 4 + 2]) : 0.f;
-            o.w = m.w > 0.f ? __uint_as_float(v[q * 4 + 3]) : 0.f;
-            if (odd) {
-              o.x += __uint_as_float(gp[q * 4 + 0]); o.y += __uint_as_float(gp[q * 4 + 1]);
-              o.z += __uint_as_float(gp[q * 4 + 2]); o.w += __uint_as_float(gp[q * 4 + 3]);
-              gp[q * 4 + 0] = __float_as_uint(o.x); gp[q * 4 + 1] = __float_as_uint(o.y);
-              gp[q * 4 + 2] = __float_as_uint(o.z); gp[q * 4 + 3] = __float_as_uint(o.w);
-            }
-            if (!last) {
-              a_tile[c * 128 + row] = tf32_rn4(o);
-              if (gy_out) gy_out[TT::chunk_f4(row, c)] = o;
-            } else if (valid) {
-              *reinterpret_cast<float4*>(p.g0 + r * W + c * 4) = o;
-            }
+            const float4 m = xm[TT::chunk_f4(row, c32 * 8 + q)];
+            bits |= (m.x > 0.f ? 1u : 0u) << (q * 4 + 0);
+            bits |= (m.y > 0.f ? 1u : 0u) << (q * 4 + 1);
+            bits |= (m.z > 0.f ? 1u : 0u) << (q * 4 + 2);
+            bits |= (m.w > 0.f ? 1u : 0u) << (q * 4 + 3);
           }
-          if (odd && !last) tmem_st32(tmem_base + lane_off + col_g + c32 * 32, gp);
+          mbits[c32] = bits;
+        }
+        mbar_wait(&d_ready[t], ph_d, abort_flag, p.status, 500 + s);
+        ph_d ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int cb = 0; cb < W / 64; ++cb) {
+          // two 32-column chunks of D (and of g on W1 layers) in flight per wait
+          uint32_t v[2][32], gp[2][32];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            tmem_ld32(tmem_base + lane_off + col_d + (cb * 2 + j) * 32, v[j]);
+            if (odd) tmem_ld32(tmem_base + lane_off + col_g + (cb * 2 + j) * 32, gp[j]);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int c32 = cb * 2 + j;
+            const uint32_t bits = mbits[c32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int c = c32 * 8 + q;
+              float4 o;
+              o.x = (bits >> (q * 4 + 0)) & 1u ? __uint_as_float(v[j][q * 4 + 0]) : 0.f;
+              o.y = (bits >> (q * 4 + 1)) & 1u ? __uint_as_float(v[j][q * 4 + 1]) : 0.f;
+              o.z = (bits >> (q * 4 + 2)) & 1u ? __uint_as_float(v[j][q * 4 + 2]) : 0.f;
+              o.w = (bits >> (q * 4 + 3)) & 1u ? __uint_as_float(v[j][q * 4 + 3]) : 0.f;
+              if (odd) {
+                o.x += __uint_as_float(gp[j][q * 4 + 0]); o.y += __uint_as_float(gp[j][q * 4 + 1]);
+                o.z += __uint_as_float(gp[j][q * 4 + 2]); o.w += __uint_as_float(gp[j][q * 4 + 3]);
+                gp[j][q * 4 + 0] = __float_as_uint(o.x); gp[j][q * 4 + 1] = __float_as_uint(o.y);
+                gp[j][q * 4 + 2] = __float_as_uint(o.z); gp[j][q * 4 + 3] = __float_as_uint(o.w);
+              }
+              if (!last) {
+                a_tile[c * 128 + row] = tf32_rn4(o);
+                if (gy_out) gy_out[TT::chunk_f4(row, c)] = o;
+              } else if (valid) {
+                *reinterpret_cast<float4*>(p.g0 + r * W + c * 4) = o;
+              }
+            }
+            if (odd && !last) tmem_st32(tmem_base + lane_off + col_g + c32 * 32, gp[j]);
+          }
         }
         if (odd && !last) tmem_st_wait();
         tc_fence_before();
@@ -240,18 +264,17 @@ __global__ void __launch_bounds__((4 * NT_ + 2) * 32, 1) mlp_bwd_umma_kernel(Bwd
             ph_a[t] ^= 1;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(t * 2 * W + W);
-            const uint32_t a_addr = smem_u32(a_base + t * S::kABytes);
+            const uint64_t a_desc0 = smem_desc(smem_u32(a_base + t * S::kABytes), a_lbo, sbo);
+            constexpr uint32_t a_step16 = (2 * 128 * 16) >> 4, b_step16 = (2 * W * 16) >> 4;
+#pragma unroll
             for (int sl = 0; sl < S::kSlicesPerLayer; ++sl) {
               const uint32_t qq = q + sl;
               const int slot = qq % kSlots;
-              mbar_wait(&w_full[slot], (qq / kSlots) & 1, abort_flag, p.status, 800 + s);
-              const uint32_t b_addr = smem_u32(ring + slot * kSliceBytes);
-              for (int ks = 0; ks < S::kStepsPerSlice; ++ks) {
-                const int kk = sl * S::kStepsPerSlice + ks;
-                const uint64_t ad = smem_desc(a_addr + (uint32_t)kk * 2 * a_lbo, a_lbo, sbo);
-                const uint64_t bd = smem_desc(b_addr + (uint32_t)ks * 2 * b_lbo, b_lbo, sbo);
-                mma_tf32_ss(d_tmem, ad, bd, idesc, (uint32_t)(kk > 0));
-              }
+              if (t == 0) mbar_wait(&w_full[slot], (qq / kSlots) & 1, abort_flag, p.status, 800 + s);
+              const uint64_t b_desc0 = smem_desc(smem_u32(ring + slot * kSliceBytes), b_lbo, sbo);
+              mma_tf32_ss_steps<S::kStepsPerSlice>(
+                  d_tmem, a_desc0 + (uint64_t)(sl * S::kStepsPerSlice * a_step16), b_desc0,
+                  a_step16, b_step16, idesc, sl == 0 ? 0u : 1u);
               if (t == NT - 1) mma_commit(&w_empty[slot]);
             }
             mma_commit(&d_ready[t]);

@@ -258,35 +258,36 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_ts_kernel(FwdTsParams p) 
             tc_fence_after();
             const bool mstamp = p.dbg && blockIdx.x == 0 && g == (int)blockIdx.x && i < 64;
             if (mstamp) p.dbg[(i * kNT + t) * 5 + 3] = clock64();
-            long long wwait = 0;
             const uint32_t col_p = tmem_base + (uint32_t)(t * 2 * W);
             const uint32_t col_q = col_p + W;
             // even steps write P (reading Q), odd steps write Q (reading P)
             const uint32_t d_tmem = (i & 1) ? col_q : col_p;
             const uint32_t a_tmem = (i & 1) ? col_p : col_q;
             const uint32_t act_addr = smem_u32(act_base + t * kActBytes);
-            for (int s = 0; s < nsl; ++s) {
-              const uint32_t qq = q + s;
-              const int slot = qq % p.slots;
-              const long long tw0 = mstamp ? clock64() : 0;
-              mbar_wait(&w_full[slot], (qq / p.slots) & 1, abort_flag, p.status, 400 + i);
-              if (mstamp) wwait += clock64() - tw0;
-              const uint32_t b_addr = smem_u32(ring + (size_t)slot * kSliceBytes);
-              const int kps = (i == 0) ? p.KP / 8 : kStepsPerSlice;
-              for (int ks = 0; ks < kps; ++ks) {
-                const int kk = s * kStepsPerSlice + ks;
-                const uint64_t bd = smem_desc(b_addr + (uint32_t)ks * 2 * b_lbo, b_lbo, sbo);
-                if (i == 0) {
-                  const uint64_t ad = smem_desc(act_addr + (uint32_t)kk * 2 * a_lbo, a_lbo, sbo);
-                  mma_tf32_ss(d_tmem, ad, bd, idesc, (uint32_t)(kk > 0));
-                } else {
-                  mma_tf32_ts(d_tmem, a_tmem + (uint32_t)kk * 8, bd, idesc, (uint32_t)(kk > 0));
-                }
-              }
+            constexpr uint32_t b_step16 = (2 * W * 16) >> 4;
+            if (i == 0) {
+              const uint32_t slot = q % p.slots;
+              if (t == 0) mbar_wait(&w_full[slot], (q / p.slots) & 1, abort_flag, p.status, 400);
+              const uint64_t b_desc0 = smem_desc(smem_u32(ring + (size_t)slot * kSliceBytes), b_lbo, sbo);
+              const uint64_t a_desc0 = smem_desc(act_addr, a_lbo, sbo);
+              for (int ks = 0; ks < p.KP / 8; ++ks)
+                mma_tf32_ss(d_tmem, a_desc0 + (uint64_t)(ks * ((2 * 128 * 16) >> 4)),
+                            b_desc0 + (uint64_t)(ks * b_step16), idesc, (uint32_t)(ks > 0));
               if (t == nt - 1) mma_commit(&w_empty[slot]);
+            } else {
+#pragma unroll
+              for (int s = 0; s < kSlicesPerLayer; ++s) {
+                const uint32_t qq = q + s;
+                const uint32_t slot = qq % p.slots;
+                if (t == 0) mbar_wait(&w_full[slot], (qq / p.slots) & 1, abort_flag, p.status, 400 + i);
+                const uint64_t b_desc0 = smem_desc(smem_u32(ring + (size_t)slot * kSliceBytes), b_lbo, sbo);
+                mma_tf32_ts_steps<kStepsPerSlice>(d_tmem, a_tmem + (uint32_t)(s * kStepsPerSlice * 8),
+                                                  b_desc0, b_step16, idesc, s == 0 ? 0u : 1u);
+                if (t == nt - 1) mma_commit(&w_empty[slot]);
+              }
             }
             mma_commit(&d_ready[t]);
-            if (mstamp) { p.dbg[(i * kNT + t) * 5 + 4] = clock64(); p.dbg[640 + i * kNT + t] = wwait; }
+            if (mstamp) { p.dbg[(i * kNT + t) * 5 + 4] = clock64(); p.dbg[640 + i * kNT + t] = 0; }
           }
           q += nsl;
         }
@@ -494,16 +495,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_ts_kernel(BwdTsParams p) 
             // even layer: A = P (g), D = Q ; odd layer: A = Q (u), D = P
             const uint32_t a_tmem = (i & 1) ? col_q : col_p;
             const uint32_t d_tmem = (i & 1) ? col_p : col_q;
+            constexpr uint32_t b_step16 = (2 * W * 16) >> 4;
+#pragma unroll
             for (int sl = 0; sl < kSlicesPerLayer; ++sl) {
               const uint32_t qq = q + sl;
-              const int slot = qq % p.slots;
-              mbar_wait(&w_full[slot], (qq / p.slots) & 1, abort_flag, p.status, 800 + s);
-              const uint32_t b_addr = smem_u32(ring + (size_t)slot * kSliceBytes);
-              for (int ks = 0; ks < kStepsPerSlice; ++ks) {
-                const int kk = sl * kStepsPerSlice + ks;
-                const uint64_t bd = smem_desc(b_addr + (uint32_t)ks * 2 * b_lbo, b_lbo, sbo);
-                mma_tf32_ts(d_tmem, a_tmem + (uint32_t)kk * 8, bd, idesc, (uint32_t)(kk > 0));
-              }
+              const uint32_t slot = qq % p.slots;
+              if (t == 0) mbar_wait(&w_full[slot], (qq / p.slots) & 1, abort_flag, p.status, 800 + s);
+              const uint64_t b_desc0 = smem_desc(smem_u32(ring + (size_t)slot * kSliceBytes), b_lbo, sbo);
+              mma_tf32_ts_steps<kStepsPerSlice>(d_tmem, a_tmem + (uint32_t)(sl * kStepsPerSlice * 8),
+                                                b_desc0, b_step16, idesc, sl == 0 ? 0u : 1u);
               if (t == nt - 1) mma_commit(&w_empty[slot]);
             }
             mma_commit(&d_ready[t]);

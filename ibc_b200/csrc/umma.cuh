@@ -185,6 +185,30 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// KSTEPS back-to-back K=8 steps of one accumulation: descriptors advance by a
+// constant number of 16-byte units per step, so the single issuing thread spends
+// two adds per MMA instead of rebuilding descriptors (the issue loop, not the
+// tensor pipe, was the bottleneck: scripts/mma_rate.py).
+template <int KSTEPS>
+__device__ __forceinline__ void mma_tf32_ss_steps(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                                  uint32_t a_step16, uint32_t b_step16,
+                                                  uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks)
+    mma_tf32_ss(d_tmem, adesc + (uint64_t)(ks * a_step16), bdesc + (uint64_t)(ks * b_step16), idesc,
+                ks == 0 ? acc_first : 1u);
+}
+
+template <int KSTEPS>
+__device__ __forceinline__ void mma_tf32_ts_steps(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc,
+                                                  uint32_t b_step16, uint32_t idesc,
+                                                  uint32_t acc_first) {
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks)
+    mma_tf32_ts(d_tmem, a_tmem + (uint32_t)(ks * 8), bdesc + (uint64_t)(ks * b_step16), idesc,
+                ks == 0 ? acc_first : 1u);
+}
+
 // Arrive on `bar` when all tcgen05 operations issued so far by this thread are
 // complete (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {

@@ -9,11 +9,12 @@ namespace ibc {
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // tcgen05 kind::tf32 reads the top 19 bits of each fp32 operand (truncation);
-// rounding to nearest-even on the way in halves the error and removes the bias.
+// rounding to nearest (ties away from zero, like cvt.rna.tf32.f32) on the way
+// in halves the error and removes the bias.  Done with two integer ALU ops:
+// the F2F conversion instruction runs at a quarter of the ALU rate and was the
+// epilogue's bottleneck (3750 -> cycles per layer, scripts/timeline.py).
 __device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ float4 tf32_rn4(float4 v) {
   return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
@@ -28,6 +29,7 @@ struct PackedLayout {
   int64_t rev_p;     // [W/4][AP][4]           Wp act rows, B operand of dE/dact
   int64_t vecs;      // [(2nb+1)][W] epilogue bias vectors, then we[W], be, pad
   int64_t raw;       // [(2nb+1)][W] per-step raw biases: zeros, b1_0, b2_0, b1_1, ...
+  int64_t fwd_bias;  // [(2nb+1)][2][W][4] bias as one extra K=8 step: (hi, lo, 0, 0 | 0...)
   int64_t total;
 };
 
@@ -43,7 +45,8 @@ inline PackedLayout make_packed_layout(const Layout& L) {
   p.rev_p = p.rev_l + 2 * L.nb * WW;
   p.vecs = p.rev_p + (int64_t)L.W * p.AP;
   p.raw = p.vecs + (int64_t)(2 * L.nb + 2) * L.W + 4;
-  p.total = p.raw + (int64_t)(2 * L.nb + 1) * L.W;
+  p.fwd_bias = p.raw + (int64_t)(2 * L.nb + 1) * L.W;
+  p.total = p.fwd_bias + (int64_t)(2 * L.nb + 1) * 8 * L.W;
   return p;
 }
 
