@@ -267,6 +267,15 @@ def run_b200(args):
   reps = 20
   t_act = timed(lambda i: policy.action(time_step), reps, lambda: None) / reps
 
+  # secondary configs (rank 0 only, short): Langevin chains of C3 / pushing_states-langevin
+  # and one late-fusion PixelEBM train step (C5), reported beside the headline
+  secondary = {}
+  if rank == 0:
+    try:
+      secondary = secondary_configs(device)
+    except Exception as ex:   # noqa: BLE001
+      secondary = {'error': str(ex)[:300]}
+
   result = None
   if rank == 0:
     evals = rows * world * args.steps
@@ -298,6 +307,7 @@ def run_b200(args):
                           'num_action_samples': c['dfo_samples'],
                           'iterations': c['dfo_iterations']},
         'kernel_status': status,
+        'secondary': secondary,
     }
     if fwd.get('tf32'):
       fl = rows * fwd_flops_per_row()
@@ -342,6 +352,42 @@ def run_b200(args):
     dist.barrier()
     dist.destroy_process_group()
   return result
+
+
+def secondary_configs(device):
+  """Langevin sampler throughput (C3: particle 32-D, W=256 D=2, obs 256, act 32, B*N=4096,
+  K=100; pushing_states/mlp_ebm_langevin.gin: W=128 D=16, B*N=4096, K=100) and a PixelEBM
+  train step (C5 shapes, B=32 of 128 frames pairs)."""
+  from ibc_b200 import engine as eng
+  out = {}
+  for name, (o, a, w, d) in (('C3_particle32_langevin', (256, 32, 256, 2)),
+                             ('pushing_states_langevin', (20, 2, 128, 16))):
+    e = eng.EBMEngine(o, a, w, d, device)
+    params = (torch.randn(e.param_count, device=device) * 0.05).contiguous()
+    e.bind_params(params)
+    b, n, k = 512, 8, 100
+    obs = torch.randn(b, o, device=device)
+    mn, mx = torch.full((a,), -1.1, device=device), torch.full((a,), 1.1, device=device)
+    cfg = eng.langevin_cfg(num_iterations=k)
+    acts = torch.rand(b * n, a, device=device) * 2.2 - 1.1
+    e.langevin(obs, acts.clone(), n, mn, mx, cfg, seed=1)
+    t = timed(lambda i: e.langevin(obs, acts.clone(), n, mn, mx, cfg, seed=i), 3, lambda: None) / 3
+    out[name] = {'ms_per_chain': t * 1e3, 'rows': b * n, 'iterations': k,
+                 'energy_grad_evals_per_s': b * n * k / t, 'precision': 'tf32',
+                 'kernel_status': e.kernel_status()}
+  # PixelEBM (fp32 path)
+  pe = eng.PixelEngine(2, 240, 320, 3, 180, 240, 2, 1024, 1, device)
+  pp = (torch.randn(pe.param_count, device=device) * 0.05).contiguous()
+  pe.bind_params(pp)
+  b, n = 32, 256
+  img = torch.randint(0, 256, (b, 2, 240, 320, 3), device=device, dtype=torch.uint8)
+  acts = torch.rand(b * (n + 1), 2, device=device) * 2 - 1
+  cfg = eng.loss_cfg(1.0, False)
+  pe.train_grads(img, acts, n, cfg, b)
+  t = timed(lambda i: pe.train_grads(img, acts, n, cfg, b), 2, lambda: None) / 2
+  out['C5_pixel_ebm_train_grads'] = {'ms_per_step': t * 1e3, 'images': b, 'rows': b * (n + 1),
+                                     'images_per_s': b / t, 'precision': 'fp32 (im2col + FMA GEMM)'}
+  return out
 
 
 def cpu_baseline(steps, warmup, batch=512):

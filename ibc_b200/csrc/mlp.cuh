@@ -55,6 +55,13 @@ bool umma_supported(const Layout& L);
 int umma_pack_params(ibc_handle* h, cudaStream_t s);
 int umma_forward(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
                  float* hp, float* E, float* xa_save, cudaStream_t s);
+int umma_forward_hp(ibc_handle* h, const float* act, int64_t R, int64_t n, const float* hp,
+                    float* E, float* xa_save, cudaStream_t s);
+int langevin_umma(ibc_handle* h, const float* obs, int64_t B, float* actions, int64_t n,
+                  const float* mn, const float* mx, const ibc_langevin_cfg& c,
+                  const float* normals, uint64_t seed, const std::vector<float>& steps,
+                  float* chain_actions, float* chain_energies, float* chain_grad_norms,
+                  cudaStream_t s);
 // width-128 kernels with the activations in tensor memory (mlp_umma_ts.cu)
 int ts_tiles_per_cta(ibc_handle* h, int64_t R);
 int umma_forward_ts(ibc_handle* h, const float* act, int64_t R, int64_t n, const float* hp,

@@ -591,8 +591,12 @@ int launch_fwd(ibc_handle* h, const FwdParams& p, cudaStream_t s) {
   if (smem > 227 * 1024)
     IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "tcgen05 forward: depth %d needs %zu B of shared memory",
              2 * p.nb, smem);
-  IBC_CUDA(h, cudaFuncSetAttribute(mlp_fwd_umma_kernel<W, NT>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t attr_smem = 0;     // per template instance; raised lazily
+  if (smem > attr_smem) {
+    IBC_CUDA(h, cudaFuncSetAttribute(mlp_fwd_umma_kernel<W, NT>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
   const int grid = p.num_groups < h->sm_count ? p.num_groups : h->sm_count;
   mlp_fwd_umma_kernel<W, NT><<<grid, S::kThreads, smem, s>>>(p);
   IBC_LAUNCH_CHECK(h);
@@ -635,14 +639,21 @@ int umma_forward(ibc_handle* h, const float* obs, int64_t B, const float* act, i
                  float* hp, float* E, float* xa_save, cudaStream_t s) {
   const Layout& L = h->L;
   if (h->packed_stale) IBC_TRY(umma_pack_params(h, s));
-  const PackedLayout pl = make_packed_layout(L);
-  const int64_t R = B * n;
   {  // hp = obs . Wp[:O] + bp   (fp32)
     GemmP g;
     g.A = obs; g.lda = L.O; g.B = h->params + L.wp; g.ldb = L.W; g.C = hp; g.ldc = L.W;
     g.bias = h->params + L.bp; g.M = (int)B; g.N = L.W; g.K = L.O;
     IBC_TRY(gemm(h, g, false, false, s));
   }
+  return umma_forward_hp(h, act, B * n, n, hp, E, xa_save, s);
+}
+
+// Fused forward given the hoisted observation projection hp [R / n, W].
+int umma_forward_hp(ibc_handle* h, const float* act, int64_t R, int64_t n, const float* hp,
+                    float* E, float* xa_save, cudaStream_t s) {
+  const Layout& L = h->L;
+  if (h->packed_stale) IBC_TRY(umma_pack_params(h, s));
+  const PackedLayout pl = make_packed_layout(L);
   // Experimental variant with the activations in tensor memory (mlp_umma_ts.cu):
   // correct, but measured slower on B200 (0.44 vs 0.30 ms on 131 584 rows), so
   // it is opt-in for tuning only.

@@ -23,6 +23,7 @@
 #include "mlp.cuh"
 #include "ops.cuh"
 #include "umma.cuh"
+#include "philox.cuh"
 #include "umma_pack.cuh"
 
 namespace ibc {
@@ -30,6 +31,8 @@ namespace ibc {
 using namespace umma;
 
 namespace {
+
+inline const float* act_const(const float* p) { return p; }
 
 constexpr int kSlots = 5;
 constexpr int kSliceBytes = 16384;
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__((4 * NT_ + 2) * 32, 1) mlp_bwd_umma_kernel(Bwd
       const int64_t tile_id = (int64_t)g * NT + t;
       const int64_t r = tile_id * 128 + row;
       const bool valid = r < p.R;
-      const float de = valid ? p.dE[r] : 0.f;
+      const float de = valid ? (p.dE ? p.dE[r] : 1.0f) : 0.f;
       {
         // g_top = dE (x) we   (gradient of the residual stream entering Dense(1));
         // dwe += h_nb^T dE with h_nb from the forward's last slot
@@ -464,8 +467,12 @@ __global__ void __launch_bounds__(WgradSmem::kThreads, 1) mlp_wgrad_umma_kernel(
 template <int W_, int NT_>
 static int launch_bwd(ibc_handle* h, const BwdParams& bp, cudaStream_t s) {
   using S = BwdSmem<W_, NT_>;
-  IBC_CUDA(h, cudaFuncSetAttribute(mlp_bwd_umma_kernel<W_, NT_>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
+  static bool attr_set = false;    // per template instance
+  if (!attr_set) {
+    IBC_CUDA(h, cudaFuncSetAttribute(mlp_bwd_umma_kernel<W_, NT_>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
+    attr_set = true;
+  }
   const int grid = bp.num_groups < h->sm_count ? bp.num_groups : h->sm_count;
   mlp_bwd_umma_kernel<W_, NT_><<<grid, S::kThreads, S::kBytes, s>>>(bp);
   IBC_LAUNCH_CHECK(h);
@@ -524,6 +531,108 @@ int mlp_energy_dact_umma(ibc_handle* h, const float* obs, int64_t B, const float
   g.A = g0; g.lda = L.W; g.B = h->params + L.wp + (int64_t)L.O * L.W; g.ldb = L.W;
   g.C = dEda; g.ldc = L.A; g.M = (int)R; g.N = L.A; g.K = L.W;
   return gemm(h, g, false, true, s);
+}
+
+// One warp per row: dE/dact = g0[r, :] . Wp[O:]^T (lane a owns action dimension a),
+// then the mcmc.langevin_step update (mcmc.py:238-262) -- replaces a GEMM launch
+// and the update launch of every chain iteration.
+__global__ void __launch_bounds__(256)
+langevin_dact_update_kernel(const float* __restrict__ g0, const float* __restrict__ wpa, int W,
+                            float* __restrict__ actions, int64_t R, int A,
+                            const float* __restrict__ normals, uint64_t seed, uint64_t rng_stream,
+                            float noise_scale, float grad_clip, float dclip_scale, float stepsize,
+                            const float* __restrict__ mn, const float* __restrict__ mx,
+                            int norm_type, float* __restrict__ grad_norms,
+                            float* __restrict__ chain_actions) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int a = threadIdx.x & 31;
+  if (r >= R) return;
+  float d = 0.f;
+  if (a < A) {
+    const float4* g4 = reinterpret_cast<const float4*>(g0 + r * W);
+    const float4* w4 = reinterpret_cast<const float4*>(wpa + (int64_t)a * W);
+    for (int k = 0; k < W / 4; ++k) {
+      const float4 g = g4[k], w = w4[k];
+      d = fmaf(g.x, w.x, d); d = fmaf(g.y, w.y, d); d = fmaf(g.z, w.z, d); d = fmaf(g.w, w.w, d);
+    }
+  }
+  float g = -d;                                   // de_dact = -dE/dact (mcmc.py:190)
+  float nrm = (a < A) ? fabsf(g) : 0.f;
+  if (norm_type == IBC_NORM_L2) nrm = nrm * nrm;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float t = __shfl_xor_sync(0xffffffffu, nrm, o);
+    nrm = (norm_type == IBC_NORM_INF) ? fmaxf(nrm, t) : nrm + t;
+  }
+  if (norm_type == IBC_NORM_L2) nrm = sqrtf(nrm);
+  if (norm_type == IBC_NORM_NONE) nrm = 0.f;
+  if (a == 0 && grad_norms) grad_norms[r] = nrm;
+  if (a < A) {
+    const int64_t i = r * A + a;
+    if (grad_clip > 0.f) g = fminf(fmaxf(g, -grad_clip), grad_clip);
+    const float z = normals ? normals[i] : philox_normal(seed, rng_stream, (uint64_t)i);
+    g = __fadd_rn(__fmul_rn(0.5f, g), __fmul_rn(z, noise_scale));
+    float dl = __fmul_rn(stepsize, g);
+    const float dc = __fmul_rn(dclip_scale, __fadd_rn(mx[a], -mn[a]));
+    dl = fminf(fmaxf(dl, -dc), dc);
+    float v = __fadd_rn(actions[i], -dl);
+    v = fminf(fmaxf(v, mn[a]), mx[a]);
+    actions[i] = v;
+    if (chain_actions) chain_actions[i] = v;
+  }
+}
+
+// mcmc.langevin_actions_given_obs on tensor cores: per iteration one fused forward
+// (operands saved per tile), one fused reverse chain and one dE/dact + update kernel;
+// the observation projection is hoisted out of the chain.
+int langevin_umma(ibc_handle* h, const float* obs, int64_t B, float* actions, int64_t n,
+                  const float* mn, const float* mx, const ibc_langevin_cfg& c,
+                  const float* normals, uint64_t seed, const std::vector<float>& steps,
+                  float* chain_actions, float* chain_energies, float* chain_grad_norms,
+                  cudaStream_t s) {
+  const Layout& L = h->L;
+  const int64_t R = B * n;
+  const int A = L.A;
+  const int nt = (L.W == 128) ? 2 : 1;
+  const int64_t tiles = ((R + 128 * nt - 1) / (128 * nt)) * nt;
+  const size_t xa_floats = (size_t)tiles * (2 * L.nb + 1) * 128 * L.W;
+  const size_t bytes = Workspace::rounded(xa_floats * 4) + Workspace::rounded((size_t)R * L.W * 4) +
+                       Workspace::rounded((size_t)B * L.W * 4) + 3 * Workspace::rounded((size_t)R * 4);
+  IBC_CUDA(h, h->ws.reserve(bytes));
+  h->ws.reset();
+  float* xa = h->ws.take<float>(xa_floats);
+  float* g0 = h->ws.take<float>((size_t)R * L.W);
+  float* hp = h->ws.take<float>((size_t)B * L.W);
+  float* E = h->ws.take<float>(R);
+  float* dE = h->ws.take<float>(R);
+  float* nrm = h->ws.take<float>(R);
+  if (h->packed_stale) IBC_TRY(umma_pack_params(h, s));
+  {  // hp = obs . Wp[:O] + bp, once per chain
+    GemmP g;
+    g.A = obs; g.lda = L.O; g.B = h->params + L.wp; g.ldb = L.W; g.C = hp; g.ldc = L.W;
+    g.bias = h->params + L.bp; g.M = (int)B; g.N = L.W; g.K = L.O;
+    IBC_TRY(gemm(h, g, false, false, s));
+  }
+  const float dclip_scale = (float)((double)c.delta_action_clip * 0.5);
+  const float* wpa = h->params + L.wp + (int64_t)L.O * L.W;
+  for (int k = 0; k < c.num_iterations; ++k) {
+    float* Ek = chain_energies ? chain_energies + (int64_t)k * R : E;
+    float* Nk = chain_grad_norms ? chain_grad_norms + (int64_t)k * R : nrm;
+    IBC_TRY(umma_forward_hp(h, act_const(actions), R, n, hp, Ek, xa, s));
+    const float* de = nullptr;
+    if (c.apply_exp) {
+      fill_or_exp_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(Ek, dE, R, 1);
+      IBC_LAUNCH_CHECK(h);
+      de = dE;
+    }
+    IBC_TRY(umma_reverse(h, de, R, xa, nullptr, g0, nullptr, s));
+    langevin_dact_update_kernel<<<(unsigned)((R + 7) / 8), 256, 0, s>>>(
+        g0, wpa, L.W, actions, R, A, normals ? normals + (int64_t)k * R * A : nullptr, seed,
+        (uint64_t)k + 1, c.noise_scale, c.grad_clip, dclip_scale, steps[k], mn, mx,
+        c.grad_norm_type, Nk, chain_actions ? chain_actions + (int64_t)k * R * A : nullptr);
+    IBC_LAUNCH_CHECK(h);
+  }
+  return IBC_OK;
 }
 
 bool umma_train_supported(const Layout& L) {

@@ -408,6 +408,9 @@ int langevin(ibc_handle* h, const float* obs, int64_t B, float* actions, int64_t
     IBC_FAIL(h, IBC_ERR_INVALID, "langevin: unknown grad_norm_type %d", c.grad_norm_type);
   std::vector<float> steps;
   langevin_stepsizes(c, &steps);
+  if (h->precision == IBC_PRECISION_TF32 && umma_supported(h->L))
+    return langevin_umma(h, obs, B, actions, n, mn, mx, c, normals, seed, steps, chain_actions,
+                         chain_energies, chain_grad_norms, s);
   const size_t bytes = 2 * Workspace::rounded((size_t)R * 4) + Workspace::rounded((size_t)R * A * 4);
   IBC_CUDA(h, h->ws_outer.reserve(bytes));
   h->ws_outer.reset();
