@@ -342,24 +342,35 @@ struct WgradParams {
 };
 
 struct WgradSmem {
-  static constexpr int kStages = 3;
-  static constexpr int kSubBytes = 32768;                     // one operand sub-tile
+  static constexpr int kRawStages = 3;                        // bulk-copied sub-tiles (chunk layout)
+  static constexpr int kMmaStages = 2;                        // re-arranged MN-major operand images
+  static constexpr int kSubBytes = TrainTile<kW>::kSubFloats * 4;   // one operand sub-tile (16 KB)
   static constexpr int kThreads = 6 * 32;
-  static constexpr size_t kBytes = (size_t)kStages * 2 * kSubBytes + 256;
+  static constexpr size_t kBytes =
+      (size_t)(kRawStages + kMmaStages) * 2 * kSubBytes + 256;
 };
 
+// grid = (2nb layers, row splits).  Warp 4: bulk copies of the saved XA / GY
+// sub-tiles; warps 0-3: re-arrange each sub-tile into the MN-major UMMA atoms
+// (conflict-free 16-byte moves) and take the fp32 column sums of GY (bias
+// gradient) on the way; warp 5: tcgen05.mma, accumulating dW in tensor memory
+// across all rows of the CTA; warps 0-3 flush at the end.
 __global__ void __launch_bounds__(WgradSmem::kThreads, 1) mlp_wgrad_umma_kernel(WgradParams p) {
   using S = WgradSmem;
   using TT = TrainTile<kW>;
   constexpr int W = kW;
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* stage_base = smem;                            // [stage][xa | gy]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S::kStages * 2 * S::kSubBytes);
-  uint64_t* full = bars;                 // [kStages]
-  uint64_t* empty = bars + S::kStages;   // [kStages]
-  uint64_t* done = bars + 2 * S::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 1);
+  unsigned char* raw_base = smem;                                           // [raw stage][xa | gy]
+  unsigned char* mma_base = smem + (size_t)S::kRawStages * 2 * S::kSubBytes; // [mma stage][xa | gy]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mma_base + (size_t)S::kMmaStages * 2 * S::kSubBytes);
+  uint64_t* raw_full = bars;                          // [kRawStages]
+  uint64_t* raw_empty = raw_full + S::kRawStages;     // [kRawStages]
+  uint64_t* mma_full = raw_empty + S::kRawStages;     // [kMmaStages]
+  uint64_t* mma_empty = mma_full + S::kMmaStages;     // [kMmaStages]
+  uint64_t* done = mma_empty + S::kMmaStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
   __shared__ int s_abort;
+  __shared__ float s_bias[kW];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int layer = blockIdx.x + 1;                            // forward layer index 1 .. 2nb
@@ -371,12 +382,12 @@ __global__ void __launch_bounds__(WgradSmem::kThreads, 1) mlp_wgrad_umma_kernel(
 
   if (tid == 0) {
     s_abort = 0;
-    // a stage is free again when its MMAs retired (1 commit) and the four
-    // column-sum warps have read it (4 arrivals)
-    for (int s = 0; s < S::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 5); }
+    for (int s = 0; s < S::kRawStages; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
+    for (int s = 0; s < S::kMmaStages; ++s) { mbar_init(&mma_full[s], 4); mbar_init(&mma_empty[s], 1); }
     mbar_init(done, 1);
     fence_mbar_init();
   }
+  if (tid < kW) s_bias[tid] = 0.f;
   if (warp == 0) tmem_alloc(tmem_slot, 128);
   tc_fence_before();
   __syncthreads();
@@ -388,19 +399,19 @@ __global__ void __launch_bounds__(WgradSmem::kThreads, 1) mlp_wgrad_umma_kernel(
   if (warp == 4) {
     if (lane == 0) {
       for (int u = 0; u < nsub; ++u) {
-        const int stage = u % S::kStages;
-        const uint32_t ph = (u / S::kStages) & 1;
+        const int stage = u % S::kRawStages;
+        const uint32_t ph = (u / S::kRawStages) & 1;
         const int64_t tile = t0 + u / TT::kSubTiles;
         const int sub = u % TT::kSubTiles;
-        mbar_wait(&empty[stage], ph ^ 1, abort_flag, p.status, 900);
-        mbar_arrive_expect_tx(&full[stage], 2u * S::kSubBytes);
-        unsigned char* dst = stage_base + (size_t)stage * 2 * S::kSubBytes;
+        mbar_wait(&raw_empty[stage], ph ^ 1, abort_flag, p.status, 900);
+        mbar_arrive_expect_tx(&raw_full[stage], 2u * S::kSubBytes);
+        unsigned char* dst = raw_base + (size_t)stage * 2 * S::kSubBytes;
         bulk_g2s(dst, p.xa_save + TT::slot_base(tile, xa_slots, layer - 1) +
-                          (int64_t)sub * (S::kSubBytes / 4),
-                 S::kSubBytes, &full[stage]);
+                          (int64_t)sub * TT::kSubFloats,
+                 S::kSubBytes, &raw_full[stage]);
         bulk_g2s(dst + S::kSubBytes, p.gy_save + TT::slot_base(tile, gy_slots, layer - 1) +
-                                         (int64_t)sub * (S::kSubBytes / 4),
-                 S::kSubBytes, &full[stage]);
+                                         (int64_t)sub * TT::kSubFloats,
+                 S::kSubBytes, &raw_full[stage]);
       }
     }
     __syncwarp();
@@ -410,35 +421,67 @@ __global__ void __launch_bounds__(WgradSmem::kThreads, 1) mlp_wgrad_umma_kernel(
       // one K step = 8 rows = two 512-byte K atoms
       const uint32_t idesc = idesc_tf32(128, W) | kIdescAMajorMN | kIdescBMajorMN;
       for (int u = 0; u < nsub; ++u) {
-        const int stage = u % S::kStages;
-        mbar_wait(&full[stage], (u / S::kStages) & 1, abort_flag, p.status, 901);
-        const uint32_t xa_addr = smem_u32(stage_base + (size_t)stage * 2 * S::kSubBytes);
+        const int stage = u % S::kMmaStages;
+        mbar_wait(&mma_full[stage], (u / S::kMmaStages) & 1, abort_flag, p.status, 901);
+        const uint32_t xa_addr = smem_u32(mma_base + (size_t)stage * 2 * S::kSubBytes);
         const uint32_t gy_addr = xa_addr + S::kSubBytes;
-        for (int ks = 0; ks < TT::kSubRows / 8; ++ks) {
-          const uint64_t ad = smem_desc_lt(xa_addr + (uint32_t)ks * 1024, TT::kLbo, TT::kSbo, 1);
-          const uint64_t bd = smem_desc_lt(gy_addr + (uint32_t)ks * 1024, TT::kLbo, TT::kSbo, 1);
-          mma_tf32_ss(tmem_base, ad, bd, idesc, (uint32_t)(u > 0 || ks > 0));   // dW += XA^T GY
-        }
-        mma_commit(&empty[stage]);
+        const uint64_t ad0 = smem_desc_lt(xa_addr, TT::kLbo, TT::kSbo, 1);
+        const uint64_t bd0 = smem_desc_lt(gy_addr, TT::kLbo, TT::kSbo, 1);
+#pragma unroll
+        for (int ks = 0; ks < TT::kSubRows / 8; ++ks)
+          mma_tf32_ss(tmem_base, ad0 + (uint64_t)(ks * (1024 >> 4)), bd0 + (uint64_t)(ks * (1024 >> 4)),
+                      idesc, (uint32_t)(u > 0 || ks > 0));   // dW += XA^T GY
+        mma_commit(&mma_empty[stage]);
       }
       mma_commit(done);
     }
     __syncwarp();
   } else if (nsub > 0) {
-    // warps 0-3: bias gradient = fp32 column sums of the (unrounded) output
-    // gradients while they sit in shared memory, then the dW flush
-    const int col = tid;                                         // output feature n
-    float bsum = 0.f;
+    // ---- warps 0-3: chunk layout -> MN-major atoms, bias sums, final flush ----
+    // lane = p * 8 + r8: a quarter-warp reads 8 consecutive rows of one chunk (128
+    // contiguous bytes) and writes two K atoms' lines (2-way conflicts at worst)
+    const int pq = lane >> 3, r8 = lane & 7;
+    const int rr = warp * 8 + r8;                              // row inside the sub-tile
+    float4 bacc[W / 16];
+#pragma unroll
+    for (int i = 0; i < W / 16; ++i) bacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int u = 0; u < nsub; ++u) {
-      const int stage = u % S::kStages;
-      mbar_wait(&full[stage], (u / S::kStages) & 1, abort_flag, p.status, 903);
-      const unsigned char* gy = stage_base + (size_t)stage * 2 * S::kSubBytes + S::kSubBytes;
-#pragma unroll 8
-      for (int k = 0; k < TT::kSubRows; ++k)
-        bsum += *reinterpret_cast<const float*>(gy + mn32_offset(col, k, TT::kLbo, TT::kSbo));
+      const int rs = u % S::kRawStages, ms = u % S::kMmaStages;
+      mbar_wait(&raw_full[rs], (u / S::kRawStages) & 1, abort_flag, p.status, 903);
+      mbar_wait(&mma_empty[ms], ((u / S::kMmaStages) & 1) ^ 1, abort_flag, p.status, 904);
+      const float4* raw_xa = reinterpret_cast<const float4*>(raw_base + (size_t)rs * 2 * S::kSubBytes);
+      const float4* raw_gy = raw_xa + S::kSubBytes / 16;
+      float4* mma_xa = reinterpret_cast<float4*>(mma_base + (size_t)ms * 2 * S::kSubBytes);
+      float4* mma_gy = mma_xa + S::kSubBytes / 16;
+#pragma unroll
+      for (int cg = 0; cg < W / 16; ++cg) {
+        const int c = cg * 4 + pq;
+        const float4 x = raw_xa[c * TT::kSubRows + rr];
+        const float4 g = raw_gy[c * TT::kSubRows + rr];
+        mma_xa[TT::mn_f4(rr, c)] = x;
+        mma_gy[TT::mn_f4(rr, c)] = g;
+        bacc[cg].x += g.x; bacc[cg].y += g.y; bacc[cg].z += g.z; bacc[cg].w += g.w;
+      }
+      fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (lane == 0) { mbar_arrive(&mma_full[ms]); mbar_arrive(&raw_empty[rs]); }
     }
+    // bias gradient: reduce over the 8 rows of the quarter-warp, then over warps
+#pragma unroll
+    for (int cg = 0; cg < W / 16; ++cg) {
+      float4 v = bacc[cg];
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+        v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+      }
+      if (r8 == 0) {
+        const int f = (cg * 4 + pq) * 4;
+        atomicAdd(&s_bias[f + 0], v.x); atomicAdd(&s_bias[f + 1], v.y);
+        atomicAdd(&s_bias[f + 2], v.z); atomicAdd(&s_bias[f + 3], v.w);
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");            // warps 0-3 only
     mbar_wait(done, 0, abort_flag, p.status, 902);
     tc_fence_after();
     const int row = tid;                                         // input feature k
@@ -447,7 +490,7 @@ __global__ void __launch_bounds__(WgradSmem::kThreads, 1) mlp_wgrad_umma_kernel(
     const bool is_w2 = (layer & 1) == 0;
     float* dw = p.grads + (is_w2 ? p.L.w2(j) : p.L.w1(j)) + (int64_t)row * W;
     float* db = p.grads + (is_w2 ? p.L.b2(j) : p.L.b1(j));
-    atomicAdd(db + col, bsum);
+    atomicAdd(db + tid, s_bias[tid]);
 #pragma unroll 1
     for (int c32 = 0; c32 < W / 32; ++c32) {
       uint32_t v[32];

@@ -64,27 +64,33 @@ __host__ __device__ inline uint32_t mn32_offset(int mn, int k, uint32_t lbo, uin
          (uint32_t)((oct ^ kr) << 5) + (uint32_t)(mn & 7) * 4u;
 }
 
-// Saved operand tiles of the training path: [tile][slot][sub-tile] where a
-// sub-tile is kSubRows rows x W features stored as the MN-major operand above
-// with MN = features and K = rows ([W/32 MN atoms][kSubRows/4 K atoms][512 B]),
-// so one sub-tile (32 KB) is a single contiguous bulk copy and is directly the
-// A (forward operand) or B (output gradient) operand of dW = XA^T . GY.
+// Saved operand tiles of the training path: [tile][slot][sub-tile (4)][chunk
+// (W/4)][32 rows][4 floats].  A warp of the epilogue (32 consecutive rows = one
+// sub-tile) writing one 16-byte chunk per thread covers 512 contiguous bytes, so
+// saves and reloads are fully coalesced (the earlier MN-major-in-global layout
+// cost one 128-byte line per THREAD per store and was L2-request bound); one
+// sub-tile (32 x W floats) is a single contiguous bulk copy.  The weight-gradient
+// kernel re-arranges a sub-tile into the MN-major UMMA atoms in shared memory.
 template <int W>
 struct TrainTile {
-  static constexpr int kSubRows = 8192 / W;
+  static constexpr int kSubRows = 32;
   static constexpr int kSubTiles = 128 / kSubRows;
+  static constexpr int kSubFloats = kSubRows * W;
   static constexpr int kTileFloats = 128 * W;
-  static constexpr uint32_t kSbo = 512;                        // between 4-row K atoms
-  static constexpr uint32_t kLbo = (kSubRows / 4) * 512;       // between 32-feature MN atoms
+  // MN-major operand image of one sub-tile: [W/32 MN atoms][8 K atoms][512 B]
+  static constexpr uint32_t kSbo = 512;
+  static constexpr uint32_t kLbo = (kSubRows / 4) * 512;
   __host__ __device__ static int64_t slot_base(int64_t tile, int slots, int slot) {
     return (tile * slots + slot) * (int64_t)kTileFloats;
   }
   // float4 index inside a slot of chunk c (features 4c .. 4c+3) of row `row`
   __host__ __device__ static int chunk_f4(int row, int c) {
-    const int sub = row / kSubRows, rs = row % kSubRows;
-    const int ka = rs >> 2, kr = rs & 3, ma = c >> 3, oct = (c >> 1) & 3, half = c & 1;
-    return sub * (kSubRows * W / 4) + (ma * (kSubRows / 4) + ka) * 32 + kr * 8 +
-           ((oct ^ kr) << 1) + half;
+    return (row >> 5) * (kSubFloats / 4) + c * kSubRows + (row & 31);
+  }
+  // float4 index of the same piece inside the MN-major image of its sub-tile
+  __host__ __device__ static int mn_f4(int rr, int c) {
+    const int ka = rr >> 2, kr = rr & 3, ma = c >> 3, oct = (c >> 1) & 3, half = c & 1;
+    return (ma * (kSubRows / 4) + ka) * 32 + kr * 8 + ((oct ^ kr) << 1) + half;
   }
 };
 

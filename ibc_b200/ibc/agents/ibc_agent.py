@@ -296,10 +296,32 @@ class ImplicitBCAgent(BehavioralCloningAgent):
     return counter, combined, chain_data
 
   # -- train (base_agent.py:36-62) ------------------------------------------------------
+  # check_numerics (base_agent.py:46) is an in-graph op upstream: it does not stall
+  # the Python thread.  'deferred' keeps that property (the loss of step k is
+  # checked, without a device sync of its own, when step k+1 is submitted or when
+  # the caller reads it); 'sync' raises inside the offending step.
+  check_numerics = 'deferred'
+
+  def _check_finite(self, loss):
+    if self.check_numerics == 'sync':
+      if not bool(torch.isfinite(loss)):
+        raise FloatingPointError('Loss is inf or nan')
+      return
+    prev = getattr(self, '_pending_finite', None)
+    if prev is not None:
+      flag, ev = prev
+      if ev.query() and not bool(flag):
+        raise FloatingPointError('Loss is inf or nan')
+      if not ev.query():
+        return                        # still in flight: keep waiting on the older one
+    flag = torch.isfinite(loss)
+    ev = torch.cuda.Event()
+    ev.record()
+    self._pending_finite = (flag, ev)
+
   def _train(self, experience, weights=None, draws=None):
     loss_info, grads = self._loss(experience, weights=weights, training=True, draws=draws)
-    if not bool(torch.isfinite(loss_info.loss)):                # check_numerics (:46)
-      raise FloatingPointError('Loss is inf or nan')
+    self._check_finite(loss_info.loss)
     parallel.allreduce_gradients(grads)                         # MirroredStrategy all-reduce
     self._optimizer.apply_gradients(self.cloning_network, grads)
     self.train_step_counter += 1
