@@ -53,27 +53,28 @@ int mlp_energy_dact(ibc_handle* h, const float* obs, int64_t B, const float* act
 // tcgen05 path (mlp_umma.cu) ---------------------------------------------
 bool umma_supported(const Layout& L);
 int umma_pack_params(ibc_handle* h, cudaStream_t s);
+// Saved state for the reverse chain (both nullable): xa_save = the A operands of
+// every layer (umma_save_floats() floats; the weight-gradient kernel's input),
+// mask_save = their ReLU masks as bits (umma_mask_words() words; all the
+// reverse chain itself reads).
+size_t umma_save_floats(const Layout& L, int64_t R);
+size_t umma_mask_words(const Layout& L, int64_t R);
 int umma_forward(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
-                 float* hp, float* E, float* xa_save, cudaStream_t s);
+                 float* hp, float* E, float* xa_save, uint32_t* mask_save, cudaStream_t s);
 int umma_forward_hp(ibc_handle* h, const float* act, int64_t R, int64_t n, const float* hp,
-                    float* E, float* xa_save, cudaStream_t s);
+                    float* E, float* xa_save, uint32_t* mask_save, cudaStream_t s);
 int langevin_umma(ibc_handle* h, const float* obs, int64_t B, float* actions, int64_t n,
                   const float* mn, const float* mx, const ibc_langevin_cfg& c,
                   const float* normals, uint64_t seed, const std::vector<float>& steps,
                   float* chain_actions, float* chain_energies, float* chain_grad_norms,
                   cudaStream_t s);
-// width-128 kernels with the activations in tensor memory (mlp_umma_ts.cu)
-int ts_tiles_per_cta(ibc_handle* h, int64_t R);
-int umma_forward_ts(ibc_handle* h, const float* act, int64_t R, int64_t n, const float* hp,
-                    float* E, float* xa_save, int nt, cudaStream_t s);
-int umma_backward_ts(ibc_handle* h, const float* dE, int64_t R, const float* xa_save,
-                     float* gy_save, float* g0, float* dwe, int nt, cudaStream_t s);
 // tcgen05 training path (mlp_umma_train.cu): W == 128, no gradient penalty.
 bool umma_train_supported(const Layout& L);
 int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* actions, int64_t N,
                      const ibc_loss_cfg& c, int64_t global_batch, float* per_example,
                      float* grad_loss_out, float* energies_out, float* grads, cudaStream_t s);
-int umma_reverse(ibc_handle* h, const float* dE, int64_t R, const float* xa_save, float* gy_save,
+int umma_reverse(ibc_handle* h, const float* dE, int64_t R, const float* xa_save,
+                 const uint32_t* mask_save, float* gy_save,
                  float* g0, float* dwe, cudaStream_t s);
 int mlp_energy_dact_umma(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
                          float* E, float* dEda, bool apply_exp, cudaStream_t s);

@@ -124,6 +124,7 @@ struct FwdParams {
   // fp32) are also written to global memory in the tile layout of
   // train_tile_offset() for the backward kernels.
   float* xa_save;
+  uint32_t* mask_save;   // ReLU masks of the 2nb W x W layers (TrainTile::mask_index)
   long long* dbg;   // optional timeline of CTA 0, group 0: [step][tile][5] clock64 stamps
 };
 
@@ -143,8 +144,9 @@ struct FwdSmem {
 // 32 accumulator columns of one row (bias already added by the MMA): ReLU, round
 // to tf32, write the 8 operand chunks.
 template <bool kRelu, int W>
-__device__ __forceinline__ void emit_chunks(const uint32_t (&v)[32], float4* __restrict__ a_tile,
-                                            int c32, int row, float4* __restrict__ g_slot) {
+__device__ __forceinline__ uint32_t emit_chunks(const uint32_t (&v)[32], float4* __restrict__ a_tile,
+                                                int c32, int row, float4* __restrict__ g_slot) {
+  uint32_t bits = 0;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     float4 o = make_float4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]),
@@ -155,7 +157,12 @@ __device__ __forceinline__ void emit_chunks(const uint32_t (&v)[32], float4* __r
     const float4 r4 = tf32_rn4(o);
     a_tile[(c32 * 8 + q) * 128 + row] = r4;
     if (g_slot) g_slot[TrainTile<W>::chunk_f4(row, c32 * 8 + q)] = r4;
+    bits |= (r4.x > 0.f ? 1u : 0u) << (q * 4 + 0);
+    bits |= (r4.y > 0.f ? 1u : 0u) << (q * 4 + 1);
+    bits |= (r4.z > 0.f ? 1u : 0u) << (q * 4 + 2);
+    bits |= (r4.w > 0.f ? 1u : 0u) << (q * 4 + 3);
   }
+  return bits;
 }
 
 template <int W, int NT>
@@ -227,8 +234,12 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
       const float* hp_row = p.hp + (valid ? (r / p.n_per_obs) : 0) * W;
       const int64_t tile_id = (int64_t)g * NT + t;
       for (int i = 0; i < nsteps; ++i) {
-        float4* g_slot = p.xa_save ? reinterpret_cast<float4*>(
-            p.xa_save + TrainTile<W>::slot_base(tile_id, nsteps, i)) : nullptr;
+        float4* g_slot = p.xa_save
+            ? reinterpret_cast<float4*>(p.xa_save + TrainTile<W>::slot_base(tile_id, nsteps, i))
+            : nullptr;
+        uint32_t* m_slot = (p.mask_save && i < nsteps - 1)
+            ? p.mask_save + TrainTile<W>::mask_index(tile_id, p.nb, i, row)
+            : nullptr;
         mbar_wait(&d_ready[t], ph_d, abort_flag, p.status, 100 + i);
         ph_d ^= 1;
         tc_fence_after();
@@ -271,6 +282,7 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
 #pragma unroll 1
           for (int cb = 0; cb < W / 128; ++cb) {
             uint32_t v[4][32];
+            uint32_t mb[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) tmem_ld32(taddr + cb * 128 + j * 32, v[j]);
             tmem_ld_wait();
@@ -290,8 +302,10 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
                 }
                 tmem_st32(taddr + c32 * 32, v[j]);
               }
-              emit_chunks<true, W>(v[j], a_tile, c32, row, g_slot);
+              mb[j] = emit_chunks<true, W>(v[j], a_tile, c32, row, g_slot);
             }
+            if (m_slot)
+              *reinterpret_cast<uint4*>(m_slot + cb * 4) = make_uint4(mb[0], mb[1], mb[2], mb[3]);
           }
           if (i == 0) tmem_st_wait();
           if (stamp) p.dbg[(i * NT + t) * 5 + 1] = clock64();
@@ -630,13 +644,13 @@ int mlp_energy_umma(ibc_handle* h, const float* obs, int64_t B, const float* act
   IBC_CUDA(h, h->ws.reserve(Workspace::rounded((size_t)B * L.W * 4)));
   h->ws.reset();
   float* hp = h->ws.take<float>((size_t)B * L.W);
-  return umma_forward(h, obs, B, act, n, hp, E, nullptr, s);
+  return umma_forward(h, obs, B, act, n, hp, E, nullptr, nullptr, s);
 }
 
 // Hoisted observation projection + fused forward.  hp [B, W] is caller scratch;
 // xa_save (nullable) receives the saved operand tiles for the backward pass.
 int umma_forward(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
-                 float* hp, float* E, float* xa_save, cudaStream_t s) {
+                 float* hp, float* E, float* xa_save, uint32_t* mask_save, cudaStream_t s) {
   const Layout& L = h->L;
   if (h->packed_stale) IBC_TRY(umma_pack_params(h, s));
   {  // hp = obs . Wp[:O] + bp   (fp32)
@@ -645,23 +659,15 @@ int umma_forward(ibc_handle* h, const float* obs, int64_t B, const float* act, i
     g.bias = h->params + L.bp; g.M = (int)B; g.N = L.W; g.K = L.O;
     IBC_TRY(gemm(h, g, false, false, s));
   }
-  return umma_forward_hp(h, act, B * n, n, hp, E, xa_save, s);
+  return umma_forward_hp(h, act, B * n, n, hp, E, xa_save, mask_save, s);
 }
 
 // Fused forward given the hoisted observation projection hp [R / n, W].
 int umma_forward_hp(ibc_handle* h, const float* act, int64_t R, int64_t n, const float* hp,
-                    float* E, float* xa_save, cudaStream_t s) {
+                    float* E, float* xa_save, uint32_t* mask_save, cudaStream_t s) {
   const Layout& L = h->L;
   if (h->packed_stale) IBC_TRY(umma_pack_params(h, s));
   const PackedLayout pl = make_packed_layout(L);
-  // Experimental variant with the activations in tensor memory (mlp_umma_ts.cu):
-  // correct, but measured slower on B200 (0.44 vs 0.30 ms on 131 584 rows), so
-  // it is opt-in for tuning only.
-  static const bool use_ts = getenv("IBC_TMEM_ACTIVATIONS") != nullptr;
-  if (L.W == 128 && use_ts) {
-    const int nt = xa_save ? 2 : ts_tiles_per_cta(h, R);
-    return umma_forward_ts(h, act, R, n, hp, E, xa_save, nt, s);
-  }
   FwdParams p;
   p.act = act; p.hp = hp; p.packed = h->packed; p.E = E; p.R = R; p.n_per_obs = n;
   p.nb = L.nb; p.A = L.A; p.KP = pl.KP;
@@ -669,6 +675,7 @@ int umma_forward_hp(ibc_handle* h, const float* act, int64_t R, int64_t n, const
   p.off_fwd_bias = pl.fwd_bias;
   p.status = h->dev_status;
   p.xa_save = xa_save;
+  p.mask_save = mask_save;
   p.dbg = nullptr;
   static const bool want_dbg = getenv("IBC_DBG_TIMELINE") != nullptr;
   if (want_dbg) {

@@ -44,7 +44,8 @@ constexpr int kNT = 2;
 // ---------------------------------------------------------------------------
 struct BwdParams {
   const float* dE;        // [R]   d(sum loss / global_batch) / dE
-  const float* xa_save;   // forward operand tiles, 2nb+1 slots
+  const float* xa_save;   // forward operand tiles, 2nb+1 slots (only slot 2nb is read, for dwe)
+  const uint32_t* mask_save;  // ReLU mask bits of the 2nb layers
   float* gy_save;         // output-gradient tiles, 2nb slots (slot i-1 = GY of layer i)
   float* g0;              // [R, W] row-major gradient of the first Dense output
   const float* packed;
@@ -122,6 +123,18 @@ __global__ void __launch_bounds__((4 * NT_ + 2) * 32, 1) mlp_bwd_umma_kernel(Bwd
       const int64_t r = tile_id * 128 + row;
       const bool valid = r < p.R;
       const float de = valid ? (p.dE ? p.dE[r] : 1.0f) : 0.f;
+      const uint32_t* mask_base = p.mask_save;
+      uint32_t mnext[W / 32];
+      {
+        const uint4* mp = reinterpret_cast<const uint4*>(
+            mask_base + TT::mask_index(tile_id, p.nb, nsteps - 1, row));
+#pragma unroll
+        for (int c4 = 0; c4 < W / 128; ++c4) {
+          const uint4 m = mp[c4];
+          mnext[c4 * 4 + 0] = m.x; mnext[c4 * 4 + 1] = m.y;
+          mnext[c4 * 4 + 2] = m.z; mnext[c4 * 4 + 3] = m.w;
+        }
+      }
       {
         // g_top = dE (x) we   (gradient of the residual stream entering Dense(1));
         // dwe += h_nb^T dE with h_nb from the forward's last slot
@@ -162,25 +175,22 @@ __global__ void __launch_bounds__((4 * NT_ + 2) * 32, 1) mlp_bwd_umma_kernel(Bwd
         const int i = nsteps - s;                     // forward layer index 2nb .. 1
         const bool odd = (i & 1) != 0;                // W1 layer: result adds onto g
         const bool last = (i == 1);
-        const float4* xm = reinterpret_cast<const float4*>(
-            p.xa_save + TT::slot_base(tile_id, xa_slots, i - 1));
         float4* gy_out = (last || !p.gy_save) ? nullptr : reinterpret_cast<float4*>(
             p.gy_save + TT::slot_base(tile_id, gy_slots, i - 2));
-        // ReLU masks of this layer (saved forward operand > 0) as bits, fetched
-        // while the tensor core is still working on this step's MMA
+        // ReLU masks of this layer (bits written by the forward); the next layer's
+        // are requested now so that their latency hides behind this step
         uint32_t mbits[W / 32];
 #pragma unroll
-        for (int c32 = 0; c32 < W / 32; ++c32) {
-          uint32_t bits = 0;
+        for (int c32 = 0; c32 < W / 32; ++c32) mbits[c32] = mnext[c32];
+        if (!last) {
+          const uint4* mp = reinterpret_cast<const uint4*>(
+              mask_base + TT::mask_index(tile_id, p.nb, i - 2, row));
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 m = xm[TT::chunk_f4(row, c32 * 8 + q)];
-            bits |= (m.x > 0.f ? 1u : 0u) << (q * 4 + 0);
-            bits |= (m.y > 0.f ? 1u : 0u) << (q * 4 + 1);
-            bits |= (m.z > 0.f ? 1u : 0u) << (q * 4 + 2);
-            bits |= (m.w > 0.f ? 1u : 0u) << (q * 4 + 3);
+          for (int c4 = 0; c4 < W / 128; ++c4) {
+            const uint4 m = mp[c4];
+            mnext[c4 * 4 + 0] = m.x; mnext[c4 * 4 + 1] = m.y;
+            mnext[c4 * 4 + 2] = m.z; mnext[c4 * 4 + 3] = m.w;
           }
-          mbits[c32] = bits;
         }
         mbar_wait(&d_ready[t], ph_d, abort_flag, p.status, 500 + s);
         ph_d ^= 1;
@@ -525,12 +535,14 @@ static int launch_bwd(ibc_handle* h, const BwdParams& bp, cudaStream_t s) {
 // Fused reverse chain over the tiles saved by umma_forward(..., xa_save): g0 [R, W]
 // = d(sum_r dE[r] * E[r]) / d(first Dense output).  gy_save / dwe are optional
 // (training only).
-int umma_reverse(ibc_handle* h, const float* dE, int64_t R, const float* xa_save, float* gy_save,
-                 float* g0, float* dwe, cudaStream_t s) {
+int umma_reverse(ibc_handle* h, const float* dE, int64_t R, const float* xa_save,
+                 const uint32_t* mask_save, float* gy_save, float* g0, float* dwe,
+                 cudaStream_t s) {
+  if (dwe && !xa_save) IBC_FAIL(h, IBC_ERR_INVALID, "umma_reverse: dwe needs the saved tiles");
   const Layout& L = h->L;
   const PackedLayout pl = make_packed_layout(L);
   BwdParams bp;
-  bp.dE = dE; bp.xa_save = xa_save; bp.gy_save = gy_save; bp.g0 = g0; bp.packed = h->packed;
+  bp.dE = dE; bp.xa_save = xa_save; bp.mask_save = mask_save; bp.gy_save = gy_save; bp.g0 = g0; bp.packed = h->packed;
   bp.off_rev_l = pl.rev_l; bp.off_we = pl.vecs + (int64_t)(2 * L.nb + 1) * L.W;
   bp.dwe = dwe; bp.R = R; bp.nb = L.nb; bp.status = h->dev_status;
   if (L.W == 128) {
@@ -555,21 +567,19 @@ int mlp_energy_dact_umma(ibc_handle* h, const float* obs, int64_t B, const float
                          float* E, float* dEda, bool apply_exp, cudaStream_t s) {
   const Layout& L = h->L;
   const int64_t R = B * n;
-  const int nt = (L.W == 128) ? 2 : 1;
-  const int64_t tiles = ((R + 128 * nt - 1) / (128 * nt)) * nt;
-  const size_t xa_floats = (size_t)tiles * (2 * L.nb + 1) * 128 * L.W;
-  const size_t bytes = Workspace::rounded(xa_floats * 4) + Workspace::rounded((size_t)R * L.W * 4) +
+  const size_t mask_words = umma_mask_words(L, R);
+  const size_t bytes = Workspace::rounded(mask_words * 4) + Workspace::rounded((size_t)R * L.W * 4) +
                        Workspace::rounded((size_t)B * L.W * 4) + Workspace::rounded((size_t)R * 4);
   IBC_CUDA(h, h->ws.reserve(bytes));
   h->ws.reset();
-  float* xa = h->ws.take<float>(xa_floats);
+  uint32_t* masks = h->ws.take<uint32_t>(mask_words);
   float* g0 = h->ws.take<float>((size_t)R * L.W);
   float* hp = h->ws.take<float>((size_t)B * L.W);
   float* dE = h->ws.take<float>(R);
-  IBC_TRY(umma_forward(h, obs, B, act, n, hp, E, xa, s));
+  IBC_TRY(umma_forward(h, obs, B, act, n, hp, E, nullptr, masks, s));
   fill_or_exp_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(E, dE, R, apply_exp ? 1 : 0);
   IBC_LAUNCH_CHECK(h);
-  IBC_TRY(umma_reverse(h, dE, R, xa, nullptr, g0, nullptr, s));
+  IBC_TRY(umma_reverse(h, dE, R, nullptr, masks, nullptr, g0, nullptr, s));
   GemmP g;
   g.A = g0; g.lda = L.W; g.B = h->params + L.wp + (int64_t)L.O * L.W; g.ldb = L.W;
   g.C = dEda; g.ldc = L.A; g.M = (int)R; g.N = L.A; g.K = L.W;
@@ -636,14 +646,12 @@ int langevin_umma(ibc_handle* h, const float* obs, int64_t B, float* actions, in
   const Layout& L = h->L;
   const int64_t R = B * n;
   const int A = L.A;
-  const int nt = (L.W == 128) ? 2 : 1;
-  const int64_t tiles = ((R + 128 * nt - 1) / (128 * nt)) * nt;
-  const size_t xa_floats = (size_t)tiles * (2 * L.nb + 1) * 128 * L.W;
-  const size_t bytes = Workspace::rounded(xa_floats * 4) + Workspace::rounded((size_t)R * L.W * 4) +
+  const size_t mask_words = umma_mask_words(L, R);
+  const size_t bytes = Workspace::rounded(mask_words * 4) + Workspace::rounded((size_t)R * L.W * 4) +
                        Workspace::rounded((size_t)B * L.W * 4) + 3 * Workspace::rounded((size_t)R * 4);
   IBC_CUDA(h, h->ws.reserve(bytes));
   h->ws.reset();
-  float* xa = h->ws.take<float>(xa_floats);
+  uint32_t* masks = h->ws.take<uint32_t>(mask_words);
   float* g0 = h->ws.take<float>((size_t)R * L.W);
   float* hp = h->ws.take<float>((size_t)B * L.W);
   float* E = h->ws.take<float>(R);
@@ -661,14 +669,14 @@ int langevin_umma(ibc_handle* h, const float* obs, int64_t B, float* actions, in
   for (int k = 0; k < c.num_iterations; ++k) {
     float* Ek = chain_energies ? chain_energies + (int64_t)k * R : E;
     float* Nk = chain_grad_norms ? chain_grad_norms + (int64_t)k * R : nrm;
-    IBC_TRY(umma_forward_hp(h, act_const(actions), R, n, hp, Ek, xa, s));
+    IBC_TRY(umma_forward_hp(h, act_const(actions), R, n, hp, Ek, nullptr, masks, s));
     const float* de = nullptr;
     if (c.apply_exp) {
       fill_or_exp_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(Ek, dE, R, 1);
       IBC_LAUNCH_CHECK(h);
       de = dE;
     }
-    IBC_TRY(umma_reverse(h, de, R, xa, nullptr, g0, nullptr, s));
+    IBC_TRY(umma_reverse(h, de, R, nullptr, masks, nullptr, g0, nullptr, s));
     langevin_dact_update_kernel<<<(unsigned)((R + 7) / 8), 256, 0, s>>>(
         g0, wpa, L.W, actions, R, A, normals ? normals + (int64_t)k * R * A : nullptr, seed,
         (uint64_t)k + 1, c.noise_scale, c.grad_clip, dclip_scale, steps[k], mn, mx,
@@ -676,6 +684,19 @@ int langevin_umma(ibc_handle* h, const float* obs, int64_t B, float* actions, in
     IBC_LAUNCH_CHECK(h);
   }
   return IBC_OK;
+}
+
+static int64_t umma_tiles(const Layout& L, int64_t R) {
+  const int nt = (L.W == 128) ? 2 : 1;
+  return ((R + 128 * nt - 1) / (128 * nt)) * nt;
+}
+
+size_t umma_save_floats(const Layout& L, int64_t R) {
+  return (size_t)(umma_tiles(L, R) * (2 * L.nb + 1) * (int64_t)128 * L.W);
+}
+
+size_t umma_mask_words(const Layout& L, int64_t R) {
+  return (size_t)(umma_tiles(L, R) * (2 * L.nb) * 128 * (int64_t)(L.W / 32));
 }
 
 bool umma_train_supported(const Layout& L) {
@@ -694,16 +715,18 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
   const float gscale = 1.0f / (float)global_batch;
   const int num_groups = (int)((R + 255) / 256);
   const int64_t num_tiles = (int64_t)num_groups * kNT;
-  const size_t xa_floats = (size_t)num_tiles * (2 * nb + 1) * TT::kTileFloats;
+  const size_t xa_floats = umma_save_floats(L, R);
   const size_t gy_floats = (size_t)num_tiles * (2 * nb) * TT::kTileFloats;
+  const size_t mask_words = umma_mask_words(L, R);
   const size_t bytes = Workspace::rounded(xa_floats * 4) + Workspace::rounded(gy_floats * 4) +
-                       Workspace::rounded((size_t)R * W * 4) +
+                       Workspace::rounded(mask_words * 4) + Workspace::rounded((size_t)R * W * 4) +
                        2 * Workspace::rounded((size_t)B * W * 4) +
                        2 * Workspace::rounded((size_t)R * 4) + 2 * Workspace::rounded((size_t)B * 4);
   IBC_CUDA(h, h->ws.reserve(bytes));
   h->ws.reset();
   float* xa = h->ws.take<float>(xa_floats);
   float* gy = h->ws.take<float>(gy_floats);
+  uint32_t* masks = h->ws.take<uint32_t>(mask_words);
   float* g0 = h->ws.take<float>((size_t)R * W);
   float* hp = h->ws.take<float>((size_t)B * W);
   float* gsum = h->ws.take<float>((size_t)B * W);
@@ -714,7 +737,7 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
   auto mark = [&](int i) { if (h->profiling) cudaEventRecord(h->ev[i], s); };
   IBC_CUDA(h, cudaMemsetAsync(grads, 0, (size_t)L.count * 4, s));
   mark(0);
-  IBC_TRY(umma_forward(h, obs, B, actions, n1, hp, E, xa, s));
+  IBC_TRY(umma_forward(h, obs, B, actions, n1, hp, E, xa, masks, s));
   mark(1);
   if (energies_out)
     IBC_CUDA(h, cudaMemcpyAsync(energies_out, E, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
@@ -730,12 +753,7 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
                                      (int)WgradSmem::kBytes));
     attr_done = true;
   }
-  static const bool use_ts = getenv("IBC_TMEM_ACTIVATIONS") != nullptr;
-  if (use_ts) {
-    IBC_TRY(umma_backward_ts(h, dE, R, xa, gy, g0, grads + L.we, kNT, s));
-  } else {
-    IBC_TRY(umma_reverse(h, dE, R, xa, gy, g0, grads + L.we, s));
-  }
+  IBC_TRY(umma_reverse(h, dE, R, xa, masks, gy, g0, grads + L.we, s));
   mark(3);
   {
     WgradParams wp;
@@ -765,7 +783,7 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
   {
     GemmP g;   // dWp[:O] = obs^T . sum_n g0
     g.A = obs; g.lda = L.O; g.B = gsum; g.ldb = W; g.C = grads + L.wp; g.ldc = W;
-    g.M = L.O; g.N = W; g.K = (int)B; g.k_chunk = 1024; g.atomic = 1;
+    g.M = L.O; g.N = W; g.K = (int)B; g.k_chunk = 32; g.atomic = 1;   // many small splits: latency-bound
     IBC_TRY(gemm(h, g, true, false, s));
   }
   IBC_TRY(colsum_add(h, gsum, W, B, W, grads + L.bp, s));

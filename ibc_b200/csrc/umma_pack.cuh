@@ -87,6 +87,12 @@ struct TrainTile {
   __host__ __device__ static int chunk_f4(int row, int c) {
     return (row >> 5) * (kSubFloats / 4) + c * kSubRows + (row & 31);
   }
+  // ReLU masks of the 2nb W x W layers: [tile][layer slot][128 rows][W/32 words],
+  // bit b of word w = (operand column 32w + b > 0).  The reverse chain only needs
+  // these 16 bytes per row and layer.
+  __host__ __device__ static int64_t mask_index(int64_t tile, int nb, int slot, int row) {
+    return ((tile * (2 * nb) + slot) * 128 + row) * (int64_t)(W / 32);
+  }
   // float4 index of the same piece inside the MN-major image of its sub-tile
   __host__ __device__ static int mn_f4(int rr, int c) {
     const int ka = rr >> 2, kr = rr & 3, ma = c >> 3, oct = (c >> 1) & 3, half = c & 1;
