@@ -68,6 +68,14 @@ int langevin_umma(ibc_handle* h, const float* obs, int64_t B, float* actions, in
                   const float* normals, uint64_t seed, const std::vector<float>& steps,
                   float* chain_actions, float* chain_energies, float* chain_grad_norms,
                   cudaStream_t s);
+// width-128 kernels with the activations in tensor memory (mlp_umma_tmem.cu); tile
+// ids and the saved-tile layouts are the same as the shared-memory-operand kernels'
+bool tmem_path_supported(const Layout& L);
+int tmem_forward(ibc_handle* h, const float* act, int64_t R, int64_t n, const float* hp, float* E,
+                 float* xa_save, uint32_t* mask_save, cudaStream_t s);
+int tmem_reverse(ibc_handle* h, const float* dE, int64_t R, const float* xa_save,
+                 const uint32_t* mask_save, float* gy_save, float* g0, float* dwe,
+                 cudaStream_t s);
 // tcgen05 training path (mlp_umma_train.cu): W == 128, no gradient penalty.
 bool umma_train_supported(const Layout& L);
 int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* actions, int64_t N,

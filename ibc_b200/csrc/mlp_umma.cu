@@ -68,6 +68,28 @@ __global__ void pack_kernel(const float* __restrict__ P, Layout L, PackedLayout 
       const int wq = (int)(e & 3), a = (int)((e >> 2) % pl.AP), wc = (int)((e >> 2) / pl.AP);
       const int w = wc * 4 + wq;
       v = (a < L.A) ? P[L.wp + (int64_t)(L.O + a) * W + w] : 0.f;
+    } else if (i >= pl.fwd_lb) {
+      // layer block m: the forward operand of layer m (as in fwd_l) + the bias slice of
+      // step m + 1 (as in fwd_bias)
+      const int64_t e = i - pl.fwd_lb;
+      const int64_t blk = WW + 8 * W;
+      const int m = (int)(e / blk);
+      const int64_t r = e - (int64_t)m * blk;
+      const int j = m >> 1;
+      if (r < WW) {
+        const int kq = (int)(r & 3), n = (int)((r >> 2) % W), kc = (int)((r >> 2) / W);
+        const int k = kc * 4 + kq;
+        const int64_t base = (m & 1) ? L.w2(j) : L.w1(j);
+        v = tf32_rn(P[base + (int64_t)k * W + n]);
+      } else {
+        const int rb = (int)(r - WW);
+        const int kc = rb / (4 * W), n = (rb / 4) % W, kq = rb & 3;
+        const float b = (m & 1) ? P[L.b2(j) + n] : P[L.b1(j) + n];
+        const float hi = tf32_rn(b);
+        v = (kc == 0 && kq == 0) ? hi : ((kc == 0 && kq == 1) ? tf32_rn(b - hi) : 0.f);
+      }
+      out[i] = v;
+      continue;
     } else if (i >= pl.fwd_bias) {
       // bias of step s as a K = 8 operand slice [2 chunks][W][4]: row n of chunk 0 holds
       // (hi, lo, 0, 0) with hi + lo = bias to ~2^-21; the matching A operand is a
@@ -143,7 +165,7 @@ struct FwdSmem {
 
 // 32 accumulator columns of one row (bias already added by the MMA): ReLU, round
 // to tf32, write the 8 operand chunks.
-template <bool kRelu, int W>
+template <bool kRelu, bool kMask, int W>
 __device__ __forceinline__ uint32_t emit_chunks(const uint32_t (&v)[32], float4* __restrict__ a_tile,
                                                 int c32, int row, float4* __restrict__ g_slot) {
   uint32_t bits = 0;
@@ -157,15 +179,19 @@ __device__ __forceinline__ uint32_t emit_chunks(const uint32_t (&v)[32], float4*
     const float4 r4 = tf32_rn4(o);
     a_tile[(c32 * 8 + q) * 128 + row] = r4;
     if (g_slot) g_slot[TrainTile<W>::chunk_f4(row, c32 * 8 + q)] = r4;
-    bits |= (r4.x > 0.f ? 1u : 0u) << (q * 4 + 0);
-    bits |= (r4.y > 0.f ? 1u : 0u) << (q * 4 + 1);
-    bits |= (r4.z > 0.f ? 1u : 0u) << (q * 4 + 2);
-    bits |= (r4.w > 0.f ? 1u : 0u) << (q * 4 + 3);
+    if (kMask) {
+      bits |= (r4.x > 0.f ? 1u : 0u) << (q * 4 + 0);
+      bits |= (r4.y > 0.f ? 1u : 0u) << (q * 4 + 1);
+      bits |= (r4.z > 0.f ? 1u : 0u) << (q * 4 + 2);
+      bits |= (r4.w > 0.f ? 1u : 0u) << (q * 4 + 3);
+    }
   }
   return bits;
 }
 
-template <int W, int NT>
+// kSave: the instance that also writes operand tiles / ReLU masks for a reverse
+// pass; the inference instance carries none of that work.
+template <int W, int NT, bool kSave>
 __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdParams p) {
   using S = FwdSmem<W, NT>;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -234,10 +260,10 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
       const float* hp_row = p.hp + (valid ? (r / p.n_per_obs) : 0) * W;
       const int64_t tile_id = (int64_t)g * NT + t;
       for (int i = 0; i < nsteps; ++i) {
-        float4* g_slot = p.xa_save
+        float4* g_slot = (kSave && p.xa_save)
             ? reinterpret_cast<float4*>(p.xa_save + TrainTile<W>::slot_base(tile_id, nsteps, i))
             : nullptr;
-        uint32_t* m_slot = (p.mask_save && i < nsteps - 1)
+        uint32_t* m_slot = (kSave && p.mask_save && i < nsteps - 1)
             ? p.mask_save + TrainTile<W>::mask_index(tile_id, p.nb, i, row)
             : nullptr;
         mbar_wait(&d_ready[t], ph_d, abort_flag, p.status, 100 + i);
@@ -302,7 +328,7 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
                 }
                 tmem_st32(taddr + c32 * 32, v[j]);
               }
-              mb[j] = emit_chunks<true, W>(v[j], a_tile, c32, row, g_slot);
+              mb[j] = emit_chunks<true, kSave, W>(v[j], a_tile, c32, row, g_slot);
             }
             if (m_slot)
               *reinterpret_cast<uint4*>(m_slot + cb * 4) = make_uint4(mb[0], mb[1], mb[2], mb[3]);
@@ -318,7 +344,8 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
     }
   } else if (warp == 4 * NT) {
     // ===================== producer: weight slices via bulk copy ==============
-    if (lane == 0) {
+    // converged warp, elected lane (see umma::elect_one)
+    {
       uint32_t q = 0;
       for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
         for (int i = 0; i < nsteps; ++i) {
@@ -330,27 +357,36 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
             const uint32_t bytes = (uint32_t)(W * ke * 4);
             const int slot = q % kSlots;
             const uint32_t ph = (q / kSlots) & 1;
-            mbar_wait(&w_empty[slot], ph ^ 1, abort_flag, p.status, 200 + i);
-            mbar_arrive_expect_tx(&w_full[slot], bytes);
-            bulk_g2s(ring + slot * kSliceBytes, src + (int64_t)s * (kSliceBytes / 4), bytes,
-                     &w_full[slot]);
+            if (elect_one()) {
+              mbar_wait(&w_empty[slot], ph ^ 1, abort_flag, p.status, 200 + i);
+              if (p.dbg && blockIdx.x == 0 && g == (int)blockIdx.x && i < 32 && s < 8)
+                p.dbg[1024 + i * 8 + s] = clock64();
+              mbar_arrive_expect_tx(&w_full[slot], bytes);
+              bulk_g2s(ring + slot * kSliceBytes, src + (int64_t)s * (kSliceBytes / 4), bytes,
+                       &w_full[slot]);
+            }
+            __syncwarp();
           }
           if (i > 0) {   // this step's bias as one more K = 8 operand slice
             const int slot = q % kSlots;
             const uint32_t ph = (q / kSlots) & 1;
-            mbar_wait(&w_empty[slot], ph ^ 1, abort_flag, p.status, 250 + i);
-            mbar_arrive_expect_tx(&w_full[slot], (uint32_t)(8 * W * 4));
-            bulk_g2s(ring + slot * kSliceBytes, p.packed + p.off_fwd_bias + (int64_t)i * 8 * W,
-                     (uint32_t)(8 * W * 4), &w_full[slot]);
+            if (elect_one()) {
+              mbar_wait(&w_empty[slot], ph ^ 1, abort_flag, p.status, 250 + i);
+              mbar_arrive_expect_tx(&w_full[slot], (uint32_t)(8 * W * 4));
+              bulk_g2s(ring + slot * kSliceBytes, p.packed + p.off_fwd_bias + (int64_t)i * 8 * W,
+                       (uint32_t)(8 * W * 4), &w_full[slot]);
+            }
+            __syncwarp();
             ++q;
           }
         }
       }
     }
-    __syncwarp();
   } else {
     // ===================== MMA issuer ==========================================
-    if (lane == 0) {
+    // The warp stays converged; every tcgen05 instruction is issued by the lane
+    // elect.sync picks (see umma::elect_one).
+    {
       const uint32_t idesc = idesc_tf32(128, W);
       const uint32_t a_lbo = 128 * 16, b_lbo = W * 16, sbo = 128;
       uint32_t q = 0;
@@ -364,11 +400,14 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
           const uint32_t acc0 = (to_h && i > 0) ? 1u : 0u;
 #pragma unroll
           for (int t = 0; t < NT; ++t) {
-            mbar_wait(&a_ready[t], ph_a[t], abort_flag, p.status, 300 + i);
+            const bool mstamp = p.dbg && blockIdx.x == 0 && g == (int)blockIdx.x && i < 32;
+            long long wf_wait = 0;
+            const long long t_top = mstamp ? clock64() : 0;
+            if (elect_one()) mbar_wait(&a_ready[t], ph_a[t], abort_flag, p.status, 300 + i);
+            __syncwarp();
             ph_a[t] ^= 1;
             tc_fence_after();
-            const bool mstamp = p.dbg && blockIdx.x == 0 && g == (int)blockIdx.x && i < 64;
-            if (mstamp) p.dbg[(i * NT + t) * 5 + 3] = clock64();
+            const long long t_start = mstamp ? clock64() : 0;
             const uint32_t d_tmem = tmem_base + (uint32_t)(t * 2 * W + (to_h ? 0 : W));
             const uint64_t a_desc0 = smem_desc(smem_u32(a_base + t * S::kABytes), a_lbo, sbo);
             constexpr uint32_t a_step16 = (2 * 128 * 16) >> 4, b_step16 = (2 * W * 16) >> 4;
@@ -379,43 +418,74 @@ __global__ void __launch_bounds__((4 * NT + 2) * 32, 1) mlp_fwd_umma_kernel(FwdP
                 if (t == 0) mbar_wait(&w_full[slot], (qq / kSlots) & 1, abort_flag, p.status, 400);
                 const uint64_t b_desc0 = smem_desc(smem_u32(ring + slot * kSliceBytes), b_lbo, sbo);
                 const int kps = min(S::kSliceK, p.KP - s * S::kSliceK) / 8;
-                for (int ks = 0; ks < kps; ++ks) {
-                  const int kk = s * S::kStepsPerSlice + ks;
-                  mma_tf32_ss(d_tmem, a_desc0 + (uint64_t)(kk * a_step16),
-                              b_desc0 + (uint64_t)(ks * b_step16), idesc, (uint32_t)(kk > 0));
+                if (elect_one()) {
+                  for (int ks = 0; ks < kps; ++ks) {
+                    const int kk = s * S::kStepsPerSlice + ks;
+                    mma_tf32_ss(d_tmem, a_desc0 + (uint64_t)(kk * a_step16),
+                                b_desc0 + (uint64_t)(ks * b_step16), idesc, (uint32_t)(kk > 0));
+                  }
+                  if (t == NT - 1) mma_commit(&w_empty[slot]);
                 }
-                if (t == NT - 1) mma_commit(&w_empty[slot]);
+                __syncwarp();
               }
             } else {
+              // one elected lane issues the whole layer for this tile back to back (the
+              // tensor pipe's issue queue is shallow: instructions between two MMAs
+              // show up as pipe bubbles); tile 0 polls each slice's barrier itself
+              uint32_t b_addr[S::kSlicesPerLayer + 1];
+              uint32_t b_par[S::kSlicesPerLayer + 1];
+              uint64_t* b_full[S::kSlicesPerLayer + 1];
+              uint64_t* b_empty[S::kSlicesPerLayer + 1];
 #pragma unroll
-              for (int s = 0; s < S::kSlicesPerLayer; ++s) {
+              for (int s = 0; s <= S::kSlicesPerLayer; ++s) {
                 const uint32_t qq = q + s;
-                const int slot = qq % kSlots;
-                // the second tile reuses slices the first tile already waited for
-                if (t == 0) mbar_wait(&w_full[slot], (qq / kSlots) & 1, abort_flag, p.status, 400 + i);
-                const uint64_t b_desc0 = smem_desc(smem_u32(ring + slot * kSliceBytes), b_lbo, sbo);
-                mma_tf32_ss_steps<S::kStepsPerSlice>(
-                    d_tmem, a_desc0 + (uint64_t)(s * S::kStepsPerSlice * a_step16), b_desc0,
-                    a_step16, b_step16, idesc, s == 0 ? acc0 : 1u);
-                if (t == NT - 1) mma_commit(&w_empty[slot]);
+                const uint32_t slot = qq % kSlots;
+                b_addr[s] = smem_u32(ring + slot * kSliceBytes);
+                b_par[s] = (qq / kSlots) & 1;
+                b_full[s] = &w_full[slot];
+                b_empty[s] = &w_empty[slot];
               }
-              {   // + bias: (1, 1, 0, ...) . (hi, lo, 0, ...)^T
-                const uint32_t qq = q + S::kSlicesPerLayer;
-                const int slot = qq % kSlots;
-                if (t == 0) mbar_wait(&w_full[slot], (qq / kSlots) & 1, abort_flag, p.status, 450 + i);
-                mma_tf32_ss(d_tmem, smem_desc(smem_u32(ones_tile), a_lbo, sbo),
-                            smem_desc(smem_u32(ring + slot * kSliceBytes), b_lbo, sbo), idesc, 1u);
-                if (t == NT - 1) mma_commit(&w_empty[slot]);
+              const uint64_t ones_desc = smem_desc(smem_u32(ones_tile), a_lbo, sbo);
+              if (elect_one()) {
+#pragma unroll
+                for (int s = 0; s < S::kSlicesPerLayer; ++s) {
+                  if (t == 0) {
+                    mbar_wait(b_full[s], b_par[s], abort_flag, p.status, 400 + i);
+                    if (mstamp) p.dbg[1280 + i * 8 + s] = clock64();
+                  }
+                  mma_tf32_ss_steps<S::kStepsPerSlice>(
+                      d_tmem, a_desc0 + (uint64_t)(s * S::kStepsPerSlice * a_step16),
+                      smem_desc(b_addr[s], b_lbo, sbo), a_step16, b_step16, idesc,
+                      s == 0 ? acc0 : 1u);
+                  if (t == NT - 1) mma_commit(b_empty[s]);
+                }
+                // + bias: (1, 1, 0, ...) . (hi, lo, 0, ...)^T
+                if (t == 0)
+                  mbar_wait(b_full[S::kSlicesPerLayer], b_par[S::kSlicesPerLayer], abort_flag,
+                            p.status, 450 + i);
+                mma_tf32_ss(d_tmem, ones_desc, smem_desc(b_addr[S::kSlicesPerLayer], b_lbo, sbo),
+                            idesc, 1u);
+                if (t == NT - 1) mma_commit(b_empty[S::kSlicesPerLayer]);
+                mma_commit(&d_ready[t]);
               }
+              __syncwarp();
             }
-            mma_commit(&d_ready[t]);
-            if (mstamp) p.dbg[(i * NT + t) * 5 + 4] = clock64();
+            if (i == 0) {
+              if (elect_one()) mma_commit(&d_ready[t]);
+              __syncwarp();
+            }
+            if (mstamp && lane == 0) {
+              p.dbg[(i * NT + t) * 5 + 3] = t_start;
+              p.dbg[(i * NT + t) * 5 + 4] = clock64();
+              p.dbg[768 + (i * NT + t) * 2 + 0] = t_start - t_top;
+              p.dbg[768 + (i * NT + t) * 2 + 1] = wf_wait;
+              (void)wf_wait;
+            }
           }
           q += nsl + (i > 0 ? 1 : 0);
         }
       }
     }
-    __syncwarp();
   }
 
   tc_fence_before();
@@ -470,7 +540,7 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bpac
   if (warp < 4) {
     const int row = tid;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    if (mode == 0 || mode == 20 || mode == 22 || (mode >= 25 && mode <= 27)) {
+    if (mode == 0 || mode == 20 || mode == 22 || (mode >= 25 && mode <= 27) || mode == 30 || mode == 32 || mode == 34 || mode == 36 || mode == 38 || mode == 39 || mode == 40 || mode == 42 || mode == 43) {
       for (int c = 0; c < K / 4; ++c)
         a_tile[c * 128 + row] = *reinterpret_cast<const float4*>(A + (int64_t)row * K + c * 4);
       fence_proxy_async_smem();
@@ -499,6 +569,68 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bpac
   }
   __syncthreads();
   tc_fence_after();
+  __shared__ volatile int s_done;
+  if (tid == 0) s_done = 0;
+  __syncthreads();
+  __shared__ __align__(8) uint64_t s_hbar;
+  if (mode >= 40 && tid == 0) { mbar_init(&s_hbar, 1); fence_mbar_init(); }
+  __syncthreads();
+  if (warp == 0 && mode >= 40) {
+    // bulk-copy flood (40: SS MMA, 41: TS MMA): 4 x 16 KB global -> shared copies
+    // in flight at all times while the MMA loop runs
+    unsigned char* scratch = b_tile + (size_t)N * K * 4 + 1024;
+    uint32_t ph = 0;
+    // 40/41: 4 x 16 KB per round; 42: 1 x 16 KB per round (latency); 43: 1 x 64 KB
+    const int ncopy = (mode == 42 || mode == 43) ? 1 : 4;
+    const uint32_t cbytes = (mode == 43) ? 65536u : 16384u;
+    long long rounds = 0, issue_cycles = 0;
+    const long long f0 = clock64();
+    while (!s_done) {
+      if (lane == 0) {
+        const long long i0 = clock64();
+        mbar_arrive_expect_tx(&s_hbar, ncopy * cbytes);
+        for (int c = 0; c < ncopy; ++c)
+          bulk_g2s(scratch + c * 16384, Bpacked + (c & 1) * 4096, cbytes, &s_hbar);
+        issue_cycles += clock64() - i0;
+      }
+      mbar_wait(&s_hbar, ph, abort_flag, status, 3);
+      ph ^= 1;
+      ++rounds;
+    }
+    if (lane == 0)
+      printf("[bulk probe] mode %d: %lld rounds of %d x %u B in %lld cycles = %.1f B/cycle, %.0f cycles/round, issue %.0f cycles/round\n",
+             mode, rounds, ncopy, cbytes, clock64() - f0,
+             (double)rounds * ncopy * cbytes / (double)(clock64() - f0),
+             (double)(clock64() - f0) / (double)rounds, (double)issue_cycles / (double)rounds);
+  }
+  if (warp < 4 && mode >= 34 && mode <= 37) {
+    // contention probes: while the MMA thread runs its clean loop, the four
+    // epilogue warps hammer shared memory (34: SS MMA, 37: TS MMA) or tensor
+    // memory (35: TS MMA, 36: SS MMA) the way an epilogue would
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    float4* scratch = reinterpret_cast<float4*>(b_tile + (size_t)N * K * 4 + 1024);   // 64 KB
+    uint32_t v[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) v[q] = tid + q;
+    while (!s_done) {
+      if (mode == 34 || mode == 37) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          scratch[c * 128 + tid] = make_float4(__uint_as_float(v[c]), 0.f, 1.f, 2.f);
+      } else {
+#pragma unroll 1
+        for (int c32 = 0; c32 < 4; ++c32) {
+          tmem_ld32(tmem_base + lane_off + 128 + c32 * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(fmaxf(__uint_as_float(v[q]), 0.f));
+          tmem_st32(tmem_base + lane_off + 128 + c32 * 32, v);
+          tmem_st_wait();
+        }
+      }
+    }
+    tc_fence_before();
+  }
   if (warp == 4 && lane == 0 && mode >= 20) {
     // MMA issue-rate microbenchmark: 256 passes over the K steps, results unused.
     // 20: A,B from shared memory (no swizzle); 21: A from tensor memory;
@@ -506,9 +638,60 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bpac
     mbar_wait(&bars[0], 0, abort_flag, status, 1);
     const uint32_t idesc = idesc_tf32(128, N);
     const uint32_t a_lbo = 128 * 16, b_lbo = (uint32_t)N * 16, sbo = 128;
+    bool return_early = false;
     const int nk = K / 8;
+    if (mode >= 30) {
+      // Clean pipe-rate probes (K = 128: 16 unrolled steps, descriptors hoisted).
+      // 30: SS one accumulator; 31: TS one accumulator; 32: SS two alternating
+      // accumulators; 33: TS two alternating accumulators (N <= 128)
+      const uint64_t ad0 = smem_desc(smem_u32(a_tile), a_lbo, sbo);
+      const uint64_t bd0 = smem_desc(smem_u32(b_tile), b_lbo, sbo);
+      const uint32_t a_step16 = (2 * a_lbo) >> 4, b_step16 = (2 * b_lbo) >> 4;
+      const uint32_t d1 = (N <= 128) ? 128u : 256u;
+      const long long t0 = clock64();
+      if (mode == 30 || mode == 34 || mode == 36 || mode == 40 || mode == 42 || mode == 43) {
+        for (int rep = 0; rep < 64; ++rep)
+          mma_tf32_ss_steps<16>(tmem_base, ad0, bd0, a_step16, b_step16, idesc, 1u);
+      } else if (mode == 31 || mode == 35 || mode == 37 || mode == 41) {
+        for (int rep = 0; rep < 64; ++rep)
+          mma_tf32_ts_steps<16>(tmem_base, tmem_base + a_col, bd0, b_step16, idesc, 1u);
+      } else if (mode == 38 || mode == 39) {
+        // commit-cost probe: the same MMAs with a tcgen05.commit (to a barrier nobody
+        // waits on) after every 4 (38) or 16 (39) of them
+        uint64_t* dummy = &bars[0];   // B already landed; extra arrivals are harmless here
+        for (int rep = 0; rep < 64; ++rep) {
+          if (mode == 38) {
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+              mma_tf32_ss_steps<4>(tmem_base, ad0 + (uint64_t)(s4 * 4 * a_step16),
+                                   bd0 + (uint64_t)(s4 * 4 * b_step16), a_step16, b_step16, idesc, 1u);
+              mma_commit(dummy);
+            }
+          } else {
+            mma_tf32_ss_steps<16>(tmem_base, ad0, bd0, a_step16, b_step16, idesc, 1u);
+            mma_commit(dummy);
+          }
+        }
+      } else if (mode == 32) {
+        for (int rep = 0; rep < 32; ++rep) {
+          mma_tf32_ss_steps<16>(tmem_base, ad0, bd0, a_step16, b_step16, idesc, 1u);
+          mma_tf32_ss_steps<16>(tmem_base + d1, ad0, bd0, a_step16, b_step16, idesc, 1u);
+        }
+      } else {
+        for (int rep = 0; rep < 32; ++rep) {
+          mma_tf32_ts_steps<16>(tmem_base, tmem_base + a_col, bd0, b_step16, idesc, 1u);
+          mma_tf32_ts_steps<16>(tmem_base + d1, tmem_base + a_col, bd0, b_step16, idesc, 1u);
+        }
+      }
+      mma_commit(&bars[1]);
+      mbar_wait(&bars[1], 0, abort_flag, status, 2);
+      const long long t1 = clock64();
+      if (blockIdx.x == 0) atomicExch(status, (int)((t1 - t0) * 10 / (64 * 16)));
+      s_done = 1;
+      return_early = true;
+    }
     const long long t0 = clock64();
-    for (int rep = 0; rep < 256; ++rep)
+    for (int rep = 0; rep < (return_early ? 0 : 256); ++rep)
       for (int ks = 0; ks < nk; ++ks) {
         if (mode >= 25 && mode <= 27) {
           // accumulator-dependency probes: the same work as mode 20 split over several
@@ -542,10 +725,12 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bpac
           mma_tf32_ss(tmem_base, ad, bd, idesc, 1);
         }
       }
-    mma_commit(&bars[1]);
-    mbar_wait(&bars[1], 0, abort_flag, status, 2);
-    const long long t1 = clock64();
-    atomicExch(status, (int)((t1 - t0) * 10 / (256 * nk)));      // 0.1 cycles per MMA
+    if (!return_early) {
+      mma_commit(&bars[1]);
+      mbar_wait(&bars[1], 0, abort_flag, status, 2);
+      const long long t1 = clock64();
+      atomicExch(status, (int)((t1 - t0) * 10 / (256 * nk)));      // 0.1 cycles per MMA
+    }
   } else if (warp == 4 && lane == 0) {
     mbar_wait(&bars[0], 0, abort_flag, status, 1);
     const uint32_t idesc = idesc_tf32(128, N);
@@ -598,8 +783,8 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bpac
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-template <int W, int NT>
-int launch_fwd(ibc_handle* h, const FwdParams& p, cudaStream_t s) {
+template <int W, int NT, bool kSave>
+int launch_fwd_impl(ibc_handle* h, const FwdParams& p, cudaStream_t s) {
   using S = FwdSmem<W, NT>;
   const size_t smem = S::bytes(p.nb);
   if (smem > 227 * 1024)
@@ -607,14 +792,20 @@ int launch_fwd(ibc_handle* h, const FwdParams& p, cudaStream_t s) {
              2 * p.nb, smem);
   static size_t attr_smem = 0;     // per template instance; raised lazily
   if (smem > attr_smem) {
-    IBC_CUDA(h, cudaFuncSetAttribute(mlp_fwd_umma_kernel<W, NT>,
+    IBC_CUDA(h, cudaFuncSetAttribute(mlp_fwd_umma_kernel<W, NT, kSave>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
   const int grid = p.num_groups < h->sm_count ? p.num_groups : h->sm_count;
-  mlp_fwd_umma_kernel<W, NT><<<grid, S::kThreads, smem, s>>>(p);
+  mlp_fwd_umma_kernel<W, NT, kSave><<<grid, S::kThreads, smem, s>>>(p);
   IBC_LAUNCH_CHECK(h);
   return IBC_OK;
+}
+
+template <int W, int NT>
+int launch_fwd(ibc_handle* h, const FwdParams& p, cudaStream_t s) {
+  return (p.xa_save || p.mask_save) ? launch_fwd_impl<W, NT, true>(h, p, s)
+                                    : launch_fwd_impl<W, NT, false>(h, p, s);
 }
 
 }  // namespace
@@ -668,6 +859,11 @@ int umma_forward_hp(ibc_handle* h, const float* act, int64_t R, int64_t n, const
   const Layout& L = h->L;
   if (h->packed_stale) IBC_TRY(umma_pack_params(h, s));
   const PackedLayout pl = make_packed_layout(L);
+  // width 128: activations in tensor memory; IBC_SMEM_OPERANDS=1 selects the
+  // shared-memory-operand kernel below instead (kept for width 256 and for A/B runs)
+  static const bool force_smem = getenv("IBC_SMEM_OPERANDS") != nullptr;
+  if (!force_smem && tmem_path_supported(L))
+    return tmem_forward(h, act, R, n, hp, E, xa_save, mask_save, s);
   FwdParams p;
   p.act = act; p.hp = hp; p.packed = h->packed; p.E = E; p.R = R; p.n_per_obs = n;
   p.nb = L.nb; p.A = L.A; p.KP = pl.KP;
@@ -679,15 +875,15 @@ int umma_forward_hp(ibc_handle* h, const float* act, int64_t R, int64_t n, const
   p.dbg = nullptr;
   static const bool want_dbg = getenv("IBC_DBG_TIMELINE") != nullptr;
   if (want_dbg) {
-    IBC_CUDA(h, cudaMalloc((void**)&p.dbg, (640 + 128) * sizeof(long long)));
-    IBC_CUDA(h, cudaMemsetAsync(p.dbg, 0, (640 + 128) * sizeof(long long), s));
+    IBC_CUDA(h, cudaMalloc((void**)&p.dbg, (640 + 128 + 256 + 512) * sizeof(long long)));
+    IBC_CUDA(h, cudaMemsetAsync(p.dbg, 0, (640 + 128 + 256 + 512) * sizeof(long long), s));
   }
   struct DbgDump {
     long long* d; int nsteps, nt; cudaStream_t s;
     ~DbgDump() {
       if (!d) return;
       cudaStreamSynchronize(s);
-      std::vector<long long> hbuf(640 + 128);
+      std::vector<long long> hbuf(640 + 128 + 256 + 512);
       cudaMemcpy(hbuf.data(), d, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
       cudaFree(d);
       long long t0 = hbuf[3];
@@ -695,10 +891,16 @@ int umma_forward_hp(ibc_handle* h, const float* act, int64_t R, int64_t n, const
       for (int i = 0; i < nsteps && i < 64; ++i)
         for (int t = 0; t < nt; ++t) {
           const long long* e = &hbuf[(i * nt + t) * 5];
-          fprintf(stderr, "[ibc timeline] %3d %d | %8lld %8lld | %8lld (tmem loaded +%5lld) %8lld %8lld\n", i, t,
+          fprintf(stderr, "[ibc timeline] %3d %d | %8lld %8lld | %8lld (tmem loaded +%5lld) %8lld %8lld | a_wait %5lld w_wait %5lld\n", i, t,
                   e[3] - t0, e[4] - t0, e[0] - t0, hbuf[640 + i * nt + t] ? hbuf[640 + i * nt + t] - e[0] : 0,
-                  e[1] ? e[1] - t0 : 0, e[2] ? e[2] - t0 : 0);
+                  e[1] ? e[1] - t0 : 0, e[2] ? e[2] - t0 : 0,
+                  i < 32 ? hbuf[768 + (i * nt + t) * 2] : 0, i < 32 ? hbuf[768 + (i * nt + t) * 2 + 1] : 0);
         }
+      for (int i = 8; i < 11 && i < nsteps; ++i)
+        for (int sl = 0; sl < 4; ++sl)
+          fprintf(stderr, "[ibc ring] step %d slice %d: slot free seen %8lld, data seen by MMA %8lld (+%lld)\n",
+                  i, sl, hbuf[1024 + i * 8 + sl] - t0, hbuf[1280 + i * 8 + sl] - t0,
+                  hbuf[1280 + i * 8 + sl] - hbuf[1024 + i * 8 + sl]);
     }
   } dump{p.dbg, 2 * L.nb + 1, L.W == 128 ? 2 : 1, s};
   if (L.W == 128) {
@@ -714,8 +916,16 @@ int umma_forward_hp(ibc_handle* h, const float* act, int64_t R, int64_t n, const
 int umma_selftest(const float* A, const float* Bt, int N, int K, int mode, float* D,
                   int* status_host, cudaStream_t s) {
   ibc_handle* h = nullptr;
+  // modes 50+: the same probe as mode - 20 on every SM at once (chip-wide rate)
+  int grid = 1;
+  if (mode >= 50) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&grid, cudaDevAttrMultiProcessorCount, dev);
+    mode -= 20;
+  }
   if (N < 16 || N > 256 || (N % 16) || K < 8 || K > 128 || (K % 8) ||
-      ((mode == 1 || mode == 21 || mode == 23 || mode == 24) && (K % 32)))
+      ((mode == 1 || mode == 21 || mode == 23 || mode == 24 || mode == 31 || mode == 33 || mode == 35 || mode == 37 || mode == 41) && (K % 32)))
     IBC_FAIL(h, IBC_ERR_INVALID, "umma_selftest: need 16<=N<=256 (x16), 8<=K<=128 (x8; x32 for mode 1)");
   float* bp = nullptr;
   int* st = nullptr;
@@ -724,10 +934,10 @@ int umma_selftest(const float* A, const float* Bt, int N, int K, int mode, float
   IBC_CUDA(h, cudaMemsetAsync(st, 0, sizeof(int), s));
   pack_rows_kernel<<<(N * K + 255) / 256, 256, 0, s>>>(Bt, N, K, mode == 2 ? 1 : (mode == 3 ? 2 : 0), bp);
   count_launch();
-  const size_t smem = (size_t)128 * K * 4 + (size_t)N * K * 4 + 64;
+  const size_t smem = (size_t)128 * K * 4 + (size_t)N * K * 4 + 64 + ((mode >= 34 && mode <= 37) || mode >= 40 ? 66 * 1024 : 0);
   IBC_CUDA(h, cudaFuncSetAttribute(umma_selftest_kernel,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  umma_selftest_kernel<<<1, 160, smem, s>>>(A, bp, N, K, mode, D, st);
+  umma_selftest_kernel<<<grid, 160, smem, s>>>(A, bp, N, K, mode, D, st);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);

@@ -1,0 +1,689 @@
+// Width-128 MLPEBM forward and reverse chain with the activations held in
+// TENSOR MEMORY end to end (tcgen05 "TS" form: A operand from TMEM, B = weights
+// from shared memory) -- networks/layers/resnet.py:135-153 and its reverse,
+// ibc/agents/mcmc.py:161-191.
+//
+// Why (measured on B200 with scripts/mma_rate.py and scripts/timeline.py): a
+// 128x128x8 kind::tf32 MMA runs at its 64-cycle floor from either operand
+// source and under any concurrent shared-memory / tensor-memory / bulk-copy
+// traffic, so the tensor pipe is never the problem; what limited the
+// shared-memory-operand kernel (mlp_umma.cu, still used for width 256) was that
+// two 64 KB activation tiles left room for only one layer of weights in the
+// ring, so every layer waited ~800 cycles for its first slice (a 16 KB bulk
+// copy takes ~780 cycles round trip from L2).  Here the activations never touch
+// shared memory:
+//   * two TMEM regions X, Y (128 columns each) per 128-row tile alternate as
+//     "A operand of this layer" / "accumulator of this layer";
+//   * the epilogue rewrites an accumulator IN PLACE into the next A operand
+//     (tcgen05.ld -> ReLU/round -> tcgen05.st, lane-local);
+//   * the residual stream h (forward) / its gradient g (reverse) lives in the
+//     epilogue thread's registers (128 fp32 per row);
+//   * shared memory holds the weight ring (up to 13 x 16 KB K-slices = three
+//     layers of prefetch), the per-layer bias operands (2 KB each; the bias is
+//     added by one extra K = 8 MMA against a constant (1, 1, 0, ...) tile) and
+//     nothing else.
+// Two tiles per CTA (8 epilogue warps) overlap one tile's MMAs with the other's
+// epilogue; with few rows (policy inference) a CTA takes a single tile so that
+// more SMs are busy.  The MMA and producer warps stay converged and issue under
+// elect.sync (umma::elect_one).
+#include <stdlib.h>
+
+#include <vector>
+
+#include "mlp.cuh"
+#include "umma.cuh"
+#include "umma_pack.cuh"
+
+namespace ibc {
+
+using namespace umma;
+
+namespace {
+
+constexpr int kW = 128;
+constexpr int kNT = 2;
+constexpr int kLayerWBytes = kW * kW * 4;               // one layer's operand: 64 KB
+constexpr int kBiasBytes = 8 * kW * 4;                   // its K = 8 bias slice: 4 KB
+constexpr int kKSteps = kW / 8;                          // 16 MMAs (K = 8) per layer
+// 8 epilogue warps + one full service warpgroup (producer, one MMA issuer per
+// tile, one idle warp) so that setmaxnreg can move registers from the service
+// warpgroup to the epilogue warpgroups: each epilogue thread holds a 128-float
+// residual row.
+constexpr int kThreads = (4 * kNT + 4) * 32;
+constexpr int kEpilogueRegs = 224, kServiceRegs = 40;
+// The weight ring holds whole layers: one bulk copy and one full/empty barrier
+// pair per layer.  (With 16 KB slices the producer, which does not get past an
+// mbarrier wait while its previous bulk copy is in flight, could not stay ahead
+// of the tensor pipe.)
+constexpr int kRing = 3;
+constexpr int kDbgWords = 1024;
+
+// forward: ring (3 x 68 KB) | step-0 operand (KP x W) | ones tile (4 KB) | we, be | barriers
+// reverse: ring (3 x 64 KB) | we | dwe accumulator | barriers
+inline size_t smem_bytes(bool forward, int KP) {
+  const size_t ring = (size_t)kRing * (kLayerWBytes + (forward ? kBiasBytes : 0));
+  const size_t tail = forward ? (size_t)KP * kW * 4 + 4096 + (kW + 4) * 4 : 2 * (size_t)kW * 4;
+  return ring + tail + (size_t)(2 * kNT + 2 * kRing + 1) * 8 + 64;
+}
+
+// Tensor-pipe token.  Two issuer threads sharing the pipe 1:1 finish their layers
+// together, which puts both tiles' epilogues (and then both MMA phases) in lockstep
+// and loses the MMA/epilogue overlap; handing the pipe over a layer at a time keeps
+// the tiles half a period apart.
+__device__ __forceinline__ void pipe_acquire(int* lock, volatile int* abort_flag) {
+  while (atomicCAS(lock, 0, 1) != 0) {
+    if (*abort_flag) return;
+    __nanosleep(32);
+  }
+}
+__device__ __forceinline__ void pipe_release(int* lock) { atomicExch(lock, 0); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------
+struct FwdTmemParams {
+  const float* act;      // [R, A]
+  const float* hp;       // [B, W]  obs . Wp[:O] + bp
+  const float* packed;
+  float* E;              // [R]
+  float* xa_save;        // nullable, 2nb+1 slots per tile (training)
+  uint32_t* mask_save;   // nullable, ReLU masks of the 2nb W x W layers
+  int64_t R, n_per_obs;
+  int nb, A, KP, nt, num_groups;
+  int64_t off_fwd_p, off_fwd_lb, off_we;
+  int* status;
+  long long* dbg;
+  int dbg_mode;   // timeline experiments: 1 = epilogue does no work (MMA chain alone)
+};
+
+template <bool kSave>
+__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tmem_kernel(FwdTmemParams p) {
+  using TT = TrainTile<kW>;
+  constexpr int W = kW;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int nsteps = 2 * p.nb + 1;
+  constexpr int kLayerBytes = kLayerWBytes + kBiasBytes;
+  unsigned char* ring = smem;                                         // [kRing][68 KB]
+  unsigned char* p0_buf = ring + (size_t)kRing * kLayerBytes;         // step-0 operand [KP/4][W][4]
+  float4* ones_tile = reinterpret_cast<float4*>(p0_buf + (size_t)p.KP * W * 4);   // [2][128]
+  float* we = reinterpret_cast<float*>(ones_tile + 256);              // we[W], be
+  uint64_t* bars = reinterpret_cast<uint64_t*>(we + W + 4);
+  uint64_t* a_ready = bars;                    // [kNT]
+  uint64_t* d_ready = bars + kNT;              // [kNT]
+  uint64_t* w_full = bars + 2 * kNT;           // [kRing]
+  uint64_t* w_empty = w_full + kRing;          // [kRing]
+  uint64_t* p0_full = w_empty + kRing;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p0_full + 1);
+  __shared__ int s_abort;
+  __shared__ int s_pipe;    // tensor-pipe token: one tile's layer is issued at a time
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nt = p.nt;
+
+  if (tid == 0) {
+    s_abort = 0;
+    s_pipe = 0;
+    for (int t = 0; t < kNT; ++t) { mbar_init(&a_ready[t], 128); mbar_init(&d_ready[t], 1); }
+    for (int s = 0; s < kRing; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], nt); }
+    mbar_init(p0_full, 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < 256; i += kThreads)
+    ones_tile[i] = (i < 128) ? make_float4(1.f, 1.f, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < W + 4; i += kThreads) we[i] = p.packed[p.off_we + i];
+  fence_proxy_async_smem();
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  volatile int* abort_flag = &s_abort;
+  const float be = we[W];
+
+  if (warp < 4 * kNT) {
+    // ===================== epilogue warpgroup t ==============================
+    setmaxnreg_inc<kEpilogueRegs>();
+    const int t = warp >> 2;
+    if (t < nt) {
+      const int row = tid & 127;
+      const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+      const uint32_t col_x = tmem_base + lane_off + (uint32_t)(t * 2 * W);
+      const uint32_t col_y = col_x + W;
+      uint32_t ph_d = 0;
+      for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+        const int64_t tile_id = (int64_t)g * nt + t;
+        const int64_t r = tile_id * 128 + row;
+        const bool valid = r < p.R;
+        {   // step-0 operand: this row's action (zero padded) into X[:, 0:32)
+          uint32_t v[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            v[k] = (valid && k < p.A) ? tf32_rn_bits(__float_as_uint(p.act[r * p.A + k])) : 0u;
+          tmem_st32(col_x, v);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&a_ready[t]);
+        }
+        // residual stream of this row, seeded with the hoisted observation projection
+        float h[W];
+        {
+          const float4* hp4 = reinterpret_cast<const float4*>(
+              p.hp + (valid ? (r / p.n_per_obs) : 0) * W);
+#pragma unroll
+          for (int c = 0; c < W / 4; ++c) {
+            const float4 v = hp4[c];
+            h[c * 4 + 0] = v.x; h[c * 4 + 1] = v.y; h[c * 4 + 2] = v.z; h[c * 4 + 3] = v.w;
+          }
+        }
+#pragma unroll 1
+        for (int i = 0; i < nsteps; ++i) {
+          float4* g_slot = (kSave && p.xa_save) ? reinterpret_cast<float4*>(
+              p.xa_save + TT::slot_base(tile_id, nsteps, i)) : nullptr;
+          uint32_t* m_slot = (kSave && p.mask_save && i < nsteps - 1)
+              ? p.mask_save + TT::mask_index(tile_id, p.nb, i, row) : nullptr;
+          mbar_wait(&d_ready[t], ph_d, abort_flag, p.status, 100 + i);
+          ph_d ^= 1;
+          tc_fence_after();
+          const bool stamp = p.dbg && blockIdx.x == 0 && g == (int)blockIdx.x && row == 0 && i < 64;
+          if (stamp) p.dbg[(i * kNT + t) * 5 + 0] = clock64();
+          const bool last = (i == nsteps - 1);
+          uint32_t mb[W / 32];
+          if (p.dbg_mode & 1) {
+            if (!last) { tc_fence_before(); mbar_arrive(&a_ready[t]); }
+            continue;
+          }
+          // TMEM loads run one 32-column chunk ahead of the arithmetic (two register
+          // buffers): under MMA load a tcgen05.ld round trip is ~300 cycles, and four
+          // of them back to back were the whole epilogue.
+          auto save_chunk = [&](int c32, const uint32_t (&v)[32]) {
+            if (g_slot) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                g_slot[TT::chunk_f4(row, c32 * 8 + q)] =
+                    make_float4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]),
+                                __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+            }
+          };
+          if ((i & 1) == 0) {
+            // even step: the accumulator (Y after the action projection, X after a
+            // second Dense) is this block's increment of the residual stream
+            const uint32_t col_d = (i == 0) ? col_y : col_x;
+            float e = 0.f;
+            auto chunk = [&](int c32, uint32_t (&v)[32]) {
+              uint32_t bits = 0;
+#pragma unroll
+              for (int q = 0; q < 32; ++q) {
+                const float x = h[c32 * 32 + q] + __uint_as_float(v[q]);
+                h[c32 * 32 + q] = x;
+                if (last) {
+                  e = fmaf(x, we[c32 * 32 + q], e);
+                  v[q] = __float_as_uint(x);
+                } else {
+                  v[q] = relu_tf32_bits(__float_as_uint(x));
+                  if (kSave) bits |= (x > 0.f ? 1u : 0u) << q;
+                }
+              }
+              mb[c32] = bits;
+              if (!last) tmem_st32(col_x + c32 * 32, v);
+              save_chunk(c32, v);
+            };
+            uint32_t va[32], vb[32];
+            tmem_ld32(col_d, va);
+            tmem_ld_wait(va); tmem_ld32(col_d + 32, vb); chunk(0, va);
+            tmem_ld_wait(vb); tmem_ld32(col_d + 64, va); chunk(1, vb);
+            tmem_ld_wait(va); tmem_ld32(col_d + 96, vb); chunk(2, va);
+            tmem_ld_wait(vb); chunk(3, vb);
+            if (last && valid) p.E[r] = e + be;          // Dense(1), mlp_ebm.py:91-94
+          } else {
+            // odd step: Y holds relu(h) . W1 + b1 -> ReLU, round, in place: the A
+            // operand of the second Dense
+            auto chunk = [&](int c32, uint32_t (&v)[32]) {
+              uint32_t bits = 0;
+#pragma unroll
+              for (int q = 0; q < 32; ++q) {
+                if (kSave) bits |= (__uint_as_float(v[q]) > 0.f ? 1u : 0u) << q;
+                v[q] = relu_tf32_bits(v[q]);
+              }
+              mb[c32] = bits;
+              tmem_st32(col_y + c32 * 32, v);
+              save_chunk(c32, v);
+            };
+            uint32_t va[32], vb[32];
+            tmem_ld32(col_y, va);
+            tmem_ld_wait(va); tmem_ld32(col_y + 32, vb); chunk(0, va);
+            tmem_ld_wait(vb); tmem_ld32(col_y + 64, va); chunk(1, vb);
+            tmem_ld_wait(va); tmem_ld32(col_y + 96, vb); chunk(2, va);
+            tmem_ld_wait(vb); chunk(3, vb);
+          }
+          if (m_slot) *reinterpret_cast<uint4*>(m_slot) = make_uint4(mb[0], mb[1], mb[2], mb[3]);
+          if (stamp) p.dbg[(i * kNT + t) * 5 + 1] = clock64();
+          if (!last) {
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&a_ready[t]);
+          } else {
+            tc_fence_before();
+          }
+          if (stamp) p.dbg[(i * kNT + t) * 5 + 2] = clock64();
+        }
+      }
+    }
+  } else if (warp == 4 * kNT) {
+    // ===================== producer: one bulk copy per layer ==================
+    setmaxnreg_dec<kServiceRegs>();
+    if (elect_one()) {    // the action rows of Wp stay resident for the whole kernel
+      mbar_arrive_expect_tx(p0_full, (uint32_t)(W * p.KP * 4));
+      bulk_g2s(p0_buf, p.packed + p.off_fwd_p, (uint32_t)(W * p.KP * 4), p0_full);
+    }
+    __syncwarp();
+    uint32_t q = 0;
+    for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+      for (int i = 1; i < nsteps; ++i, ++q) {
+        const int slot = q % kRing;
+        const uint32_t ph = (q / kRing) & 1;
+        if (elect_one()) {
+          mbar_wait(&w_empty[slot], ph ^ 1, abort_flag, p.status, 200 + i);
+          mbar_arrive_expect_tx(&w_full[slot], (uint32_t)kLayerBytes);
+          bulk_g2s(ring + (size_t)slot * kLayerBytes,
+                   p.packed + p.off_fwd_lb + (int64_t)(i - 1) * (kLayerBytes / 4),
+                   (uint32_t)kLayerBytes, &w_full[slot]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4 * kNT + 1 + nt) {
+    setmaxnreg_dec<kServiceRegs>();     // idle members of the service warpgroup
+  } else {
+    // ===================== MMA issuer of tile t ================================
+    // One issuer warp per tile: the thread that issued a tile's MMAs does not get
+    // past its next mbarrier wait until they have drained (~400 cycles, measured),
+    // so a single issuer serialises the two tiles and idles the tensor pipe between
+    // them; with two issuers the other tile's MMAs are already queued.
+    setmaxnreg_dec<kServiceRegs>();
+    const int t = warp - (4 * kNT + 1);
+    const uint32_t idesc = idesc_tf32(128, W);
+    const uint32_t a_lbo = 128 * 16, b_lbo = W * 16, sbo = 128;
+    constexpr uint32_t b_step16 = (2 * W * 16) >> 4;
+    const uint64_t ones_desc = smem_desc(smem_u32(ones_tile), a_lbo, sbo);
+    const uint32_t col_x = tmem_base + (uint32_t)(t * 2 * W);
+    const uint32_t col_y = col_x + W;
+    uint32_t q = 0;
+    uint32_t ph_a = 0;
+    for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+      for (int i = 0; i < nsteps; ++i) {
+        const bool mstamp = p.dbg && blockIdx.x == 0 && g == (int)blockIdx.x && i < 64;
+        // step 0 and odd steps read X and write Y; even steps >= 2 read Y, write X
+        const bool x_to_y = (i == 0) || (i & 1);
+        const uint32_t a_tmem = x_to_y ? col_x : col_y;
+        const uint32_t d_tmem = x_to_y ? col_y : col_x;
+        const uint32_t slot = q % kRing;
+        if (elect_one()) {
+          mbar_wait(&a_ready[t], ph_a, abort_flag, p.status, 300 + i);
+          // The layer's weights before the first MMA: an mbarrier wait issued behind
+          // tcgen05.mma instructions does not return until they have (nearly) drained
+          // (~100 cycles each, measured).
+          if (i == 0) mbar_wait(p0_full, 0, abort_flag, p.status, 400);
+          else mbar_wait(&w_full[slot], (q / kRing) & 1, abort_flag, p.status, 400 + i);
+          tc_fence_after();
+          pipe_acquire(&s_pipe, abort_flag);
+          if (mstamp) p.dbg[(i * kNT + t) * 5 + 3] = clock64();
+          if (i == 0) {
+            const uint64_t b_desc0 = smem_desc(smem_u32(p0_buf), b_lbo, sbo);
+            for (int ks = 0; ks < p.KP / 8; ++ks)
+              mma_tf32_ts(d_tmem, a_tmem + (uint32_t)(ks * 8), b_desc0 + (uint64_t)(ks * b_step16),
+                          idesc, (uint32_t)(ks > 0));
+          } else {
+            const uint32_t layer = smem_u32(ring + (size_t)slot * kLayerBytes);
+            mma_tf32_ts_steps<kKSteps>(d_tmem, a_tmem, smem_desc(layer, b_lbo, sbo), b_step16,
+                                       idesc, 0u);
+            // + bias: (1, 1, 0, ...) . (hi, lo, 0, ...)^T, the slice behind the weights
+            mma_tf32_ss(d_tmem, ones_desc, smem_desc(layer + kLayerWBytes, b_lbo, sbo), idesc, 1u);
+            mma_commit(&w_empty[slot]);     // free once every tile's issuer has arrived
+          }
+          mma_commit(&d_ready[t]);
+          pipe_release(&s_pipe);
+          if (mstamp) p.dbg[(i * kNT + t) * 5 + 4] = clock64();
+        }
+        __syncwarp();
+        ph_a ^= 1;
+        if (i > 0) ++q;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------
+// reverse chain
+// ---------------------------------------------------------------------------
+struct BwdTmemParams {
+  const float* dE;            // [R]; null = ones (dE/dact of the plain energy)
+  const float* xa_save;       // forward tiles; only slot 2nb (h_nb) is read, for dwe
+  const uint32_t* mask_save;  // ReLU masks of the 2nb layers
+  float* gy_save;             // nullable: output-gradient tiles, 2nb slots (training)
+  float* g0;                  // [R, W] row-major gradient of the first Dense output
+  const float* packed;
+  int64_t off_rev_l, off_we;
+  float* dwe;                 // nullable [W], atomics
+  int64_t R;
+  int nb, nt, num_groups;
+  int* status;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams p) {
+  using TT = TrainTile<kW>;
+  constexpr int W = kW;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* ring = smem;                                         // [kRing][64 KB]
+  float* we = reinterpret_cast<float*>(ring + (size_t)kRing * kLayerWBytes);
+  float* dwe_acc = we + W;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dwe_acc + W);
+  uint64_t* a_ready = bars;
+  uint64_t* d_ready = bars + kNT;
+  uint64_t* w_full = bars + 2 * kNT;
+  uint64_t* w_empty = w_full + kRing;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + kRing + 1);
+  __shared__ int s_abort;
+  __shared__ int s_pipe;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nt = p.nt;
+  const int nsteps = 2 * p.nb;
+  const int xa_slots = 2 * p.nb + 1, gy_slots = 2 * p.nb;
+
+  if (tid == 0) {
+    s_abort = 0;
+    s_pipe = 0;
+    for (int t = 0; t < kNT; ++t) { mbar_init(&a_ready[t], 128); mbar_init(&d_ready[t], 1); }
+    for (int s = 0; s < kRing; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], nt); }
+    fence_mbar_init();
+  }
+  for (int i = tid; i < W; i += kThreads) { we[i] = p.packed[p.off_we + i]; dwe_acc[i] = 0.f; }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  volatile int* abort_flag = &s_abort;
+
+  if (warp < 4 * kNT) {
+    // ===================== epilogue warpgroup t ==============================
+    setmaxnreg_inc<kEpilogueRegs>();
+    const int t = warp >> 2;
+    if (t < nt) {
+      const int row = tid & 127;
+      const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+      const uint32_t col_x = tmem_base + lane_off + (uint32_t)(t * 2 * W);
+      const uint32_t col_y = col_x + W;
+      uint32_t ph_d = 0;
+      for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+        const int64_t tile_id = (int64_t)g * nt + t;
+        const int64_t r = tile_id * 128 + row;
+        const bool valid = r < p.R;
+        const float de = valid ? (p.dE ? p.dE[r] : 1.0f) : 0.f;
+        // masks of the topmost layer now, every other layer one step ahead
+        uint4 mnext = *reinterpret_cast<const uint4*>(
+            p.mask_save + TT::mask_index(tile_id, p.nb, nsteps - 1, row));
+        float gr[W];                        // gradient of the residual stream of this row
+        {
+          // g_top = dE (x) we ; dwe += h_nb^T dE (h_nb = the forward's last slot)
+          const float4* hn = p.dwe ? reinterpret_cast<const float4*>(
+              p.xa_save + TT::slot_base(tile_id, xa_slots, 2 * p.nb)) : nullptr;
+          float4* gy_top = p.gy_save ? reinterpret_cast<float4*>(
+              p.gy_save + TT::slot_base(tile_id, gy_slots, 2 * p.nb - 1)) : nullptr;
+#pragma unroll
+          for (int c32 = 0; c32 < W / 32; ++c32) {
+            uint32_t v[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int c = c32 * 8 + q;
+              const float4 w4 = *reinterpret_cast<const float4*>(we + c * 4);
+              const float4 g4 = make_float4(de * w4.x, de * w4.y, de * w4.z, de * w4.w);
+              gr[c * 4 + 0] = g4.x; gr[c * 4 + 1] = g4.y; gr[c * 4 + 2] = g4.z; gr[c * 4 + 3] = g4.w;
+              v[q * 4 + 0] = tf32_rn_bits(__float_as_uint(g4.x));
+              v[q * 4 + 1] = tf32_rn_bits(__float_as_uint(g4.y));
+              v[q * 4 + 2] = tf32_rn_bits(__float_as_uint(g4.z));
+              v[q * 4 + 3] = tf32_rn_bits(__float_as_uint(g4.w));
+              if (gy_top) gy_top[TT::chunk_f4(row, c)] = g4;   // fp32: exact bias sums
+              if (hn) {
+                const float4 h4 = hn[TT::chunk_f4(row, c)];
+                const float s0 = warp_sum(de * h4.x), s1 = warp_sum(de * h4.y);
+                const float s2 = warp_sum(de * h4.z), s3 = warp_sum(de * h4.w);
+                if (lane == 0) {
+                  atomicAdd(&dwe_acc[c * 4 + 0], s0); atomicAdd(&dwe_acc[c * 4 + 1], s1);
+                  atomicAdd(&dwe_acc[c * 4 + 2], s2); atomicAdd(&dwe_acc[c * 4 + 3], s3);
+                }
+              }
+            }
+            tmem_st32(col_x + c32 * 32, v);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&a_ready[t]);
+        }
+#pragma unroll 1
+        for (int s = 0; s < nsteps; ++s) {
+          const int i = nsteps - s;                   // forward layer index 2nb .. 1
+          const bool odd = (i & 1) != 0;              // W1 layer: result adds onto g
+          const bool last = (i == 1);
+          float4* gy_out = (last || !p.gy_save) ? nullptr : reinterpret_cast<float4*>(
+              p.gy_save + TT::slot_base(tile_id, gy_slots, i - 2));
+          const uint32_t mbits[4] = {mnext.x, mnext.y, mnext.z, mnext.w};
+          if (!last)
+            mnext = *reinterpret_cast<const uint4*>(
+                p.mask_save + TT::mask_index(tile_id, p.nb, i - 2, row));
+          mbar_wait(&d_ready[t], ph_d, abort_flag, p.status, 500 + s);
+          ph_d ^= 1;
+          tc_fence_after();
+          // even layer (W2_j): D = Y, masked in place -> A operand of the W1_j step
+          // odd  layer (W1_j): D = X, g += masked D -> A operand of the next W2 step
+          const uint32_t col_d = odd ? col_x : col_y;
+          auto chunk = [&](int c32, uint32_t (&v)[32]) {
+            const uint32_t bits = mbits[c32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int c = c32 * 8 + q;
+              float4 o;
+              o.x = (bits >> (q * 4 + 0)) & 1u ? __uint_as_float(v[q * 4 + 0]) : 0.f;
+              o.y = (bits >> (q * 4 + 1)) & 1u ? __uint_as_float(v[q * 4 + 1]) : 0.f;
+              o.z = (bits >> (q * 4 + 2)) & 1u ? __uint_as_float(v[q * 4 + 2]) : 0.f;
+              o.w = (bits >> (q * 4 + 3)) & 1u ? __uint_as_float(v[q * 4 + 3]) : 0.f;
+              if (odd) {
+                o.x += gr[c * 4 + 0]; o.y += gr[c * 4 + 1]; o.z += gr[c * 4 + 2]; o.w += gr[c * 4 + 3];
+                gr[c * 4 + 0] = o.x; gr[c * 4 + 1] = o.y; gr[c * 4 + 2] = o.z; gr[c * 4 + 3] = o.w;
+              }
+              if (!last) {
+                if (gy_out) gy_out[TT::chunk_f4(row, c)] = o;   // fp32: exact bias sums
+                v[q * 4 + 0] = tf32_rn_bits(__float_as_uint(o.x));
+                v[q * 4 + 1] = tf32_rn_bits(__float_as_uint(o.y));
+                v[q * 4 + 2] = tf32_rn_bits(__float_as_uint(o.z));
+                v[q * 4 + 3] = tf32_rn_bits(__float_as_uint(o.w));
+              } else if (valid) {
+                *reinterpret_cast<float4*>(p.g0 + r * W + c * 4) = o;
+              }
+            }
+            if (!last) tmem_st32(col_d + c32 * 32, v);
+          };
+          // TMEM loads one chunk ahead of the arithmetic (see the forward kernel)
+          uint32_t va[32], vb[32];
+          tmem_ld32(col_d, va);
+          tmem_ld_wait(va); tmem_ld32(col_d + 32, vb); chunk(0, va);
+          tmem_ld_wait(vb); tmem_ld32(col_d + 64, va); chunk(1, vb);
+          tmem_ld_wait(va); tmem_ld32(col_d + 96, vb); chunk(2, va);
+          tmem_ld_wait(vb); chunk(3, vb);
+          if (!last) {
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&a_ready[t]);
+          } else {
+            tc_fence_before();
+          }
+        }
+      }
+    }
+  } else if (warp == 4 * kNT) {
+    // ===================== producer: one bulk copy per layer ==================
+    setmaxnreg_dec<kServiceRegs>();
+    uint32_t q = 0;
+    for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+      for (int s = 0; s < nsteps; ++s, ++q) {
+        const int slot = q % kRing;
+        const uint32_t ph = (q / kRing) & 1;
+        if (elect_one()) {
+          mbar_wait(&w_empty[slot], ph ^ 1, abort_flag, p.status, 600 + s);
+          mbar_arrive_expect_tx(&w_full[slot], (uint32_t)kLayerWBytes);
+          bulk_g2s(ring + (size_t)slot * kLayerWBytes, p.packed + p.off_rev_l + (int64_t)s * W * W,
+                   (uint32_t)kLayerWBytes, &w_full[slot]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4 * kNT + 1 + nt) {
+    setmaxnreg_dec<kServiceRegs>();     // idle members of the service warpgroup
+  } else {
+    // ===================== MMA issuer of tile t (see the forward kernel) =======
+    setmaxnreg_dec<kServiceRegs>();
+    const int t = warp - (4 * kNT + 1);
+    const uint32_t idesc = idesc_tf32(128, W);
+    const uint32_t b_lbo = W * 16, sbo = 128;
+    constexpr uint32_t b_step16 = (2 * W * 16) >> 4;
+    const uint32_t col_x = tmem_base + (uint32_t)(t * 2 * W);
+    const uint32_t col_y = col_x + W;
+    uint32_t q = 0;
+    uint32_t ph_a = 0;
+    for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+      for (int s = 0; s < nsteps; ++s, ++q) {
+        const int i = nsteps - s;
+        // even layer: A = X (g), D = Y ; odd layer: A = Y (u), D = X
+        const uint32_t a_tmem = (i & 1) ? col_y : col_x;
+        const uint32_t d_tmem = (i & 1) ? col_x : col_y;
+        const uint32_t slot = q % kRing;
+        if (elect_one()) {
+          mbar_wait(&a_ready[t], ph_a, abort_flag, p.status, 700 + s);
+          mbar_wait(&w_full[slot], (q / kRing) & 1, abort_flag, p.status, 800 + s);
+          tc_fence_after();
+          pipe_acquire(&s_pipe, abort_flag);
+          mma_tf32_ts_steps<kKSteps>(
+              d_tmem, a_tmem, smem_desc(smem_u32(ring + (size_t)slot * kLayerWBytes), b_lbo, sbo),
+              b_step16, idesc, 0u);
+          mma_commit(&w_empty[slot]);
+          mma_commit(&d_ready[t]);
+          pipe_release(&s_pipe);
+        }
+        __syncwarp();
+        ph_a ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  if (p.dwe)
+    for (int i = tid; i < W; i += kThreads) atomicAdd(p.dwe + i, dwe_acc[i]);
+}
+
+// With few rows one tile per CTA keeps more SMs busy than two.
+inline int choose_nt(int64_t R, int sm_count) {
+  const int64_t tiles = (R + 127) / 128;
+  return tiles <= sm_count ? 1 : 2;
+}
+
+template <typename K>
+int raise_smem(ibc_handle* h, K kernel) {
+  IBC_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024 - 1024));
+  return IBC_OK;
+}
+
+}  // namespace
+
+bool tmem_path_supported(const Layout& L) {
+  return L.W == kW && L.A <= 32 && smem_bytes(true, round_up(L.A, 8)) <= 227 * 1024 - 1024;
+}
+
+int tmem_tiles_per_cta(ibc_handle* h, int64_t R) { return choose_nt(R, h->sm_count); }
+
+int tmem_forward(ibc_handle* h, const float* act, int64_t R, int64_t n, const float* hp, float* E,
+                 float* xa_save, uint32_t* mask_save, cudaStream_t s) {
+  const Layout& L = h->L;
+  const PackedLayout pl = make_packed_layout(L);
+  const bool saving = xa_save || mask_save;
+  FwdTmemParams p;
+  p.act = act; p.hp = hp; p.packed = h->packed; p.E = E; p.xa_save = xa_save;
+  p.mask_save = mask_save;
+  p.R = R; p.n_per_obs = n; p.nb = L.nb; p.A = L.A; p.KP = pl.KP;
+  p.nt = tmem_tiles_per_cta(h, R);
+  p.num_groups = (int)((R + 128 * p.nt - 1) / (128 * p.nt));
+  p.off_fwd_p = pl.fwd_p; p.off_fwd_lb = pl.fwd_lb;
+  p.off_we = pl.vecs + (int64_t)(2 * L.nb + 1) * L.W;
+  p.status = h->dev_status;
+  p.dbg = nullptr;
+  p.dbg_mode = getenv("IBC_DBG_MODE") ? atoi(getenv("IBC_DBG_MODE")) : 0;
+  static const bool want_dbg = getenv("IBC_DBG_TIMELINE") != nullptr;
+  if (want_dbg) {
+    IBC_CUDA(h, cudaMalloc((void**)&p.dbg, kDbgWords * sizeof(long long)));
+    IBC_CUDA(h, cudaMemsetAsync(p.dbg, 0, kDbgWords * sizeof(long long), s));
+  }
+  static bool attr = false;
+  if (!attr) {
+    IBC_TRY(raise_smem(h, mlp_fwd_tmem_kernel<true>));
+    IBC_TRY(raise_smem(h, mlp_fwd_tmem_kernel<false>));
+    attr = true;
+  }
+  const int grid = p.num_groups < h->sm_count ? p.num_groups : h->sm_count;
+  const size_t smem = smem_bytes(true, p.KP);
+  if (saving) mlp_fwd_tmem_kernel<true><<<grid, kThreads, smem, s>>>(p);
+  else mlp_fwd_tmem_kernel<false><<<grid, kThreads, smem, s>>>(p);
+  IBC_LAUNCH_CHECK(h);
+  if (p.dbg) {
+    cudaStreamSynchronize(s);
+    std::vector<long long> hb(kDbgWords);
+    cudaMemcpy(hb.data(), p.dbg, hb.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(p.dbg);
+    const long long t0 = hb[3];
+    fprintf(stderr, "[ibc timeline tmem nt=%d] step tile | mma_start mma_issued | epi_start epi_done arrived\n",
+            p.nt);
+    for (int i = 0; i < 2 * L.nb + 1 && i < 64; ++i)
+      for (int t = 0; t < p.nt; ++t) {
+        const long long* e = &hb[(i * kNT + t) * 5];
+        fprintf(stderr, "[ibc timeline tmem] %3d %d | %8lld %8lld | %8lld %8lld %8lld\n", i, t,
+                e[3] - t0, e[4] - t0, e[0] - t0, e[1] - t0, e[2] - t0);
+      }
+  }
+  return IBC_OK;
+}
+
+int tmem_reverse(ibc_handle* h, const float* dE, int64_t R, const float* xa_save,
+                 const uint32_t* mask_save, float* gy_save, float* g0, float* dwe,
+                 cudaStream_t s) {
+  const Layout& L = h->L;
+  const PackedLayout pl = make_packed_layout(L);
+  BwdTmemParams p;
+  p.dE = dE; p.xa_save = xa_save; p.mask_save = mask_save; p.gy_save = gy_save; p.g0 = g0;
+  p.packed = h->packed;
+  p.off_rev_l = pl.rev_l; p.off_we = pl.vecs + (int64_t)(2 * L.nb + 1) * L.W;
+  p.dwe = dwe; p.R = R; p.nb = L.nb; p.nt = tmem_tiles_per_cta(h, R);
+  p.num_groups = (int)((R + 128 * p.nt - 1) / (128 * p.nt));
+  p.status = h->dev_status;
+  static bool attr = false;
+  if (!attr) {
+    IBC_TRY(raise_smem(h, mlp_bwd_tmem_kernel));
+    attr = true;
+  }
+  const int grid = p.num_groups < h->sm_count ? p.num_groups : h->sm_count;
+  mlp_bwd_tmem_kernel<<<grid, kThreads, smem_bytes(false, 0), s>>>(p);
+  IBC_LAUNCH_CHECK(h);
+  return IBC_OK;
+}
+
+}  // namespace ibc

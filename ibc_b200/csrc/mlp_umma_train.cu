@@ -540,6 +540,9 @@ int umma_reverse(ibc_handle* h, const float* dE, int64_t R, const float* xa_save
                  cudaStream_t s) {
   if (dwe && !xa_save) IBC_FAIL(h, IBC_ERR_INVALID, "umma_reverse: dwe needs the saved tiles");
   const Layout& L = h->L;
+  static const bool force_smem = getenv("IBC_SMEM_OPERANDS") != nullptr;
+  if (!force_smem && tmem_path_supported(L))
+    return tmem_reverse(h, dE, R, xa_save, mask_save, gy_save, g0, dwe, s);
   const PackedLayout pl = make_packed_layout(L);
   BwdParams bp;
   bp.dE = dE; bp.xa_save = xa_save; bp.mask_save = mask_save; bp.gy_save = gy_save; bp.g0 = g0; bp.packed = h->packed;

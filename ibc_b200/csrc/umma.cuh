@@ -96,6 +96,15 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// The same wait, with the loaded registers threaded through the statement so that
+// no use of them can be scheduled above it (needed once loads are pipelined and
+// the wait is no longer right behind its load).
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -164,6 +173,32 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
 
 constexpr uint32_t kIdescAMajorMN = 1u << 15;   // A operand is M-major (transposed)
 constexpr uint32_t kIdescBMajorMN = 1u << 16;   // B operand is N-major (transposed)
+
+// One lane of a fully converged warp.  Issuing tcgen05.mma / commit / bulk copies
+// under elect.sync from warp-uniform control flow lets the compiler keep the
+// descriptors in uniform registers; issuing from an `if (lane == 0)` region
+// makes it wrap every instruction in an R2UR + vote loop (measured 90-100
+// cycles per MMA issued instead of the 64-cycle pipe rate).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// Register re-allocation between warpgroups (all 4 warps of a warpgroup execute
+// it): service warps give registers up, epilogue warpgroups take them.
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 
 // D[tmem] (+)= A[smem] . B[smem]^T   (single elected thread)
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,

@@ -16,6 +16,15 @@ __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m *
 __device__ __forceinline__ float tf32_rn(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
+// relu + round-to-nearest-tf32 of an accumulator in ONE integer instruction
+// (VIADDMNMX): max(bits + 0x1000, 0).  The low 13 bits are left for the tensor
+// core to truncate, which completes the rounding; negative inputs (sign bit =
+// negative integer) clamp to +0.  The result is only meant to be an MMA operand.
+__device__ __forceinline__ uint32_t relu_tf32_bits(uint32_t x) {
+  return (uint32_t)__viaddmax_s32((int)x, 0x1000, 0);
+}
+// round-to-nearest-tf32 of a signed value, low bits left for the MMA to truncate
+__device__ __forceinline__ uint32_t tf32_rn_bits(uint32_t x) { return x + 0x1000u; }
 __device__ __forceinline__ float4 tf32_rn4(float4 v) {
   return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
 }
@@ -30,6 +39,8 @@ struct PackedLayout {
   int64_t vecs;      // [(2nb+1)][W] epilogue bias vectors, then we[W], be, pad
   int64_t raw;       // [(2nb+1)][W] per-step raw biases: zeros, b1_0, b2_0, b1_1, ...
   int64_t fwd_bias;  // [(2nb+1)][2][W][4] bias as one extra K=8 step: (hi, lo, 0, 0 | 0...)
+  int64_t fwd_lb;    // 2*nb blocks [W/4][W][4] + [2][W][4]: layer i's operand followed by its
+                     // bias slice, so that one bulk copy brings a whole layer
   int64_t total;
 };
 
@@ -46,7 +57,8 @@ inline PackedLayout make_packed_layout(const Layout& L) {
   p.vecs = p.rev_p + (int64_t)L.W * p.AP;
   p.raw = p.vecs + (int64_t)(2 * L.nb + 2) * L.W + 4;
   p.fwd_bias = p.raw + (int64_t)(2 * L.nb + 1) * L.W;
-  p.total = p.fwd_bias + (int64_t)(2 * L.nb + 1) * 8 * L.W;
+  p.fwd_lb = p.fwd_bias + (int64_t)(2 * L.nb + 1) * 8 * L.W;
+  p.total = p.fwd_lb + (int64_t)(2 * L.nb) * (WW + 8 * L.W);
   return p;
 }
 

@@ -13,3 +13,7 @@ obs = torch.randn(512, 20).cuda(); act = torch.rand(rows, 2).cuda()
 for _ in range(2):
   e.energy(obs, act, 257)
 torch.cuda.synchronize()
+if len(sys.argv) > 1 and sys.argv[1] == 'train':
+  # the operand-saving instance of the forward (training step)
+  e.train_grads(obs, act, 256, eng.loss_cfg(add_grad_penalty=False), 512)
+  torch.cuda.synchronize()
