@@ -28,6 +28,7 @@
 // elect.sync (umma::elect_one).
 #include <stdlib.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "mlp.cuh"
@@ -50,7 +51,8 @@ constexpr int kKSteps = kW / 8;                          // 16 MMAs (K = 8) per 
 // warpgroup to the epilogue warpgroups: each epilogue thread holds a 128-float
 // residual row.
 constexpr int kThreads = (4 * kNT + 4) * 32;
-constexpr int kEpilogueRegs = 224, kServiceRegs = 40;
+// register budgets after setmaxnreg (per instance: chosen so that ptxas does not spill)
+constexpr int kFwdRegs = 232, kFwdSaveRegs = 224, kBwdRegs = 232, kServiceRegs = 40;
 // The weight ring holds whole layers: one bulk copy and one full/empty barrier
 // pair per layer.  (With 16 KB slices the producer, which does not get past an
 // mbarrier wait while its previous bulk copy is in flight, could not stay ahead
@@ -64,6 +66,39 @@ inline size_t smem_bytes(bool forward, int KP) {
   const size_t ring = (size_t)kRing * (kLayerWBytes + (forward ? kBiasBytes : 0));
   const size_t tail = forward ? (size_t)KP * kW * 4 + 4096 + (kW + 4) * 4 : 2 * (size_t)kW * 4;
   return ring + tail + (size_t)(2 * kNT + 2 * kRing + 1) * 8 + 64;
+}
+
+// Work items of one CTA: `rounds` full rounds in which every CTA takes two
+// consecutive 128-row tiles, then one tail round.  When no more than gridDim.x
+// tiles are left the tail hands them out one per CTA (a lone tile runs without
+// MMA/epilogue overlap, but every SM gets one, instead of half the SMs getting
+// two: 131 584 rows = 1028 tiles over 148 SMs are 7 tiles per SM rather than 8).
+struct Tiling {
+  int64_t tiles;      // ceil(R / 128)
+  int rounds;         // full two-tile rounds
+  int tail_single;    // tail round: one tile per CTA
+};
+
+inline Tiling make_tiling(int64_t R, int grid) {
+  Tiling w;
+  w.tiles = (R + 127) / 128;
+  w.rounds = (int)(w.tiles / (2 * (int64_t)grid));
+  const int64_t rem = w.tiles - (int64_t)w.rounds * 2 * grid;
+  w.tail_single = rem <= grid ? 1 : 0;
+  return w;
+}
+
+// item k of this CTA -> first tile and tile count (0 = no more work)
+__device__ __forceinline__ int work_item(const Tiling& w, int k, int64_t& tile0) {
+  if (k < w.rounds) {
+    tile0 = ((int64_t)k * gridDim.x + blockIdx.x) * 2;
+    return 2;
+  }
+  if (k > w.rounds) return 0;
+  const int64_t base = (int64_t)w.rounds * 2 * gridDim.x;
+  tile0 = base + (w.tail_single ? (int64_t)blockIdx.x : 2 * (int64_t)blockIdx.x);
+  const int64_t left = w.tiles - tile0;
+  return left <= 0 ? 0 : (w.tail_single ? 1 : (left < 2 ? 1 : 2));
 }
 
 // Tensor-pipe token.  Two issuer threads sharing the pipe 1:1 finish their layers
@@ -95,7 +130,8 @@ struct FwdTmemParams {
   float* xa_save;        // nullable, 2nb+1 slots per tile (training)
   uint32_t* mask_save;   // nullable, ReLU masks of the 2nb W x W layers
   int64_t R, n_per_obs;
-  int nb, A, KP, nt, num_groups;
+  int nb, A, KP;
+  Tiling work;
   int64_t off_fwd_p, off_fwd_lb, off_we;
   int* status;
   long long* dbg;
@@ -124,13 +160,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tmem_kernel(FwdTmemParams
   __shared__ int s_pipe;    // tensor-pipe token: one tile's layer is issued at a time
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nt = p.nt;
 
   if (tid == 0) {
     s_abort = 0;
     s_pipe = 0;
     for (int t = 0; t < kNT; ++t) { mbar_init(&a_ready[t], 128); mbar_init(&d_ready[t], 1); }
-    for (int s = 0; s < kRing; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], nt); }
+    for (int s = 0; s < kRing; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kNT); }
     mbar_init(p0_full, 1);
     fence_mbar_init();
   }
@@ -148,16 +183,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tmem_kernel(FwdTmemParams
 
   if (warp < 4 * kNT) {
     // ===================== epilogue warpgroup t ==============================
-    setmaxnreg_inc<kEpilogueRegs>();
+    setmaxnreg_inc<(kSave ? kFwdSaveRegs : kFwdRegs)>();
     const int t = warp >> 2;
-    if (t < nt) {
+    {
       const int row = tid & 127;
       const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
       const uint32_t col_x = tmem_base + lane_off + (uint32_t)(t * 2 * W);
       const uint32_t col_y = col_x + W;
       uint32_t ph_d = 0;
-      for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
-        const int64_t tile_id = (int64_t)g * nt + t;
+      for (int k = 0;; ++k) {
+        int64_t tile0;
+        const int n = work_item(p.work, k, tile0);
+        if (n == 0) break;
+        if (t >= n) continue;
+        const int64_t tile_id = tile0 + t;
         const int64_t r = tile_id * 128 + row;
         const bool valid = r < p.R;
         {   // step-0 operand: this row's action (zero padded) into X[:, 0:32)
@@ -181,27 +220,53 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tmem_kernel(FwdTmemParams
             h[c * 4 + 0] = v.x; h[c * 4 + 1] = v.y; h[c * 4 + 2] = v.z; h[c * 4 + 3] = v.w;
           }
         }
-#pragma unroll 1
-        for (int i = 0; i < nsteps; ++i) {
+        // One epilogue step.  kEven: the accumulator (Y after the action projection,
+        // X after a second Dense) is this block's increment of the residual stream:
+        // h += D, next operand relu(h) -> X.  Odd: Y holds relu(h) . W1 + b1 -> ReLU,
+        // round, in place (the A operand of the second Dense).  kLast: Dense(1) on
+        // the final residual stream instead of a next operand.  TMEM loads run one
+        // 32-column chunk ahead of the arithmetic (two register buffers): under MMA
+        // load a tcgen05.ld round trip is ~300 cycles.
+        auto step = [&](auto even_tag, auto last_tag, int i) {
+          constexpr bool kEven = decltype(even_tag)::value;
+          constexpr bool kLast = decltype(last_tag)::value;
           float4* g_slot = (kSave && p.xa_save) ? reinterpret_cast<float4*>(
               p.xa_save + TT::slot_base(tile_id, nsteps, i)) : nullptr;
-          uint32_t* m_slot = (kSave && p.mask_save && i < nsteps - 1)
-              ? p.mask_save + TT::mask_index(tile_id, p.nb, i, row) : nullptr;
           mbar_wait(&d_ready[t], ph_d, abort_flag, p.status, 100 + i);
           ph_d ^= 1;
           tc_fence_after();
-          const bool stamp = p.dbg && blockIdx.x == 0 && g == (int)blockIdx.x && row == 0 && i < 64;
+          const bool stamp = p.dbg && blockIdx.x == 0 && k == 0 && row == 0 && i < 64;
           if (stamp) p.dbg[(i * kNT + t) * 5 + 0] = clock64();
-          const bool last = (i == nsteps - 1);
-          uint32_t mb[W / 32];
           if (p.dbg_mode & 1) {
-            if (!last) { tc_fence_before(); mbar_arrive(&a_ready[t]); }
-            continue;
+            if (!kLast) { tc_fence_before(); mbar_arrive(&a_ready[t]); }
+            return;
           }
-          // TMEM loads run one 32-column chunk ahead of the arithmetic (two register
-          // buffers): under MMA load a tcgen05.ld round trip is ~300 cycles, and four
-          // of them back to back were the whole epilogue.
-          auto save_chunk = [&](int c32, const uint32_t (&v)[32]) {
+          const uint32_t col_d = kEven ? ((i == 0) ? col_y : col_x) : col_y;
+          const uint32_t col_a = kEven ? col_x : col_y;
+          uint32_t mb[W / 32];
+          float e = 0.f;
+          auto chunk = [&](int c32, uint32_t (&v)[32]) {
+            uint32_t nbits = 0;     // bit (31 - q) = NOT (operand q > 0)
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              uint32_t xb = v[q];
+              if (kEven) {
+                const float x = h[c32 * 32 + q] + __uint_as_float(v[q]);
+                h[c32 * 32 + q] = x;
+                xb = __float_as_uint(x);
+                if (kLast) e = fmaf(x, we[c32 * 32 + q], e);
+              }
+              if (!kLast) {
+                // relu + round in one VIADDMNMX; o > 0x1000 <=> x > 0 exactly, so the
+                // mask bit is the sign of o - 0x1001, shifted in with one funnel shift
+                const uint32_t o = relu_tf32_bits(xb);
+                if (kSave) nbits = __funnelshift_l(o - 0x1001u, nbits, 1);
+                xb = o;
+              }
+              v[q] = xb;
+            }
+            if (kSave && !kLast) mb[c32] = ~__brev(nbits);
+            if (!kLast) tmem_st32(col_a + c32 * 32, v);
             if (g_slot) {
 #pragma unroll
               for (int q = 0; q < 8; ++q)
@@ -210,68 +275,34 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tmem_kernel(FwdTmemParams
                                 __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
             }
           };
-          if ((i & 1) == 0) {
-            // even step: the accumulator (Y after the action projection, X after a
-            // second Dense) is this block's increment of the residual stream
-            const uint32_t col_d = (i == 0) ? col_y : col_x;
-            float e = 0.f;
-            auto chunk = [&](int c32, uint32_t (&v)[32]) {
-              uint32_t bits = 0;
-#pragma unroll
-              for (int q = 0; q < 32; ++q) {
-                const float x = h[c32 * 32 + q] + __uint_as_float(v[q]);
-                h[c32 * 32 + q] = x;
-                if (last) {
-                  e = fmaf(x, we[c32 * 32 + q], e);
-                  v[q] = __float_as_uint(x);
-                } else {
-                  v[q] = relu_tf32_bits(__float_as_uint(x));
-                  if (kSave) bits |= (x > 0.f ? 1u : 0u) << q;
-                }
-              }
-              mb[c32] = bits;
-              if (!last) tmem_st32(col_x + c32 * 32, v);
-              save_chunk(c32, v);
-            };
-            uint32_t va[32], vb[32];
-            tmem_ld32(col_d, va);
-            tmem_ld_wait(va); tmem_ld32(col_d + 32, vb); chunk(0, va);
-            tmem_ld_wait(vb); tmem_ld32(col_d + 64, va); chunk(1, vb);
-            tmem_ld_wait(va); tmem_ld32(col_d + 96, vb); chunk(2, va);
-            tmem_ld_wait(vb); chunk(3, vb);
-            if (last && valid) p.E[r] = e + be;          // Dense(1), mlp_ebm.py:91-94
+          uint32_t va[32], vb[32];
+          tmem_ld32(col_d, va);
+          tmem_ld_wait(va); tmem_ld32(col_d + 32, vb); chunk(0, va);
+          tmem_ld_wait(vb); tmem_ld32(col_d + 64, va); chunk(1, vb);
+          tmem_ld_wait(va); tmem_ld32(col_d + 96, vb); chunk(2, va);
+          tmem_ld_wait(vb); chunk(3, vb);
+          if (kLast) {
+            if (valid) p.E[r] = e + be;          // Dense(1), mlp_ebm.py:91-94
+            tc_fence_before();
           } else {
-            // odd step: Y holds relu(h) . W1 + b1 -> ReLU, round, in place: the A
-            // operand of the second Dense
-            auto chunk = [&](int c32, uint32_t (&v)[32]) {
-              uint32_t bits = 0;
-#pragma unroll
-              for (int q = 0; q < 32; ++q) {
-                if (kSave) bits |= (__uint_as_float(v[q]) > 0.f ? 1u : 0u) << q;
-                v[q] = relu_tf32_bits(v[q]);
-              }
-              mb[c32] = bits;
-              tmem_st32(col_y + c32 * 32, v);
-              save_chunk(c32, v);
-            };
-            uint32_t va[32], vb[32];
-            tmem_ld32(col_y, va);
-            tmem_ld_wait(va); tmem_ld32(col_y + 32, vb); chunk(0, va);
-            tmem_ld_wait(vb); tmem_ld32(col_y + 64, va); chunk(1, vb);
-            tmem_ld_wait(va); tmem_ld32(col_y + 96, vb); chunk(2, va);
-            tmem_ld_wait(vb); chunk(3, vb);
-          }
-          if (m_slot) *reinterpret_cast<uint4*>(m_slot) = make_uint4(mb[0], mb[1], mb[2], mb[3]);
-          if (stamp) p.dbg[(i * kNT + t) * 5 + 1] = clock64();
-          if (!last) {
+            if (kSave && p.mask_save)
+              *reinterpret_cast<uint4*>(p.mask_save + TT::mask_index(tile_id, p.nb, i, row)) =
+                  make_uint4(mb[0], mb[1], mb[2], mb[3]);
+            if (stamp) p.dbg[(i * kNT + t) * 5 + 1] = clock64();
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&a_ready[t]);
-          } else {
-            tc_fence_before();
           }
           if (stamp) p.dbg[(i * kNT + t) * 5 + 2] = clock64();
+        };
+        using T_ = std::true_type;
+        using F_ = std::false_type;
+#pragma unroll 1
+        for (int j = 0; j < p.nb; ++j) {
+          step(T_{}, F_{}, 2 * j);        // h_j (j = 0: action projection + hp)
+          step(F_{}, F_{}, 2 * j + 1);    // first Dense of block j
         }
+        step(T_{}, T_{}, 2 * p.nb);       // last block's second Dense + Dense(1)
       }
     }
   } else if (warp == 4 * kNT) {
@@ -283,7 +314,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tmem_kernel(FwdTmemParams
     }
     __syncwarp();
     uint32_t q = 0;
-    for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+    for (int k = 0;; ++k) {
+      int64_t tile0;
+      if (work_item(p.work, k, tile0) == 0) break;
       for (int i = 1; i < nsteps; ++i, ++q) {
         const int slot = q % kRing;
         const uint32_t ph = (q / kRing) & 1;
@@ -297,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tmem_kernel(FwdTmemParams
         __syncwarp();
       }
     }
-  } else if (warp >= 4 * kNT + 1 + nt) {
+  } else if (warp >= 4 * kNT + 1 + kNT) {
     setmaxnreg_dec<kServiceRegs>();     // idle members of the service warpgroup
   } else {
     // ===================== MMA issuer of tile t ================================
@@ -315,9 +348,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tmem_kernel(FwdTmemParams
     const uint32_t col_y = col_x + W;
     uint32_t q = 0;
     uint32_t ph_a = 0;
-    for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+    for (int k = 0;; ++k) {
+      int64_t tile0;
+      const int n = work_item(p.work, k, tile0);
+      if (n == 0) break;
+      if (t >= n) {
+        // no tile for this issuer in the item: still hand every layer's ring slot back
+        for (int i = 1; i < nsteps; ++i, ++q) {
+          if (elect_one()) {
+            mbar_wait(&w_full[q % kRing], (q / kRing) & 1, abort_flag, p.status, 450 + i);
+            mbar_arrive(&w_empty[q % kRing]);
+          }
+          __syncwarp();
+        }
+        continue;
+      }
       for (int i = 0; i < nsteps; ++i) {
-        const bool mstamp = p.dbg && blockIdx.x == 0 && g == (int)blockIdx.x && i < 64;
+        const bool mstamp = p.dbg && blockIdx.x == 0 && k == 0 && i < 64;
         // step 0 and odd steps read X and write Y; even steps >= 2 read Y, write X
         const bool x_to_y = (i == 0) || (i & 1);
         const uint32_t a_tmem = x_to_y ? col_x : col_y;
@@ -375,7 +422,8 @@ struct BwdTmemParams {
   int64_t off_rev_l, off_we;
   float* dwe;                 // nullable [W], atomics
   int64_t R;
-  int nb, nt, num_groups;
+  int nb;
+  Tiling work;
   int* status;
 };
 
@@ -396,7 +444,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
   __shared__ int s_pipe;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nt = p.nt;
   const int nsteps = 2 * p.nb;
   const int xa_slots = 2 * p.nb + 1, gy_slots = 2 * p.nb;
 
@@ -404,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
     s_abort = 0;
     s_pipe = 0;
     for (int t = 0; t < kNT; ++t) { mbar_init(&a_ready[t], 128); mbar_init(&d_ready[t], 1); }
-    for (int s = 0; s < kRing; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], nt); }
+    for (int s = 0; s < kRing; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kNT); }
     fence_mbar_init();
   }
   for (int i = tid; i < W; i += kThreads) { we[i] = p.packed[p.off_we + i]; dwe_acc[i] = 0.f; }
@@ -417,16 +464,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
 
   if (warp < 4 * kNT) {
     // ===================== epilogue warpgroup t ==============================
-    setmaxnreg_inc<kEpilogueRegs>();
+    setmaxnreg_inc<kBwdRegs>();
     const int t = warp >> 2;
-    if (t < nt) {
+    {
       const int row = tid & 127;
       const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
       const uint32_t col_x = tmem_base + lane_off + (uint32_t)(t * 2 * W);
       const uint32_t col_y = col_x + W;
       uint32_t ph_d = 0;
-      for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
-        const int64_t tile_id = (int64_t)g * nt + t;
+      for (int k = 0;; ++k) {
+        int64_t tile0;
+        const int n = work_item(p.work, k, tile0);
+        if (n == 0) break;
+        if (t >= n) continue;
+        const int64_t tile_id = tile0 + t;
         const int64_t r = tile_id * 128 + row;
         const bool valid = r < p.R;
         const float de = valid ? (p.dE ? p.dE[r] : 1.0f) : 0.f;
@@ -470,23 +521,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
           tc_fence_before();
           mbar_arrive(&a_ready[t]);
         }
-#pragma unroll 1
-        for (int s = 0; s < nsteps; ++s) {
-          const int i = nsteps - s;                   // forward layer index 2nb .. 1
-          const bool odd = (i & 1) != 0;              // W1 layer: result adds onto g
-          const bool last = (i == 1);
-          float4* gy_out = (last || !p.gy_save) ? nullptr : reinterpret_cast<float4*>(
+        // One reverse step for forward layer i (2nb .. 1).
+        //   even layer (W2_j): D = Y, masked in place -> A operand of the W1_j step
+        //   odd  layer (W1_j): D = X, g += masked D  -> A operand of the next W2 step
+        //   last (i = 1): g is the gradient of the first Dense output -> g0
+        auto step = [&](auto odd_tag, auto last_tag, int i) {
+          constexpr bool kOdd = decltype(odd_tag)::value;
+          constexpr bool kLast = decltype(last_tag)::value;
+          float4* gy_out = (kLast || !p.gy_save) ? nullptr : reinterpret_cast<float4*>(
               p.gy_save + TT::slot_base(tile_id, gy_slots, i - 2));
           const uint32_t mbits[4] = {mnext.x, mnext.y, mnext.z, mnext.w};
-          if (!last)
+          if (!kLast)
             mnext = *reinterpret_cast<const uint4*>(
                 p.mask_save + TT::mask_index(tile_id, p.nb, i - 2, row));
-          mbar_wait(&d_ready[t], ph_d, abort_flag, p.status, 500 + s);
+          mbar_wait(&d_ready[t], ph_d, abort_flag, p.status, 500 + i);
           ph_d ^= 1;
           tc_fence_after();
-          // even layer (W2_j): D = Y, masked in place -> A operand of the W1_j step
-          // odd  layer (W1_j): D = X, g += masked D -> A operand of the next W2 step
-          const uint32_t col_d = odd ? col_x : col_y;
+          const uint32_t col_d = kOdd ? col_x : col_y;
           auto chunk = [&](int c32, uint32_t (&v)[32]) {
             const uint32_t bits = mbits[c32];
 #pragma unroll
@@ -497,11 +548,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
               o.y = (bits >> (q * 4 + 1)) & 1u ? __uint_as_float(v[q * 4 + 1]) : 0.f;
               o.z = (bits >> (q * 4 + 2)) & 1u ? __uint_as_float(v[q * 4 + 2]) : 0.f;
               o.w = (bits >> (q * 4 + 3)) & 1u ? __uint_as_float(v[q * 4 + 3]) : 0.f;
-              if (odd) {
+              if (kOdd) {
                 o.x += gr[c * 4 + 0]; o.y += gr[c * 4 + 1]; o.z += gr[c * 4 + 2]; o.w += gr[c * 4 + 3];
                 gr[c * 4 + 0] = o.x; gr[c * 4 + 1] = o.y; gr[c * 4 + 2] = o.z; gr[c * 4 + 3] = o.w;
               }
-              if (!last) {
+              if (!kLast) {
                 if (gy_out) gy_out[TT::chunk_f4(row, c)] = o;   // fp32: exact bias sums
                 v[q * 4 + 0] = tf32_rn_bits(__float_as_uint(o.x));
                 v[q * 4 + 1] = tf32_rn_bits(__float_as_uint(o.y));
@@ -511,7 +562,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
                 *reinterpret_cast<float4*>(p.g0 + r * W + c * 4) = o;
               }
             }
-            if (!last) tmem_st32(col_d + c32 * 32, v);
+            if (!kLast) tmem_st32(col_d + c32 * 32, v);
           };
           // TMEM loads one chunk ahead of the arithmetic (see the forward kernel)
           uint32_t va[32], vb[32];
@@ -520,21 +571,32 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
           tmem_ld_wait(vb); tmem_ld32(col_d + 64, va); chunk(1, vb);
           tmem_ld_wait(va); tmem_ld32(col_d + 96, vb); chunk(2, va);
           tmem_ld_wait(vb); chunk(3, vb);
-          if (!last) {
+          if (!kLast) {
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&a_ready[t]);
           } else {
             tc_fence_before();
           }
+        };
+        using T_ = std::true_type;
+        using F_ = std::false_type;
+#pragma unroll 1
+        for (int j = p.nb - 1; j >= 1; --j) {
+          step(F_{}, F_{}, 2 * j + 2);
+          step(T_{}, F_{}, 2 * j + 1);
         }
+        step(F_{}, F_{}, 2);
+        step(T_{}, T_{}, 1);
       }
     }
   } else if (warp == 4 * kNT) {
     // ===================== producer: one bulk copy per layer ==================
     setmaxnreg_dec<kServiceRegs>();
     uint32_t q = 0;
-    for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+    for (int k = 0;; ++k) {
+      int64_t tile0;
+      if (work_item(p.work, k, tile0) == 0) break;
       for (int s = 0; s < nsteps; ++s, ++q) {
         const int slot = q % kRing;
         const uint32_t ph = (q / kRing) & 1;
@@ -547,7 +609,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
         __syncwarp();
       }
     }
-  } else if (warp >= 4 * kNT + 1 + nt) {
+  } else if (warp >= 4 * kNT + 1 + kNT) {
     setmaxnreg_dec<kServiceRegs>();     // idle members of the service warpgroup
   } else {
     // ===================== MMA issuer of tile t (see the forward kernel) =======
@@ -560,7 +622,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
     const uint32_t col_y = col_x + W;
     uint32_t q = 0;
     uint32_t ph_a = 0;
-    for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+    for (int k = 0;; ++k) {
+      int64_t tile0;
+      const int n = work_item(p.work, k, tile0);
+      if (n == 0) break;
+      if (t >= n) {
+        for (int s = 0; s < nsteps; ++s, ++q) {
+          if (elect_one()) {
+            mbar_wait(&w_full[q % kRing], (q / kRing) & 1, abort_flag, p.status, 850 + s);
+            mbar_arrive(&w_empty[q % kRing]);
+          }
+          __syncwarp();
+        }
+        continue;
+      }
       for (int s = 0; s < nsteps; ++s, ++q) {
         const int i = nsteps - s;
         // even layer: A = X (g), D = Y ; odd layer: A = Y (u), D = X
@@ -592,12 +667,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
     for (int i = tid; i < W; i += kThreads) atomicAdd(p.dwe + i, dwe_acc[i]);
 }
 
-// With few rows one tile per CTA keeps more SMs busy than two.
-inline int choose_nt(int64_t R, int sm_count) {
-  const int64_t tiles = (R + 127) / 128;
-  return tiles <= sm_count ? 1 : 2;
-}
-
 template <typename K>
 int raise_smem(ibc_handle* h, K kernel) {
   IBC_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -611,8 +680,6 @@ bool tmem_path_supported(const Layout& L) {
   return L.W == kW && L.A <= 32 && smem_bytes(true, round_up(L.A, 8)) <= 227 * 1024 - 1024;
 }
 
-int tmem_tiles_per_cta(ibc_handle* h, int64_t R) { return choose_nt(R, h->sm_count); }
-
 int tmem_forward(ibc_handle* h, const float* act, int64_t R, int64_t n, const float* hp, float* E,
                  float* xa_save, uint32_t* mask_save, cudaStream_t s) {
   const Layout& L = h->L;
@@ -622,8 +689,9 @@ int tmem_forward(ibc_handle* h, const float* act, int64_t R, int64_t n, const fl
   p.act = act; p.hp = hp; p.packed = h->packed; p.E = E; p.xa_save = xa_save;
   p.mask_save = mask_save;
   p.R = R; p.n_per_obs = n; p.nb = L.nb; p.A = L.A; p.KP = pl.KP;
-  p.nt = tmem_tiles_per_cta(h, R);
-  p.num_groups = (int)((R + 128 * p.nt - 1) / (128 * p.nt));
+  const int64_t tiles = (R + 127) / 128;
+  const int grid = tiles < h->sm_count ? (int)tiles : h->sm_count;
+  p.work = make_tiling(R, grid);
   p.off_fwd_p = pl.fwd_p; p.off_fwd_lb = pl.fwd_lb;
   p.off_we = pl.vecs + (int64_t)(2 * L.nb + 1) * L.W;
   p.status = h->dev_status;
@@ -640,7 +708,6 @@ int tmem_forward(ibc_handle* h, const float* act, int64_t R, int64_t n, const fl
     IBC_TRY(raise_smem(h, mlp_fwd_tmem_kernel<false>));
     attr = true;
   }
-  const int grid = p.num_groups < h->sm_count ? p.num_groups : h->sm_count;
   const size_t smem = smem_bytes(true, p.KP);
   if (saving) mlp_fwd_tmem_kernel<true><<<grid, kThreads, smem, s>>>(p);
   else mlp_fwd_tmem_kernel<false><<<grid, kThreads, smem, s>>>(p);
@@ -651,13 +718,17 @@ int tmem_forward(ibc_handle* h, const float* act, int64_t R, int64_t n, const fl
     cudaMemcpy(hb.data(), p.dbg, hb.size() * sizeof(long long), cudaMemcpyDeviceToHost);
     cudaFree(p.dbg);
     const long long t0 = hb[3];
-    fprintf(stderr, "[ibc timeline tmem nt=%d] step tile | mma_start mma_issued | epi_start epi_done arrived\n",
-            p.nt);
+    fprintf(stderr, "[ibc timeline tmem rounds=%d tail_single=%d] step tile | mma_start mma_issued | epi_start epi_done arrived\n",
+            p.work.rounds, p.work.tail_single);
     for (int i = 0; i < 2 * L.nb + 1 && i < 64; ++i)
-      for (int t = 0; t < p.nt; ++t) {
+      for (int t = 0; t < kNT; ++t) {
         const long long* e = &hb[(i * kNT + t) * 5];
         fprintf(stderr, "[ibc timeline tmem] %3d %d | %8lld %8lld | %8lld %8lld %8lld\n", i, t,
                 e[3] - t0, e[4] - t0, e[0] - t0, e[1] - t0, e[2] - t0);
+        if (t == 0 && (i & 1) == 0 && i < 46)
+          fprintf(stderr, "[ibc timeline tmem]       even-step chunks (from epi_start): ld0 %lld c0 %lld ld1 %lld c1 %lld c2 %lld c3 %lld\n",
+                  hb[640 + i * 8 + 0] - e[0], hb[640 + i * 8 + 1] - e[0], hb[640 + i * 8 + 2] - e[0],
+                  hb[640 + i * 8 + 3] - e[0], hb[640 + i * 8 + 4] - e[0], hb[640 + i * 8 + 5] - e[0]);
       }
   }
   return IBC_OK;
@@ -672,15 +743,16 @@ int tmem_reverse(ibc_handle* h, const float* dE, int64_t R, const float* xa_save
   p.dE = dE; p.xa_save = xa_save; p.mask_save = mask_save; p.gy_save = gy_save; p.g0 = g0;
   p.packed = h->packed;
   p.off_rev_l = pl.rev_l; p.off_we = pl.vecs + (int64_t)(2 * L.nb + 1) * L.W;
-  p.dwe = dwe; p.R = R; p.nb = L.nb; p.nt = tmem_tiles_per_cta(h, R);
-  p.num_groups = (int)((R + 128 * p.nt - 1) / (128 * p.nt));
+  p.dwe = dwe; p.R = R; p.nb = L.nb;
+  const int64_t tiles = (R + 127) / 128;
+  const int grid = tiles < h->sm_count ? (int)tiles : h->sm_count;
+  p.work = make_tiling(R, grid);
   p.status = h->dev_status;
   static bool attr = false;
   if (!attr) {
     IBC_TRY(raise_smem(h, mlp_bwd_tmem_kernel));
     attr = true;
   }
-  const int grid = p.num_groups < h->sm_count ? p.num_groups : h->sm_count;
   mlp_bwd_tmem_kernel<<<grid, kThreads, smem_bytes(false, 0), s>>>(p);
   IBC_LAUNCH_CHECK(h);
   return IBC_OK;

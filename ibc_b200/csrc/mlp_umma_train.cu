@@ -761,10 +761,11 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
   {
     WgradParams wp;
     wp.xa_save = xa; wp.gy_save = gy; wp.grads = grads; wp.L = L; wp.nb = nb;
-    wp.num_tiles = (int)num_tiles;
+    // only tiles that hold rows: the forward / reverse kernels never touch a padding tile
+    wp.num_tiles = (int)((R + 127) / 128);
     int splits = h->sm_count / (2 * nb);
     if (splits < 1) splits = 1;
-    if (splits > num_tiles) splits = (int)num_tiles;
+    if (splits > wp.num_tiles) splits = wp.num_tiles;
     wp.splits = splits;
     wp.status = h->dev_status;
     dim3 grid(2 * nb, splits);

@@ -36,14 +36,20 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                "r"(bytes)
                : "memory");
 }
+// The suspend-time hint lets the hardware park the thread until the phase
+// completes (or the hint expires) instead of returning at once: without it the
+// waiting warps (issuers, producer, the idle tile's epilogue) re-polled shared
+// memory ~10^5 times per kernel and their SYNCS/LDS traffic slowed the working
+// epilogue's tcgen05.ld/st down several-fold (ncu source counters, r1).
+constexpr uint32_t kSuspendHintNs = 20000;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs)
       : "memory");
   return ok != 0;
 }
@@ -52,7 +58,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // returns immediately (results are then garbage, which the host reports).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag,
                                           int* status, int code) {
-  for (uint32_t it = 0; it < (1u << 22); ++it) {
+  for (uint32_t it = 0; it < (1u << 17); ++it) {      // ~2.6 s at the hint's 20 us
     if (mbar_try_wait(bar, parity)) return true;
     if (*abort_flag) return false;
   }
