@@ -310,9 +310,13 @@ __global__ void __launch_bounds__((4 * NT_ + 2) * 32, 1) mlp_bwd_umma_kernel(Bwd
 // streams 256 rows (coalesced g0 reads, broadcast action reads), A <= 32
 // accumulators in registers, one atomic per (a, w) per block.
 template <int AMAX>
-__global__ void __launch_bounds__(kW) act_wgrad_kernel(const float* __restrict__ act,
-                                                        const float* __restrict__ g0, int64_t R,
-                                                        int A, float* __restrict__ dw) {
+__global__ void __launch_bounds__(kW) first_layer_grads_kernel(
+    const float* __restrict__ act, const float* __restrict__ g0, const float* __restrict__ dE,
+    int64_t R, int A, int64_t n1, float* __restrict__ dw, float* __restrict__ gsum,
+    float* __restrict__ dbe) {
+  // One pass over g0 [R, W]: dWp[O:] += act^T . g0 (per-thread accumulators, thread =
+  // column), gsum[b] += sum of the rows of observation b (for dWp[:O] and dbp), and
+  // dbe += sum(dE).  Rows of a 256-row block span at most a few observations.
   __shared__ float s_act[64 * AMAX];
   const int w = threadIdx.x;
   const int64_t r0 = (int64_t)blockIdx.x * 256;
@@ -320,6 +324,9 @@ __global__ void __launch_bounds__(kW) act_wgrad_kernel(const float* __restrict__
   float acc[AMAX];
 #pragma unroll
   for (int a = 0; a < AMAX; ++a) acc[a] = 0.f;
+  float gs = 0.f;
+  int64_t cur_b = r0 / n1;
+  int64_t next_edge = (cur_b + 1) * n1;
   for (int64_t rb = r0; rb < r1; rb += 64) {
     const int nr = (int)min((int64_t)64, r1 - rb);
     __syncthreads();
@@ -328,15 +335,41 @@ __global__ void __launch_bounds__(kW) act_wgrad_kernel(const float* __restrict__
       s_act[i] = (a < A) ? act[(rb + k) * A + a] : 0.f;
     }
     __syncthreads();
-    for (int k = 0; k < nr; ++k) {
-      const float g = g0[(rb + k) * kW + w];
+    const float* gp = g0 + rb * kW + w;
+    // first row (relative to rb) of the next observation's group
+    int edge = (int)min(next_edge - rb, (int64_t)1 << 20);
+    const int n1i = (int)min(n1, (int64_t)1 << 20);
+    for (int k0 = 0; k0 < nr; k0 += 8) {
+      float g[8];
 #pragma unroll
-      for (int a = 0; a < AMAX; ++a) acc[a] = fmaf(s_act[k * AMAX + a], g, acc[a]);
+      for (int u = 0; u < 8; ++u) g[u] = (k0 + u < nr) ? gp[(int64_t)(k0 + u) * kW] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + u;
+        if (k == edge) {
+          atomicAdd(gsum + cur_b * kW + w, gs);
+          gs = 0.f;
+          ++cur_b;
+          next_edge += n1;
+          edge += n1i;
+        }
+        gs += g[u];
+#pragma unroll
+        for (int a = 0; a < AMAX; ++a) acc[a] = fmaf(s_act[(k < nr ? k : 0) * AMAX + a], g[u], acc[a]);
+      }
     }
   }
+  if (r1 > r0) atomicAdd(gsum + cur_b * kW + w, gs);
 #pragma unroll
   for (int a = 0; a < AMAX; ++a)
     if (a < A) atomicAdd(dw + (int64_t)a * kW + w, acc[a]);
+  if (w < 32) {            // dbe: the block's 256 dE values through one warp
+    float sde = 0.f;
+    for (int64_t r = r0 + w; r < r1; r += 32) sde += dE[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sde += __shfl_xor_sync(0xffffffffu, sde, o);
+    if (w == 0) atomicAdd(dbe, sde);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -774,16 +807,19 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
   }
   mark(4);
   // Dense(1) bias and the first Dense layer (x = [obs tiled, act]) in fp32
-  IBC_TRY(sum_add(h, dE, R, grads + L.be, s));
-  {  // dWp[O:] = act^T . g0 : K = all rows, M = act_dim (tiny) -> row-streaming kernel
+  {  // one pass over g0: dWp[O:] = act^T . g0, per-observation sums, dbe
+    IBC_CUDA(h, cudaMemsetAsync(gsum, 0, (size_t)B * W * 4, s));
     const int blocks = (int)((R + 255) / 256);
     float* dwa = grads + L.wp + (int64_t)L.O * W;
-    if (A <= 2) act_wgrad_kernel<2><<<blocks, kW, 0, s>>>(actions, g0, R, A, dwa);
-    else if (A <= 8) act_wgrad_kernel<8><<<blocks, kW, 0, s>>>(actions, g0, R, A, dwa);
-    else act_wgrad_kernel<32><<<blocks, kW, 0, s>>>(actions, g0, R, A, dwa);
+    float* dbe = grads + L.be;
+    if (A <= 2)
+      first_layer_grads_kernel<2><<<blocks, kW, 0, s>>>(actions, g0, dE, R, A, n1, dwa, gsum, dbe);
+    else if (A <= 8)
+      first_layer_grads_kernel<8><<<blocks, kW, 0, s>>>(actions, g0, dE, R, A, n1, dwa, gsum, dbe);
+    else
+      first_layer_grads_kernel<32><<<blocks, kW, 0, s>>>(actions, g0, dE, R, A, n1, dwa, gsum, dbe);
     IBC_LAUNCH_CHECK(h);
   }
-  IBC_TRY(groupsum(h, g0, B, n1, W, gsum, s));
   {
     GemmP g;   // dWp[:O] = obs^T . sum_n g0
     g.A = obs; g.lda = L.O; g.B = gsum; g.ldb = W; g.C = grads + L.wp; g.ldc = W;

@@ -46,6 +46,26 @@ class BehavioralCloningAgent:
     return loss_dict
 
 
+_CONST_VECTORS = {}
+
+
+def _scaled_sum(x, scale):
+  """sum(x) * scale as one dot product with a cached constant vector."""
+  key = (x.device, x.numel(), float(scale))
+  c = _CONST_VECTORS.get(key)
+  if c is None:
+    if len(_CONST_VECTORS) > 64:
+      _CONST_VECTORS.clear()
+    c = torch.full((x.numel(),), float(scale), device=x.device, dtype=x.dtype)
+    _CONST_VECTORS[key] = c
+  return torch.dot(x.reshape(-1), c)
+
+
+def _scaled_sq_diff_sum(a, b, scale):
+  d = (a - b).reshape(-1)
+  return torch.dot(d, d) * scale
+
+
 @gin.configurable
 class ImplicitBCAgent(BehavioralCloningAgent):
   """TFAgent look-alike implementing implicit behavioral cloning."""
@@ -172,15 +192,18 @@ class ImplicitBCAgent(BehavioralCloningAgent):
       raw, eff = net.effective_params_for_training()             # spectral norm, training=True
     per_example, grad_loss, _, grads = net.engine.train_grads(
         obs_flat, combined, n, self._loss_cfg(), global_batch, self._grads)
-    total_loss = per_example.sum() / float(global_batch)
+    total_loss = _scaled_sum(per_example, 1.0 / float(global_batch))
     losses_dict['ebm_total_loss'] = total_loss
     if self._add_grad_penalty:
       losses_dict['grad_loss'] = grad_loss.mean()
     if self._compute_mse:
       # Keras MSE(NONE) -> [B, N]; aggregate_losses averages the extra axis then
-      # sums / global batch (ibc_agent.py:182-189)
-      mse = ((counter_example_actions - expanded_actions) ** 2).mean(dim=-1).mean(dim=1)
-      losses_dict['mse_counter_examples'] = mse.sum() / float(global_batch)
+      # sums / global batch (ibc_agent.py:182-189).  All groups have the same size,
+      # so that is sum((c - a)^2) / (N * A * global_batch): two kernels instead of six.
+      losses_dict['mse_counter_examples'] = _scaled_sq_diff_sum(
+          counter_example_actions, expanded_actions,
+          1.0 / (float(global_batch) * counter_example_actions.shape[1]
+                 * counter_example_actions.shape[2]))
     if chain_data is not None and chain_data.energies is not None:
       e = chain_data.energies
       losses_dict['overall_energies_avg'] = e.mean()
@@ -220,11 +243,12 @@ class ImplicitBCAgent(BehavioralCloningAgent):
     global_batch = batch_size * self._num_replicas()
     per_example, _, grads = net.engine.train_grads(images, combined, n, self._loss_cfg(),
                                                    global_batch, self._grads)
-    total_loss = per_example.sum() / float(global_batch)
+    total_loss = _scaled_sum(per_example, 1.0 / float(global_batch))
     losses_dict = {'ebm_total_loss': total_loss}
     if self._compute_mse:
-      mse = ((counter - expanded_actions) ** 2).mean(dim=-1).mean(dim=1)
-      losses_dict['mse_counter_examples'] = mse.sum() / float(global_batch)
+      losses_dict['mse_counter_examples'] = _scaled_sq_diff_sum(
+          counter, expanded_actions,
+          1.0 / (float(global_batch) * counter.shape[1] * counter.shape[2]))
     self.last_losses_dict = losses_dict
     if training:
       return specs.LossInfo(total_loss, ()), grads
@@ -304,20 +328,19 @@ class ImplicitBCAgent(BehavioralCloningAgent):
 
   def _check_finite(self, loss):
     if self.check_numerics == 'sync':
-      if not bool(torch.isfinite(loss)):
+      if not math.isfinite(float(loss)):
         raise FloatingPointError('Loss is inf or nan')
       return
     prev = getattr(self, '_pending_finite', None)
     if prev is not None:
-      flag, ev = prev
-      if ev.query() and not bool(flag):
-        raise FloatingPointError('Loss is inf or nan')
+      prev_loss, ev = prev
       if not ev.query():
         return                        # still in flight: keep waiting on the older one
-    flag = torch.isfinite(loss)
+      if not math.isfinite(float(prev_loss)):     # event done: a 4-byte read, no stall
+        raise FloatingPointError('Loss is inf or nan')
     ev = torch.cuda.Event()
     ev.record()
-    self._pending_finite = (flag, ev)
+    self._pending_finite = (loss, ev)
 
   def _train(self, experience, weights=None, draws=None):
     loss_info, grads = self._loss(experience, weights=weights, training=True, draws=draws)
