@@ -313,7 +313,7 @@ def run_b200(args):
       fl = rows * fwd_flops_per_row()
       a = fl / fwd['tf32'] / 1e12
       result['roofline_energy_fwd'] = {
-          'kernel': 'mlp_fwd_umma_kernel<128,2> (tcgen05 kind::tf32)', 'bound': 'tensor',
+          'kernel': 'mlp_fwd_tmem_kernel (tcgen05 kind::tf32, activations in tensor memory)', 'bound': 'tensor',
           'achieved': a, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': a / tf32_peak,
           'traffic': None, 'ms_per_launch': fwd['tf32'] * 1e3, 'rows': rows,
           'fp32_path_ms': fwd['fp32'] * 1e3 if fwd.get('fp32') else None}
@@ -322,24 +322,43 @@ def run_b200(args):
     if kt is not None:
       # dominant kernel of the step = the one with the largest measured share
       wflops = 2.0 * c['depth'] * c['width'] ** 2 * rows     # one pass over the W x W layers
-      names = ['mlp_fwd_umma_kernel<128,2> (fused forward + operand save)', 'info_nce_kernel',
-               'mlp_bwd_umma_kernel (fused reverse chain)', 'mlp_wgrad_umma_kernel (dW GEMM)',
+      names = ['mlp_fwd_tmem_kernel<save> (fused forward, operands + ReLU masks saved)',
+               'info_nce_kernel',
+               'mlp_bwd_tmem_kernel (fused reverse chain, output gradients saved)',
+               'mlp_wgrad_umma_kernel (dW GEMM over the saved tiles)',
                'first/last-layer fp32 kernels']
       flops = [rows * fwd_flops_per_row(), 0.0, wflops, wflops, 0.0]
-      # algorithmic HBM bytes: saved operand tiles written / read once
+      # algorithmic HBM bytes per launch (DESIGN.md "bytes per unit"): one fp32 tile
+      # = rows * W * 4 B; masks = rows * W / 8 B per layer
       tile_bytes = rows * c['width'] * 4.0
-      hbm = [(c['depth'] + 1) * tile_bytes, 0.0, 2 * c['depth'] * tile_bytes + tile_bytes,
-             2 * c['depth'] * tile_bytes, 0.0]
+      mask_bytes = rows * c['width'] / 8.0
+      hbm = [(c['depth'] + 1) * tile_bytes + c['depth'] * mask_bytes,          # fwd: writes
+             0.0,
+             (c['depth'] + 1) * tile_bytes + tile_bytes + c['depth'] * mask_bytes,  # rev: GY + g0 out, h_nb + masks in
+             2 * c['depth'] * tile_bytes,                                      # wgrad: reads
+             0.0]
       top = int(np.argmax(kt))
-      result['kernel_ms'] = dict(zip(['forward', 'info_nce', 'reverse', 'wgrad', 'first_last'], kt))
-      a = flops[top] / (kt[top] * 1e-3) / 1e12 if flops[top] else 0.0
+      keys = ['forward', 'info_nce', 'reverse', 'wgrad', 'first_last']
+      result['kernel_ms'] = dict(zip(keys, kt))
+      traffic = _ncu_traffic().get(keys[top])
+      tfl = flops[top] / (kt[top] * 1e-3) / 1e12 if flops[top] else 0.0
       gbs = hbm[top] / (kt[top] * 1e-3) / 1e9
-      result['roofline'] = {
-          'kernel': names[top], 'bound': 'tensor', 'achieved': a, 'peak': tf32_peak,
-          'unit': 'TFLOP/s', 'frac': a / tf32_peak, 'traffic': None,
-          'ms_per_launch': kt[top], 'share_of_step': kt[top] / sum(kt),
-          'hbm_algorithmic_GBs': gbs, 'hbm_frac_of_measured': gbs / peaks['hbm'],
-          'peak_source': '%s bf16 burst / 2 (tf32 nominal ratio)' % peaks['source']}
+      frac_t, frac_h = tfl / tf32_peak, gbs / peaks['hbm']
+      if frac_h >= frac_t:
+        result['roofline'] = {
+            'kernel': names[top], 'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm'],
+            'unit': 'GB/s', 'frac': frac_h, 'traffic': traffic,
+            'ms_per_launch': kt[top], 'share_of_step': kt[top] / sum(kt),
+            'algorithmic_bytes_per_launch': hbm[top],
+            'tensor_TFLOPs': tfl, 'tensor_frac_of_measured': frac_t,
+            'peak_source': '%s copy bandwidth (MEASURED_PEAKS.json hbm_gbs)' % peaks['source']}
+      else:
+        result['roofline'] = {
+            'kernel': names[top], 'bound': 'tensor', 'achieved': tfl, 'peak': tf32_peak,
+            'unit': 'TFLOP/s', 'frac': frac_t, 'traffic': traffic,
+            'ms_per_launch': kt[top], 'share_of_step': kt[top] / sum(kt),
+            'hbm_algorithmic_GBs': gbs, 'hbm_frac_of_measured': frac_h,
+            'peak_source': '%s bf16 burst / 2 (tf32 nominal ratio)' % peaks['source']}
       result['roofline_kernels'] = [
           {'kernel': names[i], 'ms': kt[i], 'tflops': flops[i] / (kt[i] * 1e-3) / 1e12 if flops[i] else None,
            'hbm_GBs': hbm[i] / (kt[i] * 1e-3) / 1e9 if hbm[i] else None} for i in range(5)]
@@ -352,6 +371,17 @@ def run_b200(args):
     dist.barrier()
     dist.destroy_process_group()
   return result
+
+
+def _ncu_traffic():
+  """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step's kernels,
+  from the committed `ncu --set full` capture (profiles/r1_dram_traffic.json)."""
+  path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_dram_traffic.json')
+  try:
+    with open(path) as f:
+      return json.load(f)
+  except (OSError, ValueError):
+    return {}
 
 
 def secondary_configs(device):

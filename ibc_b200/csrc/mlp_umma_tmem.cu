@@ -58,13 +58,16 @@ constexpr int kFwdRegs = 232, kFwdSaveRegs = 224, kBwdRegs = 232, kServiceRegs =
 // mbarrier wait while its previous bulk copy is in flight, could not stay ahead
 // of the tensor pipe.)
 constexpr int kRing = 3;
+// reverse kernel: per-warp staging to write g0 row-major with coalesced stores
+constexpr int kStageBytes = 32 * 16 * 4;
 constexpr int kDbgWords = 1024;
 
 // forward: ring (3 x 68 KB) | step-0 operand (KP x W) | ones tile (4 KB) | we, be | barriers
 // reverse: ring (3 x 64 KB) | we | dwe accumulator | barriers
 inline size_t smem_bytes(bool forward, int KP) {
   const size_t ring = (size_t)kRing * (kLayerWBytes + (forward ? kBiasBytes : 0));
-  const size_t tail = forward ? (size_t)KP * kW * 4 + 4096 + (kW + 4) * 4 : 2 * (size_t)kW * 4;
+  const size_t tail = forward ? (size_t)KP * kW * 4 + 4096 + (kW + 4) * 4
+                              : 2 * (size_t)kW * 4 + (size_t)4 * kNT * kStageBytes;
   return ring + tail + (size_t)(2 * kNT + 2 * kRing + 1) * 8 + 64;
 }
 
@@ -425,6 +428,8 @@ struct BwdTmemParams {
   int nb;
   Tiling work;
   int* status;
+  long long* dbg;   // optional timeline, same layout as the forward's
+  int dbg_item;     // which work item of CTA 0 is stamped
 };
 
 __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams p) {
@@ -434,7 +439,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
   unsigned char* ring = smem;                                         // [kRing][64 KB]
   float* we = reinterpret_cast<float*>(ring + (size_t)kRing * kLayerWBytes);
   float* dwe_acc = we + W;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dwe_acc + W);
+  float4* stage_all = reinterpret_cast<float4*>(dwe_acc + W);          // [8 warps][32 rows][4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + 4 * kNT * (kStageBytes / 16));
   uint64_t* a_ready = bars;
   uint64_t* d_ready = bars + kNT;
   uint64_t* w_full = bars + 2 * kNT;
@@ -472,6 +478,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
       const uint32_t col_x = tmem_base + lane_off + (uint32_t)(t * 2 * W);
       const uint32_t col_y = col_x + W;
       uint32_t ph_d = 0;
+      if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[999] = clock64();
       for (int k = 0;; ++k) {
         int64_t tile0;
         const int n = work_item(p.work, k, tile0);
@@ -480,6 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
         const int64_t tile_id = tile0 + t;
         const int64_t r = tile_id * 128 + row;
         const bool valid = r < p.R;
+        if (p.dbg && blockIdx.x == 0 && row == 0 && t == 0 && k < 8) p.dbg[960 + k * 4 + 0] = clock64();
         const float de = valid ? (p.dE ? p.dE[r] : 1.0f) : 0.f;
         // masks of the topmost layer now, every other layer one step ahead
         uint4 mnext = *reinterpret_cast<const uint4*>(
@@ -494,6 +502,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
 #pragma unroll
           for (int c32 = 0; c32 < W / 32; ++c32) {
             uint32_t v[32];
+            // the chunk's eight h_nb loads together: one exposed latency per chunk, not
+            // per float4 (the serial version cost ~60k cycles per work item, measured)
+            float4 hbuf[8];
+            if (hn) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) hbuf[q] = hn[TT::chunk_f4(row, c32 * 8 + q)];
+            }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const int c = c32 * 8 + q;
@@ -506,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
               v[q * 4 + 3] = tf32_rn_bits(__float_as_uint(g4.w));
               if (gy_top) gy_top[TT::chunk_f4(row, c)] = g4;   // fp32: exact bias sums
               if (hn) {
-                const float4 h4 = hn[TT::chunk_f4(row, c)];
+                const float4 h4 = hbuf[q];
                 const float s0 = warp_sum(de * h4.x), s1 = warp_sum(de * h4.y);
                 const float s2 = warp_sum(de * h4.z), s3 = warp_sum(de * h4.w);
                 if (lane == 0) {
@@ -517,9 +532,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
             }
             tmem_st32(col_x + c32 * 32, v);
           }
+          if (p.dbg && blockIdx.x == 0 && row == 0 && t == 0 && k < 8) p.dbg[960 + k * 4 + 1] = clock64();
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&a_ready[t]);
+          if (p.dbg && blockIdx.x == 0 && row == 0 && t == 0 && k < 8) p.dbg[960 + k * 4 + 2] = clock64();
         }
         // One reverse step for forward layer i (2nb .. 1).
         //   even layer (W2_j): D = Y, masked in place -> A operand of the W1_j step
@@ -537,6 +554,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
           mbar_wait(&d_ready[t], ph_d, abort_flag, p.status, 500 + i);
           ph_d ^= 1;
           tc_fence_after();
+          const bool stamp = p.dbg && blockIdx.x == 0 && k == p.dbg_item && row == 0;
+          const int si = 2 * p.nb - i;          // step number 0 .. 2nb-1
+          if (stamp) p.dbg[(si * kNT + t) * 5 + 0] = clock64();
           const uint32_t col_d = kOdd ? col_x : col_y;
           auto chunk = [&](int c32, uint32_t (&v)[32]) {
             const uint32_t bits = mbits[c32];
@@ -558,11 +578,37 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
                 v[q * 4 + 1] = tf32_rn_bits(__float_as_uint(o.y));
                 v[q * 4 + 2] = tf32_rn_bits(__float_as_uint(o.z));
                 v[q * 4 + 3] = tf32_rn_bits(__float_as_uint(o.w));
-              } else if (valid) {
-                *reinterpret_cast<float4*>(p.g0 + r * W + c * 4) = o;
+              } else {
+                v[q * 4 + 0] = __float_as_uint(o.x); v[q * 4 + 1] = __float_as_uint(o.y);
+                v[q * 4 + 2] = __float_as_uint(o.z); v[q * 4 + 3] = __float_as_uint(o.w);
               }
             }
-            if (!kLast) tmem_st32(col_d + c32 * 32, v);
+            if (!kLast) {
+              tmem_st32(col_d + c32 * 32, v);
+            } else {
+              // g0 is row-major [R, W]: a thread owns a row, so its own stores would hit
+              // one 128-byte line per lane.  Transpose 32 rows x 16 columns at a time
+              // through a swizzled per-warp staging buffer: 8 rows x 64 B per store.
+              float4* stage = stage_all + warp * (kStageBytes / 16);
+              const int64_t row0 = tile_id * 128 + (warp & 3) * 32;
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  stage[lane * 4 + (j ^ ((lane >> 1) & 3))] = make_float4(
+                      __uint_as_float(v[half * 16 + j * 4 + 0]), __uint_as_float(v[half * 16 + j * 4 + 1]),
+                      __uint_as_float(v[half * 16 + j * 4 + 2]), __uint_as_float(v[half * 16 + j * 4 + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  const int rr = kk * 8 + (lane >> 2), jj = lane & 3;
+                  const float4 x = stage[rr * 4 + (jj ^ ((rr >> 1) & 3))];
+                  if (row0 + rr < p.R)
+                    *reinterpret_cast<float4*>(p.g0 + (row0 + rr) * W + c32 * 32 + half * 16 + jj * 4) = x;
+                }
+                __syncwarp();
+              }
+            }
           };
           // TMEM loads one chunk ahead of the arithmetic (see the forward kernel)
           uint32_t va[32], vb[32];
@@ -571,6 +617,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
           tmem_ld_wait(vb); tmem_ld32(col_d + 64, va); chunk(1, vb);
           tmem_ld_wait(va); tmem_ld32(col_d + 96, vb); chunk(2, va);
           tmem_ld_wait(vb); chunk(3, vb);
+          if (stamp) p.dbg[(si * kNT + t) * 5 + 1] = clock64();
           if (!kLast) {
             tmem_st_wait();
             tc_fence_before();
@@ -578,6 +625,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
           } else {
             tc_fence_before();
           }
+          if (stamp) p.dbg[(si * kNT + t) * 5 + 2] = clock64();
         };
         using T_ = std::true_type;
         using F_ = std::false_type;
@@ -588,6 +636,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
         }
         step(F_{}, F_{}, 2);
         step(T_{}, T_{}, 1);
+        if (p.dbg && blockIdx.x == 0 && row == 0 && k < 8) p.dbg[1000 + k * 2 + t] = clock64();
       }
     }
   } else if (warp == 4 * kNT) {
@@ -647,12 +696,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
           mbar_wait(&w_full[slot], (q / kRing) & 1, abort_flag, p.status, 800 + s);
           tc_fence_after();
           pipe_acquire(&s_pipe, abort_flag);
+          const bool mstamp = p.dbg && blockIdx.x == 0 && k == p.dbg_item;
+          if (mstamp) p.dbg[(s * kNT + t) * 5 + 3] = clock64();
           mma_tf32_ts_steps<kKSteps>(
               d_tmem, a_tmem, smem_desc(smem_u32(ring + (size_t)slot * kLayerWBytes), b_lbo, sbo),
               b_step16, idesc, 0u);
           mma_commit(&w_empty[slot]);
           mma_commit(&d_ready[t]);
           pipe_release(&s_pipe);
+          if (mstamp) p.dbg[(s * kNT + t) * 5 + 4] = clock64();
         }
         __syncwarp();
         ph_a ^= 1;
@@ -725,10 +777,6 @@ int tmem_forward(ibc_handle* h, const float* act, int64_t R, int64_t n, const fl
         const long long* e = &hb[(i * kNT + t) * 5];
         fprintf(stderr, "[ibc timeline tmem] %3d %d | %8lld %8lld | %8lld %8lld %8lld\n", i, t,
                 e[3] - t0, e[4] - t0, e[0] - t0, e[1] - t0, e[2] - t0);
-        if (t == 0 && (i & 1) == 0 && i < 46)
-          fprintf(stderr, "[ibc timeline tmem]       even-step chunks (from epi_start): ld0 %lld c0 %lld ld1 %lld c1 %lld c2 %lld c3 %lld\n",
-                  hb[640 + i * 8 + 0] - e[0], hb[640 + i * 8 + 1] - e[0], hb[640 + i * 8 + 2] - e[0],
-                  hb[640 + i * 8 + 3] - e[0], hb[640 + i * 8 + 4] - e[0], hb[640 + i * 8 + 5] - e[0]);
       }
   }
   return IBC_OK;
@@ -753,8 +801,38 @@ int tmem_reverse(ibc_handle* h, const float* dE, int64_t R, const float* xa_save
     IBC_TRY(raise_smem(h, mlp_bwd_tmem_kernel));
     attr = true;
   }
+  p.dbg = nullptr;
+  p.dbg_item = getenv("IBC_DBG_ITEM") ? atoi(getenv("IBC_DBG_ITEM")) : 0;
+  static const bool want_dbg = getenv("IBC_DBG_TIMELINE") != nullptr;
+  if (want_dbg) {
+    IBC_CUDA(h, cudaMalloc((void**)&p.dbg, kDbgWords * sizeof(long long)));
+    IBC_CUDA(h, cudaMemsetAsync(p.dbg, 0, kDbgWords * sizeof(long long), s));
+  }
   mlp_bwd_tmem_kernel<<<grid, kThreads, smem_bytes(false, 0), s>>>(p);
   IBC_LAUNCH_CHECK(h);
+  if (p.dbg) {
+    cudaStreamSynchronize(s);
+    std::vector<long long> hb(kDbgWords);
+    cudaMemcpy(hb.data(), p.dbg, hb.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(p.dbg);
+    const long long t0 = hb[3];
+    for (int k = 0; k < 8; ++k)
+      if (hb[960 + k * 4])
+        fprintf(stderr, "[ibc timeline rev] CTA 0 tile 0 item %d: start %lld, top-of-chain done %lld, arrived %lld\n", k,
+                hb[960 + k * 4] - hb[999], hb[960 + k * 4 + 1] - hb[999], hb[960 + k * 4 + 2] - hb[999]);
+    for (int k = 0; k < 8; ++k)
+      if (hb[1000 + k * 2] || hb[1000 + k * 2 + 1])
+        fprintf(stderr, "[ibc timeline rev] CTA 0 item %d done at %lld / %lld cycles after kernel start\n", k,
+                hb[1000 + k * 2] ? hb[1000 + k * 2] - hb[999] : 0,
+                hb[1000 + k * 2 + 1] ? hb[1000 + k * 2 + 1] - hb[999] : 0);
+    fprintf(stderr, "[ibc timeline rev] step tile | mma_start mma_issued | epi_start epi_done arrived\n");
+    for (int i = 0; i < 2 * L.nb && i < 64; ++i)
+      for (int t = 0; t < kNT; ++t) {
+        const long long* e = &hb[(i * kNT + t) * 5];
+        fprintf(stderr, "[ibc timeline rev] %3d %d | %8lld %8lld | %8lld %8lld %8lld\n", i, t,
+                e[3] - t0, e[4] - t0, e[0] - t0, e[1] - t0, e[2] - t0);
+      }
+  }
   return IBC_OK;
 }
 

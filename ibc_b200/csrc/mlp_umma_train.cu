@@ -372,6 +372,46 @@ __global__ void __launch_bounds__(kW) first_layer_grads_kernel(
   }
 }
 
+// dwe[w] += sum_r dE[r] * h_nb[r, w] over the forward's last saved slot (tile layout
+// [sub-tile][chunk][32 rows][4]).  Lane = row of a sub-tile, warp = 4 of the 32
+// chunks: loads are 512 contiguous bytes per warp, every lane keeps 16 partial sums
+// across all the tiles its block visits, and the cross-row reduction happens once
+// per block.  (Doing this inside the reverse kernel cost 128 warp reductions per
+// tile in front of every chain: ~20% of that kernel.)
+__global__ void __launch_bounds__(256) dwe_kernel(const float* __restrict__ xa_save,
+                                                  const float* __restrict__ dE, int64_t R,
+                                                  int num_tiles, int nb, float* __restrict__ dwe) {
+  using TT = TrainTile<kW>;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const float4* hn = reinterpret_cast<const float4*>(
+        xa_save + TT::slot_base(tile, 2 * nb + 1, 2 * nb));
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+      const int64_t r = (int64_t)tile * 128 + sub * 32 + lane;
+      const float de = r < R ? dE[r] : 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const float4 h4 = hn[TT::chunk_f4(sub * 32 + lane, warp * 4 + cc)];
+        acc[cc * 4 + 0] = fmaf(de, h4.x, acc[cc * 4 + 0]);
+        acc[cc * 4 + 1] = fmaf(de, h4.y, acc[cc * 4 + 1]);
+        acc[cc * 4 + 2] = fmaf(de, h4.z, acc[cc * 4 + 2]);
+        acc[cc * 4 + 3] = fmaf(de, h4.w, acc[cc * 4 + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) atomicAdd(dwe + warp * 16 + i, v);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // weight gradient
 // ---------------------------------------------------------------------------
@@ -789,7 +829,13 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
                                      (int)WgradSmem::kBytes));
     attr_done = true;
   }
-  IBC_TRY(umma_reverse(h, dE, R, xa, masks, gy, g0, grads + L.we, s));
+  IBC_TRY(umma_reverse(h, dE, R, xa, masks, gy, g0, nullptr, s));
+  {  // Dense(1) weight gradient from the forward's last slot
+    const int tiles = (int)((R + 127) / 128);
+    const int blocks = tiles < 2 * h->sm_count ? tiles : 2 * h->sm_count;
+    dwe_kernel<<<blocks, 256, 0, s>>>(xa, dE, R, tiles, nb, grads + L.we);
+    IBC_LAUNCH_CHECK(h);
+  }
   mark(3);
   {
     WgradParams wp;
