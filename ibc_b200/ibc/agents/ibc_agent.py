@@ -331,16 +331,28 @@ class ImplicitBCAgent(BehavioralCloningAgent):
       if not math.isfinite(float(loss)):
         raise FloatingPointError('Loss is inf or nan')
       return
-    prev = getattr(self, '_pending_finite', None)
-    if prev is not None:
-      prev_loss, ev = prev
+    # Deferred: the loss is copied to pinned host memory behind the step's kernels and
+    # looked at (a plain host read, no CUDA call, no stream sync) once its event has
+    # completed -- typically while the next step is being submitted.
+    pending = getattr(self, '_pending_finite', None)
+    if pending is not None:
+      host, ev = pending
       if not ev.query():
         return                        # still in flight: keep waiting on the older one
-      if not math.isfinite(float(prev_loss)):     # event done: a 4-byte read, no stall
+      self._pending_finite = None
+      if not math.isfinite(float(host[0])):
         raise FloatingPointError('Loss is inf or nan')
+    else:
+      host = None
+    if host is None:
+      host = getattr(self, '_finite_host', None)
+      if host is None:
+        host = torch.empty(1, dtype=torch.float32, pin_memory=True)
+        self._finite_host = host
+    host.copy_(loss.detach().reshape(1), non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
-    self._pending_finite = (loss, ev)
+    self._pending_finite = (host, ev)
 
   def _train(self, experience, weights=None, draws=None):
     loss_info, grads = self._loss(experience, weights=weights, training=True, draws=draws)
