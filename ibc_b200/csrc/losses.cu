@@ -50,7 +50,9 @@ info_nce_kernel(const float* __restrict__ pred, int n1, float temperature, float
   for (int j = tid; j < n1; j += 128) {
     const float p = __fdiv_rn(expf(__fdiv_rn(row[j], temperature) - mx), sum);
     const float yt = (j == n1 - 1) ? 1.0f : kKerasEps;
-    const float yp = fminf(fmaxf(p, kKerasEps), 1.0f);
+    // tf.clip_by_value propagates NaN (fminf / fmaxf would swallow it and hide a
+    // diverged network from check_numerics, base_agent.py:46)
+    const float yp = (p != p) ? p : fminf(fmaxf(p, kKerasEps), 1.0f);
     l += yt * logf(__fdiv_rn(yt, yp));
     // d loss / d p_j = -yt / p_j where the clip passes gradient
     const bool inside = (p >= kKerasEps) && (p <= 1.0f);
@@ -94,7 +96,7 @@ grad_penalty_kernel(const float* __restrict__ dEda, int n1, int A, int norm_type
     if (margin >= 0.f) {
       x = nrm - margin;
       dx = (x >= 0.f && x <= 1e10f) ? 1.f : 0.f;
-      x = fminf(fmaxf(x, 0.f), 1e10f);
+      x = (x != x) ? x : fminf(fmaxf(x, 0.f), 1e10f);
     }
     float pen = x;
     if (square) { pen = x * x; dx *= 2.f * x; }

@@ -176,6 +176,28 @@ def test_agent_tf32_training_reduces_loss():
   assert 'ebm_total_loss' in ev and torch.isfinite(ev['ebm_total_loss'])
 
 
+def test_check_numerics_raises_on_non_finite_loss():
+  """base_agent.py:46 (tf.debugging.check_numerics on the loss): the deferred check
+  raises within a couple of steps after the parameters go non-finite, 'sync' raises
+  inside the offending step."""
+  from ibc_b200 import _lib
+  spec = omlp.MLPSpec(20, 2, 128, 2)
+  obs = torch.randn(32, 1, spec.obs_dim)
+  act = torch.rand(32, 2) * 2 - 1
+  for mode in ('deferred', 'sync'):
+    net, agent = _build(spec, 16, _lib.PRECISION_TF32, fraction_langevin_samples=0.0,
+                        add_grad_penalty=False)
+    agent.check_numerics = mode
+    agent.train((({'obs': obs}, act), ()))
+    torch.cuda.synchronize()
+    net.params.fill_(float('nan'))
+    net.params_changed()
+    with pytest.raises(FloatingPointError):
+      for _ in range(4):
+        agent.train((({'obs': obs}, act), ()))
+        torch.cuda.synchronize()
+
+
 def test_policy_dfo_action():
   from ibc_b200 import _lib
   from ibc_b200.ibc import specs
