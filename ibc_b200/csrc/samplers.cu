@@ -70,52 +70,105 @@ resample_kernel(const float* __restrict__ logits, const double* __restrict__ uni
   __syncthreads();
   const double dmx = (double)s_max;
 
-  // 2. weights (parallel), 3. strictly sequential fp64 accumulation
-  for (int j = tid; j < n; j += nt) {
-    const float l = row[j];
-    cdf[j] = isfinite(l) ? exp64_portable(__dadd_rn((double)l, -dmx)) : 0.0;
-    cnt[j] = 0;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    // same left-to-right order as the CPU loop; loads are batched ahead of the
-    // dependent add chain so only the fp64 add latency is serial
-    double total = 0.0;
-    int j = 0;
-    for (; j + 16 <= n; j += 16) {
-      double w[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) w[q] = cdf[j + q];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) { total = __dadd_rn(total, w[q]); w[q] = total; }
-#pragma unroll
-      for (int q = 0; q < 16; ++q) cdf[j + q] = w[q];
+  // 2. weights (parallel).  3. CDF.  The specification is the strictly sequential
+  // fp64 accumulation of TF's CPU multinomial kernel.  16 384 dependent fp64 adds are
+  // ~150 us of a 190 us kernel, so the CDF is first built by a parallel scan (same
+  // terms, another association): both sums carry a relative error <= n * 2^-53 of the
+  // running total, hence a draw whose to_find is farther than eps = 4 n 2^-53 * total
+  // from both neighbouring CDF entries selects the same index under either CDF (the
+  // code uses twice that margin).  Draws
+  // are searched in the scanned CDF and checked against that margin; only if one of
+  // them is ambiguous (probability ~2 n count 2^-51, about 1e-3 per call at n = count
+  // = 16 384) does the block fall back to the sequential chain and repeat its draws.
+  // The result is bit-identical to the sequential specification in every case.
+  __shared__ int s_ambiguous;
+  __shared__ double s_warp_tot[32];
+  const double eps_rel = 8.0 * (double)n * 1.1102230246251565e-16;   // 2x margin
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int j = tid; j < n; j += nt) {
+      const float l = row[j];
+      cdf[j] = isfinite(l) ? exp64_portable(__dadd_rn((double)l, -dmx)) : 0.0;
+      cnt[j] = 0;
     }
-    for (; j < n; ++j) {
-      total = __dadd_rn(total, cdf[j]);
-      cdf[j] = total;
+    if (tid == 0) s_ambiguous = 0;
+    __syncthreads();
+    if (pass == 0) {
+      // blocked inclusive scan: contiguous segment per thread, then across threads
+      const int seg = (n + nt - 1) / nt;
+      const int j0 = min(n, tid * seg), j1 = min(n, j0 + seg);
+      double local = 0.0;
+      for (int j = j0; j < j1; ++j) local += cdf[j];
+      double incl = local;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((tid & 31) >= o) incl += up;
+      }
+      if ((tid & 31) == 31) s_warp_tot[tid >> 5] = incl;
+      __syncthreads();
+      if (tid < 32) {
+        double w = (tid < (nt + 31) / 32) ? s_warp_tot[tid] : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double up = __shfl_up_sync(0xffffffffu, w, o);
+          if (tid >= o) w += up;
+        }
+        s_warp_tot[tid] = w;        // inclusive totals of the warps
+      }
+      __syncthreads();
+      double run = (incl - local) + ((tid >> 5) > 0 ? s_warp_tot[(tid >> 5) - 1] : 0.0);
+      for (int j = j0; j < j1; ++j) { run += cdf[j]; cdf[j] = run; }
+    } else if (tid == 0) {
+      // same left-to-right order as the CPU loop; loads are batched ahead of the
+      // dependent add chain so only the fp64 add latency is serial
+      double total = 0.0;
+      int j = 0;
+      for (; j + 16 <= n; j += 16) {
+        double w[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) w[q] = cdf[j + q];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) { total = __dadd_rn(total, w[q]); w[q] = total; }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) cdf[j + q] = w[q];
+      }
+      for (; j < n; ++j) {
+        total = __dadd_rn(total, cdf[j]);
+        cdf[j] = total;
+      }
     }
-  }
-  __syncthreads();
-  const double total = n > 0 ? cdf[n - 1] : 0.0;
+    __syncthreads();
+    const double total = n > 0 ? cdf[n - 1] : 0.0;
+    const double eps = eps_rel * total;
 
-  // 4. draws: to_find = u * total; std::upper_bound
-  for (int s = tid; s < count; s += nt) {
-    double u;
-    if (uniforms) {
-      u = uniforms[(int64_t)b * count + s];
-    } else {
-      u = philox_uniform_double(seed, rng_stream, (uint64_t)b * (uint64_t)count + s);
+    // 4. draws: to_find = u * total; std::upper_bound
+    bool ambiguous = false;
+    for (int s = tid; s < count; s += nt) {
+      double u;
+      if (uniforms) {
+        u = uniforms[(int64_t)b * count + s];
+      } else {
+        u = philox_uniform_double(seed, rng_stream, (uint64_t)b * (uint64_t)count + s);
+      }
+      const double to_find = __dmul_rn(u, total);
+      int lo = 0, hi = n;
+      while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (cdf[mid] > to_find) hi = mid; else lo = mid + 1;
+      }
+      if (pass == 0) {
+        // cdf[lo - 1] <= to_find < cdf[lo]: too close to either neighbour?
+        if (lo > 0 && to_find - cdf[lo - 1] <= eps) ambiguous = true;
+        if (lo < n && cdf[lo] - to_find <= eps) ambiguous = true;
+      }
+      if (lo > n - 1) lo = n - 1;
+      if (draws) draws[(int64_t)b * count + s] = lo;
+      atomicAdd(&cnt[lo], 1);
     }
-    const double to_find = __dmul_rn(u, total);
-    int lo = 0, hi = n;
-    while (lo < hi) {
-      const int mid = lo + ((hi - lo) >> 1);
-      if (cdf[mid] > to_find) hi = mid; else lo = mid + 1;
-    }
-    if (lo > n - 1) lo = n - 1;
-    if (draws) draws[(int64_t)b * count + s] = lo;
-    atomicAdd(&cnt[lo], 1);
+    if (pass == 0 && ambiguous) s_ambiguous = 1;
+    __syncthreads();
+    if (pass == 1 || !s_ambiguous) break;
+    __syncthreads();
   }
   __syncthreads();
   if (counts)

@@ -36,17 +36,21 @@ def collect_particle_episodes(num_episodes, n_dim=2, seed=0, **oracle_kwargs):
 
 
 def windows_from_episodes(episodes, sequence_length=2):
-  """Every window of `sequence_length` consecutive steps that lies inside an episode:
-  observations [S, T, d] per key, action [S, A] = the action taken at the window's last
-  step (get_data.py:57-59)."""
+  """One window per step t of every episode: the `sequence_length` most recent
+  observations, the episode's first frame replicated where the window would reach
+  before it (data/dataset.py:29-84, 114-125 of the reference: "a sequence of [0, 1, 2]
+  with seq_len = 2 produces [0, 0], [0, 1], [1, 2]" -- the same padding the evaluation
+  environment's HistoryWrapper applies), and the action taken at step t
+  (get_data.py:57-59).  Returns observations [S, T, d] per key and actions [S, A]."""
   obs_out, act_out = None, []
   for obs, act in episodes:
     steps = act.shape[0]
-    for t in range(sequence_length - 1, steps):
+    for t in range(steps):
+      idx = np.maximum(np.arange(t - sequence_length + 1, t + 1), 0)
       if obs_out is None:
         obs_out = {k: [] for k in obs}
       for k in obs:
-        obs_out[k].append(obs[k][t - sequence_length + 1:t + 1])
+        obs_out[k].append(obs[k][idx])
       act_out.append(act[t])
   observations = {k: np.stack(v).astype(np.float32) for k, v in obs_out.items()}
   return observations, np.stack(act_out).astype(np.float32)

@@ -53,7 +53,7 @@ def train_eval(task='PARTICLE', root_dir=None, dataset_path=None, loss_type='ebm
                decay_steps=100, replay_capacity=100000, eval_interval=1000, eval_episodes=20,
                fused_train_steps=100, sequence_length=2, uniform_boundary_buffer=0.05,
                goal_tolerance=0.02, seed=0, dataset_eval_fraction=0.0, image_obs=False,
-               num_demo_episodes=2000, log=print):
+               num_demo_episodes=2000, precision=None, log=print):
   del root_dir, dataset_path, replay_capacity, fused_train_steps, goal_tolerance
   del dataset_eval_fraction
   if task != 'PARTICLE':
@@ -92,6 +92,10 @@ def train_eval(task='PARTICLE', root_dir=None, dataset_path=None, loss_type='ebm
                                          observation=obs_tensor_spec)
   cloning_network = MLPEBM((obs_tensor_spec, action_tensor_spec), specs.TensorSpec((1,)),
                            seed=seed)
+  if precision is not None:          # 'fp32' forces the exact FMA kernels (A/B runs)
+    from ibc_b200 import _lib
+    cloning_network.engine.set_precision(
+        {'fp32': _lib.PRECISION_FP32, 'tf32': _lib.PRECISION_TF32}[precision])
   agent = agent_module.get_agent(
       loss_type, time_step_tensor_spec, action_tensor_spec, action_sampling_spec,
       norm_info.obs_norm_layer, norm_info.act_norm_layer, norm_info.act_denorm_layer,

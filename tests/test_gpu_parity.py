@@ -180,6 +180,31 @@ def test_resample_bit_exact(b, n, count, scale):
   assert np.array_equal(rows.cpu().numpy(), want_rows)
 
 
+def test_resample_bit_exact_on_cdf_boundaries():
+  """Draws that land (to rounding) exactly on CDF boundaries: the parallel-scan CDF
+  cannot decide them, the kernel must fall back to the sequential chain and still
+  agree with the oracle bit for bit."""
+  from ibc_b200 import engine as eng
+  rs = np.random.RandomState(7)
+  b, n = 3, 4096
+  logits = (rs.randn(b, n) * 2.0).astype(np.float32)
+  w = np.exp(logits.astype(np.float64) - logits.max(axis=1, keepdims=True))
+  cdf = np.cumsum(w, axis=1)
+  u = rs.rand(b, n)
+  pick = rs.randint(0, n - 1, size=(b, 64))
+  for i in range(b):
+    u[i, :64] = cdf[i, pick[i]] / cdf[i, -1]          # on (or one ulp off) a boundary
+    u[i, 64:96] = np.nextafter(u[i, :32], 0.0)
+    u[i, 96:128] = np.nextafter(u[i, :32], 1.0)
+  u = np.clip(u, 0.0, np.nextafter(1.0, 0.0))
+  want_draws, want_counts, want_rows = resample_c.resample(logits, u)
+  rows, draws, counts = eng.resample(torch.from_numpy(logits).cuda(),
+                                     torch.from_numpy(u).cuda(), True, True)
+  assert np.array_equal(draws.cpu().numpy(), want_draws)
+  assert np.array_equal(counts.cpu().numpy(), want_counts)
+  assert np.array_equal(rows.cpu().numpy(), want_rows)
+
+
 def test_resample_known_answer():
   from ibc_b200 import engine as eng
   logits = torch.tensor([[0.0, math.log(3.0)]], dtype=torch.float32)

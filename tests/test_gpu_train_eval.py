@@ -25,7 +25,7 @@ def test_particle_train_eval_short_run():
     gin.clear_config()
   hist = out['history']
   assert [r['step'] for r in hist] == [60, 120]
-  assert out['num_windows'] == 100 * 49 and out['n_dim'] == 2
+  assert out['num_windows'] == 100 * 50 and out['n_dim'] == 2
   for r in hist:
     for key in ('loss', 'ebm_total_loss', 'grad_loss', 'mse_counter_examples',
                 'AverageSuccessMetric', 'AverageFirstGoalDistance',

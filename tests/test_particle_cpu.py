@@ -81,11 +81,18 @@ def test_history_wrapper_tiles_first_observation():
 def test_windows_from_episodes():
   eps = in_memory.collect_particle_episodes(3, n_dim=2, seed=5)
   obs, act = in_memory.windows_from_episodes(eps, sequence_length=2)
-  assert act.shape == (3 * 49, 2) and obs['pos_agent'].shape == (3 * 49, 2, 2)
+  assert act.shape == (3 * 50, 2) and obs['pos_agent'].shape == (3 * 50, 2, 2)
   e_obs, e_act = eps[0]
-  np.testing.assert_array_equal(obs['pos_agent'][0], e_obs['pos_agent'][0:2])
-  np.testing.assert_array_equal(act[0], e_act[1])            # action of the window's last step
-  np.testing.assert_array_equal(obs['pos_agent'][48], e_obs['pos_agent'][48:50])
+  # first step: the first frame is replicated (dataset.py:122-125), action of step 0
+  np.testing.assert_array_equal(obs['pos_agent'][0], e_obs['pos_agent'][[0, 0]])
+  np.testing.assert_array_equal(act[0], e_act[0])
+  np.testing.assert_array_equal(obs['pos_agent'][1], e_obs['pos_agent'][0:2])
+  np.testing.assert_array_equal(act[1], e_act[1])            # action of the window's last step
+  np.testing.assert_array_equal(obs['pos_agent'][49], e_obs['pos_agent'][48:50])
+  # second episode starts with its own replicated first frame
+  np.testing.assert_array_equal(obs['pos_agent'][50], eps[1][0]['pos_agent'][[0, 0]])
+  obs3, _ = in_memory.windows_from_episodes(eps[:1], sequence_length=3)
+  np.testing.assert_array_equal(obs3['pos_agent'][1], e_obs['pos_agent'][[0, 0, 1]])
   # the oracle's action is one of the two goals
   assert np.all(np.isclose(act[:, None, :], np.stack(
       [obs['pos_first_goal'][:, -1], obs['pos_second_goal'][:, -1]], 1)).all(-1).any(-1))
