@@ -34,8 +34,83 @@ __device__ __forceinline__ double exp64_portable(double x) {
   return __dmul_rn(p, __longlong_as_double(bits));
 }
 
+constexpr int kResampleBuckets = 2048;    // value-space index over the CDF (power of two)
+constexpr int kResampleHeavy = 512;       // classes expanded by the whole block
+
+// Block-wide inclusive scans over shared memory, element j = base + tid (no bank
+// conflicts; a contiguous segment per thread is a 32-way conflict on every access
+// and made the two scans 40% of the kernel).
+__device__ __forceinline__ void block_scan_inplace(double* a, int n, double* s_w) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int nw = (nt + 31) >> 5;
+  double carry = 0.0;
+  for (int base = 0; base < n; base += nt) {
+    const int j = base + tid;
+    double v = (j < n) ? a[j] : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double up = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += up;
+    }
+    if (lane == 31) s_w[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      double w = (lane < nw) ? s_w[lane] : 0.0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += up;
+      }
+      s_w[lane] = w;
+    }
+    __syncthreads();
+    if (j < n) a[j] = v + (carry + (warp > 0 ? s_w[warp - 1] : 0.0));
+    carry += s_w[nw - 1];
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void block_scan_inplace(int* a, int n, int* s_w) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int nw = (nt + 31) >> 5;
+  int carry = 0;
+  for (int base = 0; base < n; base += nt) {
+    const int j = base + tid;
+    int v = (j < n) ? a[j] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += up;
+    }
+    if (lane == 31) s_w[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      int w = (lane < nw) ? s_w[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += up;
+      }
+      s_w[lane] = w;
+    }
+    __syncthreads();
+    if (j < n) a[j] = v + carry + (warp > 0 ? s_w[warp - 1] : 0);
+    carry += s_w[nw - 1];
+    __syncthreads();
+  }
+}
+
+// std::upper_bound over a[lo, hi): first index with a[j] > x, hi if none
+__device__ __forceinline__ int upper_bound_range(const double* a, int lo, int hi, double x) {
+  while (lo < hi) {
+    const int mid = lo + ((hi - lo) >> 1);
+    if (a[mid] > x) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
 // One block per observation row.  Dynamic smem: double cdf[n]; int cnt[n];
-// int part[blockDim.x].
+// int tab[kResampleBuckets + 1]; int heavy[kResampleHeavy].
 __global__ void __launch_bounds__(1024)
 resample_kernel(const float* __restrict__ logits, const double* __restrict__ uniforms,
                 int n, int count, uint64_t seed, uint64_t rng_stream,
@@ -44,9 +119,14 @@ resample_kernel(const float* __restrict__ logits, const double* __restrict__ uni
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* cdf = reinterpret_cast<double*>(smem_raw);
   int* cnt = reinterpret_cast<int*>(cdf + n);
-  int* part = cnt + n;
+  int* tab = cnt + n;
+  int* heavy = tab + kResampleBuckets + 1;
   __shared__ float s_red[32];
   __shared__ float s_max;
+  __shared__ double s_wd[32];
+  __shared__ int s_wi[32];
+  __shared__ int s_ambiguous;
+  __shared__ int s_nheavy;
   const int b = blockIdx.x;
   const int tid = threadIdx.x, nt = blockDim.x;
   const float* row = logits + (int64_t)b * n;
@@ -72,18 +152,22 @@ resample_kernel(const float* __restrict__ logits, const double* __restrict__ uni
 
   // 2. weights (parallel).  3. CDF.  The specification is the strictly sequential
   // fp64 accumulation of TF's CPU multinomial kernel.  16 384 dependent fp64 adds are
-  // ~150 us of a 190 us kernel, so the CDF is first built by a parallel scan (same
-  // terms, another association): both sums carry a relative error <= n * 2^-53 of the
-  // running total, hence a draw whose to_find is farther than eps = 4 n 2^-53 * total
-  // from both neighbouring CDF entries selects the same index under either CDF (the
-  // code uses twice that margin).  Draws
-  // are searched in the scanned CDF and checked against that margin; only if one of
-  // them is ambiguous (probability ~2 n count 2^-51, about 1e-3 per call at n = count
-  // = 16 384) does the block fall back to the sequential chain and repeat its draws.
-  // The result is bit-identical to the sequential specification in every case.
-  __shared__ int s_ambiguous;
-  __shared__ double s_warp_tot[32];
-  const double eps_rel = 8.0 * (double)n * 1.1102230246251565e-16;   // 2x margin
+  // ~80 us on one thread, so the CDF is first built by a parallel scan (same terms,
+  // another association): both sums carry a relative error <= n * 2^-53 of the running
+  // total, hence a draw whose to_find is farther than 4 n 2^-53 * total from both
+  // neighbouring CDF entries selects the same index under either CDF (the code uses
+  // twice that margin).  Draws are searched in the scanned CDF and checked against the
+  // margin; only if one of them is ambiguous (probability ~4 n count 2^-51, about
+  // 2e-3 per call at n = count = 16 384) does the block fall back to the sequential
+  // chain and repeat its draws.  The result is bit-identical to the sequential
+  // specification in every case.
+  // 4. Draws: to_find = u * total; std::upper_bound.  A value-space index (tab[k] =
+  // upper_bound(cdf, k/K * total)) confines each search to the entries of its bucket
+  // (v_k <= to_find < v_k+1 implies tab[k] <= answer <= tab[k+1] by monotonicity), so a
+  // draw costs a couple of shared-memory probes instead of log2(n) conflicting ones.
+  const double eps_rel = 8.0 * (double)n * 1.1102230246251565e-16;
+  const bool use_tab = n >= 4 * kResampleBuckets;
+  constexpr double kInvBuckets = 1.0 / kResampleBuckets;
   for (int pass = 0; pass < 2; ++pass) {
     for (int j = tid; j < n; j += nt) {
       const float l = row[j];
@@ -93,31 +177,7 @@ resample_kernel(const float* __restrict__ logits, const double* __restrict__ uni
     if (tid == 0) s_ambiguous = 0;
     __syncthreads();
     if (pass == 0) {
-      // blocked inclusive scan: contiguous segment per thread, then across threads
-      const int seg = (n + nt - 1) / nt;
-      const int j0 = min(n, tid * seg), j1 = min(n, j0 + seg);
-      double local = 0.0;
-      for (int j = j0; j < j1; ++j) local += cdf[j];
-      double incl = local;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const double up = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((tid & 31) >= o) incl += up;
-      }
-      if ((tid & 31) == 31) s_warp_tot[tid >> 5] = incl;
-      __syncthreads();
-      if (tid < 32) {
-        double w = (tid < (nt + 31) / 32) ? s_warp_tot[tid] : 0.0;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const double up = __shfl_up_sync(0xffffffffu, w, o);
-          if (tid >= o) w += up;
-        }
-        s_warp_tot[tid] = w;        // inclusive totals of the warps
-      }
-      __syncthreads();
-      double run = (incl - local) + ((tid >> 5) > 0 ? s_warp_tot[(tid >> 5) - 1] : 0.0);
-      for (int j = j0; j < j1; ++j) { run += cdf[j]; cdf[j] = run; }
+      block_scan_inplace(cdf, n, s_wd);
     } else if (tid == 0) {
       // same left-to-right order as the CPU loop; loads are batched ahead of the
       // dependent add chain so only the fp64 add latency is serial
@@ -140,8 +200,12 @@ resample_kernel(const float* __restrict__ logits, const double* __restrict__ uni
     __syncthreads();
     const double total = n > 0 ? cdf[n - 1] : 0.0;
     const double eps = eps_rel * total;
+    if (use_tab) {
+      for (int k = tid; k <= kResampleBuckets; k += nt)
+        tab[k] = upper_bound_range(cdf, 0, n, __dmul_rn((double)k * kInvBuckets, total));
+      __syncthreads();
+    }
 
-    // 4. draws: to_find = u * total; std::upper_bound
     bool ambiguous = false;
     for (int s = tid; s < count; s += nt) {
       double u;
@@ -152,10 +216,20 @@ resample_kernel(const float* __restrict__ logits, const double* __restrict__ uni
       }
       const double to_find = __dmul_rn(u, total);
       int lo = 0, hi = n;
-      while (lo < hi) {
-        const int mid = lo + ((hi - lo) >> 1);
-        if (cdf[mid] > to_find) hi = mid; else lo = mid + 1;
+      if (use_tab) {
+        int k = (int)(u * (double)kResampleBuckets);
+        k = max(0, min(kResampleBuckets - 1, k));
+        while (k > 0 && to_find < __dmul_rn((double)k * kInvBuckets, total)) --k;
+        while (k < kResampleBuckets - 1 &&
+               to_find >= __dmul_rn((double)(k + 1) * kInvBuckets, total)) ++k;
+        // u >= 1 (not produced by the samplers) or a NaN falls outside every bucket
+        if (to_find >= __dmul_rn((double)k * kInvBuckets, total) &&
+            to_find < __dmul_rn((double)(k + 1) * kInvBuckets, total)) {
+          lo = tab[k];
+          hi = tab[k + 1];
+        }
       }
+      lo = upper_bound_range(cdf, lo, hi, to_find);
       if (pass == 0) {
         // cdf[lo - 1] <= to_find < cdf[lo]: too close to either neighbour?
         if (lo > 0 && to_find - cdf[lo - 1] <= eps) ambiguous = true;
@@ -170,34 +244,30 @@ resample_kernel(const float* __restrict__ logits, const double* __restrict__ uni
     if (pass == 1 || !s_ambiguous) break;
     __syncthreads();
   }
-  __syncthreads();
   if (counts)
     for (int j = tid; j < n; j += nt) counts[(int64_t)b * n + j] = cnt[j];
   if (!rows) return;
 
-  // 5. rows = repeat(arange, counts): inclusive scan of cnt, then each output
-  // position looks its class up.
-  const int chunk = (n + nt - 1) / nt;
-  const int j0 = min(n, tid * chunk), j1 = min(n, j0 + chunk);
-  int local = 0;
-  for (int j = j0; j < j1; ++j) local += cnt[j];
-  part[tid] = local;
-  __syncthreads();
-  if (tid == 0) {
-    int run = 0;
-    for (int t = 0; t < nt; ++t) { const int v = part[t]; part[t] = run; run += v; }
+  // 5. rows = repeat(arange, counts): inclusive scan of cnt, then every class writes
+  // its own run; classes with long runs are left to the whole block.
+  if (tid == 0) s_nheavy = 0;
+  block_scan_inplace(cnt, n, s_wi);        // ends with __syncthreads()
+  int64_t* out = rows + (int64_t)b * count;
+  for (int j = tid; j < n; j += nt) {
+    const int end = cnt[j], start = (j > 0) ? cnt[j - 1] : 0;
+    const int c = end - start;
+    if (c >= 64) {
+      const int slot = atomicAdd(&s_nheavy, 1);
+      if (slot < kResampleHeavy) { heavy[slot] = j; continue; }
+    }
+    for (int q = start; q < end; ++q) out[q] = (int64_t)b * n + j;
   }
   __syncthreads();
-  int run = part[tid];
-  for (int j = j0; j < j1; ++j) { run += cnt[j]; cnt[j] = run; }   // inclusive
-  __syncthreads();
-  for (int p = tid; p < count; p += nt) {
-    int lo = 0, hi = n;
-    while (lo < hi) {
-      const int mid = lo + ((hi - lo) >> 1);
-      if (cnt[mid] > p) hi = mid; else lo = mid + 1;
-    }
-    rows[(int64_t)b * count + p] = (int64_t)b * n + lo;
+  const int nheavy = min(s_nheavy, kResampleHeavy);
+  for (int hslot = 0; hslot < nheavy; ++hslot) {
+    const int j = heavy[hslot];
+    const int end = cnt[j], start = (j > 0) ? cnt[j - 1] : 0;
+    for (int q = start + tid; q < end; q += nt) out[q] = (int64_t)b * n + j;
   }
 }
 
@@ -228,25 +298,26 @@ __global__ void scale_div_kernel(const float* __restrict__ x, float t, int64_t n
 }
 
 // One block per row: probs = softmax(logits / temperature).
-__global__ void __launch_bounds__(256)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 softmax_rows_kernel(const float* __restrict__ logits, int n, float temperature,
                     float* __restrict__ probs) {
-  __shared__ float s_red[8];
+  __shared__ float s_red[32];
   __shared__ float s_b;
   const int tid = threadIdx.x;
   const float* row = logits + (int64_t)blockIdx.x * n;
   float* out = probs + (int64_t)blockIdx.x * n;
   float mx = -INFINITY;
-  for (int j = tid; j < n; j += 256) mx = fmaxf(mx, __fdiv_rn(row[j], temperature));
+  for (int j = tid; j < n; j += NT) mx = fmaxf(mx, __fdiv_rn(row[j], temperature));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((tid & 31) == 0) s_red[tid >> 5] = mx;
   __syncthreads();
-  if (tid == 0) { float v = s_red[0]; for (int i = 1; i < 8; ++i) v = fmaxf(v, s_red[i]); s_b = v; }
+  if (tid == 0) { float v = s_red[0]; for (int i = 1; i < NT / 32; ++i) v = fmaxf(v, s_red[i]); s_b = v; }
   __syncthreads();
   mx = s_b;
   float sum = 0.f;
-  for (int j = tid; j < n; j += 256) {
+  for (int j = tid; j < n; j += NT) {
     const float e = expf(__fdiv_rn(row[j], temperature) - mx);
     out[j] = e;
     sum += e;
@@ -256,10 +327,10 @@ softmax_rows_kernel(const float* __restrict__ logits, int n, float temperature,
   __syncthreads();
   if ((tid & 31) == 0) s_red[tid >> 5] = sum;
   __syncthreads();
-  if (tid == 0) { float v = 0.f; for (int i = 0; i < 8; ++i) v += s_red[i]; s_b = v; }
+  if (tid == 0) { float v = 0.f; for (int i = 0; i < NT / 32; ++i) v += s_red[i]; s_b = v; }
   __syncthreads();
   const float inv = s_b;
-  for (int j = tid; j < n; j += 256) out[j] = __fdiv_rn(out[j], inv);
+  for (int j = tid; j < n; j += NT) out[j] = __fdiv_rn(out[j], inv);
 }
 
 __global__ void uniform_actions_kernel(const float* __restrict__ u, int64_t rows, int A,
@@ -318,10 +389,10 @@ int resample(ibc_handle* h, const float* logits, const double* uniforms, int64_t
              (long long)n, (long long)count);
   int threads = 1024;
   while (threads > 64 && threads / 2 >= n) threads >>= 1;
-  const size_t smem = (size_t)n * 12 + (size_t)threads * 4;
+  const size_t smem = (size_t)n * 12 + (size_t)(kResampleBuckets + 1 + kResampleHeavy) * 4 + 16;
   if (smem > 220 * 1024)
     IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "resample: n=%lld exceeds the shared-memory CDF (max %d)",
-             (long long)n, (int)((220 * 1024 - 4096) / 12));
+             (long long)n, (int)((220 * 1024 - 16384) / 12));
   static bool attr_set = false;
   if (!attr_set) {
     IBC_CUDA(h, cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -337,7 +408,9 @@ int resample(ibc_handle* h, const float* logits, const double* uniforms, int64_t
 int softmax_rows(ibc_handle* h, const float* logits, int64_t B, int64_t n, float temperature,
                  float* probs, cudaStream_t s) {
   if (B <= 0 || n <= 0) IBC_FAIL(h, IBC_ERR_INVALID, "softmax_rows: bad shape");
-  softmax_rows_kernel<<<(unsigned)B, 256, 0, s>>>(logits, (int)n, temperature, probs);
+  // few long rows (policy inference: one row of 16 384): more threads per row
+  if (n >= 4096) softmax_rows_kernel<1024><<<(unsigned)B, 1024, 0, s>>>(logits, (int)n, temperature, probs);
+  else softmax_rows_kernel<256><<<(unsigned)B, 256, 0, s>>>(logits, (int)n, temperature, probs);
   IBC_LAUNCH_CHECK(h);
   return IBC_OK;
 }
