@@ -81,6 +81,8 @@ int ibc_destroy(ibc_handle* h) {
     if (h->packed) cudaFree(h->packed);
     if (h->dev_status) cudaFree(h->dev_status);
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (auto& g : h->langevin_graphs) g.release();
+    if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
     if (h->ws.base) cudaFree(h->ws.base);
     if (h->ws_outer.base) cudaFree(h->ws_outer.base);
   }

@@ -74,6 +74,28 @@ struct Workspace {
   static size_t rounded(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
 };
 
+// One captured Langevin chain (mlp_umma_train.cu::langevin_umma): the chain is
+// launch-bound (three ~15 us kernels per iteration, 100 iterations), so it is
+// recorded once into a CUDA graph that runs on handle-owned staging buffers.
+struct LangevinGraph {
+  std::vector<unsigned char> key;    // shapes, config, step sizes, workspace / parameter identity
+  bool warm = false;                 // the chain has run once un-captured (lazy kernel attributes)
+  cudaGraphExec_t exec = nullptr;
+  float* obs = nullptr;              // staging: [B, O]
+  float* act = nullptr;              //          [R, A]
+  float* chain_actions = nullptr;    //          [K, R, A] when requested
+  float* chain_energies = nullptr;   //          [K, R]
+  float* chain_norms = nullptr;      //          [K, R]
+  uint64_t* seed = nullptr;          // device copy of the call's Philox seed
+  uint64_t last_use = 0;
+  void release() {
+    if (exec) cudaGraphExecDestroy(exec);
+    cudaFree(obs); cudaFree(act); cudaFree(chain_actions); cudaFree(chain_energies);
+    cudaFree(chain_norms); cudaFree(seed);
+    *this = LangevinGraph();
+  }
+};
+
 }  // namespace ibc
 
 struct ibc_handle {
@@ -92,6 +114,10 @@ struct ibc_handle {
   bool ev_valid = false;          // a full set of events has been recorded
   ibc::Workspace ws;        // dense-stack passes (reset by each pass)
   ibc::Workspace ws_outer;  // sampler / trainer scratch that outlives a pass
+  std::vector<ibc::LangevinGraph> langevin_graphs;
+  cudaStream_t capture_stream = nullptr;   // graphs are recorded here (the caller's stream may
+                                           // be the legacy default stream, which cannot capture)
+  uint64_t graph_clock = 0;
   std::string err;
 };
 

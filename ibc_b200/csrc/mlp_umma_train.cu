@@ -672,7 +672,9 @@ langevin_dact_update_kernel(const float* __restrict__ g0, const float* __restric
                             float noise_scale, float grad_clip, float dclip_scale, float stepsize,
                             const float* __restrict__ mn, const float* __restrict__ mx,
                             int norm_type, float* __restrict__ grad_norms,
-                            float* __restrict__ chain_actions) {
+                            float* __restrict__ chain_actions,
+                            const uint64_t* __restrict__ seed_ptr) {
+  if (seed_ptr) seed = *seed_ptr;     // captured chains read the call's seed from memory
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int a = threadIdx.x & 31;
   if (r >= R) return;
@@ -711,29 +713,22 @@ langevin_dact_update_kernel(const float* __restrict__ g0, const float* __restric
   }
 }
 
-// mcmc.langevin_actions_given_obs on tensor cores: per iteration one fused forward
-// (operands saved per tile), one fused reverse chain and one dE/dact + update kernel;
-// the observation projection is hoisted out of the chain.
-int langevin_umma(ibc_handle* h, const float* obs, int64_t B, float* actions, int64_t n,
-                  const float* mn, const float* mx, const ibc_langevin_cfg& c,
-                  const float* normals, uint64_t seed, const std::vector<float>& steps,
-                  float* chain_actions, float* chain_energies, float* chain_grad_norms,
-                  cudaStream_t s) {
+// The chain itself: every launch goes to `s` (directly or under stream capture).
+static int langevin_chain(ibc_handle* h, const float* obs, int64_t B, float* actions, int64_t n,
+                          const float* mn, const float* mx, const ibc_langevin_cfg& c,
+                          const float* normals, uint64_t seed, const uint64_t* seed_ptr,
+                          const std::vector<float>& steps, float* chain_actions,
+                          float* chain_energies, float* chain_grad_norms, cudaStream_t s) {
   const Layout& L = h->L;
   const int64_t R = B * n;
   const int A = L.A;
-  const size_t mask_words = umma_mask_words(L, R);
-  const size_t bytes = Workspace::rounded(mask_words * 4) + Workspace::rounded((size_t)R * L.W * 4) +
-                       Workspace::rounded((size_t)B * L.W * 4) + 3 * Workspace::rounded((size_t)R * 4);
-  IBC_CUDA(h, h->ws.reserve(bytes));
   h->ws.reset();
-  uint32_t* masks = h->ws.take<uint32_t>(mask_words);
+  uint32_t* masks = h->ws.take<uint32_t>(umma_mask_words(L, R));
   float* g0 = h->ws.take<float>((size_t)R * L.W);
   float* hp = h->ws.take<float>((size_t)B * L.W);
   float* E = h->ws.take<float>(R);
   float* dE = h->ws.take<float>(R);
   float* nrm = h->ws.take<float>(R);
-  if (h->packed_stale) IBC_TRY(umma_pack_params(h, s));
   {  // hp = obs . Wp[:O] + bp, once per chain
     GemmP g;
     g.A = obs; g.lda = L.O; g.B = h->params + L.wp; g.ldb = L.W; g.C = hp; g.ldc = L.W;
@@ -756,9 +751,109 @@ int langevin_umma(ibc_handle* h, const float* obs, int64_t B, float* actions, in
     langevin_dact_update_kernel<<<(unsigned)((R + 7) / 8), 256, 0, s>>>(
         g0, wpa, L.W, actions, R, A, normals ? normals + (int64_t)k * R * A : nullptr, seed,
         (uint64_t)k + 1, c.noise_scale, c.grad_clip, dclip_scale, steps[k], mn, mx,
-        c.grad_norm_type, Nk, chain_actions ? chain_actions + (int64_t)k * R * A : nullptr);
+        c.grad_norm_type, Nk, chain_actions ? chain_actions + (int64_t)k * R * A : nullptr,
+        seed_ptr);
     IBC_LAUNCH_CHECK(h);
   }
+  return IBC_OK;
+}
+
+// mcmc.langevin_actions_given_obs on tensor cores: per iteration one fused forward
+// (ReLU masks saved per tile), one fused reverse chain and one dE/dact + update kernel;
+// the observation projection is hoisted out of the chain.  With Philox noise (no
+// caller-supplied normals) the whole chain is replayed from a CUDA graph: the second
+// call with the same shapes / config captures it, later calls stage their inputs into
+// the graph's buffers and launch it (IBC_NO_GRAPHS=1 disables this).
+int langevin_umma(ibc_handle* h, const float* obs, int64_t B, float* actions, int64_t n,
+                  const float* mn, const float* mx, const ibc_langevin_cfg& c,
+                  const float* normals, uint64_t seed, const std::vector<float>& steps,
+                  float* chain_actions, float* chain_energies, float* chain_grad_norms,
+                  cudaStream_t s) {
+  const Layout& L = h->L;
+  const int64_t R = B * n;
+  const int K = c.num_iterations;
+  const size_t bytes = Workspace::rounded(umma_mask_words(L, R) * 4) +
+                       Workspace::rounded((size_t)R * L.W * 4) +
+                       Workspace::rounded((size_t)B * L.W * 4) + 3 * Workspace::rounded((size_t)R * 4);
+  IBC_CUDA(h, h->ws.reserve(bytes));
+  if (h->packed_stale) IBC_TRY(umma_pack_params(h, s));
+  static const bool no_graphs =
+      getenv("IBC_NO_GRAPHS") != nullptr || getenv("IBC_DBG_TIMELINE") != nullptr;
+  if (normals || no_graphs || K < 4)
+    return langevin_chain(h, obs, B, actions, n, mn, mx, c, normals, seed, nullptr, steps,
+                          chain_actions, chain_energies, chain_grad_norms, s);
+
+  // ---- graph path ---------------------------------------------------------------
+  std::vector<unsigned char> key;
+  auto put = [&](const void* p, size_t nbytes) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    key.insert(key.end(), b, b + nbytes);
+  };
+  const void* idents[5] = {h->params, h->packed, h->ws.base, mn, mx};
+  const int flags[3] = {chain_actions != nullptr, chain_energies != nullptr,
+                        chain_grad_norms != nullptr};
+  put(&B, sizeof(B)); put(&n, sizeof(n)); put(&c, sizeof(c)); put(idents, sizeof(idents));
+  put(flags, sizeof(flags)); put(&h->precision, sizeof(int));
+  put(steps.data(), steps.size() * sizeof(float));
+  LangevinGraph* g = nullptr;
+  for (auto& e : h->langevin_graphs)
+    if (e.key == key) g = &e;
+  if (!g) {
+    if (h->langevin_graphs.size() >= 4) {        // evict the least recently used
+      size_t lru = 0;
+      for (size_t i = 1; i < h->langevin_graphs.size(); ++i)
+        if (h->langevin_graphs[i].last_use < h->langevin_graphs[lru].last_use) lru = i;
+      IBC_CUDA(h, cudaStreamSynchronize(s));
+      h->langevin_graphs[lru].release();
+      h->langevin_graphs.erase(h->langevin_graphs.begin() + lru);
+    }
+    h->langevin_graphs.emplace_back();
+    g = &h->langevin_graphs.back();
+    g->key = key;
+    IBC_CUDA(h, cudaMalloc((void**)&g->obs, (size_t)B * L.O * 4));
+    IBC_CUDA(h, cudaMalloc((void**)&g->act, (size_t)R * L.A * 4));
+    IBC_CUDA(h, cudaMalloc((void**)&g->seed, sizeof(uint64_t)));
+    if (chain_actions) IBC_CUDA(h, cudaMalloc((void**)&g->chain_actions, (size_t)K * R * L.A * 4));
+    if (chain_energies) IBC_CUDA(h, cudaMalloc((void**)&g->chain_energies, (size_t)K * R * 4));
+    if (chain_grad_norms) IBC_CUDA(h, cudaMalloc((void**)&g->chain_norms, (size_t)K * R * 4));
+  }
+  g->last_use = ++h->graph_clock;
+  IBC_CUDA(h, cudaMemcpyAsync(g->obs, obs, (size_t)B * L.O * 4, cudaMemcpyDeviceToDevice, s));
+  IBC_CUDA(h, cudaMemcpyAsync(g->act, actions, (size_t)R * L.A * 4, cudaMemcpyDeviceToDevice, s));
+  IBC_CUDA(h, cudaMemcpyAsync(g->seed, &seed, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+  if (!g->exec && g->warm) {
+    cudaGraph_t graph = nullptr;
+    if (!h->capture_stream)
+      IBC_CUDA(h, cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = h->capture_stream;
+    IBC_CUDA(h, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    const int rc = langevin_chain(h, g->obs, B, g->act, n, mn, mx, c, nullptr, 0, g->seed, steps,
+                                  g->chain_actions, g->chain_energies, g->chain_norms, cs);
+    const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    if (rc != IBC_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    IBC_CUDA(h, ce);
+    const cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    IBC_CUDA(h, ie);
+  }
+  if (g->exec) {
+    IBC_CUDA(h, cudaGraphLaunch(g->exec, s));
+    count_launch();
+  } else {
+    IBC_TRY(langevin_chain(h, g->obs, B, g->act, n, mn, mx, c, nullptr, 0, g->seed, steps,
+                           g->chain_actions, g->chain_energies, g->chain_norms, s));
+    g->warm = true;
+  }
+  IBC_CUDA(h, cudaMemcpyAsync(actions, g->act, (size_t)R * L.A * 4, cudaMemcpyDeviceToDevice, s));
+  if (chain_actions)
+    IBC_CUDA(h, cudaMemcpyAsync(chain_actions, g->chain_actions, (size_t)K * R * L.A * 4,
+                                cudaMemcpyDeviceToDevice, s));
+  if (chain_energies)
+    IBC_CUDA(h, cudaMemcpyAsync(chain_energies, g->chain_energies, (size_t)K * R * 4,
+                                cudaMemcpyDeviceToDevice, s));
+  if (chain_grad_norms)
+    IBC_CUDA(h, cudaMemcpyAsync(chain_grad_norms, g->chain_norms, (size_t)K * R * 4,
+                                cudaMemcpyDeviceToDevice, s));
   return IBC_OK;
 }
 

@@ -215,6 +215,44 @@ def test_resample_known_answer():
   assert rows.cpu().tolist() == [0, 0, 1, 1]
 
 
+def test_langevin_graph_replay_is_bit_identical():
+  """With Philox noise the Langevin chain is captured into a CUDA graph on its second
+  call and replayed afterwards: plain run, capture run and replays of the same inputs
+  and seed must agree bit for bit (and a different seed must not)."""
+  from ibc_b200 import engine as eng
+  for width, depth, obs_dim, act_dim in ((128, 4, 20, 2), (256, 2, 64, 8)):
+    spec = omlp.MLPSpec(obs_dim, act_dim, width, depth)
+    e = eng.EBMEngine(obs_dim, act_dim, width, depth)
+    p = omlp.init_params(spec, seed=5).cuda().contiguous()
+    e.bind_params(p)
+    b, n = 8, 64
+    g = torch.Generator().manual_seed(1)
+    obs = torch.randn(b, obs_dim, generator=g).cuda()
+    act0 = (torch.rand(b * n, act_dim, generator=g) * 2 - 1).cuda()
+    mn = torch.full((act_dim,), -1.1).cuda()
+    mx = torch.full((act_dim,), 1.1).cuda()
+    cfg = eng.langevin_cfg(num_iterations=12)
+    outs = []
+    for call in range(4):
+      a = act0.clone()
+      chain = e.langevin(obs.clone(), a, n, mn, mx, cfg, seed=77, return_chain=True)
+      torch.cuda.synchronize()
+      outs.append((a.cpu(), [c.cpu() for c in chain]))
+    for a, chain in outs[1:]:
+      assert torch.equal(a, outs[0][0])
+      for c, c0 in zip(chain, outs[0][1]):
+        assert torch.equal(c, c0)
+    a = act0.clone()
+    e.langevin(obs, a, n, mn, mx, cfg, seed=78)       # same shapes, other config key (no chain)
+    b2 = act0.clone()
+    e.langevin(obs, b2, n, mn, mx, cfg, seed=78)
+    c2 = act0.clone()
+    e.langevin(obs, c2, n, mn, mx, cfg, seed=78)
+    assert torch.equal(a.cpu(), b2.cpu()) and torch.equal(a.cpu(), c2.cpu())
+    assert not torch.equal(a.cpu(), outs[0][0])
+    assert e.kernel_status() == 0
+
+
 # ------------------------------ losses -------------------------------------------
 @pytest.mark.parametrize('b,n1,temp,scale', [(512, 257, 1.0, 1.0), (16, 9, 0.5, 20.0),
                                              (3, 2, 1.0, 50.0)])
