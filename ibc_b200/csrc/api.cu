@@ -68,7 +68,8 @@ int ibc_create(const ibc_mlp_arch* arch, int device, ibc_handle** out) {
     IBC_FAIL(h, IBC_ERR_CUDA, "ibc_create: cudaMalloc failed");
   }
   cudaMemset(nh->dev_status, 0, sizeof(int));
-  nh->precision = umma_supported(nh->L) ? IBC_PRECISION_TF32 : IBC_PRECISION_FP32;
+  nh->precision = (umma_supported(nh->L) || wide_supported(nh->L)) ? IBC_PRECISION_TF32
+                                                                    : IBC_PRECISION_FP32;
   *out = nh;
   return IBC_OK;
 }
@@ -98,10 +99,10 @@ int ibc_set_precision(ibc_handle* h, int precision) {
   IBC_ENTER(h);
   if (precision != IBC_PRECISION_FP32 && precision != IBC_PRECISION_TF32)
     IBC_FAIL(h, IBC_ERR_INVALID, "unknown precision %d", precision);
-  if (precision == IBC_PRECISION_TF32 && !umma_supported(h->L))
+  if (precision == IBC_PRECISION_TF32 && !umma_supported(h->L) && !wide_supported(h->L))
     IBC_FAIL(h, IBC_ERR_UNSUPPORTED,
-             "tcgen05 kernels cover width 128/256, depth >= 2, act_dim <= 32 (got W=%d D=%d A=%d)",
-             h->L.W, h->L.D, h->L.A);
+             "tcgen05 kernels cover width 128/256 (act_dim <= 32) and multiples of 128 above, "
+             "depth >= 2 (got W=%d D=%d A=%d)", h->L.W, h->L.D, h->L.A);
   h->precision = precision;
   return IBC_OK;
 }

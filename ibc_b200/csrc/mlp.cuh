@@ -68,6 +68,10 @@ int langevin_umma(ibc_handle* h, const float* obs, int64_t B, float* actions, in
                   const float* normals, uint64_t seed, const std::vector<float>& steps,
                   float* chain_actions, float* chain_energies, float* chain_grad_norms,
                   cudaStream_t s);
+// widths that are a multiple of 128 above 256: one tcgen05 GEMM kernel per layer (mlp_wide.cu)
+bool wide_supported(const Layout& L);
+int mlp_energy_wide(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
+                    float* E, float* dEda, bool apply_exp, cudaStream_t s);
 // width-128 kernels with the activations in tensor memory (mlp_umma_tmem.cu); tile
 // ids and the saved-tile layouts are the same as the shared-memory-operand kernels'
 bool tmem_path_supported(const Layout& L);

@@ -829,8 +829,10 @@ int umma_pack_params(ibc_handle* h, cudaStream_t s) {
 int mlp_energy_umma(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
                     float* E, float* dEda, bool apply_exp, cudaStream_t s) {
   const Layout& L = h->L;
+  if (wide_supported(L)) return mlp_energy_wide(h, obs, B, act, n, E, dEda, apply_exp, s);
   if (!umma_supported(L))
-    IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "tcgen05 path supports width 128/256, act_dim <= 32");
+    IBC_FAIL(h, IBC_ERR_UNSUPPORTED,
+             "tcgen05 path supports width 128/256 (act_dim <= 32) and multiples of 128 above");
   if (dEda) return mlp_energy_dact_umma(h, obs, B, act, n, E, dEda, apply_exp, s);
   IBC_CUDA(h, h->ws.reserve(Workspace::rounded((size_t)B * L.W * 4)));
   h->ws.reset();

@@ -26,3 +26,24 @@ for name, (o, a, w, d, b, n) in (('pushing_states W=128 D=16 R=4096', (20, 2, 12
   t.record(); torch.cuda.synchronize()
   print('%-40s %.3f ms/chain (%s)' % (name, s.elapsed_time(t) / 10,
         'no graphs' if os.environ.get('IBC_NO_GRAPHS') else 'graph replay'))
+
+# wide stacks (per-layer tensor-core GEMMs, mlp_wide.cu) against the fp32 FMA path
+from ibc_b200 import _lib
+for name, (o, a, w, d, b, n) in (('C4 d4rl W=512 D=8 R=4096', (39, 28, 512, 8, 512, 8)),
+                                 ('particle best W=2048 D=2 R=4096', (16, 2, 2048, 2, 512, 8))):
+  spec = omlp.MLPSpec(o, a, w, d)
+  e = eng.EBMEngine(o, a, w, d)
+  e.bind_params(omlp.init_params(spec).cuda().contiguous())
+  obs = torch.randn(b, o).cuda()
+  acts = (torch.rand(b * n, a) * 2.2 - 1.1).cuda()
+  for prec, label in ((_lib.PRECISION_TF32, 'tf32 tcgen05'), (_lib.PRECISION_FP32, 'fp32 FMA')):
+    e.set_precision(prec)
+    for i in range(2):
+      e.energy_dact(obs, acts, n)
+    torch.cuda.synchronize()
+    s = torch.cuda.Event(enable_timing=True); t = torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(5):
+      e.energy_dact(obs, acts, n)
+    t.record(); torch.cuda.synchronize()
+    print('%-36s energy + dE/dact %.3f ms (%s)' % (name, s.elapsed_time(t) / 5, label))

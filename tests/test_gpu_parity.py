@@ -71,6 +71,8 @@ SPECS_TF32 = [
     omlp.MLPSpec(20, 2, 128, 16),
     omlp.MLPSpec(256, 32, 256, 2),   # C3 particle-32D
     omlp.MLPSpec(20, 2, 128, 2),
+    omlp.MLPSpec(39, 28, 512, 8),    # C4 d4rl door-human: per-layer tensor-core GEMMs
+    omlp.MLPSpec(16, 2, 1024, 2),    # wide and shallow (particle "best" is 2048 x 2)
 ]
 
 
@@ -135,14 +137,16 @@ def test_energy_dact_fp32(spec):
 
 
 @pytest.mark.parametrize('spec', [omlp.MLPSpec(20, 2, 128, 4), omlp.MLPSpec(256, 32, 256, 2),
-                                  omlp.MLPSpec(16, 2, 256, 2), omlp.MLPSpec(20, 2, 128, 16)], ids=str)
+                                  omlp.MLPSpec(16, 2, 256, 2), omlp.MLPSpec(20, 2, 128, 16),
+                                  omlp.MLPSpec(39, 28, 512, 8), omlp.MLPSpec(16, 2, 1024, 2)],
+                         ids=str)
 @pytest.mark.parametrize('b,n', [(4, 9), (8, 100)])
 def test_energy_dact_tf32(spec, b, n):
   """gradient_wrt_act on tensor cores (fused forward with saved operands + fused
   reverse chain).  dE/dact of a ReLU stack flips discretely with the masks, so
   the exact-vs-tf32 gap is a few percent by itself; the bound is calibrated:
   relative Frobenius error of the GPU <= 2x that of the oracle's tf32
-  emulation (oracle/tf32_emul.py) + 2e-3."""
+  emulation (oracle/tf32_emul.py) + 2e-3 (x sqrt(width / 256) above width 256)."""
   from ibc_b200 import _lib
   from oracle import tf32_emul
   e, flat = _engine(spec, precision=_lib.PRECISION_TF32, scale=1.0)
@@ -156,7 +160,10 @@ def test_energy_dact_tf32(spec, b, n):
   _close(got_e, want_e, TF32_TOL, 'E')
   rel = float((got_g.double().cpu() - want_g).norm() / want_g.norm())
   rel_emul = float((emul_g - want_g).norm() / want_g.norm())
-  assert rel <= 2 * rel_emul + 2e-3, (rel, rel_emul)
+  # the emulation accumulates in fp64; the tensor core's fp32 accumulation over K = width
+  # terms adds an error that grows like sqrt(K) (measured 3.0e-3 at width 1024)
+  floor = 2e-3 * max(1.0, (spec.width / 256.0) ** 0.5)
+  assert rel <= 2 * rel_emul + floor, (rel, rel_emul)
 
 
 # ------------------------------ resample ---------------------------------------
@@ -343,7 +350,8 @@ def test_dfo_device_rng_behaviour():
 @pytest.mark.parametrize('spec,precision', [(omlp.MLPSpec(16, 2, 256, 2), 0),
                                             (omlp.MLPSpec(39, 28, 64, 4), 0),
                                             (omlp.MLPSpec(16, 2, 256, 2), 1),
-                                            (omlp.MLPSpec(20, 2, 128, 4), 1)], ids=str)
+                                            (omlp.MLPSpec(20, 2, 128, 4), 1),
+                                            (omlp.MLPSpec(39, 28, 512, 4), 1)], ids=str)
 def test_langevin_matches_oracle(spec, precision):
   from ibc_b200 import _lib
   from ibc_b200 import engine as eng
