@@ -12,6 +12,13 @@
 // block in tensor memory over K-slices streamed through a 6-stage ring, then applies
 // bias / ReLU mask / residual in the epilogue and writes the fp32 stream and/or the
 // tf32-rounded operand of the next layer (+ ReLU mask bits for the reverse pass).
+//
+// Roofline: a 128 x 128 tf32 tile consumes 32 KB of operands per 256 MMA cycles (128
+// B/cycle) while one SM's bulk copies from L2 deliver ~50 B/cycle (scripts/mma_rate.py),
+// so this kernel is L2->shared bound at ~40 % of the tensor rate (measured: 0.36 ms for
+// energy + dE/dact of the d4rl net on 4096 rows vs 1.84 ms on the fp32 FMA path).
+// Grouping the issuer's waits did not help; 256-wide tiles / CTA pairs with multicast
+// are the next step.
 #include <stdlib.h>
 
 #include "gemm_simt.cuh"
