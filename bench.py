@@ -392,7 +392,8 @@ def secondary_configs(device):
   from ibc_b200 import engine as eng
   out = {}
   for name, (o, a, w, d) in (('C3_particle32_langevin', (256, 32, 256, 2)),
-                             ('pushing_states_langevin', (20, 2, 128, 16))):
+                             ('pushing_states_langevin', (20, 2, 128, 16)),
+                             ('C4_d4rl_door_langevin', (39, 28, 512, 8))):
     e = eng.EBMEngine(o, a, w, d, device)
     params = (torch.randn(e.param_count, device=device) * 0.05).contiguous()
     e.bind_params(params)
