@@ -72,6 +72,13 @@ int langevin_umma(ibc_handle* h, const float* obs, int64_t B, float* actions, in
 bool wide_supported(const Layout& L);
 int mlp_energy_wide(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
                     float* E, float* dEda, bool apply_exp, cudaStream_t s);
+// the whole Langevin chain of a width-128 stack as one persistent kernel (langevin_tmem.cu)
+bool langevin_fused_supported(const Layout& L);
+int langevin_fused(ibc_handle* h, const float* hp, int64_t B, float* actions, int64_t n,
+                   const float* mn, const float* mx, const ibc_langevin_cfg& c,
+                   const float* normals, uint64_t seed, const uint64_t* seed_ptr,
+                   const float* steps_dev, float* chain_actions, float* chain_energies,
+                   float* chain_grad_norms, cudaStream_t s);
 // width-128 kernels with the activations in tensor memory (mlp_umma_tmem.cu); tile
 // ids and the saved-tile layouts are the same as the shared-memory-operand kernels'
 bool tmem_path_supported(const Layout& L);

@@ -777,6 +777,20 @@ int langevin_umma(ibc_handle* h, const float* obs, int64_t B, float* actions, in
                        Workspace::rounded((size_t)B * L.W * 4) + 3 * Workspace::rounded((size_t)R * 4);
   IBC_CUDA(h, h->ws.reserve(bytes));
   if (h->packed_stale) IBC_TRY(umma_pack_params(h, s));
+  static const bool no_fused = getenv("IBC_NO_FUSED_LANGEVIN") != nullptr;
+  if (!no_fused && K > 0 && langevin_fused_supported(L)) {
+    // width 128: the whole chain in one persistent kernel (langevin_tmem.cu)
+    h->ws.reset();
+    float* hp = h->ws.take<float>((size_t)B * L.W);
+    float* steps_dev = h->ws.take<float>((size_t)K);
+    GemmP g;   // hp = obs . Wp[:O] + bp, once per chain
+    g.A = obs; g.lda = L.O; g.B = h->params + L.wp; g.ldb = L.W; g.C = hp; g.ldc = L.W;
+    g.bias = h->params + L.bp; g.M = (int)B; g.N = L.W; g.K = L.O;
+    IBC_TRY(gemm(h, g, false, false, s));
+    IBC_CUDA(h, cudaMemcpyAsync(steps_dev, steps.data(), (size_t)K * 4, cudaMemcpyHostToDevice, s));
+    return langevin_fused(h, hp, B, actions, n, mn, mx, c, normals, seed, nullptr, steps_dev,
+                          chain_actions, chain_energies, chain_grad_norms, s);
+  }
   static const bool no_graphs =
       getenv("IBC_NO_GRAPHS") != nullptr || getenv("IBC_DBG_TIMELINE") != nullptr;
   if (normals || no_graphs || K < 4)

@@ -260,6 +260,46 @@ def test_langevin_graph_replay_is_bit_identical():
     assert e.kernel_status() == 0
 
 
+_FUSED_SCRIPT = r'''
+import hashlib, sys, torch
+sys.path.insert(0, %r)
+from oracle import mlp_ebm as omlp
+from ibc_b200 import engine as eng
+spec = omlp.MLPSpec(20, 2, 128, 4)
+e = eng.EBMEngine(20, 2, 128, 4)
+p = omlp.init_params(spec, seed=5).cuda().contiguous(); e.bind_params(p)
+g = torch.Generator().manual_seed(1)
+b, n = 3, 100                                   # 300 rows: two full tiles and a ragged one
+obs = torch.randn(b, 20, generator=g).cuda()
+act = (torch.rand(b * n, 2, generator=g) * 2 - 1).cuda()
+mn = torch.full((2,), -1.1).cuda(); mx = torch.full((2,), 1.1).cuda()
+cfg = eng.langevin_cfg(num_iterations=9, noise_scale=0.5)
+chain = e.langevin(obs, act, n, mn, mx, cfg, seed=123, return_chain=True)
+torch.cuda.synchronize()
+assert e.kernel_status() == 0
+h = hashlib.sha256()
+for t in (act,) + tuple(chain):
+  h.update(t.cpu().numpy().tobytes())
+print('DIGEST', h.hexdigest())
+'''
+
+
+def test_fused_langevin_kernel_is_bit_identical_to_the_three_kernel_chain():
+  """langevin_tmem.cu (one persistent kernel for the whole chain) against the forward /
+  reverse / update kernels it fuses (IBC_NO_FUSED_LANGEVIN=1): same arithmetic in the same
+  order, so actions and the recorded chain must agree bit for bit."""
+  import os, subprocess, sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  digests = []
+  for env_extra in ({}, {'IBC_NO_FUSED_LANGEVIN': '1'}):
+    env = dict(os.environ, **env_extra)
+    out = subprocess.run([sys.executable, '-c', _FUSED_SCRIPT % root], env=env, cwd=root,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    digests.append([l for l in out.stdout.splitlines() if l.startswith('DIGEST')][0])
+  assert digests[0] == digests[1]
+
+
 # ------------------------------ losses -------------------------------------------
 @pytest.mark.parametrize('b,n1,temp,scale', [(512, 257, 1.0, 1.0), (16, 9, 0.5, 20.0),
                                              (3, 2, 1.0, 50.0)])
