@@ -471,7 +471,14 @@ def run_reference(args):
   if rank != 0:
     return None
   c = CFG
-  base = cpu_baseline(steps=max(1, min(args.steps, 5)), warmup=max(1, min(args.warmup, 2)))
+  # every one of the K timed steps runs on a bounded sample of the workload (a batch of b'
+  # of the 512 observations, N and the network unchanged) sized from a calibration step so
+  # that warm-up + K steps take about two minutes of host time
+  cal = cpu_baseline(steps=1, warmup=1, batch=64)
+  per_obs = cal['seconds_per_step'] / 64.0
+  total = max(1, args.steps + min(args.warmup, 3))
+  batch = int(max(8, min(c['batch'], 120.0 / (total * per_obs))))
+  base = cpu_baseline(steps=max(1, args.steps), warmup=max(1, min(args.warmup, 3)), batch=batch)
   world = int(os.environ.get('WORLD_SIZE', '1'))
   return {
       'impl': 'reference', 'metric': 'ebm_train_energy_evals_per_s', 'value': base['value'],
