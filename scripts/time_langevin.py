@@ -3,15 +3,13 @@ plain and with IBC_NO_GRAPHS=1)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import mlp_ebm as omlp
 from ibc_b200 import engine as eng
 
 for name, (o, a, w, d, b, n) in (('pushing_states W=128 D=16 R=4096', (20, 2, 128, 16, 512, 8)),
                                  ('C3 W=256 D=2 R=4096', (256, 32, 256, 2, 512, 8)),
                                  ('particle inference W=256 D=2 R=512', (16, 2, 256, 2, 1, 512))):
-  spec = omlp.MLPSpec(o, a, w, d)
-  e = eng.EBMEngine(o, a, w, d)
-  e.bind_params(omlp.init_params(spec).cuda().contiguous())
+    e = eng.EBMEngine(o, a, w, d)
+  e.bind_params((torch.randn(e.param_count) * 0.05).cuda())
   obs = torch.randn(b, o).cuda()
   mn, mx = torch.full((a,), -1.1).cuda(), torch.full((a,), 1.1).cuda()
   cfg = eng.langevin_cfg(num_iterations=100)
@@ -31,9 +29,8 @@ for name, (o, a, w, d, b, n) in (('pushing_states W=128 D=16 R=4096', (20, 2, 12
 from ibc_b200 import _lib
 for name, (o, a, w, d, b, n) in (('C4 d4rl W=512 D=8 R=4096', (39, 28, 512, 8, 512, 8)),
                                  ('particle best W=2048 D=2 R=4096', (16, 2, 2048, 2, 512, 8))):
-  spec = omlp.MLPSpec(o, a, w, d)
-  e = eng.EBMEngine(o, a, w, d)
-  e.bind_params(omlp.init_params(spec).cuda().contiguous())
+    e = eng.EBMEngine(o, a, w, d)
+  e.bind_params((torch.randn(e.param_count) * 0.05).cuda())
   obs = torch.randn(b, o).cuda()
   acts = (torch.rand(b * n, a) * 2.2 - 1.1).cuda()
   for prec, label in ((_lib.PRECISION_TF32, 'tf32 tcgen05'), (_lib.PRECISION_FP32, 'fp32 FMA')):

@@ -2,7 +2,6 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import mlp_ebm as omlp
 from ibc_b200 import engine as eng
 
 def timed(fn, reps=50):
@@ -15,9 +14,8 @@ def timed(fn, reps=50):
   return s.elapsed_time(e) / reps * 1e3
 
 n = 16384
-spec = omlp.MLPSpec(20, 2, 128, 16)
 e = eng.EBMEngine(20, 2, 128, 16)
-p = omlp.init_params(spec).cuda().contiguous(); e.bind_params(p)
+p = (torch.randn(e.param_count) * 0.05).cuda(); e.bind_params(p)
 obs = torch.randn(1, 20).cuda(); act = torch.rand(n, 2).cuda() * 2 - 1
 logits = e.energy(obs, act, n).reshape(1, n).contiguous()
 u = torch.rand(1, n, dtype=torch.float64).cuda()

@@ -3,11 +3,9 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ['IBC_DBG_TIMELINE'] = '1'
 import torch
-from oracle import mlp_ebm as omlp
 from ibc_b200 import engine as eng
-spec = omlp.MLPSpec(20, 2, 128, 16)
 e = eng.EBMEngine(20, 2, 128, 16)
-p = omlp.init_params(spec).cuda().contiguous(); e.bind_params(p)
+p = (torch.randn(e.param_count) * 0.05).cuda(); e.bind_params(p)
 rows = 131584
 obs = torch.randn(512, 20).cuda(); act = torch.rand(rows, 2).cuda()
 for _ in range(2):

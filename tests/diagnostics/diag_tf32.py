@@ -1,6 +1,6 @@
 """Diagnostic (not a test): tf32 energy error statistics per shape."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import mlp_ebm as omlp
 from ibc_b200 import engine as eng, _lib

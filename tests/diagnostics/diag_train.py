@@ -1,6 +1,6 @@
 """Diagnostic: per-tensor relative error of train_grads (tf32 and fp32) vs oracle autograd."""
 import sys, os, math
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import mlp_ebm as omlp, losses as olosses
 from ibc_b200 import engine as eng
