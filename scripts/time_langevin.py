@@ -8,7 +8,7 @@ from ibc_b200 import engine as eng
 for name, (o, a, w, d, b, n) in (('pushing_states W=128 D=16 R=4096', (20, 2, 128, 16, 512, 8)),
                                  ('C3 W=256 D=2 R=4096', (256, 32, 256, 2, 512, 8)),
                                  ('particle inference W=256 D=2 R=512', (16, 2, 256, 2, 1, 512))):
-    e = eng.EBMEngine(o, a, w, d)
+  e = eng.EBMEngine(o, a, w, d)
   e.bind_params((torch.randn(e.param_count) * 0.05).cuda())
   obs = torch.randn(b, o).cuda()
   mn, mx = torch.full((a,), -1.1).cuda(), torch.full((a,), 1.1).cuda()
@@ -29,7 +29,7 @@ for name, (o, a, w, d, b, n) in (('pushing_states W=128 D=16 R=4096', (20, 2, 12
 from ibc_b200 import _lib
 for name, (o, a, w, d, b, n) in (('C4 d4rl W=512 D=8 R=4096', (39, 28, 512, 8, 512, 8)),
                                  ('particle best W=2048 D=2 R=4096', (16, 2, 2048, 2, 512, 8))):
-    e = eng.EBMEngine(o, a, w, d)
+  e = eng.EBMEngine(o, a, w, d)
   e.bind_params((torch.randn(e.param_count) * 0.05).cuda())
   obs = torch.randn(b, o).cuda()
   acts = (torch.rand(b * n, a) * 2.2 - 1.1).cuda()
