@@ -7,6 +7,7 @@
 
 #include "gemm_simt.cuh"
 #include "mlp.cuh"
+#include "chain_graph.cuh"
 #include "ops.cuh"
 #include "philox.cuh"
 
@@ -351,7 +352,9 @@ __global__ void langevin_update_kernel(float* __restrict__ actions,
                                        float dclip_scale, float stepsize,
                                        const float* __restrict__ mn, const float* __restrict__ mx,
                                        int norm_type, float* __restrict__ grad_norms,
-                                       float* __restrict__ chain_actions) {
+                                       float* __restrict__ chain_actions,
+                                       const uint64_t* __restrict__ seed_ptr) {
+  if (seed_ptr) seed = *seed_ptr;     // captured chains read the call's seed from memory
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   float nrm = 0.f;
@@ -443,7 +446,7 @@ int langevin_update(ibc_handle* h, float* actions, const float* dEda, int64_t R,
   const float dclip_scale = (float)((double)delta_action_clip * 0.5);
   langevin_update_kernel<<<(unsigned)((R + 127) / 128), 128, 0, s>>>(
       actions, dEda, R, A, normals, seed, rng_stream, noise_scale, grad_clip, dclip_scale,
-      stepsize, mn, mx, norm_type, grad_norms, nullptr);
+      stepsize, mn, mx, norm_type, grad_norms, nullptr, nullptr);
   IBC_LAUNCH_CHECK(h);
   return IBC_OK;
 }
@@ -539,23 +542,36 @@ int langevin(ibc_handle* h, const float* obs, int64_t B, float* actions, int64_t
                          chain_energies, chain_grad_norms, s);
   const size_t bytes = 2 * Workspace::rounded((size_t)R * 4) + Workspace::rounded((size_t)R * A * 4);
   IBC_CUDA(h, h->ws_outer.reserve(bytes));
-  h->ws_outer.reset();
-  float* E = h->ws_outer.take<float>(R);
-  float* nrm = h->ws_outer.take<float>(R);
-  float* dEda = h->ws_outer.take<float>((size_t)R * A);
   // delta_action_clip * 0.5 evaluated in double like the Python scalar product
   const float dclip_scale = (float)((double)c.delta_action_clip * 0.5);
-  for (int k = 0; k < c.num_iterations; ++k) {
-    float* Ek = chain_energies ? chain_energies + (int64_t)k * R : E;
-    float* Nk = chain_grad_norms ? chain_grad_norms + (int64_t)k * R : nrm;
-    IBC_TRY(mlp_energy_dact(h, obs, B, actions, n, Ek, dEda, c.apply_exp != 0, s));
-    langevin_update_kernel<<<(unsigned)((R + 127) / 128), 128, 0, s>>>(
-        actions, dEda, R, A, normals ? normals + (int64_t)k * R * A : nullptr, seed,
-        (uint64_t)k + 1, c.noise_scale, c.grad_clip, dclip_scale, steps[k], mn, mx,
-        c.grad_norm_type, Nk, chain_actions ? chain_actions + (int64_t)k * R * A : nullptr);
-    IBC_LAUNCH_CHECK(h);
+  auto chain = [&](const float* o, float* a, const float* nrmls, const uint64_t* seed_ptr,
+                   float* ca, float* ce, float* cn, cudaStream_t cs) -> int {
+    h->ws_outer.reset();
+    float* E = h->ws_outer.take<float>(R);
+    float* nrm = h->ws_outer.take<float>(R);
+    float* dEda = h->ws_outer.take<float>((size_t)R * A);
+    for (int k = 0; k < c.num_iterations; ++k) {
+      float* Ek = ce ? ce + (int64_t)k * R : E;
+      float* Nk = cn ? cn + (int64_t)k * R : nrm;
+      IBC_TRY(mlp_energy_dact(h, o, B, a, n, Ek, dEda, c.apply_exp != 0, cs));
+      langevin_update_kernel<<<(unsigned)((R + 127) / 128), 128, 0, cs>>>(
+          a, dEda, R, A, nrmls ? nrmls + (int64_t)k * R * A : nullptr, seed, (uint64_t)k + 1,
+          c.noise_scale, c.grad_clip, dclip_scale, steps[k], mn, mx, c.grad_norm_type, Nk,
+          ca ? ca + (int64_t)k * R * A : nullptr, seed_ptr);
+      IBC_LAUNCH_CHECK(h);
+    }
+    return IBC_OK;
+  };
+  // per-layer tensor-core stacks: ~20 small launches per iteration -> replay from a graph
+  if (h->precision == IBC_PRECISION_TF32 && wide_supported(h->L) && !normals &&
+      chain_graphs_enabled() && c.num_iterations >= 4) {
+    return run_chain_graphed(
+        h, obs, B, actions, n, mn, mx, c, seed, steps, chain_actions, chain_energies,
+        chain_grad_norms, s,
+        [&](const float* o, float* a, const uint64_t* seed_ptr, float* ca, float* ce, float* cn,
+            cudaStream_t cs) { return chain(o, a, nullptr, seed_ptr, ca, ce, cn, cs); });
   }
-  return IBC_OK;
+  return chain(obs, actions, normals, nullptr, chain_actions, chain_energies, chain_grad_norms, s);
 }
 
 }  // namespace ibc

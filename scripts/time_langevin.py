@@ -44,3 +44,22 @@ for name, (o, a, w, d, b, n) in (('C4 d4rl W=512 D=8 R=4096', (39, 28, 512, 8, 5
       e.energy_dact(obs, acts, n)
     t.record(); torch.cuda.synchronize()
     print('%-36s energy + dE/dact %.3f ms (%s)' % (name, s.elapsed_time(t) / 5, label))
+
+# C4 chain (wide path, graph replay)
+o, a, w, d, b, n = 39, 28, 512, 8, 512, 8
+e = eng.EBMEngine(o, a, w, d)
+e.bind_params((torch.randn(e.param_count) * 0.05).cuda())
+obs = torch.randn(b, o).cuda()
+mn, mx = torch.full((a,), -1.1).cuda(), torch.full((a,), 1.1).cuda()
+cfg = eng.langevin_cfg(num_iterations=100)
+acts = (torch.rand(b * n, a) * 2.2 - 1.1).cuda()
+for i in range(4):
+  e.langevin(obs, acts.clone(), n, mn, mx, cfg, seed=i)
+torch.cuda.synchronize()
+s = torch.cuda.Event(enable_timing=True); t = torch.cuda.Event(enable_timing=True)
+s.record()
+for i in range(5):
+  e.langevin(obs, acts.clone(), n, mn, mx, cfg, seed=10 + i)
+t.record(); torch.cuda.synchronize()
+print('C4 d4rl W=512 D=8 R=4096 chain        %.3f ms/chain (%s)' % (s.elapsed_time(t) / 5,
+      'no graphs' if os.environ.get('IBC_NO_GRAPHS') else 'graph replay'))

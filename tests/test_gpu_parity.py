@@ -227,7 +227,7 @@ def test_langevin_graph_replay_is_bit_identical():
   call and replayed afterwards: plain run, capture run and replays of the same inputs
   and seed must agree bit for bit (and a different seed must not)."""
   from ibc_b200 import engine as eng
-  for width, depth, obs_dim, act_dim in ((128, 4, 20, 2), (256, 2, 64, 8)):
+  for width, depth, obs_dim, act_dim in ((128, 4, 20, 2), (256, 2, 64, 8), (512, 2, 39, 28)):
     spec = omlp.MLPSpec(obs_dim, act_dim, width, depth)
     e = eng.EBMEngine(obs_dim, act_dim, width, depth)
     p = omlp.init_params(spec, seed=5).cuda().contiguous()
