@@ -109,6 +109,9 @@ SIGNATURES = {
     'ibc_pixel_last_error': (c_char_p, [c_void_p]),
     'ibc_pixel_param_count': (c_int64, [POINTER(PixelArch)]),
     'ibc_pixel_bind_params': (c_int, [c_void_p, c_void_p]),
+    'ibc_pixel_set_precision': (c_int, [c_void_p, c_int]),
+    'ibc_pixel_get_precision': (c_int, [c_void_p]),
+    'ibc_pixel_kernel_status': (c_int, [c_void_p, POINTER(c_int32)]),
     'ibc_pixel_encode': (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
     'ibc_pixel_energy': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                  c_void_p]),
@@ -125,6 +128,9 @@ SIGNATURES = {
     'ibc_reset_launch_count': (None, []),
     'ibc_umma_selftest': (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                   c_void_p, POINTER(c_int32), c_void_p]),
+    'ibc_gemm_tf32': (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p,
+                              c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                              c_int32, c_int32, c_int32, POINTER(c_int32), c_void_p]),
 }
 
 _lib = None

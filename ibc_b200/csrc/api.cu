@@ -308,4 +308,51 @@ int ibc_umma_selftest(const float* A, const float* Bt, int32_t N, int32_t K, int
   return umma_selftest(A, Bt, N, K, mode, D, status_host, (cudaStream_t)stream);
 }
 
+int ibc_gemm_tf32(const float* A, int64_t lda, int32_t trans_a, const float* B, int64_t ldb,
+                  int32_t trans_b, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
+                  const float* bias, const float* gate_c, const float* res, int32_t relu_a,
+                  int32_t relu_out, int32_t accumulate, int32_t* status_host, void* stream) {
+  ibc_handle* none = nullptr;
+  if (!A || !B || !C || M < 1 || N < 1 || K < 1)
+    IBC_FAIL(none, IBC_ERR_INVALID, "ibc_gemm_tf32: bad argument");
+  // per-device state of this handle-less entry point: SM count and a status word
+  constexpr int kMaxDev = 64;
+  static int sm_count[kMaxDev] = {0};
+  static int* dev_status[kMaxDev] = {nullptr};
+  int dev = 0;
+  IBC_CUDA(none, cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDev) IBC_FAIL(none, IBC_ERR_INVALID, "ibc_gemm_tf32: device index");
+  if (!dev_status[dev]) {
+    int major = 0, sms = 0;
+    IBC_CUDA(none, cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    IBC_CUDA(none, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (major != 10) IBC_FAIL(none, IBC_ERR_UNSUPPORTED, "ibc_b200 is built for sm_100a only");
+    IBC_CUDA(none, cudaMalloc((void**)&dev_status[dev], sizeof(int)));
+    IBC_CUDA(none, cudaMemset(dev_status[dev], 0, sizeof(int)));
+    sm_count[dev] = sms;
+  }
+  ibc_handle tmp;                       // carries the error string, SM count and status word
+  tmp.device = dev;
+  tmp.sm_count = sm_count[dev];
+  tmp.dev_status = dev_status[dev];
+  ibc::GemmP g;
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K; g.bias = bias;
+  g.gateC = gate_c; g.ldgc = ldc; g.res = res; g.ldres = ldc;
+  g.aop = relu_a ? ibc::AOP_RELU : ibc::AOP_ID; g.relu_out = relu_out; g.atomic = accumulate;
+  const int rc = ibc::gemm_tc(&tmp, g, trans_a != 0, trans_b != 0, (cudaStream_t)stream);
+  if (rc != IBC_OK) {
+    strncpy(ibc::g_create_error, tmp.err.empty() ? "ibc_gemm_tf32 failed" : tmp.err.c_str(), 511);
+    return rc;
+  }
+  if (status_host) {                    // optional: waits for the product
+    int st = 0;
+    IBC_CUDA(none, cudaStreamSynchronize((cudaStream_t)stream));
+    IBC_CUDA(none, cudaMemcpy(&st, dev_status[dev], sizeof(int), cudaMemcpyDeviceToHost));
+    if (st) IBC_CUDA(none, cudaMemset(dev_status[dev], 0, sizeof(int)));
+    *status_host = st;
+  }
+  return IBC_OK;
+}
+
 }  // extern "C"

@@ -163,6 +163,9 @@ __global__ void sum_kernel(const float* __restrict__ d, int64_t R, float* __rest
 
 int gemm(ibc_handle* h, const GemmP& p, bool ta, bool tb, cudaStream_t s) {
   if (p.M <= 0 || p.N <= 0) return IBC_OK;
+  if (p.tc && h && h->precision == IBC_PRECISION_TF32 && p.M >= 32 && p.K >= 16 &&
+      gemm_tc_supported(p))
+    return gemm_tc(h, p, ta, tb, s);
   const int kc = p.k_chunk > 0 ? p.k_chunk : p.K;
   const int splits = p.K > 0 ? (p.K + kc - 1) / kc : 1;
   if (splits > 1 && !p.atomic)

@@ -29,9 +29,22 @@ struct GemmP {
   int atomic = 0;    // accumulate into C with atomicAdd
   int relu_out = 0;  // C = max(C, 0) (not with split-K)
   float alpha = 1.f;
+  int tc = 0;        // tcgen05 tf32 kernel (gemm_tc.cu) when the handle's precision is TF32
+  // Implicit 3x3 'same' convolution (gemm_tc only): when conv_C > 0, A points at an NHWC
+  // tensor [*, conv_H, conv_W, conv_C] and the logical A operand is its im2col matrix
+  //   A[(b, y, x), (ky, kx, c)] = X[b, y + ky - 1, x + kx - 1, c]   (zero outside the frame)
+  // of shape [rows, 9 * conv_C]; lda is ignored.  With `ta` the logical operand is its
+  // transpose (weight-gradient form: M = 9 * conv_C, K = rows).
+  int conv_H = 0, conv_W = 0, conv_C = 0;
 };
 
+// fp32 FMA kernel, or gemm_tc when p.tc is set, the handle computes in tf32 and the
+// block is large enough to fill an MMA tile.
 int gemm(ibc_handle* h, const GemmP& p, bool ta, bool tb, cudaStream_t s);
+// tcgen05 kind::tf32 kernel (operands rounded to nearest tf32, fp32 accumulation);
+// with p.atomic the K split is chosen by the kernel's own occupancy rule.
+int gemm_tc(ibc_handle* h, const GemmP& p, bool ta, bool tb, cudaStream_t s);
+bool gemm_tc_supported(const GemmP& p);
 
 // E[r] = sum_w X[r*ldx + w] * v[w] + (b ? b[0] : 0)
 int rowdot(ibc_handle* h, const float* X, int64_t ldx, const float* v,

@@ -7,8 +7,9 @@
 //   networks/pixel_ebm.py:79-125             encode / call with observation_encoding
 //   ibc/agents/ibc_agent.py:191-213          late-fusion loss (encode once, tile N+1)
 //
-// Convolutions are im2col (per batch chunk) + the fp32 GEMM with fused
-// bias/ReLU; the tcgen05 implicit-GEMM version is future work.
+// Convolutions are im2col (per batch chunk) + a GEMM with fused bias/ReLU: the
+// tcgen05 tf32 kernel of gemm_tc.cu (IBC_PRECISION_TF32, the default) or the
+// fp32 FMA kernel (IBC_PRECISION_FP32).
 // Flat parameter layout: conv{1..4} kernel [3,3,cin,cout] + bias, value dense0
 // [256+A, Wv] + b, per block d0 [Wv,Wv/4], d1 [Wv/4,Wv/4], d2 [Wv/4,Wv] (+ biases),
 // dense1 [Wv] + b.
@@ -66,19 +67,29 @@ PixelLayout make_pixel_layout(const ibc_pixel_arch& a) {
   return L;
 }
 
+// Every contraction of the pixel path may run on the tcgen05 tf32 kernel (gemm_tc.cu);
+// gemm() picks it when the handle's precision is IBC_PRECISION_TF32.
+int pgemm(ibc_handle* h, GemmP g, bool ta, bool tb, cudaStream_t s) {
+  g.tc = 1;
+  return gemm(h, g, ta, tb, s);
+}
+
 // ---- elementwise / data-movement kernels ----------------------------------------------
 // out[b, y, x, c] (NHWC, c < CT): bilinear sample (half-pixel centres, no
 // antialias) of the input viewed as [B, H, W, CT] -- the reference's raw
 // reshape of [B, T, H, W, C] (image_prepro.py:28).
+// The output has Cp >= CT channels per pixel; channels CT .. Cp-1 are zero (the tf32 path
+// pads to a multiple of 4 so that the convolution's loader moves 16-byte pieces).
 __global__ void preprocess_kernel(const void* __restrict__ img, int is_u8, int64_t B, int H, int W,
-                                  int CT, int th, int tw, float* __restrict__ out) {
+                                  int CT, int Cp, int th, int tw, float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t tot = B * th * tw * CT;
+  const int64_t tot = B * th * tw * Cp;
   if (i >= tot) return;
-  const int c = (int)(i % CT);
-  const int x = (int)((i / CT) % tw);
-  const int y = (int)((i / ((int64_t)CT * tw)) % th);
-  const int64_t b = i / ((int64_t)CT * tw * th);
+  const int c = (int)(i % Cp);
+  const int x = (int)((i / Cp) % tw);
+  const int y = (int)((i / ((int64_t)Cp * tw)) % th);
+  const int64_t b = i / ((int64_t)Cp * tw * th);
+  if (c >= CT) { out[i] = 0.f; return; }
   const float sy = (float)H / (float)th, sx = (float)W / (float)tw;
   float fy = sy * ((float)y + 0.5f) - 0.5f, fx = sx * ((float)x + 0.5f) - 0.5f;
   fy = fmaxf(fy, 0.f); fx = fmaxf(fx, 0.f);
@@ -135,6 +146,33 @@ __global__ void col2im3x3_kernel(const float* __restrict__ dcol, int64_t nb, int
   dX[i] = s;
 }
 
+// Kd[(8 - tap), co, c] = K[tap, c, co]: the data gradient of a 3x3 'same' convolution is
+// the convolution of dY with the taps flipped and the channel roles exchanged.
+__global__ void flip_kernel3x3_kernel(const float* __restrict__ K, int Ci, int Co,
+                                      float* __restrict__ Kd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * Ci * Co) return;
+  const int co = i % Co, c = (i / Co) % Ci, tap = i / (Co * Ci);
+  Kd[((8 - tap) * Co + co) * Ci + c] = K[i];
+}
+
+// Kp[tap, c, co] (c < Cp) = c < C ? K[tap, c, co] : 0
+__global__ void pad_kernel_channels_kernel(const float* __restrict__ K, int C, int Cp, int Co,
+                                           float* __restrict__ Kp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * Cp * Co) return;
+  const int co = i % Co, c = (i / Co) % Cp, tap = i / (Co * Cp);
+  Kp[i] = c < C ? K[(tap * C + c) * Co + co] : 0.f;
+}
+// dK[tap, c, co] += dKp[tap, c, co] for c < C
+__global__ void unpad_kernel_channels_add_kernel(const float* __restrict__ dKp, int C, int Cp,
+                                                 int Co, float* __restrict__ dK) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * C * Co) return;
+  const int co = i % Co, c = (i / Co) % C, tap = i / (Co * C);
+  dK[i] += dKp[(tap * Cp + c) * Co + co];
+}
+
 __global__ void maxpool2_fwd_kernel(const float* __restrict__ Y, int64_t n, int H, int W, int C,
                                     float* __restrict__ P) {
   const int Hp = H / 2, Wp = W / 2;
@@ -148,28 +186,52 @@ __global__ void maxpool2_fwd_kernel(const float* __restrict__ Y, int64_t n, int 
 }
 
 // dY = (first maximum of its 2x2 window ? dP : 0) * (Y > 0)   (MaxPool + ReLU backward)
+// One thread = one 2x2 window (or unpooled edge pixel pair) x 4 channels: four 16-byte
+// loads of Y, one of dP, four 16-byte stores.  C must be a multiple of 4 (32 .. 256).
 __global__ void maxpool2_relu_bwd_kernel(const float* __restrict__ Y, const float* __restrict__ dP,
                                          int64_t n, int H, int W, int C, float* __restrict__ dY) {
   const int Hp = H / 2, Wp = W / 2;
+  const int Hc = (H + 1) / 2, Wc = (W + 1) / 2, C4 = C / 4;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * H * W * C) return;
-  const int c = (int)(i % C);
-  const int x = (int)((i / C) % W), y = (int)((i / ((int64_t)C * W)) % H);
-  const int64_t b = i / ((int64_t)C * W * H);
-  const int yp = y >> 1, xp = x >> 1;
-  float g = 0.f;
-  const float v = Y[i];
-  if (yp < Hp && xp < Wp && v > 0.f) {
-    const float* p = Y + ((b * H + 2 * yp) * W + 2 * xp) * C + c;
-    const float w00 = p[0], w01 = p[C], w10 = p[(int64_t)W * C], w11 = p[(int64_t)W * C + C];
-    const int me = (y & 1) * 2 + (x & 1);
-    int arg = 0; float mx = w00;
-    if (w01 > mx) { mx = w01; arg = 1; }
-    if (w10 > mx) { mx = w10; arg = 2; }
-    if (w11 > mx) { mx = w11; arg = 3; }
-    if (arg == me) g = dP[((b * Hp + yp) * Wp + xp) * C + c];
+  if (i >= n * Hc * Wc * C4) return;
+  const int c4 = (int)(i % C4);
+  const int xp = (int)((i / C4) % Wc), yp = (int)((i / ((int64_t)C4 * Wc)) % Hc);
+  const int64_t b = i / ((int64_t)C4 * Wc * Hc);
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t base = ((b * H + 2 * yp) * W + 2 * xp) * C + c4 * 4;
+  const int64_t row = (int64_t)W * C;
+  const bool has_x = 2 * xp + 1 < W, has_y = 2 * yp + 1 < H;
+  float4* o00 = reinterpret_cast<float4*>(dY + base);
+  if (yp >= Hp || xp >= Wp) {          // pixels outside every 'valid' window get no gradient
+    *o00 = zero;
+    if (has_x) *reinterpret_cast<float4*>(dY + base + C) = zero;
+    if (has_y) *reinterpret_cast<float4*>(dY + base + row) = zero;
+    if (has_x && has_y) *reinterpret_cast<float4*>(dY + base + row + C) = zero;
+    return;
   }
-  dY[i] = g;
+  const float4 w00 = *reinterpret_cast<const float4*>(Y + base);
+  const float4 w01 = *reinterpret_cast<const float4*>(Y + base + C);
+  const float4 w10 = *reinterpret_cast<const float4*>(Y + base + row);
+  const float4 w11 = *reinterpret_cast<const float4*>(Y + base + row + C);
+  const float4 g = *reinterpret_cast<const float4*>(dP + ((b * Hp + yp) * Wp + xp) * C + c4 * 4);
+  float4 r00 = zero, r01 = zero, r10 = zero, r11 = zero;
+  auto one = [](float a00, float a01, float a10, float a11, float gv, float& q00, float& q01,
+                float& q10, float& q11) {
+    int arg = 0; float mx = a00;
+    if (a01 > mx) { mx = a01; arg = 1; }
+    if (a10 > mx) { mx = a10; arg = 2; }
+    if (a11 > mx) { mx = a11; arg = 3; }
+    if (!(mx > 0.f)) return;            // ReLU gate of the selected pixel
+    if (arg == 0) q00 = gv; else if (arg == 1) q01 = gv; else if (arg == 2) q10 = gv; else q11 = gv;
+  };
+  one(w00.x, w01.x, w10.x, w11.x, g.x, r00.x, r01.x, r10.x, r11.x);
+  one(w00.y, w01.y, w10.y, w11.y, g.y, r00.y, r01.y, r10.y, r11.y);
+  one(w00.z, w01.z, w10.z, w11.z, g.z, r00.z, r01.z, r10.z, r11.z);
+  one(w00.w, w01.w, w10.w, w11.w, g.w, r00.w, r01.w, r10.w, r11.w);
+  *o00 = r00;
+  *reinterpret_cast<float4*>(dY + base + C) = r01;
+  *reinterpret_cast<float4*>(dY + base + row) = r10;
+  *reinterpret_cast<float4*>(dY + base + row + C) = r11;
 }
 
 __global__ void gap_fwd_kernel(const float* __restrict__ P, int64_t B, int HW, int C,
@@ -196,9 +258,11 @@ inline unsigned nblocks(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 struct EncDims { int H[5], W[5], C[5]; };   // [0] = preprocessed input, [l] = conv l output (pre-pool)
 
-EncDims enc_dims(const ibc_pixel_arch& a) {
+// pad = true: the preprocessed frames carry C*T rounded up to a multiple of 4 channels
+EncDims enc_dims(const ibc_pixel_arch& a, bool pad = false) {
   EncDims d;
   d.H[0] = a.target_height; d.W[0] = a.target_width; d.C[0] = a.channels * a.seq_len;
+  if (pad) d.C[0] = (d.C[0] + 3) / 4 * 4;
   int h = d.H[0], w = d.W[0];
   for (int l = 1; l <= 4; ++l) {
     d.H[l] = h; d.W[l] = w; d.C[l] = kConvCh[l - 1];
@@ -211,12 +275,16 @@ struct EncSave {
   float* X0 = nullptr;
   float* Y[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // conv + relu outputs
   float* P[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // pooled
-  float* col = nullptr;
+  float* col = nullptr;     // im2col rows of one batch chunk (fp32 path only)
+  float* wflip = nullptr;   // flipped kernel of the data-gradient convolution (tf32 path)
+  float* w1pad = nullptr;   // first kernel with zero rows for the padding channels (tf32 path)
+  float* dw1pad = nullptr;  // its gradient
   int chunk = 1;
+  bool tc = false;          // implicit-GEMM convolutions on the tcgen05 kernel
 };
 
-size_t enc_bytes(const ibc_pixel_arch& a, int64_t B, int* chunk_out) {
-  const EncDims d = enc_dims(a);
+size_t enc_bytes(const ibc_pixel_arch& a, int64_t B, int* chunk_out, bool tc) {
+  const EncDims d = enc_dims(a, tc);
   size_t bytes = Workspace::rounded((size_t)B * d.H[0] * d.W[0] * d.C[0] * 4);
   size_t col_per_img = 0;
   for (int l = 1; l <= 4; ++l) {
@@ -231,13 +299,16 @@ size_t enc_bytes(const ibc_pixel_arch& a, int64_t B, int* chunk_out) {
   // keep the GEMM's grid.y (M / 64) under 65535
   while (chunk > 1 && (int64_t)chunk * d.H[1] * d.W[1] / 64 > 60000) --chunk;
   *chunk_out = chunk;
-  bytes += Workspace::rounded((size_t)chunk * col_per_img);
+  if (!tc) bytes += Workspace::rounded((size_t)chunk * col_per_img);
+  bytes += Workspace::rounded((size_t)9 * kConvCh[3] * kConvCh[2] * 4);
+  bytes += 2 * Workspace::rounded((size_t)9 * d.C[0] * kConvCh[0] * 4);
   return bytes;
 }
 
-void carve_enc(ibc_handle* h, const ibc_pixel_arch& a, int64_t B, int chunk, EncSave* s) {
-  const EncDims d = enc_dims(a);
+void carve_enc(ibc_handle* h, const ibc_pixel_arch& a, int64_t B, int chunk, bool tc, EncSave* s) {
+  const EncDims d = enc_dims(a, tc);
   s->chunk = chunk;
+  s->tc = tc;
   s->X0 = h->ws.take<float>((size_t)B * d.H[0] * d.W[0] * d.C[0]);
   size_t col_per_img = 0;
   for (int l = 1; l <= 4; ++l) {
@@ -246,22 +317,39 @@ void carve_enc(ibc_handle* h, const ibc_pixel_arch& a, int64_t B, int chunk, Enc
     const size_t c = (size_t)d.H[l] * d.W[l] * 9 * d.C[l - 1];
     if (c > col_per_img) col_per_img = c;
   }
-  s->col = h->ws.take<float>((size_t)chunk * col_per_img);
+  if (!tc) s->col = h->ws.take<float>((size_t)chunk * col_per_img);
+  s->wflip = h->ws.take<float>((size_t)9 * kConvCh[3] * kConvCh[2]);
+  s->w1pad = h->ws.take<float>((size_t)9 * d.C[0] * kConvCh[0]);
+  s->dw1pad = h->ws.take<float>((size_t)9 * d.C[0] * kConvCh[0]);
 }
 
 int encode_fwd(ibc_pixel_handle* ph, const PixelLayout& L, const void* images, int is_u8,
                int64_t B, const EncSave& sv, float* enc, cudaStream_t s) {
   ibc_handle* h = &ph->core;
   const ibc_pixel_arch& a = ph->arch;
-  const EncDims d = enc_dims(a);
+  const EncDims d = enc_dims(a, sv.tc);
   const float* P = ph->params;
+  const int CT = a.channels * a.seq_len;
   preprocess_kernel<<<nblocks((int64_t)B * d.H[0] * d.W[0] * d.C[0]), 256, 0, s>>>(
-      images, is_u8, B, a.height, a.width, d.C[0], d.H[0], d.W[0], sv.X0);
+      images, is_u8, B, a.height, a.width, CT, d.C[0], d.H[0], d.W[0], sv.X0);
   IBC_LAUNCH_CHECK(h);
+  if (sv.tc) {
+    pad_kernel_channels_kernel<<<nblocks(9 * d.C[0] * kConvCh[0]), 256, 0, s>>>(
+        P + L.conv_k[0], CT, d.C[0], kConvCh[0], sv.w1pad);
+    IBC_LAUNCH_CHECK(h);
+  }
   const float* in = sv.X0;
   for (int l = 1; l <= 4; ++l) {
     const int H = d.H[l], W = d.W[l], Ci = d.C[l - 1], Co = d.C[l];
-    for (int64_t b0 = 0; b0 < B; b0 += sv.chunk) {
+    if (sv.tc) {   // implicit GEMM: the loader gathers the im2col rows from the NHWC input
+      GemmP g;     // Y = relu(im2col(in) . K + b)
+      g.A = in; g.conv_H = H; g.conv_W = W; g.conv_C = Ci; g.lda = 9 * Ci;
+      g.B = (l == 1) ? sv.w1pad : P + L.conv_k[l - 1]; g.ldb = Co; g.C = sv.Y[l]; g.ldc = Co;
+      g.bias = P + L.conv_b[l - 1]; g.M = (int)(B * H * W); g.N = Co; g.K = 9 * Ci;
+      g.relu_out = 1;
+      IBC_TRY(gemm_tc(h, g, false, false, s));
+    }
+    for (int64_t b0 = 0; !sv.tc && b0 < B; b0 += sv.chunk) {
       const int64_t nb = std::min<int64_t>(sv.chunk, B - b0);
       const int64_t M = nb * H * W;
       im2col3x3_kernel<<<nblocks(M * 9 * Ci), 256, 0, s>>>(in + b0 * H * W * Ci, nb, H, W, Ci, sv.col);
@@ -270,7 +358,7 @@ int encode_fwd(ibc_pixel_handle* ph, const PixelLayout& L, const void* images, i
       g.A = sv.col; g.lda = 9 * Ci; g.B = P + L.conv_k[l - 1]; g.ldb = Co;
       g.C = sv.Y[l] + b0 * H * W * Co; g.ldc = Co; g.bias = P + L.conv_b[l - 1];
       g.M = (int)M; g.N = Co; g.K = 9 * Ci; g.relu_out = 1;
-      IBC_TRY(gemm(h, g, false, false, s));
+      IBC_TRY(pgemm(h, g, false, false, s));
     }
     maxpool2_fwd_kernel<<<nblocks((int64_t)B * (H / 2) * (W / 2) * Co), 256, 0, s>>>(
         sv.Y[l], B, H, W, Co, sv.P[l]);
@@ -286,8 +374,9 @@ int encode_fwd(ibc_pixel_handle* ph, const PixelLayout& L, const void* images, i
 int encode_bwd(ibc_pixel_handle* ph, const PixelLayout& L, int64_t B, const EncSave& sv,
                const float* dEnc, float* grads, float* dbufA, float* dbufB, cudaStream_t s) {
   ibc_handle* h = &ph->core;
-  const EncDims d = enc_dims(ph->arch);
+  const EncDims d = enc_dims(ph->arch, sv.tc);
   const float* P = ph->params;
+  const int CT = ph->arch.channels * ph->arch.seq_len;
   // dP4
   float* dP = dbufA;
   gap_bwd_kernel<<<nblocks(B * (d.H[4] / 2) * (d.W[4] / 2) * kEnc), 256, 0, s>>>(
@@ -296,13 +385,39 @@ int encode_bwd(ibc_pixel_handle* ph, const PixelLayout& L, int64_t B, const EncS
   float* dY = dbufB;
   for (int l = 4; l >= 1; --l) {
     const int H = d.H[l], W = d.W[l], Ci = d.C[l - 1], Co = d.C[l];
-    maxpool2_relu_bwd_kernel<<<nblocks((int64_t)B * H * W * Co), 256, 0, s>>>(sv.Y[l], dP, B, H, W,
-                                                                            Co, dY);
+    maxpool2_relu_bwd_kernel<<<nblocks((int64_t)B * ((H + 1) / 2) * ((W + 1) / 2) * (Co / 4)),
+                               256, 0, s>>>(sv.Y[l], dP, B, H, W, Co, dY);
     IBC_LAUNCH_CHECK(h);
     IBC_TRY(colsum_add(h, dY, Co, (int64_t)B * H * W, Co, grads + L.conv_b[l - 1], s));
     const float* in = (l == 1) ? sv.X0 : sv.P[l - 1];
     float* dIn = dP;   // overwritten with the gradient of this layer's input (l > 1)
-    for (int64_t b0 = 0; b0 < B; b0 += sv.chunk) {
+    if (sv.tc) {
+      GemmP gk;   // dK += im2col(in)^T . dY   (rows split over CTAs, atomics)
+      gk.A = in; gk.conv_H = H; gk.conv_W = W; gk.conv_C = Ci; gk.lda = 9 * Ci;
+      gk.B = dY; gk.ldb = Co; gk.C = grads + L.conv_k[l - 1]; gk.ldc = Co;
+      gk.M = 9 * Ci; gk.N = Co; gk.K = (int)(B * H * W); gk.atomic = 1;
+      if (l == 1 && Ci != CT) {
+        gk.C = sv.dw1pad;
+        IBC_CUDA(h, cudaMemsetAsync(sv.dw1pad, 0, (size_t)9 * Ci * Co * 4, s));
+      }
+      IBC_TRY(gemm_tc(h, gk, true, false, s));
+      if (l == 1 && Ci != CT) {
+        unpad_kernel_channels_add_kernel<<<nblocks(9 * CT * Co), 256, 0, s>>>(
+            sv.dw1pad, CT, Ci, Co, grads + L.conv_k[0]);
+        IBC_LAUNCH_CHECK(h);
+      }
+      if (l > 1) {
+        flip_kernel3x3_kernel<<<nblocks(9 * Ci * Co), 256, 0, s>>>(P + L.conv_k[l - 1], Ci, Co,
+                                                                  sv.wflip);
+        IBC_LAUNCH_CHECK(h);
+        GemmP gd;   // dIn = im2col(dY) . Kflip
+        gd.A = dY; gd.conv_H = H; gd.conv_W = W; gd.conv_C = Co; gd.lda = 9 * Co;
+        gd.B = sv.wflip; gd.ldb = Ci; gd.C = dIn; gd.ldc = Ci;
+        gd.M = (int)(B * H * W); gd.N = Ci; gd.K = 9 * Co;
+        IBC_TRY(gemm_tc(h, gd, false, false, s));
+      }
+    }
+    for (int64_t b0 = 0; !sv.tc && b0 < B; b0 += sv.chunk) {
       const int64_t nb = std::min<int64_t>(sv.chunk, B - b0);
       const int64_t M = nb * H * W;
       im2col3x3_kernel<<<nblocks(M * 9 * Ci), 256, 0, s>>>(in + b0 * H * W * Ci, nb, H, W, Ci, sv.col);
@@ -311,12 +426,12 @@ int encode_bwd(ibc_pixel_handle* ph, const PixelLayout& L, int64_t B, const EncS
       gk.A = sv.col; gk.lda = 9 * Ci; gk.B = dY + b0 * H * W * Co; gk.ldb = Co;
       gk.C = grads + L.conv_k[l - 1]; gk.ldc = Co; gk.M = 9 * Ci; gk.N = Co; gk.K = (int)M;
       gk.k_chunk = 2048; gk.atomic = 1;
-      IBC_TRY(gemm(h, gk, true, false, s));
+      IBC_TRY(pgemm(h, gk, true, false, s));
       if (l > 1) {
         GemmP gd;   // dcol = dY . K^T
         gd.A = dY + b0 * H * W * Co; gd.lda = Co; gd.B = P + L.conv_k[l - 1]; gd.ldb = Co;
         gd.C = sv.col; gd.ldc = 9 * Ci; gd.M = (int)M; gd.N = 9 * Ci; gd.K = Co;
-        IBC_TRY(gemm(h, gd, false, true, s));
+        IBC_TRY(pgemm(h, gd, false, true, s));
         col2im3x3_kernel<<<nblocks(M * Ci), 256, 0, s>>>(sv.col, nb, H, W, Ci,
                                                           dIn + b0 * H * W * Ci);
         IBC_LAUNCH_CHECK(h);
@@ -362,14 +477,14 @@ int value_fwd(ibc_pixel_handle* ph, const PixelLayout& L, const float* enc, int6
     GemmP g;
     g.A = enc; g.lda = kEnc; g.B = P + L.d0_w; g.ldb = Wv; g.C = v.encp; g.ldc = Wv;
     g.bias = P + L.d0_b; g.M = (int)B; g.N = Wv; g.K = kEnc;
-    IBC_TRY(gemm(h, g, false, false, s));
+    IBC_TRY(pgemm(h, g, false, false, s));
   }
   {  // x0 = act . W0[256:] + encp[row / n]
     GemmP g;
     g.A = act; g.lda = L.A; g.B = P + L.d0_w + (int64_t)kEnc * Wv; g.ldb = Wv;
     g.C = v.X; g.ldc = Wv; g.rowbias = v.encp; g.ldrb = Wv; g.rows_per_group = n;
     g.M = (int)R; g.N = Wv; g.K = L.A;
-    IBC_TRY(gemm(h, g, false, false, s));
+    IBC_TRY(pgemm(h, g, false, false, s));
   }
   for (int j = 0; j < L.nblk; ++j) {
     const float* x = v.X + (int64_t)j * R * Wv;
@@ -379,16 +494,16 @@ int value_fwd(ibc_pixel_handle* ph, const PixelLayout& L, const float* enc, int6
     GemmP g0;  // y0 = relu(x) . D0 + b
     g0.A = x; g0.lda = Wv; g0.aop = AOP_RELU; g0.B = P + L.b_d0w(j); g0.ldb = Wq;
     g0.C = y0; g0.ldc = Wq; g0.bias = P + L.b_d0b(j); g0.M = (int)R; g0.N = Wq; g0.K = Wv;
-    IBC_TRY(gemm(h, g0, false, false, s));
+    IBC_TRY(pgemm(h, g0, false, false, s));
     GemmP g1;  // y1 = relu(y0) . D1 + b
     g1.A = y0; g1.lda = Wq; g1.aop = AOP_RELU; g1.B = P + L.b_d1w(j); g1.ldb = Wq;
     g1.C = y1; g1.ldc = Wq; g1.bias = P + L.b_d1b(j); g1.M = (int)R; g1.N = Wq; g1.K = Wq;
-    IBC_TRY(gemm(h, g1, false, false, s));
+    IBC_TRY(pgemm(h, g1, false, false, s));
     GemmP g2;  // x' = x + relu(y1) . D2 + b
     g2.A = y1; g2.lda = Wq; g2.aop = AOP_RELU; g2.B = P + L.b_d2w(j); g2.ldb = Wv;
     g2.C = xn; g2.ldc = Wv; g2.bias = P + L.b_d2b(j); g2.res = x; g2.ldres = Wv;
     g2.M = (int)R; g2.N = Wv; g2.K = Wq;
-    IBC_TRY(gemm(h, g2, false, false, s));
+    IBC_TRY(pgemm(h, g2, false, false, s));
   }
   IBC_TRY(rowdot(h, v.X + (int64_t)L.nblk * R * Wv, Wv, P + L.d1_w, P + L.d1_b, R, Wv, E, s));
   return IBC_OK;
@@ -399,7 +514,7 @@ static int dwg(ibc_handle* h, const float* X, int64_t ldx, int aop, const float*
   GemmP g;
   g.A = X; g.lda = ldx; g.aop = aop; g.B = Y; g.ldb = ldy; g.C = dW; g.ldc = Nout;
   g.M = Kin; g.N = Nout; g.K = (int)R; g.k_chunk = 1024; g.atomic = 1;
-  return gemm(h, g, true, false, s);
+  return pgemm(h, g, true, false, s);
 }
 
 // Value-head backward: parameter gradients (accumulated) and dEnc [B, 256].
@@ -430,19 +545,19 @@ int value_bwd(ibc_pixel_handle* ph, const PixelLayout& L, const float* enc, int6
     GemmP a1;  // g1 = (G . D2^T) (.) (y1 > 0)
     a1.A = G; a1.lda = Wv; a1.B = P + L.b_d2w(j); a1.ldb = Wv; a1.C = g1b; a1.ldc = Wq;
     a1.gateC = y1; a1.ldgc = Wq; a1.M = (int)R; a1.N = Wq; a1.K = Wv;
-    IBC_TRY(gemm(h, a1, false, true, s));
+    IBC_TRY(pgemm(h, a1, false, true, s));
     IBC_TRY(dwg(h, y0, Wq, AOP_RELU, g1b, Wq, R, Wq, Wq, grads + L.b_d1w(j), s));
     IBC_TRY(colsum_add(h, g1b, Wq, R, Wq, grads + L.b_d1b(j), s));
     GemmP a0;  // g0 = (g1 . D1^T) (.) (y0 > 0)
     a0.A = g1b; a0.lda = Wq; a0.B = P + L.b_d1w(j); a0.ldb = Wq; a0.C = g0b; a0.ldc = Wq;
     a0.gateC = y0; a0.ldgc = Wq; a0.M = (int)R; a0.N = Wq; a0.K = Wq;
-    IBC_TRY(gemm(h, a0, false, true, s));
+    IBC_TRY(pgemm(h, a0, false, true, s));
     IBC_TRY(dwg(h, x, Wv, AOP_RELU, g0b, Wq, R, Wv, Wq, grads + L.b_d0w(j), s));
     IBC_TRY(colsum_add(h, g0b, Wq, R, Wq, grads + L.b_d0b(j), s));
     GemmP ax;  // G' = G + (g0 . D0^T) (.) (x > 0)
     ax.A = g0b; ax.lda = Wq; ax.B = P + L.b_d0w(j); ax.ldb = Wq; ax.C = Gn; ax.ldc = Wv;
     ax.gateC = x; ax.ldgc = Wv; ax.res = G; ax.ldres = Wv; ax.M = (int)R; ax.N = Wv; ax.K = Wq;
-    IBC_TRY(gemm(h, ax, false, true, s));
+    IBC_TRY(pgemm(h, ax, false, true, s));
     G = Gn;
   }
   // dense0 on x = [enc tiled, act]
@@ -454,7 +569,7 @@ int value_bwd(ibc_pixel_handle* ph, const PixelLayout& L, const float* enc, int6
     GemmP g;
     g.A = gsum; g.lda = Wv; g.B = P + L.d0_w; g.ldb = Wv; g.C = dEnc; g.ldc = kEnc;
     g.M = (int)B; g.N = kEnc; g.K = Wv;
-    IBC_TRY(gemm(h, g, false, true, s));
+    IBC_TRY(pgemm(h, g, false, true, s));
   }
   return IBC_OK;
 }
@@ -505,6 +620,17 @@ int ibc_pixel_create(const ibc_pixel_arch* arch, int device, ibc_pixel_handle** 
   ph->arch = *arch;
   ph->core.device = device;
   ph->core.sm_count = prop.multiProcessorCount;
+  ph->core.precision = IBC_PRECISION_TF32;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(device);
+  const cudaError_t me = cudaMalloc((void**)&ph->core.dev_status, sizeof(int));
+  if (me == cudaSuccess) cudaMemset(ph->core.dev_status, 0, sizeof(int));
+  if (prev >= 0) cudaSetDevice(prev);
+  if (me != cudaSuccess) {
+    delete ph;
+    IBC_FAIL(h, IBC_ERR_CUDA, "ibc_pixel_create: cudaMalloc failed: %s", cudaGetErrorString(me));
+  }
   *out = ph;
   return IBC_OK;
 }
@@ -517,6 +643,7 @@ int ibc_pixel_destroy(ibc_pixel_handle* ph) {
   cudaDeviceSynchronize();
   if (ph->core.ws.base) cudaFree(ph->core.ws.base);
   if (ph->core.ws_outer.base) cudaFree(ph->core.ws_outer.base);
+  if (ph->core.dev_status) cudaFree(ph->core.dev_status);
   if (prev >= 0) cudaSetDevice(prev);
   delete ph;
   return IBC_OK;
@@ -524,6 +651,29 @@ int ibc_pixel_destroy(ibc_pixel_handle* ph) {
 
 const char* ibc_pixel_last_error(const ibc_pixel_handle* ph) {
   return ph ? ph->core.err.c_str() : ibc::g_create_error;
+}
+
+int ibc_pixel_set_precision(ibc_pixel_handle* ph, int precision) {
+  PIX_ENTER(ph);
+  if (precision != IBC_PRECISION_FP32 && precision != IBC_PRECISION_TF32)
+    IBC_FAIL(h, IBC_ERR_INVALID, "unknown precision %d", precision);
+  h->precision = precision;
+  return IBC_OK;
+}
+
+int ibc_pixel_get_precision(const ibc_pixel_handle* ph) {
+  return ph ? ph->core.precision : IBC_ERR_INVALID;
+}
+
+int ibc_pixel_kernel_status(ibc_pixel_handle* ph, int32_t* status_host) {
+  PIX_ENTER(ph);
+  if (!status_host) IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_kernel_status: null argument");
+  IBC_CUDA(h, cudaDeviceSynchronize());
+  int st = 0;
+  IBC_CUDA(h, cudaMemcpy(&st, h->dev_status, sizeof(int), cudaMemcpyDeviceToHost));
+  IBC_CUDA(h, cudaMemset(h->dev_status, 0, sizeof(int)));
+  *status_host = st;
+  return IBC_OK;
 }
 
 int ibc_pixel_bind_params(ibc_pixel_handle* ph, const float* params) {
@@ -540,11 +690,12 @@ int ibc_pixel_encode(ibc_pixel_handle* ph, const void* images, int32_t is_uint8,
   if (!ph->params) IBC_FAIL(h, IBC_ERR_INVALID, "no parameters bound (ibc_pixel_bind_params)");
   const PixelLayout L = make_pixel_layout(ph->arch);
   int chunk = 1;
-  const size_t bytes = enc_bytes(ph->arch, B, &chunk);
+  const bool tc = h->precision == IBC_PRECISION_TF32;
+  const size_t bytes = enc_bytes(ph->arch, B, &chunk, tc);
   IBC_CUDA(h, h->ws.reserve(bytes));
   h->ws.reset();
   EncSave sv;
-  carve_enc(h, ph->arch, B, chunk, &sv);
+  carve_enc(h, ph->arch, B, chunk, tc, &sv);
   return encode_fwd(ph, L, images, is_uint8, B, sv, enc, (cudaStream_t)stream);
 }
 
@@ -603,7 +754,8 @@ int ibc_pixel_train_grads(ibc_pixel_handle* ph, const void* images, int32_t is_u
   size_t dmax = 0;   // largest activation tensor (gradient ping-pong buffers)
   for (int l = 1; l <= 4; ++l)
     dmax = std::max(dmax, (size_t)B * d.H[l] * d.W[l] * d.C[l]);
-  size_t bytes = enc_bytes(ph->arch, B, &chunk) + val_bytes(L, B, R) +
+  const bool tc = h->precision == IBC_PRECISION_TF32;
+  size_t bytes = enc_bytes(ph->arch, B, &chunk, tc) + val_bytes(L, B, R) +
                  2 * Workspace::rounded(dmax * 4) + 2 * Workspace::rounded((size_t)R * L.Wv * 4) +
                  2 * Workspace::rounded((size_t)R * L.Wq * 4) +
                  Workspace::rounded((size_t)B * L.Wv * 4) + 2 * Workspace::rounded((size_t)B * kEnc * 4) +
@@ -611,7 +763,7 @@ int ibc_pixel_train_grads(ibc_pixel_handle* ph, const void* images, int32_t is_u
   IBC_CUDA(h, h->ws.reserve(bytes));
   h->ws.reset();
   EncSave sv;
-  carve_enc(h, ph->arch, B, chunk, &sv);
+  carve_enc(h, ph->arch, B, chunk, tc, &sv);
   ValSave v;
   carve_val(h, L, B, R, &v);
   float* dA = h->ws.take<float>(dmax);

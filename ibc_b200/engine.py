@@ -252,6 +252,18 @@ class PixelEngine:
     self._params = params
     _lib.check(self.lib.ibc_pixel_bind_params(self._h, _ptr(params)), self._h, pixel=True)
 
+  @property
+  def precision(self) -> int:
+    return int(self.lib.ibc_pixel_get_precision(self._h))
+
+  def set_precision(self, precision: int):
+    _lib.check(self.lib.ibc_pixel_set_precision(self._h, int(precision)), self._h, pixel=True)
+
+  def kernel_status(self) -> int:
+    st = ctypes.c_int32(-1)
+    _lib.check(self.lib.ibc_pixel_kernel_status(self._h, ctypes.byref(st)), self._h, pixel=True)
+    return int(st.value)
+
   def _check_images(self, images):
     a = self.arch
     if not images.is_cuda or not images.is_contiguous():
@@ -427,6 +439,30 @@ def langevin_stepsizes(cfg: LangevinCfg):
   out = (ctypes.c_float * max(cfg.num_iterations, 1))()
   _lib.check(_lib.load().ibc_langevin_stepsizes(ctypes.byref(cfg), out))
   return [float(out[i]) for i in range(cfg.num_iterations)]
+
+
+def gemm_tf32(a: torch.Tensor, b: torch.Tensor, m: int, n: int, k: int, trans_a=False,
+              trans_b=False, bias=None, gate_c=None, res=None, relu_a=False, relu_out=False,
+              out: Optional[torch.Tensor] = None, check: bool = True):
+  """C[m, n] = f(op(A) . op(B) + bias) (.) (gate_c > 0) + res) on the general tcgen05 tf32
+  GEMM (ibc_gemm_tf32); A / B are 2-D row-major (their row stride is the leading
+  dimension); with `out` the product is accumulated into it (split-K atomics).
+  Returns (C, status); with check=False the call does not wait and status is None."""
+  for t, name in ((a, 'A'), (b, 'B')):
+    if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1):
+      raise ValueError('%s must be a 2-D CUDA float32 tensor with unit column stride' % name)
+  for t in (bias, gate_c, res):
+    if t is not None:
+      _check_f32(t, 'epilogue operand')
+  c = out if out is not None else torch.empty(m, n, device=a.device, dtype=torch.float32)
+  st = ctypes.c_int32(-1)
+  _lib.check(_lib.load().ibc_gemm_tf32(
+      _ptr(a), a.stride(0), int(trans_a), _ptr(b), b.stride(0), int(trans_b), _ptr(c), c.stride(0),
+      m, n, k, _ptr(bias) if bias is not None else None,
+      _ptr(gate_c) if gate_c is not None else None, _ptr(res) if res is not None else None,
+      int(relu_a), int(relu_out), int(out is not None), ctypes.byref(st) if check else None,
+      _stream()))
+  return c, (int(st.value) if check else None)
 
 
 def umma_selftest(a: torch.Tensor, bt: torch.Tensor, mode: int = 0):

@@ -257,6 +257,13 @@ int ibc_pixel_destroy(ibc_pixel_handle* h);
 const char* ibc_pixel_last_error(const ibc_pixel_handle* h);
 int64_t ibc_pixel_param_count(const ibc_pixel_arch* arch);
 int ibc_pixel_bind_params(ibc_pixel_handle* h, const float* params);
+/* IBC_PRECISION_TF32 (default): convolutions (as im2col rows), value head and all
+ * their data / weight gradients on the tcgen05 kind::tf32 GEMM; IBC_PRECISION_FP32:
+ * the same contractions on fp32 FMA kernels. */
+int ibc_pixel_set_precision(ibc_pixel_handle* h, int precision);
+int ibc_pixel_get_precision(const ibc_pixel_handle* h);
+/* As ibc_kernel_status, for the kernels launched through a pixel handle. */
+int ibc_pixel_kernel_status(ibc_pixel_handle* h, int32_t* status_host);
 
 /* PixelEBM.encode (pixel_ebm.py:79-96): images [B, T, H, W, C] uint8 (is_uint8)
  * or float32 in [0,1] -> u8/255, RAW reshape to [B, H, W, C*T]
@@ -316,6 +323,24 @@ int ibc_kernel_status(ibc_handle* h, int32_t* status_host);
 int ibc_umma_selftest(const float* A, const float* Bt, int32_t N, int32_t K,
                       int32_t mode, float* D, int32_t* status_host,
                       void* stream);
+
+/* The general tcgen05 tf32 GEMM behind the Keras Dense / Conv2D contractions that
+ * are not layer-fused (networks/layers/dense_resnet_value.py:31-69,
+ * networks/layers/conv_maxpool.py:20-48, the second-order passes of
+ * ibc/losses/gradient_loss.py:23-72), exposed for parity tests and benchmarks:
+ *   C[M, N] (+)= f((op(A) . op(B)) + bias) (.) (gate_c > 0) + res),  f = id or relu
+ *   op(A)(m, k) = trans_a ? A[k * lda + m] : A[m * lda + k], ReLU'd first when relu_a
+ *   op(B)(k, n) = trans_b ? B[n * ldb + k] : B[k * ldb + n]
+ * bias [N], gate_c / res [M, N] with leading dimension ldc (each may be NULL).
+ * Operands are rounded to nearest tf32, accumulation is fp32.  accumulate != 0
+ * adds into C with atomics over a K split (weight-gradient form).
+ * status_host, when not NULL, makes the call wait for the product and receives 0,
+ * or the code of a barrier that timed out. */
+int ibc_gemm_tf32(const float* A, int64_t lda, int32_t trans_a, const float* B,
+                  int64_t ldb, int32_t trans_b, float* C, int64_t ldc, int32_t M,
+                  int32_t N, int32_t K, const float* bias, const float* gate_c,
+                  const float* res, int32_t relu_a, int32_t relu_out,
+                  int32_t accumulate, int32_t* status_host, void* stream);
 
 #ifdef __cplusplus
 }

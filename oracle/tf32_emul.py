@@ -45,3 +45,58 @@ def energy(flat: torch.Tensor, spec: omlp.MLPSpec, obs: torch.Tensor,
     v = _MatmulTF32.apply(torch.relu(h), p[f'W1_{j}']) + p[f'b1_{j}']
     h = h + _MatmulTF32.apply(torch.relu(v), p[f'W2_{j}']) + p[f'b2_{j}']
   return h @ p['we'] + p['be']
+
+
+# ---- PixelEBM on the general tf32 GEMM (csrc/gemm_tc.cu) ------------------------------
+# Every operand of a contraction is rounded to nearest on the way into shared memory,
+# in the forward, data-gradient and weight-gradient products alike.
+
+
+class _RoundOperand(torch.autograd.Function):
+  @staticmethod
+  def forward(ctx, x):
+    return round_tf32(x)
+
+  @staticmethod
+  def backward(ctx, g):
+    return g
+
+
+class _RoundGradient(torch.autograd.Function):
+  @staticmethod
+  def forward(ctx, y):
+    return y.clone()
+
+  @staticmethod
+  def backward(ctx, g):
+    return round_tf32(g)
+
+
+def _mm(a, w):
+  return _RoundGradient.apply(_RoundOperand.apply(a) @ _RoundOperand.apply(w))
+
+
+def pixel_energy(flat: torch.Tensor, spec, images: torch.Tensor, act: torch.Tensor) -> torch.Tensor:
+  """Same signature as oracle.pixel_ebm.energy (networks/pixel_ebm.py:98-125) with tf32
+  operands in the convolutions and the value head; the K = act_dim product and the
+  [B, 256] encoding projection stay exact (the CUDA path keeps blocks of fewer than 64
+  rows or K < 16 on the fp32 kernel)."""
+  import torch.nn.functional as F
+  from oracle import pixel_ebm as opix
+  p = opix.unpack(flat, spec)
+  x = opix.preprocess(images, spec).permute(0, 3, 1, 2)
+  for i in range(4):
+    k = p[f'conv{i + 1}_k'].permute(3, 2, 0, 1)
+    y = F.conv2d(_RoundOperand.apply(x), _RoundOperand.apply(k), None, padding=1)
+    x = F.relu(_RoundGradient.apply(y) + p[f'conv{i + 1}_b'].reshape(1, -1, 1, 1))
+    x = F.max_pool2d(x, 2)
+  enc = x.mean(dim=(2, 3))
+  n = act.shape[0] // images.shape[0]
+  w0 = p['v_dense0_W']
+  x = torch.repeat_interleave(enc @ w0[:256] + p['v_dense0_b'], n, dim=0) + act @ w0[256:]
+  for j in range(spec.value_blocks):
+    y = _mm(torch.relu(x), p[f'v_blk{j}_d0_W']) + p[f'v_blk{j}_d0_b']
+    y = _mm(torch.relu(y), p[f'v_blk{j}_d1_W']) + p[f'v_blk{j}_d1_b']
+    y = _mm(torch.relu(y), p[f'v_blk{j}_d2_W']) + p[f'v_blk{j}_d2_b']
+    x = x + y
+  return x @ p['v_dense1_W'] + p['v_dense1_b']
