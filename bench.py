@@ -408,18 +408,28 @@ def secondary_configs(device):
     out[name] = {'ms_per_chain': t * 1e3, 'rows': b * n, 'iterations': k,
                  'energy_grad_evals_per_s': b * n * k / t, 'precision': 'tf32',
                  'kernel_status': e.kernel_status()}
-  # PixelEBM (fp32 path)
+  # C5 PixelEBM (pushing_pixels/pixel_ebm_best.gin shapes): late-fusion train step at the
+  # gin's batch 128 with 256 counter-examples, tf32 tensor-core path and the fp32 path
+  from ibc_b200 import _lib
   pe = eng.PixelEngine(2, 240, 320, 3, 180, 240, 2, 1024, 1, device)
   pp = (torch.randn(pe.param_count, device=device) * 0.05).contiguous()
   pe.bind_params(pp)
-  b, n = 32, 256
+  b, n = 128, 256
   img = torch.randint(0, 256, (b, 2, 240, 320, 3), device=device, dtype=torch.uint8)
   acts = torch.rand(b * (n + 1), 2, device=device) * 2 - 1
   cfg = eng.loss_cfg(1.0, False)
-  pe.train_grads(img, acts, n, cfg, b)
-  t = timed(lambda i: pe.train_grads(img, acts, n, cfg, b), 2, lambda: None) / 2
-  out['C5_pixel_ebm_train_grads'] = {'ms_per_step': t * 1e3, 'images': b, 'rows': b * (n + 1),
-                                     'images_per_s': b / t, 'precision': 'fp32 (im2col + FMA GEMM)'}
+  # canonical FLOPs: encoder 1.335 G / image, value head 1 710 080 / row, x 3
+  flops = 3.0 * (b * 1.335e9 + b * (n + 1) * 1710080.0)
+  for prec, key, label in ((_lib.PRECISION_TF32, 'C5_pixel_ebm_train_grads',
+                            'tf32 (tcgen05 implicit-GEMM convolutions + value head, fp32 accumulate)'),
+                           (_lib.PRECISION_FP32, 'C5_pixel_ebm_train_grads_fp32',
+                            'fp32 (im2col + FMA GEMM)')):
+    pe.set_precision(prec)
+    pe.train_grads(img, acts, n, cfg, b)
+    t = timed(lambda i: pe.train_grads(img, acts, n, cfg, b), 3, lambda: None) / 3
+    out[key] = {'ms_per_step': t * 1e3, 'images': b, 'rows': b * (n + 1), 'images_per_s': b / t,
+                'energy_evals_per_s': b * (n + 1) / t, 'tflops': flops / t * 1e-12,
+                'precision': label, 'kernel_status': pe.kernel_status()}
   return out
 
 

@@ -30,6 +30,9 @@ struct GemmP {
   int relu_out = 0;  // C = max(C, 0) (not with split-K)
   float alpha = 1.f;
   int tc = 0;        // tcgen05 tf32 kernel (gemm_tc.cu) when the handle's precision is TF32
+  // gemm_tc only: the operand's values are already tf32 (rounded by their producer), so
+  // the kernel's in-place rounding pass over that operand is skipped
+  int a_tf32 = 0, b_tf32 = 0;
   // Implicit 3x3 'same' convolution (gemm_tc only): when conv_C > 0, A points at an NHWC
   // tensor [*, conv_H, conv_W, conv_C] and the logical A operand is its im2col matrix
   //   A[(b, y, x), (ky, kx, c)] = X[b, y + ky - 1, x + kx - 1, c]   (zero outside the frame)

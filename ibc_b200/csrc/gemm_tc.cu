@@ -12,9 +12,10 @@
 // the MMA wants -- chosen per operand so that neither side transposes -- and each thread
 // then applies the prologue (ReLU / gate, round-to-nearest tf32) in place to the pieces
 // it copied:
-//   * operand contiguous along K (A[m, k], B^T[n, k]):  K-major SWIZZLE_NONE "chunk-major"
-//     [K/4][rows][4]; a quarter-warp takes 8 consecutive rows of one chunk (128
-//     contiguous bytes of shared memory, 64 contiguous bytes of each global row);
+//   * operand contiguous along K (A[m, k], B^T[n, k]):  K-major SWIZZLE_128B, a row of 32
+//     K-elements is one 128-byte line; eight lanes take a row (128 contiguous bytes of
+//     global memory -> one conflict-free line; the unswizzled chunk-major layout made
+//     the asynchronous copies 8-way bank conflicted, ncu r1);
 //   * operand contiguous along M / N (A^T[k, m], B[k, n]):  MN-major
 //     SWIZZLE_128B_BASE32B atoms (umma_pack.cuh::mn32_offset); a warp takes one K-row
 //     (512 contiguous bytes of global memory, conflict-free 128-byte lines).
@@ -84,6 +85,29 @@ __device__ __forceinline__ float4 ld_shared16(uint32_t src) {
   return v;
 }
 
+// Bounded mbarrier wait without a suspend-time hint (the hardware's default time limit):
+// the waits of this kernel sit on the critical path of every K-slice, and the 20 us hint
+// of umma::mbar_wait (chosen for the layer-fused kernels' long idle waits) delays wake-ups.
+__device__ __forceinline__ bool tc_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag,
+                                        int* status, int code) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t it = 0; it < (1u << 22); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return true;
+    if ((it & 63) == 63 && *abort_flag) return false;
+  }
+  *abort_flag = 1;
+  if (status) atomicCAS(status, 0, code);
+  return false;
+}
+
 // Four consecutive elements along the contiguous dimension of a row-major operand.
 //   KC  (contiguous along K):   element j = src[r * ld + k + j]   (valid: r < rlim, k + j < klim)
 //   !KC (contiguous along M/N): element j = src[k * ld + r + j]   (valid: k < klim, r + j < rlim)
@@ -126,11 +150,13 @@ __device__ __forceinline__ void issue4(uint32_t dst, const float* __restrict__ s
 template <bool KC, int ROWS>
 __device__ __forceinline__ uint32_t piece(int idx, int& r, int& k) {
   if (KC) {
-    const int u = idx >> 5, lane = idx & 31;
-    r = (u >> 1) * 8 + (lane & 7);
-    const int chunk = (u & 1) * 4 + (lane >> 3);
+    // K-major SWIZZLE_128B: row r is one 128-byte line (32 K-elements), its 16-byte chunk c
+    // sits at position c ^ (r & 7).  Eight lanes take one row: 128 contiguous bytes of
+    // global memory land in one conflict-free shared-memory line.
+    r = idx >> 3;
+    const int chunk = idx & 7;
     k = chunk * 4;
-    return (uint32_t)chunk * (ROWS * 16) + (uint32_t)r * 16;
+    return (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
   } else {
     const int mn4 = idx % (ROWS / 4);
     k = idx / (ROWS / 4);
@@ -280,12 +306,14 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_kernel(GemmP p, int* stat
     };
     // Stage ks has landed: each thread applies the prologue to the pieces it copied
     // itself (ReLU / gate on A, round-to-nearest tf32 on both), in place.
+    const bool fin_a = !(p.a_tf32 && p.aop == AOP_ID), fin_b = !p.b_tf32;
     auto finish = [&](int ks) {
       const int k0 = kbeg + ks * kBK;
       const uint32_t sa = ring_addr + (uint32_t)((ks % S) * C::kStageBytes);
       const uint32_t sb = sa + C::kABytes;
 #pragma unroll
       for (int j = 0; j < NA; ++j) {
+        if (!fin_a) break;
         int r, k;
         const uint32_t dst = sa + piece<AKC, kBM>(j * kLoaderThreads + tid, r, k);
         float4 v = ld_shared16(dst);
@@ -302,6 +330,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_kernel(GemmP p, int* stat
       }
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
+        if (!fin_b) break;
         int r, k;
         const uint32_t dst = sb + piece<BKC, BN>(j * kLoaderThreads + tid, r, k);
         st_shared16(dst, tf32_rn4(ld_shared16(dst)));
@@ -320,14 +349,14 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_kernel(GemmP p, int* stat
       // refill the stage MMA ks-1 read (it ran while this stage was being finished)
       const int nxt = ks + S - 1;
       if (nxt < nks) {
-        mbar_wait(&empty[nxt % S], ((nxt / S) & 1) ^ 1, abort_flag, status, 930);
+        tc_wait(&empty[nxt % S], ((nxt / S) & 1) ^ 1, abort_flag, status, 930);
         issue(nxt);
       }
       cp_async_commit();
     }
 
     // ===================== epilogue ==================================================
-    if (nks > 0) mbar_wait(d_ready, 0, abort_flag, status, 931);
+    if (nks > 0) tc_wait(d_ready, 0, abort_flag, status, 931);
     tc_fence_after();
     const int q = warp & 3, hh = warp >> 2;
     float* stg = reinterpret_cast<float*>(ring) + warp * (32 * 33);
@@ -370,18 +399,19 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_kernel(GemmP p, int* stat
     // ===================== MMA issuer ================================================
     constexpr uint32_t idesc = idesc_tf32(kBM, BN) | (TA ? kIdescAMajorMN : 0u) |
                                (TB ? 0u : kIdescBMajorMN);
-    constexpr uint32_t a_step16 = AKC ? (2u * kBM * 16u) >> 4 : 1024u >> 4;
-    constexpr uint32_t b_step16 = BKC ? (2u * BN * 16u) >> 4 : 1024u >> 4;
+    // one K = 8 step: 32 bytes along the swizzled line (K-major), two 512-byte K atoms (MN-major)
+    constexpr uint32_t a_step16 = AKC ? 32u >> 4 : 1024u >> 4;
+    constexpr uint32_t b_step16 = BKC ? 32u >> 4 : 1024u >> 4;
     for (int ks = 0; ks < nks; ++ks) {
       const int st = ks % S;
       if (elect_one()) {
-        mbar_wait(&full[st], (ks / S) & 1, abort_flag, status, 932);
+        tc_wait(&full[st], (ks / S) & 1, abort_flag, status, 932);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(ring + st * C::kStageBytes);
         const uint32_t b_addr = a_addr + C::kABytes;
-        const uint64_t ad = AKC ? smem_desc(a_addr, kBM * 16, 128)
+        const uint64_t ad = AKC ? smem_desc_lt(a_addr, 16, 1024, 2)
                                 : smem_desc_lt(a_addr, kMnLbo, kMnSbo, 1);
-        const uint64_t bd = BKC ? smem_desc(b_addr, BN * 16, 128)
+        const uint64_t bd = BKC ? smem_desc_lt(b_addr, 16, 1024, 2)
                                 : smem_desc_lt(b_addr, kMnLbo, kMnSbo, 1);
         mma_tf32_ss_steps<kBK / 8>(tmem_base, ad, bd, a_step16, b_step16, idesc,
                                    ks == 0 ? 0u : 1u);

@@ -17,6 +17,7 @@
 
 #include "gemm_simt.cuh"
 #include "ops.cuh"
+#include "umma_pack.cuh"
 
 struct ibc_pixel_handle {
   ibc_handle core;          // workspaces, error string, launch accounting
@@ -81,7 +82,8 @@ int pgemm(ibc_handle* h, GemmP g, bool ta, bool tb, cudaStream_t s) {
 // The output has Cp >= CT channels per pixel; channels CT .. Cp-1 are zero (the tf32 path
 // pads to a multiple of 4 so that the convolution's loader moves 16-byte pieces).
 __global__ void preprocess_kernel(const void* __restrict__ img, int is_u8, int64_t B, int H, int W,
-                                  int CT, int Cp, int th, int tw, float* __restrict__ out) {
+                                  int CT, int Cp, int th, int tw, int round,
+                                  float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t tot = B * th * tw * Cp;
   if (i >= tot) return;
@@ -104,7 +106,8 @@ __global__ void preprocess_kernel(const void* __restrict__ img, int is_u8, int64
   };
   const float top = at(y0, x0) + lx * (at(y0, x1) - at(y0, x0));
   const float bot = at(y1, x0) + lx * (at(y1, x1) - at(y1, x0));
-  out[i] = top + ly * (bot - top);
+  const float v = top + ly * (bot - top);
+  out[i] = round ? tf32_rn(v) : v;
 }
 
 // col[(b,y,x), (ky,kx,c)] = X[b, y+ky-1, x+kx-1, c] (zero padded), X is NHWC.
@@ -146,23 +149,30 @@ __global__ void col2im3x3_kernel(const float* __restrict__ dcol, int64_t nb, int
   dX[i] = s;
 }
 
-// Kd[(8 - tap), co, c] = K[tap, c, co]: the data gradient of a 3x3 'same' convolution is
+// Kd[(8 - tap), co, c] = tf32(K[tap, c, co]): the data gradient of a 3x3 'same' convolution is
 // the convolution of dY with the taps flipped and the channel roles exchanged.
 __global__ void flip_kernel3x3_kernel(const float* __restrict__ K, int Ci, int Co,
                                       float* __restrict__ Kd) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 9 * Ci * Co) return;
   const int co = i % Co, c = (i / Co) % Ci, tap = i / (Co * Ci);
-  Kd[((8 - tap) * Co + co) * Ci + c] = K[i];
+  Kd[((8 - tap) * Co + co) * Ci + c] = tf32_rn(K[i]);
 }
 
-// Kp[tap, c, co] (c < Cp) = c < C ? K[tap, c, co] : 0
+// out[i] = tf32(in[i]): the weights as MMA operands (rounded once per call instead of
+// in every block of every product that reads them)
+__global__ void round_copy_kernel(const float* __restrict__ in, int64_t n, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = tf32_rn(in[i]);
+}
+
+// Kp[tap, c, co] (c < Cp) = c < C ? tf32(K[tap, c, co]) : 0
 __global__ void pad_kernel_channels_kernel(const float* __restrict__ K, int C, int Cp, int Co,
                                            float* __restrict__ Kp) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 9 * Cp * Co) return;
   const int co = i % Co, c = (i / Co) % Cp, tap = i / (Co * Cp);
-  Kp[i] = c < C ? K[(tap * C + c) * Co + co] : 0.f;
+  Kp[i] = c < C ? tf32_rn(K[(tap * C + c) * Co + co]) : 0.f;
 }
 // dK[tap, c, co] += dKp[tap, c, co] for c < C
 __global__ void unpad_kernel_channels_add_kernel(const float* __restrict__ dKp, int C, int Cp,
@@ -173,8 +183,10 @@ __global__ void unpad_kernel_channels_add_kernel(const float* __restrict__ dKp, 
   dK[i] += dKp[(tap * Cp + c) * Co + co];
 }
 
+// round: the pooled map is only ever a tf32 MMA operand (the next convolution and its
+// weight gradient), so the tf32 path rounds it here instead of in every consumer.
 __global__ void maxpool2_fwd_kernel(const float* __restrict__ Y, int64_t n, int H, int W, int C,
-                                    float* __restrict__ P) {
+                                    int round, float* __restrict__ P) {
   const int Hp = H / 2, Wp = W / 2;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * Hp * Wp * C) return;
@@ -182,14 +194,16 @@ __global__ void maxpool2_fwd_kernel(const float* __restrict__ Y, int64_t n, int 
   const int x = (int)((i / C) % Wp), y = (int)((i / ((int64_t)C * Wp)) % Hp);
   const int64_t b = i / ((int64_t)C * Wp * Hp);
   const float* p = Y + ((b * H + 2 * y) * W + 2 * x) * C + c;
-  P[i] = fmaxf(fmaxf(p[0], p[C]), fmaxf(p[(int64_t)W * C], p[(int64_t)W * C + C]));
+  const float v = fmaxf(fmaxf(p[0], p[C]), fmaxf(p[(int64_t)W * C], p[(int64_t)W * C + C]));
+  P[i] = round ? tf32_rn(v) : v;
 }
 
 // dY = (first maximum of its 2x2 window ? dP : 0) * (Y > 0)   (MaxPool + ReLU backward)
 // One thread = one 2x2 window (or unpooled edge pixel pair) x 4 channels: four 16-byte
 // loads of Y, one of dP, four 16-byte stores.  C must be a multiple of 4 (32 .. 256).
 __global__ void maxpool2_relu_bwd_kernel(const float* __restrict__ Y, const float* __restrict__ dP,
-                                         int64_t n, int H, int W, int C, float* __restrict__ dY) {
+                                         int64_t n, int H, int W, int C, int round,
+                                         float* __restrict__ dY) {
   const int Hp = H / 2, Wp = W / 2;
   const int Hc = (H + 1) / 2, Wc = (W + 1) / 2, C4 = C / 4;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -213,7 +227,8 @@ __global__ void maxpool2_relu_bwd_kernel(const float* __restrict__ Y, const floa
   const float4 w01 = *reinterpret_cast<const float4*>(Y + base + C);
   const float4 w10 = *reinterpret_cast<const float4*>(Y + base + row);
   const float4 w11 = *reinterpret_cast<const float4*>(Y + base + row + C);
-  const float4 g = *reinterpret_cast<const float4*>(dP + ((b * Hp + yp) * Wp + xp) * C + c4 * 4);
+  float4 g = *reinterpret_cast<const float4*>(dP + ((b * Hp + yp) * Wp + xp) * C + c4 * 4);
+  if (round) g = tf32_rn4(g);   // dY is a tf32 MMA operand of both gradient products
   float4 r00 = zero, r01 = zero, r10 = zero, r11 = zero;
   auto one = [](float a00, float a01, float a10, float a11, float gv, float& q00, float& q01,
                 float& q10, float& q11) {
@@ -279,6 +294,7 @@ struct EncSave {
   float* wflip = nullptr;   // flipped kernel of the data-gradient convolution (tf32 path)
   float* w1pad = nullptr;   // first kernel with zero rows for the padding channels (tf32 path)
   float* dw1pad = nullptr;  // its gradient
+  float* wr = nullptr;      // tf32-rounded copy of the conv parameters, same offsets (tf32 path)
   int chunk = 1;
   bool tc = false;          // implicit-GEMM convolutions on the tcgen05 kernel
 };
@@ -302,6 +318,7 @@ size_t enc_bytes(const ibc_pixel_arch& a, int64_t B, int* chunk_out, bool tc) {
   if (!tc) bytes += Workspace::rounded((size_t)chunk * col_per_img);
   bytes += Workspace::rounded((size_t)9 * kConvCh[3] * kConvCh[2] * 4);
   bytes += 2 * Workspace::rounded((size_t)9 * d.C[0] * kConvCh[0] * 4);
+  if (tc) bytes += Workspace::rounded((size_t)make_pixel_layout(a).d0_w * 4);
   return bytes;
 }
 
@@ -321,6 +338,7 @@ void carve_enc(ibc_handle* h, const ibc_pixel_arch& a, int64_t B, int chunk, boo
   s->wflip = h->ws.take<float>((size_t)9 * kConvCh[3] * kConvCh[2]);
   s->w1pad = h->ws.take<float>((size_t)9 * d.C[0] * kConvCh[0]);
   s->dw1pad = h->ws.take<float>((size_t)9 * d.C[0] * kConvCh[0]);
+  if (tc) s->wr = h->ws.take<float>((size_t)make_pixel_layout(a).d0_w);
 }
 
 int encode_fwd(ibc_pixel_handle* ph, const PixelLayout& L, const void* images, int is_u8,
@@ -331,9 +349,11 @@ int encode_fwd(ibc_pixel_handle* ph, const PixelLayout& L, const void* images, i
   const float* P = ph->params;
   const int CT = a.channels * a.seq_len;
   preprocess_kernel<<<nblocks((int64_t)B * d.H[0] * d.W[0] * d.C[0]), 256, 0, s>>>(
-      images, is_u8, B, a.height, a.width, CT, d.C[0], d.H[0], d.W[0], sv.X0);
+      images, is_u8, B, a.height, a.width, CT, d.C[0], d.H[0], d.W[0], sv.tc ? 1 : 0, sv.X0);
   IBC_LAUNCH_CHECK(h);
   if (sv.tc) {
+    round_copy_kernel<<<nblocks(L.d0_w), 256, 0, s>>>(P, L.d0_w, sv.wr);
+    IBC_LAUNCH_CHECK(h);
     pad_kernel_channels_kernel<<<nblocks(9 * d.C[0] * kConvCh[0]), 256, 0, s>>>(
         P + L.conv_k[0], CT, d.C[0], kConvCh[0], sv.w1pad);
     IBC_LAUNCH_CHECK(h);
@@ -344,9 +364,9 @@ int encode_fwd(ibc_pixel_handle* ph, const PixelLayout& L, const void* images, i
     if (sv.tc) {   // implicit GEMM: the loader gathers the im2col rows from the NHWC input
       GemmP g;     // Y = relu(im2col(in) . K + b)
       g.A = in; g.conv_H = H; g.conv_W = W; g.conv_C = Ci; g.lda = 9 * Ci;
-      g.B = (l == 1) ? sv.w1pad : P + L.conv_k[l - 1]; g.ldb = Co; g.C = sv.Y[l]; g.ldc = Co;
+      g.B = (l == 1) ? sv.w1pad : sv.wr + L.conv_k[l - 1]; g.ldb = Co; g.C = sv.Y[l]; g.ldc = Co;
       g.bias = P + L.conv_b[l - 1]; g.M = (int)(B * H * W); g.N = Co; g.K = 9 * Ci;
-      g.relu_out = 1;
+      g.relu_out = 1; g.a_tf32 = 1; g.b_tf32 = 1;   // X0 / P[l-1] / weights are rounded
       IBC_TRY(gemm_tc(h, g, false, false, s));
     }
     for (int64_t b0 = 0; !sv.tc && b0 < B; b0 += sv.chunk) {
@@ -361,7 +381,7 @@ int encode_fwd(ibc_pixel_handle* ph, const PixelLayout& L, const void* images, i
       IBC_TRY(pgemm(h, g, false, false, s));
     }
     maxpool2_fwd_kernel<<<nblocks((int64_t)B * (H / 2) * (W / 2) * Co), 256, 0, s>>>(
-        sv.Y[l], B, H, W, Co, sv.P[l]);
+        sv.Y[l], B, H, W, Co, (sv.tc && l < 4) ? 1 : 0, sv.P[l]);
     IBC_LAUNCH_CHECK(h);
     in = sv.P[l];
   }
@@ -386,7 +406,7 @@ int encode_bwd(ibc_pixel_handle* ph, const PixelLayout& L, int64_t B, const EncS
   for (int l = 4; l >= 1; --l) {
     const int H = d.H[l], W = d.W[l], Ci = d.C[l - 1], Co = d.C[l];
     maxpool2_relu_bwd_kernel<<<nblocks((int64_t)B * ((H + 1) / 2) * ((W + 1) / 2) * (Co / 4)),
-                               256, 0, s>>>(sv.Y[l], dP, B, H, W, Co, dY);
+                               256, 0, s>>>(sv.Y[l], dP, B, H, W, Co, sv.tc ? 1 : 0, dY);
     IBC_LAUNCH_CHECK(h);
     IBC_TRY(colsum_add(h, dY, Co, (int64_t)B * H * W, Co, grads + L.conv_b[l - 1], s));
     const float* in = (l == 1) ? sv.X0 : sv.P[l - 1];
@@ -396,6 +416,7 @@ int encode_bwd(ibc_pixel_handle* ph, const PixelLayout& L, int64_t B, const EncS
       gk.A = in; gk.conv_H = H; gk.conv_W = W; gk.conv_C = Ci; gk.lda = 9 * Ci;
       gk.B = dY; gk.ldb = Co; gk.C = grads + L.conv_k[l - 1]; gk.ldc = Co;
       gk.M = 9 * Ci; gk.N = Co; gk.K = (int)(B * H * W); gk.atomic = 1;
+      gk.a_tf32 = 1; gk.b_tf32 = 1;
       if (l == 1 && Ci != CT) {
         gk.C = sv.dw1pad;
         IBC_CUDA(h, cudaMemsetAsync(sv.dw1pad, 0, (size_t)9 * Ci * Co * 4, s));
@@ -413,7 +434,7 @@ int encode_bwd(ibc_pixel_handle* ph, const PixelLayout& L, int64_t B, const EncS
         GemmP gd;   // dIn = im2col(dY) . Kflip
         gd.A = dY; gd.conv_H = H; gd.conv_W = W; gd.conv_C = Co; gd.lda = 9 * Co;
         gd.B = sv.wflip; gd.ldb = Ci; gd.C = dIn; gd.ldc = Ci;
-        gd.M = (int)(B * H * W); gd.N = Ci; gd.K = 9 * Co;
+        gd.M = (int)(B * H * W); gd.N = Ci; gd.K = 9 * Co; gd.a_tf32 = 1; gd.b_tf32 = 1;
         IBC_TRY(gemm_tc(h, gd, false, false, s));
       }
     }
@@ -447,6 +468,8 @@ struct ValSave {
   float* X = nullptr;      // [(nblk+1), R, Wv]
   float* Y0 = nullptr;     // [nblk, R, Wq]
   float* Y1 = nullptr;     // [nblk, R, Wq]
+  float* wr = nullptr;     // [param count] tf32-rounded copy of the value parameters at the flat
+                           // vector's offsets (filled by value_fwd on the tf32 path)
   int64_t R = 0;
 };
 
@@ -454,7 +477,8 @@ size_t val_bytes(const PixelLayout& L, int64_t B, int64_t R) {
   const int nb = L.nblk > 0 ? L.nblk : 1;
   return Workspace::rounded((size_t)B * L.Wv * 4) +
          Workspace::rounded((size_t)(L.nblk + 1) * R * L.Wv * 4) +
-         2 * Workspace::rounded((size_t)nb * R * L.Wq * 4);
+         2 * Workspace::rounded((size_t)nb * R * L.Wq * 4) +
+         Workspace::rounded((size_t)L.count * 4);
 }
 
 void carve_val(ibc_handle* h, const PixelLayout& L, int64_t B, int64_t R, ValSave* v) {
@@ -464,6 +488,7 @@ void carve_val(ibc_handle* h, const PixelLayout& L, int64_t B, int64_t R, ValSav
   v->X = h->ws.take<float>((size_t)(L.nblk + 1) * R * L.Wv);
   v->Y0 = h->ws.take<float>((size_t)nb * R * L.Wq);
   v->Y1 = h->ws.take<float>((size_t)nb * R * L.Wq);
+  v->wr = h->ws.take<float>((size_t)L.count);
 }
 
 // E[r] for enc [B, 256] (un-tiled) and act [B*n, A]   (pixel_ebm.py:113-125)
@@ -473,6 +498,14 @@ int value_fwd(ibc_pixel_handle* ph, const PixelLayout& L, const float* enc, int6
   const float* P = ph->params;
   const int Wv = L.Wv, Wq = L.Wq;
   const int64_t R = B * n;
+  const bool tc = h->precision == IBC_PRECISION_TF32;
+  const float* PB = P;          // B operands of the block products
+  if (tc) {
+    round_copy_kernel<<<nblocks(L.count - L.d0_w), 256, 0, s>>>(P + L.d0_w, L.count - L.d0_w,
+                                                                 v.wr + L.d0_w);
+    IBC_LAUNCH_CHECK(h);
+    PB = v.wr;
+  }
   {  // encp = enc . W0[:256] + b0
     GemmP g;
     g.A = enc; g.lda = kEnc; g.B = P + L.d0_w; g.ldb = Wv; g.C = v.encp; g.ldc = Wv;
@@ -492,15 +525,15 @@ int value_fwd(ibc_pixel_handle* ph, const PixelLayout& L, const float* enc, int6
     float* y0 = v.Y0 + (int64_t)j * R * Wq;
     float* y1 = v.Y1 + (int64_t)j * R * Wq;
     GemmP g0;  // y0 = relu(x) . D0 + b
-    g0.A = x; g0.lda = Wv; g0.aop = AOP_RELU; g0.B = P + L.b_d0w(j); g0.ldb = Wq;
+    g0.A = x; g0.lda = Wv; g0.aop = AOP_RELU; g0.B = PB + L.b_d0w(j); g0.ldb = Wq; g0.b_tf32 = tc;
     g0.C = y0; g0.ldc = Wq; g0.bias = P + L.b_d0b(j); g0.M = (int)R; g0.N = Wq; g0.K = Wv;
     IBC_TRY(pgemm(h, g0, false, false, s));
     GemmP g1;  // y1 = relu(y0) . D1 + b
-    g1.A = y0; g1.lda = Wq; g1.aop = AOP_RELU; g1.B = P + L.b_d1w(j); g1.ldb = Wq;
+    g1.A = y0; g1.lda = Wq; g1.aop = AOP_RELU; g1.B = PB + L.b_d1w(j); g1.ldb = Wq; g1.b_tf32 = tc;
     g1.C = y1; g1.ldc = Wq; g1.bias = P + L.b_d1b(j); g1.M = (int)R; g1.N = Wq; g1.K = Wq;
     IBC_TRY(pgemm(h, g1, false, false, s));
     GemmP g2;  // x' = x + relu(y1) . D2 + b
-    g2.A = y1; g2.lda = Wq; g2.aop = AOP_RELU; g2.B = P + L.b_d2w(j); g2.ldb = Wv;
+    g2.A = y1; g2.lda = Wq; g2.aop = AOP_RELU; g2.B = PB + L.b_d2w(j); g2.ldb = Wv; g2.b_tf32 = tc;
     g2.C = xn; g2.ldc = Wv; g2.bias = P + L.b_d2b(j); g2.res = x; g2.ldres = Wv;
     g2.M = (int)R; g2.N = Wv; g2.K = Wq;
     IBC_TRY(pgemm(h, g2, false, false, s));
@@ -530,6 +563,8 @@ int value_bwd(ibc_pixel_handle* ph, const PixelLayout& L, const float* enc, int6
   float* g1b = h->ws.take<float>((size_t)R * Wq);
   float* g0b = h->ws.take<float>((size_t)R * Wq);
   float* gsum = h->ws.take<float>((size_t)B * Wv);
+  const bool tc = h->precision == IBC_PRECISION_TF32;
+  const float* PB = tc ? v.wr : P;   // rounded by value_fwd earlier in the same call
   const float* xl = v.X + (int64_t)L.nblk * R * Wv;
   IBC_TRY(wcolsum_add(h, xl, Wv, dE, R, Wv, grads + L.d1_w, s));
   IBC_TRY(sum_add(h, dE, R, grads + L.d1_b, s));
@@ -543,19 +578,22 @@ int value_bwd(ibc_pixel_handle* ph, const PixelLayout& L, const float* enc, int6
     IBC_TRY(dwg(h, y1, Wq, AOP_RELU, G, Wv, R, Wq, Wv, grads + L.b_d2w(j), s));
     IBC_TRY(colsum_add(h, G, Wv, R, Wv, grads + L.b_d2b(j), s));
     GemmP a1;  // g1 = (G . D2^T) (.) (y1 > 0)
-    a1.A = G; a1.lda = Wv; a1.B = P + L.b_d2w(j); a1.ldb = Wv; a1.C = g1b; a1.ldc = Wq;
+    a1.A = G; a1.lda = Wv; a1.B = PB + L.b_d2w(j); a1.ldb = Wv; a1.C = g1b; a1.ldc = Wq;
+    a1.b_tf32 = tc;
     a1.gateC = y1; a1.ldgc = Wq; a1.M = (int)R; a1.N = Wq; a1.K = Wv;
     IBC_TRY(pgemm(h, a1, false, true, s));
     IBC_TRY(dwg(h, y0, Wq, AOP_RELU, g1b, Wq, R, Wq, Wq, grads + L.b_d1w(j), s));
     IBC_TRY(colsum_add(h, g1b, Wq, R, Wq, grads + L.b_d1b(j), s));
     GemmP a0;  // g0 = (g1 . D1^T) (.) (y0 > 0)
-    a0.A = g1b; a0.lda = Wq; a0.B = P + L.b_d1w(j); a0.ldb = Wq; a0.C = g0b; a0.ldc = Wq;
+    a0.A = g1b; a0.lda = Wq; a0.B = PB + L.b_d1w(j); a0.ldb = Wq; a0.C = g0b; a0.ldc = Wq;
+    a0.b_tf32 = tc;
     a0.gateC = y0; a0.ldgc = Wq; a0.M = (int)R; a0.N = Wq; a0.K = Wq;
     IBC_TRY(pgemm(h, a0, false, true, s));
     IBC_TRY(dwg(h, x, Wv, AOP_RELU, g0b, Wq, R, Wv, Wq, grads + L.b_d0w(j), s));
     IBC_TRY(colsum_add(h, g0b, Wq, R, Wq, grads + L.b_d0b(j), s));
     GemmP ax;  // G' = G + (g0 . D0^T) (.) (x > 0)
-    ax.A = g0b; ax.lda = Wq; ax.B = P + L.b_d0w(j); ax.ldb = Wq; ax.C = Gn; ax.ldc = Wv;
+    ax.A = g0b; ax.lda = Wq; ax.B = PB + L.b_d0w(j); ax.ldb = Wq; ax.C = Gn; ax.ldc = Wv;
+    ax.b_tf32 = tc;
     ax.gateC = x; ax.ldgc = Wv; ax.res = G; ax.ldres = Wv; ax.M = (int)R; ax.N = Wv; ax.K = Wq;
     IBC_TRY(pgemm(h, ax, false, true, s));
     G = Gn;
