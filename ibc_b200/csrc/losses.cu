@@ -174,11 +174,11 @@ int adam_step(ibc_handle* h, float* p, const float* g, float* m, float* v, int64
 // dW (+)= f(X)^T . Y with split-K over the R rows.
 static int dw_gemm(ibc_handle* h, const float* X, int64_t ldx, int aop, const float* gate,
                    const float* Y, int64_t ldy, int64_t R, int Kin, int Nout, float* dW,
-                   cudaStream_t s) {
+                   cudaStream_t s, bool tc = true) {
   GemmP g;
   g.A = X; g.lda = ldx; g.aop = aop; g.gateA = gate; g.B = Y; g.ldb = ldy;
   g.C = dW; g.ldc = Nout; g.M = Kin; g.N = Nout; g.K = (int)R;
-  g.k_chunk = 1024; g.atomic = 1;
+  g.k_chunk = 1024; g.atomic = 1; g.tc = tc ? 1 : 0;
   return gemm(h, g, true, false, s);
 }
 
@@ -237,6 +237,7 @@ int train_grads_fp32(ibc_handle* h, const float* obs, int64_t B, const float* ac
       GemmP g;
       g.A = cot; g.lda = A; g.B = WpA; g.ldb = W; g.C = Ta; g.ldc = W;
       g.M = (int)R; g.N = W; g.K = A;
+      g.tc = 1;
       IBC_TRY(gemm(h, g, false, false, s));
     }
     // dWp[O:] += cot^T . G0
@@ -249,6 +250,7 @@ int train_grads_fp32(ibc_handle* h, const float* obs, int64_t B, const float* ac
       g1.A = Tcur; g1.lda = W; g1.aop = AOP_GATE; g1.gateA = f.Hj(j, W);
       g1.B = P + L.w1(j); g1.ldb = W; g1.C = Sj; g1.ldc = W;
       g1.gateC = f.Vj(j, W); g1.ldgc = W; g1.M = (int)R; g1.N = W; g1.K = W;
+      g1.tc = 1;
       IBC_TRY(gemm(h, g1, false, false, s));
       // dW1 += (T (.) mh)^T . U_j ;  dW2 += S^T . G_{j+1}
       IBC_TRY(dw_gemm(h, Tcur, W, AOP_GATE, f.Hj(j, W), rv.Uj(j, W), W, R, W, W,
@@ -257,6 +259,7 @@ int train_grads_fp32(ibc_handle* h, const float* obs, int64_t B, const float* ac
       GemmP g2;  // T' = T + S . W2
       g2.A = Sj; g2.lda = W; g2.B = P + L.w2(j); g2.ldb = W; g2.C = Tnext; g2.ldc = W;
       g2.res = Tcur; g2.ldres = W; g2.M = (int)R; g2.N = W; g2.K = W;
+      g2.tc = 1;
       IBC_TRY(gemm(h, g2, false, false, s));
       Tcur = Tnext;
     }
@@ -282,6 +285,7 @@ int train_grads_fp32(ibc_handle* h, const float* obs, int64_t B, const float* ac
     GemmP g1;  // gu = (g . W2^T) (.) (V > 0)
     g1.A = Gcur; g1.lda = W; g1.B = P + L.w2(j); g1.ldb = W; g1.C = GU; g1.ldc = W;
     g1.gateC = f.Vj(j, W); g1.ldgc = W; g1.M = (int)R; g1.N = W; g1.K = W;
+    g1.tc = 1;
     IBC_TRY(gemm(h, g1, false, true, s));
     IBC_TRY(dw_gemm(h, f.Hj(j, W), W, AOP_RELU, nullptr, GU, W, R, W, W, grads + L.w1(j), s));
     IBC_TRY(colsum_add(h, GU, W, R, W, grads + L.b1(j), s));
@@ -289,6 +293,7 @@ int train_grads_fp32(ibc_handle* h, const float* obs, int64_t B, const float* ac
     g2.A = GU; g2.lda = W; g2.B = P + L.w1(j); g2.ldb = W; g2.C = Gnext; g2.ldc = W;
     g2.gateC = f.Hj(j, W); g2.ldgc = W; g2.res = Gcur; g2.ldres = W;
     g2.M = (int)R; g2.N = W; g2.K = W;
+    g2.tc = 1;
     IBC_TRY(gemm(h, g2, false, true, s));
     Gcur = Gnext;
   }
@@ -296,7 +301,7 @@ int train_grads_fp32(ibc_handle* h, const float* obs, int64_t B, const float* ac
   IBC_TRY(dw_gemm(h, actions, A, AOP_ID, nullptr, Gcur, W, R, A, W,
                   grads + L.wp + (int64_t)L.O * W, s));
   IBC_TRY(groupsum(h, Gcur, B, n1, W, gsum, s));
-  IBC_TRY(dw_gemm(h, obs, L.O, AOP_ID, nullptr, gsum, W, B, L.O, W, grads + L.wp, s));
+  IBC_TRY(dw_gemm(h, obs, L.O, AOP_ID, nullptr, gsum, W, B, L.O, W, grads + L.wp, s, false));
   IBC_TRY(colsum_add(h, gsum, W, B, W, grads + L.bp, s));
   return IBC_OK;
 }

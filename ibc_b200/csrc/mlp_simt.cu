@@ -1,4 +1,7 @@
-// fp32 dense-stack passes (per-layer GEMMs with fused prologue/epilogue).
+// Per-layer dense-stack passes (GEMMs with fused prologue/epilogue): fp32 FMA kernels on
+// IBC_PRECISION_FP32 handles; on IBC_PRECISION_TF32 handles the same products run on the
+// general tcgen05 tf32 GEMM (gemm_tc.cu) -- this is the training path of the widths and
+// options the layer-fused kernels do not cover (gradient penalty, W = 256 / 512 / 2048).
 //
 //   forward   networks/mlp_ebm.py:72-96, networks/layers/resnet.py:135-153
 //   reverse   dE/dact of mcmc.gradient_wrt_act (ibc/agents/mcmc.py:161-191)
@@ -47,7 +50,7 @@ int mlp_forward_fp32(ibc_handle* h, const float* obs, int64_t B, const float* ac
     GemmP g;
     g.A = obs; g.lda = L.O; g.B = P + L.wp; g.ldb = W; g.C = hp; g.ldc = W;
     g.bias = P + L.bp; g.M = (int)B; g.N = W; g.K = L.O;
-    IBC_TRY(gemm(h, g, false, false, s));
+    IBC_TRY(gemm(h, g, false, false, s));   // always fp32 (once per observation)
   }
   float* Hcur = save ? save->Hj(0, W) : Ha;
   {  // H0 = act . Wp[O:] + hp[row / n]
@@ -55,6 +58,7 @@ int mlp_forward_fp32(ibc_handle* h, const float* obs, int64_t B, const float* ac
     g.A = act; g.lda = L.A; g.B = P + L.wp + (int64_t)L.O * W; g.ldb = W;
     g.C = Hcur; g.ldc = W; g.rowbias = hp; g.ldrb = W; g.rows_per_group = n;
     g.M = (int)R; g.N = W; g.K = L.A;
+    g.tc = 1;
     IBC_TRY(gemm(h, g, false, false, s));
   }
   for (int j = 0; j < L.nb; ++j) {
@@ -63,11 +67,13 @@ int mlp_forward_fp32(ibc_handle* h, const float* obs, int64_t B, const float* ac
     GemmP g1;  // V = relu(H) . W1 + b1
     g1.A = Hcur; g1.lda = W; g1.aop = AOP_RELU; g1.B = P + L.w1(j); g1.ldb = W;
     g1.C = Vj; g1.ldc = W; g1.bias = P + L.b1(j); g1.M = (int)R; g1.N = W; g1.K = W;
+    g1.tc = 1;
     IBC_TRY(gemm(h, g1, false, false, s));
     GemmP g2;  // H' = H + relu(V) . W2 + b2
     g2.A = Vj; g2.lda = W; g2.aop = AOP_RELU; g2.B = P + L.w2(j); g2.ldb = W;
     g2.C = Hnext; g2.ldc = W; g2.bias = P + L.b2(j); g2.res = Hcur; g2.ldres = W;
     g2.M = (int)R; g2.N = W; g2.K = W;
+    g2.tc = 1;
     IBC_TRY(gemm(h, g2, false, false, s));
     Hcur = Hnext;
   }
@@ -95,11 +101,13 @@ int mlp_reverse_fp32(ibc_handle* h, const FwdSave& f, const float* row_scale, fl
     GemmP g1;  // U = (G . W2^T) (.) (V > 0)
     g1.A = Gcur; g1.lda = W; g1.B = P + L.w2(j); g1.ldb = W; g1.C = Uj; g1.ldc = W;
     g1.gateC = f.Vj(j, W); g1.ldgc = W; g1.M = (int)R; g1.N = W; g1.K = W;
+    g1.tc = 1;
     IBC_TRY(gemm(h, g1, false, true, s));
     GemmP g2;  // G' = G + (U . W1^T) (.) (H > 0)
     g2.A = Uj; g2.lda = W; g2.B = P + L.w1(j); g2.ldb = W; g2.C = Gnext; g2.ldc = W;
     g2.gateC = f.Hj(j, W); g2.ldgc = W; g2.res = Gcur; g2.ldres = W;
     g2.M = (int)R; g2.N = W; g2.K = W;
+    g2.tc = 1;
     IBC_TRY(gemm(h, g2, false, true, s));
     Gcur = Gnext;
   }
@@ -107,6 +115,7 @@ int mlp_reverse_fp32(ibc_handle* h, const FwdSave& f, const float* row_scale, fl
     GemmP g;
     g.A = Gcur; g.lda = W; g.B = P + L.wp + (int64_t)L.O * W; g.ldb = W;
     g.C = dEda; g.ldc = L.A; g.M = (int)R; g.N = L.A; g.K = W;
+    g.tc = 1;
     IBC_TRY(gemm(h, g, false, true, s));
   }
   return IBC_OK;
