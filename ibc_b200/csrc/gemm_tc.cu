@@ -267,13 +267,64 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_kernel(GemmP p, int* stat
       }
     }
     const uint32_t ring_addr = smem_u32(ring);
+    // Fast path of whole K-slices (every slice but a ragged last one): per piece, the
+    // source of slice 0, the shared-memory offset and whether the piece is inside the
+    // matrix are fixed for the thread, so a slice costs one address add and one copy
+    // per piece (the generic path re-derives rows, limits and alignment: ~30
+    // instructions per piece, which made the loaders issue-bound; ncu r1).
+    const float* pa_src[NA]; uint32_t pa_dst[NA]; uint32_t pa_ok = 0, pa_fast = 1;
+    const float* pb_src[NB]; uint32_t pb_dst[NB]; uint32_t pb_ok = 0, pb_fast = 1;
+    const int64_t a_step = AKC ? (int64_t)kBK : (int64_t)kBK * p.lda;
+    const int64_t b_step = BKC ? (int64_t)kBK : (int64_t)kBK * p.ldb;
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+      int r, k;
+      pa_dst[j] = piece<AKC, kBM>(j * kLoaderThreads + tid, r, k);
+      const bool in = (m0 + r) < p.M;
+      if (!AKC && in && m0 + r + 4 > p.M) pa_fast = 0;       // ragged 16-byte piece
+      if (in) pa_ok |= 1u << j;
+      pa_src[j] = !in ? p.A
+                      : (AKC ? p.A + (int64_t)(m0 + r) * p.lda + kbeg + k
+                             : p.A + (int64_t)(kbeg + k) * p.lda + m0 + r);
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      int r, k;
+      pb_dst[j] = C::kABytes + piece<BKC, BN>(j * kLoaderThreads + tid, r, k);
+      const bool in = (n0 + r) < p.N;
+      if (!BKC && in && n0 + r + 4 > p.N) pb_fast = 0;
+      if (in) pb_ok |= 1u << j;
+      pb_src[j] = !in ? p.B
+                      : (BKC ? p.B + (int64_t)(n0 + r) * p.ldb + kbeg + k
+                             : p.B + (int64_t)(kbeg + k) * p.ldb + n0 + r);
+    }
+    if (!avec || CONV) pa_fast = 0;
+    if (!bvec) pb_fast = 0;
     // Stage ks on its way: asynchronous copies straight into the operand images.
     auto issue = [&](int ks) {
       const int k0 = kbeg + ks * kBK;
       const uint32_t sa = ring_addr + (uint32_t)((ks % S) * C::kStageBytes);
       const uint32_t sb = sa + C::kABytes;
+      const bool whole = k0 + kBK <= kend;
+      if (whole && pa_fast) {
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+          const bool in = (pa_ok >> j) & 1u;
+          cp_async16<false>(sa + pa_dst[j], in ? pa_src[j] + (int64_t)ks * a_step : p.A,
+                            in ? 16u : 0u);
+        }
+      }
+      if (whole && pb_fast) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const bool in = (pb_ok >> j) & 1u;
+          cp_async16<false>(sa + pb_dst[j], in ? pb_src[j] + (int64_t)ks * b_step : p.B,
+                            in ? 16u : 0u);
+        }
+      }
 #pragma unroll
       for (int j = 0; j < NA; ++j) {
+        if (whole && pa_fast) break;
         int r, k;
         const uint32_t dst = sa + piece<AKC, kBM>(j * kLoaderThreads + tid, r, k);
         if (CONV) {
@@ -299,6 +350,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_kernel(GemmP p, int* stat
       }
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
+        if (whole && pb_fast) break;
         int r, k;
         const uint32_t dst = sb + piece<BKC, BN>(j * kLoaderThreads + tid, r, k);
         issue4<BKC>(dst, p.B, p.ldb, n0 + r, k0 + k, p.N, kend, bvec);
@@ -307,33 +359,57 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_kernel(GemmP p, int* stat
     // Stage ks has landed: each thread applies the prologue to the pieces it copied
     // itself (ReLU / gate on A, round-to-nearest tf32 on both), in place.
     const bool fin_a = !(p.a_tf32 && p.aop == AOP_ID), fin_b = !p.b_tf32;
+    // Round-to-nearest tf32 is one integer add per element (the MMA truncates the low 13
+    // bits), ReLU + rounding one VIADDMNMX (umma_pack.cuh).
     auto finish = [&](int ks) {
-      const int k0 = kbeg + ks * kBK;
       const uint32_t sa = ring_addr + (uint32_t)((ks % S) * C::kStageBytes);
-      const uint32_t sb = sa + C::kABytes;
+      if (fin_a) {
+        if (p.aop == AOP_GATE) {
+          const int k0 = kbeg + ks * kBK;
 #pragma unroll
-      for (int j = 0; j < NA; ++j) {
-        if (!fin_a) break;
-        int r, k;
-        const uint32_t dst = sa + piece<AKC, kBM>(j * kLoaderThreads + tid, r, k);
-        float4 v = ld_shared16(dst);
-        if (p.aop == AOP_RELU) {
-          v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-        } else if (!CONV && p.aop == AOP_GATE) {
-          const float4 g = fetch4<AKC>(p.gateA, p.lda, m0 + r, k0 + k, p.M, kend, avec);
-          if (!(g.x > 0.f)) v.x = 0.f;
-          if (!(g.y > 0.f)) v.y = 0.f;
-          if (!(g.z > 0.f)) v.z = 0.f;
-          if (!(g.w > 0.f)) v.w = 0.f;
+          for (int j = 0; j < NA; ++j) {
+            int r, k;
+            piece<AKC, kBM>(j * kLoaderThreads + tid, r, k);
+            float4 v = ld_shared16(sa + pa_dst[j]);
+            const float4 g = fetch4<AKC>(p.gateA, p.lda, m0 + r, k0 + k, p.M, kend, avec);
+            if (!(g.x > 0.f)) v.x = 0.f;
+            if (!(g.y > 0.f)) v.y = 0.f;
+            if (!(g.z > 0.f)) v.z = 0.f;
+            if (!(g.w > 0.f)) v.w = 0.f;
+            st_shared16(sa + pa_dst[j], tf32_rn4(v));
+          }
+        } else if (p.aop == AOP_RELU) {
+#pragma unroll
+          for (int j = 0; j < NA; ++j) {
+            const float4 v = ld_shared16(sa + pa_dst[j]);
+            st_shared16(sa + pa_dst[j],
+                        make_float4(__uint_as_float(relu_tf32_bits(__float_as_uint(v.x))),
+                                    __uint_as_float(relu_tf32_bits(__float_as_uint(v.y))),
+                                    __uint_as_float(relu_tf32_bits(__float_as_uint(v.z))),
+                                    __uint_as_float(relu_tf32_bits(__float_as_uint(v.w)))));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NA; ++j) {
+            const float4 v = ld_shared16(sa + pa_dst[j]);
+            st_shared16(sa + pa_dst[j],
+                        make_float4(__uint_as_float(tf32_rn_bits(__float_as_uint(v.x))),
+                                    __uint_as_float(tf32_rn_bits(__float_as_uint(v.y))),
+                                    __uint_as_float(tf32_rn_bits(__float_as_uint(v.z))),
+                                    __uint_as_float(tf32_rn_bits(__float_as_uint(v.w)))));
+          }
         }
-        st_shared16(dst, tf32_rn4(v));
       }
+      if (fin_b) {
 #pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        if (!fin_b) break;
-        int r, k;
-        const uint32_t dst = sb + piece<BKC, BN>(j * kLoaderThreads + tid, r, k);
-        st_shared16(dst, tf32_rn4(ld_shared16(dst)));
+        for (int j = 0; j < NB; ++j) {
+          const float4 v = ld_shared16(sa + pb_dst[j]);
+          st_shared16(sa + pb_dst[j],
+                      make_float4(__uint_as_float(tf32_rn_bits(__float_as_uint(v.x))),
+                                  __uint_as_float(tf32_rn_bits(__float_as_uint(v.y))),
+                                  __uint_as_float(tf32_rn_bits(__float_as_uint(v.z))),
+                                  __uint_as_float(tf32_rn_bits(__float_as_uint(v.w)))));
+        }
       }
     };
     for (int ks = 0; ks < S - 1; ++ks) {
