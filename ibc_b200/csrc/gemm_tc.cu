@@ -37,22 +37,25 @@ using namespace umma;
 namespace {
 
 constexpr int kBM = 128, kBK = 32;
-constexpr int kLoaderWarps = 8;
+constexpr int kLoaderWarps = 16;
 constexpr int kLoaderThreads = kLoaderWarps * 32;
-constexpr int kThreads = kLoaderThreads + 32;
+constexpr int kIssuerWarp = kLoaderWarps;           // one MMA-issuer warp
+constexpr int kFirstEpiWarp = kLoaderWarps + 1;     // eight epilogue warps (two per TMEM lane quarter)
+constexpr int kEpiWarps = 8;
+constexpr int kEpiLd = 36;                          // floats per row of an epilogue staging tile
+constexpr int kThreads = (kLoaderWarps + 1 + kEpiWarps) * 32;
 constexpr uint32_t kMnLbo = (kBK / 4) * 512u;   // between 32-element MN atoms of a stage
 constexpr uint32_t kMnSbo = 512u;               // between 4-row K atoms
 
 template <int BN>
 struct TcCfg {
-  static constexpr int kStages = BN <= 64 ? 4 : 3;
+  static constexpr int kStages = BN > 64 ? 5 : 6;   // 32 KB stages at BN = 128: 160 KB + 36 KB epilogue staging
   static constexpr int kABytes = kBM * kBK * 4;
   static constexpr int kBBytes = BN * kBK * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kRing = kStages * kStageBytes;
-  static constexpr int kStageFloats = kLoaderWarps * 32 * 33;   // epilogue transposing stage
-  static_assert(kStageFloats * 4 <= kRing, "epilogue stage must fit in the ring");
-  static constexpr size_t kSmem = (size_t)kRing + 1024 + 128;
+  static constexpr int kEpiStage = kEpiWarps * 32 * kEpiLd * 4;   // epilogue transposing stage
+  static constexpr size_t kSmem = (size_t)kRing + kEpiStage + 1024 + 256;
 };
 
 // ---- Ampere-style asynchronous 16-byte copies (LDGSTS): global -> shared without
@@ -213,35 +216,57 @@ __device__ __forceinline__ void conv_issue4(uint32_t dst, const GemmP& p, const 
     cp_async16<true>(dst, p.A + ((int64_t)s.pr + (ky - 1) * p.conv_W + (kx - 1)) * p.conv_C + s.c, 16u);
 }
 
+// One output block of the persistent schedule.
+struct TileCoord {
+  int m0, n0, kbeg, kend, nks;
+  bool first;        // first K split: bias / row bias / residual are added here
+};
+template <int BN>
+__device__ __forceinline__ TileCoord tile_coord(const GemmP& p, int t, int tm, int tn) {
+  TileCoord c;
+  const int per = tm * tn;
+  const int split = t / per, rem = t - split * per;
+  const int nt = rem / tm, mt = rem - nt * tm;      // consecutive blocks share the B tile
+  const int kc = p.k_chunk > 0 ? p.k_chunk : p.K;
+  c.m0 = mt * kBM; c.n0 = nt * BN;
+  c.kbeg = split * kc; c.kend = min(p.K, c.kbeg + kc);
+  c.nks = (c.kend - c.kbeg + kBK - 1) / kBK;
+  c.first = split == 0;
+  return c;
+}
+
+// Persistent: CTA b walks blocks b, b + grid, ... with three sets of warps running ahead
+// of one another -- loaders (K-slices of the next blocks are already in flight while a
+// block finishes), the MMA issuer (two accumulators in tensor memory) and the epilogue.
 template <bool TA, bool TB, int BN, bool CONV>
-__global__ void __launch_bounds__(kThreads, 2) gemm_tc_kernel(GemmP p, int* status) {
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(GemmP p, int* status, int tm, int tn,
+                                                              int total) {
   using C = TcCfg<BN>;
   constexpr int S = C::kStages;
   constexpr bool AKC = !TA, BKC = TB;
-  constexpr int NA = kBM / 32, NB = BN / 32;     // 16-byte pieces per loader thread and stage
+  // 16-byte pieces per loader thread and stage (B: the last threads idle when BN = 32)
+  constexpr int NA = kBM * 8 / kLoaderThreads, NB = (BN * 8 + kLoaderThreads - 1) / kLoaderThreads;
+  constexpr bool kBAll = (BN * 8) % kLoaderThreads == 0;   // every thread has B pieces
   extern __shared__ unsigned char smem_raw[];
   unsigned char* ring = reinterpret_cast<unsigned char*>(
       ((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + C::kRing);
+  float* epi_stage = reinterpret_cast<float*>(ring + C::kRing);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + C::kRing + C::kEpiStage);
   uint64_t* empty = full + S;
-  uint64_t* d_ready = empty + S;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_ready + 1);
+  uint64_t* acc_full = empty + S;        // [2] issuer -> epilogue
+  uint64_t* acc_empty = acc_full + 2;    // [2] epilogue -> issuer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   __shared__ int s_abort;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
-  const int kc = p.k_chunk > 0 ? p.k_chunk : p.K;
-  const int kbeg = blockIdx.z * kc;
-  const int kend = min(p.K, kbeg + kc);
-  const int nks = (kend - kbeg + kBK - 1) / kBK;
 
   if (tid == 0) {
     s_abort = 0;
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], kLoaderWarps); mbar_init(&empty[s], 1); }
-    mbar_init(d_ready, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
     fence_mbar_init();
   }
-  if (warp == kLoaderWarps) tmem_alloc(tmem_slot, BN);
+  if (warp == kIssuerWarp) tmem_alloc(tmem_slot, 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -253,59 +278,67 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_kernel(GemmP p, int* stat
     const bool avec = ((p.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) &&
                       (p.aop != AOP_GATE || (reinterpret_cast<uintptr_t>(p.gateA) & 15) == 0);
     const bool bvec = ((p.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0);
-    // implicit convolution: per-piece walking state (columns advance in the forward /
-    // data-gradient form, pixel rows in the weight-gradient form)
     const bool cvec = CONV && ((p.conv_C & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
-    ConvPiece cs[CONV ? NA : 1];
-    if (CONV && cvec) {
-#pragma unroll
-      for (int j = 0; j < NA; ++j) {
-        int r, k;
-        piece<AKC, kBM>(j * kLoaderThreads + tid, r, k);
-        if (AKC) { cs[j] = conv_piece(p, m0 + r, kbeg + k); cs[j].ok = (m0 + r) < p.M; }
-        else { cs[j] = conv_piece(p, kbeg + k, m0 + r); cs[j].ok = (m0 + r) < p.M; }
-      }
-    }
     const uint32_t ring_addr = smem_u32(ring);
-    // Fast path of whole K-slices (every slice but a ragged last one): per piece, the
-    // source of slice 0, the shared-memory offset and whether the piece is inside the
-    // matrix are fixed for the thread, so a slice costs one address add and one copy
-    // per piece (the generic path re-derives rows, limits and alignment: ~30
-    // instructions per piece, which made the loaders issue-bound; ncu r1).
-    const float* pa_src[NA]; uint32_t pa_dst[NA]; uint32_t pa_ok = 0, pa_fast = 1;
-    const float* pb_src[NB]; uint32_t pb_dst[NB]; uint32_t pb_ok = 0, pb_fast = 1;
     const int64_t a_step = AKC ? (int64_t)kBK : (int64_t)kBK * p.lda;
     const int64_t b_step = BKC ? (int64_t)kBK : (int64_t)kBK * p.ldb;
+    // fixed per thread: where its pieces sit in a stage
+    uint32_t pa_dst[NA], pb_dst[NB];
 #pragma unroll
-    for (int j = 0; j < NA; ++j) {
-      int r, k;
-      pa_dst[j] = piece<AKC, kBM>(j * kLoaderThreads + tid, r, k);
-      const bool in = (m0 + r) < p.M;
-      if (!AKC && in && m0 + r + 4 > p.M) pa_fast = 0;       // ragged 16-byte piece
-      if (in) pa_ok |= 1u << j;
-      pa_src[j] = !in ? p.A
-                      : (AKC ? p.A + (int64_t)(m0 + r) * p.lda + kbeg + k
-                             : p.A + (int64_t)(kbeg + k) * p.lda + m0 + r);
-    }
+    for (int j = 0; j < NA; ++j) { int r, k; pa_dst[j] = piece<AKC, kBM>(j * kLoaderThreads + tid, r, k); }
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
       int r, k;
       pb_dst[j] = C::kABytes + piece<BKC, BN>(j * kLoaderThreads + tid, r, k);
-      const bool in = (n0 + r) < p.N;
-      if (!BKC && in && n0 + r + 4 > p.N) pb_fast = 0;
-      if (in) pb_ok |= 1u << j;
-      pb_src[j] = !in ? p.B
-                      : (BKC ? p.B + (int64_t)(n0 + r) * p.ldb + kbeg + k
-                             : p.B + (int64_t)(kbeg + k) * p.ldb + n0 + r);
     }
-    if (!avec || CONV) pa_fast = 0;
-    if (!bvec) pb_fast = 0;
-    // Stage ks on its way: asynchronous copies straight into the operand images.
-    auto issue = [&](int ks) {
-      const int k0 = kbeg + ks * kBK;
-      const uint32_t sa = ring_addr + (uint32_t)((ks % S) * C::kStageBytes);
-      const uint32_t sb = sa + C::kABytes;
-      const bool whole = k0 + kBK <= kend;
+    const bool has_b = kBAll || tid < BN * 8;      // (NB == 1 whenever some threads have none)
+    // Per block (issue side).  Fast path of whole K-slices: per piece, the source of slice
+    // 0 and whether the piece is inside the matrix, so a slice costs one address add and
+    // one copy per piece (the generic path re-derives rows, limits and alignment: ~30
+    // instructions per piece, which made the loaders issue-bound; ncu r1).  Implicit
+    // convolution: per-piece walking state (columns advance in the forward / data-gradient
+    // form, pixel rows in the weight-gradient form).
+    const float* pa_src[NA]; uint32_t pa_ok = 0, pa_fast = 0;
+    const float* pb_src[NB]; uint32_t pb_ok = 0, pb_fast = 0;
+    ConvPiece cs[CONV ? NA : 1];
+    auto setup = [&](const TileCoord& c) {
+      pa_ok = 0; pb_ok = 0; pa_fast = (avec && !CONV) ? 1u : 0u; pb_fast = bvec ? 1u : 0u;
+#pragma unroll
+      for (int j = 0; j < NA; ++j) {
+        int r, k;
+        piece<AKC, kBM>(j * kLoaderThreads + tid, r, k);
+        const bool in = (c.m0 + r) < p.M;
+        if (!AKC && in && c.m0 + r + 4 > p.M) pa_fast = 0;       // ragged 16-byte piece
+        if (in) pa_ok |= 1u << j;
+        if (CONV) {
+          if (cvec) {
+            cs[j] = AKC ? conv_piece(p, c.m0 + r, c.kbeg + k) : conv_piece(p, c.kbeg + k, c.m0 + r);
+            cs[j].ok = in;
+          }
+        } else {
+          pa_src[j] = !in ? p.A
+                          : (AKC ? p.A + (int64_t)(c.m0 + r) * p.lda + c.kbeg + k
+                                 : p.A + (int64_t)(c.kbeg + k) * p.lda + c.m0 + r);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        int r, k;
+        piece<BKC, BN>(j * kLoaderThreads + tid, r, k);
+        const bool in = has_b && (c.n0 + r) < p.N;
+        if (!BKC && in && c.n0 + r + 4 > p.N) pb_fast = 0;
+        if (in) pb_ok |= 1u << j;
+        pb_src[j] = !in ? p.B
+                        : (BKC ? p.B + (int64_t)(c.n0 + r) * p.ldb + c.kbeg + k
+                               : p.B + (int64_t)(c.kbeg + k) * p.ldb + c.n0 + r);
+      }
+    };
+    // K-slice ks of block c on its way into stage st: asynchronous copies straight into
+    // the operand images.
+    auto issue = [&](const TileCoord& c, int ks, int st) {
+      const int k0 = c.kbeg + ks * kBK;
+      const uint32_t sa = ring_addr + (uint32_t)(st * C::kStageBytes);
+      const bool whole = k0 + kBK <= c.kend;
       if (whole && pa_fast) {
 #pragma unroll
         for (int j = 0; j < NA; ++j) {
@@ -313,70 +346,78 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_kernel(GemmP p, int* stat
           cp_async16<false>(sa + pa_dst[j], in ? pa_src[j] + (int64_t)ks * a_step : p.A,
                             in ? 16u : 0u);
         }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+          int r, k;
+          piece<AKC, kBM>(j * kLoaderThreads + tid, r, k);
+          const uint32_t dst = sa + pa_dst[j];
+          if (CONV) {
+            if (cvec) {
+              conv_issue4(dst, p, cs[j], k0 + k < c.kend);
+              if (AKC) {          // next slice: 32 columns further
+                cs[j].c += kBK;
+                while (cs[j].c >= p.conv_C) { cs[j].c -= p.conv_C; ++cs[j].tap; }
+              } else {            // next slice: 32 pixel rows further
+                cs[j].pr += kBK; cs[j].x += kBK;
+                while (cs[j].x >= p.conv_W) {
+                  cs[j].x -= p.conv_W;
+                  if (++cs[j].y == p.conv_H) cs[j].y = 0;
+                }
+              }
+            } else {
+              st_shared16(dst, AKC ? conv_scalar4(p, c.m0 + r, k0 + k, p.M, c.kend)
+                                   : conv_scalar4(p, k0 + k, c.m0 + r, c.kend, p.M));
+            }
+          } else {
+            issue4<AKC>(dst, p.A, p.lda, c.m0 + r, k0 + k, p.M, c.kend, avec);
+          }
+        }
       }
-      if (whole && pb_fast) {
+      if (!has_b) {
+      } else if (whole && pb_fast) {
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
           const bool in = (pb_ok >> j) & 1u;
           cp_async16<false>(sa + pb_dst[j], in ? pb_src[j] + (int64_t)ks * b_step : p.B,
                             in ? 16u : 0u);
         }
-      }
+      } else {
 #pragma unroll
-      for (int j = 0; j < NA; ++j) {
-        if (whole && pa_fast) break;
-        int r, k;
-        const uint32_t dst = sa + piece<AKC, kBM>(j * kLoaderThreads + tid, r, k);
-        if (CONV) {
-          if (cvec) {
-            conv_issue4(dst, p, cs[j], k0 + k < kend);
-            if (AKC) {          // next stage: 32 columns further
-              cs[j].c += kBK;
-              while (cs[j].c >= p.conv_C) { cs[j].c -= p.conv_C; ++cs[j].tap; }
-            } else {            // next stage: 32 pixel rows further
-              cs[j].pr += kBK; cs[j].x += kBK;
-              while (cs[j].x >= p.conv_W) {
-                cs[j].x -= p.conv_W;
-                if (++cs[j].y == p.conv_H) cs[j].y = 0;
-              }
-            }
-          } else {
-            st_shared16(dst, AKC ? conv_scalar4(p, m0 + r, k0 + k, p.M, kend)
-                                 : conv_scalar4(p, k0 + k, m0 + r, kend, p.M));
-          }
-        } else {
-          issue4<AKC>(dst, p.A, p.lda, m0 + r, k0 + k, p.M, kend, avec);
+        for (int j = 0; j < NB; ++j) {
+          int r, k;
+          piece<BKC, BN>(j * kLoaderThreads + tid, r, k);
+          issue4<BKC>(sa + pb_dst[j], p.B, p.ldb, c.n0 + r, k0 + k, p.N, c.kend, bvec);
         }
       }
-#pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        if (whole && pb_fast) break;
-        int r, k;
-        const uint32_t dst = sb + piece<BKC, BN>(j * kLoaderThreads + tid, r, k);
-        issue4<BKC>(dst, p.B, p.ldb, n0 + r, k0 + k, p.N, kend, bvec);
-      }
     };
-    // Stage ks has landed: each thread applies the prologue to the pieces it copied
-    // itself (ReLU / gate on A, round-to-nearest tf32 on both), in place.
+    // A slice has landed: each thread applies the prologue to the pieces it copied itself
+    // (ReLU / gate on A, round-to-nearest tf32 on both), in place.  Rounding is one
+    // integer add per element (the MMA truncates the low 13 bits), ReLU + rounding one
+    // VIADDMNMX (umma_pack.cuh).
     const bool fin_a = !(p.a_tf32 && p.aop == AOP_ID), fin_b = !p.b_tf32;
-    // Round-to-nearest tf32 is one integer add per element (the MMA truncates the low 13
-    // bits), ReLU + rounding one VIADDMNMX (umma_pack.cuh).
-    auto finish = [&](int ks) {
-      const uint32_t sa = ring_addr + (uint32_t)((ks % S) * C::kStageBytes);
+    auto round4 = [](float4 v) {
+      return make_float4(__uint_as_float(tf32_rn_bits(__float_as_uint(v.x))),
+                         __uint_as_float(tf32_rn_bits(__float_as_uint(v.y))),
+                         __uint_as_float(tf32_rn_bits(__float_as_uint(v.z))),
+                         __uint_as_float(tf32_rn_bits(__float_as_uint(v.w))));
+    };
+    auto finish = [&](const TileCoord& c, int ks, int st) {
+      const uint32_t sa = ring_addr + (uint32_t)(st * C::kStageBytes);
       if (fin_a) {
         if (p.aop == AOP_GATE) {
-          const int k0 = kbeg + ks * kBK;
+          const int k0 = c.kbeg + ks * kBK;
 #pragma unroll
           for (int j = 0; j < NA; ++j) {
             int r, k;
             piece<AKC, kBM>(j * kLoaderThreads + tid, r, k);
             float4 v = ld_shared16(sa + pa_dst[j]);
-            const float4 g = fetch4<AKC>(p.gateA, p.lda, m0 + r, k0 + k, p.M, kend, avec);
+            const float4 g = fetch4<AKC>(p.gateA, p.lda, c.m0 + r, k0 + k, p.M, c.kend, avec);
             if (!(g.x > 0.f)) v.x = 0.f;
             if (!(g.y > 0.f)) v.y = 0.f;
             if (!(g.z > 0.f)) v.z = 0.f;
             if (!(g.w > 0.f)) v.w = 0.f;
-            st_shared16(sa + pa_dst[j], tf32_rn4(v));
+            st_shared16(sa + pa_dst[j], round4(v));
           }
         } else if (p.aop == AOP_RELU) {
 #pragma unroll
@@ -390,120 +431,211 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_kernel(GemmP p, int* stat
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < NA; ++j) {
-            const float4 v = ld_shared16(sa + pa_dst[j]);
-            st_shared16(sa + pa_dst[j],
-                        make_float4(__uint_as_float(tf32_rn_bits(__float_as_uint(v.x))),
-                                    __uint_as_float(tf32_rn_bits(__float_as_uint(v.y))),
-                                    __uint_as_float(tf32_rn_bits(__float_as_uint(v.z))),
-                                    __uint_as_float(tf32_rn_bits(__float_as_uint(v.w)))));
-          }
+          for (int j = 0; j < NA; ++j) st_shared16(sa + pa_dst[j], round4(ld_shared16(sa + pa_dst[j])));
         }
       }
-      if (fin_b) {
+      if (fin_b && has_b) {
 #pragma unroll
-        for (int j = 0; j < NB; ++j) {
-          const float4 v = ld_shared16(sa + pb_dst[j]);
-          st_shared16(sa + pb_dst[j],
-                      make_float4(__uint_as_float(tf32_rn_bits(__float_as_uint(v.x))),
-                                  __uint_as_float(tf32_rn_bits(__float_as_uint(v.y))),
-                                  __uint_as_float(tf32_rn_bits(__float_as_uint(v.z))),
-                                  __uint_as_float(tf32_rn_bits(__float_as_uint(v.w)))));
-        }
+        for (int j = 0; j < NB; ++j) st_shared16(sa + pb_dst[j], round4(ld_shared16(sa + pb_dst[j])));
       }
     };
-    for (int ks = 0; ks < S - 1; ++ks) {
-      if (ks < nks) issue(ks);
+
+    // issue cursor (runs S - 1 slices ahead, across block boundaries) and finish cursor
+    int ti = blockIdx.x, ks_i = 0;
+    bool have_i = ti < total;
+    TileCoord ci = tile_coord<BN>(p, have_i ? ti : 0, tm, tn);
+    if (have_i) setup(ci);
+    int tf = ti, ks_f = 0;
+    bool have_f = have_i;
+    TileCoord cf = ci;
+    uint32_t it_i = 0, it_f = 0;
+    auto issue_next = [&]() {
+      issue(ci, ks_i, (int)(it_i % S));
+      ++it_i;
+      if (++ks_i == ci.nks) {
+        ti += gridDim.x; ks_i = 0;
+        have_i = ti < total;
+        if (have_i) { ci = tile_coord<BN>(p, ti, tm, tn); setup(ci); }
+      }
+    };
+    for (int s = 0; s < S - 1; ++s) {
+      if (have_i) issue_next();
       cp_async_commit();
     }
-    for (int ks = 0; ks < nks; ++ks) {
-      cp_async_wait<S - 2>();            // this thread's copies of stage ks are complete
-      finish(ks);
+    while (have_f) {
+      cp_async_wait<S - 2>();            // this thread's copies of the oldest slice are complete
+      const int st = (int)(it_f % S);
+      finish(cf, ks_f, st);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[ks % S]);
-      // refill the stage MMA ks-1 read (it ran while this stage was being finished)
-      const int nxt = ks + S - 1;
-      if (nxt < nks) {
-        tc_wait(&empty[nxt % S], ((nxt / S) & 1) ^ 1, abort_flag, status, 930);
-        issue(nxt);
+      if (lane == 0) mbar_arrive(&full[st]);
+      ++it_f;
+      if (++ks_f == cf.nks) {
+        tf += gridDim.x; ks_f = 0;
+        have_f = tf < total;
+        if (have_f) cf = tile_coord<BN>(p, tf, tm, tn);
+      }
+      // refill the stage the previous slice's MMAs read (they ran during this finish)
+      if (have_i) {
+        tc_wait(&empty[it_i % S], ((it_i / S) & 1) ^ 1, abort_flag, status, 930);
+        issue_next();
       }
       cp_async_commit();
     }
-
-    // ===================== epilogue ==================================================
-    if (nks > 0) tc_wait(d_ready, 0, abort_flag, status, 931);
-    tc_fence_after();
-    const int q = warp & 3, hh = warp >> 2;
-    float* stg = reinterpret_cast<float*>(ring) + warp * (32 * 33);
-    const bool first = (blockIdx.z == 0);
-    const int rpg = (int)p.rows_per_group;
-    for (int c32 = hh; c32 < NB; c32 += 2) {
-      uint32_t v[32];
-      if (nks > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c32 * 32), v);
-        tmem_ld_wait(v);
-      } else {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] = 0u;
-      }
-#pragma unroll
-      for (int c = 0; c < 32; ++c) stg[lane * 33 + c] = __uint_as_float(v[c]);
-      __syncwarp();
-      const int n = n0 + c32 * 32 + lane;
-      const bool nok = n < p.N;
-      const float bias_n = (first && p.bias && nok) ? p.bias[n] : 0.f;
-      const int mrows = min(32, p.M - (m0 + q * 32));
-      for (int rr = 0; rr < mrows; ++rr) {
-        const int m = m0 + q * 32 + rr;
-        float x = stg[rr * 33 + lane] * p.alpha;
-        if (nok) {
-          if (first) {
-            x += bias_n;
-            if (p.rowbias) x += p.rowbias[(int64_t)(m / rpg) * p.ldrb + n];
-          }
-          if (p.gateC) x = (p.gateC[(int64_t)m * p.ldgc + n] > 0.f) ? x : 0.f;
-          if (first && p.res) x += p.res[(int64_t)m * p.ldres + n];
-          if (p.relu_out) x = fmaxf(x, 0.f);
-          float* c = p.C + (int64_t)m * p.ldc + n;
-          if (p.atomic) atomicAdd(c, x); else *c = x;
-        }
-      }
-      __syncwarp();
-    }
-  } else {
+  } else if (warp == kIssuerWarp) {
     // ===================== MMA issuer ================================================
     constexpr uint32_t idesc = idesc_tf32(kBM, BN) | (TA ? kIdescAMajorMN : 0u) |
                                (TB ? 0u : kIdescBMajorMN);
     // one K = 8 step: 32 bytes along the swizzled line (K-major), two 512-byte K atoms (MN-major)
     constexpr uint32_t a_step16 = AKC ? 32u >> 4 : 1024u >> 4;
     constexpr uint32_t b_step16 = BKC ? 32u >> 4 : 1024u >> 4;
-    for (int ks = 0; ks < nks; ++ks) {
-      const int st = ks % S;
-      if (elect_one()) {
-        tc_wait(&full[st], (ks / S) & 1, abort_flag, status, 932);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(ring + st * C::kStageBytes);
-        const uint32_t b_addr = a_addr + C::kABytes;
-        const uint64_t ad = AKC ? smem_desc_lt(a_addr, 16, 1024, 2)
-                                : smem_desc_lt(a_addr, kMnLbo, kMnSbo, 1);
-        const uint64_t bd = BKC ? smem_desc_lt(b_addr, 16, 1024, 2)
-                                : smem_desc_lt(b_addr, kMnLbo, kMnSbo, 1);
-        mma_tf32_ss_steps<kBK / 8>(tmem_base, ad, bd, a_step16, b_step16, idesc,
-                                   ks == 0 ? 0u : 1u);
-        mma_commit(&empty[st]);
-        if (ks == nks - 1) mma_commit(d_ready);
+    uint32_t it = 0;
+    int li = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++li) {
+      const TileCoord c = tile_coord<BN>(p, t, tm, tn);
+      const int buf = li & 1;
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+      for (int ks = 0; ks < c.nks; ++ks, ++it) {
+        const int st = (int)(it % S);
+        if (elect_one()) {
+          if (ks == 0)      // the epilogue has drained this accumulator (two blocks ago)
+            tc_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1, abort_flag, status, 933);
+          tc_wait(&full[st], (it / S) & 1, abort_flag, status, 932);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(ring + st * C::kStageBytes);
+          const uint32_t b_addr = a_addr + C::kABytes;
+          const uint64_t ad = AKC ? smem_desc_lt(a_addr, 16, 1024, 2)
+                                  : smem_desc_lt(a_addr, kMnLbo, kMnSbo, 1);
+          const uint64_t bd = BKC ? smem_desc_lt(b_addr, 16, 1024, 2)
+                                  : smem_desc_lt(b_addr, kMnLbo, kMnSbo, 1);
+          mma_tf32_ss_steps<kBK / 8>(d_tmem, ad, bd, a_step16, b_step16, idesc, ks == 0 ? 0u : 1u);
+          mma_commit(&empty[st]);
+          if (ks == c.nks - 1) mma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue ==================================================
+    // Two warps per accumulator lane quarter (32 rows) share its 32-column chunks.  A chunk
+    // is re-read from tensor memory (thread = row), transposed through shared memory, and
+    // leaves as 16-byte pieces: a warp instruction covers 4 rows x 128 contiguous bytes of
+    // C (and of the gate / residual operands).
+    const int ew = warp - kFirstEpiWarp;
+    const int q = warp & 3, hh = ew >> 2;
+    float* stg = epi_stage + ew * (32 * kEpiLd);
+    const int rpg = (int)p.rows_per_group;
+    const bool vec_c = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                       (!p.gateC || (((p.ldgc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.gateC) & 15) == 0))) &&
+                       (!p.res || (((p.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0))) &&
+                       (!p.rowbias || (((p.ldrb & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.rowbias) & 15) == 0))) &&
+                       (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
+    int li = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++li) {
+      const TileCoord c = tile_coord<BN>(p, t, tm, tn);
+      const int buf = li & 1;
+      tc_wait(&acc_full[buf], (li >> 1) & 1, abort_flag, status, 931);
+      tc_fence_after();
+      constexpr int kChunks = BN / 32;
+      // this warp's last chunk of the block (-1: none, BN = 32 keeps only one warp of a pair busy)
+      const int my_last = (kChunks - 1 - hh >= 0) ? hh + ((kChunks - 1 - hh) / 2) * 2 : -1;
+      if (my_last < 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        continue;
+      }
+      for (int c32 = hh; c32 < kChunks; c32 += 2) {
+        {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c32 * 32), v);
+          tmem_ld_wait(v);
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc)
+            *reinterpret_cast<float4*>(stg + lane * kEpiLd + cc * 4) =
+                make_float4(__uint_as_float(v[cc * 4]), __uint_as_float(v[cc * 4 + 1]),
+                            __uint_as_float(v[cc * 4 + 2]), __uint_as_float(v[cc * 4 + 3]));
+        }
+        if (c32 == my_last) {            // accumulator drained by this warp: the issuer may reuse it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        __syncwarp();
+        const int nbase = c.n0 + c32 * 32;
+        const int mbase = c.m0 + q * 32;
+        if (vec_c && nbase + 32 <= p.N) {
+          const int l8 = lane & 7, r4 = lane >> 3;
+          const int n = nbase + l8 * 4;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c.first && p.bias) b4 = *reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll 2
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + r4;
+            const int m = mbase + rr;
+            if (m >= p.M) continue;
+            float4 x = *reinterpret_cast<const float4*>(stg + rr * kEpiLd + l8 * 4);
+            x.x *= p.alpha; x.y *= p.alpha; x.z *= p.alpha; x.w *= p.alpha;
+            if (c.first) {
+              x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+              if (p.rowbias) {
+                const float4 rb = *reinterpret_cast<const float4*>(p.rowbias + (int64_t)(m / rpg) * p.ldrb + n);
+                x.x += rb.x; x.y += rb.y; x.z += rb.z; x.w += rb.w;
+              }
+            }
+            if (p.gateC) {
+              const float4 g = *reinterpret_cast<const float4*>(p.gateC + (int64_t)m * p.ldgc + n);
+              if (!(g.x > 0.f)) x.x = 0.f;
+              if (!(g.y > 0.f)) x.y = 0.f;
+              if (!(g.z > 0.f)) x.z = 0.f;
+              if (!(g.w > 0.f)) x.w = 0.f;
+            }
+            if (c.first && p.res) {
+              const float4 rs = *reinterpret_cast<const float4*>(p.res + (int64_t)m * p.ldres + n);
+              x.x += rs.x; x.y += rs.y; x.z += rs.z; x.w += rs.w;
+            }
+            if (p.relu_out) {
+              x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+            }
+            float* cp = p.C + (int64_t)m * p.ldc + n;
+            if (p.atomic) {
+              atomicAdd(cp, x.x); atomicAdd(cp + 1, x.y); atomicAdd(cp + 2, x.z); atomicAdd(cp + 3, x.w);
+            } else {
+              *reinterpret_cast<float4*>(cp) = x;
+            }
+          }
+        } else {
+          const int n = nbase + lane;
+          const bool nok = n < p.N;
+          const float bias_n = (c.first && p.bias && nok) ? p.bias[n] : 0.f;
+          const int mrows = min(32, p.M - mbase);
+          for (int rr = 0; rr < mrows; ++rr) {
+            const int m = mbase + rr;
+            float x = stg[rr * kEpiLd + lane] * p.alpha;
+            if (nok) {
+              if (c.first) {
+                x += bias_n;
+                if (p.rowbias) x += p.rowbias[(int64_t)(m / rpg) * p.ldrb + n];
+              }
+              if (p.gateC) x = (p.gateC[(int64_t)m * p.ldgc + n] > 0.f) ? x : 0.f;
+              if (c.first && p.res) x += p.res[(int64_t)m * p.ldres + n];
+              if (p.relu_out) x = fmaxf(x, 0.f);
+              float* cp = p.C + (int64_t)m * p.ldc + n;
+              if (p.atomic) atomicAdd(cp, x); else *cp = x;
+            }
+          }
+        }
+        __syncwarp();
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kLoaderWarps) tmem_dealloc(tmem_base, BN);
+  if (warp == kIssuerWarp) tmem_dealloc(tmem_base, 2 * BN);
 }
 
 template <bool TA, bool TB, int BN, bool CONV>
-int launch_tc(ibc_handle* h, const GemmP& p, dim3 grid, cudaStream_t s) {
+int launch_tc(ibc_handle* h, const GemmP& p, int tm, int tn, int splits, cudaStream_t s) {
   using C = TcCfg<BN>;
   static bool attr = false;
   if (!attr) {
@@ -511,16 +643,21 @@ int launch_tc(ibc_handle* h, const GemmP& p, dim3 grid, cudaStream_t s) {
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
     attr = true;
   }
-  gemm_tc_kernel<TA, TB, BN, CONV><<<grid, kThreads, C::kSmem, s>>>(p, h ? h->dev_status : nullptr);
+  const int64_t total = (int64_t)tm * tn * splits;
+  if (total > 0x7fffffff) IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "gemm_tc: too many output blocks");
+  const int sms = h ? h->sm_count : 148;
+  const unsigned grid = (unsigned)(total < sms ? total : sms);
+  gemm_tc_kernel<TA, TB, BN, CONV><<<grid, kThreads, C::kSmem, s>>>(
+      p, h ? h->dev_status : nullptr, tm, tn, (int)total);
   IBC_LAUNCH_CHECK(h);
   return IBC_OK;
 }
 
 template <bool TA, bool TB, bool CONV>
-int launch_tc_bn(ibc_handle* h, const GemmP& p, int bn, dim3 grid, cudaStream_t s) {
-  if (bn == 32) return launch_tc<TA, TB, 32, CONV>(h, p, grid, s);
-  if (bn == 64) return launch_tc<TA, TB, 64, CONV>(h, p, grid, s);
-  return launch_tc<TA, TB, 128, CONV>(h, p, grid, s);
+int launch_tc_bn(ibc_handle* h, const GemmP& p, int bn, int tm, int tn, int splits, cudaStream_t s) {
+  if (bn == 32) return launch_tc<TA, TB, 32, CONV>(h, p, tm, tn, splits, s);
+  if (bn == 64) return launch_tc<TA, TB, 64, CONV>(h, p, tm, tn, splits, s);
+  return launch_tc<TA, TB, 128, CONV>(h, p, tm, tn, splits, s);
 }
 
 }  // namespace
@@ -553,19 +690,17 @@ int gemm_tc(ibc_handle* h, const GemmP& p_in, bool ta, bool tb, cudaStream_t s) 
   } else {
     p.k_chunk = 0;
   }
-  if (tn > 65535 || splits > 65535) IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "gemm_tc: grid too large");
-  dim3 grid((unsigned)tm, (unsigned)tn, (unsigned)splits);
   if (p.conv_C > 0) {       // implicit convolution: the weights are always [K, N] row-major
     if (tb) IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "gemm_tc: implicit convolution takes B as [K, N]");
     const int kdim = ta ? p.M : p.K;
     if (kdim != 9 * p.conv_C) IBC_FAIL(h, IBC_ERR_INVALID, "gemm_tc: convolution needs 9 * C columns");
-    if (ta) return launch_tc_bn<true, false, true>(h, p, bn, grid, s);
-    return launch_tc_bn<false, false, true>(h, p, bn, grid, s);
+    if (ta) return launch_tc_bn<true, false, true>(h, p, bn, tm, tn, splits, s);
+    return launch_tc_bn<false, false, true>(h, p, bn, tm, tn, splits, s);
   }
-  if (ta && tb) return launch_tc_bn<true, true, false>(h, p, bn, grid, s);
-  if (ta) return launch_tc_bn<true, false, false>(h, p, bn, grid, s);
-  if (tb) return launch_tc_bn<false, true, false>(h, p, bn, grid, s);
-  return launch_tc_bn<false, false, false>(h, p, bn, grid, s);
+  if (ta && tb) return launch_tc_bn<true, true, false>(h, p, bn, tm, tn, splits, s);
+  if (ta) return launch_tc_bn<true, false, false>(h, p, bn, tm, tn, splits, s);
+  if (tb) return launch_tc_bn<false, true, false>(h, p, bn, tm, tn, splits, s);
+  return launch_tc_bn<false, false, false>(h, p, bn, tm, tn, splits, s);
 }
 
 }  // namespace ibc
