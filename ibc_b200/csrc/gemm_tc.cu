@@ -26,6 +26,8 @@
 // epilogue re-reads the accumulator by 32-column chunks, transposes each chunk through
 // shared memory (the ring is free by then) so that a warp's loads of gate / residual and
 // its stores (or atomics, split-K) cover 128 contiguous bytes of a C row.
+#include <stdlib.h>
+
 #include "gemm_simt.cuh"
 #include "umma.cuh"
 #include "umma_pack.cuh"
@@ -54,6 +56,8 @@ struct TcCfg {
   static constexpr int kBBytes = BN * kBK * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kRing = kStages * kStageBytes;
+  // accumulators in tensor memory: the issuer runs that many output blocks ahead of the epilogue
+  static constexpr int kBufs = BN > 64 ? 2 : 4;
   static constexpr int kEpiStage = kEpiWarps * 32 * kEpiLd * 4;   // epilogue transposing stage
   static constexpr size_t kSmem = (size_t)kRing + kEpiStage + 1024 + 256;
 };
@@ -237,10 +241,10 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmP& p, int t, int tm, i
 
 // Persistent: CTA b walks blocks b, b + grid, ... with three sets of warps running ahead
 // of one another -- loaders (K-slices of the next blocks are already in flight while a
-// block finishes), the MMA issuer (two accumulators in tensor memory) and the epilogue.
+// block finishes), the MMA issuer (2-4 accumulators in tensor memory) and the epilogue.
 template <bool TA, bool TB, int BN, bool CONV>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(GemmP p, int* status, int tm, int tn,
-                                                              int total) {
+                                                              int total, int dbg) {
   using C = TcCfg<BN>;
   constexpr int S = C::kStages;
   constexpr bool AKC = !TA, BKC = TB;
@@ -253,9 +257,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(GemmP p, int* stat
   float* epi_stage = reinterpret_cast<float*>(ring + C::kRing);
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + C::kRing + C::kEpiStage);
   uint64_t* empty = full + S;
-  uint64_t* acc_full = empty + S;        // [2] issuer -> epilogue
-  uint64_t* acc_empty = acc_full + 2;    // [2] epilogue -> issuer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  constexpr int NBUF = C::kBufs;
+  uint64_t* acc_full = empty + S;            // [NBUF] issuer -> epilogue
+  uint64_t* acc_empty = acc_full + NBUF;     // [NBUF] epilogue -> issuer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NBUF);
   __shared__ int s_abort;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -263,10 +268,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(GemmP p, int* stat
   if (tid == 0) {
     s_abort = 0;
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], kLoaderWarps); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
+    for (int s = 0; s < NBUF; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
     fence_mbar_init();
   }
-  if (warp == kIssuerWarp) tmem_alloc(tmem_slot, 2 * BN);
+  if (warp == kIssuerWarp) tmem_alloc(tmem_slot, NBUF * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -450,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(GemmP p, int* stat
     TileCoord cf = ci;
     uint32_t it_i = 0, it_f = 0;
     auto issue_next = [&]() {
-      issue(ci, ks_i, (int)(it_i % S));
+      if (!(dbg & 1)) issue(ci, ks_i, (int)(it_i % S));
       ++it_i;
       if (++ks_i == ci.nks) {
         ti += gridDim.x; ks_i = 0;
@@ -465,7 +470,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(GemmP p, int* stat
     while (have_f) {
       cp_async_wait<S - 2>();            // this thread's copies of the oldest slice are complete
       const int st = (int)(it_f % S);
-      finish(cf, ks_f, st);
+      if (!(dbg & 1)) finish(cf, ks_f, st);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[st]);
@@ -493,13 +498,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(GemmP p, int* stat
     int li = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++li) {
       const TileCoord c = tile_coord<BN>(p, t, tm, tn);
-      const int buf = li & 1;
+      const int buf = li % NBUF;
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
       for (int ks = 0; ks < c.nks; ++ks, ++it) {
         const int st = (int)(it % S);
         if (elect_one()) {
-          if (ks == 0)      // the epilogue has drained this accumulator (two blocks ago)
-            tc_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1, abort_flag, status, 933);
+          if (ks == 0)      // the epilogue has drained this accumulator (NBUF blocks ago)
+            tc_wait(&acc_empty[buf], ((li / NBUF) & 1) ^ 1, abort_flag, status, 933);
           tc_wait(&full[st], (it / S) & 1, abort_flag, status, 932);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(ring + st * C::kStageBytes);
@@ -508,7 +513,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(GemmP p, int* stat
                                   : smem_desc_lt(a_addr, kMnLbo, kMnSbo, 1);
           const uint64_t bd = BKC ? smem_desc_lt(b_addr, 16, 1024, 2)
                                   : smem_desc_lt(b_addr, kMnLbo, kMnSbo, 1);
-          mma_tf32_ss_steps<kBK / 8>(d_tmem, ad, bd, a_step16, b_step16, idesc, ks == 0 ? 0u : 1u);
+          if (!(dbg & 2))
+            mma_tf32_ss_steps<kBK / 8>(d_tmem, ad, bd, a_step16, b_step16, idesc, ks == 0 ? 0u : 1u);
           mma_commit(&empty[st]);
           if (ks == c.nks - 1) mma_commit(&acc_full[buf]);
         }
@@ -533,19 +539,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(GemmP p, int* stat
     int li = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++li) {
       const TileCoord c = tile_coord<BN>(p, t, tm, tn);
-      const int buf = li & 1;
-      tc_wait(&acc_full[buf], (li >> 1) & 1, abort_flag, status, 931);
+      const int buf = li % NBUF;
+      tc_wait(&acc_full[buf], (li / NBUF) & 1, abort_flag, status, 931);
       tc_fence_after();
       constexpr int kChunks = BN / 32;
-      // this warp's last chunk of the block (-1: none, BN = 32 keeps only one warp of a pair busy)
-      const int my_last = (kChunks - 1 - hh >= 0) ? hh + ((kChunks - 1 - hh) / 2) * 2 : -1;
+      // The two warps of a lane quarter take alternate (block, chunk) units: with one chunk
+      // per block (BN = 32) they alternate blocks, so two epilogues are in flight per quarter.
+      const int c_first = (hh + li * kChunks) & 1;     // this warp's first chunk of the block
+      const int my_last = (kChunks - 1 - c_first >= 0) ? c_first + ((kChunks - 1 - c_first) / 2) * 2 : -1;
       if (my_last < 0) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
         continue;
       }
-      for (int c32 = hh; c32 < kChunks; c32 += 2) {
+      for (int c32 = c_first; c32 < kChunks; c32 += 2) {
         {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c32 * 32), v);
@@ -631,7 +639,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(GemmP p, int* stat
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kIssuerWarp) tmem_dealloc(tmem_base, 2 * BN);
+  if (warp == kIssuerWarp) tmem_dealloc(tmem_base, NBUF * BN);
+}
+
+// IBC_TC_DBG (diagnostics only, results are garbage): bit 0 = loaders skip the copies and
+// the prologue (barrier traffic only), bit 1 = the issuer skips the MMAs.  Separates the
+// loaders' rate from the issuer's (scripts/dbg_gemm_tc.py): with both off a K-slice still
+// costs ~570 cycles of mbarrier hand-overs between the 16 loader warps and the issuer,
+// which is what bounds blocks with few K-slices today.
+int debug_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("IBC_TC_DBG");
+    mode = e ? atoi(e) : 0;
+  }
+  return mode;
 }
 
 template <bool TA, bool TB, int BN, bool CONV>
@@ -648,7 +670,7 @@ int launch_tc(ibc_handle* h, const GemmP& p, int tm, int tn, int splits, cudaStr
   const int sms = h ? h->sm_count : 148;
   const unsigned grid = (unsigned)(total < sms ? total : sms);
   gemm_tc_kernel<TA, TB, BN, CONV><<<grid, kThreads, C::kSmem, s>>>(
-      p, h ? h->dev_status : nullptr, tm, tn, (int)total);
+      p, h ? h->dev_status : nullptr, tm, tn, (int)total, debug_mode());
   IBC_LAUNCH_CHECK(h);
   return IBC_OK;
 }
