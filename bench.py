@@ -408,6 +408,49 @@ def secondary_configs(device):
     out[name] = {'ms_per_chain': t * 1e3, 'rows': b * n, 'iterations': k,
                  'energy_grad_evals_per_s': b * n * k / t, 'precision': 'tf32',
                  'kernel_status': e.kernel_status()}
+  # Full train steps of the Langevin configs through ImplicitBCAgent.train (the reference's
+  # call): uniform seeds -> 100-step Langevin chain on B*N = 4096 rows -> InfoNCE + gradient
+  # penalty forward / second-order backward on B*(N+1) rows -> Adam (energy
+  # evals per step = K*B*N + 2*B*(N+1))
+  from ibc_b200 import gin_lite as gin
+  from ibc_b200.ibc import specs
+  from ibc_b200.ibc.agents import ibc_agent
+  from ibc_b200.ibc.train import get_agent
+  from ibc_b200.networks.mlp_ebm import MLPEBM
+  for name, (o, a, w, d), extra in (
+      ('C3_particle32_train_step', (256, 32, 256, 2), ''),
+      ('C4_d4rl_door_train_step', (39, 28, 512, 8),
+       'langevin_actions_given_obs.sampler_stepsize_init = 0.5\n'
+       'langevin_actions_given_obs.delta_action_clip = 0.5\n'
+       'langevin_actions_given_obs.noise_scale = 0.5\n')):
+    gin.clear_config()
+    gin.parse_config('langevin_actions_given_obs.num_iterations = 100\n' + extra)
+    try:
+      b, n, k = 512, 8, 100
+      obs_spec = {'obs': specs.TensorSpec((1, o))}
+      act_spec = specs.BoundedTensorSpec((a,), minimum=-1.0, maximum=1.0)
+      samp = specs.BoundedTensorSpec((a,), minimum=-1.1, maximum=1.1)
+      net = MLPEBM((obs_spec, act_spec), specs.TensorSpec((1,)), width=w, depth=d, rate=0.0,
+                   layers='ResNetPreActivation', seed=1)
+      opt = get_agent.Adam(get_agent.ExponentialDecay(1e-3, 100, 0.99))
+      agent = ibc_agent.ImplicitBCAgent(obs_spec, act_spec, samp, net, opt, num_counter_examples=n,
+                                        fraction_langevin_samples=1.0, add_grad_penalty=True,
+                                        run_full_chain_under_gradient=True)
+      g = torch.Generator().manual_seed(0)
+      exp = (({'obs': torch.randn(b, 1, o, generator=g).to(device)},
+              (torch.rand(b, a, generator=g) * 2 - 1).to(device)), ())
+      for _ in range(3):
+        agent.train(exp)
+      t = timed(lambda i: agent.train(exp), 5, lambda: None) / 5
+      evals = k * b * n + 2 * b * (n + 1)
+      fwd = 2.0 * ((o + a) * w + d * w * w + w)
+      flops = (k * b * n * 2 + b * (n + 1) * 7) * fwd
+      out[name] = {'ms_per_step': t * 1e3, 'batch': b, 'num_counter_examples': n,
+                   'langevin_iterations': k, 'energy_evals_per_s': evals / t,
+                   'tflops': flops / t * 1e-12, 'precision': 'tf32',
+                   'kernel_status': net.engine.kernel_status()}
+    finally:
+      gin.clear_config()
   # C5 PixelEBM (pushing_pixels/pixel_ebm_best.gin shapes): late-fusion train step at the
   # gin's batch 128 with 256 counter-examples, tf32 tensor-core path and the fp32 path
   from ibc_b200 import _lib
