@@ -540,7 +540,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(GemmP p, int* stat
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++li) {
       const TileCoord c = tile_coord<BN>(p, t, tm, tn);
       const int buf = li % NBUF;
-      tc_wait(&acc_full[buf], (li / NBUF) & 1, abort_flag, status, 931);
+      // a whole main loop away: wait with the suspend-time hint (umma::mbar_wait) so that the
+      // 8 idle warps do not take issue slots from the loaders by polling
+      mbar_wait(&acc_full[buf], (li / NBUF) & 1, abort_flag, status, 931);
       tc_fence_after();
       constexpr int kChunks = BN / 32;
       // The two warps of a lane quarter take alternate (block, chunk) units: with one chunk
