@@ -183,9 +183,14 @@ class IbcPolicy:
   def _clip_to_spec(self, action):
     if not self._clip or not hasattr(self.action_spec, 'minimum'):
       return action
-    lo = torch.as_tensor(self.action_spec.minimum).to(action.device).reshape(-1)
-    hi = torch.as_tensor(self.action_spec.maximum).to(action.device).reshape(-1)
-    return torch.minimum(torch.maximum(action, lo), hi)
+    bounds = getattr(self, '_clip_bounds', None)
+    if bounds is None or bounds[0].device != action.device:
+      # device copies made once: a per-call host -> device copy is a synchronous transfer
+      # that waits for the sampler's kernels (it was half of an action's wall time)
+      bounds = tuple(torch.as_tensor(np.asarray(v, np.float32)).to(action.device).reshape(-1)
+                     for v in (self.action_spec.minimum, self.action_spec.maximum))
+      self._clip_bounds = bounds
+    return torch.minimum(torch.maximum(action, bounds[0]), bounds[1])
 
 
 class GreedyPolicy:
