@@ -417,12 +417,16 @@ def secondary_configs(device):
   from ibc_b200.ibc.agents import ibc_agent
   from ibc_b200.ibc.train import get_agent
   from ibc_b200.networks.mlp_ebm import MLPEBM
-  for name, (o, a, w, d), extra in (
+  import torch.distributed as dist
+  # (single-process runs only: with a process group up, ImplicitBCAgent.train all-reduces its
+  # gradients and rank 0 alone would wait for the other ranks forever)
+  solo = not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+  for name, (o, a, w, d), extra in (() if not solo else (
       ('C3_particle32_train_step', (256, 32, 256, 2), ''),
       ('C4_d4rl_door_train_step', (39, 28, 512, 8),
        'langevin_actions_given_obs.sampler_stepsize_init = 0.5\n'
        'langevin_actions_given_obs.delta_action_clip = 0.5\n'
-       'langevin_actions_given_obs.noise_scale = 0.5\n')):
+       'langevin_actions_given_obs.noise_scale = 0.5\n'))):
     gin.clear_config()
     gin.parse_config('langevin_actions_given_obs.num_iterations = 100\n' + extra)
     try:
