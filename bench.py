@@ -408,6 +408,27 @@ def secondary_configs(device):
     out[name] = {'ms_per_chain': t * 1e3, 'rows': b * n, 'iterations': k,
                  'energy_grad_evals_per_s': b * n * k / t, 'precision': 'tf32',
                  'kernel_status': e.kernel_status()}
+  # C1 (particle 2-D, DFO-style training: W=256 D=2, B=512, N=256 uniform negatives, no
+  # gradient penalty): loss forward + backward + weight gradients on 131 584 rows; width 256
+  # trains through the per-layer passes on the general tcgen05 GEMM
+  from ibc_b200 import _lib as _l
+  e = eng.EBMEngine(16, 2, 256, 2, device)
+  e.bind_params((torch.randn(e.param_count, device=device) * 0.05).contiguous())
+  b, n = 512, 256
+  obs = torch.randn(b, 16, device=device)
+  acts = torch.rand(b * (n + 1), 2, device=device) * 2.2 - 1.1
+  cfg = eng.loss_cfg(1.0, False)
+  fwd = 2.0 * (18 * 256 + 2 * 256 * 256 + 256)
+  for prec, key in ((_l.PRECISION_TF32, 'C1_particle2d_train_grads'),
+                    (_l.PRECISION_FP32, 'C1_particle2d_train_grads_fp32')):
+    e.set_precision(prec)
+    for _ in range(2):
+      e.train_grads(obs, acts, n, cfg, b)
+    t = timed(lambda i: e.train_grads(obs, acts, n, cfg, b), 5, lambda: None) / 5
+    out[key] = {'ms_per_step': t * 1e3, 'rows': b * (n + 1), 'energy_evals_per_s': b * (n + 1) / t,
+                'tflops': 3.0 * b * (n + 1) * fwd / t * 1e-12,
+                'precision': 'tf32' if prec == _l.PRECISION_TF32 else 'fp32',
+                'kernel_status': e.kernel_status()}
   # Full train steps of the Langevin configs through ImplicitBCAgent.train (the reference's
   # call): uniform seeds -> 100-step Langevin chain on B*N = 4096 rows -> InfoNCE + gradient
   # penalty forward / second-order backward on B*(N+1) rows -> Adam (energy
