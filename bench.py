@@ -498,6 +498,23 @@ def secondary_configs(device):
     out[key] = {'ms_per_step': t * 1e3, 'images': b, 'rows': b * (n + 1), 'images_per_s': b / t,
                 'energy_evals_per_s': b * (n + 1) / t, 'tflops': flops / t * 1e-12,
                 'precision': label, 'kernel_status': pe.kernel_status()}
+  # C5 inference (pixel_ebm_best.gin: one frame pair, late fusion: encode once, DFO over 2048
+  # candidates, 3 iterations) on the tf32 path
+  pe.set_precision(_lib.PRECISION_TF32)
+  mn, mx = torch.full((2,), -1.1, device=device), torch.full((2,), 1.1, device=device)
+  frame = img[:1].contiguous()
+
+  def pixel_action(i):
+    enc = pe.encode(frame)
+    cand = eng.uniform_actions(2048, mn, mx, None, 100 + i)
+    probs = pe.dfo(enc, cand, 2048, mn, mx, 1.0, 3, 0.33, None, None, seed=200 + i)
+    return cand[torch.argmax(probs)]
+  for i in range(3):
+    pixel_action(i)
+  t = timed(pixel_action, 20, lambda: None) / 20
+  out['C5_pixel_dfo_inference'] = {'ms_per_action': t * 1e3, 'actions_per_s': 1.0 / t,
+                                   'num_action_samples': 2048, 'iterations': 3,
+                                   'kernel_status': pe.kernel_status()}
   return out
 
 
