@@ -498,6 +498,32 @@ def secondary_configs(device):
     out[key] = {'ms_per_step': t * 1e3, 'images': b, 'rows': b * (n + 1), 'images_per_s': b / t,
                 'energy_evals_per_s': b * (n + 1) / t, 'tflops': flops / t * 1e-12,
                 'precision': label, 'kernel_status': pe.kernel_status()}
+  # C5 whole train step through the reference's call (late-fusion ImplicitBCAgent.train on a
+  # PixelEBM: uniform negatives, encode once, tile, InfoNCE, backward, Adam), frames resident
+  # on the device; single-process runs only (see above)
+  if solo:
+    from ibc_b200.networks.pixel_ebm import PixelEBM
+    gin.clear_config()
+    gin.parse_config('DenseResnetValue.width = 1024\nDenseResnetValue.num_blocks = 1')
+    try:
+      p_obs = {'rgb': specs.TensorSpec((2, 240, 320, 3), dtype=torch.uint8)}
+      p_act = specs.BoundedTensorSpec((2,), minimum=-1.0, maximum=1.0)
+      p_samp = specs.BoundedTensorSpec((2,), minimum=-1.1, maximum=1.1)
+      pnet = PixelEBM((p_obs, p_act), specs.TensorSpec((1,)), 'ConvMaxpoolEncoder',
+                      'DenseResnetValue', target_height=180, target_width=240, seed=0)
+      pagent = ibc_agent.ImplicitBCAgent(p_obs, p_act, p_samp, pnet, get_agent.Adam(1e-3),
+                                         num_counter_examples=n, fraction_langevin_samples=0.0,
+                                         late_fusion=True, add_grad_penalty=False)
+      pexp = (({'rgb': img}, torch.rand(b, 2, device=device) * 2 - 1), ())
+      for _ in range(2):
+        pagent.train(pexp)
+      t = timed(lambda i: pagent.train(pexp), 3, lambda: None) / 3
+      out['C5_pixel_ebm_train_step'] = {
+          'ms_per_step': t * 1e3, 'images': b, 'images_per_s': b / t,
+          'energy_evals_per_s': b * (n + 1) / t, 'tflops': flops / t * 1e-12,
+          'precision': 'tf32', 'kernel_status': pnet.engine.kernel_status()}
+    finally:
+      gin.clear_config()
   # C5 inference (pixel_ebm_best.gin: one frame pair, late fusion: encode once, DFO over 2048
   # candidates, 3 iterations) on the tf32 path
   pe.set_precision(_lib.PRECISION_TF32)
