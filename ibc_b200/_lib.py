@@ -131,6 +131,9 @@ SIGNATURES = {
     'ibc_gemm_tf32': (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p,
                               c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                               c_int32, c_int32, c_int32, POINTER(c_int32), c_void_p]),
+    'ibc_conv3x3_tf32': (c_int, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_int32,
+                                 c_void_p, c_int32, c_int32, c_void_p, c_void_p, POINTER(c_int32),
+                                 c_void_p]),
 }
 
 _lib = None

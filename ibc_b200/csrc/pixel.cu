@@ -822,4 +822,54 @@ int ibc_pixel_train_grads(ibc_pixel_handle* ph, const void* images, int32_t is_u
   return IBC_OK;
 }
 
+int ibc_conv3x3_tf32(const float* X, int64_t nb, int32_t H, int32_t W, int32_t C, const float* K,
+                     int32_t Co, const float* bias, int32_t relu, int32_t mode, const float* dY,
+                     float* out, int32_t* status_host, void* stream) {
+  ibc_handle* none = nullptr;
+  if (!K || !out || nb < 1 || H < 1 || W < 1 || C < 1 || Co < 1 || mode < 0 || mode > 2 ||
+      (mode != 2 && !X) || (mode != 0 && !dY) || nb * H * W > 0x7fffffffLL)
+    IBC_FAIL(none, IBC_ERR_INVALID, "ibc_conv3x3_tf32: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  int dev = 0, major = 0, sms = 0;
+  IBC_CUDA(none, cudaGetDevice(&dev));
+  IBC_CUDA(none, cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  IBC_CUDA(none, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (major != 10) IBC_FAIL(none, IBC_ERR_UNSUPPORTED, "ibc_b200 is built for sm_100a only");
+  ibc_handle tmp;                       // error string, SM count and status word
+  tmp.device = dev;
+  tmp.sm_count = sms;
+  float* flipped = nullptr;
+  IBC_CUDA(none, cudaMalloc((void**)&tmp.dev_status, sizeof(int)));
+  cudaMemsetAsync(tmp.dev_status, 0, sizeof(int), s);
+  const int rows = (int)(nb * H * W);
+  GemmP g;
+  int rc = IBC_OK;
+  if (mode == 0) {          // Y = f(im2col(X) . K + b)
+    g.A = X; g.conv_H = H; g.conv_W = W; g.conv_C = C; g.B = K; g.ldb = Co; g.C = out; g.ldc = Co;
+    g.bias = bias; g.M = rows; g.N = Co; g.K = 9 * C; g.relu_out = relu;
+    rc = gemm_tc(&tmp, g, false, false, s);
+  } else if (mode == 1) {   // dK += im2col(X)^T . dY
+    g.A = X; g.conv_H = H; g.conv_W = W; g.conv_C = C; g.B = dY; g.ldb = Co; g.C = out; g.ldc = Co;
+    g.M = 9 * C; g.N = Co; g.K = rows; g.atomic = 1;
+    rc = gemm_tc(&tmp, g, true, false, s);
+  } else {                  // dX = im2col(dY) . flip(K)
+    if (cudaMalloc((void**)&flipped, (size_t)9 * C * Co * 4) != cudaSuccess) rc = IBC_ERR_CUDA;
+    if (rc == IBC_OK) {
+      flip_kernel3x3_kernel<<<nblocks(9 * C * Co), 256, 0, s>>>(K, C, Co, flipped);
+      g.A = dY; g.conv_H = H; g.conv_W = W; g.conv_C = Co; g.B = flipped; g.ldb = C; g.C = out;
+      g.ldc = C; g.M = rows; g.N = C; g.K = 9 * Co; g.b_tf32 = 1;
+      rc = gemm_tc(&tmp, g, false, false, s);
+    }
+  }
+  int st = 0;
+  if (cudaStreamSynchronize(s) != cudaSuccess && rc == IBC_OK) rc = IBC_ERR_CUDA;
+  if (rc == IBC_OK) cudaMemcpy(&st, tmp.dev_status, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(tmp.dev_status);
+  if (flipped) cudaFree(flipped);
+  if (rc != IBC_OK)
+    strncpy(ibc::g_create_error, tmp.err.empty() ? "ibc_conv3x3_tf32 failed" : tmp.err.c_str(), 511);
+  if (status_host) *status_host = st;
+  return rc;
+}
+
 }  // extern "C"

@@ -472,6 +472,28 @@ def gemm_tf32(a: torch.Tensor, b: torch.Tensor, m: int, n: int, k: int, trans_a=
   return c, (int(st.value) if check else None)
 
 
+def conv3x3_tf32(x, kernel, bias=None, relu=False, mode=0, dy=None, out=None):
+  """The encoder's implicit-GEMM convolution on its own (ibc_conv3x3_tf32): mode 0 forward
+  (x [nb,H,W,C], kernel [3,3,C,Co]) -> [nb,H,W,Co]; mode 1 weight gradient accumulated into
+  `out` [3,3,C,Co] from x and dy [nb,H,W,Co]; mode 2 data gradient of dy -> [nb,H,W,C].
+  Returns (result, status)."""
+  _check_f32(kernel, 'kernel')
+  c, co = int(kernel.shape[2]), int(kernel.shape[3])
+  ref = x if x is not None else dy
+  nb, h, w = int(ref.shape[0]), int(ref.shape[1]), int(ref.shape[2])
+  for t in (x, dy, bias):
+    if t is not None:
+      _check_f32(t, 'operand')
+  if out is None:
+    shape = {0: (nb, h, w, co), 1: (3, 3, c, co), 2: (nb, h, w, c)}[mode]
+    out = torch.zeros(shape, device=kernel.device, dtype=torch.float32)
+  st = ctypes.c_int32(-1)
+  _lib.check(_lib.load().ibc_conv3x3_tf32(_ptr(x), nb, h, w, c, _ptr(kernel), co, _ptr(bias),
+                                          int(relu), int(mode), _ptr(dy), _ptr(out),
+                                          ctypes.byref(st), _stream()))
+  return out, int(st.value)
+
+
 def umma_selftest(a: torch.Tensor, bt: torch.Tensor, mode: int = 0):
   """D = A[128,K] . Bt[N,K]^T through tcgen05; returns (D, status)."""
   _check_f32(a, 'A')

@@ -342,6 +342,18 @@ int ibc_gemm_tf32(const float* A, int64_t lda, int32_t trans_a, const float* B,
                   const float* res, int32_t relu_a, int32_t relu_out,
                   int32_t accumulate, int32_t* status_host, void* stream);
 
+/* The implicit-GEMM 3x3 'same' convolution of the ConvMaxpool encoder (Keras Conv2D,
+ * networks/layers/conv_maxpool.py:20-48) on its own, for parity tests: NHWC tensors,
+ * kernel K [3, 3, C, Co] in the Keras layout, tf32 operands, fp32 accumulation.
+ *   mode 0: out [nb, H, W, Co] = f(conv(X, K) + bias),  f = relu when `relu`
+ *   mode 1: out [3, 3, C, Co] += dK = im2col(X)^T . dY   (accumulates into out)
+ *   mode 2: out [nb, H, W, C]  = dX = conv(dY [nb, H, W, Co], K flipped and transposed)
+ * Waits for the result; status_host as in ibc_gemm_tf32. */
+int ibc_conv3x3_tf32(const float* X, int64_t nb, int32_t H, int32_t W, int32_t C,
+                     const float* K, int32_t Co, const float* bias, int32_t relu,
+                     int32_t mode, const float* dY, float* out, int32_t* status_host,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

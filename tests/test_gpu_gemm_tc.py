@@ -127,3 +127,51 @@ def test_pixel_engine_tf32_matches_its_fp32_path():
   e.set_precision(_lib.PRECISION_FP32)
   enc_f = e.encode(img)
   _close(enc_t, enc_f, TF32_TOL, 'encoder tf32 vs fp32')
+
+
+# ---- implicit 3x3 convolution (the A operand gathered from the NHWC tensor) --------------
+CONV_SHAPES = [
+    (2, 9, 13, 8, 32),        # vector path, ragged frame, BN = 32
+    (3, 22, 30, 64, 128),     # conv4-like
+    (1, 45, 60, 32, 64),      # conv2-like, odd height
+    (2, 7, 5, 6, 32),         # 6 channels: element-wise gather (un-padded first layer)
+    (1, 4, 6, 128, 256),      # frame smaller than a K-slice's row walk
+]
+
+
+def _conv_ref(x, k, bias=None, relu=False):
+  import torch.nn.functional as F
+  y = F.conv2d(round_tf32(x).double().permute(0, 3, 1, 2),
+               round_tf32(k).double().permute(3, 2, 0, 1), None, padding=1).permute(0, 2, 3, 1)
+  if bias is not None:
+    y = y + bias.double()
+  return y.clamp_min(0) if relu else y
+
+
+@pytest.mark.parametrize('nb,h,w,c,co', CONV_SHAPES)
+def test_implicit_convolution_forward_and_gradients(nb, h, w, c, co):
+  """Keras Conv2D(3x3, 'same') (conv_maxpool.py:20-48): forward with fused bias + ReLU, data
+  gradient (convolution with the flipped kernel) and weight gradient (split over rows,
+  accumulated) against PyTorch conv2d / autograd in fp64 on the tf32-rounded operands."""
+  from ibc_b200 import engine as eng
+  g = torch.Generator().manual_seed(nb * 1000 + h * 10 + c)
+  x = torch.randn(nb, h, w, c, generator=g)
+  k = torch.randn(3, 3, c, co, generator=g) * 0.1
+  bias = torch.randn(co, generator=g)
+  dy = torch.randn(nb, h, w, co, generator=g)
+  y, st = eng.conv3x3_tf32(x.cuda(), k.cuda(), bias=bias.cuda(), relu=True, mode=0)
+  assert st == 0
+  _close(y, _conv_ref(x, k, bias, relu=True), EXACT_TOL, 'forward')
+  # gradients of sum(conv(x, k) * dy) with every MMA operand rounded
+  xr = round_tf32(x).double().requires_grad_(True)
+  kr = round_tf32(k).double().requires_grad_(True)
+  import torch.nn.functional as F
+  yy = F.conv2d(xr.permute(0, 3, 1, 2), kr.permute(3, 2, 0, 1), None, padding=1).permute(0, 2, 3, 1)
+  gx, gk = torch.autograd.grad((yy * round_tf32(dy).double()).sum(), (xr, kr))
+  dk0 = torch.randn(3, 3, c, co, generator=g)
+  dk, st = eng.conv3x3_tf32(x.cuda(), k.cuda(), mode=1, dy=dy.cuda(), out=dk0.cuda().clone())
+  assert st == 0
+  _close(dk, dk0.double() + gk, 2 * EXACT_TOL, 'weight gradient')
+  dx, st = eng.conv3x3_tf32(None, k.cuda(), mode=2, dy=dy.cuda())
+  assert st == 0
+  _close(dx, gx, EXACT_TOL, 'data gradient')
