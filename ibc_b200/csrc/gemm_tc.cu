@@ -193,31 +193,27 @@ __device__ __forceinline__ float4 conv_scalar4(const GemmP& p, int pr, int kc, i
   if (kc + 3 < kclim) v.w = conv_elem(p, pr, kc + 3);
   return v;
 }
-// Walking state of one 16-byte piece (4 consecutive channels of one tap at one pixel):
-// the loader advances either the column (forward / data-gradient form: 32 columns per
-// stage) or the pixel row (weight-gradient form: 32 rows per stage) without divisions.
-struct ConvPiece {
-  int x, y;        // pixel
-  int tap, c;      // column = tap * C + c
-  int pr;          // pixel row index
-  bool ok;         // the fixed coordinate is inside the matrix
+// Vector gather (channel counts that are multiples of 4): everything that does not change
+// from slice to slice is worked out once per output block, so a piece costs a mask test, an
+// add and the copy (the first version re-derived taps, bounds and a 64-bit product per piece:
+// the large convolutions were bound by instruction issue, profiles/r1_ncu_full_pixel_step_gemms.csv).
+//   forward / data-gradient form (rows = pixels, K walks (tap, channel)): per piece the
+//     pixel's base pointer and a 9-bit mask of the taps that fall inside the frame; per
+//     thread the (tap, channel) of the slice -- all pieces of a thread share the K chunk;
+//   weight-gradient form (rows = (tap, channel), K walks pixels): per piece the tap's
+//     (dy, dx) and element offset, and a walking (x, y, row pointer).
+struct ConvRow {            // forward form, per piece
+  const float* pix;         // &X[pixel, 0]
+  uint32_t taps;            // bit t: tap t of this pixel is inside the frame (0: row outside M)
 };
-__device__ __forceinline__ ConvPiece conv_piece(const GemmP& p, int pr, int kc) {
-  ConvPiece s;
-  s.pr = pr;
-  s.x = pr % p.conv_W; s.y = (pr / p.conv_W) % p.conv_H;
-  s.tap = kc / p.conv_C; s.c = kc - s.tap * p.conv_C;
-  s.ok = true;
-  return s;
-}
-__device__ __forceinline__ void conv_issue4(uint32_t dst, const GemmP& p, const ConvPiece& s,
-                                            bool inside) {
-  const int ky = (s.tap * 11) >> 5, kx = s.tap - ky * 3;
-  const int yy = s.y + ky - 1, xx = s.x + kx - 1;
-  if (!inside || !s.ok || (unsigned)yy >= (unsigned)p.conv_H || (unsigned)xx >= (unsigned)p.conv_W)
-    cp_async16<true>(dst, p.A, 0u);
-  else   // neighbouring taps re-read the same pixels: keep them in L1
-    cp_async16<true>(dst, p.A + ((int64_t)s.pr + (ky - 1) * p.conv_W + (kx - 1)) * p.conv_C + s.c, 16u);
+struct ConvCol {            // weight-gradient form, per piece
+  const float* ptr;         // &X[pixel row of the current slice, 0] + tap / channel offset
+  int x, y, dy, dx;
+  bool ok;                  // the (tap, channel) column is inside the matrix
+};
+__device__ __forceinline__ uint32_t conv_tap_mask(int x, int y, int W, int H) {
+  const uint32_t colm = (x > 0 ? 1u : 0u) | 2u | (x < W - 1 ? 4u : 0u);
+  return (y > 0 ? colm : 0u) | (colm << 3) | (y < H - 1 ? colm << 6 : 0u);
 }
 
 // One output block of the persistent schedule.
@@ -305,7 +301,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(GemmP p, int* stat
     // form, pixel rows in the weight-gradient form).
     const float* pa_src[NA]; uint32_t pa_ok = 0, pa_fast = 0;
     const float* pb_src[NB]; uint32_t pb_ok = 0, pb_fast = 0;
-    ConvPiece cs[CONV ? NA : 1];
+    ConvRow crow[CONV && AKC ? NA : 1];
+    ConvCol ccol[CONV && !AKC ? NA : 1];
+    int ctap = 0, cch = 0;      // forward form: (tap, channel) of this thread's chunk in the next slice
     auto setup = [&](const TileCoord& c) {
       pa_ok = 0; pb_ok = 0; pa_fast = (avec && !CONV) ? 1u : 0u; pb_fast = bvec ? 1u : 0u;
 #pragma unroll
@@ -316,9 +314,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(GemmP p, int* stat
         if (!AKC && in && c.m0 + r + 4 > p.M) pa_fast = 0;       // ragged 16-byte piece
         if (in) pa_ok |= 1u << j;
         if (CONV) {
-          if (cvec) {
-            cs[j] = AKC ? conv_piece(p, c.m0 + r, c.kbeg + k) : conv_piece(p, c.kbeg + k, c.m0 + r);
-            cs[j].ok = in;
+          if (cvec && AKC) {
+            const int pr = c.m0 + r;
+            crow[j].pix = p.A + (int64_t)pr * p.conv_C;
+            crow[j].taps = in ? conv_tap_mask(pr % p.conv_W, (pr / p.conv_W) % p.conv_H,
+                                              p.conv_W, p.conv_H) : 0u;
+            const int kc0 = c.kbeg + k;                  // the same chunk for all of a thread's pieces
+            ctap = kc0 / p.conv_C; cch = kc0 - ctap * p.conv_C;
+          } else if (cvec) {
+            const int col = c.m0 + r, pr = c.kbeg + k;
+            const int tap = col / p.conv_C, ch = col - tap * p.conv_C;
+            const int ky = (tap * 11) >> 5, kx = tap - ky * 3;
+            ccol[j].dy = ky - 1; ccol[j].dx = kx - 1;
+            ccol[j].x = pr % p.conv_W; ccol[j].y = (pr / p.conv_W) % p.conv_H;
+            ccol[j].ptr = p.A + ((int64_t)pr + (ky - 1) * p.conv_W + (kx - 1)) * p.conv_C + ch;
+            ccol[j].ok = in;
           }
         } else {
           pa_src[j] = !in ? p.A
@@ -358,17 +368,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(GemmP p, int* stat
           piece<AKC, kBM>(j * kLoaderThreads + tid, r, k);
           const uint32_t dst = sa + pa_dst[j];
           if (CONV) {
-            if (cvec) {
-              conv_issue4(dst, p, cs[j], k0 + k < c.kend);
-              if (AKC) {          // next slice: 32 columns further
-                cs[j].c += kBK;
-                while (cs[j].c >= p.conv_C) { cs[j].c -= p.conv_C; ++cs[j].tap; }
-              } else {            // next slice: 32 pixel rows further
-                cs[j].pr += kBK; cs[j].x += kBK;
-                while (cs[j].x >= p.conv_W) {
-                  cs[j].x -= p.conv_W;
-                  if (++cs[j].y == p.conv_H) cs[j].y = 0;
-                }
+            if (cvec && AKC) {
+              const bool ok = (k0 + k < c.kend) && ((crow[j].taps >> ctap) & 1u);
+              const int ky = (ctap * 11) >> 5, kx = ctap - ky * 3;
+              const int off = ((ky - 1) * p.conv_W + (kx - 1)) * p.conv_C + cch;
+              cp_async16<true>(dst, ok ? crow[j].pix + off : p.A, ok ? 16u : 0u);
+            } else if (cvec) {
+              ConvCol& q = ccol[j];
+              const bool ok = q.ok && (k0 + k < c.kend) &&
+                              (unsigned)(q.y + q.dy) < (unsigned)p.conv_H &&
+                              (unsigned)(q.x + q.dx) < (unsigned)p.conv_W;
+              cp_async16<true>(dst, ok ? q.ptr : p.A, ok ? 16u : 0u);
+              q.ptr += (int64_t)kBK * p.conv_C;       // next slice: 32 pixel rows further
+              q.x += kBK;
+              while (q.x >= p.conv_W) {
+                q.x -= p.conv_W;
+                if (++q.y == p.conv_H) q.y = 0;
               }
             } else {
               st_shared16(dst, AKC ? conv_scalar4(p, c.m0 + r, k0 + k, p.M, c.kend)
@@ -377,6 +392,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(GemmP p, int* stat
           } else {
             issue4<AKC>(dst, p.A, p.lda, c.m0 + r, k0 + k, p.M, c.kend, avec);
           }
+        }
+        if (CONV && AKC && cvec) {       // next slice: 32 columns further
+          cch += kBK;
+          while (cch >= p.conv_C) { cch -= p.conv_C; ++ctap; }
         }
       }
       if (!has_b) {
