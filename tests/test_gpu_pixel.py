@@ -30,6 +30,11 @@ def _close(got, want, tol, name=''):
   assert worst <= 1.0, '%s: err/bound %.3g (rms %.3g)' % (name, worst, rms)
 
 
+# value head 128 wide: the width from which the fused action-projection kernels of the tf32
+# path (act_rows_kernel / act_rows_bwd_kernel, 128-column blocks) take over
+WIDE = opix.PixelSpec(seq_len=2, height=40, width=56, channels=3, target_height=32,
+                      target_width=48, act_dim=2, value_width=128, value_blocks=1)
+
 PRECISIONS = ['fp32', 'tf32']
 ACT_TOL = {'fp32': 1e-4, 'tf32': 3e-3}
 GRAD_TOL = {'fp32': 2e-3, 'tf32': 5e-3}
@@ -80,9 +85,11 @@ def test_value_energy_matches_oracle(b, n, precision):
 
 
 @pytest.mark.parametrize('precision', PRECISIONS)
-@pytest.mark.parametrize('b,n', [(4, 7), (6, 40)])
-def test_train_grads_match_oracle_autograd(b, n, precision):
+@pytest.mark.parametrize('spec,b,n', [(SMALL, 4, 7), (SMALL, 6, 40), (WIDE, 5, 33)],
+                         ids=['small-4-7', 'small-6-40', 'wide-5-33'])
+def test_train_grads_match_oracle_autograd(spec, b, n, precision):
   from ibc_b200 import engine as eng
+  SMALL = spec          # noqa: N806  (the body below is written against one spec)
   e, flat = _engine(SMALL, precision=precision)
   img = _images(SMALL, b, seed=3)
   g = torch.Generator().manual_seed(4)
