@@ -233,6 +233,11 @@ __global__ void act_rows_bwd_kernel(const float* __restrict__ G, const float* __
   }
 }
 
+__global__ void add_rows_kernel(float* __restrict__ a, const float* __restrict__ b, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += b[i];
+}
+
 // out[i] = tf32(in[i]): the weights as MMA operands (rounded once per call instead of
 // in every block of every product that reads them)
 __global__ void round_copy_kernel(const float* __restrict__ in, int64_t n, float* __restrict__ out) {
@@ -706,6 +711,154 @@ int value_bwd(ibc_pixel_handle* ph, const PixelLayout& L, const float* enc, int6
   return IBC_OK;
 }
 
+// ---- value head: dE/dact and the gradient penalty ---------------------------------------------
+// The ones-seeded reverse chain of the value head (mcmc.gradient_wrt_act on a late-fusion
+// PixelEBM, mcmc.py:161-191): G_L = w1 in every row, then per block (last to first)
+//   g1 = (G . D2^T) (.) (y1 > 0),  g0 = (g1 . D1^T) (.) (y0 > 0),  G' = G + (g0 . D0^T) (.) (x > 0)
+// and dE/dact = G_0 . W0[256:]^T.  With `keep` every level is kept for the tangent pass of
+// the gradient penalty; without it two levels ping-pong.
+struct ValRev {
+  float* G = nullptr;    // [levels, R, Wv]
+  float* g0 = nullptr;   // [blocks kept, R, Wq]
+  float* g1 = nullptr;
+  int64_t R = 0;
+  int Wv = 0, Wq = 0;
+  bool keep = false;
+  float* Gl(int j) const { return G + (int64_t)(keep ? j : (j & 1)) * R * Wv; }
+  float* q0(int j) const { return g0 + (int64_t)(keep ? j : 0) * R * Wq; }
+  float* q1(int j) const { return g1 + (int64_t)(keep ? j : 0) * R * Wq; }
+};
+
+size_t val_rev_bytes(const PixelLayout& L, int64_t R, bool keep) {
+  const int lv = keep ? L.nblk + 1 : 2, lq = keep ? (L.nblk > 0 ? L.nblk : 1) : 1;
+  return Workspace::rounded((size_t)lv * R * L.Wv * 4) +
+         2 * Workspace::rounded((size_t)lq * R * L.Wq * 4);
+}
+
+void carve_val_rev(ibc_handle* h, const PixelLayout& L, int64_t R, bool keep, ValRev* r) {
+  const int lv = keep ? L.nblk + 1 : 2, lq = keep ? (L.nblk > 0 ? L.nblk : 1) : 1;
+  r->R = R; r->Wv = L.Wv; r->Wq = L.Wq; r->keep = keep;
+  r->G = h->ws.take<float>((size_t)lv * R * L.Wv);
+  r->g0 = h->ws.take<float>((size_t)lq * R * L.Wq);
+  r->g1 = h->ws.take<float>((size_t)lq * R * L.Wq);
+}
+
+// dEda [R, A] = +dE/dact for the rows value_fwd has just evaluated into `v`.
+int value_dact(ibc_pixel_handle* ph, const PixelLayout& L, const ValSave& v, const ValRev& rv,
+               float* dEda, cudaStream_t s) {
+  ibc_handle* h = &ph->core;
+  const float* P = ph->params;
+  const int Wv = L.Wv, Wq = L.Wq;
+  const int64_t R = v.R;
+  const bool tc = h->precision == IBC_PRECISION_TF32;
+  const float* PB = tc ? v.wr : P;   // rounded by value_fwd earlier in the same call
+  IBC_TRY(rowfill(h, P + L.d1_w, nullptr, R, Wv, rv.Gl(L.nblk), s));
+  for (int j = L.nblk - 1; j >= 0; --j) {
+    const float* G = rv.Gl(j + 1);
+    GemmP a1;  // g1 = (G . D2^T) (.) (y1 > 0)
+    a1.A = G; a1.lda = Wv; a1.B = PB + L.b_d2w(j); a1.ldb = Wv; a1.b_tf32 = tc;
+    a1.C = rv.q1(j); a1.ldc = Wq; a1.gateC = v.Y1 + (int64_t)j * R * Wq; a1.ldgc = Wq;
+    a1.M = (int)R; a1.N = Wq; a1.K = Wv;
+    IBC_TRY(pgemm(h, a1, false, true, s));
+    GemmP a0;  // g0 = (g1 . D1^T) (.) (y0 > 0)
+    a0.A = rv.q1(j); a0.lda = Wq; a0.B = PB + L.b_d1w(j); a0.ldb = Wq; a0.b_tf32 = tc;
+    a0.C = rv.q0(j); a0.ldc = Wq; a0.gateC = v.Y0 + (int64_t)j * R * Wq; a0.ldgc = Wq;
+    a0.M = (int)R; a0.N = Wq; a0.K = Wq;
+    IBC_TRY(pgemm(h, a0, false, true, s));
+    GemmP ax;  // G' = G + (g0 . D0^T) (.) (x > 0)
+    ax.A = rv.q0(j); ax.lda = Wq; ax.B = PB + L.b_d0w(j); ax.ldb = Wq; ax.b_tf32 = tc;
+    ax.C = rv.Gl(j); ax.ldc = Wv; ax.gateC = v.X + (int64_t)j * R * Wv; ax.ldgc = Wv;
+    ax.res = G; ax.ldres = Wv; ax.M = (int)R; ax.N = Wv; ax.K = Wq;
+    IBC_TRY(pgemm(h, ax, false, true, s));
+  }
+  GemmP g;  // dE/dact = G_0 . W0[256:]^T   (N = act_dim: a bandwidth-bound pass over G_0)
+  g.A = rv.Gl(0); g.lda = Wv; g.B = P + L.d0_w + (int64_t)kEnc * Wv; g.ldb = Wv;
+  g.C = dEda; g.ldc = L.A; g.M = (int)R; g.N = L.A; g.K = Wv;
+  return gemm(h, g, false, true, s);
+}
+
+// gradient_loss.grad_penalty on the late-fusion PixelEBM (gradient_loss.py:35-72 through
+// PixelEBM.call without a prior encoding, pixel_ebm.py:107-114): dE/dact at the combined
+// actions, the penalty per observation (added to per_example) and its parameter gradients
+// (accumulated into grads).  dE/dact depends on the parameters of the value head only --
+// on the encoding, the biases and the encoder only through the ReLU masks -- so the
+// gradient is a fixed-mask tangent pass T through the blocks (first to last):
+//   T_0 = cot . W0[256:],                      dW0[256:] += cot^T . G_0
+//   S0 = ((T (.) mx) . D0) (.) m0,             dD0 += (T (.) mx)^T . g0
+//   S1 = (S0 . D1) (.) m1,                     dD1 += S0^T . g1
+//   T' = T + S1 . D2,                          dD2 += S1^T . G_{j+1}
+//   dw1 += sum_r T_L
+int value_grad_penalty(ibc_pixel_handle* ph, const PixelLayout& L, int64_t B, int64_t n1,
+                       const ValSave& v, const ibc_loss_cfg& c, float gscale, float* per_example,
+                       float* grad_loss_out, float* grads, cudaStream_t s) {
+  ibc_handle* h = &ph->core;
+  const float* P = ph->params;
+  const int Wv = L.Wv, Wq = L.Wq, A = L.A;
+  const int64_t R = B * n1;
+  const bool tc = h->precision == IBC_PRECISION_TF32;
+  const float* PB = tc ? v.wr : P;
+  ValRev rv;
+  carve_val_rev(h, L, R, true, &rv);
+  float* dEda = h->ws.take<float>((size_t)R * A);
+  float* cot = h->ws.take<float>((size_t)R * A);
+  float* gl = h->ws.take<float>((size_t)B);
+  float* Ta = h->ws.take<float>((size_t)R * Wv);
+  float* Tb = h->ws.take<float>((size_t)R * Wv);
+  float* S0 = h->ws.take<float>((size_t)R * Wq);
+  float* S1 = h->ws.take<float>((size_t)R * Wq);
+  IBC_TRY(value_dact(ph, L, v, rv, dEda, s));
+  IBC_TRY(grad_penalty_from_dact(h, dEda, B, n1, A, c, gscale, gl, cot, s));
+  add_rows_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(per_example, gl, B);
+  IBC_LAUNCH_CHECK(h);
+  if (grad_loss_out)
+    IBC_CUDA(h, cudaMemcpyAsync(grad_loss_out, gl, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
+  const float* Wa = P + L.d0_w + (int64_t)kEnc * Wv;
+  {  // T_0 = cot . Wa
+    GemmP g;
+    g.A = cot; g.lda = A; g.B = Wa; g.ldb = Wv; g.C = Ta; g.ldc = Wv;
+    g.M = (int)R; g.N = Wv; g.K = A;
+    IBC_TRY(pgemm(h, g, false, false, s));
+  }
+  IBC_TRY(dwg(h, cot, A, AOP_ID, rv.Gl(0), Wv, R, A, Wv, grads + L.d0_w + (int64_t)kEnc * Wv, s));
+  float* T = Ta;
+  for (int j = 0; j < L.nblk; ++j) {
+    float* Tn = (T == Ta) ? Tb : Ta;
+    const float* x = v.X + (int64_t)j * R * Wv;
+    const float* y0 = v.Y0 + (int64_t)j * R * Wq;
+    const float* y1 = v.Y1 + (int64_t)j * R * Wq;
+    GemmP s0;  // S0 = ((T (.) mx) . D0) (.) m0
+    s0.A = T; s0.lda = Wv; s0.aop = AOP_GATE; s0.gateA = x; s0.B = PB + L.b_d0w(j); s0.ldb = Wq;
+    s0.b_tf32 = tc; s0.C = S0; s0.ldc = Wq; s0.gateC = y0; s0.ldgc = Wq;
+    s0.M = (int)R; s0.N = Wq; s0.K = Wv;
+    IBC_TRY(pgemm(h, s0, false, false, s));
+    {  // dD0 += (T (.) mx)^T . g0
+      GemmP g;
+      g.A = T; g.lda = Wv; g.aop = AOP_GATE; g.gateA = x; g.B = rv.q0(j); g.ldb = Wq;
+      g.C = grads + L.b_d0w(j); g.ldc = Wq; g.M = Wv; g.N = Wq; g.K = (int)R;
+      g.k_chunk = 1024; g.atomic = 1;
+      IBC_TRY(pgemm(h, g, true, false, s));
+    }
+    GemmP s1;  // S1 = (S0 . D1) (.) m1
+    s1.A = S0; s1.lda = Wq; s1.B = PB + L.b_d1w(j); s1.ldb = Wq; s1.b_tf32 = tc;
+    s1.C = S1; s1.ldc = Wq; s1.gateC = y1; s1.ldgc = Wq; s1.M = (int)R; s1.N = Wq; s1.K = Wq;
+    IBC_TRY(pgemm(h, s1, false, false, s));
+    IBC_TRY(dwg(h, S0, Wq, AOP_ID, rv.q1(j), Wq, R, Wq, Wq, grads + L.b_d1w(j), s));
+    IBC_TRY(dwg(h, S1, Wq, AOP_ID, rv.Gl(j + 1), Wv, R, Wq, Wv, grads + L.b_d2w(j), s));
+    GemmP t;  // T' = T + S1 . D2
+    t.A = S1; t.lda = Wq; t.B = PB + L.b_d2w(j); t.ldb = Wv; t.b_tf32 = tc;
+    t.C = Tn; t.ldc = Wv; t.res = T; t.ldres = Wv; t.M = (int)R; t.N = Wv; t.K = Wq;
+    IBC_TRY(pgemm(h, t, false, false, s));
+    T = Tn;
+  }
+  return colsum_add(h, T, Wv, R, Wv, grads + L.d1_w, s);
+}
+
+size_t val_gp_bytes(const PixelLayout& L, int64_t B, int64_t R) {
+  return val_rev_bytes(L, R, true) + 2 * Workspace::rounded((size_t)R * L.A * 4) +
+         Workspace::rounded((size_t)B * 4) + 2 * Workspace::rounded((size_t)R * L.Wv * 4) +
+         2 * Workspace::rounded((size_t)R * L.Wq * 4);
+}
+
 int check_arch(ibc_handle* h, const ibc_pixel_arch& a) {
   if (a.seq_len < 1 || a.height < 1 || a.width < 1 || a.channels < 1 || a.act_dim < 1 ||
       a.value_width < 4 || a.value_width % 4 || a.value_blocks < 0)
@@ -866,18 +1019,85 @@ int ibc_pixel_dfo(ibc_pixel_handle* ph, const float* enc, int64_t B, float* acti
                      num_iterations, iteration_std, uniforms, normals, seed, probs, energy_fn, s);
 }
 
+int ibc_pixel_energy_dact(ibc_pixel_handle* ph, const float* enc, int64_t B, const float* act,
+                          int64_t n, float* energy, float* dE_dact, void* stream) {
+  PIX_ENTER(ph);
+  if (!enc || !act || !energy || !dE_dact || B < 1 || n < 1)
+    IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_energy_dact: bad argument");
+  if (!ph->params) IBC_FAIL(h, IBC_ERR_INVALID, "no parameters bound (ibc_pixel_bind_params)");
+  const PixelLayout L = make_pixel_layout(ph->arch);
+  const int64_t R = B * n;
+  IBC_CUDA(h, h->ws.reserve(val_bytes(L, B, R) + val_rev_bytes(L, R, false)));
+  h->ws.reset();
+  ValSave v;
+  carve_val(h, L, B, R, &v);
+  ValRev rv;
+  carve_val_rev(h, L, R, false, &rv);
+  IBC_TRY(value_fwd(ph, L, enc, B, act, n, v, energy, (cudaStream_t)stream));
+  return value_dact(ph, L, v, rv, dE_dact, (cudaStream_t)stream);
+}
+
+int ibc_pixel_langevin(ibc_pixel_handle* ph, const float* enc, int64_t B, float* actions, int64_t n,
+                       const float* min_actions, const float* max_actions,
+                       const ibc_langevin_cfg* cfg, const float* normals, uint64_t seed,
+                       float* chain_actions, float* chain_energies, float* chain_grad_norms,
+                       void* stream) {
+  PIX_ENTER(ph);
+  if (!enc || !actions || !min_actions || !max_actions || !cfg || B < 1 || n < 1)
+    IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_langevin: bad argument");
+  if (!ph->params) IBC_FAIL(h, IBC_ERR_INVALID, "no parameters bound (ibc_pixel_bind_params)");
+  if (cfg->num_iterations < 0) IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_langevin: num_iterations < 0");
+  if (cfg->grad_norm_type < IBC_NORM_NONE || cfg->grad_norm_type > IBC_NORM_INF)
+    IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_langevin: unknown grad_norm_type %d",
+             cfg->grad_norm_type);
+  if (cfg->apply_exp)
+    IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "ibc_pixel_langevin: apply_exp is not built (no gin sets it)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const PixelLayout L = make_pixel_layout(ph->arch);
+  const int A = L.A;
+  const int64_t R = B * n;
+  std::vector<float> steps;
+  langevin_stepsizes(*cfg, &steps);
+  IBC_CUDA(h, h->ws.reserve(val_bytes(L, B, R) + val_rev_bytes(L, R, false) +
+                            2 * Workspace::rounded((size_t)R * 4) +
+                            Workspace::rounded((size_t)R * A * 4)));
+  for (int k = 0; k < cfg->num_iterations; ++k) {
+    h->ws.reset();
+    ValSave v;
+    carve_val(h, L, B, R, &v);
+    ValRev rv;
+    carve_val_rev(h, L, R, false, &rv);
+    float* E = h->ws.take<float>(R);
+    float* nrm = h->ws.take<float>(R);
+    float* dEda = h->ws.take<float>((size_t)R * A);
+    float* Ek = chain_energies ? chain_energies + (int64_t)k * R : E;
+    float* Nk = chain_grad_norms ? chain_grad_norms + (int64_t)k * R : nrm;
+    IBC_TRY(value_fwd(ph, L, enc, B, actions, n, v, Ek, s));
+    IBC_TRY(value_dact(ph, L, v, rv, dEda, s));
+    IBC_TRY(langevin_update(h, actions, dEda, R, A, normals ? normals + (int64_t)k * R * A : nullptr,
+                            seed, (uint64_t)k + 1, cfg->noise_scale, cfg->grad_clip,
+                            cfg->delta_action_clip, steps[k], min_actions, max_actions,
+                            cfg->grad_norm_type, Nk, s));
+    if (chain_actions)   // post-step actions (update_chain_data, mcmc.py:297-327)
+      IBC_CUDA(h, cudaMemcpyAsync(chain_actions + (int64_t)k * R * A, actions, (size_t)R * A * 4,
+                                  cudaMemcpyDeviceToDevice, s));
+  }
+  return IBC_OK;
+}
+
 int ibc_pixel_train_grads(ibc_pixel_handle* ph, const void* images, int32_t is_uint8, int64_t B,
                           const float* actions, int64_t N, const ibc_loss_cfg* cfg,
-                          int64_t global_batch, float* per_example_loss, float* energies,
-                          float* grads, void* stream) {
+                          int64_t global_batch, float* per_example_loss, float* grad_loss,
+                          float* energies, float* grads, void* stream) {
   PIX_ENTER(ph);
   if (!images || !actions || !cfg || !per_example_loss || !grads || B < 1 || N < 0 ||
       global_batch < 1)
     IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_train_grads: bad argument");
   if (!ph->params) IBC_FAIL(h, IBC_ERR_INVALID, "no parameters bound (ibc_pixel_bind_params)");
-  if (cfg->add_grad_penalty)
-    IBC_FAIL(h, IBC_ERR_UNSUPPORTED,
-             "gradient penalty for PixelEBM is not built (pixel_ebm_best.gin trains without it)");
+  if (cfg->grad_norm_type < IBC_NORM_NONE || cfg->grad_norm_type > IBC_NORM_INF)
+    IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_train_grads: unknown grad_norm_type %d",
+             cfg->grad_norm_type);
+  const bool gp = cfg->add_grad_penalty != 0 && cfg->grad_norm_type != IBC_NORM_NONE;
   cudaStream_t s = (cudaStream_t)stream;
   const PixelLayout L = make_pixel_layout(ph->arch);
   const EncDims d = enc_dims(ph->arch);
@@ -892,6 +1112,7 @@ int ibc_pixel_train_grads(ibc_pixel_handle* ph, const void* images, int32_t is_u
                  2 * Workspace::rounded((size_t)R * L.Wq * 4) +
                  Workspace::rounded((size_t)B * L.Wv * 4) + 2 * Workspace::rounded((size_t)B * kEnc * 4) +
                  2 * Workspace::rounded((size_t)R * 4) + (1 << 16);
+  if (gp) bytes += val_gp_bytes(L, B, R);
   IBC_CUDA(h, h->ws.reserve(bytes));
   h->ws.reset();
   EncSave sv;
@@ -913,6 +1134,12 @@ int ibc_pixel_train_grads(ibc_pixel_handle* ph, const void* images, int32_t is_u
                    per_example_loss, dE, s));
   IBC_TRY(value_bwd(ph, L, enc, B, actions, n1, v, dE, grads, dEnc, s));
   IBC_TRY(encode_bwd(ph, L, B, sv, dEnc, grads, dA, dB, s));
+  if (gp) {
+    IBC_TRY(value_grad_penalty(ph, L, B, n1, v, *cfg, 1.0f / (float)global_batch,
+                               per_example_loss, grad_loss, grads, s));
+  } else if (grad_loss) {
+    IBC_CUDA(h, cudaMemsetAsync(grad_loss, 0, (size_t)B * 4, s));
+  }
   return IBC_OK;
 }
 

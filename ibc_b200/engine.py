@@ -319,8 +319,52 @@ class PixelEngine:
                                       int(seed), _ptr(probs), _stream()), self._h, pixel=True)
     return probs
 
+  def energy_dact(self, enc: torch.Tensor, act: torch.Tensor, n: int):
+    """(energies [B*n], +dE/dact [B*n, A]) of the value head on an un-tiled encoding."""
+    _check_f32(enc, 'enc')
+    _check_f32(act, 'act')
+    b = enc.shape[0]
+    if enc.shape[1] != 256 or tuple(act.shape) != (b * n, self.act_dim):
+      raise ValueError('enc must be [B, 256] and act [B*n, A]')
+    e = torch.empty(b * n, device=enc.device, dtype=torch.float32)
+    g = torch.empty(b * n, self.act_dim, device=enc.device, dtype=torch.float32)
+    _lib.check(self.lib.ibc_pixel_energy_dact(self._h, _ptr(enc), b, _ptr(act), n, _ptr(e),
+                                              _ptr(g), _stream()), self._h, pixel=True)
+    return e, g
+
+  def langevin(self, enc, actions, n, min_actions, max_actions, cfg: LangevinCfg,
+               normals=None, seed=0, return_chain=False):
+    """Late-fusion Langevin chain, in place on `actions`; returns
+    (chain_actions, energies, grad_norms) or None."""
+    _check_f32(enc, 'enc')
+    _check_f32(actions, 'actions')
+    _check_f32(min_actions, 'min_actions')
+    _check_f32(max_actions, 'max_actions')
+    b = enc.shape[0]
+    if enc.shape[1] != 256 or tuple(actions.shape) != (b * n, self.act_dim):
+      raise ValueError('enc must be [B, 256] and actions [B*n, A]')
+    r, k = b * n, cfg.num_iterations
+    if normals is not None:
+      _check_f32(normals, 'normals')
+      if normals.numel() != k * r * self.act_dim:
+        raise ValueError('normals must have K*B*n*A elements')
+    ca = ce = cg = None
+    if return_chain:
+      ca = torch.empty(k, r, self.act_dim, device=enc.device, dtype=torch.float32)
+      ce = torch.empty(k, r, device=enc.device, dtype=torch.float32)
+      cg = torch.empty(k, r, device=enc.device, dtype=torch.float32)
+    _lib.check(self.lib.ibc_pixel_langevin(self._h, _ptr(enc), b, _ptr(actions), n,
+                                           _ptr(min_actions), _ptr(max_actions),
+                                           ctypes.byref(cfg), _ptr(normals), int(seed),
+                                           _ptr(ca), _ptr(ce), _ptr(cg), _stream()),
+               self._h, pixel=True)
+    return (ca, ce, cg) if return_chain else None
+
   def train_grads(self, images, actions, num_counter_examples, cfg: LossCfg, global_batch,
-                  grads: Optional[torch.Tensor] = None, want_energies=False):
+                  grads: Optional[torch.Tensor] = None, want_energies=False,
+                  want_grad_loss=False):
+    """Returns (per_example_loss [B], energies or None, grads), or with
+    want_grad_loss (per_example_loss, grad_loss [B], energies or None, grads)."""
     b, is_u8 = self._check_images(images)
     n1 = num_counter_examples + 1
     _check_f32(actions, 'actions')
@@ -330,11 +374,15 @@ class PixelEngine:
       grads = torch.empty(self.param_count, device=images.device, dtype=torch.float32)
     per_example = torch.empty(b, device=images.device, dtype=torch.float32)
     energies = torch.empty(b * n1, device=images.device, dtype=torch.float32) if want_energies else None
+    grad_loss = torch.empty(b, device=images.device, dtype=torch.float32) if want_grad_loss else None
     _lib.check(self.lib.ibc_pixel_train_grads(self._h, _ptr(images), is_u8, b, _ptr(actions),
                                               int(num_counter_examples), ctypes.byref(cfg),
                                               int(global_batch), _ptr(per_example),
-                                              _ptr(energies), _ptr(grads), _stream()),
+                                              _ptr(grad_loss), _ptr(energies), _ptr(grads),
+                                              _stream()),
                self._h, pixel=True)
+    if want_grad_loss:
+      return per_example, grad_loss, energies, grads
     return per_example, energies, grads
 
 

@@ -117,11 +117,6 @@ class ImplicitBCAgent(BehavioralCloningAgent):
       raise ValueError('Unsupported EBM loss type.')                 # ibc_agent.py:336
     if late_fusion != isinstance(cloning_network, PixelEBM):
       raise NotImplementedError('late_fusion must be used with (and only with) PixelEBM')
-    if late_fusion and (fraction_dfo_samples > 0. or fraction_langevin_samples > 0.
-                        or add_grad_penalty):
-      raise NotImplementedError(
-          'late-fusion training is built for uniform counter-examples without gradient '
-          'penalty (pushing_pixels/pixel_ebm_best.gin)')
     self._run_full_chain_under_gradient = run_full_chain_under_gradient
     self._return_full_chain = return_full_chain
     self._add_grad_penalty = add_grad_penalty
@@ -204,6 +199,18 @@ class ImplicitBCAgent(BehavioralCloningAgent):
           counter_example_actions, expanded_actions,
           1.0 / (float(global_batch) * counter_example_actions.shape[1]
                  * counter_example_actions.shape[2]))
+    self._chain_metrics(chain_data, losses_dict)
+    self.last_losses_dict = losses_dict
+    if training:
+      if raw is not None:   # chain dL/dW_bar through the spectral normalisation
+        (graw,) = torch.autograd.grad(eff, raw, grad_outputs=grads)
+        grads.copy_(graw)
+      return specs.LossInfo(total_loss, ()), grads
+    return losses_dict
+
+  @staticmethod
+  def _chain_metrics(chain_data, losses_dict):
+    """ibc_agent.py:263-280: logged averages over the training-time chain."""
     if chain_data is not None and chain_data.energies is not None:
       e = chain_data.energies
       losses_dict['overall_energies_avg'] = e.mean()
@@ -214,13 +221,6 @@ class ImplicitBCAgent(BehavioralCloningAgent):
       losses_dict['overall_grad_norms_avg'] = g.mean()
       losses_dict['first_grad_norms_avg'] = g[0].mean()
       losses_dict['final_grad_norms_avg'] = g[-1].mean()
-    self.last_losses_dict = losses_dict
-    if training:
-      if raw is not None:   # chain dL/dW_bar through the spectral normalisation
-        (graw,) = torch.autograd.grad(eff, raw, grad_outputs=grads)
-        grads.copy_(graw)
-      return specs.LossInfo(total_loss, ()), grads
-    return losses_dict
 
   def _loss_late_fusion(self, experience, training, draws):
     """ibc_agent.py:191-213: encode once (training=True), tile the encoding N+1
@@ -233,18 +233,18 @@ class ImplicitBCAgent(BehavioralCloningAgent):
     batch_size = images.shape[0]
     n = self._num_counter_examples
     expanded_actions = actions[:, None, :]
-    a_dim = actions.shape[-1]
-    u = draws.get('uniform_u')
-    counter = eng.uniform_actions(batch_size * n, self._min, self._max,
-                                  None if u is None else u.reshape(batch_size * n, a_dim)
-                                  .contiguous(), mcmc._next_seed()).view(batch_size, n, a_dim)
-    combined = torch.cat([counter, expanded_actions], dim=1).reshape(
-        batch_size * (n + 1), a_dim).contiguous()
+    # negatives: uniform, optionally refined by DFO / Langevin on the value head over one
+    # encoding of the un-tiled observations (ibc_agent.py:340-475 with late fusion)
+    counter, combined, chain_data = self._make_counter_example_actions(
+        images, expanded_actions, batch_size, training, draws)
     global_batch = batch_size * self._num_replicas()
-    per_example, _, grads = net.engine.train_grads(images, combined, n, self._loss_cfg(),
-                                                   global_batch, self._grads)
+    per_example, grad_loss, _, grads = net.engine.train_grads(
+        images, combined, n, self._loss_cfg(), global_batch, self._grads, want_grad_loss=True)
     total_loss = _scaled_sum(per_example, 1.0 / float(global_batch))
     losses_dict = {'ebm_total_loss': total_loss}
+    if self._add_grad_penalty:
+      losses_dict['grad_loss'] = grad_loss.mean()
+    self._chain_metrics(chain_data, losses_dict)
     if self._compute_mse:
       losses_dict['mse_counter_examples'] = _scaled_sq_diff_sum(
           counter, expanded_actions,
@@ -266,7 +266,8 @@ class ImplicitBCAgent(BehavioralCloningAgent):
   # -- negatives (ibc_agent.py:340-475) -----------------------------------------------
   def _make_counter_example_actions(self, obs_flat, expanded_actions, batch_size,
                                     training=False, draws=None):
-    """obs_flat [B, O] (un-tiled), expanded_actions [B, 1, A].  Returns
+    """obs_flat [B, O] (un-tiled; the frames [B, T, H, W, C] with late fusion),
+    expanded_actions [B, 1, A].  Returns
     (counter_example_actions [B, N, A], combined [B*(N+1), A], chain_data)."""
     del training   # sampler network calls always use training=False (:388, :403)
     draws = draws or {}
@@ -286,15 +287,19 @@ class ImplicitBCAgent(BehavioralCloningAgent):
         if self._return_full_chain:
           raise NotImplementedError('Not implemented to return dfo chain.')   # :374-375
         dfo_actions = random_uniform.clone()
-        net.engine.dfo(obs_flat, dfo_actions, n, self._min, self._max, 1.0, 3, 0.33,
+        dfo_obs = net.encode(obs_flat, training=False) if self._late_fusion else obs_flat
+        net.engine.dfo(dfo_obs, dfo_actions, n, self._min, self._max, 1.0, 3, 0.33,
                        draws.get('dfo_uniforms'), draws.get('dfo_normals'), mcmc._next_seed())
       if self._fraction_langevin_samples > 0.:
-        tiled = torch.repeat_interleave(obs_flat, n, dim=0)
+        # late fusion: un-tiled frames, encoded once inside the sampler (mcmc.py:384-388;
+        # upstream binds langevin_actions_given_obs.late_fusion in the gin file)
+        tiled = obs_flat if self._late_fusion else torch.repeat_interleave(obs_flat, n, dim=0)
+        lf = {'late_fusion': True} if self._late_fusion else {}
         out = mcmc.langevin_actions_given_obs(
             net, tiled, random_uniform, policy_state=(), min_actions=self._min,
             max_actions=self._max, num_action_samples=n, training=False,
             return_chain=self._return_full_chain, grad_norm_type=self._grad_norm_type,
-            normal_draws=draws.get('langevin_normals'))
+            normal_draws=draws.get('langevin_normals'), **lf)
         if self._return_full_chain:
           lang_actions, chain_data = out
         else:

@@ -157,6 +157,19 @@ def gradient_wrt_act(energy_network,
     act = actions.to(torch.float32).contiguous()
     e, g = energy_network.engine.energy_dact(obs, act, 1)
     return -g, e
+  if isinstance(energy_network, PixelEBM) and not apply_exp:
+    # late fusion: the value head on a prior encoding (pixel_ebm.py:113-125); without one
+    # the network encodes and tiles itself (pixel_ebm.py:107-112, gradient_loss.py:38-45)
+    act = actions.to(energy_network.device, torch.float32).contiguous()
+    if obs_encoding is None:
+      enc = energy_network.encode(observations, training)
+      e, g = energy_network.engine.energy_dact(enc, act, act.shape[0] // enc.shape[0])
+    else:
+      enc = obs_encoding.to(energy_network.device, torch.float32).contiguous()
+      if enc.shape[0] != act.shape[0]:
+        raise ValueError('observation_encoding must be tiled to the actions')
+      e, g = energy_network.engine.energy_dact(enc, act, 1)
+    return -g, e
   a = actions.detach().clone().requires_grad_(True)
   with torch.enable_grad():
     if obs_encoding is not None:
@@ -302,6 +315,22 @@ def langevin_actions_given_obs(
                            apply_exp)
     obs = _untile(energy_network._flat_obs(observations), r // n, n)
     chain = energy_network.engine.langevin(obs, actions, n, min_actions, max_actions, cfg,
+                                           normal_draws, seed, return_chain)
+    if return_chain:
+      return actions, ChainData(*chain)
+    return actions
+
+  if isinstance(energy_network, PixelEBM) and late_fusion and not apply_exp:
+    # encode once, then the whole chain on the value head (mcmc.py:384-388)
+    cfg = eng.langevin_cfg(num_iterations, sampler_stepsize_init, sampler_stepsize_decay,
+                           noise_scale, grad_clip, delta_action_clip, use_polynomial_rate,
+                           sampler_stepsize_final, sampler_stepsize_power, grad_norm_type,
+                           apply_exp)
+    enc = energy_network.encode(observations, training=training)
+    if enc.shape[0] * n != r:
+      raise ValueError('late fusion expects un-tiled observations: %d x %d != %d'
+                       % (enc.shape[0], n, r))
+    chain = energy_network.engine.langevin(enc, actions, n, min_actions, max_actions, cfg,
                                            normal_draws, seed, return_chain)
     if return_chain:
       return actions, ChainData(*chain)

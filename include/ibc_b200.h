@@ -286,15 +286,39 @@ int ibc_pixel_dfo(ibc_pixel_handle* h, const float* enc, int64_t B, float* actio
                   const double* uniforms, const float* normals, uint64_t seed,
                   float* probs, void* stream);
 
+/* mcmc.gradient_wrt_act on the late-fusion network (mcmc.py:161-191 with
+ * PixelEBM.call's observation_encoding, pixel_ebm.py:113-125): energy [B*n] and
+ * dE_dact [B*n, A] = +dE/dact (the caller negates, as gradient_wrt_act returns
+ * -dE/dact) for enc [B, 256] un-tiled and act [B*n, A]. */
+int ibc_pixel_energy_dact(ibc_pixel_handle* h, const float* enc, int64_t B,
+                          const float* act, int64_t n, float* energy,
+                          float* dE_dact, void* stream);
+
+/* mcmc.langevin_actions_given_obs with late_fusion=True (mcmc.py:384-388: the
+ * observation is encoded once -- here by the caller, ibc_pixel_encode -- and
+ * every step evaluates the value head only); same contract as ibc_langevin
+ * (in-place actions, normals [K, B*n, A] or NULL -> seed, optional chain
+ * outputs).  cfg->apply_exp must be 0. */
+int ibc_pixel_langevin(ibc_pixel_handle* h, const float* enc, int64_t B,
+                       float* actions, int64_t n, const float* min_actions,
+                       const float* max_actions, const ibc_langevin_cfg* cfg,
+                       const float* normals, uint64_t seed, float* chain_actions,
+                       float* chain_energies, float* chain_grad_norms,
+                       void* stream);
+
 /* Late-fusion ImplicitBCAgent._loss + tape.gradient (ibc_agent.py:191-250):
  * encode (training=True), tile the encoding N+1 times, value head, InfoNCE,
- * backward through the value head and the conv encoder.  cfg->add_grad_penalty
- * must be 0.  grads [param_count] is overwritten. */
+ * backward through the value head and the conv encoder.  With
+ * cfg->add_grad_penalty (pushing_pixels/pixel_ebm_langevin.gin) the gradient
+ * penalty of gradient_loss.py:35-72 on dE/dact at the combined actions is added
+ * to per_example_loss and its parameter gradients (value head only: dE/dact
+ * depends on the encoder through ReLU masks alone) to grads; grad_loss [B]
+ * (nullable) receives the penalty term.  grads [param_count] is overwritten. */
 int ibc_pixel_train_grads(ibc_pixel_handle* h, const void* images, int32_t is_uint8,
                           int64_t B, const float* actions, int64_t N,
                           const ibc_loss_cfg* cfg, int64_t global_batch,
-                          float* per_example_loss, float* energies, float* grads,
-                          void* stream);
+                          float* per_example_loss, float* grad_loss,
+                          float* energies, float* grads, void* stream);
 
 /* ---- diagnostics ------------------------------------------------------- */
 

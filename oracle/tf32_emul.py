@@ -91,7 +91,15 @@ def pixel_energy(flat: torch.Tensor, spec, images: torch.Tensor, act: torch.Tens
     x = F.relu(_RoundGradient.apply(y) + p[f'conv{i + 1}_b'].reshape(1, -1, 1, 1))
     x = F.max_pool2d(x, 2)
   enc = x.mean(dim=(2, 3))
-  n = act.shape[0] // images.shape[0]
+  return pixel_value(flat, spec, enc, act)
+
+
+def pixel_value(flat: torch.Tensor, spec, enc: torch.Tensor, act: torch.Tensor) -> torch.Tensor:
+  """The value head of pixel_energy on an un-tiled encoding [B, 256] and act [B*n, A]
+  (PixelEBM.call with observation_encoding, pixel_ebm.py:113-125)."""
+  from oracle import pixel_ebm as opix
+  p = opix.unpack(flat, spec)
+  n = act.shape[0] // enc.shape[0]
   w0 = p['v_dense0_W']
   x = torch.repeat_interleave(enc @ w0[:256] + p['v_dense0_b'], n, dim=0) + act @ w0[256:]
   for j in range(spec.value_blocks):
