@@ -715,7 +715,16 @@ bool gemm_tc_supported(const GemmP& p) {
 int gemm_tc(ibc_handle* h, const GemmP& p_in, bool ta, bool tb, cudaStream_t s) {
   if (!gemm_tc_supported(p_in)) IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "gemm_tc: unsupported shape");
   GemmP p = p_in;
-  const int bn = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : 128);
+  int bn = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : 128);
+  if (!p.atomic && p.conv_C == 0) {
+    // Few-row products (sampler chains: 1024-2048 rows) leave most SMs idle with 128-column
+    // blocks and a block's K loop is latency-bound, so narrower blocks on more SMs finish
+    // sooner: halve the block width while fewer than half of the SMs would have a block.
+    static const bool narrow = getenv("IBC_TC_WIDE_BLOCKS") == nullptr;
+    const int sms = h ? h->sm_count : 148;
+    const int64_t rows_m = (p.M + kBM - 1) / kBM;
+    while (narrow && bn > 32 && rows_m * ((p.N + bn - 1) / bn) * 2 < sms) bn >>= 1;
+  }
   const int tm = (p.M + kBM - 1) / kBM, tn = (p.N + bn - 1) / bn;
   int splits = 1;
   if (p.atomic) {

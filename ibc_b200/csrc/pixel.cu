@@ -238,6 +238,37 @@ __global__ void add_rows_kernel(float* __restrict__ a, const float* __restrict__
   if (i < n) a[i] += b[i];
 }
 
+// dEda[r, a] = sum_c G[r, c] * W[a, c]   (dE/dact from the gradient at the value head's first
+// layer: N = act_dim columns, a bandwidth-bound pass over G; one warp per row, 16-byte loads)
+__global__ void act_rows_dact_kernel(const float* __restrict__ G, const float* __restrict__ W,
+                                     int64_t R, int A, int Wv, float* __restrict__ dEda) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  float acc[kMaxActRows];
+#pragma unroll
+  for (int a = 0; a < kMaxActRows; ++a) acc[a] = 0.f;
+  for (int c4 = lane; c4 < Wv / 4; c4 += 32) {
+    const float4 g = *reinterpret_cast<const float4*>(G + r * Wv + c4 * 4);
+#pragma unroll
+    for (int a = 0; a < kMaxActRows; ++a) {
+      if (a < A) {
+        const float4 w = *reinterpret_cast<const float4*>(W + (int64_t)a * Wv + c4 * 4);
+        acc[a] = fmaf(g.x, w.x, fmaf(g.y, w.y, fmaf(g.z, w.z, fmaf(g.w, w.w, acc[a]))));
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < kMaxActRows; ++a) {
+    if (a < A) {
+      float v = acc[a];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) dEda[r * A + a] = v;
+    }
+  }
+}
+
 // out[i] = tf32(in[i]): the weights as MMA operands (rounded once per call instead of
 // in every block of every product that reads them)
 __global__ void round_copy_kernel(const float* __restrict__ in, int64_t n, float* __restrict__ out) {
@@ -580,27 +611,35 @@ void carve_val(ibc_handle* h, const PixelLayout& L, int64_t B, int64_t R, ValSav
   v->wr = h->ws.take<float>((size_t)L.count);
 }
 
-// E[r] for enc [B, 256] (un-tiled) and act [B*n, A]   (pixel_ebm.py:113-125)
-int value_fwd(ibc_pixel_handle* ph, const PixelLayout& L, const float* enc, int64_t B,
-              const float* act, int64_t n, const ValSave& v, float* E, cudaStream_t s) {
+// The part of the value head that does not depend on the actions: the tf32-rounded copy of
+// the block weights and encp = enc . W0[:256] + b0 for enc [B, 256] (un-tiled).  A Langevin
+// chain on a fixed encoding runs it once for all of its iterations.
+int value_prepare(ibc_pixel_handle* ph, const PixelLayout& L, const float* enc, int64_t B,
+                  const ValSave& v, cudaStream_t s) {
+  ibc_handle* h = &ph->core;
+  const float* P = ph->params;
+  const int Wv = L.Wv;
+  if (h->precision == IBC_PRECISION_TF32) {
+    round_copy_kernel<<<nblocks(L.count - L.d0_w), 256, 0, s>>>(P + L.d0_w, L.count - L.d0_w,
+                                                                 v.wr + L.d0_w);
+    IBC_LAUNCH_CHECK(h);
+  }
+  GemmP g;  // encp = enc . W0[:256] + b0
+  g.A = enc; g.lda = kEnc; g.B = P + L.d0_w; g.ldb = Wv; g.C = v.encp; g.ldc = Wv;
+  g.bias = P + L.d0_b; g.M = (int)B; g.N = Wv; g.K = kEnc;
+  return pgemm(h, g, false, false, s);
+}
+
+// E[r] for act [B*n, A] on the encoding value_prepare has projected into `v`
+// (pixel_ebm.py:113-125)
+int value_rows(ibc_pixel_handle* ph, const PixelLayout& L, int64_t B, const float* act, int64_t n,
+               const ValSave& v, float* E, cudaStream_t s) {
   ibc_handle* h = &ph->core;
   const float* P = ph->params;
   const int Wv = L.Wv, Wq = L.Wq;
   const int64_t R = B * n;
   const bool tc = h->precision == IBC_PRECISION_TF32;
-  const float* PB = P;          // B operands of the block products
-  if (tc) {
-    round_copy_kernel<<<nblocks(L.count - L.d0_w), 256, 0, s>>>(P + L.d0_w, L.count - L.d0_w,
-                                                                 v.wr + L.d0_w);
-    IBC_LAUNCH_CHECK(h);
-    PB = v.wr;
-  }
-  {  // encp = enc . W0[:256] + b0
-    GemmP g;
-    g.A = enc; g.lda = kEnc; g.B = P + L.d0_w; g.ldb = Wv; g.C = v.encp; g.ldc = Wv;
-    g.bias = P + L.d0_b; g.M = (int)B; g.N = Wv; g.K = kEnc;
-    IBC_TRY(pgemm(h, g, false, false, s));
-  }
+  const float* PB = tc ? v.wr : P;          // B operands of the block products
   if (tc) {   // x0 = act . W0[256:] + encp[row / n]
     act_rows_kernel<<<nblocks(R * (Wv / 4)), 256, 0, s>>>(act, P + L.d0_w + (int64_t)kEnc * Wv, v.encp,
                                                         R, n, L.A, Wv, v.X);
@@ -633,6 +672,13 @@ int value_fwd(ibc_pixel_handle* ph, const PixelLayout& L, const float* enc, int6
   }
   IBC_TRY(rowdot(h, v.X + (int64_t)L.nblk * R * Wv, Wv, P + L.d1_w, P + L.d1_b, R, Wv, E, s));
   return IBC_OK;
+}
+
+// E[r] for enc [B, 256] (un-tiled) and act [B*n, A]   (pixel_ebm.py:113-125)
+int value_fwd(ibc_pixel_handle* ph, const PixelLayout& L, const float* enc, int64_t B,
+              const float* act, int64_t n, const ValSave& v, float* E, cudaStream_t s) {
+  IBC_TRY(value_prepare(ph, L, enc, B, v, s));
+  return value_rows(ph, L, B, act, n, v, E, s);
 }
 
 static int dwg(ibc_handle* h, const float* X, int64_t ldx, int aop, const float* Y, int64_t ldy,
@@ -771,7 +817,13 @@ int value_dact(ibc_pixel_handle* ph, const PixelLayout& L, const ValSave& v, con
     ax.res = G; ax.ldres = Wv; ax.M = (int)R; ax.N = Wv; ax.K = Wq;
     IBC_TRY(pgemm(h, ax, false, true, s));
   }
-  GemmP g;  // dE/dact = G_0 . W0[256:]^T   (N = act_dim: a bandwidth-bound pass over G_0)
+  if (L.A <= kMaxActRows) {   // dE/dact = G_0 . W0[256:]^T
+    act_rows_dact_kernel<<<(unsigned)((R + 7) / 8), 256, 0, s>>>(
+        rv.Gl(0), P + L.d0_w + (int64_t)kEnc * Wv, R, L.A, Wv, dEda);
+    IBC_LAUNCH_CHECK(h);
+    return IBC_OK;
+  }
+  GemmP g;
   g.A = rv.Gl(0); g.lda = Wv; g.B = P + L.d0_w + (int64_t)kEnc * Wv; g.ldb = Wv;
   g.C = dEda; g.ldc = L.A; g.M = (int)R; g.N = L.A; g.K = Wv;
   return gemm(h, g, false, true, s);
@@ -1061,18 +1113,20 @@ int ibc_pixel_langevin(ibc_pixel_handle* ph, const float* enc, int64_t B, float*
   IBC_CUDA(h, h->ws.reserve(val_bytes(L, B, R) + val_rev_bytes(L, R, false) +
                             2 * Workspace::rounded((size_t)R * 4) +
                             Workspace::rounded((size_t)R * A * 4)));
+  h->ws.reset();
+  ValSave v;
+  carve_val(h, L, B, R, &v);
+  ValRev rv;
+  carve_val_rev(h, L, R, false, &rv);
+  float* E = h->ws.take<float>(R);
+  float* nrm = h->ws.take<float>(R);
+  float* dEda = h->ws.take<float>((size_t)R * A);
+  // the encoding is fixed along the chain: its projection and the rounded weights once
+  if (cfg->num_iterations > 0) IBC_TRY(value_prepare(ph, L, enc, B, v, s));
   for (int k = 0; k < cfg->num_iterations; ++k) {
-    h->ws.reset();
-    ValSave v;
-    carve_val(h, L, B, R, &v);
-    ValRev rv;
-    carve_val_rev(h, L, R, false, &rv);
-    float* E = h->ws.take<float>(R);
-    float* nrm = h->ws.take<float>(R);
-    float* dEda = h->ws.take<float>((size_t)R * A);
     float* Ek = chain_energies ? chain_energies + (int64_t)k * R : E;
     float* Nk = chain_grad_norms ? chain_grad_norms + (int64_t)k * R : nrm;
-    IBC_TRY(value_fwd(ph, L, enc, B, actions, n, v, Ek, s));
+    IBC_TRY(value_rows(ph, L, B, actions, n, v, Ek, s));
     IBC_TRY(value_dact(ph, L, v, rv, dEda, s));
     IBC_TRY(langevin_update(h, actions, dEda, R, A, normals ? normals + (int64_t)k * R * A : nullptr,
                             seed, (uint64_t)k + 1, cfg->noise_scale, cfg->grad_clip,
