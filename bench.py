@@ -524,6 +524,48 @@ def secondary_configs(device):
           'precision': 'tf32', 'kernel_status': pnet.engine.kernel_status()}
     finally:
       gin.clear_config()
+  # C5 Langevin variant (pushing_pixels/pixel_ebm_langevin.gin): 8 Langevin counter-examples
+  # (100 iterations on the value head over one encoding), gradient penalty, Adam; and a
+  # policy action (2048 samples, 100 + 100 "again" iterations, probabilities, arg max)
+  if solo:
+    from ibc_b200.networks.pixel_ebm import PixelEBM
+    from ibc_b200.ibc.agents import ibc_policy
+    gin.clear_config()
+    gin.parse_config('DenseResnetValue.width = 1024\nDenseResnetValue.num_blocks = 1\n'
+                     'langevin_actions_given_obs.late_fusion = True\n'
+                     'langevin_actions_given_obs.num_iterations = 100')
+    try:
+      p_obs = {'rgb': specs.TensorSpec((2, 240, 320, 3), dtype=torch.uint8)}
+      p_act = specs.BoundedTensorSpec((2,), minimum=-1.0, maximum=1.0)
+      p_samp = specs.BoundedTensorSpec((2,), minimum=-1.1, maximum=1.1)
+      lnet = PixelEBM((p_obs, p_act), specs.TensorSpec((1,)), 'ConvMaxpoolEncoder',
+                      'DenseResnetValue', target_height=180, target_width=240, seed=0)
+      ln, lk = 8, 100
+      lagent = ibc_agent.ImplicitBCAgent(p_obs, p_act, p_samp, lnet, get_agent.Adam(1e-3),
+                                         num_counter_examples=ln, fraction_langevin_samples=1.0,
+                                         late_fusion=True, add_grad_penalty=True,
+                                         run_full_chain_under_gradient=True, compute_mse=True)
+      lexp = (({'rgb': img}, torch.rand(b, 2, device=device) * 2 - 1), ())
+      for _ in range(2):
+        lagent.train(lexp)
+      t = timed(lambda i: lagent.train(lexp), 3, lambda: None) / 3
+      out['C5_pixel_langevin_train_step'] = {
+          'ms_per_step': t * 1e3, 'images': b, 'images_per_s': b / t, 'num_counter_examples': ln,
+          'langevin_iterations': lk, 'grad_penalty': True,
+          'energy_evals_per_s': (lk * b * ln + 2 * b * (ln + 1)) / t,
+          'precision': 'tf32', 'kernel_status': lnet.engine.kernel_status()}
+      lpol = ibc_policy.GreedyPolicy(ibc_policy.IbcPolicy(
+          p_obs, p_act, p_samp, lnet, num_action_samples=2048, use_dfo=False, use_langevin=True,
+          optimize_again=True, late_fusion=True))
+      ts = specs.restart({'rgb': img[:1].contiguous()})
+      for _ in range(2):
+        lpol.action(ts)
+      t = timed(lambda i: lpol.action(ts), 5, lambda: None) / 5
+      out['C5_pixel_langevin_inference'] = {
+          'ms_per_action': t * 1e3, 'actions_per_s': 1.0 / t, 'num_action_samples': 2048,
+          'langevin_iterations': 2 * lk, 'kernel_status': lnet.engine.kernel_status()}
+    finally:
+      gin.clear_config()
   # C5 inference (pixel_ebm_best.gin: one frame pair, late fusion: encode once, DFO over 2048
   # candidates, 3 iterations) on the tf32 path
   pe.set_precision(_lib.PRECISION_TF32)

@@ -269,6 +269,21 @@ __global__ void act_rows_dact_kernel(const float* __restrict__ G, const float* _
   }
 }
 
+// out[r, q] = gate[r, q] > 0 ? c[q] : 0   (a constant row through a ReLU mask; Wq % 4 == 0)
+__global__ void gate_const_rows_kernel(const float* __restrict__ c, const float* __restrict__ gate,
+                                       int64_t R, int Wq, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int W4 = Wq / 4;
+  if (i >= R * W4) return;
+  const int q4 = (int)(i % W4);
+  const float4 g = *reinterpret_cast<const float4*>(gate + i * 4);
+  const float4 v = *reinterpret_cast<const float4*>(c + q4 * 4);
+  float4 o;
+  o.x = g.x > 0.f ? v.x : 0.f; o.y = g.y > 0.f ? v.y : 0.f;
+  o.z = g.z > 0.f ? v.z : 0.f; o.w = g.w > 0.f ? v.w : 0.f;
+  *reinterpret_cast<float4*>(out + i * 4) = o;
+}
+
 // out[i] = tf32(in[i]): the weights as MMA operands (rounded once per call instead of
 // in every block of every product that reads them)
 __global__ void round_copy_kernel(const float* __restrict__ in, int64_t n, float* __restrict__ out) {
@@ -767,6 +782,7 @@ struct ValRev {
   float* G = nullptr;    // [levels, R, Wv]
   float* g0 = nullptr;   // [blocks kept, R, Wq]
   float* g1 = nullptr;
+  float* c = nullptr;    // [Wq] D2_last . w1: every row of G_L . D2_last^T (G_L's rows are all w1)
   int64_t R = 0;
   int Wv = 0, Wq = 0;
   bool keep = false;
@@ -778,7 +794,7 @@ struct ValRev {
 size_t val_rev_bytes(const PixelLayout& L, int64_t R, bool keep) {
   const int lv = keep ? L.nblk + 1 : 2, lq = keep ? (L.nblk > 0 ? L.nblk : 1) : 1;
   return Workspace::rounded((size_t)lv * R * L.Wv * 4) +
-         2 * Workspace::rounded((size_t)lq * R * L.Wq * 4);
+         2 * Workspace::rounded((size_t)lq * R * L.Wq * 4) + Workspace::rounded((size_t)L.Wq * 4);
 }
 
 void carve_val_rev(ibc_handle* h, const PixelLayout& L, int64_t R, bool keep, ValRev* r) {
@@ -787,6 +803,15 @@ void carve_val_rev(ibc_handle* h, const PixelLayout& L, int64_t R, bool keep, Va
   r->G = h->ws.take<float>((size_t)lv * R * L.Wv);
   r->g0 = h->ws.take<float>((size_t)lq * R * L.Wq);
   r->g1 = h->ws.take<float>((size_t)lq * R * L.Wq);
+  r->c = h->ws.take<float>((size_t)L.Wq);
+}
+
+// The action-independent part of value_dact (once per chain): c = D2_last . w1 in fp32.
+int value_dact_prepare(ibc_pixel_handle* ph, const PixelLayout& L, const ValRev& rv,
+                       cudaStream_t s) {
+  if (L.nblk < 1 || rv.keep || (L.Wq & 3)) return IBC_OK;
+  const float* P = ph->params;
+  return rowdot(&ph->core, P + L.b_d2w(L.nblk - 1), L.Wv, P + L.d1_w, nullptr, L.Wq, L.Wv, rv.c, s);
 }
 
 // dEda [R, A] = +dE/dact for the rows value_fwd has just evaluated into `v`.
@@ -798,14 +823,26 @@ int value_dact(ibc_pixel_handle* ph, const PixelLayout& L, const ValSave& v, con
   const int64_t R = v.R;
   const bool tc = h->precision == IBC_PRECISION_TF32;
   const float* PB = tc ? v.wr : P;   // rounded by value_fwd earlier in the same call
-  IBC_TRY(rowfill(h, P + L.d1_w, nullptr, R, Wv, rv.Gl(L.nblk), s));
+  // Every row of G_L is w1, so the last block's G . D2^T is the constant row c of
+  // value_dact_prepare: no product and no materialised G_L (the residual reads w1 with a
+  // zero row stride).  The tangent pass of the gradient penalty reads G_L, so `keep` fills it.
+  const bool const_top = L.nblk >= 1 && !rv.keep && (Wq & 3) == 0;
+  if (!const_top) IBC_TRY(rowfill(h, P + L.d1_w, nullptr, R, Wv, rv.Gl(L.nblk), s));
   for (int j = L.nblk - 1; j >= 0; --j) {
-    const float* G = rv.Gl(j + 1);
-    GemmP a1;  // g1 = (G . D2^T) (.) (y1 > 0)
-    a1.A = G; a1.lda = Wv; a1.B = PB + L.b_d2w(j); a1.ldb = Wv; a1.b_tf32 = tc;
-    a1.C = rv.q1(j); a1.ldc = Wq; a1.gateC = v.Y1 + (int64_t)j * R * Wq; a1.ldgc = Wq;
-    a1.M = (int)R; a1.N = Wq; a1.K = Wv;
-    IBC_TRY(pgemm(h, a1, false, true, s));
+    const bool top = const_top && j == L.nblk - 1;
+    const float* G = top ? P + L.d1_w : rv.Gl(j + 1);
+    const int64_t ldG = top ? 0 : Wv;
+    if (top) {  // g1 = c (.) (y1 > 0)
+      gate_const_rows_kernel<<<nblocks(R * (Wq / 4)), 256, 0, s>>>(
+          rv.c, v.Y1 + (int64_t)j * R * Wq, R, Wq, rv.q1(j));
+      IBC_LAUNCH_CHECK(h);
+    } else {
+      GemmP a1;  // g1 = (G . D2^T) (.) (y1 > 0)
+      a1.A = G; a1.lda = Wv; a1.B = PB + L.b_d2w(j); a1.ldb = Wv; a1.b_tf32 = tc;
+      a1.C = rv.q1(j); a1.ldc = Wq; a1.gateC = v.Y1 + (int64_t)j * R * Wq; a1.ldgc = Wq;
+      a1.M = (int)R; a1.N = Wq; a1.K = Wv;
+      IBC_TRY(pgemm(h, a1, false, true, s));
+    }
     GemmP a0;  // g0 = (g1 . D1^T) (.) (y0 > 0)
     a0.A = rv.q1(j); a0.lda = Wq; a0.B = PB + L.b_d1w(j); a0.ldb = Wq; a0.b_tf32 = tc;
     a0.C = rv.q0(j); a0.ldc = Wq; a0.gateC = v.Y0 + (int64_t)j * R * Wq; a0.ldgc = Wq;
@@ -814,7 +851,7 @@ int value_dact(ibc_pixel_handle* ph, const PixelLayout& L, const ValSave& v, con
     GemmP ax;  // G' = G + (g0 . D0^T) (.) (x > 0)
     ax.A = rv.q0(j); ax.lda = Wq; ax.B = PB + L.b_d0w(j); ax.ldb = Wq; ax.b_tf32 = tc;
     ax.C = rv.Gl(j); ax.ldc = Wv; ax.gateC = v.X + (int64_t)j * R * Wv; ax.ldgc = Wv;
-    ax.res = G; ax.ldres = Wv; ax.M = (int)R; ax.N = Wv; ax.K = Wq;
+    ax.res = G; ax.ldres = ldG; ax.M = (int)R; ax.N = Wv; ax.K = Wq;
     IBC_TRY(pgemm(h, ax, false, true, s));
   }
   if (L.A <= kMaxActRows) {   // dE/dact = G_0 . W0[256:]^T
@@ -1086,6 +1123,7 @@ int ibc_pixel_energy_dact(ibc_pixel_handle* ph, const float* enc, int64_t B, con
   ValRev rv;
   carve_val_rev(h, L, R, false, &rv);
   IBC_TRY(value_fwd(ph, L, enc, B, act, n, v, energy, (cudaStream_t)stream));
+  IBC_TRY(value_dact_prepare(ph, L, rv, (cudaStream_t)stream));
   return value_dact(ph, L, v, rv, dE_dact, (cudaStream_t)stream);
 }
 
@@ -1122,7 +1160,10 @@ int ibc_pixel_langevin(ibc_pixel_handle* ph, const float* enc, int64_t B, float*
   float* nrm = h->ws.take<float>(R);
   float* dEda = h->ws.take<float>((size_t)R * A);
   // the encoding is fixed along the chain: its projection and the rounded weights once
-  if (cfg->num_iterations > 0) IBC_TRY(value_prepare(ph, L, enc, B, v, s));
+  if (cfg->num_iterations > 0) {
+    IBC_TRY(value_prepare(ph, L, enc, B, v, s));
+    IBC_TRY(value_dact_prepare(ph, L, rv, s));
+  }
   for (int k = 0; k < cfg->num_iterations; ++k) {
     float* Ek = chain_energies ? chain_energies + (int64_t)k * R : E;
     float* Nk = chain_grad_norms ? chain_grad_norms + (int64_t)k * R : nrm;
