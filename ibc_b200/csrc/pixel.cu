@@ -269,6 +269,31 @@ __global__ void act_rows_dact_kernel(const float* __restrict__ G, const float* _
   }
 }
 
+// E[r] = x[r, :] . w1 + relu(y1[r, :]) . c[0:Wq] + c[Wq]   (one warp per row, 16-byte loads;
+// Wv % 4 == 0, Wq % 4 == 0)
+__global__ void energy_top_kernel(const float* __restrict__ x, const float* __restrict__ w1,
+                                  const float* __restrict__ y1, const float* __restrict__ c,
+                                  int64_t R, int Wv, int Wq, float* __restrict__ E) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  float acc = 0.f;
+  for (int c4 = lane; c4 < Wv / 4; c4 += 32) {
+    const float4 a = *reinterpret_cast<const float4*>(x + r * Wv + c4 * 4);
+    const float4 w = *reinterpret_cast<const float4*>(w1 + c4 * 4);
+    acc = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, fmaf(a.w, w.w, acc))));
+  }
+  for (int q4 = lane; q4 < Wq / 4; q4 += 32) {
+    const float4 a = *reinterpret_cast<const float4*>(y1 + r * Wq + q4 * 4);
+    const float4 w = *reinterpret_cast<const float4*>(c + q4 * 4);
+    acc = fmaf(fmaxf(a.x, 0.f), w.x, fmaf(fmaxf(a.y, 0.f), w.y,
+          fmaf(fmaxf(a.z, 0.f), w.z, fmaf(fmaxf(a.w, 0.f), w.w, acc))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) E[r] = acc + c[Wq];
+}
+
 // out[r, q] = gate[r, q] > 0 ? c[q] : 0   (a constant row through a ReLU mask; Wq % 4 == 0)
 __global__ void gate_const_rows_kernel(const float* __restrict__ c, const float* __restrict__ gate,
                                        int64_t R, int Wq, float* __restrict__ out) {
@@ -605,15 +630,24 @@ struct ValSave {
   float* Y1 = nullptr;     // [nblk, R, Wq]
   float* wr = nullptr;     // [param count] tf32-rounded copy of the value parameters at the flat
                            // vector's offsets (filled by value_fwd on the tf32 path)
+  // Energy-only evaluation (samplers): E = x_L . w1 + b1 with x_L = x + relu(y1) . D2 + b2 is
+  // x . w1 + relu(y1) . (D2 w1) + (b2 . w1 + b1) -- the last block's widest product collapses
+  // into the vector ctop[0:Wq] = D2_last . w1 and the scalar ctop[Wq] = b2_last . w1 + b1
+  // (fp32, value_prepare).  `top` says whether this evaluation uses them (x_L is then NOT
+  // formed; the training pass needs x_L for dw1 and keeps the product).
+  float* ctop = nullptr;   // [Wq + 4]
+  bool top = false;
   int64_t R = 0;
 };
+
+inline bool top_shortcut_ok(const PixelLayout& L) { return L.nblk >= 1 && (L.Wq & 3) == 0; }
 
 size_t val_bytes(const PixelLayout& L, int64_t B, int64_t R) {
   const int nb = L.nblk > 0 ? L.nblk : 1;
   return Workspace::rounded((size_t)B * L.Wv * 4) +
          Workspace::rounded((size_t)(L.nblk + 1) * R * L.Wv * 4) +
          2 * Workspace::rounded((size_t)nb * R * L.Wq * 4) +
-         Workspace::rounded((size_t)L.count * 4);
+         Workspace::rounded((size_t)L.count * 4) + Workspace::rounded((size_t)(L.Wq + 4) * 4);
 }
 
 void carve_val(ibc_handle* h, const PixelLayout& L, int64_t B, int64_t R, ValSave* v) {
@@ -624,6 +658,7 @@ void carve_val(ibc_handle* h, const PixelLayout& L, int64_t B, int64_t R, ValSav
   v->Y0 = h->ws.take<float>((size_t)nb * R * L.Wq);
   v->Y1 = h->ws.take<float>((size_t)nb * R * L.Wq);
   v->wr = h->ws.take<float>((size_t)L.count);
+  v->ctop = h->ws.take<float>((size_t)L.Wq + 4);
 }
 
 // The part of the value head that does not depend on the actions: the tf32-rounded copy of
@@ -638,6 +673,11 @@ int value_prepare(ibc_pixel_handle* ph, const PixelLayout& L, const float* enc, 
     round_copy_kernel<<<nblocks(L.count - L.d0_w), 256, 0, s>>>(P + L.d0_w, L.count - L.d0_w,
                                                                  v.wr + L.d0_w);
     IBC_LAUNCH_CHECK(h);
+  }
+  if (v.top) {
+    const int jl = L.nblk - 1;
+    IBC_TRY(rowdot(h, P + L.b_d2w(jl), Wv, P + L.d1_w, nullptr, L.Wq, Wv, v.ctop, s));
+    IBC_TRY(rowdot(h, P + L.b_d2b(jl), Wv, P + L.d1_w, P + L.d1_b, 1, Wv, v.ctop + L.Wq, s));
   }
   GemmP g;  // encp = enc . W0[:256] + b0
   g.A = enc; g.lda = kEnc; g.B = P + L.d0_w; g.ldb = Wv; g.C = v.encp; g.ldc = Wv;
@@ -679,6 +719,12 @@ int value_rows(ibc_pixel_handle* ph, const PixelLayout& L, int64_t B, const floa
     g1.A = y0; g1.lda = Wq; g1.aop = AOP_RELU; g1.B = PB + L.b_d1w(j); g1.ldb = Wq; g1.b_tf32 = tc;
     g1.C = y1; g1.ldc = Wq; g1.bias = P + L.b_d1b(j); g1.M = (int)R; g1.N = Wq; g1.K = Wq;
     IBC_TRY(pgemm(h, g1, false, false, s));
+    if (v.top && j == L.nblk - 1) {   // E = x . w1 + relu(y1) . ctop + ctop[Wq]
+      energy_top_kernel<<<(unsigned)((R + 7) / 8), 256, 0, s>>>(x, P + L.d1_w, y1, v.ctop, R, Wv,
+                                                                Wq, E);
+      IBC_LAUNCH_CHECK(h);
+      return IBC_OK;
+    }
     GemmP g2;  // x' = x + relu(y1) . D2 + b
     g2.A = y1; g2.lda = Wq; g2.aop = AOP_RELU; g2.B = PB + L.b_d2w(j); g2.ldb = Wv; g2.b_tf32 = tc;
     g2.C = xn; g2.ldc = Wv; g2.bias = P + L.b_d2b(j); g2.res = x; g2.ldres = Wv;
@@ -782,7 +828,6 @@ struct ValRev {
   float* G = nullptr;    // [levels, R, Wv]
   float* g0 = nullptr;   // [blocks kept, R, Wq]
   float* g1 = nullptr;
-  float* c = nullptr;    // [Wq] D2_last . w1: every row of G_L . D2_last^T (G_L's rows are all w1)
   int64_t R = 0;
   int Wv = 0, Wq = 0;
   bool keep = false;
@@ -794,7 +839,7 @@ struct ValRev {
 size_t val_rev_bytes(const PixelLayout& L, int64_t R, bool keep) {
   const int lv = keep ? L.nblk + 1 : 2, lq = keep ? (L.nblk > 0 ? L.nblk : 1) : 1;
   return Workspace::rounded((size_t)lv * R * L.Wv * 4) +
-         2 * Workspace::rounded((size_t)lq * R * L.Wq * 4) + Workspace::rounded((size_t)L.Wq * 4);
+         2 * Workspace::rounded((size_t)lq * R * L.Wq * 4);
 }
 
 void carve_val_rev(ibc_handle* h, const PixelLayout& L, int64_t R, bool keep, ValRev* r) {
@@ -803,15 +848,6 @@ void carve_val_rev(ibc_handle* h, const PixelLayout& L, int64_t R, bool keep, Va
   r->G = h->ws.take<float>((size_t)lv * R * L.Wv);
   r->g0 = h->ws.take<float>((size_t)lq * R * L.Wq);
   r->g1 = h->ws.take<float>((size_t)lq * R * L.Wq);
-  r->c = h->ws.take<float>((size_t)L.Wq);
-}
-
-// The action-independent part of value_dact (once per chain): c = D2_last . w1 in fp32.
-int value_dact_prepare(ibc_pixel_handle* ph, const PixelLayout& L, const ValRev& rv,
-                       cudaStream_t s) {
-  if (L.nblk < 1 || rv.keep || (L.Wq & 3)) return IBC_OK;
-  const float* P = ph->params;
-  return rowdot(&ph->core, P + L.b_d2w(L.nblk - 1), L.Wv, P + L.d1_w, nullptr, L.Wq, L.Wv, rv.c, s);
 }
 
 // dEda [R, A] = +dE/dact for the rows value_fwd has just evaluated into `v`.
@@ -823,10 +859,10 @@ int value_dact(ibc_pixel_handle* ph, const PixelLayout& L, const ValSave& v, con
   const int64_t R = v.R;
   const bool tc = h->precision == IBC_PRECISION_TF32;
   const float* PB = tc ? v.wr : P;   // rounded by value_fwd earlier in the same call
-  // Every row of G_L is w1, so the last block's G . D2^T is the constant row c of
-  // value_dact_prepare: no product and no materialised G_L (the residual reads w1 with a
-  // zero row stride).  The tangent pass of the gradient penalty reads G_L, so `keep` fills it.
-  const bool const_top = L.nblk >= 1 && !rv.keep && (Wq & 3) == 0;
+  // Every row of G_L is w1, so the last block's G . D2^T is the constant row ctop = D2 w1 of
+  // value_prepare: no product and no materialised G_L (the residual reads w1 with a zero row
+  // stride).  The tangent pass of the gradient penalty reads G_L, so `keep` fills it.
+  const bool const_top = v.top && !rv.keep;
   if (!const_top) IBC_TRY(rowfill(h, P + L.d1_w, nullptr, R, Wv, rv.Gl(L.nblk), s));
   for (int j = L.nblk - 1; j >= 0; --j) {
     const bool top = const_top && j == L.nblk - 1;
@@ -834,7 +870,7 @@ int value_dact(ibc_pixel_handle* ph, const PixelLayout& L, const ValSave& v, con
     const int64_t ldG = top ? 0 : Wv;
     if (top) {  // g1 = c (.) (y1 > 0)
       gate_const_rows_kernel<<<nblocks(R * (Wq / 4)), 256, 0, s>>>(
-          rv.c, v.Y1 + (int64_t)j * R * Wq, R, Wq, rv.q1(j));
+          v.ctop, v.Y1 + (int64_t)j * R * Wq, R, Wq, rv.q1(j));
       IBC_LAUNCH_CHECK(h);
     } else {
       GemmP a1;  // g1 = (G . D2^T) (.) (y1 > 0)
@@ -1084,6 +1120,7 @@ int ibc_pixel_energy(ibc_pixel_handle* ph, const float* enc, int64_t B, const fl
   h->ws.reset();
   ValSave v;
   carve_val(h, L, B, B * n, &v);
+  v.top = top_shortcut_ok(L);
   return value_fwd(ph, L, enc, B, act, n, v, energy, (cudaStream_t)stream);
 }
 
@@ -1102,6 +1139,7 @@ int ibc_pixel_dfo(ibc_pixel_handle* ph, const float* enc, int64_t B, float* acti
     h->ws.reset();
     ValSave v;
     carve_val(h, L, B, B * n, &v);
+    v.top = top_shortcut_ok(L);
     return value_fwd(ph, L, enc, B, acts, n, v, E, s);
   };
   return dfo_generic(h, ph->arch.act_dim, B, actions, n, min_actions, max_actions, temperature,
@@ -1120,10 +1158,10 @@ int ibc_pixel_energy_dact(ibc_pixel_handle* ph, const float* enc, int64_t B, con
   h->ws.reset();
   ValSave v;
   carve_val(h, L, B, R, &v);
+  v.top = top_shortcut_ok(L);
   ValRev rv;
   carve_val_rev(h, L, R, false, &rv);
   IBC_TRY(value_fwd(ph, L, enc, B, act, n, v, energy, (cudaStream_t)stream));
-  IBC_TRY(value_dact_prepare(ph, L, rv, (cudaStream_t)stream));
   return value_dact(ph, L, v, rv, dE_dact, (cudaStream_t)stream);
 }
 
@@ -1160,10 +1198,8 @@ int ibc_pixel_langevin(ibc_pixel_handle* ph, const float* enc, int64_t B, float*
   float* nrm = h->ws.take<float>(R);
   float* dEda = h->ws.take<float>((size_t)R * A);
   // the encoding is fixed along the chain: its projection and the rounded weights once
-  if (cfg->num_iterations > 0) {
-    IBC_TRY(value_prepare(ph, L, enc, B, v, s));
-    IBC_TRY(value_dact_prepare(ph, L, rv, s));
-  }
+  v.top = top_shortcut_ok(L);
+  if (cfg->num_iterations > 0) IBC_TRY(value_prepare(ph, L, enc, B, v, s));
   for (int k = 0; k < cfg->num_iterations; ++k) {
     float* Ek = chain_energies ? chain_energies + (int64_t)k * R : E;
     float* Nk = chain_grad_norms ? chain_grad_norms + (int64_t)k * R : nrm;
