@@ -126,6 +126,10 @@ SIGNATURES = {
     'ibc_pixel_train_grads': (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_int64,
                                       POINTER(LossCfg), c_int64, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p]),
+    'ibc_pixel_train_begin': (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_void_p,
+                                      c_void_p]),
+    'ibc_pixel_train_finish': (c_int, [c_void_p, c_void_p, POINTER(LossCfg), c_int64, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p]),
     'ibc_kernel_status': (c_int, [c_void_p, POINTER(c_int32)]),
     'ibc_set_profiling': (c_int, [c_void_p, c_int32]),
     'ibc_get_train_timings': (c_int, [c_void_p, POINTER(c_float)]),

@@ -23,6 +23,9 @@ struct ibc_pixel_handle {
   ibc_handle core;          // workspaces, error string, launch accounting
   ibc_pixel_arch arch;
   const float* params = nullptr;
+  // ibc_pixel_train_begin .. ibc_pixel_train_finish: the encoder pass of a training step
+  // whose saved activations wait in core.ws (ibc::PendingTrain; null when none is open)
+  void* pending = nullptr;
 };
 
 namespace ibc {
@@ -650,15 +653,18 @@ size_t val_bytes(const PixelLayout& L, int64_t B, int64_t R) {
          Workspace::rounded((size_t)L.count * 4) + Workspace::rounded((size_t)(L.Wq + 4) * 4);
 }
 
-void carve_val(ibc_handle* h, const PixelLayout& L, int64_t B, int64_t R, ValSave* v) {
+// The sampler entry points (energy, DFO, dE/dact, Langevin) carve from core.ws_outer, the
+// training pass from core.ws: a chain may run between ibc_pixel_train_begin and
+// ibc_pixel_train_finish without touching the encoder activations saved in core.ws.
+void carve_val(Workspace& w, const PixelLayout& L, int64_t B, int64_t R, ValSave* v) {
   const int nb = L.nblk > 0 ? L.nblk : 1;
   v->R = R;
-  v->encp = h->ws.take<float>((size_t)B * L.Wv);
-  v->X = h->ws.take<float>((size_t)(L.nblk + 1) * R * L.Wv);
-  v->Y0 = h->ws.take<float>((size_t)nb * R * L.Wq);
-  v->Y1 = h->ws.take<float>((size_t)nb * R * L.Wq);
-  v->wr = h->ws.take<float>((size_t)L.count);
-  v->ctop = h->ws.take<float>((size_t)L.Wq + 4);
+  v->encp = w.take<float>((size_t)B * L.Wv);
+  v->X = w.take<float>((size_t)(L.nblk + 1) * R * L.Wv);
+  v->Y0 = w.take<float>((size_t)nb * R * L.Wq);
+  v->Y1 = w.take<float>((size_t)nb * R * L.Wq);
+  v->wr = w.take<float>((size_t)L.count);
+  v->ctop = w.take<float>((size_t)L.Wq + 4);
 }
 
 // The part of the value head that does not depend on the actions: the tf32-rounded copy of
@@ -842,12 +848,12 @@ size_t val_rev_bytes(const PixelLayout& L, int64_t R, bool keep) {
          2 * Workspace::rounded((size_t)lq * R * L.Wq * 4);
 }
 
-void carve_val_rev(ibc_handle* h, const PixelLayout& L, int64_t R, bool keep, ValRev* r) {
+void carve_val_rev(Workspace& w, const PixelLayout& L, int64_t R, bool keep, ValRev* r) {
   const int lv = keep ? L.nblk + 1 : 2, lq = keep ? (L.nblk > 0 ? L.nblk : 1) : 1;
   r->R = R; r->Wv = L.Wv; r->Wq = L.Wq; r->keep = keep;
-  r->G = h->ws.take<float>((size_t)lv * R * L.Wv);
-  r->g0 = h->ws.take<float>((size_t)lq * R * L.Wq);
-  r->g1 = h->ws.take<float>((size_t)lq * R * L.Wq);
+  r->G = w.take<float>((size_t)lv * R * L.Wv);
+  r->g0 = w.take<float>((size_t)lq * R * L.Wq);
+  r->g1 = w.take<float>((size_t)lq * R * L.Wq);
 }
 
 // dEda [R, A] = +dE/dact for the rows value_fwd has just evaluated into `v`.
@@ -923,7 +929,7 @@ int value_grad_penalty(ibc_pixel_handle* ph, const PixelLayout& L, int64_t B, in
   const bool tc = h->precision == IBC_PRECISION_TF32;
   const float* PB = tc ? v.wr : P;
   ValRev rv;
-  carve_val_rev(h, L, R, true, &rv);
+  carve_val_rev(h->ws, L, R, true, &rv);
   float* dEda = h->ws.take<float>((size_t)R * A);
   float* cot = h->ws.take<float>((size_t)R * A);
   float* gl = h->ws.take<float>((size_t)B);
@@ -982,6 +988,21 @@ size_t val_gp_bytes(const PixelLayout& L, int64_t B, int64_t R) {
   return val_rev_bytes(L, R, true) + 2 * Workspace::rounded((size_t)R * L.A * 4) +
          Workspace::rounded((size_t)B * 4) + 2 * Workspace::rounded((size_t)R * L.Wv * 4) +
          2 * Workspace::rounded((size_t)R * L.Wq * 4);
+}
+
+// An open training step (ibc_pixel_train_begin): everything carved from core.ws.
+struct PendingTrain {
+  int64_t B = 0, N = 0;
+  int precision = 0;
+  const float* params = nullptr;
+  EncSave sv;
+  ValSave v;
+  float *dA = nullptr, *dB = nullptr, *enc = nullptr, *dEnc = nullptr, *E = nullptr, *dE = nullptr;
+};
+
+void drop_pending(ibc_pixel_handle* ph) {
+  delete static_cast<PendingTrain*>(ph->pending);
+  ph->pending = nullptr;
 }
 
 int check_arch(ibc_handle* h, const ibc_pixel_arch& a) {
@@ -1055,6 +1076,7 @@ int ibc_pixel_destroy(ibc_pixel_handle* ph) {
   if (ph->core.ws_outer.base) cudaFree(ph->core.ws_outer.base);
   if (ph->core.dev_status) cudaFree(ph->core.dev_status);
   if (prev >= 0) cudaSetDevice(prev);
+  drop_pending(ph);
   delete ph;
   return IBC_OK;
 }
@@ -1067,6 +1089,7 @@ int ibc_pixel_set_precision(ibc_pixel_handle* ph, int precision) {
   PIX_ENTER(ph);
   if (precision != IBC_PRECISION_FP32 && precision != IBC_PRECISION_TF32)
     IBC_FAIL(h, IBC_ERR_INVALID, "unknown precision %d", precision);
+  drop_pending(ph);
   h->precision = precision;
   return IBC_OK;
 }
@@ -1089,6 +1112,7 @@ int ibc_pixel_kernel_status(ibc_pixel_handle* ph, int32_t* status_host) {
 int ibc_pixel_bind_params(ibc_pixel_handle* ph, const float* params) {
   PIX_ENTER(ph);
   if (!params) IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_bind_params: null params");
+  drop_pending(ph);
   ph->params = params;
   return IBC_OK;
 }
@@ -1096,6 +1120,7 @@ int ibc_pixel_bind_params(ibc_pixel_handle* ph, const float* params) {
 int ibc_pixel_encode(ibc_pixel_handle* ph, const void* images, int32_t is_uint8, int64_t B,
                      float* enc, void* stream) {
   PIX_ENTER(ph);
+  drop_pending(ph);   // core.ws is re-carved below
   if (!images || !enc || B < 1) IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_encode: bad argument");
   if (!ph->params) IBC_FAIL(h, IBC_ERR_INVALID, "no parameters bound (ibc_pixel_bind_params)");
   const PixelLayout L = make_pixel_layout(ph->arch);
@@ -1116,10 +1141,10 @@ int ibc_pixel_energy(ibc_pixel_handle* ph, const float* enc, int64_t B, const fl
     IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_energy: bad argument");
   if (!ph->params) IBC_FAIL(h, IBC_ERR_INVALID, "no parameters bound (ibc_pixel_bind_params)");
   const PixelLayout L = make_pixel_layout(ph->arch);
-  IBC_CUDA(h, h->ws.reserve(val_bytes(L, B, B * n)));
-  h->ws.reset();
+  IBC_CUDA(h, h->ws_outer.reserve(val_bytes(L, B, B * n)));
+  h->ws_outer.reset();
   ValSave v;
-  carve_val(h, L, B, B * n, &v);
+  carve_val(h->ws_outer, L, B, B * n, &v);
   v.top = top_shortcut_ok(L);
   return value_fwd(ph, L, enc, B, act, n, v, energy, (cudaStream_t)stream);
 }
@@ -1134,13 +1159,21 @@ int ibc_pixel_dfo(ibc_pixel_handle* ph, const float* enc, int64_t B, float* acti
   if (!ph->params) IBC_FAIL(h, IBC_ERR_INVALID, "no parameters bound (ibc_pixel_bind_params)");
   const PixelLayout L = make_pixel_layout(ph->arch);
   cudaStream_t s = (cudaStream_t)stream;
+  // dfo_generic keeps its own buffers at the start of core.ws_outer (reserved here together
+  // with the value head's, so that its reserve is a no-op); the energy pass carves behind them
+  const int64_t R = B * n;
+  IBC_CUDA(h, h->ws_outer.reserve(2 * Workspace::rounded((size_t)R * 4) +
+                                  Workspace::rounded((size_t)R * 8) +
+                                  Workspace::rounded((size_t)R * ph->arch.act_dim * 4) +
+                                  val_bytes(L, B, R)));
   auto energy_fn = [&](const float* acts, float* E) -> int {
-    IBC_CUDA(h, h->ws.reserve(val_bytes(L, B, B * n)));
-    h->ws.reset();
+    const size_t mark = h->ws_outer.used;
     ValSave v;
-    carve_val(h, L, B, B * n, &v);
+    carve_val(h->ws_outer, L, B, R, &v);
     v.top = top_shortcut_ok(L);
-    return value_fwd(ph, L, enc, B, acts, n, v, E, s);
+    const int rc = value_fwd(ph, L, enc, B, acts, n, v, E, s);
+    h->ws_outer.used = mark;
+    return rc;
   };
   return dfo_generic(h, ph->arch.act_dim, B, actions, n, min_actions, max_actions, temperature,
                      num_iterations, iteration_std, uniforms, normals, seed, probs, energy_fn, s);
@@ -1154,13 +1187,13 @@ int ibc_pixel_energy_dact(ibc_pixel_handle* ph, const float* enc, int64_t B, con
   if (!ph->params) IBC_FAIL(h, IBC_ERR_INVALID, "no parameters bound (ibc_pixel_bind_params)");
   const PixelLayout L = make_pixel_layout(ph->arch);
   const int64_t R = B * n;
-  IBC_CUDA(h, h->ws.reserve(val_bytes(L, B, R) + val_rev_bytes(L, R, false)));
-  h->ws.reset();
+  IBC_CUDA(h, h->ws_outer.reserve(val_bytes(L, B, R) + val_rev_bytes(L, R, false)));
+  h->ws_outer.reset();
   ValSave v;
-  carve_val(h, L, B, R, &v);
+  carve_val(h->ws_outer, L, B, R, &v);
   v.top = top_shortcut_ok(L);
   ValRev rv;
-  carve_val_rev(h, L, R, false, &rv);
+  carve_val_rev(h->ws_outer, L, R, false, &rv);
   IBC_TRY(value_fwd(ph, L, enc, B, act, n, v, energy, (cudaStream_t)stream));
   return value_dact(ph, L, v, rv, dE_dact, (cudaStream_t)stream);
 }
@@ -1186,17 +1219,17 @@ int ibc_pixel_langevin(ibc_pixel_handle* ph, const float* enc, int64_t B, float*
   const int64_t R = B * n;
   std::vector<float> steps;
   langevin_stepsizes(*cfg, &steps);
-  IBC_CUDA(h, h->ws.reserve(val_bytes(L, B, R) + val_rev_bytes(L, R, false) +
-                            2 * Workspace::rounded((size_t)R * 4) +
-                            Workspace::rounded((size_t)R * A * 4)));
-  h->ws.reset();
+  IBC_CUDA(h, h->ws_outer.reserve(val_bytes(L, B, R) + val_rev_bytes(L, R, false) +
+                                  2 * Workspace::rounded((size_t)R * 4) +
+                                  Workspace::rounded((size_t)R * A * 4)));
+  h->ws_outer.reset();
   ValSave v;
-  carve_val(h, L, B, R, &v);
+  carve_val(h->ws_outer, L, B, R, &v);
   ValRev rv;
-  carve_val_rev(h, L, R, false, &rv);
-  float* E = h->ws.take<float>(R);
-  float* nrm = h->ws.take<float>(R);
-  float* dEda = h->ws.take<float>((size_t)R * A);
+  carve_val_rev(h->ws_outer, L, R, false, &rv);
+  float* E = h->ws_outer.take<float>(R);
+  float* nrm = h->ws_outer.take<float>(R);
+  float* dEda = h->ws_outer.take<float>((size_t)R * A);
   // the encoding is fixed along the chain: its projection and the rounded weights once
   v.top = top_shortcut_ok(L);
   if (cfg->num_iterations > 0) IBC_TRY(value_prepare(ph, L, enc, B, v, s));
@@ -1216,19 +1249,12 @@ int ibc_pixel_langevin(ibc_pixel_handle* ph, const float* enc, int64_t B, float*
   return IBC_OK;
 }
 
-int ibc_pixel_train_grads(ibc_pixel_handle* ph, const void* images, int32_t is_uint8, int64_t B,
-                          const float* actions, int64_t N, const ibc_loss_cfg* cfg,
-                          int64_t global_batch, float* per_example_loss, float* grad_loss,
-                          float* energies, float* grads, void* stream) {
+int ibc_pixel_train_begin(ibc_pixel_handle* ph, const void* images, int32_t is_uint8, int64_t B,
+                          int64_t N, float* enc_out, void* stream) {
   PIX_ENTER(ph);
-  if (!images || !actions || !cfg || !per_example_loss || !grads || B < 1 || N < 0 ||
-      global_batch < 1)
-    IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_train_grads: bad argument");
+  drop_pending(ph);
+  if (!images || B < 1 || N < 0) IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_train_begin: bad argument");
   if (!ph->params) IBC_FAIL(h, IBC_ERR_INVALID, "no parameters bound (ibc_pixel_bind_params)");
-  if (cfg->grad_norm_type < IBC_NORM_NONE || cfg->grad_norm_type > IBC_NORM_INF)
-    IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_train_grads: unknown grad_norm_type %d",
-             cfg->grad_norm_type);
-  const bool gp = cfg->add_grad_penalty != 0 && cfg->grad_norm_type != IBC_NORM_NONE;
   cudaStream_t s = (cudaStream_t)stream;
   const PixelLayout L = make_pixel_layout(ph->arch);
   const EncDims d = enc_dims(ph->arch);
@@ -1242,36 +1268,74 @@ int ibc_pixel_train_grads(ibc_pixel_handle* ph, const void* images, int32_t is_u
                  2 * Workspace::rounded(dmax * 4) + 2 * Workspace::rounded((size_t)R * L.Wv * 4) +
                  2 * Workspace::rounded((size_t)R * L.Wq * 4) +
                  Workspace::rounded((size_t)B * L.Wv * 4) + 2 * Workspace::rounded((size_t)B * kEnc * 4) +
-                 2 * Workspace::rounded((size_t)R * 4) + (1 << 16);
-  if (gp) bytes += val_gp_bytes(L, B, R);
+                 2 * Workspace::rounded((size_t)R * 4) + val_gp_bytes(L, B, R) + (1 << 16);
   IBC_CUDA(h, h->ws.reserve(bytes));
   h->ws.reset();
-  EncSave sv;
-  carve_enc(h, ph->arch, B, chunk, tc, &sv);
-  ValSave v;
-  carve_val(h, L, B, R, &v);
-  float* dA = h->ws.take<float>(dmax);
-  float* dB = h->ws.take<float>(dmax);
-  float* enc = h->ws.take<float>((size_t)B * kEnc);
-  float* dEnc = h->ws.take<float>((size_t)B * kEnc);
-  float* E = h->ws.take<float>(R);
-  float* dE = h->ws.take<float>(R);
+  PendingTrain* pt = new PendingTrain;
+  pt->B = B; pt->N = N; pt->precision = h->precision; pt->params = ph->params;
+  carve_enc(h, ph->arch, B, chunk, tc, &pt->sv);
+  carve_val(h->ws, L, B, R, &pt->v);
+  pt->dA = h->ws.take<float>(dmax);
+  pt->dB = h->ws.take<float>(dmax);
+  pt->enc = h->ws.take<float>((size_t)B * kEnc);
+  pt->dEnc = h->ws.take<float>((size_t)B * kEnc);
+  pt->E = h->ws.take<float>(R);
+  pt->dE = h->ws.take<float>(R);
+  const int rc = encode_fwd(ph, L, images, is_uint8, B, pt->sv, pt->enc, s);
+  if (rc != IBC_OK) { delete pt; return rc; }
+  if (enc_out)
+    IBC_CUDA(h, cudaMemcpyAsync(enc_out, pt->enc, (size_t)B * kEnc * 4, cudaMemcpyDeviceToDevice, s));
+  ph->pending = pt;
+  return IBC_OK;
+}
+
+int ibc_pixel_train_finish(ibc_pixel_handle* ph, const float* actions, const ibc_loss_cfg* cfg,
+                           int64_t global_batch, float* per_example_loss, float* grad_loss,
+                           float* energies, float* grads, void* stream) {
+  PIX_ENTER(ph);
+  PendingTrain* pt = static_cast<PendingTrain*>(ph->pending);
+  if (!pt)
+    IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_train_finish: no open ibc_pixel_train_begin (any "
+                                 "encode / parameter / precision call on the handle closes it)");
+  struct Close { ibc_pixel_handle* p; ~Close() { drop_pending(p); } } close{ph};
+  if (!actions || !cfg || !per_example_loss || !grads || global_batch < 1)
+    IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_train_finish: bad argument");
+  if (cfg->grad_norm_type < IBC_NORM_NONE || cfg->grad_norm_type > IBC_NORM_INF)
+    IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_train_finish: unknown grad_norm_type %d",
+             cfg->grad_norm_type);
+  const bool gp = cfg->add_grad_penalty != 0 && cfg->grad_norm_type != IBC_NORM_NONE;
+  cudaStream_t s = (cudaStream_t)stream;
+  const PixelLayout L = make_pixel_layout(ph->arch);
+  const int64_t B = pt->B, n1 = pt->N + 1, R = B * n1;
   IBC_CUDA(h, cudaMemsetAsync(grads, 0, (size_t)L.count * 4, s));
-  IBC_TRY(encode_fwd(ph, L, images, is_uint8, B, sv, enc, s));
-  IBC_TRY(value_fwd(ph, L, enc, B, actions, n1, v, E, s));
+  IBC_TRY(value_fwd(ph, L, pt->enc, B, actions, n1, pt->v, pt->E, s));
   if (energies)
-    IBC_CUDA(h, cudaMemcpyAsync(energies, E, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
-  IBC_TRY(info_nce(h, E, B, n1, cfg->softmax_temperature, 1.0f / (float)global_batch,
-                   per_example_loss, dE, s));
-  IBC_TRY(value_bwd(ph, L, enc, B, actions, n1, v, dE, grads, dEnc, s));
-  IBC_TRY(encode_bwd(ph, L, B, sv, dEnc, grads, dA, dB, s));
+    IBC_CUDA(h, cudaMemcpyAsync(energies, pt->E, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
+  IBC_TRY(info_nce(h, pt->E, B, n1, cfg->softmax_temperature, 1.0f / (float)global_batch,
+                   per_example_loss, pt->dE, s));
+  IBC_TRY(value_bwd(ph, L, pt->enc, B, actions, n1, pt->v, pt->dE, grads, pt->dEnc, s));
+  IBC_TRY(encode_bwd(ph, L, B, pt->sv, pt->dEnc, grads, pt->dA, pt->dB, s));
   if (gp) {
-    IBC_TRY(value_grad_penalty(ph, L, B, n1, v, *cfg, 1.0f / (float)global_batch,
+    IBC_TRY(value_grad_penalty(ph, L, B, n1, pt->v, *cfg, 1.0f / (float)global_batch,
                                per_example_loss, grad_loss, grads, s));
   } else if (grad_loss) {
     IBC_CUDA(h, cudaMemsetAsync(grad_loss, 0, (size_t)B * 4, s));
   }
   return IBC_OK;
+}
+
+int ibc_pixel_train_grads(ibc_pixel_handle* ph, const void* images, int32_t is_uint8, int64_t B,
+                          const float* actions, int64_t N, const ibc_loss_cfg* cfg,
+                          int64_t global_batch, float* per_example_loss, float* grad_loss,
+                          float* energies, float* grads, void* stream) {
+  if (ph && (!actions || !cfg || !per_example_loss || !grads || global_batch < 1)) {
+    ibc_handle* h = &ph->core;
+    IBC_FAIL(h, IBC_ERR_INVALID, "ibc_pixel_train_grads: bad argument");
+  }
+  const int rc = ibc_pixel_train_begin(ph, images, is_uint8, B, N, nullptr, stream);
+  if (rc != IBC_OK) return rc;
+  return ibc_pixel_train_finish(ph, actions, cfg, global_batch, per_example_loss, grad_loss,
+                                energies, grads, stream);
 }
 
 int ibc_conv3x3_tf32(const float* X, int64_t nb, int32_t H, int32_t W, int32_t C, const float* K,

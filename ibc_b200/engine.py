@@ -360,6 +360,40 @@ class PixelEngine:
                self._h, pixel=True)
     return (ca, ce, cg) if return_chain else None
 
+  def train_begin(self, images, num_counter_examples) -> torch.Tensor:
+    """First half of train_grads: the encoder pass (activations stay in the handle);
+    returns the encoding [B, 256] for the counter-example sampler."""
+    b, is_u8 = self._check_images(images)
+    enc = torch.empty(b, 256, device=images.device, dtype=torch.float32)
+    _lib.check(self.lib.ibc_pixel_train_begin(self._h, _ptr(images), is_u8, b,
+                                              int(num_counter_examples), _ptr(enc), _stream()),
+               self._h, pixel=True)
+    self._open = (b, int(num_counter_examples))
+    return enc
+
+  def train_finish(self, actions, cfg: LossCfg, global_batch,
+                   grads: Optional[torch.Tensor] = None, want_energies=False):
+    """Second half: (per_example_loss, grad_loss, energies or None, grads)."""
+    opened = getattr(self, '_open', None)
+    if opened is None:
+      raise _lib.IbcError('train_finish without train_begin')
+    self._open = None
+    b, n = opened
+    _check_f32(actions, 'actions')
+    if tuple(actions.shape) != (b * (n + 1), self.act_dim):
+      raise ValueError('actions must be [B*(N+1), A]')
+    if grads is None:
+      grads = torch.empty(self.param_count, device=actions.device, dtype=torch.float32)
+    per_example = torch.empty(b, device=actions.device, dtype=torch.float32)
+    grad_loss = torch.empty(b, device=actions.device, dtype=torch.float32)
+    energies = torch.empty(b * (n + 1), device=actions.device, dtype=torch.float32) \
+        if want_energies else None
+    _lib.check(self.lib.ibc_pixel_train_finish(self._h, _ptr(actions), ctypes.byref(cfg),
+                                               int(global_batch), _ptr(per_example),
+                                               _ptr(grad_loss), _ptr(energies), _ptr(grads),
+                                               _stream()), self._h, pixel=True)
+    return per_example, grad_loss, energies, grads
+
   def train_grads(self, images, actions, num_counter_examples, cfg: LossCfg, global_batch,
                   grads: Optional[torch.Tensor] = None, want_energies=False,
                   want_grad_loss=False):

@@ -235,11 +235,23 @@ class ImplicitBCAgent(BehavioralCloningAgent):
     expanded_actions = actions[:, None, :]
     # negatives: uniform, optionally refined by DFO / Langevin on the value head over one
     # encoding of the un-tiled observations (ibc_agent.py:340-475 with late fusion)
-    counter, combined, chain_data = self._make_counter_example_actions(
-        images, expanded_actions, batch_size, training, draws)
     global_batch = batch_size * self._num_replicas()
-    per_example, grad_loss, _, grads = net.engine.train_grads(
-        images, combined, n, self._loss_cfg(), global_batch, self._grads, want_grad_loss=True)
+    if self._fraction_dfo_samples > 0. or self._fraction_langevin_samples > 0.:
+      # one encoder pass serves the sampler and the backward (upstream encodes twice, with
+      # identical results: the encoder has no dropout / batch norm)
+      self._enc = net.engine.train_begin(images, n)
+      try:
+        counter, combined, chain_data = self._make_counter_example_actions(
+            images, expanded_actions, batch_size, training, draws)
+      finally:
+        self._enc = None
+      per_example, grad_loss, _, grads = net.engine.train_finish(
+          combined, self._loss_cfg(), global_batch, self._grads)
+    else:
+      counter, combined, chain_data = self._make_counter_example_actions(
+          images, expanded_actions, batch_size, training, draws)
+      per_example, grad_loss, _, grads = net.engine.train_grads(
+          images, combined, n, self._loss_cfg(), global_batch, self._grads, want_grad_loss=True)
     total_loss = _scaled_sum(per_example, 1.0 / float(global_batch))
     losses_dict = {'ebm_total_loss': total_loss}
     if self._add_grad_penalty:
@@ -287,14 +299,19 @@ class ImplicitBCAgent(BehavioralCloningAgent):
         if self._return_full_chain:
           raise NotImplementedError('Not implemented to return dfo chain.')   # :374-375
         dfo_actions = random_uniform.clone()
-        dfo_obs = net.encode(obs_flat, training=False) if self._late_fusion else obs_flat
+        dfo_obs = obs_flat
+        if self._late_fusion:
+          dfo_obs = getattr(self, '_enc', None)
+          if dfo_obs is None:
+            dfo_obs = net.encode(obs_flat, training=False)
         net.engine.dfo(dfo_obs, dfo_actions, n, self._min, self._max, 1.0, 3, 0.33,
                        draws.get('dfo_uniforms'), draws.get('dfo_normals'), mcmc._next_seed())
       if self._fraction_langevin_samples > 0.:
         # late fusion: un-tiled frames, encoded once inside the sampler (mcmc.py:384-388;
         # upstream binds langevin_actions_given_obs.late_fusion in the gin file)
         tiled = obs_flat if self._late_fusion else torch.repeat_interleave(obs_flat, n, dim=0)
-        lf = {'late_fusion': True} if self._late_fusion else {}
+        lf = {'late_fusion': True,
+              'observation_encoding': getattr(self, '_enc', None)} if self._late_fusion else {}
         out = mcmc.langevin_actions_given_obs(
             net, tiled, random_uniform, policy_state=(), min_actions=self._min,
             max_actions=self._max, num_action_samples=n, training=False,

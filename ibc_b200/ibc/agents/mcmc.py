@@ -295,8 +295,11 @@ def langevin_actions_given_obs(
     late_fusion=False,
     *,
     normal_draws=None,
-    seed=None):
-  """mcmc.py:330-425.  normal_draws [num_iterations, B*n, A] float32."""
+    seed=None,
+    observation_encoding=None):
+  """mcmc.py:330-425.  normal_draws [num_iterations, B*n, A] float32.
+  observation_encoding (late fusion on a PixelEBM only): the [B, 256] encoding of
+  `observations` when the caller already has it (skips the encode of :384-388)."""
   if not stop_chain_grad:
     raise NotImplementedError('stop_chain_grad=False (gradients through the chain) is not built; '
                               'no shipped gin uses it')
@@ -326,7 +329,8 @@ def langevin_actions_given_obs(
                            noise_scale, grad_clip, delta_action_clip, use_polynomial_rate,
                            sampler_stepsize_final, sampler_stepsize_power, grad_norm_type,
                            apply_exp)
-    enc = energy_network.encode(observations, training=training)
+    enc = observation_encoding if observation_encoding is not None else \
+        energy_network.encode(observations, training=training)
     if enc.shape[0] * n != r:
       raise ValueError('late fusion expects un-tiled observations: %d x %d != %d'
                        % (enc.shape[0], n, r))

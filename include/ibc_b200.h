@@ -320,6 +320,24 @@ int ibc_pixel_train_grads(ibc_pixel_handle* h, const void* images, int32_t is_ui
                           float* per_example_loss, float* grad_loss,
                           float* energies, float* grads, void* stream);
 
+/* ibc_pixel_train_grads in two calls, so that the counter-example sampler can run on the
+ * encoding of the SAME encoder pass the backward uses (the reference encodes twice:
+ * once inside langevin_actions_given_obs, mcmc.py:384-388, once in _loss,
+ * ibc_agent.py:191-197; the encoder has no dropout / batch norm, so both passes
+ * give the same [B, 256]).  begin runs encode (training=True) keeping its
+ * activations in the handle and writes enc_out [B, 256] (nullable); finish takes
+ * the combined actions [B*(N+1), A] and does the rest of ibc_pixel_train_grads.
+ * Between the two only the sampler entry points (ibc_pixel_energy / _energy_dact /
+ * _dfo / _langevin) may be called on the handle; ibc_pixel_encode, _bind_params,
+ * _set_precision or another begin discard the open step, and finish then fails
+ * with IBC_ERR_INVALID. */
+int ibc_pixel_train_begin(ibc_pixel_handle* h, const void* images, int32_t is_uint8,
+                          int64_t B, int64_t N, float* enc_out, void* stream);
+int ibc_pixel_train_finish(ibc_pixel_handle* h, const float* actions,
+                           const ibc_loss_cfg* cfg, int64_t global_batch,
+                           float* per_example_loss, float* grad_loss,
+                           float* energies, float* grads, void* stream);
+
 /* ---- diagnostics ------------------------------------------------------- */
 
 /* Number of kernels this library has launched since the handle was created

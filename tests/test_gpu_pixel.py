@@ -427,3 +427,39 @@ def test_late_fusion_agent_with_langevin_negatives_and_grad_penalty():
     assert tuple(a.shape) == (1, 2) and bool((a.abs() <= 1.0).all())
   finally:
     gin.clear_config()
+
+
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_train_begin_finish_equals_train_grads(precision):
+  """ibc_pixel_train_begin / _finish with sampler calls in between == ibc_pixel_train_grads."""
+  from ibc_b200 import _lib
+  from ibc_b200 import engine as eng
+  spec, b, n = SMALL, 4, 8
+  flat = _scaled_params(spec)
+  e = _engine_with(spec, flat, precision)
+  img = _images(spec, b, seed=12).cuda()
+  g = torch.Generator().manual_seed(13)
+  act = (torch.rand(b * (n + 1), 2, generator=g) * 2 - 1).cuda()
+  cfg = eng.loss_cfg(1.0, True, 'inf', 0.05)
+  per0, gl0, en0, gr0 = e.train_grads(img, act, n, cfg, b, want_energies=True, want_grad_loss=True)
+  gr0 = gr0.clone()
+  enc_ref = e.encode(img)
+  enc = e.train_begin(img, n)
+  assert torch.equal(enc, enc_ref)
+  # sampler traffic on the handle between the two halves
+  mn, mx = torch.full((2,), -1.1).cuda(), torch.full((2,), 1.1).cuda()
+  neg = (torch.rand(b * n, 2, generator=g) * 2 - 1).cuda()
+  e.langevin(enc, neg, n, mn, mx, eng.langevin_cfg(5), None, 3)
+  e.dfo(enc, neg.clone(), n, mn, mx, seed=4)
+  e.energy_dact(enc, neg, n)
+  per1, gl1, en1, gr1 = e.train_finish(act, cfg, b, want_energies=True)
+  assert e.kernel_status() == 0
+  assert torch.equal(en0, en1) and torch.equal(per0, per1) and torch.equal(gl0, gl1)
+  assert _fro(gr1, gr0) < 1e-5        # split-K atomics order only
+  # a discarded step fails loudly
+  e.train_begin(img, n)
+  e.encode(img)
+  with pytest.raises(ValueError):      # IBC_ERR_INVALID from the library
+    e.train_finish(act, cfg, b)
+  with pytest.raises(_lib.IbcError):   # the wrapper's own guard
+    e.train_finish(act, cfg, b)
