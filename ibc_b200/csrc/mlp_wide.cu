@@ -285,6 +285,55 @@ __global__ void t1_gtop_kernel(const float* __restrict__ dE, const float* __rest
                  tf32_rn_bits(__float_as_uint(v.z)), tf32_rn_bits(__float_as_uint(v.w)));
 }
 
+// Energy without the last block's second product: h_L = h + a . W2 + b2 gives
+// E = h . we + a . (W2 we) + (b2 . we + be), so with c2[0:W] = W2_last . we and
+// c2[W] = b2_last . we + be (fp32, two row-dot launches)
+//   E[r] = hs[r, :] . we + aop[r, :] . c2[0:W] + c2[W]
+// over the T1 stream hs and the T1 operand aop = relu(h . W1 + b1) of the last block.
+__global__ void t1_rowdot_top_kernel(const float* __restrict__ hs, const float* __restrict__ we,
+                                     const float* __restrict__ aop, const float* __restrict__ c2,
+                                     int64_t R, int W, float* __restrict__ E) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int64_t base = (r >> 7) * (int64_t)(W / 4) * 128 + (r & 127);
+  const float4* t = reinterpret_cast<const float4*>(hs) + base;
+  const float4* a = reinterpret_cast<const float4*>(aop) + base;
+  float e = 0.f, f = 0.f;
+  for (int c = 0; c < W / 4; ++c) {
+    const float4 v = t[(int64_t)c * 128];
+    const float4 w = *reinterpret_cast<const float4*>(we + c * 4);
+    e = fmaf(v.x, w.x, e); e = fmaf(v.y, w.y, e); e = fmaf(v.z, w.z, e); e = fmaf(v.w, w.w, e);
+    const float4 u = a[(int64_t)c * 128];
+    const float4 q = *reinterpret_cast<const float4*>(c2 + c * 4);
+    f = fmaf(u.x, q.x, f); f = fmaf(u.y, q.y, f); f = fmaf(u.z, q.z, f); f = fmaf(u.w, q.w, f);
+  }
+  E[r] = e + f + c2[W];
+}
+
+// The reverse chain's first product on the same vector: every row of G_top is dE[r] * we, so
+// mask(v_last) (.) (G_top . W2_last^T) = mask (.) (dE[r] * c2): the T1 operand without a GEMM.
+__global__ void t1_utop_kernel(const float* __restrict__ dE, const float* __restrict__ c2,
+                               const uint32_t* __restrict__ mask, int64_t R, int W,
+                               float* __restrict__ uop) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (tile, chunk, row)
+  const int64_t per_tile = (int64_t)(W / 4) * 128;
+  const int64_t tile = i / per_tile;
+  const int64_t rem = i - tile * per_tile;
+  const int c = (int)(rem >> 7), row = (int)(rem & 127);
+  const int64_t r = tile * 128 + row;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (r < R) {
+    const float de = dE ? dE[r] : 1.0f;
+    const uint32_t nib = (mask[r * (W / 32) + (c >> 3)] >> ((c & 7) * 4)) & 15u;
+    const float4 q = *reinterpret_cast<const float4*>(c2 + c * 4);
+    if (nib & 1u) o.x = tf32_rn_bits(__float_as_uint(de * q.x));
+    if (nib & 2u) o.y = tf32_rn_bits(__float_as_uint(de * q.y));
+    if (nib & 4u) o.z = tf32_rn_bits(__float_as_uint(de * q.z));
+    if (nib & 8u) o.w = tf32_rn_bits(__float_as_uint(de * q.w));
+  }
+  reinterpret_cast<uint4*>(uop)[i] = o;
+}
+
 // T1 -> row-major [R, W]
 __global__ void t1_to_rowmajor_kernel(const float* __restrict__ t1, int64_t R, int W,
                                       float* __restrict__ x) {
@@ -334,9 +383,10 @@ int mlp_energy_wide(ibc_handle* h, const float* obs, int64_t B, const float* act
   const size_t mask_words = dEda ? (size_t)tiles * 128 * (W / 32) * (2 * nb) : 0;
   const size_t bytes = Workspace::rounded((size_t)B * W * 4) + Workspace::rounded((size_t)R * W * 4) +
                        3 * Workspace::rounded(t1 * 4) + Workspace::rounded(mask_words * 4) +
-                       Workspace::rounded((size_t)R * 4);
+                       Workspace::rounded((size_t)R * 4) + Workspace::rounded((size_t)(W + 4) * 4);
   IBC_CUDA(h, h->ws.reserve(bytes));
   h->ws.reset();
+  float* c2 = h->ws.take<float>((size_t)W + 4);      // W2_last . we, then b2_last . we + be
   float* hp = h->ws.take<float>((size_t)B * W);
   float* rowm = h->ws.take<float>((size_t)R * W);     // first-layer output / g0, row-major
   float* hs = h->ws.take<float>(t1);                  // residual stream (forward), G (reverse)
@@ -345,6 +395,12 @@ int mlp_energy_wide(ibc_handle* h, const float* obs, int64_t B, const float* act
   uint32_t* masks = mask_words ? h->ws.take<uint32_t>(mask_words) : nullptr;
   float* dE = h->ws.take<float>(R);
   if (h->packed_stale) IBC_TRY(wide_pack(h, s));
+  // the last block's second product collapses onto the vector W2 we in both directions
+  // Measured (scripts/time_langevin.py): 0.92 -> 0.85 ms for energy + dE/dact at W = 2048, D = 2,
+  // nothing at W = 512, D = 8 (two of sixteen 17 us products against four small launches), so
+  // it is on from W = 1024; IBC_WIDE_TOP=1 / IBC_WIDE_NO_TOP=1 force it on / off.
+  static const int top_env = getenv("IBC_WIDE_TOP") ? 1 : (getenv("IBC_WIDE_NO_TOP") ? -1 : 0);
+  const bool top = top_env > 0 || (top_env == 0 && W >= 1024);
   const size_t mslot = (size_t)tiles * 128 * (W / 32);
   const int64_t WW = (int64_t)W * W;
 
@@ -371,6 +427,7 @@ int mlp_energy_wide(ibc_handle* h, const float* obs, int64_t B, const float* act
     v.K = W; v.N = W; v.relu = 1; v.status = h->dev_status;
     IBC_TRY(dense_wide(h, v, tiles, s));
     const bool last = (j == nb - 1);
+    if (last && top) break;   // E below from hs, aop and c2: h_L is never formed
     DenseParams u;      // h += a . W2 + b2 ; next operand relu(h)
     u.a = aop; u.w = h->packed + (int64_t)(2 * j + 1) * WW; u.bias = P + L.b2(j); u.res = hs;
     u.mask_in = nullptr; u.out_f = hs; u.out_op = last ? nullptr : hop;
@@ -378,7 +435,13 @@ int mlp_energy_wide(ibc_handle* h, const float* obs, int64_t B, const float* act
     u.K = W; u.N = W; u.relu = 1; u.status = h->dev_status;
     IBC_TRY(dense_wide(h, u, tiles, s));
   }
-  t1_rowdot_kernel<<<(unsigned)((R + 127) / 128), 128, 0, s>>>(hs, P + L.we, P + L.be, R, W, E);
+  if (top) {
+    IBC_TRY(rowdot(h, P + L.w2(nb - 1), W, P + L.we, nullptr, W, W, c2, s));
+    IBC_TRY(rowdot(h, P + L.b2(nb - 1), W, P + L.we, P + L.be, 1, W, c2 + W, s));
+    t1_rowdot_top_kernel<<<(unsigned)((R + 127) / 128), 128, 0, s>>>(hs, P + L.we, aop, c2, R, W, E);
+  } else {
+    t1_rowdot_kernel<<<(unsigned)((R + 127) / 128), 128, 0, s>>>(hs, P + L.we, P + L.be, R, W, E);
+  }
   IBC_LAUNCH_CHECK(h);
   if (!dEda) return IBC_OK;
 
@@ -397,11 +460,17 @@ int mlp_energy_wide(ibc_handle* h, const float* obs, int64_t B, const float* act
   const float* rev = h->packed + 2 * (int64_t)nb * WW;
   for (int j = nb - 1; j >= 0; --j) {
     const int m = 2 * (nb - 1 - j);
+    if (top && j == nb - 1) {   // constant-row product (t1_utop_kernel)
+      t1_utop_kernel<<<(unsigned)((t1_f4 + 255) / 256), 256, 0, s>>>(
+          de, c2, masks + (size_t)(2 * j + 1) * mslot, R, W, uop);
+      IBC_LAUNCH_CHECK(h);
+    } else {
     DenseParams u;      // u = mask(v_j) (.) (g . W2_j^T)
     u.a = gop; u.w = rev + (int64_t)m * WW; u.bias = nullptr; u.res = nullptr;
     u.mask_in = masks + (size_t)(2 * j + 1) * mslot; u.out_f = nullptr; u.out_op = uop;
     u.mask_out = nullptr; u.K = W; u.N = W; u.relu = 0; u.status = h->dev_status;
     IBC_TRY(dense_wide(h, u, tiles, s));
+    }
     DenseParams g;      // g += mask(h_j) (.) (u . W1_j^T)
     g.a = uop; g.w = rev + (int64_t)(m + 1) * WW; g.bias = nullptr; g.res = G;
     g.mask_in = masks + (size_t)(2 * j) * mslot; g.out_f = G; g.out_op = (j > 0) ? gop : nullptr;
