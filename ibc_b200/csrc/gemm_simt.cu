@@ -106,6 +106,92 @@ __global__ void rowdot_kernel(const float* __restrict__ X, int64_t ldx,
   if (lane == 0) E[r] = s + (b ? b[0] : 0.f);
 }
 
+// X[r, :] = encp[r / n, :] + sum_a act[r, a] * W[a, :]   (the action half of the value head's
+// first Dense layer: K = act_dim is far too short for an MMA tile, the product is a
+// bandwidth-bound rank-A update; one thread = 4 columns of one row, 16-byte stores)
+__global__ void act_rows_kernel(const float* __restrict__ act, const float* __restrict__ W,
+                                const float* __restrict__ encp, int64_t R, int64_t n, int A,
+                                int Wv, float* __restrict__ X) {
+  const int W4 = Wv / 4;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * W4) return;
+  const int c4 = (int)(i % W4);
+  const int64_t r = i / W4;
+  float4 v = *reinterpret_cast<const float4*>(encp + (r / n) * Wv + c4 * 4);
+  for (int a = 0; a < A; ++a) {
+    const float s = act[r * A + a];
+    const float4 w = *reinterpret_cast<const float4*>(W + (int64_t)a * Wv + c4 * 4);
+    v.x = fmaf(s, w.x, v.x); v.y = fmaf(s, w.y, v.y); v.z = fmaf(s, w.z, v.z); v.w = fmaf(s, w.w, v.w);
+  }
+  *reinterpret_cast<float4*>(X + r * Wv + c4 * 4) = v;
+}
+
+// Its reverse in one pass over G [B*n, Wv]: gsum[b, :] = sum of the group's rows (the
+// gradient of the tiled encoding projection) and dW[a, :] += sum_r act[r, a] * G[r, :].
+// grid (B, Wv / 128), block 256 = 32 column quads x 8 row lanes; A <= kMaxActRows.
+__global__ void act_rows_bwd_kernel(const float* __restrict__ G, const float* __restrict__ act,
+                                    int64_t n, int A, int Wv, float* __restrict__ gsum,
+                                    float* __restrict__ dW) {
+  __shared__ float4 part[8][32];
+  const int b = blockIdx.x, c4 = blockIdx.y * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 dw[kMaxActRows];
+#pragma unroll
+  for (int a = 0; a < kMaxActRows; ++a) dw[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = rl; i < n; i += 8) {
+    const int64_t r = (int64_t)b * n + i;
+    const float4 g = *reinterpret_cast<const float4*>(G + r * Wv + c4 * 4);
+    gs.x += g.x; gs.y += g.y; gs.z += g.z; gs.w += g.w;
+#pragma unroll
+    for (int a = 0; a < kMaxActRows; ++a) {
+      if (a < A) {
+        const float s = act[r * A + a];
+        dw[a].x = fmaf(s, g.x, dw[a].x); dw[a].y = fmaf(s, g.y, dw[a].y);
+        dw[a].z = fmaf(s, g.z, dw[a].z); dw[a].w = fmaf(s, g.w, dw[a].w);
+      }
+    }
+  }
+  auto reduce = [&](float4 v) -> float4 {      // sum over the 8 row lanes, result in lane row 0
+    part[rl][threadIdx.x & 31] = v;
+    __syncthreads();
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rl == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 q = part[k][threadIdx.x & 31];
+        t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
+      }
+    }
+    __syncthreads();
+    return t;
+  };
+  const float4 gt = reduce(gs);
+  if (rl == 0) *reinterpret_cast<float4*>(gsum + (int64_t)b * Wv + c4 * 4) = gt;
+  for (int a = 0; a < A; ++a) {
+    float4 pick = dw[0];
+#pragma unroll
+    for (int k = 1; k < kMaxActRows; ++k) if (k == a) pick = dw[k];
+    const float4 t = reduce(pick);
+    if (rl == 0) {
+      float* o = dW + (int64_t)a * Wv + c4 * 4;
+      atomicAdd(o, t.x); atomicAdd(o + 1, t.y); atomicAdd(o + 2, t.z); atomicAdd(o + 3, t.w);
+    }
+  }
+}
+
+
+// float4 form of rowfill_kernel (W4 = W / 4 column quads per row)
+__global__ void rowfill4_kernel(const float* __restrict__ v, const float* __restrict__ scale,
+                                int64_t R, int W4, float* __restrict__ G) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * W4) return;
+  const int64_t r = i / W4;
+  const int w4 = (int)(i - r * W4);
+  const float sc = scale ? scale[r] : 1.f;
+  const float4 x = *reinterpret_cast<const float4*>(v + w4 * 4);
+  *reinterpret_cast<float4*>(G + i * 4) = make_float4(sc * x.x, sc * x.y, sc * x.z, sc * x.w);
+}
+
 __global__ void rowfill_kernel(const float* __restrict__ v, const float* __restrict__ scale,
                                int64_t R, int W, float* __restrict__ G) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -193,7 +279,32 @@ int rowfill(ibc_handle* h, const float* v, const float* scale, int64_t R, int W,
             cudaStream_t s) {
   if (R <= 0) return IBC_OK;
   const int64_t tot = R * W;
-  rowfill_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(v, scale, R, W, G);
+  if ((W & 3) == 0 && ((reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(v)) & 15) == 0) {
+    rowfill4_kernel<<<(unsigned)((tot / 4 + 255) / 256), 256, 0, s>>>(v, scale, R, W / 4, G);
+  } else {
+    rowfill_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(v, scale, R, W, G);
+  }
+  IBC_LAUNCH_CHECK(h);
+  return IBC_OK;
+}
+
+int act_rows(ibc_handle* h, const float* act, const float* Wa, const float* rowbias, int64_t R,
+             int64_t n, int A, int W, float* X, cudaStream_t s) {
+  if (R <= 0) return IBC_OK;
+  if (W & 3) IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "act_rows: width must be a multiple of 4");
+  const int64_t tot = R * (W / 4);
+  act_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(act, Wa, rowbias, R, n, A, W, X);
+  IBC_LAUNCH_CHECK(h);
+  return IBC_OK;
+}
+
+int act_rows_bwd(ibc_handle* h, const float* G, const float* act, int64_t B, int64_t n, int A,
+                 int W, float* gsum, float* dW, cudaStream_t s) {
+  if (B <= 0) return IBC_OK;
+  if (A > kMaxActRows || W % 128)
+    IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "act_rows_bwd: needs act_dim <= %d and width %% 128 == 0",
+             kMaxActRows);
+  act_rows_bwd_kernel<<<dim3((unsigned)B, (unsigned)(W / 128)), 256, 0, s>>>(G, act, n, A, W, gsum, dW);
   IBC_LAUNCH_CHECK(h);
   return IBC_OK;
 }

@@ -55,6 +55,16 @@ int rowdot(ibc_handle* h, const float* X, int64_t ldx, const float* v,
 // G[r, w] = (scale ? scale[r] : 1) * v[w]
 int rowfill(ibc_handle* h, const float* v, const float* scale, int64_t R, int W,
             float* G, cudaStream_t s);
+// X[r, :] = rowbias[r / n, :] + sum_a act[r, a] * Wa[a, :]   (the action half of a first Dense
+// layer on tiled observations: K = act_dim is far too short for an MMA tile; a bandwidth-bound
+// rank-A update with 16-byte stores; W % 4 == 0)
+int act_rows(ibc_handle* h, const float* act, const float* Wa, const float* rowbias, int64_t R,
+             int64_t n, int A, int W, float* X, cudaStream_t s);
+// Its reverse in one pass over G [B*n, W]: gsum[b, :] = sum of the group's rows and
+// dW[a, :] += sum_r act[r, a] * G[r, :]   (atomic).  A <= kMaxActRows, W % 128 == 0.
+constexpr int kMaxActRows = 8;
+int act_rows_bwd(ibc_handle* h, const float* G, const float* act, int64_t B, int64_t n, int A,
+                 int W, float* gsum, float* dW, cudaStream_t s);
 // out[n] += sum_m X[m*ldx + n]   (atomic)
 int colsum_add(ibc_handle* h, const float* X, int64_t ldx, int64_t M, int N,
                float* out, cudaStream_t s);

@@ -178,7 +178,8 @@ static int dw_gemm(ibc_handle* h, const float* X, int64_t ldx, int aop, const fl
   GemmP g;
   g.A = X; g.lda = ldx; g.aop = aop; g.gateA = gate; g.B = Y; g.ldb = ldy;
   g.C = dW; g.ldc = Nout; g.M = Kin; g.N = Nout; g.K = (int)R;
-  g.k_chunk = 1024; g.atomic = 1; g.tc = tc ? 1 : 0;
+  g.k_chunk = R <= 1024 ? 64 : 1024;   // few rows (per-observation sums): still 8+ K slices
+  g.atomic = 1; g.tc = tc ? 1 : 0;
   return gemm(h, g, true, false, s);
 }
 
@@ -298,9 +299,15 @@ int train_grads_fp32(ibc_handle* h, const float* obs, int64_t B, const float* ac
     Gcur = Gnext;
   }
   // first layer: x = [obs tiled, act]
-  IBC_TRY(dw_gemm(h, actions, A, AOP_ID, nullptr, Gcur, W, R, A, W,
-                  grads + L.wp + (int64_t)L.O * W, s));
-  IBC_TRY(groupsum(h, Gcur, B, n1, W, gsum, s));
+  if (h->precision == IBC_PRECISION_TF32 && A <= kMaxActRows && W % 128 == 0) {
+    // one pass over G for both reductions (the K = R FMA product for two rows of dW took
+    // 187 us on C1's 135 MB of G, the group sum another 28)
+    IBC_TRY(act_rows_bwd(h, Gcur, actions, B, n1, A, W, gsum, grads + L.wp + (int64_t)L.O * W, s));
+  } else {
+    IBC_TRY(dw_gemm(h, actions, A, AOP_ID, nullptr, Gcur, W, R, A, W,
+                    grads + L.wp + (int64_t)L.O * W, s));
+    IBC_TRY(groupsum(h, Gcur, B, n1, W, gsum, s));
+  }
   IBC_TRY(dw_gemm(h, obs, L.O, AOP_ID, nullptr, gsum, W, B, L.O, W, grads + L.wp, s, false));
   IBC_TRY(colsum_add(h, gsum, W, B, W, grads + L.bp, s));
   return IBC_OK;

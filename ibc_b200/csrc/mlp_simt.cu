@@ -53,7 +53,12 @@ int mlp_forward_fp32(ibc_handle* h, const float* obs, int64_t B, const float* ac
     IBC_TRY(gemm(h, g, false, false, s));   // always fp32 (once per observation)
   }
   float* Hcur = save ? save->Hj(0, W) : Ha;
-  {  // H0 = act . Wp[O:] + hp[row / n]
+  if (h->precision == IBC_PRECISION_TF32 && (W & 3) == 0) {
+    // H0 = act . Wp[O:] + hp[row / n] as a bandwidth-bound rank-A pass (the FMA GEMM with
+    // K = act_dim took 145 us for the 135 MB of C1's H0; the exact fp32 mode keeps the GEMM
+    // and its summation order)
+    IBC_TRY(act_rows(h, act, P + L.wp + (int64_t)L.O * W, hp, R, n, L.A, W, Hcur, s));
+  } else {  // H0 = act . Wp[O:] + hp[row / n]
     GemmP g;
     g.A = act; g.lda = L.A; g.B = P + L.wp + (int64_t)L.O * W; g.ldb = W;
     g.C = Hcur; g.ldc = W; g.rowbias = hp; g.ldrb = W; g.rows_per_group = n;

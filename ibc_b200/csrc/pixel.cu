@@ -162,80 +162,6 @@ __global__ void flip_kernel3x3_kernel(const float* __restrict__ K, int Ci, int C
   Kd[((8 - tap) * Co + co) * Ci + c] = tf32_rn(K[i]);
 }
 
-// X[r, :] = encp[r / n, :] + sum_a act[r, a] * W[a, :]   (the action half of the value head's
-// first Dense layer: K = act_dim is far too short for an MMA tile, the product is a
-// bandwidth-bound rank-A update; one thread = 4 columns of one row, 16-byte stores)
-__global__ void act_rows_kernel(const float* __restrict__ act, const float* __restrict__ W,
-                                const float* __restrict__ encp, int64_t R, int64_t n, int A,
-                                int Wv, float* __restrict__ X) {
-  const int W4 = Wv / 4;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= R * W4) return;
-  const int c4 = (int)(i % W4);
-  const int64_t r = i / W4;
-  float4 v = *reinterpret_cast<const float4*>(encp + (r / n) * Wv + c4 * 4);
-  for (int a = 0; a < A; ++a) {
-    const float s = act[r * A + a];
-    const float4 w = *reinterpret_cast<const float4*>(W + (int64_t)a * Wv + c4 * 4);
-    v.x = fmaf(s, w.x, v.x); v.y = fmaf(s, w.y, v.y); v.z = fmaf(s, w.z, v.z); v.w = fmaf(s, w.w, v.w);
-  }
-  *reinterpret_cast<float4*>(X + r * Wv + c4 * 4) = v;
-}
-
-// Its reverse in one pass over G [B*n, Wv]: gsum[b, :] = sum of the group's rows (the
-// gradient of the tiled encoding projection) and dW[a, :] += sum_r act[r, a] * G[r, :].
-// grid (B, Wv / 128), block 256 = 32 column quads x 8 row lanes; A <= kMaxActRows.
-constexpr int kMaxActRows = 8;
-__global__ void act_rows_bwd_kernel(const float* __restrict__ G, const float* __restrict__ act,
-                                    int64_t n, int A, int Wv, float* __restrict__ gsum,
-                                    float* __restrict__ dW) {
-  __shared__ float4 part[8][32];
-  const int b = blockIdx.x, c4 = blockIdx.y * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
-  float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 dw[kMaxActRows];
-#pragma unroll
-  for (int a = 0; a < kMaxActRows; ++a) dw[a] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int64_t i = rl; i < n; i += 8) {
-    const int64_t r = (int64_t)b * n + i;
-    const float4 g = *reinterpret_cast<const float4*>(G + r * Wv + c4 * 4);
-    gs.x += g.x; gs.y += g.y; gs.z += g.z; gs.w += g.w;
-#pragma unroll
-    for (int a = 0; a < kMaxActRows; ++a) {
-      if (a < A) {
-        const float s = act[r * A + a];
-        dw[a].x = fmaf(s, g.x, dw[a].x); dw[a].y = fmaf(s, g.y, dw[a].y);
-        dw[a].z = fmaf(s, g.z, dw[a].z); dw[a].w = fmaf(s, g.w, dw[a].w);
-      }
-    }
-  }
-  auto reduce = [&](float4 v) -> float4 {      // sum over the 8 row lanes, result in lane row 0
-    part[rl][threadIdx.x & 31] = v;
-    __syncthreads();
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (rl == 0) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float4 q = part[k][threadIdx.x & 31];
-        t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
-      }
-    }
-    __syncthreads();
-    return t;
-  };
-  const float4 gt = reduce(gs);
-  if (rl == 0) *reinterpret_cast<float4*>(gsum + (int64_t)b * Wv + c4 * 4) = gt;
-  for (int a = 0; a < A; ++a) {
-    float4 pick = dw[0];
-#pragma unroll
-    for (int k = 1; k < kMaxActRows; ++k) if (k == a) pick = dw[k];
-    const float4 t = reduce(pick);
-    if (rl == 0) {
-      float* o = dW + (int64_t)a * Wv + c4 * 4;
-      atomicAdd(o, t.x); atomicAdd(o + 1, t.y); atomicAdd(o + 2, t.z); atomicAdd(o + 3, t.w);
-    }
-  }
-}
-
 __global__ void add_rows_kernel(float* __restrict__ a, const float* __restrict__ b, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] += b[i];
@@ -702,9 +628,7 @@ int value_rows(ibc_pixel_handle* ph, const PixelLayout& L, int64_t B, const floa
   const bool tc = h->precision == IBC_PRECISION_TF32;
   const float* PB = tc ? v.wr : P;          // B operands of the block products
   if (tc) {   // x0 = act . W0[256:] + encp[row / n]
-    act_rows_kernel<<<nblocks(R * (Wv / 4)), 256, 0, s>>>(act, P + L.d0_w + (int64_t)kEnc * Wv, v.encp,
-                                                        R, n, L.A, Wv, v.X);
-    IBC_LAUNCH_CHECK(h);
+    IBC_TRY(act_rows(h, act, P + L.d0_w + (int64_t)kEnc * Wv, v.encp, R, n, L.A, Wv, v.X, s));
   } else {
     GemmP g;
     g.A = act; g.lda = L.A; g.B = P + L.d0_w + (int64_t)kEnc * Wv; g.ldb = Wv;
@@ -806,9 +730,7 @@ int value_bwd(ibc_pixel_handle* ph, const PixelLayout& L, const float* enc, int6
   }
   // dense0 on x = [enc tiled, act]
   if (tc && L.A <= kMaxActRows && Wv % 128 == 0) {   // one pass over G for both reductions
-    act_rows_bwd_kernel<<<dim3((unsigned)B, (unsigned)(Wv / 128)), 256, 0, s>>>(
-        G, act, n, L.A, Wv, gsum, grads + L.d0_w + (int64_t)kEnc * Wv);
-    IBC_LAUNCH_CHECK(h);
+    IBC_TRY(act_rows_bwd(h, G, act, B, n, L.A, Wv, gsum, grads + L.d0_w + (int64_t)kEnc * Wv, s));
   } else {
     IBC_TRY(dwg(h, act, L.A, AOP_ID, G, Wv, R, L.A, Wv, grads + L.d0_w + (int64_t)kEnc * Wv, s));
     IBC_TRY(groupsum(h, G, B, n, Wv, gsum, s));
