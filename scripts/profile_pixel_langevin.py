@@ -1,5 +1,7 @@
+"""Diagnostic: two 4-iteration Langevin chains on the PixelEBM value head (1024 rows) for the
+ncu launch list / --set full captures under profiles/."""
 import os, sys
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ibc_b200 import engine as eng
 dev = torch.device('cuda', 0)
