@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_float,
-                    c_int, c_int32, c_int64, c_uint64, c_void_p)
+                    c_int, c_int32, c_int64, c_uint32, c_uint64, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libibc_b200.so')
@@ -137,6 +137,9 @@ SIGNATURES = {
     'ibc_reset_launch_count': (None, []),
     'ibc_umma_selftest': (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                   c_void_p, POINTER(c_int32), c_void_p]),
+    'ibc_umma_f16_selftest': (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_uint32, c_uint32,
+                                      c_uint32, c_uint32, c_uint32, c_void_p, POINTER(c_int32),
+                                      c_void_p]),
     'ibc_gemm_tf32': (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p,
                               c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                               c_int32, c_int32, c_int32, POINTER(c_int32), c_void_p]),

@@ -308,6 +308,13 @@ int ibc_umma_selftest(const float* A, const float* Bt, int32_t N, int32_t K, int
   return umma_selftest(A, Bt, N, K, mode, D, status_host, (cudaStream_t)stream);
 }
 
+int ibc_umma_f16_selftest(const float* A, const float* B, int32_t N, int32_t K, uint32_t lbo_a,
+                          uint32_t lbo_b, uint32_t sbo, uint32_t layout_type, uint32_t kstep_bytes,
+                          float* D, int32_t* status_host, void* stream) {
+  return umma_f16_selftest(A, B, N, K, lbo_a, lbo_b, sbo, layout_type, kstep_bytes, D, status_host,
+                           (cudaStream_t)stream);
+}
+
 int ibc_gemm_tf32(const float* A, int64_t lda, int32_t trans_a, const float* B, int64_t ldb,
                   int32_t trans_b, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
                   const float* bias, const float* gate_c, const float* res, int32_t relu_a,

@@ -9,6 +9,7 @@
 
 #include "gemm_simt.cuh"
 #include "mlp.cuh"
+#include "ops.cuh"
 
 namespace ibc {
 namespace {
@@ -36,7 +37,8 @@ __device__ __forceinline__ float block_reduce(float v, float* s_red, bool is_max
 // [1e-7, 1].
 __global__ void __launch_bounds__(128)
 info_nce_kernel(const float* __restrict__ pred, int n1, float temperature, float grad_scale,
-                float* __restrict__ loss, float* __restrict__ dpred) {
+                float* __restrict__ loss, float* __restrict__ dpred,
+                unsigned int* __restrict__ dpred_absmax) {
   __shared__ float s_red[4];
   const int tid = threadIdx.x;
   const float* row = pred + (int64_t)blockIdx.x * n1;
@@ -63,12 +65,19 @@ info_nce_kernel(const float* __restrict__ pred, int n1, float temperature, float
   if (tid == 0) loss[blockIdx.x] = l;
   if (dpred) {
     float* drow = dpred + (int64_t)blockIdx.x * n1;
+    float dmax = 0.f;
     for (int j = tid; j < n1; j += 128) {
       const float p = __fdiv_rn(expf(__fdiv_rn(row[j], temperature) - mx), sum);
       const float yt = (j == n1 - 1) ? 1.0f : kKerasEps;
       const bool inside = (p >= kKerasEps) && (p <= 1.0f);
       const float q = inside ? yt : 0.f;
-      drow[j] = grad_scale * (p * qsum - q) / temperature;
+      const float d = grad_scale * (p * qsum - q) / temperature;
+      drow[j] = d;
+      dmax = fmaxf(dmax, fabsf(d));
+    }
+    if (dpred_absmax) {     // max |dpred| over the batch (non-negative floats order like their bits)
+      dmax = block_reduce(dmax, s_red, true);
+      if (tid == 0) atomicMax(dpred_absmax, __float_as_uint(dmax));
     }
   }
 }
@@ -142,10 +151,12 @@ __global__ void add_vec_kernel(float* __restrict__ a, const float* __restrict__ 
 }  // namespace
 
 int info_nce(ibc_handle* h, const float* pred, int64_t B, int64_t n1, float temperature,
-             float grad_scale, float* loss, float* dpred, cudaStream_t s) {
+             float grad_scale, float* loss, float* dpred, cudaStream_t s,
+             unsigned int* dpred_absmax) {
   if (B <= 0 || n1 <= 0) IBC_FAIL(h, IBC_ERR_INVALID, "info_nce: bad shape");
   if (temperature <= 0.f) IBC_FAIL(h, IBC_ERR_INVALID, "info_nce: temperature must be > 0");
-  info_nce_kernel<<<(unsigned)B, 128, 0, s>>>(pred, (int)n1, temperature, grad_scale, loss, dpred);
+  info_nce_kernel<<<(unsigned)B, 128, 0, s>>>(pred, (int)n1, temperature, grad_scale, loss, dpred,
+                                              dpred_absmax);
   IBC_LAUNCH_CHECK(h);
   return IBC_OK;
 }

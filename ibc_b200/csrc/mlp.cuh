@@ -84,9 +84,18 @@ int langevin_fused(ibc_handle* h, const float* hp, int64_t B, float* actions, in
 bool tmem_path_supported(const Layout& L);
 int tmem_forward(ibc_handle* h, const float* act, int64_t R, int64_t n, const float* hp, float* E,
                  float* xa_save, uint32_t* mask_save, cudaStream_t s);
+int tmem_forward_f16(ibc_handle* h, const float* act, int64_t R, int64_t n, const float* hp, float* E,
+                     float* xa_save, void* xa16, float* hn_save, uint32_t* mask_save,
+                     cudaStream_t s);
 int tmem_reverse(ibc_handle* h, const float* dE, int64_t R, const float* xa_save,
                  const uint32_t* mask_save, float* gy_save, float* g0, float* dwe,
                  cudaStream_t s);
+// reverse chain + weight / bias gradients of the W x W layers in one block-major
+// kernel (mlp_bwd_wgrad.cu); scratch sizes in floats
+size_t bwd_wgrad_scratch_floats(const ibc_handle* h, int64_t R, size_t* park, size_t* pw, size_t* pb);
+int tmem_reverse_wgrad(ibc_handle* h, const float* dE, const uint32_t* dE_absmax, int64_t R,
+                       const void* xa16, const uint32_t* mask_save, float* gpark, float* part_w,
+                       float* part_b, float* grads, cudaStream_t s);
 // tcgen05 training path (mlp_umma_train.cu): W == 128, no gradient penalty.
 bool umma_train_supported(const Layout& L);
 int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* actions, int64_t N,

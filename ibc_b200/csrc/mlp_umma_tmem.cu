@@ -33,6 +33,7 @@
 
 #include "mlp.cuh"
 #include "umma.cuh"
+#include "umma_f16.cuh"
 #include "umma_pack.cuh"
 
 namespace ibc {
@@ -130,7 +131,9 @@ struct FwdTmemParams {
   const float* hp;       // [B, W]  obs . Wp[:O] + bp
   const float* packed;
   float* E;              // [R]
-  float* xa_save;        // nullable, 2nb+1 slots per tile (training)
+  float* xa_save;        // nullable, 2nb+1 slots per tile (training, fp32 tiles: kSave == 1)
+  uint4* xa16;           // kSave == 2: fp16 operands [tile][2nb slots][16 chunks of 8][128 rows][16 B]
+  float* hn_save;        // kSave == 2: final residual stream [tile][32 chunks][128 rows][4] (fp32)
   uint32_t* mask_save;   // nullable, ReLU masks of the 2nb W x W layers
   int64_t R, n_per_obs;
   int nb, A, KP;
@@ -141,7 +144,12 @@ struct FwdTmemParams {
   int dbg_mode;   // timeline experiments: 1 = epilogue does no work (MMA chain alone)
 };
 
-template <bool kSave>
+// kSave: 0 = energies only; 1 = fp32 operand tiles + masks (round 1's split backward, the
+// dE/dact paths save masks only); 2 = fp16 operand tiles + masks for the block-major
+// backward (mlp_bwd_wgrad.cu): a saved operand is relu(.) rounded to tf32 -- non-negative
+// with a 10-bit mantissa, i.e. exactly an fp16 value inside fp16's exponent range -- so the
+// weight-gradient GEMM runs in kind::f16 on half the bytes.
+template <int kSave>
 __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tmem_kernel(FwdTmemParams p) {
   using TT = TrainTile<kW>;
   constexpr int W = kW;
@@ -233,8 +241,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tmem_kernel(FwdTmemParams
         auto step = [&](auto even_tag, auto last_tag, int i) {
           constexpr bool kEven = decltype(even_tag)::value;
           constexpr bool kLast = decltype(last_tag)::value;
-          float4* g_slot = (kSave && p.xa_save) ? reinterpret_cast<float4*>(
+          float4* g_slot = (kSave == 1 && p.xa_save) ? reinterpret_cast<float4*>(
               p.xa_save + TT::slot_base(tile_id, nsteps, i)) : nullptr;
+          uint4* h_slot = (kSave == 2 && !kLast)
+                              ? p.xa16 + (tile_id * (nsteps - 1) + i) * (int64_t)(16 * 128) + row : nullptr;
+          float4* hn_slot = (kSave == 2 && kLast)
+                                ? reinterpret_cast<float4*>(p.hn_save) + tile_id * (int64_t)(32 * 128) + row
+                                : nullptr;
           mbar_wait(&d_ready[t], ph_d, abort_flag, p.status, 100 + i);
           ph_d ^= 1;
           tc_fence_after();
@@ -274,6 +287,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tmem_kernel(FwdTmemParams
 #pragma unroll
               for (int q = 0; q < 8; ++q)
                 g_slot[TT::chunk_f4(row, c32 * 8 + q)] =
+                    make_float4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]),
+                                __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+            }
+            if (kSave == 2 && !kLast) {
+              // what the tensor core reads of the operand (low 13 bits truncated), as fp16
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 w;
+                w.x = pack_half2(__uint_as_float(v[q * 8 + 0] & 0xFFFFE000u), __uint_as_float(v[q * 8 + 1] & 0xFFFFE000u));
+                w.y = pack_half2(__uint_as_float(v[q * 8 + 2] & 0xFFFFE000u), __uint_as_float(v[q * 8 + 3] & 0xFFFFE000u));
+                w.z = pack_half2(__uint_as_float(v[q * 8 + 4] & 0xFFFFE000u), __uint_as_float(v[q * 8 + 5] & 0xFFFFE000u));
+                w.w = pack_half2(__uint_as_float(v[q * 8 + 6] & 0xFFFFE000u), __uint_as_float(v[q * 8 + 7] & 0xFFFFE000u));
+                h_slot[(c32 * 4 + q) * 128] = w;
+              }
+            }
+            if (kSave == 2 && kLast) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                hn_slot[(c32 * 8 + q) * 128] =
                     make_float4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]),
                                 __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
             }
@@ -734,11 +766,21 @@ bool tmem_path_supported(const Layout& L) {
 
 int tmem_forward(ibc_handle* h, const float* act, int64_t R, int64_t n, const float* hp, float* E,
                  float* xa_save, uint32_t* mask_save, cudaStream_t s) {
+  return tmem_forward_f16(h, act, R, n, hp, E, xa_save, nullptr, nullptr, mask_save, s);
+}
+
+// xa16 / hn_save non-null: fp16 operand tiles for the block-major backward (and no fp32 tiles)
+int tmem_forward_f16(ibc_handle* h, const float* act, int64_t R, int64_t n, const float* hp, float* E,
+                     float* xa_save, void* xa16, float* hn_save, uint32_t* mask_save,
+                     cudaStream_t s) {
   const Layout& L = h->L;
   const PackedLayout pl = make_packed_layout(L);
   const bool saving = xa_save || mask_save;
+  if (xa16 && (!hn_save || !mask_save || xa_save))
+    IBC_FAIL(h, IBC_ERR_INVALID, "tmem_forward_f16: fp16 tiles come with hn_save and mask_save only");
   FwdTmemParams p;
   p.act = act; p.hp = hp; p.packed = h->packed; p.E = E; p.xa_save = xa_save;
+  p.xa16 = reinterpret_cast<uint4*>(xa16); p.hn_save = hn_save;
   p.mask_save = mask_save;
   p.R = R; p.n_per_obs = n; p.nb = L.nb; p.A = L.A; p.KP = pl.KP;
   const int64_t tiles = (R + 127) / 128;
@@ -754,15 +796,18 @@ int tmem_forward(ibc_handle* h, const float* act, int64_t R, int64_t n, const fl
     IBC_CUDA(h, cudaMalloc((void**)&p.dbg, kDbgWords * sizeof(long long)));
     IBC_CUDA(h, cudaMemsetAsync(p.dbg, 0, kDbgWords * sizeof(long long), s));
   }
-  static bool attr = false;
-  if (!attr) {
-    IBC_TRY(raise_smem(h, mlp_fwd_tmem_kernel<true>));
-    IBC_TRY(raise_smem(h, mlp_fwd_tmem_kernel<false>));
-    attr = true;
+  constexpr int kMaxDev = 64;
+  static bool attr[kMaxDev] = {false};          // the attribute is per device
+  if (h->device >= 0 && h->device < kMaxDev && !attr[h->device]) {
+    IBC_TRY(raise_smem(h, mlp_fwd_tmem_kernel<0>));
+    IBC_TRY(raise_smem(h, mlp_fwd_tmem_kernel<1>));
+    IBC_TRY(raise_smem(h, mlp_fwd_tmem_kernel<2>));
+    attr[h->device] = true;
   }
   const size_t smem = smem_bytes(true, p.KP);
-  if (saving) mlp_fwd_tmem_kernel<true><<<grid, kThreads, smem, s>>>(p);
-  else mlp_fwd_tmem_kernel<false><<<grid, kThreads, smem, s>>>(p);
+  if (xa16) mlp_fwd_tmem_kernel<2><<<grid, kThreads, smem, s>>>(p);
+  else if (saving) mlp_fwd_tmem_kernel<1><<<grid, kThreads, smem, s>>>(p);
+  else mlp_fwd_tmem_kernel<0><<<grid, kThreads, smem, s>>>(p);
   IBC_LAUNCH_CHECK(h);
   if (p.dbg) {
     cudaStreamSynchronize(s);
@@ -796,10 +841,11 @@ int tmem_reverse(ibc_handle* h, const float* dE, int64_t R, const float* xa_save
   const int grid = tiles < h->sm_count ? (int)tiles : h->sm_count;
   p.work = make_tiling(R, grid);
   p.status = h->dev_status;
-  static bool attr = false;
-  if (!attr) {
+  constexpr int kMaxDev = 64;
+  static bool attr[kMaxDev] = {false};          // the attribute is per device
+  if (h->device >= 0 && h->device < kMaxDev && !attr[h->device]) {
     IBC_TRY(raise_smem(h, mlp_bwd_tmem_kernel));
-    attr = true;
+    attr[h->device] = true;
   }
   p.dbg = nullptr;
   p.dbg_item = getenv("IBC_DBG_ITEM") ? atoi(getenv("IBC_DBG_ITEM")) : 0;

@@ -373,30 +373,95 @@ __global__ void __launch_bounds__(kW) first_layer_grads_kernel(
   }
 }
 
+// The same pass over g0 in the TILE layout the block-major backward leaves it in
+// ([tile][chunk (32)][128 rows][4], mlp_bwd_wgrad.cu): one block per 128-row tile, 32 rows
+// at a time through shared memory (coalesced 512-byte reads; rows of 33 float4 make the
+// per-column reads of thread = column conflict-free).
+template <int AMAX>
+__global__ void __launch_bounds__(kW) first_layer_grads_tiled_kernel(
+    const float* __restrict__ act, const float* __restrict__ g0t, const float* __restrict__ dE,
+    int64_t R, int A, int64_t n1, float* __restrict__ dw, float* __restrict__ gsum,
+    float* __restrict__ dbe) {
+  __shared__ float4 s_g[32 * 33];
+  __shared__ float s_act[32 * AMAX];
+  const int w = threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * 128;
+  const int64_t r1 = min(R, r0 + 128);
+  const float4* tile = reinterpret_cast<const float4*>(g0t) + (int64_t)blockIdx.x * (128 * kW / 4);
+  float acc[AMAX];
+#pragma unroll
+  for (int a = 0; a < AMAX; ++a) acc[a] = 0.f;
+  float gs = 0.f;
+  int64_t cur_b = r0 / n1;
+  int64_t next_edge = (cur_b + 1) * n1;
+  const float* sg = reinterpret_cast<const float*>(s_g) + (w >> 2) * (33 * 4) + (w & 3);
+  for (int64_t rb = r0; rb < r1; rb += 32) {
+    const int nr = (int)min((int64_t)32, r1 - rb);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = i * kW + w, c = idx >> 5, rr = idx & 31;
+      s_g[c * 33 + rr] = tile[c * 128 + (int)(rb - r0) + rr];
+    }
+    for (int i = w; i < nr * AMAX; i += kW) {
+      const int k = i / AMAX, a = i % AMAX;
+      s_act[i] = (a < A) ? act[(rb + k) * A + a] : 0.f;
+    }
+    __syncthreads();
+    for (int k = 0; k < nr; ++k) {
+      if (rb + k == next_edge) {
+        atomicAdd(gsum + cur_b * kW + w, gs);
+        gs = 0.f;
+        ++cur_b;
+        next_edge += n1;
+      }
+      const float g = sg[k * 4];
+      gs += g;
+#pragma unroll
+      for (int a = 0; a < AMAX; ++a) acc[a] = fmaf(s_act[k * AMAX + a], g, acc[a]);
+    }
+  }
+  if (r1 > r0) atomicAdd(gsum + cur_b * kW + w, gs);
+#pragma unroll
+  for (int a = 0; a < AMAX; ++a)
+    if (a < A) atomicAdd(dw + (int64_t)a * kW + w, acc[a]);
+  if (w < 32) {            // dbe: the tile's dE values through one warp
+    float sde = 0.f;
+    for (int64_t r = r0 + w; r < r1; r += 32) sde += dE[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sde += __shfl_xor_sync(0xffffffffu, sde, o);
+    if (w == 0) atomicAdd(dbe, sde);
+  }
+}
+
 // dwe[w] += sum_r dE[r] * h_nb[r, w] over the forward's last saved slot (tile layout
 // [sub-tile][chunk][32 rows][4]).  Lane = row of a sub-tile, warp = 4 of the 32
 // chunks: loads are 512 contiguous bytes per warp, every lane keeps 16 partial sums
 // across all the tiles its block visits, and the cross-row reduction happens once
 // per block.  (Doing this inside the reverse kernel cost 128 warp reductions per
 // tile in front of every chain: ~20% of that kernel.)
+// hn_tiled: h_nb as the fp16-saving forward leaves it, [tile][chunk (32)][128 rows][4].
 __global__ void __launch_bounds__(256) dwe_kernel(const float* __restrict__ xa_save,
                                                   const float* __restrict__ dE, int64_t R,
-                                                  int num_tiles, int nb, float* __restrict__ dwe) {
+                                                  int num_tiles, int nb, float* __restrict__ dwe,
+                                                  int hn_tiled) {
   using TT = TrainTile<kW>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const float4* hn = reinterpret_cast<const float4*>(
-        xa_save + TT::slot_base(tile, 2 * nb + 1, 2 * nb));
+    const float4* hn = hn_tiled ? reinterpret_cast<const float4*>(xa_save) + (int64_t)tile * (32 * 128)
+                                : reinterpret_cast<const float4*>(
+                                      xa_save + TT::slot_base(tile, 2 * nb + 1, 2 * nb));
 #pragma unroll
     for (int sub = 0; sub < 4; ++sub) {
       const int64_t r = (int64_t)tile * 128 + sub * 32 + lane;
       const float de = r < R ? dE[r] : 0.f;
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
-        const float4 h4 = hn[TT::chunk_f4(sub * 32 + lane, warp * 4 + cc)];
+        const float4 h4 = hn[hn_tiled ? (warp * 4 + cc) * 128 + sub * 32 + lane
+                                      : TT::chunk_f4(sub * 32 + lane, warp * 4 + cc)];
         acc[cc * 4 + 0] = fmaf(de, h4.x, acc[cc * 4 + 0]);
         acc[cc * 4 + 1] = fmaf(de, h4.y, acc[cc * 4 + 1]);
         acc[cc * 4 + 2] = fmaf(de, h4.z, acc[cc * 4 + 2]);
@@ -835,19 +900,43 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
   const float gscale = 1.0f / (float)global_batch;
   const int num_groups = (int)((R + 255) / 256);
   const int64_t num_tiles = (int64_t)num_groups * kNT;
-  const size_t xa_floats = umma_save_floats(L, R);
-  const size_t gy_floats = (size_t)num_tiles * (2 * nb) * TT::kTileFloats;
+  size_t xa_floats = umma_save_floats(L, R);
+  // IBC_TRAIN_SPLIT=1: round 1's three-kernel backward (tile-major reverse chain writing
+  // every layer's output gradient + a separate weight-gradient kernel), kept for A/B runs
+  const bool split_env = getenv("IBC_TRAIN_SPLIT") != nullptr;
+  static const bool force_smem = getenv("IBC_SMEM_OPERANDS") != nullptr;
+  const bool fused_bwd = !split_env && !force_smem && tmem_path_supported(L);
+  size_t park_floats = 0, pw_floats = 0, pb_floats = 0;
+  // block-major backward: fp16 operand tiles (2nb slots x 32 KB per tile) + the fp32 h_nb tile
+  const int64_t tiles128 = (R + 127) / 128;
+  size_t xa16_bytes = 0, hn_floats = 0;
+  if (fused_bwd) {
+    bwd_wgrad_scratch_floats(h, R, &park_floats, &pw_floats, &pb_floats);
+    xa16_bytes = (size_t)tiles128 * (2 * nb) * 128 * kW * 2;
+    hn_floats = (size_t)tiles128 * 128 * kW;
+    xa_floats = 0;
+  }
+  const size_t gy_floats = fused_bwd ? 0 : (size_t)num_tiles * (2 * nb) * TT::kTileFloats;
   const size_t mask_words = umma_mask_words(L, R);
   const size_t bytes = Workspace::rounded(xa_floats * 4) + Workspace::rounded(gy_floats * 4) +
-                       Workspace::rounded(mask_words * 4) + Workspace::rounded((size_t)R * W * 4) +
+                       Workspace::rounded(park_floats * 4) + Workspace::rounded(pw_floats * 4) +
+                       Workspace::rounded(pb_floats * 4) + Workspace::rounded(xa16_bytes) +
+                       Workspace::rounded(hn_floats * 4) + 256 +
+                       Workspace::rounded(mask_words * 4) + Workspace::rounded(fused_bwd ? 0 : (size_t)R * W * 4) +
                        2 * Workspace::rounded((size_t)B * W * 4) +
                        2 * Workspace::rounded((size_t)R * 4) + 2 * Workspace::rounded((size_t)B * 4);
   IBC_CUDA(h, h->ws.reserve(bytes));
   h->ws.reset();
   float* xa = h->ws.take<float>(xa_floats);
   float* gy = h->ws.take<float>(gy_floats);
+  float* gpark = h->ws.take<float>(park_floats);
+  float* part_w = h->ws.take<float>(pw_floats);
+  float* part_b = h->ws.take<float>(pb_floats);
+  unsigned char* xa16 = h->ws.take<unsigned char>(xa16_bytes);
+  float* hn = h->ws.take<float>(hn_floats);
+  uint32_t* de_absmax = h->ws.take<uint32_t>(1);
   uint32_t* masks = h->ws.take<uint32_t>(mask_words);
-  float* g0 = h->ws.take<float>((size_t)R * W);
+  float* g0 = h->ws.take<float>(fused_bwd ? 0 : (size_t)R * W);
   float* hp = h->ws.take<float>((size_t)B * W);
   float* gsum = h->ws.take<float>((size_t)B * W);
   float* E = h->ws.take<float>(R);
@@ -857,11 +946,22 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
   auto mark = [&](int i) { if (h->profiling) cudaEventRecord(h->ev[i], s); };
   IBC_CUDA(h, cudaMemsetAsync(grads, 0, (size_t)L.count * 4, s));
   mark(0);
-  IBC_TRY(umma_forward(h, obs, B, actions, n1, hp, E, xa, masks, s));
+  if (fused_bwd) {
+    if (h->packed_stale) IBC_TRY(umma_pack_params(h, s));
+    GemmP g;   // hp = obs . Wp[:O] + bp   (fp32)
+    g.A = obs; g.lda = L.O; g.B = h->params + L.wp; g.ldb = L.W; g.C = hp; g.ldc = L.W;
+    g.bias = h->params + L.bp; g.M = (int)B; g.N = L.W; g.K = L.O;
+    IBC_TRY(gemm(h, g, false, false, s));
+    IBC_TRY(tmem_forward_f16(h, actions, R, n1, hp, E, nullptr, xa16, hn, masks, s));
+    IBC_CUDA(h, cudaMemsetAsync(de_absmax, 0, 4, s));
+  } else {
+    IBC_TRY(umma_forward(h, obs, B, actions, n1, hp, E, xa, masks, s));
+  }
   mark(1);
   if (energies_out)
     IBC_CUDA(h, cudaMemcpyAsync(energies_out, E, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
-  IBC_TRY(info_nce(h, E, B, n1, c.softmax_temperature, gscale, per_example, dE, s));
+  IBC_TRY(info_nce(h, E, B, n1, c.softmax_temperature, gscale, per_example, dE, s,
+                   fused_bwd ? de_absmax : nullptr));
   if (grad_loss_out) IBC_CUDA(h, cudaMemsetAsync(grad_loss_out, 0, (size_t)B * 4, s));
   (void)gl;
   mark(2);
@@ -873,15 +973,18 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
                                      (int)WgradSmem::kBytes));
     attr_done = true;
   }
-  IBC_TRY(umma_reverse(h, dE, R, xa, masks, gy, g0, nullptr, s));
+  if (fused_bwd)
+    IBC_TRY(tmem_reverse_wgrad(h, dE, de_absmax, R, xa16, masks, gpark, part_w, part_b, grads, s));
+  else
+    IBC_TRY(umma_reverse(h, dE, R, xa, masks, gy, g0, nullptr, s));
   {  // Dense(1) weight gradient from the forward's last slot
     const int tiles = (int)((R + 127) / 128);
     const int blocks = tiles < 2 * h->sm_count ? tiles : 2 * h->sm_count;
-    dwe_kernel<<<blocks, 256, 0, s>>>(xa, dE, R, tiles, nb, grads + L.we);
+    dwe_kernel<<<blocks, 256, 0, s>>>(fused_bwd ? hn : xa, dE, R, tiles, nb, grads + L.we, fused_bwd ? 1 : 0);
     IBC_LAUNCH_CHECK(h);
   }
   mark(3);
-  {
+  if (!fused_bwd) {
     WgradParams wp;
     wp.xa_save = xa; wp.gy_save = gy; wp.grads = grads; wp.L = L; wp.nb = nb;
     // only tiles that hold rows: the forward / reverse kernels never touch a padding tile
@@ -902,7 +1005,15 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
     const int blocks = (int)((R + 255) / 256);
     float* dwa = grads + L.wp + (int64_t)L.O * W;
     float* dbe = grads + L.be;
-    if (A <= 2)
+    if (fused_bwd) {     // g0 in the tile layout, left in gpark by the block-major backward
+      const int tblocks = (int)((R + 127) / 128);
+      if (A <= 2)
+        first_layer_grads_tiled_kernel<2><<<tblocks, kW, 0, s>>>(actions, gpark, dE, R, A, n1, dwa, gsum, dbe);
+      else if (A <= 8)
+        first_layer_grads_tiled_kernel<8><<<tblocks, kW, 0, s>>>(actions, gpark, dE, R, A, n1, dwa, gsum, dbe);
+      else
+        first_layer_grads_tiled_kernel<32><<<tblocks, kW, 0, s>>>(actions, gpark, dE, R, A, n1, dwa, gsum, dbe);
+    } else if (A <= 2)
       first_layer_grads_kernel<2><<<blocks, kW, 0, s>>>(actions, g0, dE, R, A, n1, dwa, gsum, dbe);
     else if (A <= 8)
       first_layer_grads_kernel<8><<<blocks, kW, 0, s>>>(actions, g0, dE, R, A, n1, dwa, gsum, dbe);

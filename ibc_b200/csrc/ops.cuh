@@ -35,7 +35,8 @@ int langevin(ibc_handle* h, const float* obs, int64_t B, float* actions, int64_t
              uint64_t seed, float* chain_actions, float* chain_energies, float* chain_grad_norms,
              cudaStream_t s);
 int info_nce(ibc_handle* h, const float* pred, int64_t B, int64_t n1, float temperature,
-             float grad_scale, float* loss, float* dpred, cudaStream_t s);
+             float grad_scale, float* loss, float* dpred, cudaStream_t s,
+             unsigned int* dpred_absmax = nullptr);
 int grad_penalty_from_dact(ibc_handle* h, const float* dEda, int64_t B, int64_t n1, int A,
                            const ibc_loss_cfg& c, float grad_scale, float* grad_loss, float* cot,
                            cudaStream_t s);
@@ -46,5 +47,8 @@ int train_grads_fp32(ibc_handle* h, const float* obs, int64_t B, const float* ac
                      float* grad_loss_out, float* energies_out, float* grads, cudaStream_t s);
 int umma_selftest(const float* A, const float* Bt, int N, int K, int mode, float* D,
                   int* status_host, cudaStream_t s);
+int umma_f16_selftest(const float* A, const float* B, int N, int K, uint32_t lbo_a, uint32_t lbo_b,
+                      uint32_t sbo, uint32_t layout_type, uint32_t kstep_bytes, float* D,
+                      int* status_host, cudaStream_t s);
 
 }  // namespace ibc

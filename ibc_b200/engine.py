@@ -576,6 +576,22 @@ def conv3x3_tf32(x, kernel, bias=None, relu=False, mode=0, dy=None, out=None):
   return out, int(st.value)
 
 
+def umma_f16_selftest(a: torch.Tensor, b: torch.Tensor, lbo_a=0, lbo_b=0, sbo=0, layout_type=0,
+                      kstep_bytes=0):
+  """D[128,N] = A[K,128]^T . B[K,N] through tcgen05 kind::f16 with MN-major operand images;
+  descriptor fields 0 = the library's own.  Returns (D, status)."""
+  _check_f32(a, 'A')
+  _check_f32(b, 'B')
+  k, n = b.shape
+  assert a.shape == (k, 128)
+  d = torch.zeros(128, n, device=a.device, dtype=torch.float32)
+  st = ctypes.c_int32(-1)
+  _lib.check(_lib.load().ibc_umma_f16_selftest(_ptr(a), _ptr(b), n, k, lbo_a, lbo_b, sbo,
+                                               layout_type, kstep_bytes, _ptr(d),
+                                               ctypes.byref(st), _stream()))
+  return d, int(st.value)
+
+
 def umma_selftest(a: torch.Tensor, bt: torch.Tensor, mode: int = 0):
   """D = A[128,K] . Bt[N,K]^T through tcgen05; returns (D, status)."""
   _check_f32(a, 'A')

@@ -366,6 +366,16 @@ int ibc_umma_selftest(const float* A, const float* Bt, int32_t N, int32_t K,
                       int32_t mode, float* D, int32_t* status_host,
                       void* stream);
 
+/* tcgen05 kind::f16 self test of the MN-major operand image the weight-gradient GEMM
+ * uses (tape.gradient of ibc/agents/base_agent.py:43-48: dW = X^T dY with the rows as
+ * the K dimension): D[128, N] = A[K, 128]^T . B[K, N], operands rounded to fp16, fp32
+ * accumulate.  lbo / sbo / layout_type / kstep_bytes are the shared-memory descriptor
+ * fields (0 = the library's own: umma_f16.cuh). */
+int ibc_umma_f16_selftest(const float* A, const float* B, int32_t N, int32_t K,
+                          uint32_t lbo_a, uint32_t lbo_b, uint32_t sbo,
+                          uint32_t layout_type, uint32_t kstep_bytes, float* D,
+                          int32_t* status_host, void* stream);
+
 /* The general tcgen05 tf32 GEMM behind the Keras Dense / Conv2D contractions that
  * are not layer-fused (networks/layers/dense_resnet_value.py:31-69,
  * networks/layers/conv_maxpool.py:20-48, the second-order passes of

@@ -533,6 +533,56 @@ def test_train_grads_tf32_match_oracle_autograd(spec, b, n, scale):
     assert rel < max(1e-2, 1.5 * rel_emul + 5e-3), (name, rel, rel_emul)
 
 
+@pytest.mark.parametrize('spec,b,n', [(omlp.MLPSpec(20, 2, 128, 16), 3, 50),      # 153 rows: ragged last tile
+                                      (omlp.MLPSpec(20, 2, 128, 4), 160, 256),   # 322 tiles: up to 3 per CTA
+                                      (omlp.MLPSpec(20, 2, 128, 16), 512, 256),  # the C2 step
+                                      (omlp.MLPSpec(39, 28, 128, 2), 37, 100)], ids=str)
+def test_train_grads_block_major_backward_matches_the_split_kernels(spec, b, n, monkeypatch):
+  """The block-major reverse + weight-gradient kernel (mlp_bwd_wgrad.cu) against round
+  1's tile-major reverse chain + separate weight-gradient kernel (IBC_TRAIN_SPLIT=1), both
+  measured against the exact fp32 FMA path of the same handle -- up to the full C2 size
+  (1028 tiles, 7 per CTA) that the oracle cannot reach in seconds.  Both run the same tf32
+  reverse chain; the weight-gradient GEMM is kind::f16 (fp16 carries tf32's 10-bit mantissa;
+  saved operands exact, dY rounded to nearest at a power-of-two scale) against kind::tf32 (dY
+  truncated).  The two roundings are independent and the InfoNCE gradient cancels across the
+  rows of an observation, so the two paths differ from each other by ~sqrt(2) x their own
+  error (measured: 1e-3 .. 2e-2 per tensor at C2 size, both 1e-2 .. 8e-2 from fp32, the
+  tf32 chain's mask flips); the parity statement is therefore: per tensor, the block-major
+  path is at most 1.25 x as far from the exact gradient as the split path, plus 2e-3."""
+  from ibc_b200 import _lib
+  from ibc_b200 import engine as eng
+  e, _ = _engine(spec, precision=_lib.PRECISION_FP32, scale=1.0 if spec.depth > 4 else 1.5)
+  obs, act = _data(spec, b, n + 1, seed=29)
+  cfg = eng.loss_cfg(1.0, False)
+  obs_d, act_d = obs.cuda(), act.cuda()
+  monkeypatch.delenv('IBC_TRAIN_SPLIT', raising=False)
+  _, _, en_f, g_f = e.train_grads(obs_d, act_d, n, cfg, b, want_energies=True)
+  g_f = g_f.double().cpu().clone()
+  e.set_precision(_lib.PRECISION_TF32)
+  per_a, _, en_a, g_a = e.train_grads(obs_d, act_d, n, cfg, b, want_energies=True)
+  g_a = g_a.double().cpu().clone()
+  assert e.kernel_status() == 0
+  monkeypatch.setenv('IBC_TRAIN_SPLIT', '1')
+  per_b, _, en_b, g_b = e.train_grads(obs_d, act_d, n, cfg, b, want_energies=True)
+  g_b = g_b.double().cpu().clone()
+  assert e.kernel_status() == 0
+  assert torch.equal(en_a, en_b) and torch.equal(per_a, per_b)
+  _close(en_a, en_f, 4 * TF32_TOL, 'energies')
+  assert bool(torch.isfinite(g_a).all())
+  grms = float(g_f.pow(2).mean().sqrt())
+  for name, off, shape in omlp.param_layout(spec):
+    cnt = math.prod(shape)
+    w = g_f[off:off + cnt]
+    denom = float(w.norm()) + 1e-2 * grms * math.sqrt(cnt)
+    rel_a = float((g_a[off:off + cnt] - w).norm()) / denom
+    rel_b = float((g_b[off:off + cnt] - w).norm()) / denom
+    assert rel_a <= 1.25 * rel_b + 2e-3, (name, rel_a, rel_b)
+    if name.startswith('b') and name != 'be':
+      # bias gradients: exact fp32 column sums of the same dY in both paths
+      mutual = float((g_a[off:off + cnt] - g_b[off:off + cnt]).norm()) / denom
+      assert mutual < 1e-3, (name, mutual)
+
+
 def test_adam_step_matches_oracle():
   from ibc_b200 import engine as eng
   g = torch.Generator().manual_seed(0)
