@@ -92,10 +92,10 @@ int tmem_reverse(ibc_handle* h, const float* dE, int64_t R, const float* xa_save
                  cudaStream_t s);
 // reverse chain + weight / bias gradients of the W x W layers in one block-major
 // kernel (mlp_bwd_wgrad.cu); scratch sizes in floats
-size_t bwd_wgrad_scratch_floats(const ibc_handle* h, int64_t R, size_t* park, size_t* pw, size_t* pb);
+size_t bwd_wgrad_scratch_floats(const ibc_handle* h, int64_t R, size_t* park, size_t* accw);
 int tmem_reverse_wgrad(ibc_handle* h, const float* dE, const uint32_t* dE_absmax, int64_t R,
-                       const void* xa16, const uint32_t* mask_save, float* gpark, float* part_w,
-                       float* part_b, float* grads, cudaStream_t s);
+                       const void* xa16, const float* hn, const uint32_t* mask_save, float* gpark,
+                       float* acc_w, float* grads, cudaStream_t s);
 // tcgen05 training path (mlp_umma_train.cu): W == 128, no gradient penalty.
 bool umma_train_supported(const Layout& L);
 int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* actions, int64_t N,

@@ -97,8 +97,11 @@ struct BwdWgradParams {
   const uint32_t* mask_save;  // ReLU masks of the 2nb layers
   float* gpark;               // [tiles][32 chunks][128 rows][4]: residual gradient between blocks;
                               // after the kernel: the gradient of the first Dense output (g0)
-  float* part_w;              // [grid][2nb][32 chunks][128 in][4]: per-CTA weight-gradient partials
-  float* part_b;              // [grid][2nb][4 sub-tiles][128]: per-CTA bias-gradient partials
+  const float* hn;            // forward's final residual stream, [tile][32 chunks][128 rows][4] (for dwe)
+  float* acc_w;               // [2nb][32 chunks][128 in][4]: weight gradients, accumulated with coalesced
+                              // vector reductions (permuted into the flat gradient afterwards)
+  float* grads;               // flat gradient: b1 / b2 / we entries accumulated here directly
+  Layout L;
   const float* packed;
   int64_t off_rev_l, off_we;
   int64_t R;
@@ -125,6 +128,10 @@ __device__ __forceinline__ float4 ldg_hint(const float4* ptr, uint64_t pol) {
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(ptr), "l"(pol));
   return v;
+}
+__device__ __forceinline__ void red_add_v4(float* ptr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
 }
 __device__ __forceinline__ void stg_hint(float4* ptr, const float4 v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
@@ -201,6 +208,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nsl = 2 * p.nb;
   const int ntile = (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // Boustrophedon: odd blocks visit the CTA's tiles in reverse, so the last tile of a block is
+  // the first of the next and its residual gradient stays in registers (no park round trip).
+  auto tile_of = [&](int blk, int i) -> int64_t {
+    const int k = (blk & 1) ? ntile - 1 - i : i;
+    return (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+  };
 
   if (tid == 0) {
     s_abort = 0;
@@ -250,10 +263,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
     uint32_t ph_d = 0;
     float gr[32];                      // gradient of the residual stream: this row, this chunk
     float bsum_g = 0.f, bsum_u = 0.f;  // lane l: column 32 cc + l of db2_j / db1_j over this CTA's rows
+    float bsum_e = 0.f;                // the same for dwe (top block only)
     for (int blk = 0; blk < p.nb; ++blk) {
       const int jb = p.nb - 1 - blk;
       for (int k = 0; k < ntile; ++k) {
-        const int64_t tile = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+        const int64_t tile = tile_of(blk, k);
+        const bool carry_in = blk > 0 && k == 0;                     // g is still in registers
+        const bool carry_out = blk < p.nb - 1 && k == ntile - 1;     // ... and stays there
         const int64_t r = tile * 128 + row;
         const bool stamp = p.dbg && blockIdx.x == 0 && tid == 0 && (blk * ntile + k) < 24;
         long long* dbg = stamp ? p.dbg + (blk * ntile + k) * 8 : nullptr;
@@ -264,10 +280,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
                        cc * 8 * 128 + row;
         uint32_t v[32];
         // ---- G: g into X (tf32), then its image and column sums -----------------
+        float de = 0.f;
         if (blk == 0) {
-          const float de = (r < p.R) ? p.dE[r] : 0.f;      // g_top = dE (x) we
+          de = (r < p.R) ? p.dE[r] : 0.f;                  // g_top = dE (x) we
 #pragma unroll
           for (int i = 0; i < 32; ++i) gr[i] = de * we[cc * 32 + i];
+        } else if (carry_in) {
         } else if (p.dbg_mode & 1) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) gr[i] = 1e-6f * we[cc * 32 + i];
@@ -300,6 +318,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
         __syncwarp();
         if (lane == 0) mbar_arrive(dy_full);
         if (!(p.dbg_mode & 4)) bsum_g += warp_colsum32(v, lane);
+        if (blk == 0) {
+          // Dense(1) weight gradient: dwe += dE (x) h_nb, this row's chunk of the forward's last slot
+          const float4* hrow = reinterpret_cast<const float4*>(p.hn) + tile * (int64_t)(32 * 128) +
+                               cc * 8 * 128 + row;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 x = __ldg(hrow + q * 128);
+            v[q * 4 + 0] = __float_as_uint(de * x.x); v[q * 4 + 1] = __float_as_uint(de * x.y);
+            v[q * 4 + 2] = __float_as_uint(de * x.z); v[q * 4 + 3] = __float_as_uint(de * x.w);
+          }
+          bsum_e += warp_colsum32(v, lane);
+        }
 
         // ---- U: u = Y (.) m1 in place; then its image and column sums -----------
         mbar_wait(d_ready, ph_d, abort_flag, p.status, 1001);
@@ -335,7 +365,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
 #pragma unroll
         for (int q = 0; q < 32; ++q)
           gr[q] += ((m0 >> q) & 1u) ? __uint_as_float(v[q]) : 0.f;
-        if (p.dbg_mode & 16) {
+        if (carry_out) {
+        } else if (p.dbg_mode & 16) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             park[q * 128] = make_float4(gr[q * 4 + 0], gr[q * 4 + 1], gr[q * 4 + 2], gr[q * 4 + 3]);
@@ -354,18 +385,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
 #pragma unroll 1
       for (int a = 0; a < 2; ++a) {
         const int layer = 2 * jb + 1 - a;        // a = 0: dW2_j (slot 2j+1), a = 1: dW1_j (slot 2j)
-        float4* pw = reinterpret_cast<float4*>(
-            p.part_w + ((int64_t)blockIdx.x * nsl + layer) * (int64_t)(W * W)) + cc * 8 * 128 + row;
+        float* pw = p.acc_w + (int64_t)layer * (W * W) + ((cc * 8 * 128) + row) * 4;
         uint32_t v[32];
         tmem_ld32(col_x + (uint32_t)((2 + a) * W), v);
         tmem_ld_wait(v);
+        // 512 contiguous bytes per warp instruction; 148 CTAs reduce into the same 64 KB
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-          pw[q * 128] = make_float4(__uint_as_float(v[q * 4 + 0]) * inv_scale, __uint_as_float(v[q * 4 + 1]) * inv_scale,
-                                    __uint_as_float(v[q * 4 + 2]) * inv_scale, __uint_as_float(v[q * 4 + 3]) * inv_scale);
-        float* pb = p.part_b + (((int64_t)blockIdx.x * nsl + layer) * 4 + wq) * W + cc * 32 + lane;
-        *pb = a ? bsum_u : bsum_g;
+          red_add_v4(pw + q * 128 * 4, __uint_as_float(v[q * 4 + 0]) * inv_scale, __uint_as_float(v[q * 4 + 1]) * inv_scale,
+                     __uint_as_float(v[q * 4 + 2]) * inv_scale, __uint_as_float(v[q * 4 + 3]) * inv_scale);
+        atomicAdd(p.grads + (a ? p.L.b1(jb) : p.L.b2(jb)) + cc * 32 + lane, a ? bsum_u : bsum_g);
       }
+      if (blk == 0) atomicAdd(p.grads + p.L.we + cc * 32 + lane, bsum_e);
       bsum_g = 0.f; bsum_u = 0.f;
       tc_fence_before();
       mbar_arrive(acc_free);
@@ -387,14 +418,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
     auto prefetch_item = [&](int T) {
       if (T >= nitems) return;
       const int blk = T / ntile, k = T - blk * ntile, jb = p.nb - 1 - blk;
-      const int64_t tile = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+      const int64_t tile = tile_of(blk, k);
       const uint4* src = p.xa16 + (tile * nsl + 2 * jb) * (int64_t)(16 * 128);
 #pragma unroll 1
       for (int i = 0; i < 4; ++i)
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + (int64_t)i * 1024),
                      "r"(16384u)
                      : "memory");
-      if (blk > 0) {     // the parked residual gradient of the same tile (L2-resident unless evicted)
+      if (blk > 0 && k > 0) {     // the parked residual gradient of the same tile (L2-resident unless evicted)
         const float* pk = p.gpark + tile * (int64_t)TT::kTileFloats;
 #pragma unroll 1
         for (int i = 0; i < 4; ++i)
@@ -413,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
       const int x = u & 7, T = u >> 3;
       const int blk = T / ntile, k = T - blk * ntile, jb = p.nb - 1 - blk;
       const int slot = (x < 4) ? 2 * jb + 1 : 2 * jb;
-      const int64_t tile = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+      const int64_t tile = tile_of(blk, k);
       const uint4* src = p.xa16 + (tile * nsl + slot) * (int64_t)(16 * 128) + (x & 3) * 32 + lane;
       const int stage = u & (kAStages - 1), sstage = stage >> 2;     // slot stage = 4 sub-tiles
       if ((u & 3) == 0)
@@ -523,62 +554,42 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-// grads += sum over CTAs of the partials; grid = (2nb * 16, splits), 256 threads.
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part_w,
-                                                           const float* __restrict__ part_b,
-                                                           int ncta, int nsl, Layout L,
-                                                           float* __restrict__ grads) {
+// The accumulated weight gradients from the reduction layout [layer][chunk c][input row m][4]
+// into the flat gradient's Keras layout [in][out].
+__global__ void __launch_bounds__(256) wgrad_permute_kernel(const float* __restrict__ acc_w, Layout L,
+                                                            float* __restrict__ grads) {
   constexpr int W = kW;
   const int layer = blockIdx.x >> 4;
   const int f = ((blockIdx.x & 15) << 8) + threadIdx.x;          // float4 index: chunk c, input row m
   const int c = f >> 7, m = f & 127;
-  const int per = (ncta + gridDim.y - 1) / gridDim.y;
-  const int c0 = blockIdx.y * per, c1 = min(ncta, c0 + per);
   const int j = layer >> 1;
-  const bool is_w2 = (layer & 1) != 0;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4* src = reinterpret_cast<const float4*>(part_w) + (int64_t)layer * (W * W / 4) + f;
-#pragma unroll 4
-  for (int cta = c0; cta < c1; ++cta) {
-    const float4 v = src[(int64_t)cta * nsl * (W * W / 4)];
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-  }
-  float* dw = grads + (is_w2 ? L.w2(j) : L.w1(j)) + (int64_t)m * W + c * 4;
-  atomicAdd(dw + 0, acc.x); atomicAdd(dw + 1, acc.y); atomicAdd(dw + 2, acc.z); atomicAdd(dw + 3, acc.w);
-  if ((blockIdx.x & 15) == 0 && threadIdx.x < W) {
-    float s = 0.f;
-    for (int cta = c0; cta < c1; ++cta) {
-      const float* pb = part_b + (((int64_t)cta * nsl + layer) * 4) * W + threadIdx.x;
-      s += pb[0] + pb[W] + pb[2 * W] + pb[3 * W];
-    }
-    atomicAdd(grads + (is_w2 ? L.b2(j) : L.b1(j)) + threadIdx.x, s);
-  }
+  const float4 v = reinterpret_cast<const float4*>(acc_w)[(int64_t)layer * (W * W / 4) + f];
+  float* dw = grads + ((layer & 1) ? L.w2(j) : L.w1(j)) + (int64_t)m * W + c * 4;
+  *reinterpret_cast<float4*>(dw) = v;
 }
 
 }  // namespace
 
-size_t bwd_wgrad_scratch_floats(const ibc_handle* h, int64_t R, size_t* park, size_t* pw, size_t* pb) {
+size_t bwd_wgrad_scratch_floats(const ibc_handle* h, int64_t R, size_t* park, size_t* accw) {
   const Layout& L = h->L;
   const int64_t tiles = (R + 127) / 128;
-  const int grid = tiles < h->sm_count ? (int)tiles : h->sm_count;
   *park = (size_t)tiles * 128 * kW;
-  *pw = (size_t)grid * (2 * L.nb) * kW * kW;
-  *pb = (size_t)grid * (2 * L.nb) * 4 * kW;
-  return *park + *pw + *pb;
+  *accw = (size_t)(2 * L.nb) * kW * kW;
+  return *park + *accw;
 }
 
-// Reverse chain + weight / bias gradients of the 2nb W x W layers.  grads must be
-// zeroed (or hold what is to be accumulated onto).  On return gpark holds g0, the gradient
-// of the first Dense output, in the tile layout [tile][chunk (32)][128 rows][4].
+// Reverse chain + weight / bias gradients of the 2nb W x W layers and of Dense(1)'s kernel.
+// grads must be zeroed (or hold what is to be accumulated onto).  On return gpark holds g0, the
+// gradient of the first Dense output, in the tile layout [tile][chunk (32)][128 rows][4].
 int tmem_reverse_wgrad(ibc_handle* h, const float* dE, const uint32_t* dE_absmax, int64_t R,
-                       const void* xa16, const uint32_t* mask_save, float* gpark, float* part_w,
-                       float* part_b, float* grads, cudaStream_t s) {
+                       const void* xa16, const float* hn, const uint32_t* mask_save, float* gpark,
+                       float* acc_w, float* grads, cudaStream_t s) {
   const Layout& L = h->L;
   const PackedLayout pl = make_packed_layout(L);
   BwdWgradParams p;
   p.dE = dE; p.dE_absmax = dE_absmax; p.xa16 = reinterpret_cast<const uint4*>(xa16);
-  p.mask_save = mask_save; p.gpark = gpark;
-  p.part_w = part_w; p.part_b = part_b; p.packed = h->packed;
+  p.mask_save = mask_save; p.gpark = gpark; p.hn = hn;
+  p.acc_w = acc_w; p.grads = grads; p.L = L; p.packed = h->packed;
   p.off_rev_l = pl.rev_l; p.off_we = pl.vecs + (int64_t)(2 * L.nb + 1) * L.W;
   p.R = R; p.nb = L.nb;
   const int64_t tiles = (R + 127) / 128;
@@ -599,14 +610,11 @@ int tmem_reverse_wgrad(ibc_handle* h, const float* dE, const uint32_t* dE_absmax
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     attr[h->device] = true;
   }
+  IBC_CUDA(h, cudaMemsetAsync(acc_w, 0, (size_t)(2 * L.nb) * kW * kW * 4, s));
   mlp_bwd_wgrad_tmem_kernel<<<grid, kThreads, kSmemBytes, s>>>(p);
   IBC_LAUNCH_CHECK(h);
-  {
-    const int splits = grid >= 16 ? 4 : 1;
-    dim3 g(2 * L.nb * 16, splits);
-    wgrad_reduce_kernel<<<g, 256, 0, s>>>(part_w, part_b, grid, 2 * L.nb, L, grads);
-    IBC_LAUNCH_CHECK(h);
-  }
+  wgrad_permute_kernel<<<2 * L.nb * 16, 256, 0, s>>>(acc_w, L, grads);
+  IBC_LAUNCH_CHECK(h);
   if (p.dbg) {
     cudaStreamSynchronize(s);
     std::vector<long long> hb(kDbgWords);
@@ -617,10 +625,10 @@ int tmem_reverse_wgrad(ibc_handle* h, const float* dE, const uint32_t* dE_absmax
     for (int i = 0; i < 24; ++i) {
       const long long* e = &hb[i * 8];
       if (!e[0]) break;
-      fprintf(stderr, "[ibc timeline bwd_wgrad] %3d | %8lld %8lld | %8lld %8lld %8lld %8lld | %8lld %8lld\n", i,
+      fprintf(stderr, "[ibc timeline bwd_wgrad] %3d | %8lld %8lld %8lld | %8lld %8lld %8lld | %8lld %8lld\n", i,
               e[0] - t0, e[1] - t0, e[2] - t0, e[3] - t0, e[4] - t0, e[5] - t0, e[6] - t0, e[7] - t0);
     }
-    fprintf(stderr, "[ibc timeline bwd_wgrad wgrad issuer] unit | start dy_full a_full issued\n");
+    fprintf(stderr, "[ibc timeline bwd_wgrad wgrad issuer] batch | start dy_full a_full issued\n");
     for (int u = 0; u < 48; ++u) {      // batches of four sub-tiles (one slot)
       const long long* e = &hb[1024 + u * 4];
       fprintf(stderr, "[ibc timeline bwd_wgrad wg] %3d | %8lld %8lld %8lld %8lld\n", u, e[0] - t0, e[1] - t0,
@@ -629,6 +637,11 @@ int tmem_reverse_wgrad(ibc_handle* h, const float* dE, const uint32_t* dE_absmax
   }
   return IBC_OK;
 }
+
+}  // namespace ibc
+
+namespace ibc {
+using namespace umma;
 
 // ---------------------------------------------------------------------------
 // Probe of the kind::f16 MN-major descriptor: D[128, N] = A[K, 128]^T . B[K, N] with

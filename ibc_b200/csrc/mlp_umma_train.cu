@@ -906,12 +906,12 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
   const bool split_env = getenv("IBC_TRAIN_SPLIT") != nullptr;
   static const bool force_smem = getenv("IBC_SMEM_OPERANDS") != nullptr;
   const bool fused_bwd = !split_env && !force_smem && tmem_path_supported(L);
-  size_t park_floats = 0, pw_floats = 0, pb_floats = 0;
+  size_t park_floats = 0, pw_floats = 0, pb_floats = 0;   // pw: the reduction-layout weight gradients
   // block-major backward: fp16 operand tiles (2nb slots x 32 KB per tile) + the fp32 h_nb tile
   const int64_t tiles128 = (R + 127) / 128;
   size_t xa16_bytes = 0, hn_floats = 0;
   if (fused_bwd) {
-    bwd_wgrad_scratch_floats(h, R, &park_floats, &pw_floats, &pb_floats);
+    bwd_wgrad_scratch_floats(h, R, &park_floats, &pw_floats);
     xa16_bytes = (size_t)tiles128 * (2 * nb) * 128 * kW * 2;
     hn_floats = (size_t)tiles128 * 128 * kW;
     xa_floats = 0;
@@ -974,10 +974,11 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
     attr_done = true;
   }
   if (fused_bwd)
-    IBC_TRY(tmem_reverse_wgrad(h, dE, de_absmax, R, xa16, masks, gpark, part_w, part_b, grads, s));
+    IBC_TRY(tmem_reverse_wgrad(h, dE, de_absmax, R, xa16, hn, masks, gpark, part_w, grads, s));
   else
     IBC_TRY(umma_reverse(h, dE, R, xa, masks, gy, g0, nullptr, s));
-  {  // Dense(1) weight gradient from the forward's last slot
+  if (!fused_bwd) {  // Dense(1) weight gradient from the forward's last slot (the block-major
+                     // backward takes it in its top block)
     const int tiles = (int)((R + 127) / 128);
     const int blocks = tiles < 2 * h->sm_count ? tiles : 2 * h->sm_count;
     dwe_kernel<<<blocks, 256, 0, s>>>(fused_bwd ? hn : xa, dE, R, tiles, nb, grads + L.we, fused_bwd ? 1 : 0);
