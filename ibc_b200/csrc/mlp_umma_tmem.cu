@@ -291,14 +291,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tmem_kernel(FwdTmemParams
                                 __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
             }
             if (kSave == 2 && !kLast) {
-              // what the tensor core reads of the operand (low 13 bits truncated), as fp16
+              // what the tensor core reads of the operand (low 13 bits truncated), as fp16:
+              // the operand carries the round-to-nearest offset, so convert toward zero
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 uint4 w;
-                w.x = pack_half2(__uint_as_float(v[q * 8 + 0] & 0xFFFFE000u), __uint_as_float(v[q * 8 + 1] & 0xFFFFE000u));
-                w.y = pack_half2(__uint_as_float(v[q * 8 + 2] & 0xFFFFE000u), __uint_as_float(v[q * 8 + 3] & 0xFFFFE000u));
-                w.z = pack_half2(__uint_as_float(v[q * 8 + 4] & 0xFFFFE000u), __uint_as_float(v[q * 8 + 5] & 0xFFFFE000u));
-                w.w = pack_half2(__uint_as_float(v[q * 8 + 6] & 0xFFFFE000u), __uint_as_float(v[q * 8 + 7] & 0xFFFFE000u));
+                w.x = pack_half2_rz(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+                w.y = pack_half2_rz(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+                w.z = pack_half2_rz(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+                w.w = pack_half2_rz(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
                 h_slot[(c32 * 4 + q) * 128] = w;
               }
             }

@@ -50,5 +50,13 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   return r;
 }
 
+// the same toward zero: for an operand that already carries the tf32 round-to-nearest offset
+// (bits + 0x1000, umma_pack.cuh) truncating to fp16's 10-bit mantissa completes the rounding
+__device__ __forceinline__ uint32_t pack_half2_rz(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rz.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 }  // namespace umma
 }  // namespace ibc

@@ -576,6 +576,10 @@ def test_train_grads_block_major_backward_matches_the_split_kernels(spec, b, n, 
     denom = float(w.norm()) + 1e-2 * grms * math.sqrt(cnt)
     rel_a = float((g_a[off:off + cnt] - w).norm()) / denom
     rel_b = float((g_b[off:off + cnt] - w).norm()) / denom
+    if name == 'be':
+      # d/d be = sum of all dE = 0 up to rounding (softmax gradients sum to zero): atomics-order
+      # noise in every path, pinned against the size of its terms by the oracle tests above
+      continue
     assert rel_a <= 1.25 * rel_b + 2e-3, (name, rel_a, rel_b)
     if name.startswith('b') and name != 'be':
       # bias gradients: exact fp32 column sums of the same dY in both paths
