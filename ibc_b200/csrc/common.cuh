@@ -147,6 +147,21 @@ struct ibc_handle {
                cudaGetErrorString(_e), __FILE__, __LINE__);                   \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: remember which devices a call
+// site has raised it on (a process-wide flag left the second device of a multi-GPU process
+// at the 48 KB default).
+#define IBC_RAISE_SMEM(h, kernel, bytes)                                                   \
+  do {                                                                                     \
+    static std::atomic<unsigned long long> _done{0};                                       \
+    int _d = 0;                                                                            \
+    if (h) _d = (h)->device; else cudaGetDevice(&_d);                                      \
+    if (_d < 0 || _d >= 64 || !((_done.load(std::memory_order_relaxed) >> _d) & 1ull)) {   \
+      IBC_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)(bytes)));                                     \
+      if (_d >= 0 && _d < 64) _done.fetch_or(1ull << _d, std::memory_order_relaxed);        \
+    }                                                                                      \
+  } while (0)
+
 #define IBC_TRY(expr)            \
   do {                           \
     int _rc = (expr);            \

@@ -680,12 +680,7 @@ int debug_mode() {
 template <bool TA, bool TB, int BN, bool CONV>
 int launch_tc(ibc_handle* h, const GemmP& p, int tm, int tn, int splits, cudaStream_t s) {
   using C = TcCfg<BN>;
-  static bool attr = false;
-  if (!attr) {
-    IBC_CUDA(h, cudaFuncSetAttribute(gemm_tc_kernel<TA, TB, BN, CONV>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
-    attr = true;
-  }
+  IBC_RAISE_SMEM(h, (gemm_tc_kernel<TA, TB, BN, CONV>), C::kSmem);
   const int64_t total = (int64_t)tm * tn * splits;
   if (total > 0x7fffffff) IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "gemm_tc: too many output blocks");
   const int sms = h ? h->sm_count : 148;

@@ -416,12 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tmem_kernel(LangevinPara
 template <int AMAX>
 int launch_langevin(ibc_handle* h, const LangevinParams& p, cudaStream_t s) {
   const size_t smem = langevin_smem_bytes(p.nb, p.KP, AMAX);
-  static size_t attr = 0;
-  if (smem > attr) {
-    IBC_CUDA(h, cudaFuncSetAttribute(langevin_tmem_kernel<AMAX>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  IBC_RAISE_SMEM(h, langevin_tmem_kernel<AMAX>, 227 * 1024 - 1024);
   const int64_t tiles = (p.R + 127) / 128;
   const int grid = tiles < h->sm_count ? (int)tiles : h->sm_count;
   langevin_tmem_kernel<AMAX><<<grid, kThreads, smem, s>>>(p);

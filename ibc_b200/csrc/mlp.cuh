@@ -70,6 +70,7 @@ int langevin_umma(ibc_handle* h, const float* obs, int64_t B, float* actions, in
                   cudaStream_t s);
 // widths that are a multiple of 128 above 256: one tcgen05 GEMM kernel per layer (mlp_wide.cu)
 bool wide_supported(const Layout& L);
+int wide_pack_if_stale(ibc_handle* h, cudaStream_t s);
 int mlp_energy_wide(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
                     float* E, float* dEda, bool apply_exp, cudaStream_t s);
 // the whole Langevin chain of a width-128 stack as one persistent kernel (langevin_tmem.cu)

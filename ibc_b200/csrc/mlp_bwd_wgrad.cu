@@ -603,13 +603,7 @@ int tmem_reverse_wgrad(ibc_handle* h, const float* dE, const uint32_t* dE_absmax
     IBC_CUDA(h, cudaMalloc((void**)&p.dbg, kDbgWords * sizeof(long long)));
     IBC_CUDA(h, cudaMemsetAsync(p.dbg, 0, kDbgWords * sizeof(long long), s));
   }
-  constexpr int kMaxDev = 64;
-  static bool attr[kMaxDev] = {false};
-  if (h->device >= 0 && h->device < kMaxDev && !attr[h->device]) {
-    IBC_CUDA(h, cudaFuncSetAttribute(mlp_bwd_wgrad_tmem_kernel,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr[h->device] = true;
-  }
+  IBC_RAISE_SMEM(h, mlp_bwd_wgrad_tmem_kernel, kSmemBytes);
   IBC_CUDA(h, cudaMemsetAsync(acc_w, 0, (size_t)(2 * L.nb) * kW * kW * 4, s));
   mlp_bwd_wgrad_tmem_kernel<<<grid, kThreads, kSmemBytes, s>>>(p);
   IBC_LAUNCH_CHECK(h);

@@ -790,12 +790,7 @@ int launch_fwd_impl(ibc_handle* h, const FwdParams& p, cudaStream_t s) {
   if (smem > 227 * 1024)
     IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "tcgen05 forward: depth %d needs %zu B of shared memory",
              2 * p.nb, smem);
-  static size_t attr_smem = 0;     // per template instance; raised lazily
-  if (smem > attr_smem) {
-    IBC_CUDA(h, cudaFuncSetAttribute(mlp_fwd_umma_kernel<W, NT, kSave>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
+  IBC_RAISE_SMEM(h, (mlp_fwd_umma_kernel<W, NT, kSave>), 227 * 1024 - 1024);    // per template instance
   const int grid = p.num_groups < h->sm_count ? p.num_groups : h->sm_count;
   mlp_fwd_umma_kernel<W, NT, kSave><<<grid, S::kThreads, smem, s>>>(p);
   IBC_LAUNCH_CHECK(h);

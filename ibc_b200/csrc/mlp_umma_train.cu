@@ -659,12 +659,7 @@ __global__ void __launch_bounds__(WgradSmem::kThreads, 1) mlp_wgrad_umma_kernel(
 template <int W_, int NT_>
 static int launch_bwd(ibc_handle* h, const BwdParams& bp, cudaStream_t s) {
   using S = BwdSmem<W_, NT_>;
-  static bool attr_set = false;    // per template instance
-  if (!attr_set) {
-    IBC_CUDA(h, cudaFuncSetAttribute(mlp_bwd_umma_kernel<W_, NT_>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
-    attr_set = true;
-  }
+  IBC_RAISE_SMEM(h, (mlp_bwd_umma_kernel<W_, NT_>), S::kBytes);    // per template instance
   const int grid = bp.num_groups < h->sm_count ? bp.num_groups : h->sm_count;
   mlp_bwd_umma_kernel<W_, NT_><<<grid, S::kThreads, S::kBytes, s>>>(bp);
   IBC_LAUNCH_CHECK(h);
@@ -966,13 +961,7 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
   (void)gl;
   mark(2);
 
-  static bool attr_done = false;
-  if (!attr_done) {
-    IBC_CUDA(h, cudaFuncSetAttribute(mlp_wgrad_umma_kernel,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)WgradSmem::kBytes));
-    attr_done = true;
-  }
+  IBC_RAISE_SMEM(h, mlp_wgrad_umma_kernel, WgradSmem::kBytes);
   if (fused_bwd)
     IBC_TRY(tmem_reverse_wgrad(h, dE, de_absmax, R, xa16, hn, masks, gpark, part_w, grads, s));
   else

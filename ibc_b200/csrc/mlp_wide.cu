@@ -186,12 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_wide_kernel(DenseParams p) 
 constexpr size_t kDenseSmem = (size_t)kStages * kStageBytes + 512 + (2 * kStages + 2) * 8 + 64;
 
 int dense_wide(ibc_handle* h, const DenseParams& p, int64_t tiles, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
-    IBC_CUDA(h, cudaFuncSetAttribute(dense_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)kDenseSmem));
-    attr = true;
-  }
+  IBC_RAISE_SMEM(h, dense_wide_kernel, kDenseSmem);
   dim3 grid((unsigned)tiles, (unsigned)(p.N / 128));
   dense_wide_kernel<<<grid, kThreads, kDenseSmem, s>>>(p);
   IBC_LAUNCH_CHECK(h);
@@ -367,6 +362,15 @@ static int wide_pack(ibc_handle* h, cudaStream_t s) {
   pack_wide_kernel<<<592, 256, 0, s>>>(h->params, L, h->packed);
   IBC_LAUNCH_CHECK(h);
   h->packed_stale = false;
+  return IBC_OK;
+}
+
+// Repack the tcgen05 operand copies if the parameters changed.  Callers that capture the wide
+// path into a CUDA graph (samplers.cu::langevin) do this BEFORE the capture / replay, on their
+// own stream: a pack recorded inside -- or left out of -- a captured chain would replay with
+// whatever was packed at capture time.
+int wide_pack_if_stale(ibc_handle* h, cudaStream_t s) {
+  if (h->packed_stale) IBC_TRY(wide_pack(h, s));
   return IBC_OK;
 }
 

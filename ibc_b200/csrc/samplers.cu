@@ -396,12 +396,7 @@ int resample(ibc_handle* h, const float* logits, const double* uniforms, int64_t
   if (smem > 220 * 1024)
     IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "resample: n=%lld exceeds the shared-memory CDF (max %d)",
              (long long)n, (int)((220 * 1024 - 16384) / 12));
-  static bool attr_set = false;
-  if (!attr_set) {
-    IBC_CUDA(h, cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     220 * 1024));
-    attr_set = true;
-  }
+  IBC_RAISE_SMEM(h, resample_kernel, 220 * 1024);
   resample_kernel<<<(unsigned)B, threads, smem, s>>>(logits, uniforms, (int)n, (int)count, seed,
                                                      rng_stream, draws, counts, rows);
   IBC_LAUNCH_CHECK(h);
@@ -565,6 +560,9 @@ int langevin(ibc_handle* h, const float* obs, int64_t B, float* actions, int64_t
   // per-layer tensor-core stacks: ~20 small launches per iteration -> replay from a graph
   if (h->precision == IBC_PRECISION_TF32 && wide_supported(h->L) && !normals &&
       chain_graphs_enabled() && c.num_iterations >= 4) {
+    // the operand copies of the current parameters, outside the capture: a replayed graph
+    // never repacks (ibc_params_changed / ibc_bind_params after the capture)
+    IBC_TRY(wide_pack_if_stale(h, s));
     return run_chain_graphed(
         h, obs, B, actions, n, mn, mx, c, seed, steps, chain_actions, chain_energies,
         chain_grad_norms, s,

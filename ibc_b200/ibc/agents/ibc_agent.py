@@ -309,7 +309,10 @@ class ImplicitBCAgent(BehavioralCloningAgent):
       if self._fraction_langevin_samples > 0.:
         # late fusion: un-tiled frames, encoded once inside the sampler (mcmc.py:384-388;
         # upstream binds langevin_actions_given_obs.late_fusion in the gin file)
-        tiled = obs_flat if self._late_fusion else torch.repeat_interleave(obs_flat, n, dim=0)
+        # the engine samplers take un-tiled observations (mcmc._untile passes them through);
+        # only a generic callable network needs the B*n-row tile_batch copy
+        tiled = obs_flat if (self._late_fusion or isinstance(net, MLPEBM)) \
+            else torch.repeat_interleave(obs_flat, n, dim=0)
         lf = {'late_fusion': True,
               'observation_encoding': getattr(self, '_enc', None)} if self._late_fusion else {}
         out = mcmc.langevin_actions_given_obs(
@@ -376,10 +379,26 @@ class ImplicitBCAgent(BehavioralCloningAgent):
     ev.record()
     self._pending_finite = (host, ev)
 
+  def flush_checks(self):
+    """Look at the last deferred finiteness check (call when training ends)."""
+    pending = getattr(self, '_pending_finite', None)
+    if pending is not None:
+      host, ev = pending
+      ev.synchronize()
+      self._pending_finite = None
+      if not math.isfinite(float(host[0])):
+        raise FloatingPointError('Loss is inf or nan')
+
   def _train(self, experience, weights=None, draws=None):
     loss_info, grads = self._loss(experience, weights=weights, training=True, draws=draws)
-    self._check_finite(loss_info.loss)
     parallel.allreduce_gradients(grads)                         # MirroredStrategy all-reduce
+    probe = loss_info.loss
+    if parallel.num_replicas() > 1:
+      # every rank must raise on the same step (a rank that raised before the all-reduce would
+      # leave the others blocked in NCCL): d/d be = sum of dE over ALL replicas is non-finite
+      # as soon as any replica's loss is, and 0 * (inf | nan) = nan
+      probe = probe + grads[-1] * 0.0
+    self._check_finite(probe)
     self._optimizer.apply_gradients(self.cloning_network, grads)
     self.train_step_counter += 1
     return loss_info

@@ -153,18 +153,31 @@ class MLPEBM:
         un = un / (torch.sum(un ** 2) ** 0.5 + 1e-12)
         sigma = (v @ w2d) @ un.t()
         t = (w2d / sigma).reshape(shape)
-        if update_u:
+        # resnet.py:136 calls the projection layer WITHOUT `training=`, so DenseSN never
+        # assigns its u (spectral_norm.py:76-80): the first layer keeps its initial u for the
+        # whole run and is still normalised with it
+        if update_u and nm != 'Wp':
           self._sn_u[nm] = un.detach()
       pieces.append(t.reshape(-1))
     return raw, torch.cat(pieces)
 
+  def _set_effective(self, eff: torch.Tensor):
+    """One persistent buffer for W_bar: the engine keys its captured Langevin graphs on the
+    bound pointer, so a fresh tensor per optimizer step would defeat (and leak) them."""
+    if self._effective is None or self._effective is self.params:
+      self._effective = eff.detach().clone().contiguous()
+      self.engine.bind_params(self._effective)
+    else:
+      self._effective.copy_(eff.detach())
+      self.engine.params_changed()
+
   def _rebind(self):
     if self._sn_u is None:
       self._effective = self.params
+      self.engine.bind_params(self._effective)
     else:
       _, eff = self._spectral_effective(update_u=False, need_graph=False)
-      self._effective = eff.detach().contiguous()
-    self.engine.bind_params(self._effective)
+      self._set_effective(eff)
 
   def effective_params_for_training(self):
     """(raw_leaf, effective_flat_with_graph) -- used by the agent to chain
@@ -174,8 +187,7 @@ class MLPEBM:
     if self._sn_u is None:
       return None, self.params
     raw, eff = self._spectral_effective(update_u=True, need_graph=True)
-    self._effective = eff.detach().contiguous()
-    self.engine.bind_params(self._effective)
+    self._set_effective(eff)
     return raw, eff
 
   # -- forward ------------------------------------------------------------------

@@ -9,6 +9,7 @@ Tolerances (stated per test):
     initialisation (measured worst case 2.1e-3; SURVEY.md 8d proposed 2e-3).
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -72,7 +73,8 @@ SPECS_TF32 = [
     omlp.MLPSpec(256, 32, 256, 2),   # C3 particle-32D
     omlp.MLPSpec(20, 2, 128, 2),
     omlp.MLPSpec(39, 28, 512, 8),    # C4 d4rl door-human: per-layer tensor-core GEMMs
-    omlp.MLPSpec(16, 2, 1024, 2),    # wide and shallow (particle "best" is 2048 x 2)
+    omlp.MLPSpec(16, 2, 1024, 2),    # wide and shallow
+    omlp.MLPSpec(256, 32, 2048, 2),  # C3 "best" (particle/mlp_ebm_langevin_best.gin:42-43)
 ]
 
 
@@ -114,6 +116,8 @@ def test_energy_fp32(spec, b, n):
 @pytest.mark.parametrize('b,n', [(3, 5), (2, 256), (5, 300), (1, 2048), (512, 257)])
 def test_energy_tf32(spec, b, n, scale, tol):
   from ibc_b200 import _lib
+  if spec.width >= 2048 and b * n > 4096:
+    pytest.skip('fp64 oracle of a 2048-wide stack on 131 584 rows takes minutes')
   e, flat = _engine(spec, precision=_lib.PRECISION_TF32, scale=scale)
   obs, act = _data(spec, b, n)
   got = e.energy(obs.cuda(), act.cuda(), n)
@@ -138,7 +142,8 @@ def test_energy_dact_fp32(spec):
 
 @pytest.mark.parametrize('spec', [omlp.MLPSpec(20, 2, 128, 4), omlp.MLPSpec(256, 32, 256, 2),
                                   omlp.MLPSpec(16, 2, 256, 2), omlp.MLPSpec(20, 2, 128, 16),
-                                  omlp.MLPSpec(39, 28, 512, 8), omlp.MLPSpec(16, 2, 1024, 2)],
+                                  omlp.MLPSpec(39, 28, 512, 8), omlp.MLPSpec(16, 2, 1024, 2),
+                                  omlp.MLPSpec(256, 32, 2048, 2)],
                          ids=str)
 @pytest.mark.parametrize('b,n', [(4, 9), (8, 100)])
 def test_energy_dact_tf32(spec, b, n):
@@ -258,6 +263,45 @@ def test_langevin_graph_replay_is_bit_identical():
     assert torch.equal(a.cpu(), b2.cpu()) and torch.equal(a.cpu(), c2.cpu())
     assert not torch.equal(a.cpu(), outs[0][0])
     assert e.kernel_status() == 0
+
+
+def test_langevin_graph_replay_follows_parameter_updates():
+  """A captured chain must sample with the CURRENT weights: capture, change the parameters
+  in place (optimizer step / checkpoint load) + params_changed(), replay, and compare with
+  a fresh handle's first (un-captured) run on the new weights -- bit for bit.  Covers the
+  per-layer wide path (width 512: the operand copies are repacked outside the capture,
+  ADVICE round 1) and the width-128 / 256 paths."""
+  from ibc_b200 import engine as eng
+  for width, depth, obs_dim, act_dim in ((512, 2, 39, 28), (256, 2, 64, 8), (128, 4, 20, 2)):
+    spec = omlp.MLPSpec(obs_dim, act_dim, width, depth)
+    e = eng.EBMEngine(obs_dim, act_dim, width, depth)
+    p = omlp.init_params(spec, seed=5).cuda().contiguous()
+    e.bind_params(p)
+    b, n = 8, 64
+    g = torch.Generator().manual_seed(1)
+    obs = torch.randn(b, obs_dim, generator=g).cuda()
+    act0 = (torch.rand(b * n, act_dim, generator=g) * 2 - 1).cuda()
+    mn = torch.full((act_dim,), -1.1).cuda()
+    mx = torch.full((act_dim,), 1.1).cuda()
+    cfg = eng.langevin_cfg(num_iterations=12)
+    before = None
+    for call in range(3):                      # plain, capture, replay
+      a = act0.clone()
+      e.langevin(obs, a, n, mn, mx, cfg, seed=77)
+      before = a.cpu()
+    p.mul_(1.5)                                # same buffer, new weights
+    e.params_changed()
+    a = act0.clone()
+    e.langevin(obs, a, n, mn, mx, cfg, seed=77)          # replay
+    after = a.cpu()
+    e2 = eng.EBMEngine(obs_dim, act_dim, width, depth)
+    e2.bind_params(p)
+    a = act0.clone()
+    e2.langevin(obs, a, n, mn, mx, cfg, seed=77)         # first call of a handle: not captured
+    fresh = a.cpu()
+    assert e.kernel_status() == 0 and e2.kernel_status() == 0
+    assert not torch.equal(before, after), (width, 'replay ignored the new weights')
+    assert torch.equal(after, fresh), (width, float((after - fresh).abs().max()))
 
 
 _FUSED_SCRIPT = r'''
@@ -419,6 +463,63 @@ def test_langevin_matches_oracle(spec, precision):
   _close(ce[0], chain.energies[0], FP32_TOL if precision == 0 else TF32_TOL, 'chain energies[0]')
   _close(cg[0], chain.grad_norms[0], 1e-4 if precision == 0 else 5e-2, 'chain grad norms[0]')
   assert float((ca[-1].cpu() - chain.actions[-1]).abs().max()) <= 5e-3 * 2.2
+
+
+@pytest.mark.parametrize('precision', [0, 1], ids=['fp32', 'tf32'])
+@pytest.mark.parametrize('name,spec,kw', [
+    ('C3', omlp.MLPSpec(256, 32, 256, 2), dict()),                       # particle/mlp_ebm_langevin.gin
+    ('C4', omlp.MLPSpec(39, 28, 512, 8),                                  # d4rl/mlp_ebm_langevin_best.gin:61-64
+     dict(noise_scale=0.5, delta_action_clip=0.5, sampler_stepsize_init=0.5)),
+    ('pushing', omlp.MLPSpec(20, 2, 128, 16), dict()),                    # pushing_states/mlp_ebm_langevin.gin
+], ids=lambda x: x if isinstance(x, str) else '')
+def test_langevin_100_iterations_on_the_training_rows(name, spec, kw, precision):
+  """SURVEY.md 8d at spec: K = 100 iterations on the training chain's B * N = 512 * 8 = 4096
+  rows with supplied normals; final actions against the oracle in fp64 (autograd dE/dact).
+
+  SURVEY proposed |da| <= 5e-3 * (max - min) and asked to calibrate it on the oracle's own
+  precision spread (scripts/diag_langevin_spread.py).  Measured: C3 and pushing_states stay
+  10x inside it in every precision, and the test holds them to it.  C4 (step size 0.5, delta
+  clip 0.5, noise 0.5 on an 8 x 512 stack, d4rl/mlp_ebm_langevin_best.gin:61-64) is an
+  expanding noisy ascent: the oracle's own fp32 run ends up to 1.0e-2 from its fp64 run, and
+  its tf32-operand emulation 1.2e-2 away ON AVERAGE (half the rows outside the bound) -- no
+  tf32 implementation can meet the per-row bound there.  So: fp32 must keep 99.5 % of the rows
+  inside the bound with a mean deviation under 5 % of it; tf32 must not be further from fp64
+  than 1.5 x the oracle's tf32 emulation (mean and 99th percentile), and where that emulation
+  itself stays inside half the bound, the bound is enforced for every row."""
+  from ibc_b200 import engine as eng
+  from oracle import tf32_emul
+  torch.set_num_threads(max(1, (os.cpu_count() or 1)))
+  e, flat = _engine(spec, precision=precision, scale=1.0)
+  b, n, k = 512, 8, 100
+  a_dim = spec.act_dim
+  obs, act0 = _data(spec, b, n, seed=13)
+  mn, mx = torch.full((a_dim,), -1.1), torch.full((a_dim,), 1.1)
+  normals = torch.randn(k, b * n, a_dim, generator=torch.Generator().manual_seed(3))
+  obs_t = torch.repeat_interleave(obs, n, 0).double()
+  f64 = flat.double()
+
+  def chain(fn):
+    return omcmc.langevin_actions_given_obs(
+        lambda _o, a: fn(f64, spec, obs_t, a), None, act0.double(), mn.double(), mx.double(),
+        normals, num_iterations=k, **kw)
+
+  want = chain(omlp.energy)
+  cfg = eng.langevin_cfg(num_iterations=k, **kw)
+  actions = act0.cuda().clone()
+  e.langevin(obs.cuda(), actions, n, mn.cuda(), mx.cuda(), cfg, normals.cuda())
+  assert e.kernel_status() == 0
+  dev = (actions.double().cpu() - want).abs().amax(dim=1)          # per row
+  bound = 5e-3 * 2.2
+  if precision == 0:
+    assert float((dev > bound).double().mean()) <= 0.005, (name, float(dev.max()))
+    assert float(dev.mean()) <= 0.05 * bound, (name, float(dev.mean()))
+  else:
+    emul = (chain(tf32_emul.energy) - want).abs().amax(dim=1)
+    assert float(dev.mean()) <= 1.5 * float(emul.mean()) + 1e-4, (name, float(dev.mean()), float(emul.mean()))
+    assert float(dev.quantile(0.99)) <= 1.5 * float(emul.quantile(0.99)) + 1e-3, (
+        name, float(dev.quantile(0.99)), float(emul.quantile(0.99)))
+    if float(emul.max()) <= 0.5 * bound:
+      assert float(dev.max()) <= bound, (name, float(dev.max()))
 
 
 def test_langevin_stepsizes_match_oracle():
@@ -601,6 +702,83 @@ def test_adam_step_matches_oracle():
     want = oagent.adam_update(want, grad, st, 1e-3)
     eng.adam_step(pg, grad.cuda(), m, v, lr_t)
   _close(pg, want, 1e-5, 'adam')
+
+
+def _ste_tf32(x):
+  """tf32 rounding with a straight-through gradient (differentiable any number of times)."""
+  from oracle import tf32_emul
+  return x + (tf32_emul.round_tf32(x) - x).detach()
+
+
+def _energy_tf32_ste(flat, spec, obs, act):
+  """oracle.mlp_ebm.energy with every tensor-core operand rounded to tf32 in the forward
+  products (so also the weights of the backward products); twice differentiable, unlike
+  oracle/tf32_emul.energy whose custom backward is not.  Calibration only."""
+  p = omlp.unpack(flat, spec)
+  o = spec.obs_dim
+  h = obs @ p['Wp'][:o] + p['bp'] + act @ p['Wp'][o:]
+  for j in range(spec.num_blocks):
+    v = _ste_tf32(torch.relu(h)) @ _ste_tf32(p[f'W1_{j}']) + p[f'b1_{j}']
+    h = h + _ste_tf32(torch.relu(v)) @ _ste_tf32(p[f'W2_{j}']) + p[f'b2_{j}']
+  return h @ p['we'] + p['be']
+
+
+@pytest.mark.parametrize('precision', [0, 1], ids=['fp32', 'tf32'])
+@pytest.mark.parametrize('spec,b,n', [(omlp.MLPSpec(256, 32, 256, 2), 64, 8),      # C3
+                                      (omlp.MLPSpec(39, 28, 512, 8), 32, 8),       # C4
+                                      (omlp.MLPSpec(256, 32, 2048, 2), 16, 8),     # C3 "best"
+                                      (omlp.MLPSpec(20, 2, 128, 16), 32, 8)],      # pushing_states langevin
+                         ids=str)
+def test_train_grads_with_penalty_match_oracle_double_backward(spec, b, n, precision):
+  """InfoNCE + gradient penalty (gradient_loss.py:37-72) at the Langevin configs' widths, BOTH
+  precisions against the oracle's fp64 autograd double backward.  fp32: 5e-4 per tensor.
+  tf32: rows whose gradient norm sits at the hinge's margin switch the penalty on or off under
+  operand rounding, so the exact-vs-tf32 gap is itself 1 - 8 % per tensor at these widths
+  (measured: the GPU and a tf32-operand emulation of the same double backward agree on it to
+  three digits, e.g. Wp of C4 4.50e-2 vs 4.50e-2, of C3-best 7.46e-2 vs 7.50e-2); the bound
+  is the calibrated one of the first-order test: at most 1.5 x the emulation's error + 5e-3."""
+  from ibc_b200 import engine as eng
+  e, flat = _engine(spec, precision=precision)
+  obs, act = _data(spec, b, n + 1, seed=31)
+  obs_t = torch.repeat_interleave(obs, n + 1, 0).double()
+  _, d0 = omlp.energy_and_dact_manual(flat.double(), spec, obs_t, act.double())
+  margin = float(d0.abs().amax(dim=1).median())       # penalty active on half the rows
+  refs = []
+  for fn in (omlp.energy, _energy_tf32_ste):
+    theta = flat.double().clone().requires_grad_(True)
+    energy_fn = lambda _o, a: fn(theta, spec, obs_t, a)    # noqa: E731
+    pred = energy_fn(None, act.double()).reshape(b, n + 1)
+    per = olosses.info_nce(pred, b, n, 1.0)
+    gl = olosses.grad_penalty(energy_fn, 'inf', b, None, act.double(), grad_margin=margin)
+    (g,) = torch.autograd.grad((per + gl).sum() / b, theta)
+    refs.append((pred.detach(), (per + gl).detach(), gl.detach(), g))
+  (pred, per, gl, want), (_, _, _, emul) = refs
+  assert float(gl.max()) > 0, 'test is vacuous: penalty inactive'
+  cfg = eng.loss_cfg(1.0, True, 'inf', margin, True, 1.0)
+  per_g, gl_g, en_g, grads = e.train_grads(obs.cuda(), act.cuda(), n, cfg, b, want_energies=True)
+  assert e.kernel_status() == 0
+  _close(en_g, pred.reshape(-1), FP32_TOL if precision == 0 else 2 * TF32_TOL, 'energies')
+  if precision == 0:
+    _close(per_g, per, 1e-4, 'per-example loss')
+  else:
+    # the hinge switches rows on and off under tf32 noise: the loss is held to the emulation's
+    # (measured worst case 3.6e-2 of |x| + rms on the C4 stack: one example per batch whose
+    # squared hinge changes by 5 %)
+    _close(per_g, refs[1][1], 5e-2, 'per-example loss (vs the tf32 emulation)')
+  grms = float(want.pow(2).mean().sqrt())
+  for name, off, shape in omlp.param_layout(spec):
+    cnt = math.prod(shape)
+    w = want[off:off + cnt]
+    g = grads[off:off + cnt].double().cpu()
+    denom = float(w.norm()) + 1e-2 * grms * math.sqrt(cnt)
+    if name == 'be':
+      continue            # vanishing sum, checked against its terms in the InfoNCE-only tests
+    rel = float((g - w).norm()) / denom
+    if precision == 0:
+      assert rel < 5e-4, (name, rel)
+    else:
+      rel_emul = float((emul[off:off + cnt] - w).norm()) / denom
+      assert rel < max(1e-2, 1.5 * rel_emul + 5e-3), (name, rel, rel_emul)
 
 
 # Langevin-config training (gradient penalty, widths 256 / 512): IBC_PRECISION_TF32 handles
