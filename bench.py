@@ -37,6 +37,48 @@ CFG = dict(name='pushing_states/mlp_ebm.gin (C2)', obs_dim=20, seq=2, act_dim=2,
            dfo_samples=16384, dfo_iterations=3)
 
 
+def workload_config(c=CFG):
+  """`config` of the JSON line -- the SAME dict in the b200 and the reference arm."""
+  rows = c['batch'] * (c['num_counter_examples'] + 1)
+  return {'workload': c['name'], 'batch_per_gpu': c['batch'],
+          'num_counter_examples': c['num_counter_examples'], 'rows_per_step_per_gpu': rows,
+          'obs_dim': c['obs_dim'], 'act_dim': c['act_dim'], 'width': c['width'], 'depth': c['depth'],
+          'l2': 'per-step saved activations (%.2f GB fp16 + fp32 residual) exceed the 126 MB L2; '
+                'the timed steps cycle over 4 resident batches' % (
+                    (c['depth'] * 2 + 4) * rows * c['width'] / 1e9)}
+
+
+def measure_tf32_peak(device, seconds=0.4):
+  """the tf32 tensor peak measured on the box -- torch.matmul (cuBLAS)
+  8192^3 with tf32 operands, best of 10 (burst) and a back-to-back loop (sustained)."""
+  try:
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    n = 8192
+    a = torch.randn(n, n, device=device)
+    b = torch.randn(n, n, device=device)
+    for _ in range(3):
+      a @ b
+    best = 1e9
+    for _ in range(10):
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record(); a @ b; e1.record(); torch.cuda.synchronize()
+      best = min(best, e0.elapsed_time(e1) * 1e-3)
+    reps = max(3, int(seconds / best))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+      a @ b
+    e1.record(); torch.cuda.synchronize()
+    sustained = e0.elapsed_time(e1) * 1e-3 / reps
+    torch.backends.cuda.matmul.allow_tf32 = prev
+    del a, b
+    return {'burst': 2.0 * n ** 3 / best / 1e12, 'sustained': 2.0 * n ** 3 / sustained / 1e12,
+            'how': 'torch.matmul fp32 inputs, allow_tf32, 8192^3: best of 10 / %d back to back' % reps}
+  except Exception as ex:   # noqa: BLE001
+    return {'burst': None, 'sustained': None, 'how': 'failed: %s' % str(ex)[:100]}
+
+
 def fwd_flops_per_row(c=CFG):
   d_in = c['obs_dim'] + c['act_dim']
   return 2 * (d_in * c['width'] + c['depth'] * c['width'] ** 2 + c['width'])
@@ -204,6 +246,10 @@ def run_b200(args):
   _lib.reset_launch_count()
   t_dev = max_over_ranks(timed(step_dev, args.steps, barrier))
   launches = _lib.launch_count()
+  # the same step for >= 0.4 s so that nvidia-smi (100 ms period) samples the clocks under
+  # load even when K is small (the driver passes --steps 20 = 15 ms)
+  sus_steps = max(args.steps, int(0.4 / max(t_dev / args.steps, 1e-5)))
+  t_sus = max_over_ranks(timed(step_dev, sus_steps, barrier))
   clocks = sampler.stop() if rank == 0 else None
 
   # end to end: pinned host buffers -> H2D -> step -> loss back on the host
@@ -240,11 +286,30 @@ def run_b200(args):
   finally:
     net.engine.set_profiling(False)
 
+  # the same step on the exact fp32 FMA path (IBC_PRECISION_FP32)
+  t_fp32 = None
+  try:
+    net.engine.set_precision(_lib.PRECISION_FP32)
+    for i in range(2):
+      step_dev(i)
+    t_fp32 = max_over_ranks(timed(step_dev, 5, barrier)) / 5
+  except Exception:   # noqa: BLE001
+    t_fp32 = None
+  finally:
+    net.engine.set_precision(_lib.PRECISION_TF32)
+
   # the fused tcgen05 energy forward timed alone on the step's rows
   obs_flat = net._flat_obs(dev_batches[0][0])
   acts = torch.rand(rows, c['act_dim'], device=device) * 2.2 - 1.1
   peaks = measured_peaks()
-  tf32_peak = peaks['bf16'] / 2.0
+  # (measured LAST -- a 0.4 s cuBLAS loop pulls the clocks down for whatever runs right after it
+  # -- and substituted into the roofline blocks below; see the end of this function)
+  tf32_meas = {'burst': None, 'sustained': None, 'how': ''}
+  # tensor roofline denominator: the tf32 cuBLAS figure measured here,
+  # else half the driver-measured bf16 burst (the nominal tf32 : bf16 ratio)
+  tf32_peak = tf32_meas['burst'] if tf32_meas.get('burst') else peaks['bf16'] / 2.0
+  tf32_peak_source = ('tf32 cuBLAS 8192^3 measured in this run' if tf32_meas.get('burst')
+                      else '%s bf16 burst / 2 (tf32 nominal ratio)' % peaks['source'])
   fwd = {}
   for prec, label in ((_lib.PRECISION_TF32, 'tf32'), (_lib.PRECISION_FP32, 'fp32')):
     try:
@@ -268,14 +333,27 @@ def run_b200(args):
   reps = 20
   t_act = timed(lambda i: policy.action(time_step), reps, lambda: None) / reps
 
-  # secondary configs (rank 0 only, short): Langevin chains of C3 / pushing_states-langevin
-  # and one late-fusion PixelEBM train step (C5), reported beside the headline
+  # batched policy inference sharded by observation (north_star): every rank
+  # evaluates 32 observations x 16384 candidates (DFO, 3 iterations) of a 32 * N batch and the
+  # actions are gathered (A floats per observation); weak scaling, no data-path collective
+  from ibc_b200 import parallel
+  obs_per_gpu = 32
+  big, _ = synthetic_batch(c, obs_per_gpu * world, 777, device=device)
+  big_ts = specs.restart(big)
+  for _ in range(2):
+    parallel.sharded_policy_action(policy, big_ts)
+  reps = 5
+  t_shard = max_over_ranks(timed(lambda i: parallel.sharded_policy_action(policy, big_ts), reps,
+                                 barrier)) / reps
+
+  # secondary configs: Langevin chains of C3 / pushing_states-langevin / C4, C1 training
+  # gradients and the PixelEBM paths on rank 0; the C3 / C4 train steps through
+  # ImplicitBCAgent.train on EVERY rank (they all-reduce their gradients)
   secondary = {}
-  if rank == 0:
-    try:
-      secondary = secondary_configs(device)
-    except Exception as ex:   # noqa: BLE001
-      secondary = {'error': str(ex)[:300]}
+  try:
+    secondary = secondary_configs(device, rank, world)
+  except Exception as ex:   # noqa: BLE001
+    secondary = {'error': str(ex)[:300]}
 
   result = None
   if rank == 0:
@@ -288,11 +366,21 @@ def run_b200(args):
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'tf32 (tcgen05 kind::tf32 operands, fp32 accumulate; first/last layer and loss in fp32)', 'data': 'synthetic',
-        'config': {'workload': c['name'], 'batch_per_gpu': b,
-                   'num_counter_examples': n, 'rows_per_step_per_gpu': rows, 'width': c['width'],
-                   'depth': c['depth'], 'l2': 'per-step activations (%.2f GB) exceed the 126 MB L2'
-                   % ((2 * c['depth'] // 2 + 1) * rows * c['width'] * 4 / 1e9)},
+        'config': workload_config(c),
         'train_steps_per_s': args.steps / t_dev,
+        'sustained': {'steps': sus_steps, 'ms_per_step': t_sus / sus_steps * 1e3,
+                      'value': rows * world * sus_steps / t_sus,
+                      'note': 'same step, long enough for the clock samples below'},
+        'fp32_exact_step': ({'ms_per_step': t_fp32 * 1e3, 'value': rows * world / t_fp32,
+                             'note': 'IBC_PRECISION_FP32: every contraction on fp32 FMA kernels'}
+                            if t_fp32 else None),
+        'tf32_tflops_measured': tf32_meas,
+        'inference_sharded': {'actions_per_s': obs_per_gpu * world / t_shard,
+                              'ms_per_batch': t_shard * 1e3, 'observations': obs_per_gpu * world,
+                              'observations_per_gpu': obs_per_gpu,
+                              'num_action_samples': c['dfo_samples'], 'iterations': c['dfo_iterations'],
+                              'collective': 'none on the data path; one all_gather of A floats per observation',
+                              'scaling': 'weak'},
         'e2e': {'value': evals / t_e2e, 'unit': 'energy evals/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': 4, 'ms_per_step': t_e2e / args.steps * 1e3,
                 'final_loss': losses[-1] if losses else None},
@@ -302,7 +390,7 @@ def run_b200(args):
         'roofline_step': {'kernel': 'whole train step (all kernels)', 'bound': 'tensor',
                           'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s',
                           'frac': achieved / tf32_peak, 'flops_per_step': step_flops,
-                          'peak_source': '%s bf16 burst / 2 (tf32 nominal ratio)' % peaks['source']},
+                          'peak_source': tf32_peak_source},
         'roofline_energy_fwd': None,
         'dfo_inference': {'actions_per_s': 1.0 / t_act, 'ms_per_action': t_act * 1e3,
                           'num_action_samples': c['dfo_samples'],
@@ -316,52 +404,49 @@ def run_b200(args):
       result['roofline_energy_fwd'] = {
           'kernel': 'mlp_fwd_tmem_kernel (tcgen05 kind::tf32, activations in tensor memory)', 'bound': 'tensor',
           'achieved': a, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': a / tf32_peak,
-          'traffic': None, 'ms_per_launch': fwd['tf32'] * 1e3, 'rows': rows,
+          'peak_source': tf32_peak_source,
+          'traffic': _ncu_traffic().get('forward_nosave'), 'ms_per_launch': fwd['tf32'] * 1e3, 'rows': rows,
           'fp32_path_ms': fwd['fp32'] * 1e3 if fwd.get('fp32') else None}
     else:
       result['roofline_energy_fwd'] = {k: v for k, v in fwd.items()}
     if kt is not None:
-      # dominant kernel of the step = the one with the largest measured share
-      wflops = 2.0 * c['depth'] * c['width'] ** 2 * rows     # one pass over the W x W layers
-      names = ['mlp_fwd_tmem_kernel<save> (fused forward, operands + ReLU masks saved)',
+      # dominant kernel of the step = the one with the largest measured share.  Algorithmic
+      # work per launch: the fused forward = rows x fwd FLOPs; the
+      # block-major backward = backward-data + backward-weights = 2 x rows x fwd FLOPs
+      # (SURVEY.md 8d canonical count).  Algorithmic HBM bytes: the forward writes, and the
+      # backward reads, D fp16 operand tiles + the fp32 final residual + D mask bit-planes per
+      # row; the backward also writes g0 (fp32) -- its parked gradients are L2 traffic.
+      fflops = rows * fwd_flops_per_row()
+      names = ['mlp_fwd_tmem_kernel<2> (fused forward, fp16 operand tiles + ReLU masks saved)',
                'info_nce_kernel',
-               'mlp_bwd_tmem_kernel (fused reverse chain, output gradients saved)',
-               'mlp_wgrad_umma_kernel (dW GEMM over the saved tiles)',
-               'first/last-layer fp32 kernels']
-      flops = [rows * fwd_flops_per_row(), 0.0, wflops, wflops, 0.0]
-      # algorithmic HBM bytes per launch (DESIGN.md "bytes per unit"): one fp32 tile
-      # = rows * W * 4 B; masks = rows * W / 8 B per layer
-      tile_bytes = rows * c['width'] * 4.0
+               'mlp_bwd_wgrad_tmem_kernel (block-major reverse chain + weight gradients)',
+               '(weight gradients: inside the backward kernel)',
+               'first-layer fp32 kernels']
+      flops = [fflops, 0.0, 2.0 * fflops, 0.0, 0.0]
+      tile16 = rows * c['width'] * 2.0
+      tile32 = rows * c['width'] * 4.0
       mask_bytes = rows * c['width'] / 8.0
-      hbm = [(c['depth'] + 1) * tile_bytes + c['depth'] * mask_bytes,          # fwd: writes
-             0.0,
-             (c['depth'] + 1) * tile_bytes + tile_bytes + c['depth'] * mask_bytes,  # rev: GY + g0 out, h_nb + masks in
-             2 * c['depth'] * tile_bytes,                                      # wgrad: reads
-             0.0]
+      saved = c['depth'] * (tile16 + mask_bytes) + tile32
+      hbm = [saved, 0.0, saved + tile32, 0.0, tile32]
       top = int(np.argmax(kt))
-      keys = ['forward', 'info_nce', 'reverse', 'wgrad', 'first_last']
+      keys = ['forward', 'info_nce', 'backward', 'wgrad', 'first_layer']
       result['kernel_ms'] = dict(zip(keys, kt))
       traffic = _ncu_traffic().get(keys[top])
       tfl = flops[top] / (kt[top] * 1e-3) / 1e12 if flops[top] else 0.0
       gbs = hbm[top] / (kt[top] * 1e-3) / 1e9
-      frac_t, frac_h = tfl / tf32_peak, gbs / peaks['hbm']
-      if frac_h >= frac_t:
-        result['roofline'] = {
-            'kernel': names[top], 'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm'],
-            'unit': 'GB/s', 'frac': frac_h, 'traffic': traffic,
-            'ms_per_launch': kt[top], 'share_of_step': kt[top] / sum(kt),
-            'algorithmic_bytes_per_launch': hbm[top],
-            'tensor_TFLOPs': tfl, 'tensor_frac_of_measured': frac_t,
-            'peak_source': '%s copy bandwidth (MEASURED_PEAKS.json hbm_gbs)' % peaks['source']}
-      else:
-        result['roofline'] = {
-            'kernel': names[top], 'bound': 'tensor', 'achieved': tfl, 'peak': tf32_peak,
-            'unit': 'TFLOP/s', 'frac': frac_t, 'traffic': traffic,
-            'ms_per_launch': kt[top], 'share_of_step': kt[top] / sum(kt),
-            'hbm_algorithmic_GBs': gbs, 'hbm_frac_of_measured': frac_h,
-            'peak_source': '%s bf16 burst / 2 (tf32 nominal ratio)' % peaks['source']}
+      result['roofline'] = {
+          'kernel': names[top], 'bound': 'tensor', 'achieved': tfl, 'peak': tf32_peak,
+          'unit': 'TFLOP/s', 'frac': tfl / tf32_peak, 'traffic': traffic,
+          'ms_per_launch': kt[top], 'share_of_step': kt[top] / sum(kt),
+          'algorithmic_flops_per_launch': flops[top],
+          'hbm_algorithmic_GBs': gbs, 'hbm_frac_of_measured': gbs / peaks['hbm'],
+          'algorithmic_bytes_per_launch': hbm[top],
+          'peak_source': tf32_peak_source,
+          'note': 'chain MMAs kind::tf32, weight-gradient MMAs kind::f16 (same 10-bit mantissa); '
+                  'both counted against the tf32 peak'}
       result['roofline_kernels'] = [
           {'kernel': names[i], 'ms': kt[i], 'tflops': flops[i] / (kt[i] * 1e-3) / 1e12 if flops[i] else None,
+           'frac_of_tf32_peak': (flops[i] / (kt[i] * 1e-3) / 1e12 / tf32_peak) if flops[i] else None,
            'hbm_GBs': hbm[i] / (kt[i] * 1e-3) / 1e9 if hbm[i] else None} for i in range(5)]
     else:
       result['roofline'] = dict(result['roofline_step'])
@@ -371,6 +456,23 @@ def run_b200(args):
       # rank 0 at N = 1 only: with more ranks the others spin in the closing barrier on the
       # same host cores and the figure means nothing (63 k instead of 300 k evals/s at N = 8)
       result['cpu_baseline'] = cpu_baseline(steps=2, warmup=1)
+      try:
+        result['cpu_baselines_secondary'] = cpu_baselines_secondary()
+      except Exception as ex:   # noqa: BLE001
+        result['cpu_baselines_secondary'] = {'error': str(ex)[:200]}
+  if rank == 0 and result is not None:
+    tf32_meas = measure_tf32_peak(device)
+    result['tf32_tflops_measured'] = tf32_meas
+    if tf32_meas.get('burst'):
+      pk = tf32_meas['burst']
+      src = 'tf32 cuBLAS 8192^3 measured at the end of this run'
+      for key in ('roofline', 'roofline_step', 'roofline_energy_fwd'):
+        blk = result.get(key)
+        if isinstance(blk, dict) and blk.get('unit') == 'TFLOP/s' and blk.get('achieved') is not None:
+          blk['peak'], blk['frac'], blk['peak_source'] = pk, blk['achieved'] / pk, src
+      for blk in result.get('roofline_kernels') or []:
+        if blk.get('tflops'):
+          blk['frac_of_tf32_peak'] = blk['tflops'] / pk
   if world > 1:
     dist.barrier()
     dist.destroy_process_group()
@@ -379,8 +481,9 @@ def run_b200(args):
 
 def _ncu_traffic():
   """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step's kernels,
-  from the committed `ncu --set full` capture (profiles/r1_dram_traffic.json)."""
-  path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_dram_traffic.json')
+  from this round's committed `ncu --set full` capture of the same step
+  (profiles/r2_dram_traffic.json, written by scripts/ncu_summary.py)."""
+  path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r2_dram_traffic.json')
   try:
     with open(path) as f:
       return json.load(f)
@@ -388,12 +491,70 @@ def _ncu_traffic():
     return {}
 
 
-def secondary_configs(device):
+def secondary_configs(device, rank=0, world=1):
   """Langevin sampler throughput (C3: particle 32-D, W=256 D=2, obs 256, act 32, B*N=4096,
   K=100; pushing_states/mlp_ebm_langevin.gin: W=128 D=16, B*N=4096, K=100) and a PixelEBM
   train step (C5 shapes, B=32 of 128 frames pairs)."""
   from ibc_b200 import engine as eng
   out = {}
+  # Full train steps of the Langevin configs through ImplicitBCAgent.train (the reference's
+  # call): uniform seeds -> 100-step Langevin chain on B*N = 4096 rows -> InfoNCE + gradient
+  # penalty forward / second-order backward on B*(N+1) rows -> Adam (SURVEY.md 8d: energy
+  # evals per step = K*B*N + 2*B*(N+1))
+  from ibc_b200 import gin_lite as gin
+  from ibc_b200.ibc import specs
+  from ibc_b200.ibc.agents import ibc_agent
+  from ibc_b200.ibc.train import get_agent
+  from ibc_b200.networks.mlp_ebm import MLPEBM
+  import torch.distributed as dist
+  # These run on EVERY rank: ImplicitBCAgent.train all-reduces its gradients (weak scaling,
+  # per-replica batch 512); the time is the max over ranks.  Everything after them runs on
+  # rank 0 only, and the single-process agent steps (PixelEBM) only without a process group.
+  solo = world == 1
+
+  def max_ranks(x):
+    if world == 1:
+      return x
+    t_ = torch.tensor([x], device=device, dtype=torch.float64)
+    dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+    return float(t_.item())
+
+  for name, (o, a, w, d), extra in (
+      ('C3_particle32_train_step', (256, 32, 256, 2), ''),
+      ('C4_d4rl_door_train_step', (39, 28, 512, 8),
+       'langevin_actions_given_obs.sampler_stepsize_init = 0.5\n'
+       'langevin_actions_given_obs.delta_action_clip = 0.5\n'
+       'langevin_actions_given_obs.noise_scale = 0.5\n')):
+    gin.clear_config()
+    gin.parse_config('langevin_actions_given_obs.num_iterations = 100\n' + extra)
+    try:
+      b, n, k = 512, 8, 100
+      obs_spec = {'obs': specs.TensorSpec((1, o))}
+      act_spec = specs.BoundedTensorSpec((a,), minimum=-1.0, maximum=1.0)
+      samp = specs.BoundedTensorSpec((a,), minimum=-1.1, maximum=1.1)
+      net = MLPEBM((obs_spec, act_spec), specs.TensorSpec((1,)), width=w, depth=d, rate=0.0,
+                   layers='ResNetPreActivation', seed=1)
+      opt = get_agent.Adam(get_agent.ExponentialDecay(1e-3, 100, 0.99))
+      agent = ibc_agent.ImplicitBCAgent(obs_spec, act_spec, samp, net, opt, num_counter_examples=n,
+                                        fraction_langevin_samples=1.0, add_grad_penalty=True,
+                                        run_full_chain_under_gradient=True)
+      g = torch.Generator().manual_seed(rank)
+      exp = (({'obs': torch.randn(b, 1, o, generator=g).to(device)},
+              (torch.rand(b, a, generator=g) * 2 - 1).to(device)), ())
+      for _ in range(3):
+        agent.train(exp)
+      t = max_ranks(timed(lambda i: agent.train(exp), 5, lambda: None) / 5)
+      evals = (k * b * n + 2 * b * (n + 1)) * world
+      fwd = 2.0 * ((o + a) * w + d * w * w + w)
+      flops = (k * b * n * 2 + b * (n + 1) * 7) * fwd * world
+      out[name] = {'ms_per_step': t * 1e3, 'batch': b, 'num_counter_examples': n,
+                   'langevin_iterations': k, 'energy_evals_per_s': evals / t,
+                   'tflops': flops / t * 1e-12, 'n_gpus': world, 'precision': 'tf32',
+                   'kernel_status': net.engine.kernel_status()}
+    finally:
+      gin.clear_config()
+  if rank != 0:
+    return out
   for name, (o, a, w, d) in (('C3_particle32_langevin', (256, 32, 256, 2)),
                              ('pushing_states_langevin', (20, 2, 128, 16)),
                              ('C4_d4rl_door_langevin', (39, 28, 512, 8))):
@@ -432,53 +593,6 @@ def secondary_configs(device):
                 'tflops': 3.0 * b * (n + 1) * fwd / t * 1e-12,
                 'precision': 'tf32' if prec == _l.PRECISION_TF32 else 'fp32',
                 'kernel_status': e.kernel_status()}
-  # Full train steps of the Langevin configs through ImplicitBCAgent.train (the reference's
-  # call): uniform seeds -> 100-step Langevin chain on B*N = 4096 rows -> InfoNCE + gradient
-  # penalty forward / second-order backward on B*(N+1) rows -> Adam (energy
-  # evals per step = K*B*N + 2*B*(N+1))
-  from ibc_b200 import gin_lite as gin
-  from ibc_b200.ibc import specs
-  from ibc_b200.ibc.agents import ibc_agent
-  from ibc_b200.ibc.train import get_agent
-  from ibc_b200.networks.mlp_ebm import MLPEBM
-  import torch.distributed as dist
-  # (single-process runs only: with a process group up, ImplicitBCAgent.train all-reduces its
-  # gradients and rank 0 alone would wait for the other ranks forever)
-  solo = not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
-  for name, (o, a, w, d), extra in (() if not solo else (
-      ('C3_particle32_train_step', (256, 32, 256, 2), ''),
-      ('C4_d4rl_door_train_step', (39, 28, 512, 8),
-       'langevin_actions_given_obs.sampler_stepsize_init = 0.5\n'
-       'langevin_actions_given_obs.delta_action_clip = 0.5\n'
-       'langevin_actions_given_obs.noise_scale = 0.5\n'))):
-    gin.clear_config()
-    gin.parse_config('langevin_actions_given_obs.num_iterations = 100\n' + extra)
-    try:
-      b, n, k = 512, 8, 100
-      obs_spec = {'obs': specs.TensorSpec((1, o))}
-      act_spec = specs.BoundedTensorSpec((a,), minimum=-1.0, maximum=1.0)
-      samp = specs.BoundedTensorSpec((a,), minimum=-1.1, maximum=1.1)
-      net = MLPEBM((obs_spec, act_spec), specs.TensorSpec((1,)), width=w, depth=d, rate=0.0,
-                   layers='ResNetPreActivation', seed=1)
-      opt = get_agent.Adam(get_agent.ExponentialDecay(1e-3, 100, 0.99))
-      agent = ibc_agent.ImplicitBCAgent(obs_spec, act_spec, samp, net, opt, num_counter_examples=n,
-                                        fraction_langevin_samples=1.0, add_grad_penalty=True,
-                                        run_full_chain_under_gradient=True)
-      g = torch.Generator().manual_seed(0)
-      exp = (({'obs': torch.randn(b, 1, o, generator=g).to(device)},
-              (torch.rand(b, a, generator=g) * 2 - 1).to(device)), ())
-      for _ in range(3):
-        agent.train(exp)
-      t = timed(lambda i: agent.train(exp), 5, lambda: None) / 5
-      evals = k * b * n + 2 * b * (n + 1)
-      fwd = 2.0 * ((o + a) * w + d * w * w + w)
-      flops = (k * b * n * 2 + b * (n + 1) * 7) * fwd
-      out[name] = {'ms_per_step': t * 1e3, 'batch': b, 'num_counter_examples': n,
-                   'langevin_iterations': k, 'energy_evals_per_s': evals / t,
-                   'tflops': flops / t * 1e-12, 'precision': 'tf32',
-                   'kernel_status': net.engine.kernel_status()}
-    finally:
-      gin.clear_config()
   # C5 PixelEBM (pushing_pixels/pixel_ebm_best.gin shapes): late-fusion train step at the
   # gin's batch 128 with 256 counter-examples, tf32 tensor-core path and the fp32 path
   from ibc_b200 import _lib
@@ -629,6 +743,76 @@ def cpu_baseline(steps, warmup, batch=512):
           'seconds_per_step': t}
 
 
+def cpu_baselines_secondary():
+  """the oracle (CPU restatement) beside C1, C3, C4 and C5 too, each
+  on a bounded sample (reduced batch and, for the Langevin configs, reduced K: the cost of a
+  chain is linear in K), all host cores, one warm-up + one timed step.  value = energy
+  evaluations per second of the sample (SURVEY.md 8d count: B (N+1) for the DFO-style steps,
+  K B N + 2 B (N+1) for the Langevin-style ones)."""
+  from oracle import agent as oagent
+  from oracle import mlp_ebm as omlp
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  out = {}
+  cases = (
+      ('C1_particle2d_train_step', omlp.MLPSpec(16, 2, 256, 2), 512, 256, 0, False, {}),
+      ('C3_particle32_train_step', omlp.MLPSpec(256, 32, 256, 2), 512, 8, 50, True, {}),
+      ('C4_d4rl_door_train_step', omlp.MLPSpec(39, 28, 512, 8), 128, 8, 20, True,
+       dict(langevin_stepsize_init=0.5, langevin_delta_action_clip=0.5, langevin_noise_scale=0.5)),
+  )
+  for name, spec, b, n, k, gp, extra in cases:
+    flat = omlp.init_params(spec, seed=1)
+    state = oagent.adam_init(flat)
+    cfg = oagent.AgentConfig(num_counter_examples=n, fraction_langevin_samples=1.0 if k else 0.0,
+                             add_grad_penalty=gp, langevin_num_iterations=max(k, 1), **extra)
+    mn, mx = torch.full((spec.act_dim,), -1.1), torch.full((spec.act_dim,), 1.1)
+    g = torch.Generator().manual_seed(0)
+
+    def make_energy_fn(theta, spec=spec):
+      return lambda obs_t, a: omlp.energy(theta, spec, obs_t, a)
+
+    t = None
+    for it in range(2):
+      obs = torch.randn(b, spec.obs_dim, generator=g)
+      act = torch.rand(b, spec.act_dim, generator=g) * 2 - 1
+      u = torch.rand(b, n, spec.act_dim, generator=g)
+      draws = {'langevin_normals': torch.randn(k, b * n, spec.act_dim, generator=g)} if k else {}
+      t0 = time.perf_counter()
+      flat, _, _, _ = oagent.train_step(make_energy_fn, flat, state, cfg, obs, act, mn, mx, u, 1e-3,
+                                        **draws)
+      t = time.perf_counter() - t0
+    evals = (k * b * n + 2 * b * (n + 1)) if k else b * (n + 1)
+    out[name] = {'value': evals / t, 'unit': 'energy evals/s', 'cores': cores, 'kind': 'port',
+                 'sample': 'oracle train step, batch %d of 512, N=%d, %s, %.2f s' % (
+                     b, n, ('Langevin K=%d of 100 + gradient penalty' % k) if k else 'uniform negatives', t)}
+  # C5: PixelEBM late-fusion forward + backward of the InfoNCE loss on 2 of 128 frame pairs
+  try:
+    from oracle import losses as olosses
+    from oracle import pixel_ebm as opix
+    spec = opix.PixelSpec() if hasattr(opix, 'PixelSpec') else None
+    if spec is not None:
+      flat = opix.init_params(spec, seed=1)
+      b, n = 16, 256
+      g = torch.Generator().manual_seed(0)
+      img = torch.randint(0, 256, (b, spec.seq_len, spec.height, spec.width, spec.channels), generator=g,
+                          dtype=torch.uint8)
+      act = torch.rand(b * (n + 1), spec.act_dim, generator=g) * 2 - 1
+      t = None
+      for it in range(2):
+        theta = flat.clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        e = opix.energy(theta, spec, img, act).reshape(b, n + 1)
+        per = olosses.info_nce(e, b, n, 1.0)
+        torch.autograd.grad(per.sum() / b, theta)
+        t = time.perf_counter() - t0
+      out['C5_pixel_ebm_train_grads'] = {
+          'value': b * (n + 1) / t, 'images_per_s': b / t, 'unit': 'energy evals/s', 'cores': cores,
+          'kind': 'port', 'sample': 'oracle PixelEBM loss + backward on %d of 128 frame pairs, N=256, %.2f s' % (b, t)}
+  except Exception as ex:   # noqa: BLE001
+    out['C5_pixel_ebm_train_grads'] = {'error': str(ex)[:160]}
+  return out
+
+
 def run_reference(args):
   """--impl reference: the reference's CPU implementation of the path.  The TF
   reference cannot be installed offline (no tensorflow / tf-agents wheels), so
@@ -651,9 +835,7 @@ def run_reference(args):
       'unit': 'energy evals/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
       'ms_per_step': base['seconds_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': {'workload': c['name'], 'batch_per_gpu': c['batch'],
-                 'num_counter_examples': c['num_counter_examples'], 'width': c['width'],
-                 'depth': c['depth']},
+      'config': workload_config(c),
       'cpu_baseline': base,
       'e2e': {'value': base['value'], 'unit': 'energy evals/s', 'h2d_bytes_per_step': 0,
               'd2h_bytes_per_step': 0},
