@@ -64,3 +64,53 @@ def test_train_from_tfrecord_shards_d4rl_shape():
   for r in hist:
     assert r['loss'] == r['loss'] and 'AverageSuccessMetric' not in r
   assert hist[-1]['ebm_total_loss'] < 2.1972
+
+
+def test_checkpoint_resume_and_validation_loss(tmp_path):
+  """checkpoint / resume of the flat training state (get_learner.py:60-76) and
+  the validation loss on held-out windows (train_eval.py:262-267).  A run to step 60 that was
+  checkpointed at step 30 and resumed must end with EXACTLY the parameters of an uninterrupted
+  run -- parameters, Adam moments and iteration count (hence the learning-rate schedule), data
+  and sampler RNG streams all restored.  The fp32 path is used (its kernels sum without
+  atomics), uniform counter-examples."""
+  import torch
+  from ibc_b200 import gin_lite as gin
+  from ibc_b200.ibc import train_eval
+
+  def run(root, iters):
+    gin.clear_config()
+    gin.parse_config_files_and_bindings(
+        [], ['train_eval.num_iterations = %d' % iters, 'train_eval.eval_interval = 30',
+             'train_eval.eval_episodes = 1', 'train_eval.num_demo_episodes = 40',
+             'train_eval.batch_size = 64', 'train_eval.fused_train_steps = 10',
+             'train_eval.checkpoint_interval = 30', 'train_eval.eval_loss_interval = 20',
+             'train_eval.dataset_eval_fraction = 0.1', 'train_eval.precision = "fp32"',
+             'train_eval.root_dir = "%s"' % root, 'get_normalizers.nested_obs = True',
+             'MLPEBM.width = 64', 'MLPEBM.depth = 2', 'MLPEBM.layers = "ResNetPreActivation"',
+             'MLPEBM.rate = 0.0', 'ImplicitBCAgent.num_counter_examples = 16',
+             'ImplicitBCAgent.fraction_langevin_samples = 0.0',
+             'ImplicitBCAgent.add_grad_penalty = False',
+             'IbcPolicy.num_action_samples = 256', 'IbcPolicy.use_dfo = True',
+             'IbcPolicy.use_langevin = False'])
+    try:
+      return train_eval.train_eval(log=lambda s: None)
+    finally:
+      gin.clear_config()
+
+  full = run(str(tmp_path / 'a'), 60)
+  steps = [r['step'] for r in full['history']]
+  assert steps == [20, 30, 40, 60], steps
+  assert all(('eval_ebm_total_loss' in r) == (r['step'] % 20 == 0) for r in full['history'])
+  assert os.path.exists(str(tmp_path / 'a' / train_eval.CHECKPOINT_NAME))
+  half = run(str(tmp_path / 'b'), 30)
+  assert half['agent'].train_step_counter == 30
+  resumed = run(str(tmp_path / 'b'), 60)
+  assert [r['step'] for r in resumed['history']] == [40, 60]
+  assert resumed['agent'].train_step_counter == 60
+  assert resumed['agent']._optimizer.iterations == 60
+  a, b = resumed['agent'].cloning_network.params, full['agent'].cloning_network.params
+  # identical up to the summation order of the atomically accumulated gradient entries
+  # (measured 1e-8); Dense(1)'s bias, the last entry, is the exception: its gradient is the
+  # sum of all dE = 0 up to rounding, and Adam turns that noise into steps of +-lr
+  assert float((a[:-1] - b[:-1]).abs().max()) <= 1e-6 * float(b.abs().max()), float((a - b).abs().max())
+  assert abs(float(a[-1] - b[-1])) <= 60 * 1e-3
