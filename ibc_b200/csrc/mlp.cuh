@@ -80,6 +80,13 @@ int langevin_fused(ibc_handle* h, const float* hp, int64_t B, float* actions, in
                    const float* normals, uint64_t seed, const uint64_t* seed_ptr,
                    const float* steps_dev, float* chain_actions, float* chain_energies,
                    float* chain_grad_norms, cudaStream_t s);
+// the same for width 256, depth 2 (langevin256.cu); cvec: W + 1 floats of scratch
+bool langevin256_supported(const Layout& L);
+int langevin256_fused(ibc_handle* h, const float* hp, int64_t B, float* actions, int64_t n,
+                      const float* mn, const float* mx, const ibc_langevin_cfg& c,
+                      const float* normals, uint64_t seed, const uint64_t* seed_ptr,
+                      const float* steps_dev, float* cvec, float* chain_actions,
+                      float* chain_energies, float* chain_grad_norms, cudaStream_t s);
 // width-128 kernels with the activations in tensor memory (mlp_umma_tmem.cu); tile
 // ids and the saved-tile layouts are the same as the shared-memory-operand kernels'
 bool tmem_path_supported(const Layout& L);

@@ -852,6 +852,20 @@ int langevin_umma(ibc_handle* h, const float* obs, int64_t B, float* actions, in
     return langevin_fused(h, hp, B, actions, n, mn, mx, c, normals, seed, nullptr, steps_dev,
                           chain_actions, chain_energies, chain_grad_norms, s);
   }
+  if (!no_fused && K > 0 && !c.apply_exp && langevin256_supported(L)) {
+    // width 256, depth 2 (C1 / C3): the whole chain in one persistent kernel (langevin256.cu)
+    h->ws.reset();
+    float* hp = h->ws.take<float>((size_t)B * L.W);
+    float* steps_dev = h->ws.take<float>((size_t)K);
+    float* cvec = h->ws.take<float>((size_t)L.W + 4);
+    GemmP g;   // hp = obs . Wp[:O] + bp, once per chain
+    g.A = obs; g.lda = L.O; g.B = h->params + L.wp; g.ldb = L.W; g.C = hp; g.ldc = L.W;
+    g.bias = h->params + L.bp; g.M = (int)B; g.N = L.W; g.K = L.O;
+    IBC_TRY(gemm(h, g, false, false, s));
+    IBC_CUDA(h, cudaMemcpyAsync(steps_dev, steps.data(), (size_t)K * 4, cudaMemcpyHostToDevice, s));
+    return langevin256_fused(h, hp, B, actions, n, mn, mx, c, normals, seed, nullptr, steps_dev, cvec,
+                             chain_actions, chain_energies, chain_grad_norms, s);
+  }
   if (normals || !chain_graphs_enabled() || K < 4)
     return langevin_chain(h, obs, B, actions, n, mn, mx, c, normals, seed, nullptr, steps,
                           chain_actions, chain_energies, chain_grad_norms, s);

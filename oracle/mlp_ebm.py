@@ -167,8 +167,12 @@ def init_sn_u(spec: MLPSpec, seed: int = 3, dtype=torch.float32):
 
 
 def sn_effective_params(flat_raw: torch.Tensor, us, spec: MLPSpec):
-  """Flat vector with every kernel replaced by W_bar; also the updated u's
-  (only written back by the caller when training=True, spectral_norm.py:76-80).
+  """Flat vector with every kernel replaced by W_bar; also the u's after a training call
+  (only written back by the caller when training=True, spectral_norm.py:76-80).  The first
+  layer is the exception: ResNetPreActivationLayer.call invokes `self._projection_layer(x)`
+  WITHOUT `training=` (networks/layers/resnet.py:136), DenseSN.call then sees training=None
+  and never assigns u (spectral_norm.py:76), so Wp keeps its initial u for the whole run
+  while still being normalised with it: new_us['Wp'] is the u that was passed in.
   """
   p = unpack(flat_raw, spec)
   pieces = []
@@ -178,7 +182,7 @@ def sn_effective_params(flat_raw: torch.Tensor, us, spec: MLPSpec):
     if name in us:
       w2d = t.view(-1, 1) if name == 'we' else t
       wbar, un = spectral_normalize(w2d, us[name])
-      new_us[name] = un.detach()
+      new_us[name] = us[name].detach() if name == 'Wp' else un.detach()
       t = wbar.reshape(shape)
     pieces.append(t.reshape(-1))
   return torch.cat(pieces), new_us

@@ -343,8 +343,9 @@ def test_spectral_norm_network_matches_oracle():
   assert abs(float(info.loss) - float(total)) < 1e-5
   rel = float((grads.cpu() - want_grad).norm() / want_grad.norm())
   assert rel < 1e-4, rel
-  for k in new_us:                                   # u <- u' because training=True
-    assert torch.allclose(net._sn_u[k].cpu(), new_us[k], atol=1e-6)
+  for k in new_us:                # u <- u' because training=True; Wp keeps its u (resnet.py:136)
+    assert torch.allclose(net._sn_u[k].cpu(), new_us[k], atol=1e-6), k
+  assert torch.equal(net._sn_u['Wp'].cpu(), us['Wp'])
 
 # ------------------------------ tf32 vs fp32 training curves --------------------------------
 def test_c2_training_curves_tf32_tracks_fp32():
