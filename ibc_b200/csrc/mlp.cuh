@@ -95,6 +95,10 @@ int tmem_forward(ibc_handle* h, const float* act, int64_t R, int64_t n, const fl
 int tmem_forward_f16(ibc_handle* h, const float* act, int64_t R, int64_t n, const float* hp, float* E,
                      float* xa_save, void* xa16, float* hn_save, uint32_t* mask_save,
                      cudaStream_t s);
+// energies only (xa16 == null) or the fp16-saving forward, eight epilogue warps per tile
+// (mlp_fwd_halves.cu)
+int tmem_forward_halves(ibc_handle* h, const float* act, int64_t R, int64_t n, const float* hp,
+                        float* E, void* xa16, float* hn_save, uint32_t* mask_save, cudaStream_t s);
 int tmem_reverse(ibc_handle* h, const float* dE, int64_t R, const float* xa_save,
                  const uint32_t* mask_save, float* gy_save, float* g0, float* dwe,
                  cudaStream_t s);

@@ -32,6 +32,7 @@
 #include <vector>
 
 #include "mlp.cuh"
+#include "mlp_tiling.cuh"
 #include "umma.cuh"
 #include "umma_f16.cuh"
 #include "umma_pack.cuh"
@@ -70,39 +71,6 @@ inline size_t smem_bytes(bool forward, int KP) {
   const size_t tail = forward ? (size_t)KP * kW * 4 + 4096 + (kW + 4) * 4
                               : 2 * (size_t)kW * 4 + (size_t)4 * kNT * kStageBytes;
   return ring + tail + (size_t)(2 * kNT + 2 * kRing + 1) * 8 + 64;
-}
-
-// Work items of one CTA: `rounds` full rounds in which every CTA takes two
-// consecutive 128-row tiles, then one tail round.  When no more than gridDim.x
-// tiles are left the tail hands them out one per CTA (a lone tile runs without
-// MMA/epilogue overlap, but every SM gets one, instead of half the SMs getting
-// two: 131 584 rows = 1028 tiles over 148 SMs are 7 tiles per SM rather than 8).
-struct Tiling {
-  int64_t tiles;      // ceil(R / 128)
-  int rounds;         // full two-tile rounds
-  int tail_single;    // tail round: one tile per CTA
-};
-
-inline Tiling make_tiling(int64_t R, int grid) {
-  Tiling w;
-  w.tiles = (R + 127) / 128;
-  w.rounds = (int)(w.tiles / (2 * (int64_t)grid));
-  const int64_t rem = w.tiles - (int64_t)w.rounds * 2 * grid;
-  w.tail_single = rem <= grid ? 1 : 0;
-  return w;
-}
-
-// item k of this CTA -> first tile and tile count (0 = no more work)
-__device__ __forceinline__ int work_item(const Tiling& w, int k, int64_t& tile0) {
-  if (k < w.rounds) {
-    tile0 = ((int64_t)k * gridDim.x + blockIdx.x) * 2;
-    return 2;
-  }
-  if (k > w.rounds) return 0;
-  const int64_t base = (int64_t)w.rounds * 2 * gridDim.x;
-  tile0 = base + (w.tail_single ? (int64_t)blockIdx.x : 2 * (int64_t)blockIdx.x);
-  const int64_t left = w.tiles - tile0;
-  return left <= 0 ? 0 : (w.tail_single ? 1 : (left < 2 ? 1 : 2));
 }
 
 // Tensor-pipe token.  Two issuer threads sharing the pipe 1:1 finish their layers
@@ -262,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tmem_kernel(FwdTmemParams
           uint32_t mb[W / 32];
           float e = 0.f;
           auto chunk = [&](int c32, uint32_t (&v)[32]) {
-            uint32_t nbits = 0;     // bit (31 - q) = NOT (operand q > 0)
+            uint32_t nbits = 0;     // bit (31 - q) = operand q > 0
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
               uint32_t xb = v[q];
@@ -273,15 +241,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tmem_kernel(FwdTmemParams
                 if (kLast) e = fmaf(x, we[c32 * 32 + q], e);
               }
               if (!kLast) {
-                // relu + round in one VIADDMNMX; o > 0x1000 <=> x > 0 exactly, so the
-                // mask bit is the sign of o - 0x1001, shifted in with one funnel shift
-                const uint32_t o = relu_tf32_bits(xb);
-                if (kSave) nbits = __funnelshift_l(o - 0x1001u, nbits, 1);
-                xb = o;
+                // relu + round in one VIADDMNMX.  The epilogue is bound by the ALU pipe (integer
+                // add / min-max / shift issue every other cycle per scheduler), so the mask bit
+                // comes from the FMA pipe: the sign of 0 - x is set exactly when x > 0 (+0 - (+-0)
+                // = +0), shifted in with one funnel shift.
+                if (kSave) nbits = __funnelshift_l(__float_as_uint(__fsub_rn(0.f, __uint_as_float(xb))), nbits, 1);
+                xb = relu_tf32_bits(xb);
               }
               v[q] = xb;
             }
-            if (kSave && !kLast) mb[c32] = ~__brev(nbits);
+            if (kSave && !kLast) mb[c32] = __brev(nbits);
             if (!kLast) tmem_st32(col_a + c32 * 32, v);
             if (g_slot) {
 #pragma unroll
@@ -779,6 +748,11 @@ int tmem_forward_f16(ibc_handle* h, const float* act, int64_t R, int64_t n, cons
   const bool saving = xa_save || mask_save;
   if (xa16 && (!hn_save || !mask_save || xa_save))
     IBC_FAIL(h, IBC_ERR_INVALID, "tmem_forward_f16: fp16 tiles come with hn_save and mask_save only");
+  // energies only and the fp16-saving forward: eight epilogue warps per tile (mlp_fwd_halves.cu);
+  // IBC_FWD_ROWS=1 keeps this file's one-thread-per-row kernel for comparison
+  static const bool rows = getenv("IBC_FWD_ROWS") != nullptr;
+  if (!rows && !xa_save && (xa16 || !mask_save))
+    return tmem_forward_halves(h, act, R, n, hp, E, xa16, hn_save, mask_save, s);
   FwdTmemParams p;
   p.act = act; p.hp = hp; p.packed = h->packed; p.E = E; p.xa_save = xa_save;
   p.xa16 = reinterpret_cast<uint4*>(xa16); p.hn_save = hn_save;

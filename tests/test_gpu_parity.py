@@ -667,7 +667,11 @@ def test_train_grads_block_major_backward_matches_the_split_kernels(spec, b, n, 
   per_b, _, en_b, g_b = e.train_grads(obs_d, act_d, n, cfg, b, want_energies=True)
   g_b = g_b.double().cpu().clone()
   assert e.kernel_status() == 0
-  assert torch.equal(en_a, en_b) and torch.equal(per_a, per_b)
+  # the two forwards (eight epilogue warps per tile / one thread per row) run the same MMAs and
+  # differ in the order of the 128-term fp32 sum of Dense(1)
+  espan = float(en_b.abs().max())
+  assert float((en_a - en_b).abs().max()) <= 4e-6 * espan
+  assert float((per_a - per_b).abs().max()) <= 1e-5 * max(1.0, float(per_b.abs().max()))
   _close(en_a, en_f, 4 * TF32_TOL, 'energies')
   assert bool(torch.isfinite(g_a).all())
   grms = float(g_f.pow(2).mean().sqrt())

@@ -109,11 +109,14 @@ def test_checkpoint_resume_and_validation_loss(tmp_path):
   assert resumed['agent'].train_step_counter == 60
   assert resumed['agent']._optimizer.iterations == 60
   a, b = resumed['agent'].cloning_network.params, full['agent'].cloning_network.params
-  # identical up to the summation order of the atomically accumulated gradient entries
-  # (measured 1e-8); Dense(1)'s bias, the last entry, is the exception: its gradient is the
-  # sum of all dE = 0 up to rounding, and Adam turns that noise into steps of +-lr
-  # (so does the top block's b2 = (sum dE) x we: a handful of entries off by a few 1e-5)
+  # Identical up to the summation order of the atomically accumulated gradient entries, which
+  # differs from run to run (alone in a process the two runs happened to agree to 1e-8; behind
+  # the rest of the suite the median difference was 3e-7).  Adam turns that rounding noise into
+  # steps of +-lr on entries whose gradient is pure noise: Dense(1)'s bias, the last entry
+  # (its gradient is the sum of all dE = 0), and the top block's b2 = (sum dE) x we.  A resume
+  # that lost the moments, the step count or an RNG stream trains on for 30 steps of lr = 1e-3
+  # from a different state: differences of 1e-3 .. 1e-2 on most entries.
   d = (a - b).abs()
-  assert float(d.median()) <= 1e-7 and float((d > 1e-6).float().mean()) <= 0.02, (
-      float(d.median()), float((d > 1e-6).float().mean()))
-  assert float(d[:-1].max()) <= 3e-4 and float(d[-1]) <= 60 * 1e-3, float(d.max())
+  assert float(d.median()) <= 1e-5 and float((d > 1e-4).float().mean()) <= 0.02, (
+      float(d.median()), float((d > 1e-4).float().mean()))
+  assert float(d[:-1].max()) <= 2e-3 and float(d[-1]) <= 60 * 1e-3, float(d.max())
