@@ -11,6 +11,8 @@
 #include "ops.cuh"
 #include "philox.cuh"
 
+#include <cooperative_groups.h>
+
 namespace ibc {
 namespace {
 
@@ -110,6 +112,121 @@ __device__ __forceinline__ int upper_bound_range(const double* a, int lo, int hi
   return lo;
 }
 
+// max over the finite logits of a row (lowest() when there is none), block-wide
+__device__ __forceinline__ float block_row_max(const float* __restrict__ row, int n, float* s_red,
+                                               float* s_max) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  float mx = -3.402823466e+38f;
+  for (int j = tid; j < n; j += nt) {
+    const float l = row[j];
+    if (isfinite(l) && l > mx) mx = l;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+  __syncthreads();
+  if (tid < 32) {
+    float v = (tid < (nt + 31) / 32) ? s_red[tid] : -3.402823466e+38f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (tid == 0) *s_max = v;
+  }
+  __syncthreads();
+  return *s_max;
+}
+
+// The strictly sequential fp64 accumulation of TF's CPU multinomial kernel, in place (one
+// thread): loads are batched ahead of the dependent add chain so only the fp64 add latency is
+// serial.
+__device__ __forceinline__ void sequential_cdf(double* cdf, int n) {
+  double total = 0.0;
+  int j = 0;
+  for (; j + 16 <= n; j += 16) {
+    double w[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) w[q] = cdf[j + q];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { total = __dadd_rn(total, w[q]); w[q] = total; }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) cdf[j + q] = w[q];
+  }
+  for (; j < n; ++j) {
+    total = __dadd_rn(total, cdf[j]);
+    cdf[j] = total;
+  }
+}
+
+// One draw: to_find = u * total; std::upper_bound over the CDF, confined to the entries of its
+// value-space bucket when the index is in use.  `check`: flag a to_find closer than eps to either
+// neighbouring CDF entry.
+__device__ __forceinline__ int draw_index(const double* cdf, const int* tab, bool use_tab, int n,
+                                          double u, double total, double eps, bool check,
+                                          bool* ambiguous) {
+  constexpr double kInvBuckets = 1.0 / kResampleBuckets;
+  const double to_find = __dmul_rn(u, total);
+  int lo = 0, hi = n;
+  if (use_tab) {
+    int k = (int)(u * (double)kResampleBuckets);
+    k = max(0, min(kResampleBuckets - 1, k));
+    while (k > 0 && to_find < __dmul_rn((double)k * kInvBuckets, total)) --k;
+    while (k < kResampleBuckets - 1 &&
+           to_find >= __dmul_rn((double)(k + 1) * kInvBuckets, total)) ++k;
+    // u >= 1 (not produced by the samplers) or a NaN falls outside every bucket
+    if (to_find >= __dmul_rn((double)k * kInvBuckets, total) &&
+        to_find < __dmul_rn((double)(k + 1) * kInvBuckets, total)) {
+      lo = tab[k];
+      hi = tab[k + 1];
+    }
+  }
+  lo = upper_bound_range(cdf, lo, hi, to_find);
+  if (check) {
+    // cdf[lo - 1] <= to_find < cdf[lo]: too close to either neighbour?
+    if (lo > 0 && to_find - cdf[lo - 1] <= eps) *ambiguous = true;
+    if (lo < n && cdf[lo] - to_find <= eps) *ambiguous = true;
+  }
+  return lo > n - 1 ? n - 1 : lo;
+}
+
+// rows = repeat(arange, counts) for the classes [j0, j0 + m) whose inclusive count scan is
+// cnt[0, m) (+ base): every class writes its own run; classes with long runs are left to the
+// whole block.
+__device__ __forceinline__ void write_runs(const int* cnt, int m, int j0, int base, int64_t row0,
+                                           int64_t* __restrict__ out, int* heavy, int* s_nheavy) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int j = tid; j < m; j += nt) {
+    const int end = cnt[j], start = (j > 0) ? cnt[j - 1] : 0;
+    const int c = end - start;
+    if (c >= 64) {
+      const int slot = atomicAdd(s_nheavy, 1);
+      if (slot < kResampleHeavy) { heavy[slot] = j; continue; }
+    }
+    for (int q = start; q < end; ++q) out[base + q] = row0 + j0 + j;
+  }
+  __syncthreads();
+  const int nheavy = min(*s_nheavy, kResampleHeavy);
+  for (int hslot = 0; hslot < nheavy; ++hslot) {
+    const int j = heavy[hslot];
+    const int end = cnt[j], start = (j > 0) ? cnt[j - 1] : 0;
+    for (int q = start + tid; q < end; q += nt) out[base + q] = row0 + j0 + j;
+  }
+}
+
+// 2. weights (parallel).  3. CDF.  The specification is the strictly sequential
+// fp64 accumulation of TF's CPU multinomial kernel.  16 384 dependent fp64 adds are
+// ~80 us on one thread, so the CDF is first built by a parallel scan (same terms,
+// another association): both sums carry a relative error <= n * 2^-53 of the running
+// total, hence a draw whose to_find is farther than 4 n 2^-53 * total from both
+// neighbouring CDF entries selects the same index under either CDF (the code uses
+// twice that margin).  Draws are searched in the scanned CDF and checked against the
+// margin; only if one of them is ambiguous (probability ~4 n count 2^-51, about
+// 2e-3 per call at n = count = 16 384) does the block fall back to the sequential
+// chain and repeat its draws.  The result is bit-identical to the sequential
+// specification in every case.
+// 4. Draws: to_find = u * total; std::upper_bound.  A value-space index (tab[k] =
+// upper_bound(cdf, k/K * total)) confines each search to the entries of its bucket
+// (v_k <= to_find < v_k+1 implies tab[k] <= answer <= tab[k+1] by monotonicity), so a
+// draw costs a couple of shared-memory probes instead of log2(n) conflicting ones.
+//
 // One block per observation row.  Dynamic smem: double cdf[n]; int cnt[n];
 // int tab[kResampleBuckets + 1]; int heavy[kResampleHeavy].
 __global__ void __launch_bounds__(1024)
@@ -133,39 +250,8 @@ resample_kernel(const float* __restrict__ logits, const double* __restrict__ uni
   const float* row = logits + (int64_t)b * n;
 
   // 1. max over finite logits (lowest() when there is none)
-  float mx = -3.402823466e+38f;
-  for (int j = tid; j < n; j += nt) {
-    const float l = row[j];
-    if (isfinite(l) && l > mx) mx = l;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if ((tid & 31) == 0) s_red[tid >> 5] = mx;
-  __syncthreads();
-  if (tid < 32) {
-    float v = (tid < (nt + 31) / 32) ? s_red[tid] : -3.402823466e+38f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    if (tid == 0) s_max = v;
-  }
-  __syncthreads();
-  const double dmx = (double)s_max;
+  const double dmx = (double)block_row_max(row, n, s_red, &s_max);
 
-  // 2. weights (parallel).  3. CDF.  The specification is the strictly sequential
-  // fp64 accumulation of TF's CPU multinomial kernel.  16 384 dependent fp64 adds are
-  // ~80 us on one thread, so the CDF is first built by a parallel scan (same terms,
-  // another association): both sums carry a relative error <= n * 2^-53 of the running
-  // total, hence a draw whose to_find is farther than 4 n 2^-53 * total from both
-  // neighbouring CDF entries selects the same index under either CDF (the code uses
-  // twice that margin).  Draws are searched in the scanned CDF and checked against the
-  // margin; only if one of them is ambiguous (probability ~4 n count 2^-51, about
-  // 2e-3 per call at n = count = 16 384) does the block fall back to the sequential
-  // chain and repeat its draws.  The result is bit-identical to the sequential
-  // specification in every case.
-  // 4. Draws: to_find = u * total; std::upper_bound.  A value-space index (tab[k] =
-  // upper_bound(cdf, k/K * total)) confines each search to the entries of its bucket
-  // (v_k <= to_find < v_k+1 implies tab[k] <= answer <= tab[k+1] by monotonicity), so a
-  // draw costs a couple of shared-memory probes instead of log2(n) conflicting ones.
   const double eps_rel = 8.0 * (double)n * 1.1102230246251565e-16;
   const bool use_tab = n >= 4 * kResampleBuckets;
   constexpr double kInvBuckets = 1.0 / kResampleBuckets;
@@ -180,23 +266,7 @@ resample_kernel(const float* __restrict__ logits, const double* __restrict__ uni
     if (pass == 0) {
       block_scan_inplace(cdf, n, s_wd);
     } else if (tid == 0) {
-      // same left-to-right order as the CPU loop; loads are batched ahead of the
-      // dependent add chain so only the fp64 add latency is serial
-      double total = 0.0;
-      int j = 0;
-      for (; j + 16 <= n; j += 16) {
-        double w[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) w[q] = cdf[j + q];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) { total = __dadd_rn(total, w[q]); w[q] = total; }
-#pragma unroll
-        for (int q = 0; q < 16; ++q) cdf[j + q] = w[q];
-      }
-      for (; j < n; ++j) {
-        total = __dadd_rn(total, cdf[j]);
-        cdf[j] = total;
-      }
+      sequential_cdf(cdf, n);     // same left-to-right order as the CPU loop
     }
     __syncthreads();
     const double total = n > 0 ? cdf[n - 1] : 0.0;
@@ -215,28 +285,7 @@ resample_kernel(const float* __restrict__ logits, const double* __restrict__ uni
       } else {
         u = philox_uniform_double(seed, rng_stream, (uint64_t)b * (uint64_t)count + s);
       }
-      const double to_find = __dmul_rn(u, total);
-      int lo = 0, hi = n;
-      if (use_tab) {
-        int k = (int)(u * (double)kResampleBuckets);
-        k = max(0, min(kResampleBuckets - 1, k));
-        while (k > 0 && to_find < __dmul_rn((double)k * kInvBuckets, total)) --k;
-        while (k < kResampleBuckets - 1 &&
-               to_find >= __dmul_rn((double)(k + 1) * kInvBuckets, total)) ++k;
-        // u >= 1 (not produced by the samplers) or a NaN falls outside every bucket
-        if (to_find >= __dmul_rn((double)k * kInvBuckets, total) &&
-            to_find < __dmul_rn((double)(k + 1) * kInvBuckets, total)) {
-          lo = tab[k];
-          hi = tab[k + 1];
-        }
-      }
-      lo = upper_bound_range(cdf, lo, hi, to_find);
-      if (pass == 0) {
-        // cdf[lo - 1] <= to_find < cdf[lo]: too close to either neighbour?
-        if (lo > 0 && to_find - cdf[lo - 1] <= eps) ambiguous = true;
-        if (lo < n && cdf[lo] - to_find <= eps) ambiguous = true;
-      }
-      if (lo > n - 1) lo = n - 1;
+      const int lo = draw_index(cdf, tab, use_tab, n, u, total, eps, pass == 0, &ambiguous);
       if (draws) draws[(int64_t)b * count + s] = lo;
       atomicAdd(&cnt[lo], 1);
     }
@@ -249,27 +298,105 @@ resample_kernel(const float* __restrict__ logits, const double* __restrict__ uni
     for (int j = tid; j < n; j += nt) counts[(int64_t)b * n + j] = cnt[j];
   if (!rows) return;
 
-  // 5. rows = repeat(arange, counts): inclusive scan of cnt, then every class writes
-  // its own run; classes with long runs are left to the whole block.
+  // 5. rows = repeat(arange, counts): inclusive scan of cnt, then the runs
   if (tid == 0) s_nheavy = 0;
   block_scan_inplace(cnt, n, s_wi);        // ends with __syncthreads()
-  int64_t* out = rows + (int64_t)b * count;
-  for (int j = tid; j < n; j += nt) {
-    const int end = cnt[j], start = (j > 0) ? cnt[j - 1] : 0;
-    const int c = end - start;
-    if (c >= 64) {
-      const int slot = atomicAdd(&s_nheavy, 1);
-      if (slot < kResampleHeavy) { heavy[slot] = j; continue; }
+  write_runs(cnt, n, 0, 0, (int64_t)b * n, rows + (int64_t)b * count, heavy, &s_nheavy);
+}
+
+// The same resample on a thread-block cluster per observation row.  One SM is instruction
+// bound on a row of 16 384 classes and draws (237 k warp instructions, 62 us, ncu): with one
+// or a few rows -- policy inference -- the other 147 SMs idle.  Every CTA of the cluster
+// builds the whole CDF (cheap, and each needs all of it to search), takes every C-th block of
+// draws, and bins a draw into the CTA that OWNS the class (slice c of ceil(n / C) classes)
+// with an atomic on distributed shared memory; after a cluster barrier each CTA scans its
+// slice of the counts, learns its output offset from the lower slices' totals and writes its
+// part of `rows`.  Same draws, same counts, same rows as resample_kernel: integer arithmetic
+// after the (identical) CDF.  Dynamic smem: double cdf[n]; int cnt[slice]; tab; heavy.
+__global__ void __launch_bounds__(1024)
+resample_cluster_kernel(const float* __restrict__ logits, const double* __restrict__ uniforms,
+                        int n, int count, uint64_t seed, uint64_t rng_stream,
+                        int32_t* __restrict__ draws, int32_t* __restrict__ counts,
+                        int64_t* __restrict__ rows) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = (int)cluster.num_blocks(), c = (int)cluster.block_rank();
+  const int slice = (n + C - 1) / C;
+  const int j0 = c * slice, m = max(0, min(n, j0 + slice) - j0);      // classes this CTA owns
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* cdf = reinterpret_cast<double*>(smem_raw);
+  int* cnt = reinterpret_cast<int*>(cdf + n);       // [slice]
+  int* tab = cnt + slice;
+  int* heavy = tab + kResampleBuckets + 1;
+  __shared__ float s_red[32];
+  __shared__ float s_max;
+  __shared__ double s_wd[32];
+  __shared__ int s_wi[32];
+  __shared__ int s_ambiguous;
+  __shared__ int s_nheavy;
+  __shared__ int s_total;
+  const int b = blockIdx.x / C;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const float* row = logits + (int64_t)b * n;
+
+  const double dmx = (double)block_row_max(row, n, s_red, &s_max);
+  const double eps_rel = 8.0 * (double)n * 1.1102230246251565e-16;
+  const bool use_tab = n >= 4 * kResampleBuckets;
+  constexpr double kInvBuckets = 1.0 / kResampleBuckets;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int j = tid; j < n; j += nt) {
+      const float l = row[j];
+      cdf[j] = isfinite(l) ? exp64_portable(__dadd_rn((double)l, -dmx)) : 0.0;
     }
-    for (int q = start; q < end; ++q) out[q] = (int64_t)b * n + j;
+    for (int j = tid; j < slice; j += nt) cnt[j] = 0;
+    if (tid == 0) s_ambiguous = 0;
+    __syncthreads();
+    if (pass == 0) {
+      block_scan_inplace(cdf, n, s_wd);
+    } else if (tid == 0) {
+      sequential_cdf(cdf, n);
+    }
+    __syncthreads();
+    const double total = n > 0 ? cdf[n - 1] : 0.0;
+    const double eps = eps_rel * total;
+    if (use_tab) {
+      for (int k = tid; k <= kResampleBuckets; k += nt)
+        tab[k] = upper_bound_range(cdf, 0, n, __dmul_rn((double)k * kInvBuckets, total));
+    }
+    cluster.sync();       // every slice of the counts is zero before the first remote atomic
+
+    bool ambiguous = false;
+    for (int s = c * nt + tid; s < count; s += C * nt) {
+      double u;
+      if (uniforms) {
+        u = uniforms[(int64_t)b * count + s];
+      } else {
+        u = philox_uniform_double(seed, rng_stream, (uint64_t)b * (uint64_t)count + s);
+      }
+      const int lo = draw_index(cdf, tab, use_tab, n, u, total, eps, pass == 0, &ambiguous);
+      if (draws) draws[(int64_t)b * count + s] = lo;
+      const int owner = lo / slice;
+      atomicAdd(cluster.map_shared_rank(cnt, owner) + (lo - owner * slice), 1);
+    }
+    if (pass == 0 && ambiguous) s_ambiguous = 1;
+    cluster.sync();
+    int any = 0;          // one ambiguous draw anywhere sends the whole cluster to the sequential CDF
+    for (int r = 0; r < C; ++r) any |= *cluster.map_shared_rank(&s_ambiguous, r);
+    if (pass == 1 || !any) break;
+    cluster.sync();       // every CTA has read the flags before they are reset
   }
-  __syncthreads();
-  const int nheavy = min(s_nheavy, kResampleHeavy);
-  for (int hslot = 0; hslot < nheavy; ++hslot) {
-    const int j = heavy[hslot];
-    const int end = cnt[j], start = (j > 0) ? cnt[j - 1] : 0;
-    for (int q = start + tid; q < end; q += nt) out[q] = (int64_t)b * n + j;
+  if (counts)
+    for (int j = tid; j < m; j += nt) counts[(int64_t)b * n + j0 + j] = cnt[j];
+  if (rows) {
+    if (tid == 0) s_nheavy = 0;
+    block_scan_inplace(cnt, m, s_wi);        // ends with __syncthreads()
+    if (tid == 0) s_total = m > 0 ? cnt[m - 1] : 0;
+    cluster.sync();
+    int base = 0;
+    for (int r = 0; r < c; ++r) base += *cluster.map_shared_rank(&s_total, r);
+    write_runs(cnt, m, j0, base, (int64_t)b * n, rows + (int64_t)b * count, heavy, &s_nheavy);
   }
+  cluster.sync();         // no CTA leaves while a peer may still read its shared memory
 }
 
 // out[r, :] = clip(src[rows[r], :] + normal * std, min, max)   (std == 0: copy)
@@ -392,6 +519,47 @@ int resample(ibc_handle* h, const float* logits, const double* uniforms, int64_t
              (long long)n, (long long)count);
   int threads = 1024;
   while (threads > 64 && threads / 2 >= n) threads >>= 1;
+  // Few rows of many classes (policy inference): a cluster of CTAs per row, as many as keep
+  // the launch within one wave.  IBC_RESAMPLE_CLUSTER=1|2|4|8 overrides.
+  int C = 1;
+  if (n >= 4096 && count >= 4096) {
+    int sms = h ? h->sm_count : 0;
+    if (!h) {      // the stateless entry point (ibc_resample without a handle)
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    C = 8;
+    while (C > 1 && B * C > sms) C >>= 1;
+  }
+  if (const char* e = getenv("IBC_RESAMPLE_CLUSTER")) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4 || v == 8) C = v;
+  }
+  if (C > 1) {
+    const int64_t slice = (n + C - 1) / C;
+    const size_t smem = (size_t)n * 8 + (size_t)slice * 4 +
+                        (size_t)(kResampleBuckets + 1 + kResampleHeavy) * 4 + 16;
+    if (smem <= 220 * 1024) {
+      IBC_RAISE_SMEM(h, resample_cluster_kernel, 220 * 1024);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(B * C));
+      cfg.blockDim = dim3((unsigned)threads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)C;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      IBC_CUDA(h, cudaLaunchKernelEx(&cfg, resample_cluster_kernel, logits, uniforms, (int)n,
+                                     (int)count, seed, rng_stream, draws, counts, rows));
+      count_launch();
+      return IBC_OK;
+    }
+  }
   const size_t smem = (size_t)n * 12 + (size_t)(kResampleBuckets + 1 + kResampleHeavy) * 4 + 16;
   if (smem > 220 * 1024)
     IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "resample: n=%lld exceeds the shared-memory CDF (max %d)",
@@ -466,8 +634,10 @@ int dfo_generic(ibc_handle* h, int A, int64_t B, float* actions, int64_t n, cons
   float* tmp = h->ws_outer.take<float>((size_t)R * A);
   float std = iteration_std;
   const float* logits = E;
+  float* cur = actions;      // the candidates ping-pong between `actions` and `tmp`
+  float* nxt = tmp;
   for (int it = 0; it < num_iterations; ++it) {
-    IBC_TRY(energy_fn(actions, E));
+    IBC_TRY(energy_fn(cur, E));
     if (temperature != 1.0f) {
       scale_div_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(E, temperature, R, logits_buf);
       IBC_LAUNCH_CHECK(h);
@@ -478,12 +648,14 @@ int dfo_generic(ibc_handle* h, int A, int64_t B, float* actions, int64_t n, cons
     const bool last = (it == num_iterations - 1);
     const float this_std = last ? 0.f : std;
     gather_perturb_kernel<<<(unsigned)((R * A + 255) / 256), 256, 0, s>>>(
-        actions, rows, R, A, (normals && !last) ? normals + (int64_t)it * R * A : nullptr, seed,
-        2ull * it + 2, this_std, mn, mx, tmp);
+        cur, rows, R, A, (normals && !last) ? normals + (int64_t)it * R * A : nullptr, seed,
+        2ull * it + 2, this_std, mn, mx, nxt);
     IBC_LAUNCH_CHECK(h);
-    IBC_CUDA(h, cudaMemcpyAsync(actions, tmp, (size_t)R * A * 4, cudaMemcpyDeviceToDevice, s));
+    float* t = cur; cur = nxt; nxt = t;
     if (!last) std *= 0.5f;
   }
+  if (cur != actions)
+    IBC_CUDA(h, cudaMemcpyAsync(actions, cur, (size_t)R * A * 4, cudaMemcpyDeviceToDevice, s));
   if (probs) IBC_TRY(softmax_rows(h, logits, B, n, 1.0f, probs, s));
   return IBC_OK;
 }

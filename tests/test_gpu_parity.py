@@ -217,6 +217,39 @@ def test_resample_bit_exact_on_cdf_boundaries():
   assert np.array_equal(rows.cpu().numpy(), want_rows)
 
 
+@pytest.mark.parametrize('cluster', [2, 4, 8])
+@pytest.mark.parametrize('b,n,count,scale', [(1, 16384, 16384, 5.0), (2, 5003, 4100, 30.0),
+                                             (3, 4096, 4096, 60.0), (2, 300, 77, 4.0)])
+def test_resample_on_a_cluster_is_bit_exact(monkeypatch, cluster, b, n, count, scale):
+  """The thread-block-cluster resample (policy inference: a few rows of many classes; every CTA
+  of the cluster takes a share of the draws and owns a slice of the classes) against the C
+  oracle: draws, counts and rows bit for bit, including class counts that do not divide by the
+  cluster size, peaked logits (long runs), and CDF-boundary draws that force the sequential
+  fallback on every CTA."""
+  from ibc_b200 import engine as eng
+  monkeypatch.setenv('IBC_RESAMPLE_CLUSTER', str(cluster))
+  rs = np.random.RandomState(n + count + cluster)
+  logits = (rs.randn(b, n) * scale).astype(np.float32)
+  logits[0, min(3, n - 1)] = -np.inf
+  if b > 1:
+    logits[1, 0] = np.inf
+  u = rs.rand(b, count)
+  u[0, 0] = 0.0
+  if b == 3:      # boundary draws in the last row only: the other clusters stay on the scan CDF
+    w = np.exp(logits.astype(np.float64) - logits.max(axis=1, keepdims=True))
+    cdf = np.cumsum(w, axis=1)
+    pick = rs.randint(0, n - 1, size=64)
+    u[2, :64] = cdf[2, pick] / cdf[2, -1]
+    u[2, 64:96] = np.nextafter(u[2, :32], 0.0)
+    u = np.clip(u, 0.0, np.nextafter(1.0, 0.0))
+  want_draws, want_counts, want_rows = resample_c.resample(logits, u)
+  rows, draws, counts = eng.resample(torch.from_numpy(logits).cuda(),
+                                     torch.from_numpy(u).cuda(), True, True)
+  assert np.array_equal(draws.cpu().numpy(), want_draws)
+  assert np.array_equal(counts.cpu().numpy(), want_counts)
+  assert np.array_equal(rows.cpu().numpy(), want_rows)
+
+
 def test_resample_known_answer():
   from ibc_b200 import engine as eng
   logits = torch.tensor([[0.0, math.log(3.0)]], dtype=torch.float32)
