@@ -40,39 +40,50 @@ __device__ __forceinline__ double exp64_portable(double x) {
 constexpr int kResampleBuckets = 2048;    // value-space index over the CDF (power of two)
 constexpr int kResampleHeavy = 512;       // classes expanded by the whole block
 
-// Block-wide inclusive scans over shared memory, element j = base + tid (no bank
-// conflicts; a contiguous segment per thread is a 32-way conflict on every access
-// and made the two scans 40% of the kernel).
-__device__ __forceinline__ void block_scan_inplace(double* a, int n, double* s_w) {
+// The fp64 scan of the CDF, with a contiguous chunk per WARP: the warps run their chunks independently
+// (a 32-element shuffle scan per step with a running carry) and meet once for the chunk
+// offsets, instead of three block barriers and a serial warp-0 pass for every blockDim.x
+// elements.  Another association of the same terms: the bound n 2^-53 on the relative error
+// of a running total holds for every order of summation.
+__device__ __forceinline__ void block_scan_chunked(double* a, int n, double* s_w) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int nw = (nt + 31) >> 5;
+  const int chunk = (((n + nw - 1) / nw) + 31) & ~31;
+  const int lo = min(n, warp * chunk), hi = min(n, lo + chunk);
   double carry = 0.0;
-  for (int base = 0; base < n; base += nt) {
-    const int j = base + tid;
-    double v = (j < n) ? a[j] : 0.0;
+  for (int base = lo; base < hi; base += 32) {
+    const int j = base + lane;
+    double v = (j < hi) ? a[j] : 0.0;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const double up = __shfl_up_sync(0xffffffffu, v, o);
       if (lane >= o) v += up;
     }
-    if (lane == 31) s_w[warp] = v;
-    __syncthreads();
-    if (warp == 0) {
-      double w = (lane < nw) ? s_w[lane] : 0.0;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const double up = __shfl_up_sync(0xffffffffu, w, o);
-        if (lane >= o) w += up;
-      }
-      s_w[lane] = w;
-    }
-    __syncthreads();
-    if (j < n) a[j] = v + (carry + (warp > 0 ? s_w[warp - 1] : 0.0));
-    carry += s_w[nw - 1];
-    __syncthreads();
+    v += carry;
+    if (j < hi) a[j] = v;
+    carry = __shfl_sync(0xffffffffu, v, 31);
   }
+  if (lane == 0) s_w[warp] = carry;
+  __syncthreads();
+  if (warp == 0) {
+    double w = (lane < nw) ? s_w[lane] : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double up = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += up;
+    }
+    s_w[lane] = w;
+  }
+  __syncthreads();
+  if (warp > 0) {
+    const double off = s_w[warp - 1];
+    for (int j = lo + lane; j < hi; j += 32) a[j] += off;
+  }
+  __syncthreads();
 }
 
+// Block-wide inclusive scan over shared memory, element j = base + tid (no bank conflicts; a
+// contiguous segment per thread is a 32-way conflict on every access).
 __device__ __forceinline__ void block_scan_inplace(int* a, int n, int* s_w) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int nw = (nt + 31) >> 5;
@@ -264,7 +275,7 @@ resample_kernel(const float* __restrict__ logits, const double* __restrict__ uni
     if (tid == 0) s_ambiguous = 0;
     __syncthreads();
     if (pass == 0) {
-      block_scan_inplace(cdf, n, s_wd);
+      block_scan_chunked(cdf, n, s_wd);
     } else if (tid == 0) {
       sequential_cdf(cdf, n);     // same left-to-right order as the CPU loop
     }
@@ -343,16 +354,22 @@ resample_cluster_kernel(const float* __restrict__ logits, const double* __restri
   const double eps_rel = 8.0 * (double)n * 1.1102230246251565e-16;
   const bool use_tab = n >= 4 * kResampleBuckets;
   constexpr double kInvBuckets = 1.0 / kResampleBuckets;
+  cluster.sync();         // every CTA of the cluster is running: its shared memory may be written
   for (int pass = 0; pass < 2; ++pass) {
-    for (int j = tid; j < n; j += nt) {
+    // weights: the fp64 exponentials are the longest serial piece on one SM (the fp64 pipe is
+    // busy ~9 us for 16 384 of them), so each CTA computes those of the classes it owns and
+    // stores them into every CTA's CDF array
+    for (int j = j0 + tid; j < j0 + m; j += nt) {
       const float l = row[j];
-      cdf[j] = isfinite(l) ? exp64_portable(__dadd_rn((double)l, -dmx)) : 0.0;
+      const double w = isfinite(l) ? exp64_portable(__dadd_rn((double)l, -dmx)) : 0.0;
+      for (int r = 0; r < C; ++r) cluster.map_shared_rank(cdf, r)[j] = w;
     }
     for (int j = tid; j < slice; j += nt) cnt[j] = 0;
     if (tid == 0) s_ambiguous = 0;
-    __syncthreads();
+    // all weights have landed, and every slice of the counts is zero before the first remote atomic
+    cluster.sync();
     if (pass == 0) {
-      block_scan_inplace(cdf, n, s_wd);
+      block_scan_chunked(cdf, n, s_wd);
     } else if (tid == 0) {
       sequential_cdf(cdf, n);
     }
@@ -363,7 +380,7 @@ resample_cluster_kernel(const float* __restrict__ logits, const double* __restri
       for (int k = tid; k <= kResampleBuckets; k += nt)
         tab[k] = upper_bound_range(cdf, 0, n, __dmul_rn((double)k * kInvBuckets, total));
     }
-    cluster.sync();       // every slice of the counts is zero before the first remote atomic
+    __syncthreads();
 
     bool ambiguous = false;
     for (int s = c * nt + tid; s < count; s += C * nt) {
