@@ -402,7 +402,7 @@ def run_b200(args):
       fl = rows * fwd_flops_per_row()
       a = fl / fwd['tf32'] / 1e12
       result['roofline_energy_fwd'] = {
-          'kernel': 'mlp_fwd_tmem_kernel (tcgen05 kind::tf32, activations in tensor memory)', 'bound': 'tensor',
+          'kernel': 'mlp_fwd_halves_kernel<0> (tcgen05 kind::tf32, activations in tensor memory)', 'bound': 'tensor',
           'achieved': a, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': a / tf32_peak,
           'peak_source': tf32_peak_source,
           'traffic': _ncu_traffic().get('forward_nosave'), 'ms_per_launch': fwd['tf32'] * 1e3, 'rows': rows,
@@ -417,7 +417,7 @@ def run_b200(args):
       # backward reads, D fp16 operand tiles + the fp32 final residual + D mask bit-planes per
       # row; the backward also writes g0 (fp32) -- its parked gradients are L2 traffic.
       fflops = rows * fwd_flops_per_row()
-      names = ['mlp_fwd_tmem_kernel<2> (fused forward, fp16 operand tiles + ReLU masks saved)',
+      names = ['mlp_fwd_halves_kernel<2> (fused forward, fp16 operand tiles + ReLU masks saved)',
                'info_nce_kernel',
                'mlp_bwd_wgrad_tmem_kernel (block-major reverse chain + weight gradients)',
                '(weight gradients: inside the backward kernel)',

@@ -699,6 +699,84 @@ umma_f16_probe_kernel(const float* __restrict__ A, const float* __restrict__ B, 
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
+
+// K-major variants of the probe (layout_type >= 100): D[m][n] = sum_k A[m][k] B[n][k] with
+// A [128][K] and B [N][K] row-major fp32 inputs rounded to fp16.  B is the no-swizzle K-major
+// image [K/8][N][8 halves] (the tf32 chain's byte geometry: 16-byte chunks, LBO = N * 16,
+// SBO = 128, K = 16 per MMA = two chunks).  mode 100: A the same image in shared memory (SS);
+// 101: A in tensor memory, two K-elements per 32-bit column, even k in the low half (TS);
+// 102: the same with odd k in the low half.
+__global__ void __launch_bounds__(128, 1)
+umma_f16_kmajor_probe_kernel(const float* __restrict__ A, const float* __restrict__ B, int N, int K,
+                             int mode, float* __restrict__ D, int* status) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* a_img = smem;                                  // [K/8][128][16 B]
+  unsigned char* b_img = smem + (size_t)K * 128 * 2;            // [K/8][N][16 B]
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ int s_abort;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) { s_abort = 0; mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  for (int c = 0; c < K / 8; ++c) {
+    const float* sa = A + (int64_t)tid * K + c * 8;
+    uint4 v;
+    v.x = pack_half2(sa[0], sa[1]); v.y = pack_half2(sa[2], sa[3]);
+    v.z = pack_half2(sa[4], sa[5]); v.w = pack_half2(sa[6], sa[7]);
+    *reinterpret_cast<uint4*>(a_img + ((size_t)c * 128 + tid) * 16) = v;
+    for (int n = tid; n < N; n += 128) {
+      const float* sb = B + (int64_t)n * K + c * 8;
+      uint4 w;
+      w.x = pack_half2(sb[0], sb[1]); w.y = pack_half2(sb[2], sb[3]);
+      w.z = pack_half2(sb[4], sb[5]); w.w = pack_half2(sb[6], sb[7]);
+      *reinterpret_cast<uint4*>(b_img + ((size_t)c * N + n) * 16) = w;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t col_a = tmem_base + 128;                       // A operand behind the accumulator
+  if (mode != 100) {
+    for (int c = 0; c < K / 2; ++c) {
+      const float lo = A[(int64_t)tid * K + 2 * c + (mode == 102 ? 1 : 0)];
+      const float hi = A[(int64_t)tid * K + 2 * c + (mode == 102 ? 0 : 1)];
+      uint32_t v[1] = {pack_half2(lo, hi)};
+      tmem_st_n<1>(col_a + lane_off + c, v);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    const uint32_t idesc = idesc_f16(128, N);
+    const uint64_t ad0 = smem_desc(smem_u32(a_img), 128 * 16, 128);
+    const uint64_t bd0 = smem_desc(smem_u32(b_img), (uint32_t)N * 16, 128);
+    for (int ks = 0; ks < K / 16; ++ks) {
+      if (mode == 100)
+        mma_f16_ss(tmem_base, ad0 + (uint64_t)(ks * ((2 * 128 * 16) >> 4)),
+                   bd0 + (uint64_t)(ks * ((2 * N * 16) >> 4)), idesc, (uint32_t)(ks > 0));
+      else
+        mma_f16_ts(tmem_base, col_a + (uint32_t)(ks * 8), bd0 + (uint64_t)(ks * ((2 * N * 16) >> 4)),
+                   idesc, (uint32_t)(ks > 0));
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0, &s_abort, status, 78);
+  tc_fence_after();
+  for (int c32 = 0; c32 < N / 32; ++c32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + lane_off + c32 * 32, v);
+    tmem_ld_wait(v);
+    for (int q = 0; q < 32; ++q) D[(int64_t)tid * N + c32 * 32 + q] = __uint_as_float(v[q]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
 }  // namespace
 
 int umma_f16_selftest(const float* A, const float* B, int N, int K, uint32_t lbo_a, uint32_t lbo_b,
@@ -707,6 +785,25 @@ int umma_f16_selftest(const float* A, const float* B, int N, int K, uint32_t lbo
   ibc_handle* h = nullptr;
   if (N < 64 || N > 256 || (N % 64) || K < 16 || K > 128 || (K % 16))
     IBC_FAIL(h, IBC_ERR_INVALID, "umma_f16_selftest: need N in {64,128,192,256}, K a multiple of 16 <= 128");
+  if (layout_type >= 100) {      // K-major operands, A from shared or tensor memory (see the kernel)
+    if (N > 128) IBC_FAIL(h, IBC_ERR_INVALID, "umma_f16_selftest: K-major modes need N <= 128");
+    int* st = nullptr;
+    IBC_CUDA(h, cudaMalloc((void**)&st, sizeof(int)));
+    IBC_CUDA(h, cudaMemsetAsync(st, 0, sizeof(int), s));
+    IBC_CUDA(h, cudaFuncSetAttribute(umma_f16_kmajor_probe_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    umma_f16_kmajor_probe_kernel<<<1, 128, (size_t)K * 128 * 2 + (size_t)K * N * 2, s>>>(
+        A, B, N, K, (int)layout_type, D, st);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    int st_host = -1;
+    if (e == cudaSuccess) e = cudaMemcpy(&st_host, st, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(st);
+    if (status_host) *status_host = st_host;
+    if (e != cudaSuccess) IBC_FAIL(h, IBC_ERR_CUDA, "umma_f16_selftest: %s", cudaGetErrorString(e));
+    return IBC_OK;
+  }
   if (!lbo_a) lbo_a = ImgF16::lbo(K);
   if (!lbo_b) lbo_b = ImgF16::lbo(K);
   if (!sbo) sbo = ImgF16::kSbo;

@@ -31,6 +31,17 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint
       : "memory");
 }
 
+// D[tmem] (+)= A[tmem] . B[smem]^T with 16-bit A packed two K-elements per 32-bit column
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Image of a [K rows][MN] 16-bit operand block, K a multiple of 8, MN a multiple of 64:
 // [MN / 64 atoms][K / 8 atoms][8 lines][128 B].
 struct ImgF16 {
