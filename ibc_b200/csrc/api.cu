@@ -80,6 +80,7 @@ int ibc_destroy(ibc_handle* h) {
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
     if (h->packed) cudaFree(h->packed);
+    if (h->packed16) cudaFree(h->packed16);
     if (h->dev_status) cudaFree(h->dev_status);
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (auto& g : h->langevin_graphs) g.release();

@@ -108,6 +108,7 @@ struct ibc_handle {
   bool packed_stale = true;
   float* packed = nullptr;        // tcgen05 operand copies of the weights
   size_t packed_bytes = 0;
+  void* packed16 = nullptr;       // fp16 operand copies (width 128, langevin_f16.cu)
   int* dev_status = nullptr;      // kernel-side barrier-timeout flag
   bool profiling = false;         // record CUDA events around the training kernels
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

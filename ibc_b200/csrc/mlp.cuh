@@ -74,6 +74,15 @@ int wide_pack_if_stale(ibc_handle* h, cudaStream_t s);
 int mlp_energy_wide(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
                     float* E, float* dEda, bool apply_exp, cudaStream_t s);
 // the whole Langevin chain of a width-128 stack as one persistent kernel (langevin_tmem.cu)
+// width 128, act_dim <= 8: the same chain with kind::f16 GEMMs and sixteen epilogue warps
+// (langevin_f16.cu); pack16_params refreshes its fp16 weight images
+bool langevin_f16_supported(const Layout& L);
+int pack16_params(ibc_handle* h, cudaStream_t s);
+int langevin_f16(ibc_handle* h, const float* hp, int64_t B, float* actions, int64_t n,
+                 const float* mn, const float* mx, const ibc_langevin_cfg& c, const float* normals,
+                 uint64_t seed, const uint64_t* seed_ptr, const float* steps_dev,
+                 float* chain_actions, float* chain_energies, float* chain_grad_norms,
+                 cudaStream_t s);
 bool langevin_fused_supported(const Layout& L);
 int langevin_fused(ibc_handle* h, const float* hp, int64_t B, float* actions, int64_t n,
                    const float* mn, const float* mx, const ibc_langevin_cfg& c,

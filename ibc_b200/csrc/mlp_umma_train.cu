@@ -849,6 +849,9 @@ int langevin_umma(ibc_handle* h, const float* obs, int64_t B, float* actions, in
     g.bias = h->params + L.bp; g.M = (int)B; g.N = L.W; g.K = L.O;
     IBC_TRY(gemm(h, g, false, false, s));
     IBC_CUDA(h, cudaMemcpyAsync(steps_dev, steps.data(), (size_t)K * 4, cudaMemcpyHostToDevice, s));
+    if (langevin_f16_supported(L))     // act_dim <= 8: kind::f16 chain, sixteen epilogue warps
+      return langevin_f16(h, hp, B, actions, n, mn, mx, c, normals, seed, nullptr, steps_dev,
+                          chain_actions, chain_energies, chain_grad_norms, s);
     return langevin_fused(h, hp, B, actions, n, mn, mx, c, normals, seed, nullptr, steps_dev,
                           chain_actions, chain_energies, chain_grad_norms, s);
   }

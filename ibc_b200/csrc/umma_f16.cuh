@@ -61,6 +61,13 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   return r;
 }
 
+// max of two packed fp16 pairs (relu on a packed pair: against 0; NaN -> the other operand)
+__device__ __forceinline__ uint32_t hmax2_bits(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
 // the same toward zero: for an operand that already carries the tf32 round-to-nearest offset
 // (bits + 0x1000, umma_pack.cuh) truncating to fp16's 10-bit mantissa completes the rounding
 __device__ __forceinline__ uint32_t pack_half2_rz(float lo, float hi) {

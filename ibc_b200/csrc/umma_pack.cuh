@@ -63,6 +63,16 @@ inline PackedLayout make_packed_layout(const Layout& L) {
 }
 
 
+// Offsets (in halves) inside the fp16 operand buffer of a width-128 stack (langevin_f16.cu)
+struct Packed16Layout {
+  int KP, AP;
+  int64_t p0;        // [KP/8][W][8]   act rows of Wp (B operand of step 0)
+  int64_t fwd;       // 2*nb blocks [W/8][W][8] + [2][W][8]: layer i's operand + its bias slice
+  int64_t rev;       // 2*nb matrices [W/8][W][8]: W2_{nb-1}^T, W1_{nb-1}^T, ..., W1_0^T
+  int64_t revp;      // [W/8][AP][8]   Wp act rows, B operand of dE/dact
+  int64_t total;
+};
+
 // MN-major tf32 operand layout (UMMA SWIZZLE_128B_BASE32B, layout type 1; the
 // only shared-memory layout tcgen05 accepts for MN-major 32-bit operands).
 // Atoms of 32 MN-elements x 4 K-rows = 512 B: K-row kr is a 128-byte line made

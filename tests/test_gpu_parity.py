@@ -362,19 +362,64 @@ print('DIGEST', h.hexdigest())
 
 
 def test_fused_langevin_kernel_is_bit_identical_to_the_three_kernel_chain():
-  """langevin_tmem.cu (one persistent kernel for the whole chain) against the forward /
-  reverse / update kernels it fuses (IBC_NO_FUSED_LANGEVIN=1): same arithmetic in the same
-  order, so actions and the recorded chain must agree bit for bit."""
+  """langevin_tmem.cu (one persistent kind::tf32 kernel for the whole chain; IBC_LANGEVIN_TF32=1
+  selects it over the kind::f16 chain of langevin_f16.cu) against the forward / reverse / update
+  kernels it fuses (IBC_NO_FUSED_LANGEVIN=1): same arithmetic in the same order, so actions and
+  the recorded chain must agree bit for bit."""
   import os, subprocess, sys
   root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
   digests = []
-  for env_extra in ({}, {'IBC_NO_FUSED_LANGEVIN': '1'}):
+  for env_extra in ({'IBC_LANGEVIN_TF32': '1'}, {'IBC_NO_FUSED_LANGEVIN': '1'}):
     env = dict(os.environ, **env_extra)
     out = subprocess.run([sys.executable, '-c', _FUSED_SCRIPT % root], env=env, cwd=root,
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     digests.append([l for l in out.stdout.splitlines() if l.startswith('DIGEST')][0])
   assert digests[0] == digests[1]
+
+
+def test_langevin_f16_chain_tracks_the_tf32_chain(monkeypatch):
+  """langevin_f16.cu runs the chain's GEMMs in kind::f16 (the same 11-bit significand as tf32,
+  fp32 accumulation; the reverse chain carried times a power of two per row) under sixteen
+  epilogue warps.  Its parity gate is the oracle (test_langevin_matches_oracle,
+  test_langevin_100_iterations_on_the_training_rows); this test measures it beside the
+  kind::tf32 kernel against the fp32 path on the pushing_states net (16 layers): at iteration 0
+  (identical actions) its energies and gradient norms must be as close to fp32 as the tf32
+  kernel's, up to 1.5 x; after K = 100 iterations of the same Philox noise its actions stay
+  inside SURVEY.md 8d's 5e-3 (max - min) of the tf32 kernel's; kernel status 0 (no operand left
+  fp16's range)."""
+  from ibc_b200 import _lib
+  from ibc_b200 import engine as eng
+  spec = omlp.MLPSpec(20, 2, 128, 16)
+  e = eng.EBMEngine(20, 2, 128, 16)
+  e.bind_params(omlp.init_params(spec, seed=11).cuda().contiguous())
+  g = torch.Generator().manual_seed(4)
+  b, n = 50, 8                                   # 400 rows: three full tiles and a ragged one
+  obs = torch.randn(b, 20, generator=g).cuda()
+  act0 = (torch.rand(b * n, 2, generator=g) * 2.2 - 1.1).cuda()
+  mn = torch.full((2,), -1.1).cuda(); mx = torch.full((2,), 1.1).cuda()
+  cfg = eng.langevin_cfg(num_iterations=100)
+  out = {}
+  for name in ('f16', 'tf32', 'fp32'):
+    monkeypatch.delenv('IBC_LANGEVIN_TF32', raising=False)
+    if name == 'tf32':
+      monkeypatch.setenv('IBC_LANGEVIN_TF32', '1')
+    e.set_precision(_lib.PRECISION_FP32 if name == 'fp32' else _lib.PRECISION_TF32)
+    a = act0.clone()
+    ca, ce, cg = e.langevin(obs, a, n, mn, mx, cfg, seed=9, return_chain=True)
+    assert e.kernel_status() == 0
+    out[name] = (a.cpu().double(), ce.cpu().double(), cg.cpu().double())
+  da = (out['f16'][0] - out['tf32'][0]).abs()
+  assert float(da.max()) > 0.0, 'both runs took the same kernel'
+  err = {k: (float((out[k][1][0] - out['fp32'][1][0]).abs().max()),
+             float((out[k][2][0] - out['fp32'][2][0]).abs().max())) for k in ('f16', 'tf32')}
+  espan, gspan = float(out['fp32'][1][0].abs().max()), float(out['fp32'][2][0].abs().max())
+  print('iteration 0 against fp32: energies f16 %.3g tf32 %.3g of %.3g; grad norms f16 %.3g tf32 %.3g of %.3g'
+        % (err['f16'][0], err['tf32'][0], espan, err['f16'][1], err['tf32'][1], gspan))
+  print('final actions f16 vs tf32: max %.3g mean %.3g' % (float(da.max()), float(da.mean())))
+  assert err['f16'][0] <= 1.5 * err['tf32'][0] + 1e-4 * espan, (err, espan)
+  assert err['f16'][1] <= 1.5 * err['tf32'][1] + 1e-3 * gspan, (err, gspan)
+  assert float(da.max()) <= 5e-3 * 2.2 and float(da.mean()) <= 5e-4, (float(da.max()), float(da.mean()))
 
 
 # ------------------------------ losses -------------------------------------------
