@@ -363,9 +363,10 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tmem_kernel(LangevinPara
           const uint32_t d_tmem = x_to_y ? col_y : col_x;
           const uint32_t slot = q % kRing;
           if (elect_one()) {
-            mbar_wait(a_ready, ph_a, abort_flag, p.status, 1400 + i);
+            // weights first: a passed wait still costs 150-300 cycles (langevin_f16.cu)
             if (i == 0) mbar_wait(p0_full, 0, abort_flag, p.status, 1450);
             else mbar_wait(&w_full[slot], (q / kRing) & 1, abort_flag, p.status, 1460);
+            mbar_wait(a_ready, ph_a, abort_flag, p.status, 1400 + i);
             tc_fence_after();
             if (i == 0) {
               const uint64_t b_desc0 = smem_desc(smem_u32(p0_buf), b_lbo, sbo);
@@ -392,8 +393,8 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tmem_kernel(LangevinPara
           const uint32_t d_tmem = (i & 1) ? col_x : col_y;
           const uint32_t slot = q % kRing;
           if (elect_one()) {
-            mbar_wait(a_ready, ph_a, abort_flag, p.status, 1500 + s);
             mbar_wait(&w_full[slot], (q / kRing) & 1, abort_flag, p.status, 1560);
+            mbar_wait(a_ready, ph_a, abort_flag, p.status, 1500 + s);
             tc_fence_after();
             mma_tf32_ts_steps<kKSteps>(
                 d_tmem, a_tmem, smem_desc(smem_u32(ring + (size_t)slot * kSlotBytes), b_lbo, sbo),

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_halves_kernel(FwdHalvesPa
   if (tid == 0) {
     s_abort = 0;
     s_pipe = 0;
-    for (int t = 0; t < kNT; ++t) { mbar_init(&a_ready[t], 256); mbar_init(&d_ready[t], 1); }
+    for (int t = 0; t < kNT; ++t) { mbar_init(&a_ready[t], 8); mbar_init(&d_ready[t], 1); }
     for (int s = 0; s < kRing; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kNT); }
     mbar_init(p0_full, 1);
     fence_mbar_init();
@@ -147,8 +147,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_halves_kernel(FwdHalvesPa
         }
         tmem_st_wait();
       }
+      // one arrival per warp: the warp's tensor-memory stores are complete and fenced
       tc_fence_before();
-      mbar_arrive(&a_ready[t]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_ready[t]);
       // residual stream of this row's half, seeded with the hoisted observation projection
       float h[64];
       {
@@ -233,7 +235,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_halves_kernel(FwdHalvesPa
                 make_uint2(mb[0], mb[1]);
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&a_ready[t]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[t]);
         }
       };
       using T_ = std::true_type;
@@ -306,9 +309,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_halves_kernel(FwdHalvesPa
         const uint32_t d_tmem = x_to_y ? col_y : col_x;
         const uint32_t slot = q % kRing;
         if (elect_one()) {
-          mbar_wait(&a_ready[t], ph_a, abort_flag, p.status, 4300 + i);
+          // the weights first: they landed long ago, and a passed mbarrier wait still costs
+          // 150-300 cycles -- spent while the epilogue is busy instead of behind its arrival
           if (i == 0) mbar_wait(p0_full, 0, abort_flag, p.status, 4400);
           else mbar_wait(&w_full[slot], (q / kRing) & 1, abort_flag, p.status, 4400 + i);
+          mbar_wait(&a_ready[t], ph_a, abort_flag, p.status, 4300 + i);
           tc_fence_after();
           pipe_acquire(&s_pipe, abort_flag);
           if (p.dbg && blockIdx.x == 0 && k == 1 && i < 40) p.dbg[(i * kNT + t) * 2] = clock64();

@@ -376,12 +376,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tmem_kernel(FwdTmemParams
         const uint32_t d_tmem = x_to_y ? col_y : col_x;
         const uint32_t slot = q % kRing;
         if (elect_one()) {
-          mbar_wait(&a_ready[t], ph_a, abort_flag, p.status, 300 + i);
           // The layer's weights before the first MMA: an mbarrier wait issued behind
           // tcgen05.mma instructions does not return until they have (nearly) drained
-          // (~100 cycles each, measured).
+          // (~100 cycles each, measured) -- and before the operand wait: a passed wait still
+          // costs 150-300 cycles, better spent while the epilogue is busy.
           if (i == 0) mbar_wait(p0_full, 0, abort_flag, p.status, 400);
           else mbar_wait(&w_full[slot], (q / kRing) & 1, abort_flag, p.status, 400 + i);
+          mbar_wait(&a_ready[t], ph_a, abort_flag, p.status, 300 + i);
           tc_fence_after();
           pipe_acquire(&s_pipe, abort_flag);
           if (mstamp) p.dbg[(i * kNT + t) * 5 + 3] = clock64();
@@ -694,8 +695,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_tmem_kernel(BwdTmemParams
         const uint32_t d_tmem = (i & 1) ? col_x : col_y;
         const uint32_t slot = q % kRing;
         if (elect_one()) {
-          mbar_wait(&a_ready[t], ph_a, abort_flag, p.status, 700 + s);
           mbar_wait(&w_full[slot], (q / kRing) & 1, abort_flag, p.status, 800 + s);
+          mbar_wait(&a_ready[t], ph_a, abort_flag, p.status, 700 + s);
           tc_fence_after();
           pipe_acquire(&s_pipe, abort_flag);
           const bool mstamp = p.dbg && blockIdx.x == 0 && k == p.dbg_item;
