@@ -68,9 +68,9 @@ using namespace umma;
 namespace {
 
 constexpr int kW = 128;
-constexpr int kLayerWBytes = kW * kW * 4;          // one transposed layer (tf32): 64 KB
+constexpr int kLayerWBytes = kW * kW * 2;          // one transposed layer (fp16, K-major chunks): 32 KB
 constexpr int kImgBytes = 32 * kW * 2;             // fp16 image of a 32-row sub-tile: 8 KB
-constexpr int kKSteps = kW / 8;
+constexpr int kKSteps = kW / 16;                   // kind::f16: K = 16 per MMA
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = (kEpiWarps + 8) * 32;
 // 768 threads start with 80 registers; the CTA's pool is redistributed by setmaxnreg
@@ -78,7 +78,7 @@ constexpr int kEpiRegs = 88, kOpRegs = 56, kServiceRegs = 72;
 constexpr int kAStages = 8;                        // A images (cp.async landing zones): 64 KB
 constexpr int kDbgWords = 2048;
 
-constexpr size_t kOffW = 0;                                        // [2][64 KB]  W2_j^T, W1_j^T
+constexpr size_t kOffW = 0;                                        // [2][32 KB]  W2_j^T, W1_j^T (fp16)
 constexpr size_t kOffDy = kOffW + 2 * (size_t)kLayerWBytes;        // [4][8 KB]   dY images, one per sub-tile
 constexpr size_t kOffA = kOffDy + 4 * (size_t)kImgBytes;           // [8][8 KB]   A images
 constexpr size_t kOffWe = kOffA + kAStages * (size_t)kImgBytes;    // we[128], scale, 1 / scale
@@ -103,7 +103,8 @@ struct BwdWgradParams {
   float* grads;               // flat gradient: b1 / b2 / we entries accumulated here directly
   Layout L;
   const float* packed;
-  int64_t off_rev_l, off_we;
+  const __half* packed16;     // fp16 operand images (Packed16Layout): the transposed layers
+  int64_t off_rev16, off_we;
   int64_t R;
   int nb, tiles;
   int* status;
@@ -151,20 +152,21 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// One row's 32 consecutive columns, scaled, as fp16 into the image of its sub-tile: four
-// 16-byte pieces of the row's line (umma_f16.cuh).  The 128-byte swizzle spreads the eight
-// rows of a quarter-warp over the eight 16-byte bank groups: conflict-free.
-__device__ __forceinline__ void sts_image_f16(unsigned char* img, int lane, int cc, float scale,
-                                              const uint32_t (&v)[32]) {
+// One row's 32 consecutive columns as 16 packed fp16 pairs (round to nearest, saturating).
+__device__ __forceinline__ void pack32_scaled(const uint32_t (&v)[32], float scale, uint32_t (&w)[16]) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 w;
-    w.x = pack_half2(__uint_as_float(v[8 * i + 0]) * scale, __uint_as_float(v[8 * i + 1]) * scale);
-    w.y = pack_half2(__uint_as_float(v[8 * i + 2]) * scale, __uint_as_float(v[8 * i + 3]) * scale);
-    w.z = pack_half2(__uint_as_float(v[8 * i + 4]) * scale, __uint_as_float(v[8 * i + 5]) * scale);
-    w.w = pack_half2(__uint_as_float(v[8 * i + 6]) * scale, __uint_as_float(v[8 * i + 7]) * scale);
-    *reinterpret_cast<uint4*>(img + ImgF16::piece(lane, cc * 4 + i, 32)) = w;
-  }
+  for (int q = 0; q < 16; ++q)
+    w[q] = pack_half2(__uint_as_float(v[2 * q]) * scale, __uint_as_float(v[2 * q + 1]) * scale);
+}
+
+// ... into the image of the row's sub-tile: four 16-byte pieces of the row's line
+// (umma_f16.cuh).  The 128-byte swizzle spreads the eight rows of a quarter-warp over the eight
+// 16-byte bank groups: conflict-free.
+__device__ __forceinline__ void sts_image_f16(unsigned char* img, int lane, int cc, const uint32_t (&w)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<uint4*>(img + ImgF16::piece(lane, cc * 4 + i, 32)) =
+        make_uint4(w[4 * i + 0], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
 }
 
 // Transposing warp reduction: v[i] of every lane summed over the 32 lanes, the sum of
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
 
   if (tid == 0) {
     s_abort = 0;
-    mbar_init(a_ready, kEpiWarps * 32);
+    mbar_init(a_ready, kEpiWarps);        // one arrival per epilogue warp
     mbar_init(d_ready, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     mbar_init(dy_full, kEpiWarps);
@@ -288,17 +290,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
         // blk > 0: g is already in registers -- carried over the block boundary (k == 0) or
         // loaded from the park at the end of the previous item (below)
         if (stamp) dbg[1] = clock64() + (long long)(gr[0] == 12345.f);   // after the loads landed
-#pragma unroll
-        for (int q = 0; q < 32; ++q) v[q] = tf32_rn_bits(__float_as_uint(gr[q]));
-        tmem_st32(col_x, v);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(a_ready);
-        if (stamp) dbg[2] = clock64();
-        mbar_wait(dy_empty, 1, abort_flag, p.status, 1000);          // previous u image consumed
+        // the chain's operand and the weight-gradient image are the same scaled fp16 values
+        uint32_t w16[16];
 #pragma unroll
         for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(gr[q]);
-        if (!(p.dbg_mode & 8)) sts_image_f16(dy_img, lane, cc, scale, v);
+        pack32_scaled(v, scale, w16);
+        tmem_st16(col_x, w16);               // packed pairs in the first 16 columns of this chunk
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);
+        if (stamp) dbg[2] = clock64();
+        mbar_wait(dy_empty, 1, abort_flag, p.status, 1000);          // previous u image consumed
+        if (!(p.dbg_mode & 8)) sts_image_f16(dy_img, lane, cc, w16);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(dy_full);
@@ -323,37 +327,28 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
         if (stamp) dbg[3] = clock64();
         tmem_ld32(col_y, v);
         tmem_ld_wait(v);
+        // Y = (scale g) . W2^T: u stays scaled -- operand, image and (until the flush) bias sums
 #pragma unroll
-        for (int q = 0; q < 32; ++q) v[q] = tf32_rn_bits(((m1 >> q) & 1u) ? v[q] : 0u);
-        tmem_st32(col_y, v);
+        for (int q = 0; q < 32; ++q) v[q] = ((m1 >> q) & 1u) ? v[q] : 0u;
+        pack32_scaled(v, 1.0f, w16);
+        tmem_st16(col_y, w16);               // in place: the first 16 columns of this thread's own chunk
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(a_ready);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);
         if (stamp) dbg[4] = clock64();
-#pragma unroll
-        for (int q = 0; q < 32; ++q) v[q] -= 0x1000u;          // undo the rounding offset: exact fp32 u
         mbar_wait(dy_empty, 0, abort_flag, p.status, 1002);          // g image consumed
-        if (!(p.dbg_mode & 8)) sts_image_f16(dy_img, lane, cc, scale, v);
+        if (!(p.dbg_mode & 8)) sts_image_f16(dy_img, lane, cc, w16);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(dy_full);
         if (stamp) dbg[5] = clock64();
         if (!(p.dbg_mode & 4)) bsum_u += warp_colsum32(v, lane);
 
-        // ---- G': g += X (.) m0, parked (after the last block this is g0) -----------
-        mbar_wait(d_ready, ph_d, abort_flag, p.status, 1003);
-        ph_d ^= 1;
-        tc_fence_after();
-        if (stamp) dbg[6] = clock64();
-        tmem_ld32(col_x, v);
-        tmem_ld_wait(v);
-#pragma unroll
-        for (int q = 0; q < 32; ++q)
-          gr[q] += ((m0 >> q) & 1u) ? __uint_as_float(v[q]) : 0.f;
         // The next item's g (another tile of this CTA, parked by these same threads one block
-        // ago) is requested BEFORE this item's stores: 64 KB of stores per item drain at the
-        // SM's ~32 B/clk write rate (~2 000 cycles, measured), and loads issued behind them
-        // would wait for all of it.  v is dead here and takes the loaded values.
+        // ago) is requested here, while the second chain MMA runs: v is free until the end of
+        // the item (G' reads its accumulator through the 16 registers of w16), and the loads
+        // are ahead of this item's 64 KB of park stores, which drain at the SM's ~32 B/clk.
         const bool load_next = blk > 0 && k + 1 < ntile;
         if (load_next) {
           const float4* pn = reinterpret_cast<const float4*>(p.gpark + tile_of(blk, k + 1) * (int64_t)TT::kTileFloats) +
@@ -364,6 +359,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
             v[q * 4 + 0] = __float_as_uint(x.x); v[q * 4 + 1] = __float_as_uint(x.y);
             v[q * 4 + 2] = __float_as_uint(x.z); v[q * 4 + 3] = __float_as_uint(x.w);
           }
+        }
+
+        // ---- G': g += X (.) m0, parked (after the last block this is g0) -----------
+        mbar_wait(d_ready, ph_d, abort_flag, p.status, 1003);
+        ph_d ^= 1;
+        tc_fence_after();
+        if (stamp) dbg[6] = clock64();
+#pragma unroll
+        for (int hq = 0; hq < 2; ++hq) {
+          tmem_ld16(col_x + (uint32_t)(hq * 16), w16);
+          tmem_ld_wait16(w16);
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            gr[hq * 16 + q] += ((m0 >> (hq * 16 + q)) & 1u) ? __uint_as_float(w16[q]) * inv_scale : 0.f;
         }
         if (!carry_out && !(p.dbg_mode & 2)) {
 #pragma unroll
@@ -393,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
         for (int q = 0; q < 8; ++q)
           red_add_v4(pw + q * 128 * 4, __uint_as_float(v[q * 4 + 0]) * inv_scale, __uint_as_float(v[q * 4 + 1]) * inv_scale,
                      __uint_as_float(v[q * 4 + 2]) * inv_scale, __uint_as_float(v[q * 4 + 3]) * inv_scale);
-        atomicAdd(p.grads + (a ? p.L.b1(jb) : p.L.b2(jb)) + cc * 32 + lane, a ? bsum_u : bsum_g);
+        atomicAdd(p.grads + (a ? p.L.b1(jb) : p.L.b2(jb)) + cc * 32 + lane, a ? bsum_u * inv_scale : bsum_g);
       }
       if (blk == 0) atomicAdd(p.grads + p.L.we + cc * 32 + lane, bsum_e);
       bsum_g = 0.f; bsum_u = 0.f;
@@ -466,16 +475,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
           mbar_wait(&w_empty[half], ((uint32_t)blk & 1u) ^ 1u, abort_flag, p.status, 1200 + half);
           mbar_arrive_expect_tx(&w_full[half], (uint32_t)kLayerWBytes);
           bulk_g2s(wbuf + (size_t)half * kLayerWBytes,
-                   p.packed + p.off_rev_l + (int64_t)(2 * blk + half) * W * W,
+                   p.packed16 + p.off_rev16 + (int64_t)(2 * blk + half) * W * W,
                    (uint32_t)kLayerWBytes, &w_full[half]);
         }
         __syncwarp();
       }
     }
   } else if (warp == kEpiWarps + 5) {
-    // ===================== chain MMA issuer (kind::tf32) ================================
+    // ===================== chain MMA issuer (kind::f16) =================================
+    // The chain's operands are the scaled fp16 values of the weight-gradient images (tf32's
+    // significand; the range is the images'), packed two K-elements per tensor-memory column in
+    // the first 16 columns of each 32-column chunk: K-step ks reads columns 32 (ks / 2) + 8 (ks % 2).
     setmaxnreg_dec<kServiceRegs>();
-    const uint32_t idesc = idesc_tf32(128, W);
+    const uint32_t idesc = idesc_f16(128, W);
     const uint32_t b_lbo = W * 16, sbo = 128;
     constexpr uint32_t b_step16 = (2 * W * 16) >> 4;
     uint32_t ph_a = 0;
@@ -483,15 +495,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
       for (int k = 0; k < ntile; ++k) {
         for (int half = 0; half < 2; ++half) {
           if (elect_one()) {
-            mbar_wait(a_ready, ph_a, abort_flag, p.status, 1300 + half);
             if (k == 0) mbar_wait(&w_full[half], (uint32_t)blk & 1u, abort_flag, p.status, 1310 + half);
+            mbar_wait(a_ready, ph_a, abort_flag, p.status, 1300 + half);
             tc_fence_after();
             // half 0: Y = X . W2^T ; half 1: X = Y . W1^T
             const uint32_t a_tmem = tmem_base + (uint32_t)(half ? W : 0);
             const uint32_t d_tmem = tmem_base + (uint32_t)(half ? 0 : W);
-            mma_tf32_ts_steps<kKSteps>(
-                d_tmem, a_tmem, smem_desc(smem_u32(wbuf + (size_t)half * kLayerWBytes), b_lbo, sbo),
-                b_step16, idesc, 0u);
+            const uint64_t bd = smem_desc(smem_u32(wbuf + (size_t)half * kLayerWBytes), b_lbo, sbo);
+#pragma unroll
+            for (int ks = 0; ks < kKSteps; ++ks)
+              mma_f16_ts(d_tmem, a_tmem + (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8),
+                         bd + (uint64_t)(ks * b_step16), idesc, (uint32_t)(ks > 0));
             if (k == ntile - 1) mma_commit(&w_empty[half]);
             mma_commit(d_ready);
           }
@@ -589,7 +603,8 @@ int tmem_reverse_wgrad(ibc_handle* h, const float* dE, const uint32_t* dE_absmax
   p.dE = dE; p.dE_absmax = dE_absmax; p.xa16 = reinterpret_cast<const uint4*>(xa16);
   p.mask_save = mask_save; p.gpark = gpark; p.hn = hn;
   p.acc_w = acc_w; p.grads = grads; p.L = L; p.packed = h->packed;
-  p.off_rev_l = pl.rev_l; p.off_we = pl.vecs + (int64_t)(2 * L.nb + 1) * L.W;
+  p.packed16 = reinterpret_cast<const __half*>(h->packed16);
+  p.off_rev16 = make_packed16_layout(L).rev; p.off_we = pl.vecs + (int64_t)(2 * L.nb + 1) * L.W;
   p.R = R; p.nb = L.nb;
   const int64_t tiles = (R + 127) / 128;
   p.tiles = (int)tiles;

@@ -817,7 +817,7 @@ int umma_pack_params(ibc_handle* h, cudaStream_t s) {
   }
   pack_kernel<<<296, 256, 0, s>>>(h->params, h->L, pl, h->packed);
   IBC_LAUNCH_CHECK(h);
-  if (langevin_f16_supported(h->L)) IBC_TRY(pack16_params(h, s));
+  if (h->L.W == 128) IBC_TRY(pack16_params(h, s));     // fp16 images: Langevin chain, block-major backward
   h->packed_stale = false;
   return IBC_OK;
 }

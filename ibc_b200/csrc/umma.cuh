@@ -95,6 +95,12 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
                "r"(smem_u32(smem_src)), "r"(bytes)
                : "memory");
 }
+// ... with an L2 eviction-priority policy (createpolicy) for the written lines
+__device__ __forceinline__ void bulk_s2g_hint(void* gdst, const void* smem_src, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+               "r"(smem_u32(smem_src)), "r"(bytes), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }

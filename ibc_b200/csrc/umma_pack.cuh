@@ -72,6 +72,7 @@ struct Packed16Layout {
   int64_t revp;      // [W/8][AP][8]   Wp act rows, B operand of dE/dact
   int64_t total;
 };
+Packed16Layout make_packed16_layout(const Layout& L);     // langevin_f16.cu
 
 // MN-major tf32 operand layout (UMMA SWIZZLE_128B_BASE32B, layout type 1; the
 // only shared-memory layout tcgen05 accepts for MN-major 32-bit operands).
