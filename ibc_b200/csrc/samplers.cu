@@ -2,6 +2,8 @@
 // (bit-exact with the CPU multinomial), its gather/perturb, the Langevin
 // update, row softmax and uniform action init.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <functional>
 
@@ -324,6 +326,8 @@ resample_kernel(const float* __restrict__ logits, const double* __restrict__ uni
 // slice of the counts, learns its output offset from the lower slices' totals and writes its
 // part of `rows`.  Same draws, same counts, same rows as resample_kernel: integer arithmetic
 // after the (identical) CDF.  Dynamic smem: double cdf[n]; int cnt[slice]; tab; heavy.
+__device__ long long g_resample_dbg[16];    // IBC_DBG_TIMELINE: phase stamps of cluster 0, CTA 0
+
 __global__ void __launch_bounds__(1024)
 resample_cluster_kernel(const float* __restrict__ logits, const double* __restrict__ uniforms,
                         int n, int count, uint64_t seed, uint64_t rng_stream,
@@ -346,41 +350,71 @@ resample_cluster_kernel(const float* __restrict__ logits, const double* __restri
   __shared__ int s_ambiguous;
   __shared__ int s_nheavy;
   __shared__ int s_total;
+  __shared__ double s_slice_total;
   const int b = blockIdx.x / C;
   const int tid = threadIdx.x, nt = blockDim.x;
   const float* row = logits + (int64_t)b * n;
 
+  const bool stamp = blockIdx.x == 0 && tid == 0;
+  if (stamp) g_resample_dbg[0] = clock64();
   const double dmx = (double)block_row_max(row, n, s_red, &s_max);
   const double eps_rel = 8.0 * (double)n * 1.1102230246251565e-16;
   const bool use_tab = n >= 4 * kResampleBuckets;
   constexpr double kInvBuckets = 1.0 / kResampleBuckets;
-  cluster.sync();         // every CTA of the cluster is running: its shared memory may be written
+  if (stamp) g_resample_dbg[1] = clock64();
+  if (stamp) g_resample_dbg[2] = clock64();
   for (int pass = 0; pass < 2; ++pass) {
-    // weights: the fp64 exponentials are the longest serial piece on one SM (the fp64 pipe is
-    // busy ~9 us for 16 384 of them), so each CTA computes those of the classes it owns and
-    // stores them into every CTA's CDF array
-    for (int j = j0 + tid; j < j0 + m; j += nt) {
-      const float l = row[j];
-      const double w = isfinite(l) ? exp64_portable(__dadd_rn((double)l, -dmx)) : 0.0;
-      for (int r = 0; r < C; ++r) cluster.map_shared_rank(cdf, r)[j] = w;
-    }
     for (int j = tid; j < slice; j += nt) cnt[j] = 0;
     if (tid == 0) s_ambiguous = 0;
-    // all weights have landed, and every slice of the counts is zero before the first remote atomic
-    cluster.sync();
     if (pass == 0) {
-      block_scan_chunked(cdf, n, s_wd);
-    } else if (tid == 0) {
-      sequential_cdf(cdf, n);
+      // The fp64 pipe is the bottleneck of the CDF (exponentials, scan and index all run on
+      // it: 13 k cycles for a 16 384-entry scan on one SM), so each CTA exponentiates and scans
+      // only the classes it owns, learns its offset from the lower slices' totals (summed in
+      // slice order, so the CDF stays monotone across slices) and stores its part of the CDF
+      // into every CTA's array.  One more association of the same positive terms: the margin
+      // below covers it.
+      for (int j = j0 + tid; j < j0 + m; j += nt) {
+        const float l = row[j];
+        cdf[j] = isfinite(l) ? exp64_portable(__dadd_rn((double)l, -dmx)) : 0.0;
+      }
+      __syncthreads();
+      if (stamp) g_resample_dbg[3] = clock64();
+      block_scan_chunked(cdf + j0, m, s_wd);
+      if (tid == 0) s_slice_total = m > 0 ? cdf[j0 + m - 1] : 0.0;
+      cluster.sync();       // slice totals; every CTA is running and has zeroed its counts
+      if (stamp) g_resample_dbg[4] = clock64();
+      double offset = 0.0;
+      for (int r = 0; r < c; ++r) offset = __dadd_rn(offset, *cluster.map_shared_rank(&s_slice_total, r));
+      // (pulling the other slices with 16-byte loads instead was slower: 10.5 k against 8.4 k cycles)
+      for (int j = j0 + tid; j < j0 + m; j += nt) {
+        const double v = __dadd_rn(offset, cdf[j]);
+        for (int r = 0; r < C; ++r) cluster.map_shared_rank(cdf, r)[j] = v;
+      }
+      cluster.sync();       // the whole CDF has landed everywhere
+    } else {
+      // sequential fallback: weights everywhere, then the CPU kernel's left-to-right chain
+      for (int j = j0 + tid; j < j0 + m; j += nt) {
+        const float l = row[j];
+        const double w = isfinite(l) ? exp64_portable(__dadd_rn((double)l, -dmx)) : 0.0;
+        for (int r = 0; r < C; ++r) cluster.map_shared_rank(cdf, r)[j] = w;
+      }
+      cluster.sync();
+      if (tid == 0) sequential_cdf(cdf, n);
+      __syncthreads();
     }
-    __syncthreads();
+    if (stamp) g_resample_dbg[5] = clock64();
     const double total = n > 0 ? cdf[n - 1] : 0.0;
     const double eps = eps_rel * total;
     if (use_tab) {
-      for (int k = tid; k <= kResampleBuckets; k += nt)
-        tab[k] = upper_bound_range(cdf, 0, n, __dmul_rn((double)k * kInvBuckets, total));
+      // the value-space index, one share of the buckets per CTA, stored into every CTA's table
+      const int per = (kResampleBuckets + 1 + C - 1) / C;
+      for (int k = c * per + tid; k < min(kResampleBuckets + 1, (c + 1) * per); k += nt) {
+        const int t = upper_bound_range(cdf, 0, n, __dmul_rn((double)k * kInvBuckets, total));
+        for (int r = 0; r < C; ++r) cluster.map_shared_rank(tab, r)[k] = t;
+      }
+      cluster.sync();
     }
-    __syncthreads();
+    if (stamp) g_resample_dbg[6] = clock64();
 
     bool ambiguous = false;
     for (int s = c * nt + tid; s < count; s += C * nt) {
@@ -396,7 +430,9 @@ resample_cluster_kernel(const float* __restrict__ logits, const double* __restri
       atomicAdd(cluster.map_shared_rank(cnt, owner) + (lo - owner * slice), 1);
     }
     if (pass == 0 && ambiguous) s_ambiguous = 1;
+    if (stamp) g_resample_dbg[7] = clock64();
     cluster.sync();
+    if (stamp) g_resample_dbg[8] = clock64();
     int any = 0;          // one ambiguous draw anywhere sends the whole cluster to the sequential CDF
     for (int r = 0; r < C; ++r) any |= *cluster.map_shared_rank(&s_ambiguous, r);
     if (pass == 1 || !any) break;
@@ -408,12 +444,16 @@ resample_cluster_kernel(const float* __restrict__ logits, const double* __restri
     if (tid == 0) s_nheavy = 0;
     block_scan_inplace(cnt, m, s_wi);        // ends with __syncthreads()
     if (tid == 0) s_total = m > 0 ? cnt[m - 1] : 0;
+    if (stamp) g_resample_dbg[9] = clock64();
     cluster.sync();
+    if (stamp) g_resample_dbg[10] = clock64();
     int base = 0;
     for (int r = 0; r < c; ++r) base += *cluster.map_shared_rank(&s_total, r);
     write_runs(cnt, m, j0, base, (int64_t)b * n, rows + (int64_t)b * count, heavy, &s_nheavy);
   }
+  if (stamp) g_resample_dbg[11] = clock64();
   cluster.sync();         // no CTA leaves while a peer may still read its shared memory
+  if (stamp) g_resample_dbg[12] = clock64();
 }
 
 // out[r, :] = clip(src[rows[r], :] + normal * std, min, max)   (std == 0: copy)
@@ -574,6 +614,16 @@ int resample(ibc_handle* h, const float* logits, const double* uniforms, int64_t
       IBC_CUDA(h, cudaLaunchKernelEx(&cfg, resample_cluster_kernel, logits, uniforms, (int)n,
                                      (int)count, seed, rng_stream, draws, counts, rows));
       count_launch();
+      static const bool want_dbg = getenv("IBC_DBG_TIMELINE") != nullptr;
+      if (want_dbg) {
+        long long t[16];
+        cudaStreamSynchronize(s);
+        cudaMemcpyFromSymbol(t, g_resample_dbg, sizeof(t));
+        fprintf(stderr, "[ibc timeline resample C=%d] max %lld | - %lld | weights %lld | scan+sync %lld | offsets+sync %lld | tab+sync %lld | "
+                "draws %lld | sync %lld | counts+scan %lld | sync %lld | rows %lld | sync %lld\n", C,
+                t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[6],
+                t[8] - t[7], t[9] - t[8], t[10] - t[9], t[11] - t[10], t[12] - t[11]);
+      }
       return IBC_OK;
     }
   }
