@@ -518,6 +518,51 @@ softmax_rows_kernel(const float* __restrict__ logits, int n, float temperature,
   for (int j = tid; j < n; j += NT) out[j] = __fdiv_rn(out[j], inv);
 }
 
+// The same softmax on a thread-block cluster per row (policy inference: one row of 16 384
+// logits kept a single SM busy for 14 us, most of it IEEE divisions and expf in sequence): every
+// CTA takes a slice; the row maximum and the normaliser are exchanged over distributed shared
+// memory (slice sums added in slice order).
+__global__ void __launch_bounds__(1024)
+softmax_rows_cluster_kernel(const float* __restrict__ logits, int n, float temperature,
+                            float* __restrict__ probs) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = (int)cluster.num_blocks(), c = (int)cluster.block_rank();
+  const int slice = (n + C - 1) / C;
+  const int j0 = c * slice, j1 = min(n, j0 + slice);
+  __shared__ float s_red[32];
+  __shared__ float s_max, s_sum;
+  const int tid = threadIdx.x, nt = blockDim.x, nw = (nt + 31) >> 5;
+  const float* row = logits + (int64_t)(blockIdx.x / C) * n;
+  float* out = probs + (int64_t)(blockIdx.x / C) * n;
+  float mx = -INFINITY;
+  for (int j = j0 + tid; j < j1; j += nt) mx = fmaxf(mx, __fdiv_rn(row[j], temperature));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+  __syncthreads();
+  if (tid == 0) { float v = s_red[0]; for (int i = 1; i < nw; ++i) v = fmaxf(v, s_red[i]); s_max = v; }
+  cluster.sync();
+  mx = -INFINITY;
+  for (int r = 0; r < C; ++r) mx = fmaxf(mx, *cluster.map_shared_rank(&s_max, r));
+  float sum = 0.f;
+  for (int j = j0 + tid; j < j1; j += nt) {
+    const float e = expf(__fdiv_rn(row[j], temperature) - mx);
+    out[j] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((tid & 31) == 0) s_red[tid >> 5] = sum;
+  __syncthreads();
+  if (tid == 0) { float v = 0.f; for (int i = 0; i < nw; ++i) v += s_red[i]; s_sum = v; }
+  cluster.sync();
+  float total = 0.f;
+  for (int r = 0; r < C; ++r) total += *cluster.map_shared_rank(&s_sum, r);
+  for (int j = j0 + tid; j < j1; j += nt) out[j] = __fdiv_rn(out[j], total);
+  cluster.sync();         // no CTA leaves while a peer may still read its shared memory
+}
+
 __global__ void uniform_actions_kernel(const float* __restrict__ u, int64_t rows, int A,
                                        const float* __restrict__ mn, const float* __restrict__ mx,
                                        uint64_t seed, float* __restrict__ out) {
@@ -641,7 +686,29 @@ int resample(ibc_handle* h, const float* logits, const double* uniforms, int64_t
 int softmax_rows(ibc_handle* h, const float* logits, int64_t B, int64_t n, float temperature,
                  float* probs, cudaStream_t s) {
   if (B <= 0 || n <= 0) IBC_FAIL(h, IBC_ERR_INVALID, "softmax_rows: bad shape");
-  // few long rows (policy inference: one row of 16 384): more threads per row
+  // few long rows (policy inference: one row of 16 384): a cluster of eight CTAs per row
+  int sms = h ? h->sm_count : 0;
+  if (!h) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (n >= 8192 && B * 8 <= sms) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * 8));
+    cfg.blockDim = dim3(1024);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 8;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    IBC_CUDA(h, cudaLaunchKernelEx(&cfg, softmax_rows_cluster_kernel, logits, (int)n, temperature, probs));
+    count_launch();
+    return IBC_OK;
+  }
   if (n >= 4096) softmax_rows_kernel<1024><<<(unsigned)B, 1024, 0, s>>>(logits, (int)n, temperature, probs);
   else softmax_rows_kernel<256><<<(unsigned)B, 256, 0, s>>>(logits, (int)n, temperature, probs);
   IBC_LAUNCH_CHECK(h);
@@ -731,8 +798,22 @@ int dfo(ibc_handle* h, const float* obs, int64_t B, float* actions, int64_t n, c
         const float* mx, float temperature, int num_iterations, float iteration_std,
         const double* uniforms, const float* normals, uint64_t seed, float* probs,
         cudaStream_t s) {
+  // The observation does not change between the iterations: on the layer-fused tensor path its
+  // projection hp = obs . Wp[:O] + bp is computed once per call (a 7 us launch for one row).
+  const Layout& L = h->L;
+  const bool hoist = h->params && h->precision == IBC_PRECISION_TF32 && umma_supported(L) &&
+                     !wide_supported(L);
+  float* hp = nullptr;
+  int it = 0;
   auto energy_fn = [&](const float* acts, float* E) -> int {
-    return mlp_energy(h, obs, B, acts, n, E, s);
+    if (!hoist) return mlp_energy(h, obs, B, acts, n, E, s);
+    if (it++ == 0) {
+      IBC_CUDA(h, h->ws.reserve(Workspace::rounded((size_t)B * L.W * 4)));
+      h->ws.reset();
+      hp = h->ws.take<float>((size_t)B * L.W);
+      return umma_forward(h, obs, B, acts, n, hp, E, nullptr, nullptr, s);
+    }
+    return umma_forward_hp(h, acts, B * n, n, hp, E, nullptr, nullptr, s);
   };
   return dfo_generic(h, h->L.A, B, actions, n, mn, mx, temperature, num_iterations, iteration_std,
                      uniforms, normals, seed, probs, energy_fn, s);
