@@ -370,7 +370,13 @@ int ibc_umma_selftest(const float* A, const float* Bt, int32_t N, int32_t K,
  * uses (tape.gradient of ibc/agents/base_agent.py:43-48: dW = X^T dY with the rows as
  * the K dimension): D[128, N] = A[K, 128]^T . B[K, N], operands rounded to fp16, fp32
  * accumulate.  lbo / sbo / layout_type / kstep_bytes are the shared-memory descriptor
- * fields (0 = the library's own: umma_f16.cuh). */
+ * fields (0 = the library's own: umma_f16.cuh).
+ * layout_type >= 100 tests the K-major forms the kind::f16 chain GEMMs use (the dependent
+ * layers of mcmc.py:161-191 in langevin_f16.cu and mlp_bwd_wgrad.cu): D[128, N] =
+ * A[128, K] . B[N, K]^T with A, B given row-major (N <= 128), B a no-swizzle K-major image in
+ * shared memory; 100: A the same kind of image (SS form); 101: A in tensor memory, two
+ * K-elements per 32-bit column, even k in the low half (TS form, the one in use); 102: odd k
+ * low (must fail). */
 int ibc_umma_f16_selftest(const float* A, const float* B, int32_t N, int32_t K,
                           uint32_t lbo_a, uint32_t lbo_b, uint32_t sbo,
                           uint32_t layout_type, uint32_t kstep_bytes, float* D,

@@ -378,6 +378,29 @@ def test_fused_langevin_kernel_is_bit_identical_to_the_three_kernel_chain():
   assert digests[0] == digests[1]
 
 
+def test_umma_f16_operand_forms():
+  """The kind::f16 operand forms the kernels rely on, against fp16-rounded inputs in fp64: the
+  MN-major 128-byte-swizzle image of the weight-gradient GEMM (default), K-major no-swizzle
+  images from shared memory (100), and the A operand in tensor memory packed two K-elements per
+  column with even k in the low half (101: the chain GEMMs of langevin_f16.cu and
+  mlp_bwd_wgrad.cu).  The swapped packing (102) must NOT match: the test can tell them apart."""
+  from ibc_b200 import engine as eng
+  g = torch.Generator().manual_seed(0)
+  a = torch.randn(64, 128, generator=g); b = torch.randn(64, 128, generator=g)
+  d, st = eng.umma_f16_selftest(a.cuda(), b.cuda())
+  want = a.half().double().t() @ b.half().double()
+  assert st == 0 and float((d.double().cpu() - want).abs().max()) <= 1e-4 * float(want.abs().max())
+  for k, n in ((16, 64), (128, 128)):
+    a = torch.randn(128, k, generator=g); b = torch.randn(n, k, generator=g)
+    want = a.half().double() @ b.half().double().t()
+    err = {}
+    for mode in (100, 101, 102):
+      d, st = eng.umma_f16_selftest(a.reshape(k, 128).cuda(), b.reshape(k, n).cuda(), layout_type=mode)
+      assert st == 0
+      err[mode] = float((d.double().cpu() - want).abs().max()) / float(want.abs().max())
+    assert err[100] <= 1e-5 and err[101] <= 1e-5 and err[102] > 0.1, err
+
+
 def test_langevin_f16_chain_tracks_the_tf32_chain(monkeypatch):
   """langevin_f16.cu runs the chain's GEMMs in kind::f16 (the same 11-bit significand as tf32,
   fp32 accumulation; the reverse chain carried times a power of two per row) under sixteen
