@@ -109,8 +109,8 @@ struct BwdWgradParams {
   int nb, tiles;
   int* status;
   long long* dbg;
-  int dbg_mode;   // timing experiments (wrong results): 2 no park stores, 4 no column sums,
-                  // 8 no dY images, 16 plain (unhinted) park accesses
+  int dbg_mode;   // timing experiments (wrong results): 1 no park loads, 2 no park stores, 4 no column
+                  // sums, 8 no dY images, 256 no copies of the saved operands
 };
 
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
     for (int i = 0; i < 2; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     mbar_init(dy_full, kEpiWarps);
     mbar_init(dy_empty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 4 * 128); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     mbar_init(acc_done, 1);
     mbar_init(acc_free, kEpiWarps * 32);
     fence_mbar_init();
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
         // ago) is requested here, while the second chain MMA runs: v is free until the end of
         // the item (G' reads its accumulator through the 16 registers of w16), and the loads
         // are ahead of this item's 64 KB of park stores, which drain at the SM's ~32 B/clk.
-        const bool load_next = blk > 0 && k + 1 < ntile;
+        const bool load_next = blk > 0 && k + 1 < ntile && !(p.dbg_mode & 1);
         if (load_next) {
           const float4* pn = reinterpret_cast<const float4*>(p.gpark + tile_of(blk, k + 1) * (int64_t)TT::kTileFloats) +
                              cc * 8 * 128 + row;
@@ -411,15 +411,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
     }
   } else if (warp < kEpiWarps + 4) {
     // ===================== operand warps ===========================================
-    // Saved fp16 A sub-tiles ([chunk of 8][128 rows][16 B] in global memory) straight into
-    // the MN-major image with 16-byte asynchronous copies (the copy's destination address IS
-    // the re-arrangement): lane = row, so a warp reads 512 contiguous bytes and the 128-byte
-    // swizzle spreads a quarter-warp's eight rows over the eight 16-byte bank groups.
+    // The forward's saved fp16 tile of a (tile, layer) -- [chunk of 8 features][128 rows][16 B],
+    // 32 KB contiguous -- IS a valid MN-major operand image without swizzle: a core matrix is 8
+    // rows x 16 B, row groups 128 B apart (LBO), feature chunks 2 KB apart (SBO); validated on
+    // hardware (ibc_umma_f16_selftest mode 200).  So one bulk copy per (tile, layer) brings the A
+    // operand of its eight weight-gradient MMAs, on the TMA engine: the 16-byte cp.async copies
+    // that used to re-arrange it into a swizzled image went through the LSU, 128 warp
+    // instructions per item, and cost the kernel 0.066 ms (IBC_DBG_MODE=256).
     setmaxnreg_dec<kOpRegs>();
     const int ow = warp - kEpiWarps;
-    const uint64_t pol_stream = l2_policy_evict_first();
     const int nitems = p.nb * ntile;
-    const int nunits = nitems * 8;
     // L2 prefetch of a whole (tile, block)'s saved operands (two adjacent slots x 32 KB) by
     // the TMA engine, two (tile, block)s ahead: the copies below then hit L2 (~2 us from
     // HBM under load against the few hundred cycles the landing zones can cover)
@@ -442,29 +443,26 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
                        : "memory");
       }
     };
-    // The copies of a unit signal its a_full barrier themselves when they land
-    // (cp.async.mbarrier.arrive.noinc, one pending arrival per operand thread): nothing is
-    // published in software: one slot (four sub-tiles, 32 KB) lands while the weight-gradient
-    // MMAs work on the other.  The MMA issuer fences the proxies.
-    if (ow == 0 && lane == 0) { prefetch_item(0); prefetch_item(1); }
-    for (int u = 0; u < nunits; ++u) {
-      if ((u & 7) == 0 && ow == 0 && lane == 0) prefetch_item((u >> 3) + 2);
-      const int x = u & 7, T = u >> 3;
-      const int blk = T / ntile, k = T - blk * ntile, jb = p.nb - 1 - blk;
-      const int slot = (x < 4) ? 2 * jb + 1 : 2 * jb;
-      const int64_t tile = tile_of(blk, k);
-      const uint4* src = p.xa16 + (tile * nsl + slot) * (int64_t)(16 * 128) + (x & 3) * 32 + lane;
-      const int stage = u & (kAStages - 1), sstage = stage >> 2;     // slot stage = 4 sub-tiles
-      if ((u & 3) == 0)
-        mbar_wait(&a_empty[sstage], ((uint32_t)(u / kAStages) & 1u) ^ 1u, abort_flag, p.status, 1100);
-      const uint32_t img = smem_u32(amn + (size_t)stage * kImgBytes);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c8 = ow * 4 + i;
-        cp_async16(img + ImgF16::piece(lane, c8, 32), src + c8 * 128, pol_stream);
+    if (ow == 0) {
+      if (lane == 0) { prefetch_item(0); prefetch_item(1); }
+      for (int u = 0; u < 2 * nitems; ++u) {       // unit = (item, half): slot 2jb+1 (dW2), then 2jb (dW1)
+        const int T = u >> 1, half = u & 1;
+        const int blk = T / ntile, k = T - blk * ntile, jb = p.nb - 1 - blk;
+        const int64_t tile = tile_of(blk, k);
+        const uint4* src = p.xa16 + (tile * nsl + (half ? 2 * jb : 2 * jb + 1)) * (int64_t)(16 * 128);
+        const int st = u & 1;
+        if (elect_one()) {
+          if (half == 0) prefetch_item(T + 2);
+          mbar_wait(&a_empty[st], ((uint32_t)(u >> 1) & 1u) ^ 1u, abort_flag, p.status, 1100);
+          mbar_arrive_expect_tx(&a_full[st], 4u * kImgBytes);
+          if (p.dbg_mode & 256) {
+            asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&a_full[st])), "r"(4u * kImgBytes) : "memory");
+          } else {
+            bulk_g2s(amn + (size_t)st * 4 * kImgBytes, src, 4u * kImgBytes, &a_full[st]);
+          }
+        }
+        __syncwarp();
       }
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&a_full[sstage]))
-                   : "memory");
     }
   } else if (warp == kEpiWarps + 4) {
     // ===================== producer: the block's two transposed weights =============
@@ -535,17 +533,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
             if (wstamp) wd[1] = clock64();
             mbar_wait(&a_full[(u >> 2) & 1], (u / kAStages) & 1u, abort_flag, p.status, 1402);
             if (wstamp) wd[2] = clock64();
-            fence_proxy_async_smem();      // the A images were written by cp.async (generic proxy)
             tc_fence_after();
             const uint32_t acc = tmem_base + (uint32_t)((2 + half) * W);
+            // A: the saved tile as it is (MN-major, no swizzle: LBO 128 B between 8-row groups,
+            // SBO 2 KB between feature chunks), 16 rows = 256 B per MMA; B: the four swizzled
+            // 32-row dY images
+            const uint64_t ad0 = smem_desc_lt(smem_u32(amn + (size_t)((u >> 2) & 1) * 4 * kImgBytes), 128u, 2048u, 0);
 #pragma unroll
             for (int sub = 0; sub < 4; ++sub) {
-              const uint32_t stage = (u + sub) & (kAStages - 1);
-              const uint64_t ad0 = smem_desc_lt(smem_u32(amn + (size_t)stage * kImgBytes), lbo, ImgF16::kSbo, 2);
               const uint64_t bd0 = smem_desc_lt(smem_u32(dyb + (size_t)sub * kImgBytes), lbo, ImgF16::kSbo, 2);
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks)
-                mma_f16_ss(acc, ad0 + (uint64_t)(ks * (2 * ImgF16::kSbo >> 4)),
+                mma_f16_ss(acc, ad0 + (uint64_t)((sub * 2 + ks) * (256 >> 4)),
                            bd0 + (uint64_t)(ks * (2 * ImgF16::kSbo >> 4)), idesc,
                            (uint32_t)(k > 0 || sub > 0 || ks > 0));
             }
@@ -677,7 +676,8 @@ umma_f16_probe_kernel(const float* __restrict__ A, const float* __restrict__ B, 
       const float* s = A + (int64_t)r * 128 + c * 8;
       v.x = pack_half2(s[0], s[1]); v.y = pack_half2(s[2], s[3]);
       v.z = pack_half2(s[4], s[5]); v.w = pack_half2(s[6], s[7]);
-      *reinterpret_cast<uint4*>(a_img + ImgF16::piece(r, c, K)) = v;
+      if (layout_type >= 200) *reinterpret_cast<uint4*>(a_img + (size_t)c * K * 16 + (size_t)r * 16) = v;
+      else *reinterpret_cast<uint4*>(a_img + ImgF16::piece(r, c, K)) = v;
     }
     for (int c = 0; c < N / 8; ++c) {
       uint4 v;
@@ -694,10 +694,20 @@ umma_f16_probe_kernel(const float* __restrict__ A, const float* __restrict__ B, 
   const uint32_t tmem_base = tmem_slot;
   if (tid == 0) {
     const uint32_t idesc = idesc_f16(128, N) | kIdescAMajorMN | kIdescBMajorMN;
-    const uint64_t ad0 = smem_desc_lt(smem_u32(a_img), lbo_a, sbo, layout_type);
-    const uint64_t bd0 = smem_desc_lt(smem_u32(b_img), lbo_b, sbo, layout_type);
+    // layout_type 200 / 201: A as the plain saved-tile layout [chunk of 8 MN][K rows][16 B] =
+    // MN-major without swizzle (core matrix = 8 K-rows x 16 B, contiguous); 200: LBO = 128
+    // (K groups), SBO = 16 K (MN chunks); 201: the two swapped.  B stays the swizzled image.
+    const bool plain_a = layout_type >= 200;
+    const uint32_t a_lbo = plain_a ? (layout_type == 200 ? 128u : (uint32_t)K * 16u) : lbo_a;
+    const uint32_t a_sbo = plain_a ? (layout_type == 200 ? (uint32_t)K * 16u : 128u) : sbo;
+    const uint32_t b_lt = plain_a ? 2u : layout_type;
+    const uint32_t b_lbo = plain_a ? ImgF16::lbo(K) : lbo_b, b_sbo = plain_a ? ImgF16::kSbo : sbo;
+    const uint32_t b_step = plain_a ? 2 * ImgF16::kSbo : kstep_bytes;
+    const uint32_t a_step = plain_a ? 256u : kstep_bytes;
+    const uint64_t ad0 = smem_desc_lt(smem_u32(a_img), a_lbo, a_sbo, plain_a ? 0u : layout_type);
+    const uint64_t bd0 = smem_desc_lt(smem_u32(b_img), b_lbo, b_sbo, b_lt);
     for (int ks = 0; ks < K / 16; ++ks)
-      mma_f16_ss(tmem_base, ad0 + (uint64_t)(ks * (kstep_bytes >> 4)), bd0 + (uint64_t)(ks * (kstep_bytes >> 4)),
+      mma_f16_ss(tmem_base, ad0 + (uint64_t)(ks * (a_step >> 4)), bd0 + (uint64_t)(ks * (b_step >> 4)),
                  idesc, (uint32_t)(ks > 0));
     mma_commit(&bar);
   }
@@ -800,7 +810,7 @@ int umma_f16_selftest(const float* A, const float* B, int N, int K, uint32_t lbo
   ibc_handle* h = nullptr;
   if (N < 64 || N > 256 || (N % 64) || K < 16 || K > 128 || (K % 16))
     IBC_FAIL(h, IBC_ERR_INVALID, "umma_f16_selftest: need N in {64,128,192,256}, K a multiple of 16 <= 128");
-  if (layout_type >= 100) {      // K-major operands, A from shared or tensor memory (see the kernel)
+  if (layout_type >= 100 && layout_type < 200) {      // K-major operands, A from shared or tensor memory (see the kernel)
     if (N > 128) IBC_FAIL(h, IBC_ERR_INVALID, "umma_f16_selftest: K-major modes need N <= 128");
     int* st = nullptr;
     IBC_CUDA(h, cudaMalloc((void**)&st, sizeof(int)));
@@ -822,7 +832,7 @@ int umma_f16_selftest(const float* A, const float* B, int N, int K, uint32_t lbo
   if (!lbo_a) lbo_a = ImgF16::lbo(K);
   if (!lbo_b) lbo_b = ImgF16::lbo(K);
   if (!sbo) sbo = ImgF16::kSbo;
-  if (!layout_type) layout_type = 2;          // SWIZZLE_128B
+  if (!layout_type) layout_type = 2;          // SWIZZLE_128B (200 / 201: see the kernel)
   if (!kstep_bytes) kstep_bytes = 2 * ImgF16::kSbo;   // K = 16 per MMA = two 8-row atoms
   int* st = nullptr;
   IBC_CUDA(h, cudaMalloc((void**)&st, sizeof(int)));

@@ -27,3 +27,14 @@ for k, n in ((16, 64), (32, 128), (128, 128)):
     d, st = eng.umma_f16_selftest(a.reshape(k, 128).cuda(), b.reshape(k, n).cuda(), layout_type=mode)
     err = (d.double().cpu() - want).abs().max().item()
     print('K=%d N=%d mode %d status %d max err %.3g (|want| max %.3g)' % (k, n, mode, st, err, want.abs().max().item()), flush=True)
+
+# MN-major A WITHOUT swizzle: the forward's saved-tile layout [chunk of 8][rows][16 B] as is
+print('MN-major no-swizzle A probes: 200 = LBO 128 / SBO 16 K, 201 = swapped')
+for k, n in ((32, 128), (128, 128)):
+  a = torch.randn(k, 128, generator=g)
+  b = torch.randn(k, n, generator=g)
+  want = a.half().double().t() @ b.half().double()
+  for mode in (200, 201):
+    d, st = eng.umma_f16_selftest(a.cuda(), b.cuda(), layout_type=mode)
+    err = (d.double().cpu() - want).abs().max().item()
+    print('K=%d N=%d mode %d status %d max err %.3g (|want| max %.3g)' % (k, n, mode, st, err, want.abs().max().item()), flush=True)
