@@ -74,8 +74,9 @@ constexpr int kKSteps = kW / 16;                   // kind::f16: K = 16 per MMA
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = (kEpiWarps + 8) * 32;
 // 768 threads start with 80 registers; the CTA's pool is redistributed by setmaxnreg
-constexpr int kEpiRegs = 88, kOpRegs = 56, kServiceRegs = 72;
-constexpr int kAStages = 8;                        // A images (cp.async landing zones): 64 KB
+constexpr int kEpiRegs = 96, kOpRegs = 32, kServiceRegs = 64;
+constexpr int kASlots = 1;                         // saved-tile landing zones (32 KB each): see below
+constexpr int kAStages = 4 * kASlots;              // in 8 KB sub-tile images
 constexpr int kDbgWords = 2048;
 
 constexpr size_t kOffW = 0;                                        // [2][32 KB]  W2_j^T, W1_j^T (fp16)
@@ -450,10 +451,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
         const int blk = T / ntile, k = T - blk * ntile, jb = p.nb - 1 - blk;
         const int64_t tile = tile_of(blk, k);
         const uint4* src = p.xa16 + (tile * nsl + (half ? 2 * jb : 2 * jb + 1)) * (int64_t)(16 * 128);
-        const int st = u & 1;
+        const int st = u % kASlots;
         if (elect_one()) {
           if (half == 0) prefetch_item(T + 2);
-          mbar_wait(&a_empty[st], ((uint32_t)(u >> 1) & 1u) ^ 1u, abort_flag, p.status, 1100);
+          mbar_wait(&a_empty[st], ((uint32_t)(u / kASlots) & 1u) ^ 1u, abort_flag, p.status, 1100);
           mbar_arrive_expect_tx(&a_full[st], 4u * kImgBytes);
           if (p.dbg_mode & 256) {
             asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&a_full[st])), "r"(4u * kImgBytes) : "memory");
@@ -531,14 +532,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
               mbar_wait(acc_free, (uint32_t)(blk - 1) & 1u, abort_flag, p.status, 1400);
             mbar_wait(dy_full, (uint32_t)half, abort_flag, p.status, 1401);
             if (wstamp) wd[1] = clock64();
-            mbar_wait(&a_full[(u >> 2) & 1], (u / kAStages) & 1u, abort_flag, p.status, 1402);
+            mbar_wait(&a_full[(u >> 2) % kASlots], ((u >> 2) / kASlots) & 1u, abort_flag, p.status, 1402);
             if (wstamp) wd[2] = clock64();
             tc_fence_after();
             const uint32_t acc = tmem_base + (uint32_t)((2 + half) * W);
             // A: the saved tile as it is (MN-major, no swizzle: LBO 128 B between 8-row groups,
             // SBO 2 KB between feature chunks), 16 rows = 256 B per MMA; B: the four swizzled
             // 32-row dY images
-            const uint64_t ad0 = smem_desc_lt(smem_u32(amn + (size_t)((u >> 2) & 1) * 4 * kImgBytes), 128u, 2048u, 0);
+            const uint64_t ad0 = smem_desc_lt(smem_u32(amn + (size_t)((u >> 2) % kASlots) * 4 * kImgBytes), 128u, 2048u, 0);
 #pragma unroll
             for (int sub = 0; sub < 4; ++sub) {
               const uint64_t bd0 = smem_desc_lt(smem_u32(dyb + (size_t)sub * kImgBytes), lbo, ImgF16::kSbo, 2);
@@ -548,7 +549,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
                            bd0 + (uint64_t)(ks * (2 * ImgF16::kSbo >> 4)), idesc,
                            (uint32_t)(k > 0 || sub > 0 || ks > 0));
             }
-            mma_commit(&a_empty[(u >> 2) & 1]);
+            mma_commit(&a_empty[(u >> 2) % kASlots]);
             mma_commit(dy_empty);
             if (k == ntile - 1 && half == 1) mma_commit(acc_done);
             if (wstamp) wd[3] = clock64();
