@@ -80,14 +80,14 @@ constexpr int kAStages = 4 * kASlots;              // in 8 KB sub-tile images
 constexpr int kDbgWords = 2048;
 
 constexpr size_t kOffW = 0;                                        // [2][32 KB]  W2_j^T, W1_j^T (fp16)
-constexpr size_t kOffDy = kOffW + 2 * (size_t)kLayerWBytes;        // [4][8 KB]   dY images, one per sub-tile
-constexpr size_t kOffA = kOffDy + 4 * (size_t)kImgBytes;           // [8][8 KB]   A images
+constexpr size_t kOffDy = kOffW + 2 * (size_t)kLayerWBytes;        // [2][4][8 KB] dY images (g | u), one per sub-tile
+constexpr size_t kOffA = kOffDy + 8 * (size_t)kImgBytes;           // saved-tile landing zones
 constexpr size_t kOffWe = kOffA + kAStages * (size_t)kImgBytes;    // we[128], scale, 1 / scale
 constexpr size_t kOffBars = kOffWe + (kW + 4) * 4;
 // a_ready, d_ready, w_full[2], w_empty[2], dy_full, dy_empty, a_full[2], a_empty[2],
 // acc_done, acc_free.  (A passed mbarrier wait still costs 150-300 cycles; the weight-gradient
 // issuer waited on 8-9 per batch of eight MMAs before the four sub-tiles of a slot shared one.)
-constexpr int kNumBars = 2 + 4 + 2 + 4 + 2;
+constexpr int kNumBars = 2 + 4 + 4 + 4 + 2;
 constexpr size_t kSmemBytes = kOffBars + kNumBars * 8 + 16;
 static_assert(kSmemBytes <= 227 * 1024 - 1024, "shared memory budget");
 
@@ -199,12 +199,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
   uint64_t* d_ready = bars + 1;       // commit: chain accumulator complete
   uint64_t* w_full = bars + 2;        // [2] weights of this block landed
   uint64_t* w_empty = bars + 4;       // [2] last chain MMA of the block has read them
-  uint64_t* dy_full = bars + 6;       // the tile's dY image written (16 epilogue warps)
-  uint64_t* dy_empty = bars + 7;      // its MMAs done
-  uint64_t* a_full = bars + 8;        // [2] a slot's four A images landed (4 x 128 cp.async arrivals)
-  uint64_t* a_empty = bars + 10;      // [2] its MMAs done
-  uint64_t* acc_done = bars + 12;     // commit: the block's last weight-gradient MMA
-  uint64_t* acc_free = bars + 13;     // epilogue threads: accumulators flushed
+  uint64_t* dy_full = bars + 6;       // [2] the tile's dY image (g | u) written (16 epilogue warps)
+  uint64_t* dy_empty = bars + 8;      // [2] its MMAs done
+  uint64_t* a_full = bars + 10;       // [2] a slot's four A images landed (4 x 128 cp.async arrivals)
+  uint64_t* a_empty = bars + 12;      // [2] its MMAs done
+  uint64_t* acc_done = bars + 14;     // commit: the block's last weight-gradient MMA
+  uint64_t* acc_free = bars + 15;     // epilogue threads: accumulators flushed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   __shared__ int s_abort;
 
@@ -223,8 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
     mbar_init(a_ready, kEpiWarps);        // one arrival per epilogue warp
     mbar_init(d_ready, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    mbar_init(dy_full, kEpiWarps);
-    mbar_init(dy_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&dy_full[i], kEpiWarps); mbar_init(&dy_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     mbar_init(acc_done, 1);
     mbar_init(acc_free, kEpiWarps * 32);
@@ -260,7 +259,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
     const int row = wq * 32 + lane;
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     const uint32_t col_x = tmem_base + lane_off + (uint32_t)(cc * 32), col_y = col_x + W;
-    unsigned char* dy_img = dyb + (size_t)wq * kImgBytes;
+    unsigned char* dy_img = dyb + (size_t)wq * kImgBytes;       // g image; u image 4 sub-tiles further
+    uint32_t item = 0;                                          // items done: the images' barrier phase
     const float scale = we[W], inv_scale = we[W + 1];
     const uint64_t pol_keep = l2_policy_evict_last();
     uint32_t ph_d = 0;
@@ -302,11 +302,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
         __syncwarp();
         if (lane == 0) mbar_arrive(a_ready);
         if (stamp) dbg[2] = clock64();
-        mbar_wait(dy_empty, 1, abort_flag, p.status, 1000);          // previous u image consumed
+        mbar_wait(&dy_empty[0], (item & 1u) ^ 1u, abort_flag, p.status, 1000);   // previous g image consumed
         if (!(p.dbg_mode & 8)) sts_image_f16(dy_img, lane, cc, w16);
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(dy_full);
+        if (lane == 0) mbar_arrive(&dy_full[0]);
         if (!(p.dbg_mode & 4)) bsum_g += warp_colsum32(v, lane);
         if (blk == 0) {
           // Dense(1) weight gradient: dwe += dE (x) h_nb, this row's chunk of the forward's last slot
@@ -338,11 +338,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
         __syncwarp();
         if (lane == 0) mbar_arrive(a_ready);
         if (stamp) dbg[4] = clock64();
-        mbar_wait(dy_empty, 0, abort_flag, p.status, 1002);          // g image consumed
-        if (!(p.dbg_mode & 8)) sts_image_f16(dy_img, lane, cc, w16);
+        mbar_wait(&dy_empty[1], (item & 1u) ^ 1u, abort_flag, p.status, 1002);   // previous u image consumed
+        if (!(p.dbg_mode & 8)) sts_image_f16(dy_img + 4 * kImgBytes, lane, cc, w16);
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(dy_full);
+        if (lane == 0) mbar_arrive(&dy_full[1]);
+        ++item;
         if (stamp) dbg[5] = clock64();
         if (!(p.dbg_mode & 4)) bsum_u += warp_colsum32(v, lane);
 
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
             if (wstamp) wd[0] = clock64();
             if (blk > 0 && k == 0 && half == 0)
               mbar_wait(acc_free, (uint32_t)(blk - 1) & 1u, abort_flag, p.status, 1400);
-            mbar_wait(dy_full, (uint32_t)half, abort_flag, p.status, 1401);
+            mbar_wait(&dy_full[half], (u >> 3) & 1u, abort_flag, p.status, 1401);
             if (wstamp) wd[1] = clock64();
             mbar_wait(&a_full[(u >> 2) % kASlots], ((u >> 2) / kASlots) & 1u, abort_flag, p.status, 1402);
             if (wstamp) wd[2] = clock64();
@@ -542,7 +543,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
             const uint64_t ad0 = smem_desc_lt(smem_u32(amn + (size_t)((u >> 2) % kASlots) * 4 * kImgBytes), 128u, 2048u, 0);
 #pragma unroll
             for (int sub = 0; sub < 4; ++sub) {
-              const uint64_t bd0 = smem_desc_lt(smem_u32(dyb + (size_t)sub * kImgBytes), lbo, ImgF16::kSbo, 2);
+              const uint64_t bd0 = smem_desc_lt(smem_u32(dyb + (size_t)(half * 4 + sub) * kImgBytes), lbo, ImgF16::kSbo, 2);
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks)
                 mma_f16_ss(acc, ad0 + (uint64_t)((sub * 2 + ks) * (256 >> 4)),
@@ -550,7 +551,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
                            (uint32_t)(k > 0 || sub > 0 || ks > 0));
             }
             mma_commit(&a_empty[(u >> 2) % kASlots]);
-            mma_commit(dy_empty);
+            mma_commit(&dy_empty[half]);
             if (k == ntile - 1 && half == 1) mma_commit(acc_done);
             if (wstamp) wd[3] = clock64();
           }
