@@ -36,7 +36,7 @@ constexpr int kLayerWBytes = kW * kW * 4;
 constexpr int kBiasBytes = 8 * kW * 4;
 constexpr int kLayerBytes = kLayerWBytes + kBiasBytes;   // 68 KB
 constexpr int kKSteps = kW / 8;
-constexpr int kRing = 3;
+constexpr int kRing = 2;     // two layers of prefetch keep the pipe fed; a third only takes L1 away from the spills
 constexpr int kEpiWarps = 8 * kNT;
 constexpr int kThreads = (kEpiWarps + 4) * 32;           // + producer, two issuers, one idle warp
 // 640 threads launch with 96 registers (61 440 in the CTA's pool); setmaxnreg then gives the
@@ -59,7 +59,7 @@ struct FwdHalvesParams {
   long long* dbg;
 };
 
-// ring (3 x 68 KB) | step-0 operand (KP x W) | ones tile (4 KB) | we, be | partial energies | barriers
+// ring (2 x 68 KB) | step-0 operand (KP x W) | ones tile (4 KB) | we, be | partial energies | barriers
 inline size_t halves_smem_bytes(int KP) {
   return (size_t)kRing * kLayerBytes + (size_t)KP * kW * 4 + 4096 + (kW + 4) * 4 + kNT * 128 * 4 +
          (size_t)(2 * kNT + 2 * kRing + 1) * 8 + 64;
