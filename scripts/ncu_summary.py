@@ -29,6 +29,7 @@ def main():
   with open(out_csv, 'w', newline='') as f:
     w = csv.writer(f)
     w.writerow(['id', 'kernel'] + [m for m, _ in cols])
+    w.writerow(['', '(units)'] + [rows[1][i] for _, i in cols])
     for r in data:
       w.writerow([r[0], r[name_i][:70]] + [r[i] for _, i in cols])
   if len(sys.argv) > 3:
@@ -42,13 +43,21 @@ def main():
         return None
       rd = float(r[hdr.index('dram__bytes_read.sum')].replace(',', ''))
       wr = float(r[hdr.index('dram__bytes_write.sum')].replace(',', ''))
-      unit_r = rows[1][hdr.index('dram__bytes_read.sum')]
-      scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(unit_r, 1)
-      return (rd + wr) * scale
+      units = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}      # one unit per COLUMN
+      return (rd * units.get(rows[1][hdr.index('dram__bytes_read.sum')], 1) +
+              wr * units.get(rows[1][hdr.index('dram__bytes_write.sum')], 1))
     out = {'forward': traffic(first('mlp_fwd_halves_kernel<2>')), 'forward_nosave': traffic(first('mlp_fwd_halves_kernel<0>')),
            'backward': traffic(first('mlp_bwd_wgrad_tmem_kernel')), 'info_nce': traffic(first('info_nce_kernel')),
            'first_layer': traffic(first('first_layer_grads_tiled_kernel')),
            'source': out_csv, 'unit': 'bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)'}
+    if out['forward_nosave'] is None:     # the energy forward has its own capture: keep its entry
+      try:
+        prev = json.load(open(sys.argv[3]))
+        for k in ('forward_nosave', 'forward_nosave_source'):
+          if prev.get(k) is not None:
+            out[k] = prev[k]
+      except (OSError, ValueError):
+        pass
     json.dump(out, open(sys.argv[3], 'w'), indent=1)
     print(out)
 
