@@ -422,6 +422,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
     // instructions per item, and cost the kernel 0.066 ms (IBC_DBG_MODE=256).
     setmaxnreg_dec<kOpRegs>();
     const int ow = warp - kEpiWarps;
+    const uint64_t pol_stream = l2_policy_evict_first();     // read once: do not displace the parked tiles
     const int nitems = p.nb * ntile;
     // L2 prefetch of a whole (tile, block)'s saved operands (two adjacent slots x 32 KB) by
     // the TMA engine, two (tile, block)s ahead: the copies below then hit L2 (~2 us from
@@ -460,7 +461,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
           if (p.dbg_mode & 256) {
             asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&a_full[st])), "r"(4u * kImgBytes) : "memory");
           } else {
-            bulk_g2s(amn + (size_t)st * 4 * kImgBytes, src, 4u * kImgBytes, &a_full[st]);
+            bulk_g2s_hint(amn + (size_t)st * 4 * kImgBytes, src, 4u * kImgBytes, &a_full[st], pol_stream);
           }
         }
         __syncwarp();

@@ -87,6 +87,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
       : "memory");
 }
 
+// ... with an L2 eviction-priority policy (createpolicy) for the lines it reads
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                              uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+
 // ---- bulk async copy shared -> global (TMA engine, 1-D, bulk-group completion) --
 // The issuing thread's generic-proxy writes (and, behind a barrier, other threads') must be
 // made visible to the async proxy with fence_proxy_async_smem() before the copy is issued.
