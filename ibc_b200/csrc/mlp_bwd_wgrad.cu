@@ -131,6 +131,11 @@ __device__ __forceinline__ float4 ldg_hint(const float4* ptr, uint64_t pol) {
                : "l"(ptr), "l"(pol));
   return v;
 }
+__device__ __forceinline__ uint32_t ldg_u32_hint(const uint32_t* ptr, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
+  return v;
+}
 __device__ __forceinline__ void red_add_v4(float* ptr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
@@ -263,6 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
     uint32_t item = 0;                                          // items done: the images' barrier phase
     const float scale = we[W], inv_scale = we[W + 1];
     const uint64_t pol_keep = l2_policy_evict_last();
+    const uint64_t pol_once = l2_policy_evict_first();
     uint32_t ph_d = 0;
     float gr[32];                      // gradient of the residual stream: this row, this chunk
     float bsum_g = 0.f, bsum_u = 0.f;  // lane l: column 32 cc + l of db2_j / db1_j over this CTA's rows
@@ -276,8 +282,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
         const bool stamp = p.dbg && blockIdx.x == 0 && tid == 0 && (blk * ntile + k) < 24;
         long long* dbg = stamp ? p.dbg + (blk * ntile + k) * 8 : nullptr;
         if (stamp) dbg[0] = clock64();
-        const uint32_t m1 = p.mask_save[TT::mask_index(tile, p.nb, 2 * jb + 1, row) + cc];
-        const uint32_t m0 = p.mask_save[TT::mask_index(tile, p.nb, 2 * jb, row) + cc];
+        // read once: evict-first, so that they do not displace the parked tiles in L2
+        const uint32_t m1 = ldg_u32_hint(p.mask_save + TT::mask_index(tile, p.nb, 2 * jb + 1, row) + cc, pol_once);
+        const uint32_t m0 = ldg_u32_hint(p.mask_save + TT::mask_index(tile, p.nb, 2 * jb, row) + cc, pol_once);
         float4* park = reinterpret_cast<float4*>(p.gpark + tile * (int64_t)TT::kTileFloats) +
                        cc * 8 * 128 + row;
         uint32_t v[32];
@@ -314,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
                                cc * 8 * 128 + row;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 x = __ldg(hrow + q * 128);
+            const float4 x = ldg_hint(hrow + q * 128, pol_once);
             v[q * 4 + 0] = __float_as_uint(de * x.x); v[q * 4 + 1] = __float_as_uint(de * x.y);
             v[q * 4 + 2] = __float_as_uint(de * x.z); v[q * 4 + 3] = __float_as_uint(de * x.w);
           }
