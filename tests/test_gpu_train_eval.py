@@ -117,6 +117,8 @@ def test_checkpoint_resume_and_validation_loss(tmp_path):
   # that lost the moments, the step count or an RNG stream trains on for 30 steps of lr = 1e-3
   # from a different state: differences of 1e-3 .. 1e-2 on most entries.
   d = (a - b).abs()
-  assert float(d.median()) <= 1e-5 and float((d > 1e-4).float().mean()) <= 0.02, (
+  # (the noise-driven entries -- be and the 64 of b2 -- are 2.4 % of this net's parameters: the
+  # fraction above 1e-4 comes out at either ~0 or 0.0243 depending on the run)
+  assert float(d.median()) <= 1e-5 and float((d > 1e-4).float().mean()) <= 0.05, (
       float(d.median()), float((d > 1e-4).float().mean()))
   assert float(d[:-1].max()) <= 2e-3 and float(d[-1]) <= 60 * 1e-3, float(d.max())
