@@ -94,6 +94,8 @@ SIGNATURES = {
                                  c_void_p]),
     'ibc_uniform_actions': (c_int, [c_void_p, c_int64, c_int32, c_void_p,
                                     c_void_p, c_uint64, c_void_p, c_void_p]),
+    'ibc_counter_examples_uniform': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
+                                             c_uint64, c_void_p, c_void_p, c_void_p]),
     'ibc_info_nce': (c_int, [c_void_p, c_int64, c_int64, c_float, c_float,
                              c_void_p, c_void_p, c_void_p]),
     'ibc_grad_penalty_from_dact': (c_int, [c_void_p, c_int64, c_int64, c_int32,
@@ -102,6 +104,7 @@ SIGNATURES = {
     'ibc_train_grads': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                 POINTER(LossCfg), c_int64, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p]),
+    'ibc_stream_wait_loss': (c_int, [c_void_p, c_void_p, POINTER(c_int32)]),
     'ibc_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                               c_float, c_float, c_float, c_float, c_void_p]),
     'ibc_pixel_create': (c_int, [POINTER(PixelArch), c_int, POINTER(c_void_p)]),

@@ -81,6 +81,7 @@ int ibc_destroy(ibc_handle* h) {
     cudaDeviceSynchronize();
     if (h->packed) cudaFree(h->packed);
     if (h->packed16) cudaFree(h->packed16);
+    if (h->loss_event) cudaEventDestroy(h->loss_event);
     if (h->dev_status) cudaFree(h->dev_status);
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (auto& g : h->langevin_graphs) g.release();
@@ -225,6 +226,16 @@ int ibc_uniform_actions(const float* u, int64_t rows, int32_t A, const float* mi
   return uniform_actions(h, u, rows, A, min_actions, max_actions, seed, out, (cudaStream_t)stream);
 }
 
+int ibc_counter_examples_uniform(const float* u, int64_t B, int64_t N, int32_t A,
+                                 const float* min_actions, const float* max_actions, uint64_t seed,
+                                 const float* actions, float* combined, void* stream) {
+  ibc_handle* h = nullptr;
+  if (!min_actions || !max_actions || !actions || !combined || B < 0 || N < 0 || A < 1)
+    IBC_FAIL(h, IBC_ERR_INVALID, "ibc_counter_examples_uniform: bad argument");
+  return uniform_combined(h, u, B, N, A, min_actions, max_actions, seed, actions, combined,
+                          (cudaStream_t)stream);
+}
+
 int ibc_info_nce(const float* predictions, int64_t B, int64_t n1, float temperature,
                  float grad_scale, float* loss, float* dpred, void* stream) {
   ibc_handle* h = nullptr;
@@ -254,12 +265,21 @@ int ibc_train_grads(ibc_handle* h, const float* obs, int64_t B, const float* act
   if (cfg->softmax_temperature <= 0.f)
     IBC_FAIL(h, IBC_ERR_INVALID, "ibc_train_grads: softmax_temperature must be > 0");
   const bool gp = cfg->add_grad_penalty != 0 && cfg->grad_norm_type != IBC_NORM_NONE;
+  h->loss_event_recorded = false;
   if (h->precision == IBC_PRECISION_TF32 && umma_train_supported(h->L) && !gp)
     return train_grads_umma(h, obs, B, actions, N, *cfg, global_batch, per_example_loss,
                             grad_loss, energies, grads, (cudaStream_t)stream);
   // gradient penalty (second order) and other widths: fp32 path
   return train_grads_fp32(h, obs, B, actions, N, *cfg, global_batch, per_example_loss, grad_loss,
                           energies, grads, (cudaStream_t)stream);
+}
+
+int ibc_stream_wait_loss(ibc_handle* h, void* stream, int32_t* recorded) {
+  IBC_ENTER(h);
+  if (!recorded) IBC_FAIL(h, IBC_ERR_INVALID, "ibc_stream_wait_loss: null argument");
+  *recorded = (h->loss_event && h->loss_event_recorded) ? 1 : 0;
+  if (*recorded) IBC_CUDA(h, cudaStreamWaitEvent((cudaStream_t)stream, h->loss_event, 0));
+  return IBC_OK;
 }
 
 int ibc_adam_step(float* params, const float* grads, float* m, float* v, int64_t count, float lr_t,

@@ -109,6 +109,10 @@ struct ibc_handle {
   float* packed = nullptr;        // tcgen05 operand copies of the weights
   size_t packed_bytes = 0;
   void* packed16 = nullptr;       // fp16 operand copies (width 128, langevin_f16.cu)
+  // Recorded on the stream of the last ibc_train_grads right behind its loss kernel (the
+  // per-example losses are final; the backward follows): ibc_stream_wait_loss
+  cudaEvent_t loss_event = nullptr;
+  bool loss_event_recorded = false;
   int* dev_status = nullptr;      // kernel-side barrier-timeout flag
   bool profiling = false;         // record CUDA events around the training kernels
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -976,6 +976,10 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
                    fused_bwd ? de_absmax : nullptr));
   if (grad_loss_out) IBC_CUDA(h, cudaMemsetAsync(grad_loss_out, 0, (size_t)B * 4, s));
   (void)gl;
+  // the per-example losses are final: a caller may read the loss while the backward runs
+  if (!h->loss_event) IBC_CUDA(h, cudaEventCreateWithFlags(&h->loss_event, cudaEventDisableTiming));
+  IBC_CUDA(h, cudaEventRecord(h->loss_event, s));
+  h->loss_event_recorded = true;
   mark(2);
 
   IBC_RAISE_SMEM(h, mlp_wgrad_umma_kernel, WgradSmem::kBytes);

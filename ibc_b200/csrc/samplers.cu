@@ -573,6 +573,23 @@ __global__ void uniform_actions_kernel(const float* __restrict__ u, int64_t rows
   out[i] = __fadd_rn(__fmul_rn(x, __fadd_rn(mx[a], -mn[a])), mn[a]);
 }
 
+// The counter-example block of a training step in one pass: combined[b, j, :] = the same uniform
+// sample uniform_actions_kernel draws for row b * N + j (j < N), combined[b, N, :] = the true
+// action (ibc_agent.py:461-473: the expert action LAST).
+__global__ void uniform_combined_kernel(const float* __restrict__ u, int64_t B, int64_t N, int A,
+                                        const float* __restrict__ mn, const float* __restrict__ mx,
+                                        uint64_t seed, const float* __restrict__ actions,
+                                        float* __restrict__ out) {
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // index into [B, N + 1, A]
+  if (o >= B * (N + 1) * A) return;
+  const int a = (int)(o % A);
+  const int64_t bj = o / A, b = bj / (N + 1), j = bj - b * (N + 1);
+  if (j == N) { out[o] = actions[b * A + a]; return; }
+  const int64_t i = (b * N + j) * A + a;                                  // index into [B * N, A]
+  const float x = u ? u[i] : philox_uniform_float(seed, 0x0u, (uint64_t)i);
+  out[o] = __fadd_rn(__fmul_rn(x, __fadd_rn(mx[a], -mn[a])), mn[a]);
+}
+
 // One thread per row: mcmc.langevin_step (mcmc.py:209-264) after dE/dact.
 __global__ void langevin_update_kernel(float* __restrict__ actions,
                                        const float* __restrict__ dEda, int64_t R, int A,
@@ -721,6 +738,17 @@ int uniform_actions(ibc_handle* h, const float* u, int64_t rows, int A, const fl
   if (tot <= 0) return IBC_OK;
   uniform_actions_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(u, rows, A, mn, mx, seed,
                                                                       out);
+  IBC_LAUNCH_CHECK(h);
+  return IBC_OK;
+}
+
+int uniform_combined(ibc_handle* h, const float* u, int64_t B, int64_t N, int A, const float* mn,
+                     const float* mx, uint64_t seed, const float* actions, float* out,
+                     cudaStream_t s) {
+  const int64_t tot = B * (N + 1) * A;
+  if (tot <= 0) return IBC_OK;
+  uniform_combined_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(u, B, N, A, mn, mx, seed,
+                                                                        actions, out);
   IBC_LAUNCH_CHECK(h);
   return IBC_OK;
 }

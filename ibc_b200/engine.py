@@ -221,6 +221,14 @@ class EBMEngine:
                                         _ptr(energies), _ptr(grads), _stream()), self._h)
     return per_example, grad_loss, energies, grads
 
+  def stream_wait_loss(self, stream: torch.cuda.Stream) -> bool:
+    """If the last train_grads recorded its loss event (per_example_loss final, backward still
+    to run), `stream` waits for it and True is returned."""
+    rec = ctypes.c_int32(0)
+    _lib.check(self.lib.ibc_stream_wait_loss(self._h, ctypes.c_void_p(stream.cuda_stream),
+                                             ctypes.byref(rec)), self._h)
+    return bool(rec.value)
+
 
 class PixelEngine:
   """Owns an ibc_pixel_handle (late-fusion PixelEBM: ConvMaxpool encoder +
@@ -459,6 +467,24 @@ def uniform_actions(rows: int, min_actions, max_actions, u=None, seed=0) -> torc
   out = torch.empty(rows, a, device=min_actions.device, dtype=torch.float32)
   _lib.check(_lib.load().ibc_uniform_actions(_ptr(u), rows, a, _ptr(min_actions),
                                              _ptr(max_actions), int(seed), _ptr(out), _stream()))
+  return out
+
+
+def counter_examples_uniform(actions, n: int, min_actions, max_actions, u=None, seed=0):
+  """[B * (n + 1), A]: n uniform negatives per row of `actions` (the samples of
+  uniform_actions(B * n, ...) with the same u / seed) followed by the row itself."""
+  _check_f32(actions, 'actions')
+  _check_f32(min_actions, 'min_actions')
+  _check_f32(max_actions, 'max_actions')
+  b, a = actions.shape
+  if u is not None:
+    _check_f32(u, 'u')
+    if u.numel() != b * n * a:
+      raise ValueError('u must have B*n*A elements')
+  out = torch.empty(b * (n + 1), a, device=actions.device, dtype=torch.float32)
+  _lib.check(_lib.load().ibc_counter_examples_uniform(_ptr(u), b, n, a, _ptr(min_actions),
+                                                      _ptr(max_actions), int(seed), _ptr(actions),
+                                                      _ptr(out), _stream()))
   return out
 
 

@@ -61,6 +61,48 @@ def _scaled_sum(x, scale):
   return torch.dot(x.reshape(-1), c)
 
 
+class _EarlyScalar(torch.Tensor):
+  """A CUDA scalar whose VALUE can be read (float(), .item()) as soon as the kernels that produced
+  it are done, without waiting for whatever the stream runs behind them: the value was also
+  copied to pinned host memory on a second stream (TF eager reads loss_info.loss the same way:
+  waiting for the op that produced it, not for the optimizer update enqueued after it).  Every
+  other use is the plain device tensor."""
+  __torch_function__ = torch._C._disabled_torch_function_impl
+
+  @staticmethod
+  def __new__(cls, dev, ring, slot, gen, ev):
+    t = torch.Tensor._make_subclass(cls, dev)
+    t._ring, t._slot, t._gen, t._ev = ring, slot, gen, ev
+    return t
+
+  def item(self):
+    self._ev.synchronize()
+    if self._ring.gen[self._slot] == self._gen:      # not yet overwritten by a later step
+      return float(self._ring.host[self._slot])
+    return self.as_subclass(torch.Tensor).item()
+
+  def __float__(self):
+    return float(self.item())
+
+  def tolist(self):
+    return self.item()
+
+
+class _HostRing:
+  """Pinned landing slots of the early loss copies (allocated once: cudaHostAlloc is slow)."""
+
+  def __init__(self, n=64):
+    self.host = torch.zeros(n, dtype=torch.float32, pin_memory=True)
+    self.gen = [0] * n
+    self.next = 0
+
+  def take(self):
+    s = self.next
+    self.next = (s + 1) % len(self.gen)
+    self.gen[s] += 1
+    return s, self.gen[s]
+
+
 def _scaled_sq_diff_sum(a, b, scale):
   d = (a - b).reshape(-1)
   return torch.dot(d, d) * scale
@@ -187,7 +229,7 @@ class ImplicitBCAgent(BehavioralCloningAgent):
       raw, eff = net.effective_params_for_training()             # spectral norm, training=True
     per_example, grad_loss, _, grads = net.engine.train_grads(
         obs_flat, combined, n, self._loss_cfg(), global_batch, self._grads)
-    total_loss = _scaled_sum(per_example, 1.0 / float(global_batch))
+    total_loss = self._early_loss(net.engine, per_example, 1.0 / float(global_batch))
     losses_dict['ebm_total_loss'] = total_loss
     if self._add_grad_penalty:
       losses_dict['grad_loss'] = grad_loss.mean()
@@ -207,6 +249,33 @@ class ImplicitBCAgent(BehavioralCloningAgent):
         grads.copy_(graw)
       return specs.LossInfo(total_loss, ()), grads
     return losses_dict
+
+  def _early_loss(self, engine, per_example, scale):
+    """sum(per_example) * scale.  When the engine recorded its loss event (the per-example losses
+    are final while the backward is still running) the sum and a copy to pinned host memory run
+    on a second stream behind that event, and the returned tensor's float() waits for that copy
+    only: a caller that reads the loss every step no longer drains the whole step before it can
+    submit the next one."""
+    if not per_example.is_cuda or not hasattr(engine, 'stream_wait_loss'):
+      return _scaled_sum(per_example, scale)
+    from ibc_b200 import parallel
+    side = parallel._side_stream(per_example.device)
+    if not engine.stream_wait_loss(side):
+      return _scaled_sum(per_example, scale)
+    ring = getattr(self, '_loss_ring', None)
+    if ring is None:
+      ring = self._loss_ring = _HostRing()
+    slot, gen = ring.take()
+    main = torch.cuda.current_stream(per_example.device)
+    with torch.cuda.stream(side):
+      loss = _scaled_sum(per_example, scale)
+      ring.host[slot:slot + 1].copy_(loss.reshape(1), non_blocking=True)
+      ev = torch.cuda.Event()
+      ev.record(side)
+    per_example.record_stream(side)
+    loss.record_stream(main)
+    main.wait_stream(side)             # later uses of the device value on the main stream
+    return _EarlyScalar(loss, ring, slot, gen, ev)
 
   @staticmethod
   def _chain_metrics(chain_data, losses_dict):
@@ -287,59 +356,65 @@ class ImplicitBCAgent(BehavioralCloningAgent):
     n = self._num_counter_examples
     a_dim = expanded_actions.shape[-1]
     u = draws.get('uniform_u')
-    random_uniform = eng.uniform_actions(batch_size * n, self._min, self._max,
-                                         None if u is None else u.reshape(batch_size * n, a_dim)
-                                         .contiguous(), mcmc._next_seed())
+    if u is not None:
+      u = u.reshape(batch_size * n, a_dim).contiguous()
     chain_data = None
     if self._fraction_dfo_samples == 0.0 and self._fraction_langevin_samples == 0.0:
-      counter = random_uniform.view(batch_size, n, a_dim)
-    else:
-      dfo_actions = lang_actions = None
-      if self._fraction_dfo_samples > 0.:
-        if self._return_full_chain:
-          raise NotImplementedError('Not implemented to return dfo chain.')   # :374-375
-        dfo_actions = random_uniform.clone()
-        dfo_obs = obs_flat
-        if self._late_fusion:
-          dfo_obs = getattr(self, '_enc', None)
-          if dfo_obs is None:
-            dfo_obs = net.encode(obs_flat, training=False)
-        net.engine.dfo(dfo_obs, dfo_actions, n, self._min, self._max, 1.0, 3, 0.33,
-                       draws.get('dfo_uniforms'), draws.get('dfo_normals'), mcmc._next_seed())
-      if self._fraction_langevin_samples > 0.:
-        # late fusion: un-tiled frames, encoded once inside the sampler (mcmc.py:384-388;
-        # upstream binds langevin_actions_given_obs.late_fusion in the gin file)
-        # the engine samplers take un-tiled observations (mcmc._untile passes them through);
-        # only a generic callable network needs the B*n-row tile_batch copy
-        tiled = obs_flat if (self._late_fusion or isinstance(net, MLPEBM)) \
-            else torch.repeat_interleave(obs_flat, n, dim=0)
-        lf = {'late_fusion': True,
-              'observation_encoding': getattr(self, '_enc', None)} if self._late_fusion else {}
-        out = mcmc.langevin_actions_given_obs(
-            net, tiled, random_uniform, policy_state=(), min_actions=self._min,
-            max_actions=self._max, num_action_samples=n, training=False,
-            return_chain=self._return_full_chain, grad_norm_type=self._grad_norm_type,
-            normal_draws=draws.get('langevin_normals'), **lf)
-        if self._return_full_chain:
-          lang_actions, chain_data = out
-        else:
-          lang_actions = out
-      frac_init = 1.0 - self._fraction_dfo_samples - self._fraction_langevin_samples
-      n_init = int(frac_init * n)
-      n_dfo = int(self._fraction_dfo_samples * n)
-      n_lang = int(self._fraction_langevin_samples * n)
-      n_init += n - n_init - n_dfo - n_lang                    # residual -> init (:416-430)
-      pieces, used = [], 0
-      if n_init > 0:
-        pieces.append(random_uniform.view(batch_size, n, a_dim)[:, :n_init])
-        used += n_init
-      if n_dfo > 0:
-        pieces.append(dfo_actions.view(batch_size, n, a_dim)[:, used:used + n_dfo])
-        used += n_dfo
-      if n_lang > 0:
-        pieces.append(lang_actions.view(batch_size, n, a_dim)[:, used:used + n_lang])
-        used += n_lang
-      counter = torch.cat(pieces, dim=1)
+      # uniform negatives only: samples and the concatenation with the expert action in one
+      # launch (the same samples as uniform_actions; two torch.cat launches less in front of
+      # the step's first large kernel)
+      combined = eng.counter_examples_uniform(
+          expanded_actions.reshape(batch_size, a_dim).contiguous(), n, self._min, self._max, u,
+          mcmc._next_seed())
+      counter = combined.view(batch_size, n + 1, a_dim)[:, :n]
+      return counter, combined, chain_data
+    random_uniform = eng.uniform_actions(batch_size * n, self._min, self._max, u, mcmc._next_seed())
+    dfo_actions = lang_actions = None
+    if self._fraction_dfo_samples > 0.:
+      if self._return_full_chain:
+        raise NotImplementedError('Not implemented to return dfo chain.')   # :374-375
+      dfo_actions = random_uniform.clone()
+      dfo_obs = obs_flat
+      if self._late_fusion:
+        dfo_obs = getattr(self, '_enc', None)
+        if dfo_obs is None:
+          dfo_obs = net.encode(obs_flat, training=False)
+      net.engine.dfo(dfo_obs, dfo_actions, n, self._min, self._max, 1.0, 3, 0.33,
+                     draws.get('dfo_uniforms'), draws.get('dfo_normals'), mcmc._next_seed())
+    if self._fraction_langevin_samples > 0.:
+      # late fusion: un-tiled frames, encoded once inside the sampler (mcmc.py:384-388;
+      # upstream binds langevin_actions_given_obs.late_fusion in the gin file)
+      # the engine samplers take un-tiled observations (mcmc._untile passes them through);
+      # only a generic callable network needs the B*n-row tile_batch copy
+      tiled = obs_flat if (self._late_fusion or isinstance(net, MLPEBM)) \
+          else torch.repeat_interleave(obs_flat, n, dim=0)
+      lf = {'late_fusion': True,
+            'observation_encoding': getattr(self, '_enc', None)} if self._late_fusion else {}
+      out = mcmc.langevin_actions_given_obs(
+          net, tiled, random_uniform, policy_state=(), min_actions=self._min,
+          max_actions=self._max, num_action_samples=n, training=False,
+          return_chain=self._return_full_chain, grad_norm_type=self._grad_norm_type,
+          normal_draws=draws.get('langevin_normals'), **lf)
+      if self._return_full_chain:
+        lang_actions, chain_data = out
+      else:
+        lang_actions = out
+    frac_init = 1.0 - self._fraction_dfo_samples - self._fraction_langevin_samples
+    n_init = int(frac_init * n)
+    n_dfo = int(self._fraction_dfo_samples * n)
+    n_lang = int(self._fraction_langevin_samples * n)
+    n_init += n - n_init - n_dfo - n_lang                    # residual -> init (:416-430)
+    pieces, used = [], 0
+    if n_init > 0:
+      pieces.append(random_uniform.view(batch_size, n, a_dim)[:, :n_init])
+      used += n_init
+    if n_dfo > 0:
+      pieces.append(dfo_actions.view(batch_size, n, a_dim)[:, used:used + n_dfo])
+      used += n_dfo
+    if n_lang > 0:
+      pieces.append(lang_actions.view(batch_size, n, a_dim)[:, used:used + n_lang])
+      used += n_lang
+    counter = torch.cat(pieces, dim=1)
     combined = torch.cat([counter, expanded_actions], dim=1)    # true action LAST (:461-473)
     combined = combined.reshape(batch_size * (n + 1), a_dim).contiguous()
     return counter, combined, chain_data
@@ -369,6 +444,10 @@ class ImplicitBCAgent(BehavioralCloningAgent):
         raise FloatingPointError('Loss is inf or nan')
     else:
       host = None
+    if isinstance(loss, _EarlyScalar) and loss._ring.gen[loss._slot] == loss._gen:
+      # the early read-out already copies this loss to pinned memory: look at that copy
+      self._pending_finite = (loss._ring.host[loss._slot:loss._slot + 1], loss._ev)
+      return
     if host is None:
       host = getattr(self, '_finite_host', None)
       if host is None:

@@ -23,6 +23,17 @@ def replica_rank() -> int:
   return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
 
 
+_side_streams = {}
+
+
+def _side_stream(device) -> 'torch.cuda.Stream':
+  """One auxiliary stream per device (early loss read-out: ibc_agent._early_loss)."""
+  key = torch.device(device).index
+  if key not in _side_streams:
+    _side_streams[key] = torch.cuda.Stream(device=device)
+  return _side_streams[key]
+
+
 def allreduce_gradients(flat_grads: torch.Tensor) -> torch.Tensor:
   """In-place SUM over replicas of the flat gradient vector."""
   if num_replicas() > 1:

@@ -193,6 +193,16 @@ int ibc_uniform_actions(const float* u, int64_t rows, int32_t A,
                         const float* min_actions, const float* max_actions,
                         uint64_t seed, float* out, void* stream);
 
+/* The counter-example block of a training step with uniform negatives only
+ * (ibc_agent.py:340-352 and 461-473 in one pass): combined [B, N + 1, A] with
+ * combined[b, j, :] = the sample ibc_uniform_actions draws for row b * N + j of a
+ * [B * N, A] call with the same u / seed (j < N) and combined[b, N, :] = actions[b, :]
+ * (the expert action last). */
+int ibc_counter_examples_uniform(const float* u, int64_t B, int64_t N, int32_t A,
+                                 const float* min_actions, const float* max_actions,
+                                 uint64_t seed, const float* actions, float* combined,
+                                 void* stream);
+
 /* ---- losses and training ---------------------------------------------- */
 
 /* ebm_loss.info_nce (ibc/losses/ebm_loss.py:21-48) in the Keras KLDivergence
@@ -224,6 +234,15 @@ int ibc_train_grads(ibc_handle* h, const float* obs, int64_t B,
                     int64_t global_batch, float* per_example_loss,
                     float* grad_loss, float* energies, float* grads,
                     void* stream);
+
+/* Reading the loss of a step does not have to wait for the step (in TF eager, reading
+ * loss_info.loss waits for the op that produced it, not for the optimizer update that follows:
+ * ibc/agents/base_agent.py:43-59).  On the layer-fused path the last ibc_train_grads records an
+ * event on its stream right behind its loss kernel, when per_example_loss is final and the
+ * backward is still to run.  ibc_stream_wait_loss sets *recorded (0: the path taken recorded
+ * none) and, if 1, makes `stream` wait for that event, so that the caller can sum and copy the
+ * loss on a second stream. */
+int ibc_stream_wait_loss(ibc_handle* h, void* stream, int32_t* recorded);
 
 /* Keras-2.6 Adam (get_agent.py:64-68): m, v, params updated in place with the
  * bias-corrected step size lr_t computed by the caller. */

@@ -1,5 +1,7 @@
+"""Diagnostic: per-layer cycle timeline of langevin_f16_kernel (CTA 0, second iteration) on the
+pushing_states net: run with IBC_DBG_TIMELINE=1."""
 import os, sys
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ibc_b200 import engine as eng
 o, a, w, d, b, n = 20, 2, 128, 16, 512, 8

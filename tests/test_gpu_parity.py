@@ -378,6 +378,22 @@ def test_fused_langevin_kernel_is_bit_identical_to_the_three_kernel_chain():
   assert digests[0] == digests[1]
 
 
+def test_counter_examples_uniform_is_the_two_step_path():
+  """ibc_counter_examples_uniform (uniform negatives + the expert action last, one launch) against
+  uniform_actions followed by the two concatenations it replaces (ibc_agent.py:340-352,
+  461-473): bit-identical, with supplied uniforms and with the Philox stream of a seed."""
+  from ibc_b200 import engine as eng
+  g = torch.Generator().manual_seed(3)
+  for b, n, a in ((5, 7, 2), (64, 256, 2), (3, 8, 28)):
+    mn = (-1.1 - torch.rand(a, generator=g)).cuda(); mx = (1.1 + torch.rand(a, generator=g)).cuda()
+    act = (torch.rand(b, a, generator=g) * 2 - 1).cuda()
+    for u in (None, torch.rand(b * n, a, generator=g).cuda()):
+      want = torch.cat([eng.uniform_actions(b * n, mn, mx, u, seed=41).view(b, n, a), act[:, None, :]],
+                       dim=1).reshape(b * (n + 1), a)
+      got = eng.counter_examples_uniform(act, n, mn, mx, u, seed=41)
+      assert torch.equal(got, want)
+
+
 def test_umma_f16_operand_forms():
   """The kind::f16 operand forms the kernels rely on, against fp16-rounded inputs in fp64: the
   MN-major 128-byte-swizzle image of the weight-gradient GEMM (default), K-major no-swizzle
