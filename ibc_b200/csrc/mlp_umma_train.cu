@@ -825,6 +825,37 @@ static int langevin_chain(ibc_handle* h, const float* obs, int64_t B, float* act
 // caller-supplied normals) the whole chain is replayed from a CUDA graph: the second
 // call with the same shapes / config captures it, later calls stage their inputs into
 // the graph's buffers and launch it (IBC_NO_GRAPHS=1 disables this).
+// The observation half of the first Dense layer's gradient from the per-observation sums of g0:
+// dWp[:O] += obs^T . gsum and dbp += column sums of gsum, in one small launch (thread = output
+// column, a block = a slice of the observations; O <= 32 accumulators per thread).  Replaces a
+// split-K SIMT GEMM launch and a column-sum launch of ~9 us each on a 512 x 128 matrix.
+template <int OMAX>
+__global__ void __launch_bounds__(kW) first_layer_obs_grads_kernel(
+    const float* __restrict__ obs, const float* __restrict__ gsum, int64_t B, int O, int rows_per_block,
+    float* __restrict__ dwp, float* __restrict__ dbp) {
+  __shared__ float s_obs[OMAX];
+  const int w = threadIdx.x;
+  const int64_t b0 = (int64_t)blockIdx.x * rows_per_block, b1 = min(B, b0 + rows_per_block);
+  float acc[OMAX];
+#pragma unroll
+  for (int o = 0; o < OMAX; ++o) acc[o] = 0.f;
+  float bs = 0.f;
+  for (int64_t b = b0; b < b1; ++b) {
+    __syncthreads();
+    if (w < O) s_obs[w] = obs[b * O + w];
+    __syncthreads();
+    const float g = gsum[b * kW + w];
+    bs += g;
+#pragma unroll
+    for (int o = 0; o < OMAX; ++o)
+      if (o < O) acc[o] = fmaf(s_obs[o], g, acc[o]);
+  }
+#pragma unroll
+  for (int o = 0; o < OMAX; ++o)
+    if (o < O) atomicAdd(dwp + (int64_t)o * kW + w, acc[o]);
+  atomicAdd(dbp + w, bs);
+}
+
 int langevin_umma(ibc_handle* h, const float* obs, int64_t B, float* actions, int64_t n,
                   const float* mn, const float* mx, const ibc_langevin_cfg& c,
                   const float* normals, uint64_t seed, const std::vector<float>& steps,
@@ -1032,13 +1063,18 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
       first_layer_grads_kernel<32><<<blocks, kW, 0, s>>>(actions, g0, dE, R, A, n1, dwa, gsum, dbe);
     IBC_LAUNCH_CHECK(h);
   }
-  {
+  if (L.O <= 32 && W == kW) {     // dWp[:O] = obs^T . sum_n g0 and dbp in one launch
+    const int rpb = 16;
+    first_layer_obs_grads_kernel<32><<<(unsigned)((B + rpb - 1) / rpb), kW, 0, s>>>(
+        obs, gsum, B, L.O, rpb, grads + L.wp, grads + L.bp);
+    IBC_LAUNCH_CHECK(h);
+  } else {
     GemmP g;   // dWp[:O] = obs^T . sum_n g0
     g.A = obs; g.lda = L.O; g.B = gsum; g.ldb = W; g.C = grads + L.wp; g.ldc = W;
     g.M = L.O; g.N = W; g.K = (int)B; g.k_chunk = 32; g.atomic = 1;   // many small splits: latency-bound
     IBC_TRY(gemm(h, g, true, false, s));
+    IBC_TRY(colsum_add(h, gsum, W, B, W, grads + L.bp, s));
   }
-  IBC_TRY(colsum_add(h, gsum, W, B, W, grads + L.bp, s));
   mark(5);
   if (h->profiling) h->ev_valid = true;
   return IBC_OK;
