@@ -96,7 +96,8 @@ struct BwdWgradParams {
   const uint32_t* dE_absmax;  // bits of max |dE| (written by the loss kernel)
   const uint4* xa16;          // forward operand tiles, fp16: [tile][2nb][16 chunks of 8][128 rows][16 B]
   const uint32_t* mask_save;  // ReLU masks of the 2nb layers
-  float* gpark;               // [tiles][32 chunks][128 rows][4]: residual gradient between blocks;
+  float* gpark;               // per tile 128 x 128 floats: the residual gradient between blocks (scaled fp16,
+                              // [16 chunks of 8][128 rows][16 B] in the first half of the region);
                               // after the kernel: the gradient of the first Dense output (g0)
   const float* hn;            // forward's final residual stream, [tile][32 chunks][128 rows][4] (for dwe)
   float* acc_w;               // [2nb][32 chunks][128 in][4]: weight gradients, accumulated with coalesced
@@ -144,6 +145,21 @@ __device__ __forceinline__ void stg_hint(float4* ptr, const float4 v, uint64_t p
   asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
                ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)
                : "memory");
+}
+__device__ __forceinline__ uint4 ldg_u4_hint(const uint4* ptr, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(ptr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg_u4_hint(uint4* ptr, const uint4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;"
+               ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ float2 half2_bits_to_float2(uint32_t w) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
 }
 // 16-byte asynchronous copy global -> shared (LDGSTS): no destination registers, so the
 // copies of several sub-tiles stay in flight without a scoreboard holding the warp
@@ -360,13 +376,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
         // are ahead of this item's 64 KB of park stores, which drain at the SM's ~32 B/clk.
         const bool load_next = blk > 0 && k + 1 < ntile && !(p.dbg_mode & 1);
         if (load_next) {
-          const float4* pn = reinterpret_cast<const float4*>(p.gpark + tile_of(blk, k + 1) * (int64_t)TT::kTileFloats) +
-                             cc * 8 * 128 + row;
+          // (parked between blocks as scaled fp16: [16 chunks of 8 columns][128 rows][16 B] in
+          // the first half of the tile's region; v holds the packed pairs until G' unpacks them)
+          const uint4* pn = reinterpret_cast<const uint4*>(p.gpark + tile_of(blk, k + 1) * (int64_t)TT::kTileFloats) +
+                            cc * 4 * 128 + row;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 x = ldg_hint(pn + q * 128, pol_keep);
-            v[q * 4 + 0] = __float_as_uint(x.x); v[q * 4 + 1] = __float_as_uint(x.y);
-            v[q * 4 + 2] = __float_as_uint(x.z); v[q * 4 + 3] = __float_as_uint(x.w);
+          for (int q = 0; q < 4; ++q) {
+            const uint4 x = ldg_u4_hint(pn + q * 128, pol_keep);
+            v[q * 4 + 0] = x.x; v[q * 4 + 1] = x.y; v[q * 4 + 2] = x.z; v[q * 4 + 3] = x.w;
           }
         }
 
@@ -384,14 +401,37 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
             gr[hq * 16 + q] += ((m0 >> (hq * 16 + q)) & 1u) ? __uint_as_float(w16[q]) * inv_scale : 0.f;
         }
         if (!carry_out && !(p.dbg_mode & 2)) {
+          if (blk == p.nb - 1) {      // g0, the kernel's output: fp32
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            stg_hint(park + q * 128, make_float4(gr[q * 4 + 0], gr[q * 4 + 1], gr[q * 4 + 2], gr[q * 4 + 3]),
-                     pol_keep);
+            for (int q = 0; q < 8; ++q)
+              stg_hint(park + q * 128, make_float4(gr[q * 4 + 0], gr[q * 4 + 1], gr[q * 4 + 2], gr[q * 4 + 3]),
+                       pol_keep);
+          } else {
+            // Between blocks the residual gradient is parked as fp16 of scale * g -- the 11-bit
+            // significand the next block's chain operand and image round it to anyway; what the
+            // parking adds is one such rounding per block on the running sum (per-tensor gradient
+            // errors of this stack against fp32 are 1e-2 .. 8e-2, from mask flips).  Half the
+            // bytes through the SM's store port, and the 1 028 parked tiles are 34 MB instead of
+            // 67: they stay in L2.
+            uint4* pk = reinterpret_cast<uint4*>(p.gpark + tile * (int64_t)TT::kTileFloats) + cc * 4 * 128 + row;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 w;
+              w.x = pack_half2(gr[q * 8 + 0] * scale, gr[q * 8 + 1] * scale);
+              w.y = pack_half2(gr[q * 8 + 2] * scale, gr[q * 8 + 3] * scale);
+              w.z = pack_half2(gr[q * 8 + 4] * scale, gr[q * 8 + 5] * scale);
+              w.w = pack_half2(gr[q * 8 + 6] * scale, gr[q * 8 + 7] * scale);
+              stg_u4_hint(pk + q * 128, w, pol_keep);
+            }
+          }
         }
         if (load_next) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) gr[q] = __uint_as_float(v[q]);
+          for (int q = 0; q < 16; ++q) {
+            const float2 f = half2_bits_to_float2(v[q]);
+            gr[2 * q] = f.x * inv_scale;
+            gr[2 * q + 1] = f.y * inv_scale;
+          }
         }
         tc_fence_before();
         if (stamp) dbg[7] = clock64();
@@ -447,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_wgrad_tmem_kernel(BwdWgra
       if (blk > 0 && k > 0) {     // the parked residual gradient of the same tile (L2-resident unless evicted)
         const float* pk = p.gpark + tile * (int64_t)TT::kTileFloats;
 #pragma unroll 1
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 2; ++i)      // fp16: the first 32 KB of the tile's region
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pk + (int64_t)i * 4096),
                        "r"(16384u)
                        : "memory");

