@@ -117,12 +117,14 @@ int ibc_bind_params(ibc_handle* h, const float* params, void* stream) {
   if (!params) IBC_FAIL(h, IBC_ERR_INVALID, "ibc_bind_params: null params");
   h->params = params;
   h->packed_stale = true;
+  h->packed_rest_stale = true;
   return IBC_OK;
 }
 
 int ibc_params_changed(ibc_handle* h) {
   IBC_ENTER(h);
   h->packed_stale = true;
+  h->packed_rest_stale = true;
   return IBC_OK;
 }
 

@@ -105,7 +105,9 @@ struct ibc_handle {
   int precision = IBC_PRECISION_FP32;
   int sm_count = 148;
   const float* params = nullptr;
-  bool packed_stale = true;
+  bool packed_stale = true;       // the operand copies every layer-fused step needs (umma_pack_core)
+  bool packed_rest_stale = true;  // ... the remaining ones (reverse chains in tf32, shared-memory-operand
+                                  // kernels, fp16 forward layers): umma_pack_params brings both up to date
   float* packed = nullptr;        // tcgen05 operand copies of the weights
   size_t packed_bytes = 0;
   void* packed16 = nullptr;       // fp16 operand copies (width 128, langevin_f16.cu)

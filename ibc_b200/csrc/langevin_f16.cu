@@ -515,12 +515,15 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_f16_kernel(LangevinF16Pa
 // layer + [2][W][8] bias slice (hi, lo, 0 ...)) | 2nb x [W/8][W][8] transposed layers, top first |
 // [W/8][AP][8] action rows of Wp for dE/dact.  Element (n, k) of a K-major image sits at
 // ((k / 8) * N + n) * 8 + k % 8.
+// Elements [lo, hi) of the buffer, without [hole_lo, hole_lo + hole_len).
 __global__ void pack16_kernel(const float* __restrict__ P, Layout L, Packed16Layout pl,
-                              __half* __restrict__ out) {
+                              __half* __restrict__ out, int64_t lo, int64_t hi, int64_t hole_lo,
+                              int64_t hole_len) {
   const int W = L.W;
   const int64_t WW = (int64_t)W * W;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pl.total;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t j = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < hi - hole_len;
+       j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = j < hole_lo ? j : j + hole_len;
     float v = 0.f;
     if (i < pl.fwd) {                       // step-0 operand: B[n][k] = Wp[O + k][n]
       const int64_t e = i - pl.p0;
@@ -580,10 +583,14 @@ bool langevin_f16_supported(const Layout& L) {
   return !off && L.W == kW && L.A <= kAMax && L.nb >= 1 && f16_smem_bytes(L.nb) <= 227 * 1024 - 512;
 }
 
-int pack16_params(ibc_handle* h, cudaStream_t s) {
+// core: the transposed layers [rev, revp) (the block-major backward's chain weights); otherwise
+// everything else (action rows, forward layers + bias slices, dE/dact operand)
+int pack16_params(ibc_handle* h, cudaStream_t s, bool core) {
   const Packed16Layout pl = make_packed16_layout(h->L);
   if (!h->packed16) IBC_CUDA(h, cudaMalloc((void**)&h->packed16, (size_t)pl.total * 2));
-  pack16_kernel<<<148, 256, 0, s>>>(h->params, h->L, pl, reinterpret_cast<__half*>(h->packed16));
+  __half* out = reinterpret_cast<__half*>(h->packed16);
+  if (core) pack16_kernel<<<148, 256, 0, s>>>(h->params, h->L, pl, out, pl.rev, pl.revp, pl.revp, 0);
+  else pack16_kernel<<<148, 256, 0, s>>>(h->params, h->L, pl, out, 0, pl.total, pl.rev, pl.revp - pl.rev);
   IBC_LAUNCH_CHECK(h);
   return IBC_OK;
 }

@@ -52,7 +52,8 @@ int mlp_energy_dact(ibc_handle* h, const float* obs, int64_t B, const float* act
 
 // tcgen05 path (mlp_umma.cu) ---------------------------------------------
 bool umma_supported(const Layout& L);
-int umma_pack_params(ibc_handle* h, cudaStream_t s);
+int umma_pack_params(ibc_handle* h, cudaStream_t s);   // every operand copy up to date
+int umma_pack_core(ibc_handle* h, cudaStream_t s);     // ... only those of the layer-fused training step
 // Saved state for the reverse chain (both nullable): xa_save = the A operands of
 // every layer (umma_save_floats() floats; the weight-gradient kernel's input),
 // mask_save = their ReLU masks as bits (umma_mask_words() words; all the
@@ -77,7 +78,7 @@ int mlp_energy_wide(ibc_handle* h, const float* obs, int64_t B, const float* act
 // width 128, act_dim <= 8: the same chain with kind::f16 GEMMs and sixteen epilogue warps
 // (langevin_f16.cu); pack16_params refreshes its fp16 weight images
 bool langevin_f16_supported(const Layout& L);
-int pack16_params(ibc_handle* h, cudaStream_t s);
+int pack16_params(ibc_handle* h, cudaStream_t s, bool core);     // core: the transposed layers; else the rest
 int langevin_f16(ibc_handle* h, const float* hp, int64_t B, float* actions, int64_t n,
                  const float* mn, const float* mx, const ibc_langevin_cfg& c, const float* normals,
                  uint64_t seed, const uint64_t* seed_ptr, const float* steps_dev,

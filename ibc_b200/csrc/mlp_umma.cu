@@ -33,12 +33,15 @@ namespace {
 constexpr int kSlots = 5;
 constexpr int kSliceBytes = 16384;
 
+// Elements [lo, hi) of the packed buffer, without [hole_lo, hole_lo + hole_len).
 __global__ void pack_kernel(const float* __restrict__ P, Layout L, PackedLayout pl,
-                            float* __restrict__ out) {
+                            float* __restrict__ out, int64_t lo, int64_t hi, int64_t hole_lo,
+                            int64_t hole_len) {
   const int W = L.W;
   const int64_t WW = (int64_t)W * W;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pl.total;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t j = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < hi - hole_len;
+       j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = j < hole_lo ? j : j + hole_len;
     float v = 0.f;
     if (i < pl.fwd_l) {                    // step-0 operand: [KP/4][W][4]
       const int64_t e = i - pl.fwd_p;
@@ -809,16 +812,41 @@ bool umma_supported(const Layout& L) {
   return (L.W == 128 || L.W == 256) && L.nb >= 1 && L.A >= 1 && L.A <= 32 && L.O >= 1;
 }
 
-int umma_pack_params(ibc_handle* h, cudaStream_t s) {
-  const PackedLayout pl = make_packed_layout(h->L);
+// The operand copies are refreshed in two parts, because a training step re-packs after every
+// optimizer update (25 us of two launches for all of them, 5 % of the C2 step): the CORE -- what
+// the layer-fused forward and the block-major backward read: action rows, forward layers with
+// their bias slices, vectors, and (width 128) the fp16 transposed layers -- and the REST: the
+// tf32 reverse layers and the shared-memory-operand kernels' copies (fwd_l, rev_l, rev_p:
+// contiguous in the buffer), the fp16 forward layers.  umma_pack_core is for the two hot paths
+// that need nothing else; every other caller uses umma_pack_params, which brings both up to date.
+static int ensure_packed_buffer(ibc_handle* h, const PackedLayout& pl) {
   if (!h->packed) {
     IBC_CUDA(h, cudaMalloc((void**)&h->packed, (size_t)pl.total * 4));
     h->packed_bytes = (size_t)pl.total * 4;
   }
-  pack_kernel<<<296, 256, 0, s>>>(h->params, h->L, pl, h->packed);
+  return IBC_OK;
+}
+
+int umma_pack_core(ibc_handle* h, cudaStream_t s) {
+  if (!h->packed_stale) return IBC_OK;
+  const PackedLayout pl = make_packed_layout(h->L);
+  IBC_TRY(ensure_packed_buffer(h, pl));
+  pack_kernel<<<148, 256, 0, s>>>(h->params, h->L, pl, h->packed, 0, pl.total, pl.fwd_l,
+                                  pl.vecs - pl.fwd_l);
   IBC_LAUNCH_CHECK(h);
-  if (h->L.W == 128) IBC_TRY(pack16_params(h, s));     // fp16 images: Langevin chain, block-major backward
+  if (h->L.W == 128) IBC_TRY(pack16_params(h, s, true));     // fp16 transposed layers (backward)
   h->packed_stale = false;
+  return IBC_OK;
+}
+
+int umma_pack_params(ibc_handle* h, cudaStream_t s) {
+  IBC_TRY(umma_pack_core(h, s));
+  if (!h->packed_rest_stale) return IBC_OK;
+  const PackedLayout pl = make_packed_layout(h->L);
+  pack_kernel<<<148, 256, 0, s>>>(h->params, h->L, pl, h->packed, pl.fwd_l, pl.vecs, pl.vecs, 0);
+  IBC_LAUNCH_CHECK(h);
+  if (h->L.W == 128) IBC_TRY(pack16_params(h, s, false));    // fp16 forward layers (Langevin chain)
+  h->packed_rest_stale = false;
   return IBC_OK;
 }
 
@@ -841,7 +869,7 @@ int mlp_energy_umma(ibc_handle* h, const float* obs, int64_t B, const float* act
 int umma_forward(ibc_handle* h, const float* obs, int64_t B, const float* act, int64_t n,
                  float* hp, float* E, float* xa_save, uint32_t* mask_save, cudaStream_t s) {
   const Layout& L = h->L;
-  if (h->packed_stale) IBC_TRY(umma_pack_params(h, s));
+  IBC_TRY(umma_pack_params(h, s));
   {  // hp = obs . Wp[:O] + bp   (fp32)
     GemmP g;
     g.A = obs; g.lda = L.O; g.B = h->params + L.wp; g.ldb = L.W; g.C = hp; g.ldc = L.W;
@@ -855,7 +883,7 @@ int umma_forward(ibc_handle* h, const float* obs, int64_t B, const float* act, i
 int umma_forward_hp(ibc_handle* h, const float* act, int64_t R, int64_t n, const float* hp,
                     float* E, float* xa_save, uint32_t* mask_save, cudaStream_t s) {
   const Layout& L = h->L;
-  if (h->packed_stale) IBC_TRY(umma_pack_params(h, s));
+  IBC_TRY(umma_pack_params(h, s));
   const PackedLayout pl = make_packed_layout(L);
   // width 128: activations in tensor memory; IBC_SMEM_OPERANDS=1 selects the
   // shared-memory-operand kernel below instead (kept for width 256 and for A/B runs)

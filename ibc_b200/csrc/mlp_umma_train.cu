@@ -868,7 +868,7 @@ int langevin_umma(ibc_handle* h, const float* obs, int64_t B, float* actions, in
                        Workspace::rounded((size_t)R * L.W * 4) +
                        Workspace::rounded((size_t)B * L.W * 4) + 3 * Workspace::rounded((size_t)R * 4);
   IBC_CUDA(h, h->ws.reserve(bytes));
-  if (h->packed_stale) IBC_TRY(umma_pack_params(h, s));
+  IBC_TRY(umma_pack_params(h, s));
   static const bool no_fused = getenv("IBC_NO_FUSED_LANGEVIN") != nullptr;
   if (!no_fused && K > 0 && langevin_fused_supported(L)) {
     // width 128: the whole chain in one persistent kernel (langevin_tmem.cu)
@@ -990,7 +990,7 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
   IBC_CUDA(h, cudaMemsetAsync(grads, 0, (size_t)L.count * 4, s));
   mark(0);
   if (fused_bwd) {
-    if (h->packed_stale) IBC_TRY(umma_pack_params(h, s));
+    IBC_TRY(umma_pack_core(h, s));     // forward layers + fp16 transposed layers: all this path reads
     GemmP g;   // hp = obs . Wp[:O] + bp   (fp32)
     g.A = obs; g.lda = L.O; g.B = h->params + L.wp; g.ldb = L.W; g.C = hp; g.ldc = L.W;
     g.bias = h->params + L.bp; g.M = (int)B; g.N = L.W; g.K = L.O;
