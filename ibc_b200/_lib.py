@@ -94,6 +94,8 @@ SIGNATURES = {
                                  c_void_p]),
     'ibc_uniform_actions': (c_int, [c_void_p, c_int64, c_int32, c_void_p,
                                     c_void_p, c_uint64, c_void_p, c_void_p]),
+    'ibc_greedy_actions': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]),
     'ibc_counter_examples_uniform': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
                                              c_uint64, c_void_p, c_void_p, c_void_p]),
     'ibc_info_nce': (c_int, [c_void_p, c_int64, c_int64, c_float, c_float,

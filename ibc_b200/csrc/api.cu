@@ -228,6 +228,14 @@ int ibc_uniform_actions(const float* u, int64_t rows, int32_t A, const float* mi
   return uniform_actions(h, u, rows, A, min_actions, max_actions, seed, out, (cudaStream_t)stream);
 }
 
+int ibc_greedy_actions(const float* probs, const float* values, int64_t B, int64_t n, int32_t A,
+                       const float* min_actions, const float* max_actions, float* out, void* stream) {
+  ibc_handle* h = nullptr;
+  if (!probs || !values || !out || (min_actions == nullptr) != (max_actions == nullptr))
+    IBC_FAIL(h, IBC_ERR_INVALID, "ibc_greedy_actions: bad argument");
+  return greedy_actions(h, probs, values, B, n, A, min_actions, max_actions, out, (cudaStream_t)stream);
+}
+
 int ibc_counter_examples_uniform(const float* u, int64_t B, int64_t N, int32_t A,
                                  const float* min_actions, const float* max_actions, uint64_t seed,
                                  const float* actions, float* combined, void* stream) {

@@ -14,6 +14,8 @@ int softmax_rows(ibc_handle* h, const float* logits, int64_t B, int64_t n, float
                  float* probs, cudaStream_t s);
 int uniform_actions(ibc_handle* h, const float* u, int64_t rows, int A, const float* mn,
                     const float* mx, uint64_t seed, float* out, cudaStream_t s);
+int greedy_actions(ibc_handle* h, const float* probs, const float* values, int64_t B, int64_t n, int A,
+                   const float* mn, const float* mx, float* out, cudaStream_t s);
 int uniform_combined(ibc_handle* h, const float* u, int64_t B, int64_t N, int A, const float* mn,
                      const float* mx, uint64_t seed, const float* actions, float* out,
                      cudaStream_t s);

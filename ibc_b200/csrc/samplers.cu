@@ -590,6 +590,52 @@ __global__ void uniform_combined_kernel(const float* __restrict__ u, int64_t B, 
   out[o] = __fadd_rn(__fmul_rn(x, __fadd_rn(mx[a], -mn[a])), mn[a]);
 }
 
+// GreedyPolicy over a MappedCategorical (ibc_policy.py:96-117, greedy_policy.py): per observation
+// the FIRST index of the largest probability and the action mapped to it.  One block per
+// observation; replaces an arg-max, an arange, a gather and (in the caller) two clips.
+__global__ void __launch_bounds__(256)
+greedy_actions_kernel(const float* __restrict__ probs, const float* __restrict__ values, int n, int A,
+                      const float* __restrict__ mn, const float* __restrict__ mx,
+                      float* __restrict__ out) {
+  __shared__ float s_v[8];
+  __shared__ int s_i[8];
+  const int tid = threadIdx.x;
+  const float* row = probs + (int64_t)blockIdx.x * n;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = tid; j < n; j += 256) {
+    const float p = row[j];
+    if (p > best || (p == best && j < bi) || (p != p && !(best != best))) { best = p; bi = j; }   // NaN wins, like arg max
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    const bool take = (ob != ob && !(best != best)) || (!(best != best) && ob > best) ||
+                      ((ob == best || (ob != ob && best != best)) && oi < bi);
+    if (take) { best = ob; bi = oi; }
+  }
+  if ((tid & 31) == 0) { s_v[tid >> 5] = best; s_i[tid >> 5] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) {
+      const float ob = s_v[w];
+      const int oi = s_i[w];
+      const bool take = (ob != ob && !(best != best)) || (!(best != best) && ob > best) ||
+                        ((ob == best || (ob != ob && best != best)) && oi < bi);
+      if (take) { best = ob; bi = oi; }
+    }
+    s_i[0] = bi;
+  }
+  __syncthreads();
+  bi = min(s_i[0], n - 1);
+  for (int a = tid; a < A; a += 256) {
+    float v = values[((int64_t)blockIdx.x * n + bi) * A + a];
+    if (mn) v = fminf(fmaxf(v, mn[a]), mx[a]);
+    out[(int64_t)blockIdx.x * A + a] = v;
+  }
+}
+
 // One thread per row: mcmc.langevin_step (mcmc.py:209-264) after dE/dact.
 __global__ void langevin_update_kernel(float* __restrict__ actions,
                                        const float* __restrict__ dEda, int64_t R, int A,
@@ -749,6 +795,14 @@ int uniform_combined(ibc_handle* h, const float* u, int64_t B, int64_t N, int A,
   if (tot <= 0) return IBC_OK;
   uniform_combined_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(u, B, N, A, mn, mx, seed,
                                                                         actions, out);
+  IBC_LAUNCH_CHECK(h);
+  return IBC_OK;
+}
+
+int greedy_actions(ibc_handle* h, const float* probs, const float* values, int64_t B, int64_t n, int A,
+                   const float* mn, const float* mx, float* out, cudaStream_t s) {
+  if (B <= 0 || n <= 0 || A <= 0) IBC_FAIL(h, IBC_ERR_INVALID, "greedy_actions: bad shape");
+  greedy_actions_kernel<<<(unsigned)B, 256, 0, s>>>(probs, values, (int)n, A, mn, mx, out);
   IBC_LAUNCH_CHECK(h);
   return IBC_OK;
 }

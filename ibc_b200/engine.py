@@ -470,6 +470,24 @@ def uniform_actions(rows: int, min_actions, max_actions, u=None, seed=0) -> torc
   return out
 
 
+def greedy_actions(probs, values, min_actions=None, max_actions=None):
+  """probs [B, n], values [B, n, A] -> [B, A]: the value at the first arg max of every row,
+  clipped to the bounds when given."""
+  _check_f32(probs, 'probs')
+  _check_f32(values, 'values')
+  b, n = probs.shape
+  a = values.shape[-1]
+  if values.numel() != b * n * a:
+    raise ValueError('values must be [B, n, A]')
+  if min_actions is not None:
+    _check_f32(min_actions, 'min_actions')
+    _check_f32(max_actions, 'max_actions')
+  out = torch.empty(b, a, device=probs.device, dtype=torch.float32)
+  _lib.check(_lib.load().ibc_greedy_actions(_ptr(probs), _ptr(values), b, n, a, _ptr(min_actions),
+                                            _ptr(max_actions), _ptr(out), _stream()))
+  return out
+
+
 def counter_examples_uniform(actions, n: int, min_actions, max_actions, u=None, seed=0):
   """[B * (n + 1), A]: n uniform negatives per row of `actions` (the samples of
   uniform_actions(B * n, ...) with the same u / seed) followed by the row itself."""

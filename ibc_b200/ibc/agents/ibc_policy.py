@@ -219,6 +219,19 @@ class GreedyPolicy:
     b = d.batch_size
     probs = d.probs.reshape(b, -1)
     values = d.mapped_values.reshape(b, probs.shape[1], -1)
+    wp = self._wrapped_policy
+    if probs.is_cuda and probs.dtype == torch.float32 and values.dtype == torch.float32:
+      # arg max, gather and clip in one launch (ibc_greedy_actions)
+      bounds = (None, None)
+      if wp._clip and hasattr(wp.action_spec, 'minimum'):
+        bounds = getattr(self, '_greedy_bounds', None)
+        if bounds is None or bounds[0].device != values.device:
+          wp._clip_to_spec(values[:1, 0])                    # creates the cached device bounds
+          a_dim = values.shape[-1]
+          bounds = tuple(v.expand(a_dim).contiguous() for v in wp._clip_bounds)
+          self._greedy_bounds = bounds
+      action = eng.greedy_actions(probs.contiguous(), values.contiguous(), *bounds)
+      return specs.PolicyStep(action, step.state, step.info)
     idx = torch.argmax(probs, dim=1)
     action = values[torch.arange(b, device=values.device), idx]
-    return specs.PolicyStep(self._wrapped_policy._clip_to_spec(action), step.state, step.info)
+    return specs.PolicyStep(wp._clip_to_spec(action), step.state, step.info)

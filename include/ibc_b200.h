@@ -193,6 +193,14 @@ int ibc_uniform_actions(const float* u, int64_t rows, int32_t A,
                         const float* min_actions, const float* max_actions,
                         uint64_t seed, float* out, void* stream);
 
+/* greedy_policy.GreedyPolicy over the MappedCategorical of ibc/agents/ibc_policy.py:96-117:
+ * out[b, :] = values[b, argmax_j probs[b, j], :] (first index of the maximum; NaN counts as the
+ * maximum, as in tf.argmax), clipped to [min_actions, max_actions] when given (both or neither;
+ * ibc_policy.py clip=True). */
+int ibc_greedy_actions(const float* probs, const float* values, int64_t B, int64_t n, int32_t A,
+                       const float* min_actions, const float* max_actions, float* out,
+                       void* stream);
+
 /* The counter-example block of a training step with uniform negatives only
  * (ibc_agent.py:340-352 and 461-473 in one pass): combined [B, N + 1, A] with
  * combined[b, j, :] = the sample ibc_uniform_actions draws for row b * N + j of a

@@ -378,6 +378,27 @@ def test_fused_langevin_kernel_is_bit_identical_to_the_three_kernel_chain():
   assert digests[0] == digests[1]
 
 
+def test_greedy_actions_is_argmax_gather_clip():
+  """ibc_greedy_actions against torch: first arg max per observation (ties and a NaN row
+  included), the mapped action, clipped."""
+  from ibc_b200 import engine as eng
+  g = torch.Generator().manual_seed(8)
+  for b, n, a in ((1, 16384, 2), (5, 300, 7), (3, 9, 28)):
+    probs = torch.rand(b, n, generator=g)
+    probs[0, n // 3] = probs[0, n - 1] = 2.0          # a tie: the first one wins
+    if b > 1:
+      probs[1, min(5, n - 1)] = float('nan')            # NaN counts as the maximum (tf.argmax)
+    values = torch.randn(b, n, a, generator=g) * 2
+    mn, mx = torch.full((a,), -1.0), torch.full((a,), 1.0)
+    idx = torch.argmax(torch.nan_to_num(probs, nan=float('inf')), dim=1)
+    idx[0] = n // 3
+    want = values[torch.arange(b), idx]
+    got = eng.greedy_actions(probs.cuda(), values.cuda())
+    assert torch.equal(got.cpu(), want)
+    got = eng.greedy_actions(probs.cuda(), values.cuda(), mn.cuda(), mx.cuda())
+    assert torch.equal(got.cpu(), want.clamp(-1.0, 1.0))
+
+
 def test_counter_examples_uniform_is_the_two_step_path():
   """ibc_counter_examples_uniform (uniform negatives + the expert action last, one launch) against
   uniform_actions followed by the two concatenations it replaces (ibc_agent.py:340-352,
