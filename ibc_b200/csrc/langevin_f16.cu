@@ -583,14 +583,14 @@ bool langevin_f16_supported(const Layout& L) {
   return !off && L.W == kW && L.A <= kAMax && L.nb >= 1 && f16_smem_bytes(L.nb) <= 227 * 1024 - 512;
 }
 
-// core: the transposed layers [rev, revp) (the block-major backward's chain weights); otherwise
-// everything else (action rows, forward layers + bias slices, dE/dact operand)
 int pack16_params(ibc_handle* h, cudaStream_t s, bool core) {
   const Packed16Layout pl = make_packed16_layout(h->L);
   if (!h->packed16) IBC_CUDA(h, cudaMalloc((void**)&h->packed16, (size_t)pl.total * 2));
   __half* out = reinterpret_cast<__half*>(h->packed16);
-  if (core) pack16_kernel<<<148, 256, 0, s>>>(h->params, h->L, pl, out, pl.rev, pl.revp, pl.revp, 0);
-  else pack16_kernel<<<148, 256, 0, s>>>(h->params, h->L, pl, out, 0, pl.total, pl.rev, pl.revp - pl.rev);
+  // core: action rows + forward layers (the training forward) + transposed layers (the backward);
+  // the rest: the dE/dact operand of the Langevin chain
+  if (core) pack16_kernel<<<148, 256, 0, s>>>(h->params, h->L, pl, out, 0, pl.revp, pl.revp, 0);
+  else pack16_kernel<<<148, 256, 0, s>>>(h->params, h->L, pl, out, pl.revp, pl.total, pl.total, 0);
   IBC_LAUNCH_CHECK(h);
   return IBC_OK;
 }

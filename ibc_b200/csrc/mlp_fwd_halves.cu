@@ -37,6 +37,7 @@ constexpr int kBiasBytes = 8 * kW * 4;
 constexpr int kLayerBytes = kLayerWBytes + kBiasBytes;   // 68 KB
 constexpr int kKSteps = kW / 8;
 constexpr int kRing = 2;     // two layers of prefetch keep the pipe fed; a third only takes L1 away from the spills
+constexpr int kLayerHBytes = kW * kW * 2 + 16 * kW * 2;  // kF16: fp16 layer + K = 16 bias slice: 36 KB
 constexpr int kEpiWarps = 8 * kNT;
 constexpr int kThreads = (kEpiWarps + 4) * 32;           // + producer, two issuers, one idle warp
 // 640 threads launch with 96 registers (61 440 in the CTA's pool); setmaxnreg then gives the
@@ -47,6 +48,8 @@ struct FwdHalvesParams {
   const float* act;      // [R, A]
   const float* hp;       // [B, W]  obs . Wp[:O] + bp
   const float* packed;
+  const __half* packed16;  // kF16: fp16 operand images (Packed16Layout: p0, forward layer blocks)
+  int64_t off16_p0, off16_fwd;
   float* E;              // [R]
   uint4* xa16;           // kSave == 2: fp16 operands [tile][2nb slots][16 chunks of 8][128 rows][16 B]
   float* hn_save;        // kSave == 2: final residual stream [tile][32 chunks][128 rows][4] (fp32)
@@ -75,14 +78,19 @@ __device__ __forceinline__ void pipe_release(int* lock) { atomicExch(lock, 0); }
 
 // kSave: 0 = energies only; 2 = fp16 operand tiles + h_nb + masks (the block-major backward's
 // inputs, mlp_bwd_wgrad.cu)
-template <int kSave>
+// kF16: the dependent GEMMs in kind::f16 (the training forward: its operands ARE the fp16 tiles
+// it saves; same 11-bit significand as tf32, see langevin_f16.cu): half the MMA time per layer
+// and fewer integer-pipe operations per element (pack once, relu on packed pairs).  The A operand
+// is packed two K-elements per column in the first 16 columns of each 32-column chunk.
+template <int kSave, bool kF16>
 __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_halves_kernel(FwdHalvesParams p) {
   using TT = TrainTile<kW>;
   constexpr int W = kW;
   extern __shared__ __align__(128) unsigned char smem[];
   const int nsteps = 2 * p.nb + 1;
-  unsigned char* ring = smem;                                         // [kRing][68 KB]
-  unsigned char* p0_buf = ring + (size_t)kRing * kLayerBytes;         // step-0 operand [KP/4][W][4]
+  constexpr int kSlot = kF16 ? kLayerHBytes : kLayerBytes;
+  unsigned char* ring = smem;                                         // [kRing][68 KB] (fp16: 36 KB)
+  unsigned char* p0_buf = ring + (size_t)kRing * kLayerBytes;         // step-0 operand [KP/4][W][4] (fp16: [2][W][8])
   float4* ones_tile = reinterpret_cast<float4*>(p0_buf + (size_t)p.KP * W * 4);   // [2][128]
   float* we = reinterpret_cast<float*>(ones_tile + 256);              // we[W], be
   float* e_part = we + W + 4;                                         // [kNT][128]
@@ -106,8 +114,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_halves_kernel(FwdHalvesPa
     mbar_init(p0_full, 1);
     fence_mbar_init();
   }
-  for (int i = tid; i < 256; i += kThreads)
-    ones_tile[i] = (i < 128) ? make_float4(1.f, 1.f, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < 256; i += kThreads) {
+    if (kF16)      // (1, 1, 0 x 6) in fp16 per row of chunk 0
+      reinterpret_cast<uint4*>(ones_tile)[i] = (i < 128) ? make_uint4(0x3C003C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    else
+      ones_tile[i] = (i < 128) ? make_float4(1.f, 1.f, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int i = tid; i < W + 4; i += kThreads) we[i] = p.packed[p.off_we + i];
   fence_proxy_async_smem();
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -128,6 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_halves_kernel(FwdHalvesPa
     const uint32_t col_y = col_x + W;
     const float* we_h = we + half * 64;
     uint32_t ph_d = 0;
+    uint32_t peak2 = 0;     // kF16: running max of the packed operands (range check)
     for (int k = 0;; ++k) {
       int64_t tile0;
       const int n = work_item(p.work, k, tile0);
@@ -137,13 +150,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_halves_kernel(FwdHalvesPa
       const int64_t r = tile_id * 128 + row;
       const bool valid = r < p.R;
       if (half == 0) {   // step-0 operand: this row's action (zero padded) into X[:, 0:32)
-        uint32_t v[16];
+        if (kF16) {      // 16 action dimensions as 8 packed columns
+          uint32_t v[8];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+          for (int q = 0; q < 8; ++q)
+            v[q] = pack_half2((valid && 2 * q < p.A) ? p.act[r * p.A + 2 * q] : 0.f,
+                              (valid && 2 * q + 1 < p.A) ? p.act[r * p.A + 2 * q + 1] : 0.f);
+          tmem_st_n<8>(col_x, v);
+        } else {
+          uint32_t v[16];
 #pragma unroll
-          for (int q = 0; q < 16; ++q)
-            v[q] = (valid && c * 16 + q < p.A) ? tf32_rn_bits(__float_as_uint(p.act[r * p.A + c * 16 + q])) : 0u;
-          tmem_st16(col_x + c * 16, v);
+          for (int c = 0; c < 2; ++c) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              v[q] = (valid && c * 16 + q < p.A) ? tf32_rn_bits(__float_as_uint(p.act[r * p.A + c * 16 + q])) : 0u;
+            tmem_st16(col_x + c * 16, v);
+          }
         }
         tmem_st_wait();
       }
@@ -193,13 +215,29 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_halves_kernel(FwdHalvesPa
             if (!kLast) {
               // mask bit from the FMA pipe: the sign of 0 - x is set exactly when x > 0
               if (kSave) nbits = __funnelshift_l(__float_as_uint(__fsub_rn(0.f, __uint_as_float(xb))), nbits, 1);
-              xb = relu_tf32_bits(xb);     // relu + round in one VIADDMNMX
+              if (!kF16) xb = relu_tf32_bits(xb);     // relu + round in one VIADDMNMX
             }
             v[q] = xb;
           }
-          if (!kLast) tmem_st16(col_a + c * 16, v);
           if (kSave && !kLast && (c & 1)) { mb[c >> 1] = __brev(nbits); nbits = 0; }
-          if (kSave == 2 && !kLast) {
+          if (kF16 && !kLast) {
+            // pack once: the packed pairs are the next operand (relu on the pairs) AND the saved
+            // tile; 16 columns = 8 words = two 16-byte pieces of the tile
+            uint32_t w[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              w[q] = hmax2_bits(pack_half2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), 0u);
+              peak2 = hmax2_bits(peak2, w[q]);
+            }
+            tmem_st_n<8>(col_a + (uint32_t)((c >> 1) * 32 + (c & 1) * 8), w);
+            if (kSave == 2) {
+              uint4* h_slot = p.xa16 + (tile_id * (nsteps - 1) + i) * (int64_t)(16 * 128) + row;
+              h_slot[(half * 8 + c * 2 + 0) * 128] = make_uint4(w[0], w[1], w[2], w[3]);
+              h_slot[(half * 8 + c * 2 + 1) * 128] = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+          }
+          if (!kF16 && !kLast) tmem_st16(col_a + c * 16, v);
+          if (!kF16 && kSave == 2 && !kLast) {
             // what the tensor core reads of the operand (low 13 bits truncated), as fp16: the
             // operand carries the round-to-nearest offset, so convert toward zero
             uint4* h_slot = p.xa16 + (tile_id * (nsteps - 1) + i) * (int64_t)(16 * 128) + row;
@@ -248,12 +286,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_halves_kernel(FwdHalvesPa
       }
       step(T_{}, T_{}, 2 * p.nb);       // last block's second Dense + Dense(1)
     }
+    // cvt.satfinite clamps at 65 504 = 0x7BFF: an operand that reached it left fp16's range
+    if (kF16 && ((peak2 & 0xFFFFu) >= 0x7BFFu || (peak2 >> 16) >= 0x7BFFu) && p.status)
+      atomicCAS(p.status, 0, 5002);
   } else if (warp == kEpiWarps) {
     // ===================== producer: one bulk copy per layer ==================
     setmaxnreg_dec<kServiceRegs>();
     if (elect_one()) {    // the action rows of Wp stay resident for the whole kernel
-      mbar_arrive_expect_tx(p0_full, (uint32_t)(W * p.KP * 4));
-      bulk_g2s(p0_buf, p.packed + p.off_fwd_p, (uint32_t)(W * p.KP * 4), p0_full);
+      if (kF16) {
+        mbar_arrive_expect_tx(p0_full, (uint32_t)(W * 16 * 2));
+        bulk_g2s(p0_buf, p.packed16 + p.off16_p0, (uint32_t)(W * 16 * 2), p0_full);
+      } else {
+        mbar_arrive_expect_tx(p0_full, (uint32_t)(W * p.KP * 4));
+        bulk_g2s(p0_buf, p.packed + p.off_fwd_p, (uint32_t)(W * p.KP * 4), p0_full);
+      }
     }
     __syncwarp();
     uint32_t q = 0;
@@ -265,10 +311,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_halves_kernel(FwdHalvesPa
         const uint32_t ph = (q / kRing) & 1;
         if (elect_one()) {
           mbar_wait(&w_empty[slot], ph ^ 1, abort_flag, p.status, 4100 + i);
-          mbar_arrive_expect_tx(&w_full[slot], (uint32_t)kLayerBytes);
-          bulk_g2s(ring + (size_t)slot * kLayerBytes,
-                   p.packed + p.off_fwd_lb + (int64_t)(i - 1) * (kLayerBytes / 4),
-                   (uint32_t)kLayerBytes, &w_full[slot]);
+          mbar_arrive_expect_tx(&w_full[slot], (uint32_t)kSlot);
+          if (kF16)
+            bulk_g2s(ring + (size_t)slot * kSlot, p.packed16 + p.off16_fwd + (int64_t)(i - 1) * (kSlot / 2),
+                     (uint32_t)kSlot, &w_full[slot]);
+          else
+            bulk_g2s(ring + (size_t)slot * kSlot,
+                     p.packed + p.off_fwd_lb + (int64_t)(i - 1) * (kSlot / 4),
+                     (uint32_t)kSlot, &w_full[slot]);
         }
         __syncwarp();
       }
@@ -317,13 +367,27 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_halves_kernel(FwdHalvesPa
           tc_fence_after();
           pipe_acquire(&s_pipe, abort_flag);
           if (p.dbg && blockIdx.x == 0 && k == 1 && i < 40) p.dbg[(i * kNT + t) * 2] = clock64();
-          if (i == 0) {
+          if (kF16) {
+            const uint32_t idesc16 = idesc_f16(128, W);
+            if (i == 0) {        // K = 16 action dimensions: one MMA
+              mma_f16_ts(d_tmem, a_tmem, smem_desc(smem_u32(p0_buf), b_lbo, sbo), idesc16, 0u);
+            } else {
+              const uint32_t layer = smem_u32(ring + (size_t)slot * kSlot);
+              const uint64_t bd = smem_desc(layer, b_lbo, sbo);
+#pragma unroll
+              for (int ks = 0; ks < W / 16; ++ks)      // packed A: 8 columns per K-step, two per chunk
+                mma_f16_ts(d_tmem, a_tmem + (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8),
+                           bd + (uint64_t)(ks * b_step16), idesc16, (uint32_t)(ks > 0));
+              mma_f16_ss(d_tmem, ones_desc, smem_desc(layer + W * W * 2, b_lbo, sbo), idesc16, 1u);   // + bias
+              mma_commit(&w_empty[slot]);
+            }
+          } else if (i == 0) {
             const uint64_t b_desc0 = smem_desc(smem_u32(p0_buf), b_lbo, sbo);
             for (int ks = 0; ks < p.KP / 8; ++ks)
               mma_tf32_ts(d_tmem, a_tmem + (uint32_t)(ks * 8), b_desc0 + (uint64_t)(ks * b_step16),
                           idesc, (uint32_t)(ks > 0));
           } else {
-            const uint32_t layer = smem_u32(ring + (size_t)slot * kLayerBytes);
+            const uint32_t layer = smem_u32(ring + (size_t)slot * kSlot);
             mma_tf32_ts_steps<kKSteps>(d_tmem, a_tmem, smem_desc(layer, b_lbo, sbo), b_step16,
                                        idesc, 0u);
             // + bias: (1, 1, 0, ...) . (hi, lo, 0, ...)^T, the slice behind the weights
@@ -346,10 +410,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_halves_kernel(FwdHalvesPa
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-template <int kSave>
+template <int kSave, bool kF16>
 int launch_halves(ibc_handle* h, FwdHalvesParams& p, int grid, cudaStream_t s) {
-  IBC_RAISE_SMEM(h, mlp_fwd_halves_kernel<kSave>, 227 * 1024 - 512);
-  mlp_fwd_halves_kernel<kSave><<<grid, kThreads, halves_smem_bytes(p.KP), s>>>(p);
+  IBC_RAISE_SMEM(h, (mlp_fwd_halves_kernel<kSave, kF16>), 227 * 1024 - 512);
+  mlp_fwd_halves_kernel<kSave, kF16><<<grid, kThreads, halves_smem_bytes(p.KP), s>>>(p);
   IBC_LAUNCH_CHECK(h);
   return IBC_OK;
 }
@@ -374,14 +438,25 @@ int tmem_forward_halves(ibc_handle* h, const float* act, int64_t R, int64_t n, c
   p.off_fwd_p = pl.fwd_p; p.off_fwd_lb = pl.fwd_lb;
   p.off_we = pl.vecs + (int64_t)(2 * L.nb + 1) * L.W;
   p.status = h->dev_status;
+  p.packed16 = nullptr; p.off16_p0 = 0; p.off16_fwd = 0;
   p.dbg = nullptr;
   static const bool want_dbg = getenv("IBC_DBG_TIMELINE") != nullptr;
   if (want_dbg) {
     IBC_CUDA(h, cudaMalloc((void**)&p.dbg, 1024 * sizeof(long long)));
     IBC_CUDA(h, cudaMemsetAsync(p.dbg, 0, 1024 * sizeof(long long), s));
   }
-  if (xa16) IBC_TRY(launch_halves<2>(h, p, grid, s));
-  else IBC_TRY(launch_halves<0>(h, p, grid, s));
+  // the training forward runs its GEMMs in kind::f16 (act_dim <= 16; IBC_FWD_TF32=1 keeps tf32)
+  const bool f16 = xa16 && L.A <= 16 && h->packed16 && getenv("IBC_FWD_TF32") == nullptr;
+  if (f16) {
+    const Packed16Layout p16 = make_packed16_layout(L);
+    p.packed16 = reinterpret_cast<const __half*>(h->packed16);
+    p.off16_p0 = p16.p0; p.off16_fwd = p16.fwd;
+    IBC_TRY((launch_halves<2, true>(h, p, grid, s)));
+  } else if (xa16) {
+    IBC_TRY((launch_halves<2, false>(h, p, grid, s)));
+  } else {
+    IBC_TRY((launch_halves<0, false>(h, p, grid, s)));
+  }
   if (p.dbg) {
     cudaStreamSynchronize(s);
     std::vector<long long> hb(1024);

@@ -805,11 +805,12 @@ def test_train_grads_block_major_backward_matches_the_split_kernels(spec, b, n, 
   per_b, _, en_b, g_b = e.train_grads(obs_d, act_d, n, cfg, b, want_energies=True)
   g_b = g_b.double().cpu().clone()
   assert e.kernel_status() == 0
-  # the two forwards (eight epilogue warps per tile / one thread per row) run the same MMAs and
-  # differ in the order of the 128-term fp32 sum of Dense(1)
+  # the fused step's forward runs its GEMMs in kind::f16 on the fp16 tiles it saves, the split
+  # step's in kind::tf32: the same 11-bit significand with different tie / range handling
+  # (measured 1.1e-4 of the energy span); both are held to the fp32 path below
   espan = float(en_b.abs().max())
-  assert float((en_a - en_b).abs().max()) <= 4e-6 * espan
-  assert float((per_a - per_b).abs().max()) <= 1e-5 * max(1.0, float(per_b.abs().max()))
+  assert float((en_a - en_b).abs().max()) <= 1e-3 * espan
+  assert float((per_a - per_b).abs().max()) <= 2e-3 * max(1.0, float(per_b.abs().max()))
   _close(en_a, en_f, 4 * TF32_TOL, 'energies')
   assert bool(torch.isfinite(g_a).all())
   grms = float(g_f.pow(2).mean().sqrt())
@@ -828,10 +829,12 @@ def test_train_grads_block_major_backward_matches_the_split_kernels(spec, b, n, 
       # bias gradients are fp32 column sums of dY in both paths, but cancelling ones (the InfoNCE
       # cotangents sum to zero over a row group), and the block-major backward parks the residual
       # gradient between blocks as fp16 (one 11-bit rounding of the running sum per block):
-      # measured mutual differences 1e-4 .. 1.7e-2 where the split path itself is 2e-2 .. 4e-2
-      # from fp32
+      # and its forward runs in kind::f16 where the split path's runs in kind::tf32 (different
+      # ReLU mask flips).  The two are independent approximations of the fp32 gradient: their
+      # mutual difference is bounded by sqrt(2) x the split path's own error (measured up to
+      # 0.72 x: b1_4 3.4e-2 against 4.7e-2)
       mutual = float((g_a[off:off + cnt] - g_b[off:off + cnt]).norm()) / denom
-      assert mutual <= 0.5 * rel_b + 2e-3, (name, mutual, rel_b)
+      assert mutual <= 1.5 * rel_b + 2e-3, (name, mutual, rel_b)
 
 
 def test_adam_step_matches_oracle():
