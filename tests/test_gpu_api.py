@@ -357,8 +357,8 @@ def test_c2_training_curves_tf32_tracks_fp32():
   a cancelling InfoNCE gradient), so the question is whether that matters for training.  The
   task is learnable (action = 0.8 tanh(obs . M), fresh batches every step); the loss curves
   must track each other -- every 50-step window mean within 15 %, the mean over the second
-  half of training within 8 % (the run-to-run spread of the tf32 trajectory itself) -- and both must have learned (last window below 80 % of the
-  first)."""
+  half of training within 8 % (the run-to-run spread of the tf32 trajectory itself) -- and both
+  must have learned (last window below 80 % of the first)."""
   import bench
   from ibc_b200 import _lib
   c = dict(bench.CFG, batch=128, lr=3e-4)
