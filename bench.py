@@ -417,7 +417,7 @@ def run_b200(args):
       # backward reads, D fp16 operand tiles + the fp32 final residual + D mask bit-planes per
       # row; the backward also writes g0 (fp32) -- its parked gradients are L2 traffic.
       fflops = rows * fwd_flops_per_row()
-      names = ['mlp_fwd_halves_kernel<2> (fused forward, fp16 operand tiles + ReLU masks saved)',
+      names = ['mlp_fwd_halves_kernel<2, true> (fused forward in kind::f16, fp16 operand tiles + ReLU masks saved)',
                'info_nce_kernel',
                'mlp_bwd_wgrad_tmem_kernel (block-major reverse chain + weight gradients)',
                '(weight gradients: inside the backward kernel)',

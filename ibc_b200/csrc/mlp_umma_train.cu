@@ -1064,7 +1064,7 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
     IBC_LAUNCH_CHECK(h);
   }
   if (L.O <= 32 && W == kW) {     // dWp[:O] = obs^T . sum_n g0 and dbp in one launch
-    const int rpb = 16;
+    const int rpb = 4;      // 128 blocks for B = 512: the launch is latency, not work
     first_layer_obs_grads_kernel<32><<<(unsigned)((B + rpb - 1) / rpb), kW, 0, s>>>(
         obs, gsum, B, L.O, rpb, grads + L.wp, grads + L.bp);
     IBC_LAUNCH_CHECK(h);

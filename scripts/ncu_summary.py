@@ -46,7 +46,7 @@ def main():
       units = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}      # one unit per COLUMN
       return (rd * units.get(rows[1][hdr.index('dram__bytes_read.sum')], 1) +
               wr * units.get(rows[1][hdr.index('dram__bytes_write.sum')], 1))
-    out = {'forward': traffic(first('mlp_fwd_halves_kernel<2>')), 'forward_nosave': traffic(first('mlp_fwd_halves_kernel<0>')),
+    out = {'forward': traffic(first('mlp_fwd_halves_kernel<2')), 'forward_nosave': traffic(first('mlp_fwd_halves_kernel<0')),
            'backward': traffic(first('mlp_bwd_wgrad_tmem_kernel')), 'info_nce': traffic(first('info_nce_kernel')),
            'first_layer': traffic(first('first_layer_grads_tiled_kernel')),
            'source': out_csv, 'unit': 'bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)'}
