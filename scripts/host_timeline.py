@@ -5,8 +5,6 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
-from ibc_b200.ibc.agents import ibc_agent
-from ibc_b200 import engine as eng
 
 device = torch.device('cuda', 0); torch.cuda.set_device(0)
 c = bench.CFG
