@@ -94,6 +94,12 @@ SIGNATURES = {
                                  c_void_p]),
     'ibc_uniform_actions': (c_int, [c_void_p, c_int64, c_int32, c_void_p,
                                     c_void_p, c_uint64, c_void_p, c_void_p]),
+    'ibc_peer_alloc': (c_int, [c_int64, c_void_p, c_void_p]),
+    'ibc_peer_open': (c_int, [c_void_p, c_void_p]),
+    'ibc_peer_close': (c_int, [c_void_p, c_int32]),
+    'ibc_peer_allreduce_adam': (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p,
+                                        c_void_p, c_void_p, c_float, c_float, c_float, c_float,
+                                        c_void_p, c_void_p, c_void_p]),
     'ibc_greedy_actions': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
     'ibc_counter_examples_uniform': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'lib', 'obj')
 LIB = os.path.join(HERE, 'lib', 'libibc_b200.so')
-SOURCES = ['api.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'mlp_simt.cu', 'mlp_umma.cu', 'mlp_umma_train.cu', 'mlp_umma_tmem.cu', 'mlp_bwd_wgrad.cu', 'mlp_fwd_halves.cu', 'mlp_wide.cu', 'langevin_tmem.cu', 'langevin_f16.cu', 'langevin256.cu', 'pixel.cu', 'samplers.cu',
+SOURCES = ['api.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'mlp_simt.cu', 'mlp_umma.cu', 'mlp_umma_train.cu', 'mlp_umma_tmem.cu', 'mlp_bwd_wgrad.cu', 'mlp_fwd_halves.cu', 'mlp_wide.cu', 'langevin_tmem.cu', 'langevin_f16.cu', 'peer_allreduce.cu', 'langevin256.cu', 'pixel.cu', 'samplers.cu',
            'losses.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',
               '-std=c++17', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']

@@ -228,6 +228,33 @@ int ibc_uniform_actions(const float* u, int64_t rows, int32_t A, const float* mi
   return uniform_actions(h, u, rows, A, min_actions, max_actions, seed, out, (cudaStream_t)stream);
 }
 
+int ibc_peer_alloc(int64_t bytes, void** ptr, void* handle64) {
+  ibc_handle* h = nullptr;
+  return peer_alloc(h, bytes, ptr, handle64);
+}
+
+int ibc_peer_open(const void* handle64, void** ptr) {
+  ibc_handle* h = nullptr;
+  return peer_open(h, handle64, ptr);
+}
+
+int ibc_peer_close(void* ptr, int32_t owned) {
+  ibc_handle* h = nullptr;
+  return peer_close(h, ptr, owned);
+}
+
+int ibc_peer_allreduce_adam(const float* const* peer_grads, int32_t* const* peer_flags, int32_t rank,
+                            int32_t world, int32_t epoch, int64_t count, float* params, float* m,
+                            float* v, float lr_t, float beta1, float beta2, float epsilon,
+                            float* tail_out, int32_t* status, void* stream) {
+  ibc_handle* h = nullptr;
+  if (!peer_grads || !peer_flags || !params || !m || !v)
+    IBC_FAIL(h, IBC_ERR_INVALID, "ibc_peer_allreduce_adam: null argument");
+  return peer_allreduce_adam(h, peer_grads, reinterpret_cast<int* const*>(peer_flags), rank, world, epoch,
+                             count, params, m, v, lr_t, beta1, beta2, epsilon, tail_out,
+                             reinterpret_cast<int*>(status), (cudaStream_t)stream);
+}
+
 int ibc_greedy_actions(const float* probs, const float* values, int64_t B, int64_t n, int32_t A,
                        const float* min_actions, const float* max_actions, float* out, void* stream) {
   ibc_handle* h = nullptr;

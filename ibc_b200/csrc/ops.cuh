@@ -14,6 +14,12 @@ int softmax_rows(ibc_handle* h, const float* logits, int64_t B, int64_t n, float
                  float* probs, cudaStream_t s);
 int uniform_actions(ibc_handle* h, const float* u, int64_t rows, int A, const float* mn,
                     const float* mx, uint64_t seed, float* out, cudaStream_t s);
+int peer_alloc(ibc_handle* h, int64_t bytes, void** ptr, void* handle64);
+int peer_open(ibc_handle* h, const void* handle64, void** ptr);
+int peer_close(ibc_handle* h, void* ptr, int owned);
+int peer_allreduce_adam(ibc_handle* h, const float* const* peer_grads, int* const* peer_flags, int rank,
+                        int world, int epoch, int64_t n, float* params, float* m, float* v, float lr_t,
+                        float b1, float b2, float eps, float* tail_out, int* status, cudaStream_t s);
 int greedy_actions(ibc_handle* h, const float* probs, const float* values, int64_t B, int64_t n, int A,
                    const float* mn, const float* mx, float* out, cudaStream_t s);
 int uniform_combined(ibc_handle* h, const float* u, int64_t B, int64_t N, int A, const float* mn,

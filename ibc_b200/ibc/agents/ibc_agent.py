@@ -468,7 +468,31 @@ class ImplicitBCAgent(BehavioralCloningAgent):
       if not math.isfinite(float(host[0])):
         raise FloatingPointError('Loss is inf or nan')
 
+  def _peer_reducer(self):
+    """parallel.PeerReducer of this agent, created on the first multi-replica step (None: NCCL).
+    Only where the flat gradient leaves the engine as it is all-reduced (no spectral-norm chain
+    rule in between) and Adam is the plain optimizer class."""
+    if not hasattr(self, '_peer'):
+      net = self.cloning_network
+      plain = (parallel.num_replicas() > 1 and net.params.is_cuda
+               and getattr(net, '_sn_u', None) is None
+               and hasattr(self._optimizer, 'apply_gradients_peer'))
+      self._peer = parallel.PeerReducer.create(net.params.numel(), net.params.device) if plain else None
+    return self._peer
+
   def _train(self, experience, weights=None, draws=None):
+    peer = self._peer_reducer()
+    if peer is not None:
+      # gradients go straight into this step's peer-visible buffer; sum + Adam are one launch
+      step = self._optimizer.iterations
+      self._grads = peer.buffer(step)
+      loss_info, grads = self._loss(experience, weights=weights, training=True, draws=draws)
+      self._optimizer.apply_gradients_peer(self.cloning_network, peer, step)
+      # d/d be summed over ALL replicas is non-finite as soon as any replica's loss is:
+      # every rank sees it (0 * (inf | nan) = nan)
+      self._check_finite(loss_info.loss + peer.tail[0] * 0.0)
+      self.train_step_counter += 1
+      return loss_info
     loss_info, grads = self._loss(experience, weights=weights, training=True, draws=draws)
     parallel.allreduce_gradients(grads)                         # MirroredStrategy all-reduce
     probe = loss_info.loss

@@ -54,6 +54,18 @@ class Adam:
     self.iterations += 1
     network.params_changed()
 
+  def apply_gradients_peer(self, network, reducer, step: int):
+    """The same update with the data-parallel gradient sum inside the launch
+    (parallel.PeerReducer: every replica reads its peers' gradients over NVLink)."""
+    params = network.params
+    if self.m is None:
+      self.m = torch.zeros_like(params)
+      self.v = torch.zeros_like(params)
+    reducer.reduce_and_adam(step, params, self.m, self.v, self.lr_t(), self.beta_1, self.beta_2,
+                            self.epsilon)
+    self.iterations += 1
+    network.params_changed()
+
 
 def get_agent(loss_type, time_step_tensor_spec, action_tensor_spec, action_sampling_spec,
               obs_norm_layer, act_norm_layer, act_denorm_layer, learning_rate, use_warmup,

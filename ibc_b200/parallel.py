@@ -34,6 +34,121 @@ def _side_stream(device) -> 'torch.cuda.Stream':
   return _side_streams[key]
 
 
+class _RawDeviceMemory:
+  """__cuda_array_interface__ over memory the library allocated (kept alive by `owner`)."""
+
+  def __init__(self, ptr, numel, typestr, owner):
+    self.owner = owner
+    self.__cuda_array_interface__ = {'shape': (numel,), 'typestr': typestr, 'data': (ptr, False),
+                                     'version': 2, 'strides': None}
+
+
+def _device_view(ptr, numel, dtype, device, owner) -> torch.Tensor:
+  typestr = {torch.float32: '<f4', torch.int32: '<i4'}[dtype]
+  return torch.as_tensor(_RawDeviceMemory(ptr, numel, typestr, owner), device=device)
+
+
+class PeerReducer:
+  """Gradient all-reduce + Adam in one launch over NVLink peer memory (ibc_peer_allreduce_adam).
+
+  Every rank owns two gradient buffers (step parity) and a flag array; their CUDA IPC handles are
+  exchanged once through the process group, so that each rank's kernel can read every peer's
+  gradient directly.  One node, 2..8 ranks, one GPU per rank.  `create` returns None when the
+  set-up is not possible (single replica, gloo / CPU, peer access missing, IBC_PEER_ALLREDUCE=0):
+  the caller then keeps the NCCL all-reduce."""
+
+  def __init__(self, numel: int, device):
+    import ctypes
+    from ibc_b200 import _lib
+    self._lib = _lib
+    lib = _lib.load()
+    self.rank, self.world = replica_rank(), num_replicas()
+    self.numel = numel
+    # one allocation per rank, made by the library (its IPC handle names it at offset 0):
+    # [gradient, even steps | gradient, odd steps | flags (64 ints)]
+    stride = (numel * 4 + 255) // 256 * 256
+    self._bytes = 2 * stride + 256
+    with torch.cuda.device(device):
+      base = ctypes.c_void_p()
+      handle = ctypes.create_string_buffer(64)
+      _lib.check(lib.ibc_peer_alloc(self._bytes, ctypes.byref(base), handle))
+      self._base = base.value
+      everyone = [None] * self.world
+      dist.all_gather_object(everyone, bytes(handle.raw))
+      self._opened = []
+      bases = []
+      for r, hd in enumerate(everyone):
+        if r == self.rank:
+          bases.append(self._base)
+          continue
+        q = ctypes.c_void_p()
+        _lib.check(lib.ibc_peer_open(ctypes.create_string_buffer(hd, 64), ctypes.byref(q)))
+        self._opened.append(q.value)
+        bases.append(q.value)
+    self.bufs = [_device_view(self._base + k * stride, numel, torch.float32, device, self) for k in range(2)]
+    arr = ctypes.c_void_p * 8
+    pad = [None] * (8 - self.world)
+    self._g = [arr(*([x + k * stride for x in bases] + pad)) for k in range(2)]
+    self._f = arr(*([x + 2 * stride for x in bases] + pad))
+    self.tail = torch.zeros(1, device=device, dtype=torch.float32)
+    self.status = torch.zeros(1, device=device, dtype=torch.int32)
+    self.epoch = 0
+    torch.cuda.synchronize(device)
+    dist.barrier()
+
+  def close(self):
+    """Unmaps the peers' buffers and frees this rank's (all ranks, after their last step)."""
+    if getattr(self, '_base', None):
+      lib = self._lib.load()
+      torch.cuda.synchronize()
+      dist.barrier()                 # no peer still reads this rank's buffers
+      for q in self._opened:
+        lib.ibc_peer_close(q, 0)
+      lib.ibc_peer_close(self._base, 1)
+      self._base, self._opened, self.bufs = None, [], []
+
+  @classmethod
+  def create(cls, numel: int, device):
+    import os
+    if num_replicas() < 2 or num_replicas() > 8 or os.environ.get('IBC_PEER_ALLREDUCE', '1') == '0':
+      return None
+    if torch.device(device).type != 'cuda' or dist.get_backend() != 'nccl':
+      return None
+    ok = torch.ones(1, device=device)
+    try:
+      red = cls(numel, device)
+    except Exception as e:                      # noqa: BLE001 -- any failure: keep NCCL
+      red = None
+      ok.zero_()
+      import warnings
+      warnings.warn('peer-memory all-reduce unavailable (%s): using NCCL' % (e,))
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)    # all ranks take the same path
+    return red if float(ok) > 0 else None
+
+  def buffer(self, step: int) -> torch.Tensor:
+    """The gradient buffer of this step (its parity): what train_grads writes."""
+    return self.bufs[step & 1]
+
+  def reduce_and_adam(self, step: int, params, m, v, lr_t, beta1, beta2, epsilon):
+    """Sum of all replicas' bufs[step & 1], Adam on this replica's (params, m, v); self.tail
+    holds the reduced last gradient entry afterwards."""
+    import ctypes
+    self.epoch += 1
+    lib = self._lib.load()
+    self._lib.check(lib.ibc_peer_allreduce_adam(
+        self._g[step & 1], self._f, self.rank, self.world, self.epoch, self.numel,
+        ctypes.c_void_p(params.data_ptr()), ctypes.c_void_p(m.data_ptr()), ctypes.c_void_p(v.data_ptr()),
+        float(lr_t), float(beta1), float(beta2), float(epsilon), ctypes.c_void_p(self.tail.data_ptr()),
+        ctypes.c_void_p(self.status.data_ptr()),
+        ctypes.c_void_p(torch.cuda.current_stream(params.device).cuda_stream)))
+
+  def check(self):
+    """Raises if a reduction timed out waiting for a peer (device sync)."""
+    st = int(self.status.item())
+    if st:
+      raise RuntimeError('peer-memory all-reduce failed: kernel status %d (a peer did not arrive)' % st)
+
+
 def allreduce_gradients(flat_grads: torch.Tensor) -> torch.Tensor:
   """In-place SUM over replicas of the flat gradient vector."""
   if num_replicas() > 1:

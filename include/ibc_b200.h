@@ -193,6 +193,27 @@ int ibc_uniform_actions(const float* u, int64_t rows, int32_t A,
                         const float* min_actions, const float* max_actions,
                         uint64_t seed, float* out, void* stream);
 
+/* Data-parallel training over NVLink peer memory: the MirroredStrategy gradient sum
+ * (ibc/agents/base_agent.py:50-58, ibc/train_eval.py:163) and the Adam update
+ * (ibc/train/get_agent.py:76-84) in one launch.  peer_grads[r] / peer_flags[r] are rank r's
+ * gradient buffer of this step's parity and its flag array (>= world ints, zero at start) as
+ * mapped into THIS process (CUDA IPC); epoch increases by one per call on every rank.  The kernel
+ * publishes the epoch to every peer, waits (bounded: status 6001) for all peers, sums the
+ * gradients in rank order and applies Adam to the local replica; tail_out (optional) receives
+ * the reduced last entry.
+ * ibc_peer_alloc makes one zeroed device allocation on the current device and writes its 64-byte
+ * CUDA IPC handle to handle64; ibc_peer_open maps a peer process's handle into the current
+ * device's address space (peer access over NVLink); ibc_peer_close unmaps (owned = 0) or frees
+ * (owned = 1).  The handles travel between the ranks by any host channel (the process group). */
+int ibc_peer_alloc(int64_t bytes, void** ptr, void* handle64);
+int ibc_peer_open(const void* handle64, void** ptr);
+int ibc_peer_close(void* ptr, int32_t owned);
+int ibc_peer_allreduce_adam(const float* const* peer_grads, int32_t* const* peer_flags,
+                            int32_t rank, int32_t world, int32_t epoch, int64_t count,
+                            float* params, float* m, float* v, float lr_t, float beta1,
+                            float beta2, float epsilon, float* tail_out, int32_t* status,
+                            void* stream);
+
 /* greedy_policy.GreedyPolicy over the MappedCategorical of ibc/agents/ibc_policy.py:96-117:
  * out[b, :] = values[b, argmax_j probs[b, j], :] (first index of the maximum; NaN counts as the
  * maximum, as in tf.argmax), clipped to [min_actions, max_actions] when given (both or neither;

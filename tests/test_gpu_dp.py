@@ -5,7 +5,8 @@
 ibc/agents/base_agent.py:50-58), and must reproduce the one-rank gradient of the whole batch:
 1e-5 relative in fp32 (reduction order), 2e-3 per tensor in tf32 (the fp16 dY scale of the
 block-major backward is taken per rank).  Skipped with fewer than two GPUs; also covers the
-observation-sharded policy (row e2): two ranks' actions == the one-rank batched actions."""
+observation-sharded policy (row e2): two ranks' actions == the one-rank batched actions, and the
+peer-memory all-reduce + Adam kernel (parallel.PeerReducer) against NCCL all-reduce + Adam."""
 import os
 import subprocess
 import sys
@@ -80,6 +81,69 @@ got, sl = parallel.sharded_policy_action(policy, ts, draws=draws_local)
 if sl != (lo, hi) or got.shape != want.shape or not torch.equal(got, want):
   ok = False
   print('SHARDED POLICY MISMATCH', rank, float((got - want).abs().max()), flush=True)
+# peer-memory all-reduce + Adam (parallel.PeerReducer, one launch) against NCCL all-reduce +
+# ibc_adam_step on the SAME per-rank gradient vectors, four consecutive steps (both parities
+# twice): equal up to the fused-multiply-add contraction of two separately compiled kernels
+# (a few ulp: 1e-6 relative + absolute); the replicas themselves stay bit-identical (below)
+numel = 268_801
+red = parallel.PeerReducer.create(numel, torch.device('cuda', rank))
+if red is None:
+  ok = False
+  print('PEER REDUCER NOT CREATED', rank, flush=True)
+else:
+  gen = torch.Generator(device='cuda').manual_seed(5)
+  state = [torch.randn(numel, device='cuda', generator=gen) for _ in range(3)]
+  state[2].abs_()
+  mine = [x.clone() for x in state]
+  ref = [x.clone() for x in state]
+  for step in range(4):
+    gvec = torch.randn(numel, device='cuda', generator=torch.Generator(device='cuda').manual_seed(100 * step + rank))
+    red.buffer(step).copy_(gvec)
+    red.reduce_and_adam(step, mine[0], mine[1], mine[2], 1e-3 * (step + 1), 0.9, 0.999, 1e-7)
+    summed = gvec.clone()
+    dist.all_reduce(summed)
+    eng.adam_step(ref[0], summed, ref[1], ref[2], 1e-3 * (step + 1), 0.9, 0.999, 1e-7)
+    red.check()
+    close = lambda x, y: torch.allclose(x, y, rtol=1e-6, atol=1e-6)
+    if not (close(mine[0], ref[0]) and close(mine[1], ref[1]) and close(mine[2], ref[2])
+            and float(red.tail[0]) == float(summed[-1])):
+      ok = False
+      print('PEER ALLREDUCE + ADAM MISMATCH', rank, step, float((mine[0] - ref[0]).abs().max()), flush=True)
+  red.close()
+# the agent on the peer path: eight data-parallel train steps from the same seed on the same
+# per-rank batches, against the NCCL path; the gradients carry atomics-order noise which Adam
+# turns into +-lr steps on noise-driven entries, so the yardstick is NCCL against NCCL re-run
+trained = {}
+for mode in ('peer', 'nccl', 'nccl_again'):
+  os.environ['IBC_PEER_ALLREDUCE'] = '1' if mode == 'peer' else '0'
+  torch.manual_seed(21)
+  net2, agent2, _ = bench.build_agent(dict(bench.CFG, batch=64), torch.device('cuda', rank), seed=9)
+  for i in range(8):
+    o2, a2 = bench.synthetic_batch(dict(bench.CFG, batch=64), 64, 300 + 10 * i + rank,
+                                   device=torch.device('cuda', rank))
+    info = agent2.train(((o2, a2), ()))
+  agent2.flush_checks()
+  used = getattr(agent2, '_peer', None) is not None
+  if used != (mode == 'peer'):
+    ok = False
+    print('PEER PATH NOT TAKEN' if mode == 'peer' else 'PEER PATH TAKEN UNDER IBC_PEER_ALLREDUCE=0', rank, flush=True)
+  if used:
+    agent2._peer.check()
+  trained[mode] = net2.params.detach().clone()
+os.environ.pop('IBC_PEER_ALLREDUCE', None)
+d = (trained['peer'] - trained['nccl']).abs()
+d0 = (trained['nccl_again'] - trained['nccl']).abs()
+stats = lambda x: (float(x.median()), float(x.mean()), float(x.max()))
+if rank == 0:
+  print('PEER_VS_NCCL median/mean/max', stats(d), 'NCCL_VS_NCCL', stats(d0), flush=True)
+if not (stats(d)[1] <= 2.0 * stats(d0)[1] + 1e-6 and stats(d)[2] <= 2.0 * stats(d0)[2] + 1e-5):
+  ok = False
+  print('PEER TRAINING MISMATCH', rank, stats(d), stats(d0), flush=True)
+both = [torch.empty_like(trained['peer']) for _ in range(world)]
+dist.all_gather(both, trained['peer'])
+if not all(torch.equal(both[0], x) for x in both):      # the replicas stay bit-identical
+  ok = False
+  print('PEER REPLICAS DIVERGED', rank, flush=True)
 t = torch.tensor([1.0 if ok else 0.0], device='cuda')
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
