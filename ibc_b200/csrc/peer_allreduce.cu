@@ -48,15 +48,43 @@ __device__ __forceinline__ void st_sys(int* ptr, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ float adam_one(float g, float& m, float& v, float p, const PeerParams& q) {
+  m = q.b1 * m + (1.f - q.b1) * g;
+  v = q.b2 * v + (1.f - q.b2) * g * g;
+  return p - q.lr_t * m / (sqrtf(v) + q.eps);
+}
+
+// One float4 per thread and ONE round of remote loads: a peer read over NVLink has microseconds
+// of latency, so the kernel is shaped by how many dependent remote round trips a thread makes
+// (a grid-stride loop made four: 25 us), not by the 1 MB it moves.  Everything local (p, m, v,
+// this rank's gradient) is loaded BEFORE the wait on the peers' flags, the world - 1 remote loads
+// are issued together after it.
 __global__ void __launch_bounds__(256) peer_allreduce_adam_kernel(PeerParams q) {
   __shared__ int s_abort;
+  const int64_t n4 = q.n >> 2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool body = i < n4;                       // one float4
+  const int64_t it = (n4 << 2) + (i - n4);        // or one scalar of the tail (n % 4 entries)
+  const bool tail = !body && it < q.n;
   if (threadIdx.x == 0) {
     s_abort = 0;
-    if (blockIdx.x == 0) {
-      // this rank's gradient was written by earlier kernels of the stream: complete and visible
-      __threadfence_system();
+    // this rank's gradient was written by earlier kernels of the stream: complete, and in the
+    // memory its peers read; the release store orders it before the flag
+    if (blockIdx.x == 0)
       for (int p = 0; p < q.world; ++p) st_sys(q.flags[p] + q.rank, q.epoch);
-    }
+  }
+  float4 g[kMaxPeers], p4, m4, v4;
+  float gt[kMaxPeers], pt = 0.f, mt = 0.f, vt = 0.f;
+  if (body) {
+    p4 = reinterpret_cast<const float4*>(q.p)[i];
+    m4 = reinterpret_cast<const float4*>(q.m)[i];
+    v4 = reinterpret_cast<const float4*>(q.v)[i];
+    g[0] = __ldcg(reinterpret_cast<const float4*>(q.g[q.rank]) + i);     // parked in slot 0
+  } else if (tail) {
+    pt = q.p[it]; mt = q.m[it]; vt = q.v[it];
+    gt[0] = __ldcg(q.g[q.rank] + it);
+  }
+  if (threadIdx.x == 0) {
     const long long t0 = clock64();
     for (int p = 0; p < q.world && !s_abort; ++p) {
       while (ld_sys(q.flags[q.rank] + p) - q.epoch < 0) {
@@ -65,25 +93,44 @@ __global__ void __launch_bounds__(256) peer_allreduce_adam_kernel(PeerParams q) 
           if (q.status) atomicCAS(q.status, 0, 6001);
           break;
         }
-        __nanosleep(200);
       }
     }
-    __threadfence_system();
   }
   __syncthreads();
   if (s_abort) return;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q.n;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    float gi = 0.f;
+  if (body) {
+    const float4 mine = g[0];
 #pragma unroll
     for (int p = 0; p < kMaxPeers; ++p)
-      if (p < q.world) gi += __ldcg(q.g[p] + i);      // rank order: identical sums on every rank
-    const float mi = q.b1 * q.m[i] + (1.f - q.b1) * gi;
-    const float vi = q.b2 * q.v[i] + (1.f - q.b2) * gi * gi;
-    q.m[i] = mi;
-    q.v[i] = vi;
-    q.p[i] = q.p[i] - q.lr_t * mi / (sqrtf(vi) + q.eps);
-    if (q.tail_out && i == q.n - 1) *q.tail_out = gi;
+      if (p < q.world && p != q.rank) g[p] = __ldcg(reinterpret_cast<const float4*>(q.g[p]) + i);
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p)
+      if (p < q.world) {                           // rank order: identical sums on every rank
+        const float4 x = p == q.rank ? mine : g[p];
+        sum.x += x.x; sum.y += x.y; sum.z += x.z; sum.w += x.w;
+      }
+    p4.x = adam_one(sum.x, m4.x, v4.x, p4.x, q);
+    p4.y = adam_one(sum.y, m4.y, v4.y, p4.y, q);
+    p4.z = adam_one(sum.z, m4.z, v4.z, p4.z, q);
+    p4.w = adam_one(sum.w, m4.w, v4.w, p4.w, q);
+    reinterpret_cast<float4*>(q.m)[i] = m4;
+    reinterpret_cast<float4*>(q.v)[i] = v4;
+    reinterpret_cast<float4*>(q.p)[i] = p4;
+    if (q.tail_out && (i << 2) + 3 == q.n - 1) *q.tail_out = sum.w;
+  } else if (tail) {
+    const float mine = gt[0];
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p)
+      if (p < q.world && p != q.rank) gt[p] = __ldcg(q.g[p] + it);
+    float sum = 0.f;
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p)
+      if (p < q.world) sum += p == q.rank ? mine : gt[p];
+    q.p[it] = adam_one(sum, mt, vt, pt, q);
+    q.m[it] = mt;
+    q.v[it] = vt;
+    if (q.tail_out && it == q.n - 1) *q.tail_out = sum;
   }
 }
 
@@ -139,8 +186,16 @@ int peer_allreduce_adam(ibc_handle* h, const float* const* peer_grads, int* cons
   }
   q.rank = rank; q.world = world; q.epoch = epoch; q.n = n; q.p = params; q.m = m; q.v = v;
   q.lr_t = lr_t; q.b1 = b1; q.b2 = b2; q.eps = eps; q.tail_out = tail_out; q.status = status;
-  int blocks = (int)((n + 255) / 256);
-  if (blocks > 296) blocks = 296;
+  if (((uintptr_t)params | (uintptr_t)m | (uintptr_t)v) & 15)
+    IBC_FAIL(h, IBC_ERR_INVALID, "peer_allreduce_adam: params / m / v must be 16-byte aligned");
+  for (int p = 0; p < world; ++p)
+    if (!peer_grads[p] || !peer_flags[p] || ((uintptr_t)peer_grads[p] & 15))
+      IBC_FAIL(h, IBC_ERR_INVALID, "peer_allreduce_adam: null or misaligned peer buffer %d", p);
+  // one thread per float4 plus n % 4 tail threads (8 x 148 blocks are resident at once: 1.2 M
+  // parameters go in one wave, larger nets in several -- blocks only wait on peers, never on
+  // each other)
+  const int64_t threads = (n >> 2) + (n & 3);
+  const int blocks = (int)((threads + 255) / 256);
   peer_allreduce_adam_kernel<<<blocks, 256, 0, s>>>(q);
   IBC_LAUNCH_CHECK(h);
   return IBC_OK;
