@@ -385,6 +385,10 @@ def run_b200(args):
                 'd2h_bytes_per_step': 4, 'ms_per_step': t_e2e / args.steps * 1e3,
                 'final_loss': losses[-1] if losses else None},
         'gpu_launches': int(launches),
+        'gradient_reduction': (None if world == 1 else
+                               'ibc_peer_allreduce_adam: sum over NVLink peer memory + Adam in one launch'
+                               if getattr(agent, '_peer', None) is not None else
+                               'torch.distributed.all_reduce (NCCL) + ibc_adam_step'),
         'clocks': clocks,
         'roofline': None,
         'roofline_step': {'kernel': 'whole train step (all kernels)', 'bound': 'tensor',
