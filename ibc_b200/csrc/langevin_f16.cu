@@ -28,6 +28,7 @@
 
 #include <type_traits>
 
+#include <algorithm>
 #include "mlp.cuh"
 #include "philox.cuh"
 #include "umma.cuh"
@@ -589,8 +590,12 @@ int pack16_params(ibc_handle* h, cudaStream_t s, bool core) {
   __half* out = reinterpret_cast<__half*>(h->packed16);
   // core: action rows + forward layers (the training forward) + transposed layers (the backward);
   // the rest: the dE/dact operand of the Langevin chain
-  if (core) pack16_kernel<<<148, 256, 0, s>>>(h->params, h->L, pl, out, 0, pl.revp, pl.revp, 0);
-  else pack16_kernel<<<148, 256, 0, s>>>(h->params, h->L, pl, out, pl.revp, pl.total, pl.total, 0);
+  // latency-bound gathers out of L2 (the parameters Adam just wrote): one or two elements per
+  // thread on a full resident wave instead of fifteen dependent rounds on 148 CTAs
+  const int64_t cnt = core ? pl.revp : pl.total - pl.revp;
+  const int grid = (int)std::min<int64_t>(std::max<int64_t>((cnt + 255) / 256, 1), 148 * 8);
+  if (core) pack16_kernel<<<grid, 256, 0, s>>>(h->params, h->L, pl, out, 0, pl.revp, pl.revp, 0);
+  else pack16_kernel<<<grid, 256, 0, s>>>(h->params, h->L, pl, out, pl.revp, pl.total, pl.total, 0);
   IBC_LAUNCH_CHECK(h);
   return IBC_OK;
 }

@@ -18,6 +18,7 @@
 // weight slice is read once per 256 rows.
 #include <stdlib.h>
 
+#include <algorithm>
 #include "gemm_simt.cuh"
 #include "mlp.cuh"
 #include "ops.cuh"
@@ -831,8 +832,11 @@ int umma_pack_core(ibc_handle* h, cudaStream_t s) {
   if (!h->packed_stale) return IBC_OK;
   const PackedLayout pl = make_packed_layout(h->L);
   IBC_TRY(ensure_packed_buffer(h, pl));
-  pack_kernel<<<148, 256, 0, s>>>(h->params, h->L, pl, h->packed, 0, pl.total, pl.fwd_l,
-                                  pl.vecs - pl.fwd_l);
+  // (grid: one element per thread up to a full resident wave -- a latency-bound gather out of L2)
+  const int64_t cnt = pl.total - (pl.vecs - pl.fwd_l);
+  const int grid = (int)std::min<int64_t>(std::max<int64_t>((cnt + 255) / 256, 1), 148 * 8);
+  pack_kernel<<<grid, 256, 0, s>>>(h->params, h->L, pl, h->packed, 0, pl.total, pl.fwd_l,
+                                   pl.vecs - pl.fwd_l);
   IBC_LAUNCH_CHECK(h);
   if (h->L.W == 128) IBC_TRY(pack16_params(h, s, true));     // fp16 transposed layers (backward)
   h->packed_stale = false;
@@ -843,7 +847,9 @@ int umma_pack_params(ibc_handle* h, cudaStream_t s) {
   IBC_TRY(umma_pack_core(h, s));
   if (!h->packed_rest_stale) return IBC_OK;
   const PackedLayout pl = make_packed_layout(h->L);
-  pack_kernel<<<148, 256, 0, s>>>(h->params, h->L, pl, h->packed, pl.fwd_l, pl.vecs, pl.vecs, 0);
+  const int64_t rest = pl.vecs - pl.fwd_l;
+  const int grid_rest = (int)std::min<int64_t>(std::max<int64_t>((rest + 255) / 256, 1), 148 * 8);
+  pack_kernel<<<grid_rest, 256, 0, s>>>(h->params, h->L, pl, h->packed, pl.fwd_l, pl.vecs, pl.vecs, 0);
   IBC_LAUNCH_CHECK(h);
   if (h->L.W == 128) IBC_TRY(pack16_params(h, s, false));    // fp16 forward layers (Langevin chain)
   h->packed_rest_stale = false;
