@@ -33,7 +33,7 @@ def mx(x):
 
 c = bench.CFG
 steps = 400
-for mode in ('peer', 'nccl', 'peer', 'nccl'):
+for mode in (('peer', 'nccl') if world > 2 else ('peer', 'nccl', 'peer', 'nccl')):
   os.environ['IBC_PEER_ALLREDUCE'] = '1' if mode == 'peer' else '0'
   net, agent, _ = bench.build_agent(c, device)
   dev = [bench.synthetic_batch(c, c['batch'], 100 + rank * 17 + i, device=device) for i in range(4)]
@@ -41,6 +41,16 @@ for mode in ('peer', 'nccl', 'peer', 'nccl'):
   for i in range(20):
     agent.train((dev[i % 4], ()))
   t = mx(bench.timed(lambda i: agent.train((dev[i % 4], ())), steps, barrier)) / steps
+  # host issue time: 200 steps queued without a sync (the launch queue holds them)
+  barrier()
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  for i in range(200):
+    agent.train((dev[i % 4], ()))
+  th = mx(time.perf_counter() - t0) / 200
+  torch.cuda.synchronize()
+  if rank == 0:
+    print('world %d  %-4s host issue %.4f ms/step' % (world, mode, th * 1e3), flush=True)
   barrier()
   torch.cuda.synchronize()
   t0 = time.perf_counter()
