@@ -517,51 +517,66 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_f16_kernel(LangevinF16Pa
 // [W/8][AP][8] action rows of Wp for dE/dact.  Element (n, k) of a K-major image sits at
 // ((k / 8) * N + n) * 8 + k % 8.
 // Elements [lo, hi) of the buffer, without [hole_lo, hole_lo + hole_len).
+__device__ __forceinline__ float pack16_value(const float* __restrict__ P, const Layout& L,
+                                              const Packed16Layout& pl, int64_t i) {
+  const int W = L.W;
+  const int64_t WW = (int64_t)W * W;
+  float v = 0.f;
+  if (i < pl.fwd) {                       // step-0 operand: B[n][k] = Wp[O + k][n]
+    const int64_t e = i - pl.p0;
+    const int kq = (int)(e & 7), n = (int)((e >> 3) % W), kc = (int)((e >> 3) / W);
+    const int k = kc * 8 + kq;
+    v = (k < L.A) ? P[L.wp + (int64_t)(L.O + k) * W + n] : 0.f;
+  } else if (i < pl.rev) {                // forward layer m + bias slice of step m + 1
+    const int64_t e = i - pl.fwd;
+    const int64_t blk = WW + 16 * W;
+    const int m = (int)(e / blk);
+    const int64_t r = e - (int64_t)m * blk;
+    const int j = m >> 1;
+    if (r < WW) {
+      const int kq = (int)(r & 7), n = (int)((r >> 3) % W), kc = (int)((r >> 3) / W);
+      const int64_t base = (m & 1) ? L.w2(j) : L.w1(j);
+      v = P[base + (int64_t)(kc * 8 + kq) * W + n];
+    } else {
+      const int rb = (int)(r - WW);
+      const int kq = rb & 7, n = (rb >> 3) % W, kc = (rb >> 3) / W;
+      const float b = (m & 1) ? P[L.b2(j) + n] : P[L.b1(j) + n];
+      const float hi = __half2float(__float2half_rn(b));
+      v = (kc == 0 && kq == 0) ? hi : ((kc == 0 && kq == 1) ? b - hi : 0.f);
+    }
+  } else if (i < pl.revp) {               // reverse layers: B[n = in][k = out] = W[in][out]
+    const int64_t e = i - pl.rev;
+    const int m = (int)(e / WW);          // 0: W2_{nb-1}, 1: W1_{nb-1}, 2: W2_{nb-2}, ...
+    const int64_t r = e - (int64_t)m * WW;
+    const int oq = (int)(r & 7), irow = (int)((r >> 3) % W), oc = (int)((r >> 3) / W);
+    const int j = L.nb - 1 - (m >> 1);
+    const int64_t base = (m & 1) ? L.w1(j) : L.w2(j);
+    v = P[base + (int64_t)irow * W + (oc * 8 + oq)];
+  } else {                                // dE/dact operand: B[n = a][k = w] = Wp[O + a][w]
+    const int64_t e = i - pl.revp;
+    const int wq = (int)(e & 7), a = (int)((e >> 3) % pl.AP), wc = (int)((e >> 3) / pl.AP);
+    v = (a < L.A) ? P[L.wp + (int64_t)(L.O + a) * W + (wc * 8 + wq)] : 0.f;
+  }
+  return v;
+}
+
+// Eight consecutive halves per thread (every image and every range boundary is a multiple of
+// eight: one (n, k / 8) group of a K-major image): eight independent loads, one 16-byte store.
 __global__ void pack16_kernel(const float* __restrict__ P, Layout L, Packed16Layout pl,
                               __half* __restrict__ out, int64_t lo, int64_t hi, int64_t hole_lo,
                               int64_t hole_len) {
-  const int W = L.W;
-  const int64_t WW = (int64_t)W * W;
-  for (int64_t j = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < hi - hole_len;
-       j += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t groups = (hi - lo - hole_len) >> 3;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups;
+       g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = lo + (g << 3);
     const int64_t i = j < hole_lo ? j : j + hole_len;
-    float v = 0.f;
-    if (i < pl.fwd) {                       // step-0 operand: B[n][k] = Wp[O + k][n]
-      const int64_t e = i - pl.p0;
-      const int kq = (int)(e & 7), n = (int)((e >> 3) % W), kc = (int)((e >> 3) / W);
-      const int k = kc * 8 + kq;
-      v = (k < L.A) ? P[L.wp + (int64_t)(L.O + k) * W + n] : 0.f;
-    } else if (i < pl.rev) {                // forward layer m + bias slice of step m + 1
-      const int64_t e = i - pl.fwd;
-      const int64_t blk = WW + 16 * W;
-      const int m = (int)(e / blk);
-      const int64_t r = e - (int64_t)m * blk;
-      const int j = m >> 1;
-      if (r < WW) {
-        const int kq = (int)(r & 7), n = (int)((r >> 3) % W), kc = (int)((r >> 3) / W);
-        const int64_t base = (m & 1) ? L.w2(j) : L.w1(j);
-        v = P[base + (int64_t)(kc * 8 + kq) * W + n];
-      } else {
-        const int rb = (int)(r - WW);
-        const int kq = rb & 7, n = (rb >> 3) % W, kc = (rb >> 3) / W;
-        const float b = (m & 1) ? P[L.b2(j) + n] : P[L.b1(j) + n];
-        const float hi = __half2float(__float2half_rn(b));
-        v = (kc == 0 && kq == 0) ? hi : ((kc == 0 && kq == 1) ? b - hi : 0.f);
-      }
-    } else if (i < pl.revp) {               // reverse layers: B[n = in][k = out] = W[in][out]
-      const int64_t e = i - pl.rev;
-      const int m = (int)(e / WW);          // 0: W2_{nb-1}, 1: W1_{nb-1}, 2: W2_{nb-2}, ...
-      const int64_t r = e - (int64_t)m * WW;
-      const int oq = (int)(r & 7), irow = (int)((r >> 3) % W), oc = (int)((r >> 3) / W);
-      const int j = L.nb - 1 - (m >> 1);
-      const int64_t base = (m & 1) ? L.w1(j) : L.w2(j);
-      v = P[base + (int64_t)irow * W + (oc * 8 + oq)];
-    } else {                                // dE/dact operand: B[n = a][k = w] = Wp[O + a][w]
-      const int64_t e = i - pl.revp;
-      const int wq = (int)(e & 7), a = (int)((e >> 3) % pl.AP), wc = (int)((e >> 3) / pl.AP);
-      v = (a < L.A) ? P[L.wp + (int64_t)(L.O + a) * W + (wc * 8 + wq)] : 0.f;
-    }
-    out[i] = __float2half_rn(v);
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = pack16_value(P, L, pl, i + q);
+    __align__(16) __half2 h2[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) h2[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+    *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<const uint4*>(h2);
   }
 }
 
@@ -590,9 +605,11 @@ int pack16_params(ibc_handle* h, cudaStream_t s, bool core) {
   __half* out = reinterpret_cast<__half*>(h->packed16);
   // core: action rows + forward layers (the training forward) + transposed layers (the backward);
   // the rest: the dE/dact operand of the Langevin chain
-  // latency-bound gathers out of L2 (the parameters Adam just wrote): one or two elements per
-  // thread on a full resident wave instead of fifteen dependent rounds on 148 CTAs
-  const int64_t cnt = core ? pl.revp : pl.total - pl.revp;
+  // latency-bound gathers out of L2 (the parameters Adam just wrote): one group of eight per
+  // thread in one wave instead of fifteen dependent rounds of single halves on 148 CTAs
+  const int64_t cnt = (core ? pl.revp : pl.total - pl.revp) / 8;       // groups of eight halves
+  if ((pl.fwd | pl.rev | pl.revp | pl.total) & 7)
+    IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "pack16: image sizes must be multiples of eight halves");
   const int grid = (int)std::min<int64_t>(std::max<int64_t>((cnt + 255) / 256, 1), 148 * 8);
   if (core) pack16_kernel<<<grid, 256, 0, s>>>(h->params, h->L, pl, out, 0, pl.revp, pl.revp, 0);
   else pack16_kernel<<<grid, 256, 0, s>>>(h->params, h->L, pl, out, pl.revp, pl.total, pl.total, 0);

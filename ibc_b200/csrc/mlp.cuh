@@ -53,6 +53,7 @@ int mlp_energy_dact(ibc_handle* h, const float* obs, int64_t B, const float* act
 // tcgen05 path (mlp_umma.cu) ---------------------------------------------
 bool umma_supported(const Layout& L);
 int umma_pack_params(ibc_handle* h, cudaStream_t s);   // every operand copy up to date
+bool train_forward_is_f16(const Layout& L);            // the saving forward runs in kind::f16 (mlp_fwd_halves.cu)
 int umma_pack_core(ibc_handle* h, cudaStream_t s);     // ... only those of the layer-fused training step
 // Saved state for the reverse chain (both nullable): xa_save = the A operands of
 // every layer (umma_save_floats() floats; the weight-gradient kernel's input),

@@ -422,6 +422,11 @@ int launch_halves(ibc_handle* h, FwdHalvesParams& p, int grid, cudaStream_t s) {
 
 // Energies only (xa16 == null) or the training forward of the block-major backward (fp16 operand
 // tiles, fp32 h_nb, masks).
+bool train_forward_is_f16(const Layout& L) {
+  static const bool off = getenv("IBC_FWD_TF32") != nullptr || getenv("IBC_FWD_ROWS") != nullptr;
+  return !off && L.W == 128 && L.A <= 16;
+}
+
 int tmem_forward_halves(ibc_handle* h, const float* act, int64_t R, int64_t n, const float* hp,
                         float* E, void* xa16, float* hn_save, uint32_t* mask_save, cudaStream_t s) {
   const Layout& L = h->L;
@@ -446,7 +451,7 @@ int tmem_forward_halves(ibc_handle* h, const float* act, int64_t R, int64_t n, c
     IBC_CUDA(h, cudaMemsetAsync(p.dbg, 0, 1024 * sizeof(long long), s));
   }
   // the training forward runs its GEMMs in kind::f16 (act_dim <= 16; IBC_FWD_TF32=1 keeps tf32)
-  const bool f16 = xa16 && L.A <= 16 && h->packed16 && getenv("IBC_FWD_TF32") == nullptr;
+  const bool f16 = xa16 && h->packed16 && train_forward_is_f16(L);
   if (f16) {
     const Packed16Layout p16 = make_packed16_layout(L);
     p.packed16 = reinterpret_cast<const __half*>(h->packed16);

@@ -828,16 +828,29 @@ static int ensure_packed_buffer(ibc_handle* h, const PackedLayout& pl) {
   return IBC_OK;
 }
 
+static int pack_range(ibc_handle* h, const PackedLayout& pl, int64_t lo, int64_t hi, int64_t hole_lo,
+                      int64_t hole_len, cudaStream_t s) {
+  // (grid: one element per thread up to a full resident wave -- a latency-bound gather out of L2)
+  const int64_t cnt = hi - lo - hole_len;
+  if (cnt <= 0) return IBC_OK;
+  const int grid = (int)std::min<int64_t>((cnt + 255) / 256, 148 * 8);
+  pack_kernel<<<grid, 256, 0, s>>>(h->params, h->L, pl, h->packed, lo, hi, hole_lo, hole_len);
+  IBC_LAUNCH_CHECK(h);
+  return IBC_OK;
+}
+
+// With the training forward in kind::f16 (train_forward_is_f16: width 128, act_dim <= 16) the
+// layer-fused step reads its MMA operands from the fp16 images only; of this buffer it reads the
+// epilogue vectors (we, be, biases: [vecs, fwd_lb)).  The tf32 forward layer blocks -- 1.1 MB,
+// the bulk of the re-pack -- then wait for the first caller that needs them (umma_pack_params).
+static bool core_is_slim(const ibc_handle* h) { return h->L.W == 128 && train_forward_is_f16(h->L); }
+
 int umma_pack_core(ibc_handle* h, cudaStream_t s) {
   if (!h->packed_stale) return IBC_OK;
   const PackedLayout pl = make_packed_layout(h->L);
   IBC_TRY(ensure_packed_buffer(h, pl));
-  // (grid: one element per thread up to a full resident wave -- a latency-bound gather out of L2)
-  const int64_t cnt = pl.total - (pl.vecs - pl.fwd_l);
-  const int grid = (int)std::min<int64_t>(std::max<int64_t>((cnt + 255) / 256, 1), 148 * 8);
-  pack_kernel<<<grid, 256, 0, s>>>(h->params, h->L, pl, h->packed, 0, pl.total, pl.fwd_l,
-                                   pl.vecs - pl.fwd_l);
-  IBC_LAUNCH_CHECK(h);
+  if (core_is_slim(h)) IBC_TRY(pack_range(h, pl, pl.vecs, pl.fwd_lb, pl.fwd_lb, 0, s));
+  else IBC_TRY(pack_range(h, pl, 0, pl.total, pl.fwd_l, pl.vecs - pl.fwd_l, s));
   if (h->L.W == 128) IBC_TRY(pack16_params(h, s, true));     // fp16 transposed layers (backward)
   h->packed_stale = false;
   return IBC_OK;
@@ -847,10 +860,8 @@ int umma_pack_params(ibc_handle* h, cudaStream_t s) {
   IBC_TRY(umma_pack_core(h, s));
   if (!h->packed_rest_stale) return IBC_OK;
   const PackedLayout pl = make_packed_layout(h->L);
-  const int64_t rest = pl.vecs - pl.fwd_l;
-  const int grid_rest = (int)std::min<int64_t>(std::max<int64_t>((rest + 255) / 256, 1), 148 * 8);
-  pack_kernel<<<grid_rest, 256, 0, s>>>(h->params, h->L, pl, h->packed, pl.fwd_l, pl.vecs, pl.vecs, 0);
-  IBC_LAUNCH_CHECK(h);
+  if (core_is_slim(h)) IBC_TRY(pack_range(h, pl, 0, pl.total, pl.vecs, pl.fwd_lb - pl.vecs, s));
+  else IBC_TRY(pack_range(h, pl, pl.fwd_l, pl.vecs, pl.vecs, 0, s));
   if (h->L.W == 128) IBC_TRY(pack16_params(h, s, false));    // fp16 forward layers (Langevin chain)
   h->packed_rest_stale = false;
   return IBC_OK;
