@@ -304,3 +304,109 @@ def test_langevin_train_loss_runs_and_grad_penalty_second_order():
   (grad,) = torch.autograd.grad(total, flat)
   assert torch.isfinite(grad).all() and 'grad_loss' in metrics
   assert 'final_grad_norms_avg' in metrics
+
+
+# ---------------- independent restatements of the third-party semantics ----------------
+# (the multinomial rule and the Keras KLD clipping were each pinned by one hand
+# case.)  None of these share code with oracle/: plain Python loops, torch.nn modules, scipy.
+def test_multinomial_rule_against_scalar_loop_and_frequencies():
+  """tf.random.categorical on CPU (MultinomialFunctor): weights exp(logit - max) in double,
+  running sum, first class whose running sum EXCEEDS u * total (std::upper_bound).  Restated
+  here as a scalar Python loop with math.exp and checked draw by draw; then the empirical class
+  frequencies of 200 000 draws against softmax(logits) (5 sigma per class)."""
+  rs = np.random.RandomState(11)
+  for n, scale in ((7, 1.0), (33, 4.0), (257, 12.0)):
+    logits = (rs.randn(2, n) * scale).astype(np.float32)
+    logits[1, n // 2] = -np.inf
+    u = rs.rand(2, 64)
+    got = omcmc.multinomial_draws(logits, u)
+    for b in range(2):
+      mx = max(float(x) for x in logits[b] if math.isfinite(x))
+      run, cdf = 0.0, []
+      for x in logits[b]:
+        run += math.exp(float(x) - mx) if math.isfinite(x) else 0.0
+        cdf.append(run)
+      for k in range(u.shape[1]):
+        target = u[b, k] * cdf[-1]
+        idx = next((i for i, c in enumerate(cdf) if c > target), n - 1)
+        assert got[b, k] == idx, (n, b, k)
+  logits = np.array([[0.3, -1.2, 2.0, 0.0, -0.4]], dtype=np.float32)
+  draws = 200_000
+  counts = omcmc.categorical_bincount(draws, logits, 5, rs.rand(1, draws))[0]
+  p = np.exp(logits[0].astype(np.float64))
+  p /= p.sum()
+  sigma = np.sqrt(draws * p * (1 - p))
+  assert np.all(np.abs(counts - draws * p) < 5 * sigma), (counts, draws * p)
+
+
+def test_info_nce_against_cross_entropy_and_scipy():
+  """KLD(one_hot || softmax) is the cross entropy up to Keras' clipping of both arguments to
+  [1e-7, 1]: against torch.nn.functional.cross_entropy where no probability is below 1e-7 (the
+  clipped zeros of the label add N * 1e-7 * log(1e-7 / p_j) exactly), and term by term against
+  scipy.special.rel_entr on the clipped arrays when predictions DO underflow the clip."""
+  import scipy.special
+  g = torch.Generator().manual_seed(4)
+  for b, n, scale in ((5, 8, 1.0), (4, 256, 1.5), (3, 16, 40.0)):
+    pred = torch.randn(b, n + 1, generator=g, dtype=torch.float64) * scale
+    got = olosses.info_nce(pred, b, n)
+    p = torch.softmax(pred, dim=-1).numpy()
+    y = np.zeros_like(p)
+    y[:, n] = 1.0
+    want = scipy.special.rel_entr(np.clip(y, 1e-7, 1.0), np.clip(p, 1e-7, 1.0)).sum(axis=1)
+    assert np.allclose(got.numpy(), want, rtol=1e-12, atol=1e-12)
+    if scale <= 1.5:
+      assert p.min() > 1e-7
+      ce = torch.nn.functional.cross_entropy(pred, torch.full((b,), n), reduction='none').numpy()
+      extra = (1e-7 * (math.log(1e-7) - np.log(p[:, :n]))).sum(axis=1)
+      assert np.allclose(got.numpy(), ce + extra, rtol=1e-10, atol=1e-12)
+
+
+def test_energy_against_independent_keras_style_modules():
+  """MLPEBM with ResNetPreActivationLayer (networks/mlp_ebm.py:72-96, layers/resnet.py:131-153)
+  rebuilt from torch.nn.Linear modules in Keras' own order -- Dense projection, then per block
+  relu -> Dense -> relu -> Dense -> add -- with the oracle's flat parameters loaded as Keras
+  kernels ([in, out] = Linear.weight.T); energies and autograd dE/dact must agree."""
+  spec = omlp.MLPSpec(7, 3, 16, 4)
+  flat = omlp.init_params(spec, seed=6, dtype=torch.float64)
+  p = omlp.unpack(flat, spec)
+
+  def dense(kernel, bias):
+    lin = torch.nn.Linear(kernel.shape[0], kernel.shape[1] if kernel.dim() == 2 else 1).double()
+    with torch.no_grad():
+      lin.weight.copy_(kernel.reshape(kernel.shape[0], -1).T)
+      lin.bias.copy_(bias.reshape(-1))
+    return lin
+
+  proj = dense(p['Wp'], p['bp'])
+  blocks = [(dense(p['W1_%d' % j], p['b1_%d' % j]), dense(p['W2_%d' % j], p['b2_%d' % j]))
+            for j in range(spec.num_blocks)]
+  head = dense(p['we'], p['be'])
+  g = torch.Generator().manual_seed(8)
+  obs = torch.randn(9, 7, generator=g, dtype=torch.float64)
+  act = torch.randn(9, 3, generator=g, dtype=torch.float64, requires_grad=True)
+  x = proj(torch.cat([obs, act], dim=-1))
+  for l1, l2 in blocks:
+    y = l1(torch.relu(x))
+    y = l2(torch.relu(y))
+    x = x + y
+  want = head(x).squeeze(-1)
+  (dwant,) = torch.autograd.grad(want.sum(), act)
+  got = omlp.energy(flat, spec, obs, act.detach())
+  assert torch.allclose(got, want.detach(), rtol=1e-12, atol=1e-12)
+  e2, dact = omlp.energy_and_dact_manual(flat, spec, obs, act.detach())
+  assert torch.allclose(e2, want.detach(), rtol=1e-12, atol=1e-12)
+  assert torch.allclose(dact, dwant, rtol=1e-10, atol=1e-12)
+
+
+def test_spectral_norm_against_torch_power_iteration():
+  """DenseSN (networks/layers/spectral_norm.py): one power iteration v = l2n(u W^T),
+  u' = l2n(v W), sigma = v W u'^T, W / sigma.  After many iterations sigma must be the largest
+  singular value (torch.linalg.svdvals) and the normalised kernel's spectral norm 1."""
+  g = torch.Generator().manual_seed(2)
+  w = torch.randn(24, 16, generator=g, dtype=torch.float64)
+  u = torch.randn(1, 16, generator=g, dtype=torch.float64)
+  for _ in range(300):
+    w_bar, u = omlp.spectral_normalize(w, u)
+  top = torch.linalg.svdvals(w)[0]
+  assert torch.allclose(torch.linalg.svdvals(w_bar)[0], torch.ones((), dtype=torch.float64), atol=1e-9)
+  assert torch.allclose(w / top, w_bar, atol=1e-9)
