@@ -24,6 +24,7 @@ PRECISION_FP32 = 0
 PRECISION_TF32 = 1
 
 NORM_NONE, NORM_L1, NORM_L2, NORM_INF = 0, 1, 2, 3
+LOSS_BY_NAME = {'info_nce': 0, 'cd': 1, 'clipped_cd': 2, 'soft_clipped_cd': 3}
 NORM_BY_NAME = {None: NORM_NONE, '1': NORM_L1, '2': NORM_L2, 'inf': NORM_INF}
 
 
@@ -49,7 +50,8 @@ class LangevinCfg(Structure):
 class LossCfg(Structure):
   _fields_ = [('softmax_temperature', c_float), ('add_grad_penalty', c_int32),
               ('grad_norm_type', c_int32), ('grad_margin', c_float),
-              ('square_grad_penalty', c_int32), ('grad_loss_weight', c_float)]
+              ('square_grad_penalty', c_int32), ('grad_loss_weight', c_float),
+              ('ebm_loss_type', c_int32)]
 
 
 class PixelArch(Structure):
@@ -106,6 +108,8 @@ SIGNATURES = {
                                              c_uint64, c_void_p, c_void_p, c_void_p]),
     'ibc_info_nce': (c_int, [c_void_p, c_int64, c_int64, c_float, c_float,
                              c_void_p, c_void_p, c_void_p]),
+    'ibc_cd_loss': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_float,
+                            c_void_p, c_void_p, c_void_p]),
     'ibc_grad_penalty_from_dact': (c_int, [c_void_p, c_int64, c_int64, c_int32,
                                            POINTER(LossCfg), c_float, c_void_p,
                                            c_void_p, c_void_p]),

@@ -281,6 +281,14 @@ int ibc_info_nce(const float* predictions, int64_t B, int64_t n1, float temperat
                   (cudaStream_t)stream);
 }
 
+int ibc_cd_loss(const float* predictions, const float* actions, int64_t B, int64_t n1, int32_t A,
+                int32_t loss_type, float grad_scale, float* loss, float* dpred, void* stream) {
+  ibc_handle* h = nullptr;
+  if (!predictions || !loss) IBC_FAIL(h, IBC_ERR_INVALID, "ibc_cd_loss: null argument");
+  return cd_loss(h, predictions, actions, B, n1, A, loss_type, grad_scale, loss, dpred,
+                 (cudaStream_t)stream);
+}
+
 int ibc_grad_penalty_from_dact(const float* dE_dact, int64_t B, int64_t n1, int32_t A,
                                const ibc_loss_cfg* cfg, float grad_scale, float* grad_loss,
                                float* cotangent, void* stream) {

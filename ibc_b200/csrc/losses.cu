@@ -148,6 +148,75 @@ __global__ void add_vec_kernel(float* __restrict__ a, const float* __restrict__ 
   if (i < n) a[i] += b[i];
 }
 
+// ebm_loss.cd / clipped_cd (ibc/losses/ebm_loss.py:51-66, 109-148): one block per example.
+// err_j = |counter_j - true|^2 over the action dimensions (tf.norm(...)**2), threshold 0.2;
+// d|x|/dx = sign(x) with 0 at 0 (tf.abs); reduce_mean over no counter examples is 0/0 = NaN
+// as upstream.
+__global__ void __launch_bounds__(128)
+cd_loss_kernel(const float* __restrict__ pred, const float* __restrict__ actions, int n1, int A,
+               int type, float grad_scale, float* __restrict__ loss, float* __restrict__ dpred,
+               unsigned int* __restrict__ dpred_absmax) {
+  __shared__ float s_red[4];
+  const int tid = threadIdx.x;
+  const int n = n1 - 1;
+  const float* row = pred + (int64_t)blockIdx.x * n1;
+  const float* arow = actions ? actions + (int64_t)blockIdx.x * n1 * A : nullptr;
+  const float e_data = row[n];
+  const float inv_n = 1.0f / (float)n;
+  float acc = 0.f, dlast = 0.f, dmax = 0.f;
+  float* drow = dpred ? dpred + (int64_t)blockIdx.x * n1 : nullptr;
+  for (int j = tid; j < n; j += 128) {
+    float term, dj, dn;
+    if (type == IBC_LOSS_CD) {
+      term = row[j];           // mean(samp) - data: the data term is subtracted once below
+      dj = 1.f; dn = 0.f;
+    } else {
+      float err = 0.f;
+      for (int a = 0; a < A; ++a) {
+        const float d = arow[(int64_t)j * A + a] - arow[(int64_t)n * A + a];
+        err = fmaf(d, d, err);
+      }
+      // tf.norm(...)**2: the square of the rounded square root
+      const float nrm = sqrtf(err);
+      err = nrm * nrm;
+      const bool outside = err > 0.2f;
+      term = outside ? row[j] - e_data : 0.f;
+      dj = outside ? 1.f : 0.f;
+      dn = outside ? -1.f : 0.f;
+      if (type == IBC_LOSS_SOFT_CLIPPED_CD && !(err > 0.2f)) {
+        const float res = (e_data - row[j]) - err;
+        term += fabsf(res);
+        const float sg = res > 0.f ? 1.f : (res < 0.f ? -1.f : 0.f);
+        dj -= sg;
+        dn += sg;
+      }
+    }
+    acc += term;
+    dlast += dn;
+    if (drow) {
+      const float d = grad_scale * dj * inv_n;
+      drow[j] = d;
+      dmax = fmaxf(dmax, fabsf(d));
+    }
+  }
+  acc = block_reduce(acc, s_red, false);
+  dlast = block_reduce(dlast, s_red, false);
+  if (tid == 0) {
+    float l = acc * inv_n, dl = grad_scale * dlast * inv_n;
+    if (type == IBC_LOSS_CD) { l -= e_data; dl = -grad_scale; }
+    loss[blockIdx.x] = l;
+    if (drow) {
+      drow[n] = dl;
+      dmax = fmaxf(dmax, fabsf(dl));
+    }
+  }
+  if (drow && dpred_absmax) {
+    dmax = block_reduce(dmax, s_red, true);
+    if (tid == 0) atomicMax(dpred_absmax, __float_as_uint(dmax));
+  }
+}
+
+
 }  // namespace
 
 int info_nce(ibc_handle* h, const float* pred, int64_t B, int64_t n1, float temperature,
@@ -159,6 +228,29 @@ int info_nce(ibc_handle* h, const float* pred, int64_t B, int64_t n1, float temp
                                               dpred_absmax);
   IBC_LAUNCH_CHECK(h);
   return IBC_OK;
+}
+
+int cd_loss(ibc_handle* h, const float* pred, const float* actions, int64_t B, int64_t n1, int A,
+            int type, float grad_scale, float* loss, float* dpred, cudaStream_t s,
+            unsigned int* dpred_absmax) {
+  if (B <= 0 || n1 <= 0) IBC_FAIL(h, IBC_ERR_INVALID, "cd_loss: bad shape");
+  if (type != IBC_LOSS_CD && type != IBC_LOSS_CLIPPED_CD && type != IBC_LOSS_SOFT_CLIPPED_CD)
+    IBC_FAIL(h, IBC_ERR_UNSUPPORTED, "cd_loss: ebm_loss_type %d is not built (cd_kl needs a second network)", type);
+  if (type != IBC_LOSS_CD && (!actions || A < 1))
+    IBC_FAIL(h, IBC_ERR_INVALID, "cd_loss: the clipped forms read the combined actions");
+  cd_loss_kernel<<<(unsigned)B, 128, 0, s>>>(pred, actions, (int)n1, A, type, grad_scale, loss, dpred,
+                                             dpred_absmax);
+  IBC_LAUNCH_CHECK(h);
+  return IBC_OK;
+}
+
+// ImplicitBCAgent._compute_ebm_loss (ibc_agent.py:303-335) on the step's energies
+int ebm_loss(ibc_handle* h, const ibc_loss_cfg& c, const float* pred, const float* actions, int64_t B,
+             int64_t n1, int A, float grad_scale, float* loss, float* dpred, cudaStream_t s,
+             unsigned int* dpred_absmax) {
+  if (c.ebm_loss_type == IBC_LOSS_INFO_NCE)
+    return info_nce(h, pred, B, n1, c.softmax_temperature, grad_scale, loss, dpred, s, dpred_absmax);
+  return cd_loss(h, pred, actions, B, n1, A, c.ebm_loss_type, grad_scale, loss, dpred, s, dpred_absmax);
 }
 
 int grad_penalty_from_dact(ibc_handle* h, const float* dEda, int64_t B, int64_t n1, int A,
@@ -225,7 +317,7 @@ int train_grads_fp32(ibc_handle* h, const float* obs, int64_t B, const float* ac
   IBC_TRY(mlp_forward_fp32(h, obs, B, actions, n1, E, &f, s));
   if (energies_out)
     IBC_CUDA(h, cudaMemcpyAsync(energies_out, E, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
-  IBC_TRY(info_nce(h, E, B, n1, c.softmax_temperature, gscale, lnce, dE, s));
+  IBC_TRY(ebm_loss(h, c, E, actions, B, n1, L.A, gscale, lnce, dE, s, nullptr));
   IBC_CUDA(h, cudaMemcpyAsync(per_example, lnce, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
 
   if (gp) {

@@ -1003,7 +1003,7 @@ int train_grads_umma(ibc_handle* h, const float* obs, int64_t B, const float* ac
   mark(1);
   if (energies_out)
     IBC_CUDA(h, cudaMemcpyAsync(energies_out, E, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
-  IBC_TRY(info_nce(h, E, B, n1, c.softmax_temperature, gscale, per_example, dE, s,
+  IBC_TRY(ebm_loss(h, c, E, actions, B, n1, L.A, gscale, per_example, dE, s,
                    fused_bwd ? de_absmax : nullptr));
   if (grad_loss_out) IBC_CUDA(h, cudaMemsetAsync(grad_loss_out, 0, (size_t)B * 4, s));
   (void)gl;

@@ -48,6 +48,12 @@ int langevin(ibc_handle* h, const float* obs, int64_t B, float* actions, int64_t
 int info_nce(ibc_handle* h, const float* pred, int64_t B, int64_t n1, float temperature,
              float grad_scale, float* loss, float* dpred, cudaStream_t s,
              unsigned int* dpred_absmax = nullptr);
+int cd_loss(ibc_handle* h, const float* pred, const float* actions, int64_t B, int64_t n1, int A,
+            int type, float grad_scale, float* loss, float* dpred, cudaStream_t s,
+            unsigned int* dpred_absmax = nullptr);
+int ebm_loss(ibc_handle* h, const ibc_loss_cfg& c, const float* pred, const float* actions, int64_t B,
+             int64_t n1, int A, float grad_scale, float* loss, float* dpred, cudaStream_t s,
+             unsigned int* dpred_absmax = nullptr);
 int grad_penalty_from_dact(ibc_handle* h, const float* dEda, int64_t B, int64_t n1, int A,
                            const ibc_loss_cfg& c, float grad_scale, float* grad_loss, float* cot,
                            cudaStream_t s);

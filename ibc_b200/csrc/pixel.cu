@@ -1233,7 +1233,7 @@ int ibc_pixel_train_finish(ibc_pixel_handle* ph, const float* actions, const ibc
   IBC_TRY(value_fwd(ph, L, pt->enc, B, actions, n1, pt->v, pt->E, s));
   if (energies)
     IBC_CUDA(h, cudaMemcpyAsync(energies, pt->E, (size_t)R * 4, cudaMemcpyDeviceToDevice, s));
-  IBC_TRY(info_nce(h, pt->E, B, n1, cfg->softmax_temperature, 1.0f / (float)global_batch,
+  IBC_TRY(ebm_loss(h, *cfg, pt->E, actions, B, n1, ph->arch.act_dim, 1.0f / (float)global_batch,
                    per_example_loss, pt->dE, s));
   IBC_TRY(value_bwd(ph, L, pt->enc, B, actions, n1, pt->v, pt->dE, grads, pt->dEnc, s));
   IBC_TRY(encode_bwd(ph, L, B, pt->sv, pt->dEnc, grads, pt->dA, pt->dB, s));

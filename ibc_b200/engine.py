@@ -57,11 +57,14 @@ def langevin_cfg(num_iterations=25, sampler_stepsize_init=1e-1,
 
 def loss_cfg(softmax_temperature=1.0, add_grad_penalty=True,
              grad_norm_type='inf', grad_margin=1.0, square_grad_penalty=True,
-             grad_loss_weight=1.0) -> LossCfg:
+             grad_loss_weight=1.0, ebm_loss_type='info_nce') -> LossCfg:
+  if ebm_loss_type not in _lib.LOSS_BY_NAME:
+    raise ValueError('Unsupported EBM loss type.')          # ibc_agent.py:335
   return LossCfg(float(softmax_temperature), int(bool(add_grad_penalty)),
                  _lib.NORM_BY_NAME[grad_norm_type],
                  -1.0 if grad_margin is None else float(grad_margin),
-                 int(bool(square_grad_penalty)), float(grad_loss_weight))
+                 int(bool(square_grad_penalty)), float(grad_loss_weight),
+                 _lib.LOSS_BY_NAME[ebm_loss_type])
 
 
 def param_count(obs_dim: int, act_dim: int, width: int, depth: int) -> int:
@@ -545,6 +548,26 @@ def info_nce(predictions: torch.Tensor, temperature=1.0, grad_scale=1.0, want_gr
   dpred = torch.empty_like(predictions) if want_grad else None
   _lib.check(_lib.load().ibc_info_nce(_ptr(predictions), b, n1, float(temperature),
                                       float(grad_scale), _ptr(loss), _ptr(dpred), _stream()))
+  return (loss, dpred) if want_grad else loss
+
+
+def cd_loss(predictions: torch.Tensor, combined_actions: Optional[torch.Tensor], loss_type='cd',
+            grad_scale=1.0, want_grad=False):
+  """ebm_loss.cd / clipped_cd (ibc/losses/ebm_loss.py:51-66, 109-148) on predictions [B, n+1];
+  combined_actions [B*(n+1), A] (counter examples, then the true action, per observation)."""
+  _check_f32(predictions, 'predictions')
+  b, n1 = predictions.shape
+  a = 0
+  if combined_actions is not None:
+    _check_f32(combined_actions, 'combined_actions')
+    if combined_actions.shape[0] != b * n1:
+      raise ValueError('combined_actions must be [B * (n + 1), A]')
+    a = combined_actions.shape[1]
+  loss = torch.empty(b, device=predictions.device, dtype=torch.float32)
+  dpred = torch.empty_like(predictions) if want_grad else None
+  _lib.check(_lib.load().ibc_cd_loss(_ptr(predictions), _ptr(combined_actions), b, n1, a,
+                                     _lib.LOSS_BY_NAME[loss_type], float(grad_scale), _ptr(loss),
+                                     _ptr(dpred), _stream()))
   return (loss, dpred) if want_grad else loss
 
 

@@ -152,10 +152,10 @@ class ImplicitBCAgent(BehavioralCloningAgent):
     assert self._fraction_dfo_samples >= 0.
     assert self._fraction_langevin_samples >= 0.
     self.ebm_loss_type = ebm_loss_type
-    if ebm_loss_type != 'info_nce':
-      if ebm_loss_type in ('cd', 'cd_kl', 'clipped_cd'):
-        raise NotImplementedError('ebm_loss_type %r is out of scope (no shipped gin selects it)'
-                                  % ebm_loss_type)
+    if ebm_loss_type == 'cd_kl':
+      raise NotImplementedError("ebm_loss_type 'cd_kl' is out of scope (no shipped gin selects it; "
+                                'it needs a copy of the network and gradients through the sampler)')
+    if ebm_loss_type not in ('info_nce', 'cd', 'clipped_cd', 'soft_clipped_cd'):
       raise ValueError('Unsupported EBM loss type.')                 # ibc_agent.py:336
     if late_fusion != isinstance(cloning_network, PixelEBM):
       raise NotImplementedError('late_fusion must be used with (and only with) PixelEBM')
@@ -194,7 +194,7 @@ class ImplicitBCAgent(BehavioralCloningAgent):
       raise NotImplementedError('only_apply_final_grad_penalty=False is not built for training')
     return eng.loss_cfg(self._softmax_temperature, self._add_grad_penalty, self._grad_norm_type,
                         b.get('grad_margin', 1.0), b.get('square_grad_penalty', True),
-                        b.get('grad_loss_weight', 1.0))
+                        b.get('grad_loss_weight', 1.0), self.ebm_loss_type)
 
   def _to_device(self, experience):
     (observations, actions), _ = experience if len(experience) == 2 and isinstance(
@@ -227,10 +227,16 @@ class ImplicitBCAgent(BehavioralCloningAgent):
     raw = eff = None
     if training and isinstance(net, MLPEBM):
       raw, eff = net.effective_params_for_training()             # spectral norm, training=True
-    per_example, grad_loss, _, grads = net.engine.train_grads(
-        obs_flat, combined, n, self._loss_cfg(), global_batch, self._grads)
+    clipped = self.ebm_loss_type in ('clipped_cd', 'soft_clipped_cd')
+    per_example, grad_loss, energies, grads = net.engine.train_grads(
+        obs_flat, combined, n, self._loss_cfg(), global_batch, self._grads, want_energies=clipped)
     total_loss = self._early_loss(net.engine, per_example, 1.0 / float(global_batch))
     losses_dict['ebm_total_loss'] = total_loss
+    if clipped:      # the logged scalars of clipped_cd (ibc_agent.py:252 losses_dict.update(debug_dict))
+      losses_dict.update(ebm_loss.clipped_cd_debug(
+          energies.view(batch_size, n + 1), counter_example_actions,
+          expanded_actions.expand(batch_size, n, expanded_actions.shape[-1]),
+          self.ebm_loss_type == 'soft_clipped_cd'))
     if self._add_grad_penalty:
       losses_dict['grad_loss'] = grad_loss.mean()
     if self._compute_mse:
@@ -338,10 +344,17 @@ class ImplicitBCAgent(BehavioralCloningAgent):
   def _compute_ebm_loss(self, batch_size, predictions, counter_example_actions,
                         expanded_actions, grad_flow_network_inputs=None):
     """ibc_agent.py:302-338 (forward value only)."""
-    del counter_example_actions, expanded_actions, grad_flow_network_inputs
+    del grad_flow_network_inputs
     if self.ebm_loss_type == 'info_nce':
       return ebm_loss.info_nce(predictions, batch_size, self._num_counter_examples,
                                self._softmax_temperature, self._kl)
+    if self.ebm_loss_type == 'cd':
+      return ebm_loss.cd(predictions)
+    if self.ebm_loss_type in ('clipped_cd', 'soft_clipped_cd'):
+      actions_size_n = expanded_actions.expand(batch_size, self._num_counter_examples,
+                                               expanded_actions.shape[-1])
+      return ebm_loss.clipped_cd(predictions, counter_example_actions, actions_size_n,
+                                 soft=self.ebm_loss_type == 'soft_clipped_cd')
     raise ValueError('Unsupported EBM loss type.')
 
   # -- negatives (ibc_agent.py:340-475) -----------------------------------------------

@@ -84,7 +84,16 @@ typedef struct {
   float grad_margin;           /* 1.0; < 0 means None                          */
   int32_t square_grad_penalty; /* 1                                            */
   float grad_loss_weight;      /* 1.0                                          */
+  int32_t ebm_loss_type;       /* IBC_LOSS_*: ImplicitBCAgent(ebm_loss_type=...) (ibc_agent.py:303-335) */
 } ibc_loss_cfg;
+
+/* ibc/losses/ebm_loss.py: info_nce (:21-48), cd (:51-66), clipped_cd with soft = False / True
+ * (:109-148; ibc_agent.py 'clipped_cd' / 'soft_clipped_cd').  'cd_kl' (:69-106) needs a second
+ * network and gradients through the sampler: not built (IBC_ERR_UNSUPPORTED). */
+#define IBC_LOSS_INFO_NCE 0
+#define IBC_LOSS_CD 1
+#define IBC_LOSS_CLIPPED_CD 2
+#define IBC_LOSS_SOFT_CLIPPED_CD 3
 
 /* ---- lifetime ---------------------------------------------------------- */
 
@@ -241,6 +250,16 @@ int ibc_info_nce(const float* predictions, int64_t B, int64_t n1,
                  float temperature, float grad_scale, float* loss,
                  float* dpred, void* stream);
 
+/* The contrastive-divergence losses of ibc/losses/ebm_loss.py on predictions [B, n1] (true action
+ * in the LAST column): loss_type IBC_LOSS_CD (cd, :51-66: mean of the counter examples'
+ * predictions minus the true one), IBC_LOSS_CLIPPED_CD / IBC_LOSS_SOFT_CLIPPED_CD (clipped_cd,
+ * :109-148: counter examples within squared distance 0.2 of the true action drop out of the
+ * difference; soft adds mean |(pred_true - pred_j) - err_j| over those inside).  actions
+ * [B*n1, A] (the combined counter-example + true actions; only read by the clipped forms).
+ * loss [B]; dpred [B, n1] (nullable) = grad_scale * dloss/dpred. */
+int ibc_cd_loss(const float* predictions, const float* actions, int64_t B, int64_t n1, int32_t A,
+                int32_t loss_type, float grad_scale, float* loss, float* dpred, void* stream);
+
 /* gradient_loss.grad_penalty given dE/dact (gradient_loss.py:49-72):
  * grad_loss [B]; cotangent [B*n1, A] (nullable) = grad_scale * d(sum_b
  * grad_loss[b]) / d(dE_dact). */
@@ -252,7 +271,7 @@ int ibc_grad_penalty_from_dact(const float* dE_dact, int64_t B, int64_t n1,
 /* ImplicitBCAgent._loss + tape.gradient (ibc_agent.py:132-300,
  * base_agent.py:43-48) for given combined actions [B*(N+1), A] (true action
  * last per observation):
- *   per_example_loss [B]  = info_nce (+ grad_penalty)
+ *   per_example_loss [B]  = info_nce | cd | clipped_cd (cfg->ebm_loss_type) (+ grad_penalty)
  *   grad_loss        [B]  (nullable; zeros when the penalty is off)
  *   energies   [B*(N+1)]  (nullable)
  *   grads [param_count]   = d( sum_b per_example_loss[b] / global_batch )/dtheta

@@ -32,6 +32,31 @@ def info_nce(predictions: torch.Tensor, batch_size: int,
   return keras_kl_divergence(labels, p)
 
 
+def cd(predictions: torch.Tensor):
+  """ibc/losses/ebm_loss.py:51-66: mean over the counter examples minus the true action's."""
+  return predictions[:, :-1].mean(dim=1) - predictions[:, -1:].mean(dim=1)
+
+
+def clipped_cd(predictions: torch.Tensor, counter_example_actions: torch.Tensor,
+               actions_size_n: torch.Tensor, soft: bool):
+  """ibc/losses/ebm_loss.py:109-148 (thresh 2e-1, w_shaping 1.0).  Returns (loss [B], debug)."""
+  energy_data = predictions[:, -1:].expand(-1, predictions.shape[1] - 1)
+  energy_samp = predictions[:, :-1]
+  errors = torch.linalg.norm(counter_example_actions - actions_size_n, dim=-1) ** 2
+  outside = (errors > 2e-1).to(predictions.dtype)
+  loss = ((energy_samp - energy_data) * outside).mean(dim=1)
+  debug = {}
+  if soft:
+    inside = (errors <= 2e-1).to(predictions.dtype)
+    residual = (energy_data - energy_samp) - errors
+    soft_loss = 1.0 * (residual.abs() * inside).mean(dim=1)
+    debug['cd_loss'] = loss.mean()
+    debug['soft_loss'] = soft_loss.mean()
+    loss = loss + soft_loss
+  debug['fraction_outside_threshold'] = outside.mean()
+  return loss, debug
+
+
 def grad_penalty(energy_fn, grad_norm_type, batch_size, observations,
                  combined_true_counter_actions, grad_margin=1.0,
                  square_grad_penalty=True, grad_loss_weight=1.0,

@@ -392,3 +392,45 @@ def test_c2_training_curves_tf32_tracks_fp32():
       float(((wt - wf).abs() / wf).max()), float(t[250:].mean()) / float(f[250:].mean())))
   assert float(((wt - wf).abs() / wf).max()) <= 0.15, (wt.tolist(), wf.tolist())
   assert abs(float(t[250:].mean()) / float(f[250:].mean()) - 1.0) <= 0.08, (wt.tolist(), wf.tolist())
+
+
+@pytest.mark.parametrize('kind', ['cd', 'clipped_cd', 'soft_clipped_cd'])
+def test_agent_with_cd_loss_types(kind):
+  """ImplicitBCAgent(ebm_loss_type=...) (ibc_agent.py:303-335): the loss on given uniform draws
+  equals the oracle's (ebm_loss.py:51-66, 109-148), the clipped forms log their debug scalars, a
+  train step runs; 'cd_kl' stays NotImplementedError and anything else ValueError as upstream."""
+  from ibc_b200 import _lib
+  from oracle import losses as olosses
+  spec = omlp.MLPSpec(6, 2, 64, 2)
+  b, n = 16, 8
+  net, agent = _build(spec, n, _lib.PRECISION_FP32, fraction_langevin_samples=0.0,
+                      add_grad_penalty=False, ebm_loss_type=kind)
+  g = torch.Generator().manual_seed(4)
+  obs = torch.randn(b, 1, spec.obs_dim, generator=g)
+  act = torch.rand(b, spec.act_dim, generator=g) * 0.4 - 0.2      # near the centre: some negatives inside
+  u = torch.rand(b, n, spec.act_dim, generator=g) * 0.4 + 0.3     # negatives in [-0.44, 0.44]
+  losses = agent._loss((({'obs': obs}, act), ()), training=False, draws={'uniform_u': u.cuda()})
+  mn, mx = torch.full((spec.act_dim,), -1.1), torch.full((spec.act_dim,), 1.1)
+  counter = (u * (mx - mn) + mn).double()                         # the action_sampling_spec bounds, fp32
+  combined = torch.cat([counter, act.double()[:, None, :]], dim=1).reshape(-1, spec.act_dim)
+  flat = net.params.detach().double().cpu()
+  pred = omlp.energy(flat, spec, torch.repeat_interleave(obs.reshape(b, -1).double(), n + 1, 0),
+                     combined).reshape(b, n + 1)
+  if kind == 'cd':
+    want = olosses.cd(pred)
+  else:
+    want, dbg = olosses.clipped_cd(pred, counter, act.double()[:, None, :].expand(b, n, -1),
+                                   soft=kind == 'soft_clipped_cd')
+    assert 0.05 < float(dbg['fraction_outside_threshold']) < 0.95, 'vacuous threshold'
+    assert abs(float(losses['fraction_outside_threshold']) - float(dbg['fraction_outside_threshold'])) < 1e-6
+    assert ('soft_loss' in losses) == (kind == 'soft_clipped_cd')
+    if kind == 'soft_clipped_cd':
+      assert abs(float(losses['soft_loss']) - float(dbg['soft_loss'])) < 1e-4
+  assert abs(float(losses['ebm_total_loss']) - float(want.sum() / b)) < 1e-4
+  before = net.params.detach().clone()
+  info = agent.train((({'obs': obs}, act), ()))
+  assert math.isfinite(float(info.loss)) and not torch.equal(before, net.params)
+  with pytest.raises(NotImplementedError):
+    _build(spec, n, _lib.PRECISION_FP32, ebm_loss_type='cd_kl')
+  with pytest.raises(ValueError):
+    _build(spec, n, _lib.PRECISION_FP32, ebm_loss_type='nce')

@@ -966,3 +966,97 @@ def test_train_grads_with_penalty_tf32_tracks_the_fp32_path(spec, b, n):
     denom = float(w.norm()) + 1e-2 * grms * math.sqrt(cnt)
     rel = float((g - w).norm()) / denom
     assert rel < (1e-1 if name.startswith('b') else 4e-2), (name, rel)
+
+
+# ------------------- contrastive-divergence losses -------------------
+def _cd_case(b, n, a, seed):
+  """Predictions, counter examples (a third of them within the 0.2 threshold of the true
+  action) and true actions."""
+  g = torch.Generator().manual_seed(seed)
+  pred = torch.randn(b, n + 1, generator=g) * 3.0
+  true = torch.rand(b, 1, a, generator=g) * 2 - 1
+  counter = torch.rand(b, n, a, generator=g) * 2 - 1
+  near = torch.rand(b, n, generator=g) < 0.33
+  counter = torch.where(near[..., None], true + 0.2 * (torch.rand(b, n, a, generator=g) - 0.5), counter)
+  return pred, counter, true
+
+
+def _oracle_cd(kind, pred, counter, true):
+  if kind == 'cd':
+    return olosses.cd(pred)
+  return olosses.clipped_cd(pred, counter, true.expand_as(counter), soft=kind == 'soft_clipped_cd')[0]
+
+
+@pytest.mark.parametrize('kind', ['cd', 'clipped_cd', 'soft_clipped_cd'])
+@pytest.mark.parametrize('b,n,a', [(7, 32, 3), (512, 256, 2), (2, 1, 28)])
+def test_cd_loss_kernel_matches_oracle(kind, b, n, a):
+  """ibc_cd_loss against the oracle restatement of ebm_loss.cd / clipped_cd (loss and autograd
+  d loss / d predictions).  fp32 sums: 1e-5."""
+  from ibc_b200 import engine as eng
+  pred, counter, true = _cd_case(b, n, a, seed=b + n)
+  p64 = pred.double().requires_grad_(True)
+  want = _oracle_cd(kind, p64, counter.double(), true.double())
+  (want_grad,) = torch.autograd.grad(want.sum() / b, p64)
+  combined = torch.cat([counter, true], dim=1).reshape(-1, a).contiguous()
+  loss, dpred = eng.cd_loss(pred.cuda(), combined.cuda(), kind, 1.0 / b, want_grad=True)
+  _close(loss, want.detach(), 1e-5, kind)
+  _close(dpred, want_grad, 1e-5, 'd ' + kind)
+  if kind != 'cd':
+    inside = (torch.linalg.norm(counter - true, dim=-1) ** 2 <= 0.2).float().mean()
+    assert 0.1 < float(inside) < 0.9, 'test is vacuous: the threshold never / always applies'
+
+
+@pytest.mark.parametrize('kind', ['cd', 'clipped_cd', 'soft_clipped_cd'])
+@pytest.mark.parametrize('spec,precision,tol', [(omlp.MLPSpec(16, 2, 64, 4), 0, 5e-4),
+                                                (omlp.MLPSpec(20, 2, 128, 4), 1, 1e-2)], ids=str)
+def test_train_grads_with_cd_losses_match_oracle_autograd(kind, spec, precision, tol):
+  """ibc_train_grads with ibc_loss_cfg.ebm_loss_type (ImplicitBCAgent(ebm_loss_type=...),
+  ibc_agent.py:303-335) against fp64 autograd of the oracle: the fp32 kernels and the layer-fused
+  tcgen05 path (its loss kernel feeds the fp16-scaled block-major backward)."""
+  from ibc_b200 import engine as eng
+  e, flat = _engine(spec, precision=precision)
+  b, n = 8, 15
+  obs, _ = _data(spec, b, n + 1, seed=31)
+  _, counter, true = _cd_case(b, n, spec.act_dim, seed=5)
+  act = torch.cat([counter, true], dim=1).reshape(-1, spec.act_dim).contiguous()
+  theta = flat.double().clone().requires_grad_(True)
+  obs_t = torch.repeat_interleave(obs, n + 1, 0).double()
+  pred = omlp.energy(theta, spec, obs_t, act.double()).reshape(b, n + 1)
+  per = _oracle_cd(kind, pred, counter.double(), true.double())
+  gb = 16
+  (want_grad,) = torch.autograd.grad(per.sum() / gb, theta, retain_graph=True)
+  dpred_l1 = float(torch.autograd.grad(per.sum() / gb, pred)[0].abs().sum())
+  we_norm = float(omlp.unpack(flat.double(), spec)['we'].norm())
+  emul_grad = None
+  if precision == 1:
+    # the same calibration as test_train_grads_tf32_match_oracle_autograd: the GPU may be at most
+    # 1.5x as far from fp64 as the oracle's own tf32 emulation, plus 5e-3 (the cd cotangents
+    # cancel within every observation, so the tf32 error is large against what is left)
+    from oracle import tf32_emul
+    theta2 = flat.double().clone().requires_grad_(True)
+    pred2 = tf32_emul.energy(theta2, spec, obs_t, act.double()).reshape(b, n + 1)
+    (emul_grad,) = torch.autograd.grad(_oracle_cd(kind, pred2, counter.double(), true.double()).sum() / gb,
+                                       theta2)
+  cfg = eng.loss_cfg(1.0, False, ebm_loss_type=kind)
+  per_g, _, en_g, grads = e.train_grads(obs.cuda(), act.cuda(), n, cfg, gb, want_energies=True)
+  assert e.kernel_status() == 0
+  _close(en_g, pred.detach().reshape(-1), FP32_TOL if precision == 0 else 4 * TF32_TOL, 'energies')
+  # the soft form's |residual| amplifies the tf32 energy error of the rows inside the threshold
+  _close(per_g, per.detach(), 1e-4 if precision == 0 else 2e-2, 'per-example loss')
+  grms = float(want_grad.pow(2).mean().sqrt())
+  for name, off, shape in omlp.param_layout(spec):
+    cnt = math.prod(shape)
+    w = want_grad[off:off + cnt]
+    g = grads[off:off + cnt].double().cpu()
+    denom = float(w.norm()) + 1e-2 * grms * math.sqrt(cnt)
+    # d/d be = sum_r dE[r] and d/d b2 of the top block = we * sum_r dE[r]: with cd the
+    # cotangents of a row sum to zero exactly, so compare against the size of the terms
+    if name == 'be':
+      denom = dpred_l1
+    elif name == 'b2_%d' % (spec.num_blocks - 1):
+      denom = dpred_l1 * we_norm
+    rel = float((g - w).norm()) / denom
+    bound = tol
+    if emul_grad is not None:
+      bound = max(tol, 1.5 * float((emul_grad[off:off + cnt] - w).norm()) / denom + 5e-3)
+    assert rel < bound, (name, rel, bound)

@@ -410,3 +410,19 @@ def test_spectral_norm_against_torch_power_iteration():
   top = torch.linalg.svdvals(w)[0]
   assert torch.allclose(torch.linalg.svdvals(w_bar)[0], torch.ones((), dtype=torch.float64), atol=1e-9)
   assert torch.allclose(w / top, w_bar, atol=1e-9)
+
+
+def test_cd_losses_known_answers():
+  """ibc/losses/ebm_loss.py:51-66, 109-148 by hand: true action (0, 0); counter examples at squared
+  distance 1 (outside the 0.2 threshold), 0.01 (inside), 0.25 (outside)."""
+  pred = torch.tensor([[3.0, 5.0, 7.0, 1.0]], dtype=torch.float64)
+  assert olosses.cd(pred).tolist() == [4.0]                          # mean(3, 5, 7) - 1
+  counter = torch.tensor([[[1.0, 0.0], [0.1, 0.0], [0.5, 0.0]]], dtype=torch.float64)
+  true = torch.zeros(1, 3, 2, dtype=torch.float64)
+  loss, dbg = olosses.clipped_cd(pred, counter, true, soft=False)
+  assert abs(float(loss) - 8.0 / 3.0) < 1e-12                        # ((3-1) + 0 + (7-1)) / 3
+  assert abs(float(dbg['fraction_outside_threshold']) - 2.0 / 3.0) < 1e-12
+  loss, dbg = olosses.clipped_cd(pred, counter, true, soft=True)
+  soft = abs((1.0 - 5.0) - 0.1 ** 2) / 3.0                           # |(data - samp) - err| inside
+  assert abs(float(loss) - (8.0 / 3.0 + soft)) < 1e-12
+  assert abs(float(dbg['soft_loss']) - soft) < 1e-12 and abs(float(dbg['cd_loss']) - 8.0 / 3.0) < 1e-12
