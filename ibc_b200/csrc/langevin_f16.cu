@@ -517,62 +517,72 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_f16_kernel(LangevinF16Pa
 // [W/8][AP][8] action rows of Wp for dE/dact.  Element (n, k) of a K-major image sits at
 // ((k / 8) * N + n) * 8 + k % 8.
 // Elements [lo, hi) of the buffer, without [hole_lo, hole_lo + hole_len).
-__device__ __forceinline__ float pack16_value(const float* __restrict__ P, const Layout& L,
-                                              const Packed16Layout& pl, int64_t i) {
-  const int W = L.W;
-  const int64_t WW = (int64_t)W * W;
-  float v = 0.f;
-  if (i < pl.fwd) {                       // step-0 operand: B[n][k] = Wp[O + k][n]
-    const int64_t e = i - pl.p0;
-    const int kq = (int)(e & 7), n = (int)((e >> 3) % W), kc = (int)((e >> 3) / W);
-    const int k = kc * 8 + kq;
-    v = (k < L.A) ? P[L.wp + (int64_t)(L.O + k) * W + n] : 0.f;
-  } else if (i < pl.rev) {                // forward layer m + bias slice of step m + 1
-    const int64_t e = i - pl.fwd;
-    const int64_t blk = WW + 16 * W;
-    const int m = (int)(e / blk);
-    const int64_t r = e - (int64_t)m * blk;
-    const int j = m >> 1;
-    if (r < WW) {
-      const int kq = (int)(r & 7), n = (int)((r >> 3) % W), kc = (int)((r >> 3) / W);
-      const int64_t base = (m & 1) ? L.w2(j) : L.w1(j);
-      v = P[base + (int64_t)(kc * 8 + kq) * W + n];
-    } else {
-      const int rb = (int)(r - WW);
-      const int kq = rb & 7, n = (rb >> 3) % W, kc = (rb >> 3) / W;
-      const float b = (m & 1) ? P[L.b2(j) + n] : P[L.b1(j) + n];
-      const float hi = __half2float(__float2half_rn(b));
-      v = (kc == 0 && kq == 0) ? hi : ((kc == 0 && kq == 1) ? b - hi : 0.f);
-    }
-  } else if (i < pl.revp) {               // reverse layers: B[n = in][k = out] = W[in][out]
-    const int64_t e = i - pl.rev;
-    const int m = (int)(e / WW);          // 0: W2_{nb-1}, 1: W1_{nb-1}, 2: W2_{nb-2}, ...
-    const int64_t r = e - (int64_t)m * WW;
-    const int oq = (int)(r & 7), irow = (int)((r >> 3) % W), oc = (int)((r >> 3) / W);
-    const int j = L.nb - 1 - (m >> 1);
-    const int64_t base = (m & 1) ? L.w1(j) : L.w2(j);
-    v = P[base + (int64_t)irow * W + (oc * 8 + oq)];
-  } else {                                // dE/dact operand: B[n = a][k = w] = Wp[O + a][w]
-    const int64_t e = i - pl.revp;
-    const int wq = (int)(e & 7), a = (int)((e >> 3) % pl.AP), wc = (int)((e >> 3) / pl.AP);
-    v = (a < L.A) ? P[L.wp + (int64_t)(L.O + a) * W + (wc * 8 + wq)] : 0.f;
-  }
-  return v;
-}
-
-// Eight consecutive halves per thread (every image and every range boundary is a multiple of
-// eight: one (n, k / 8) group of a K-major image): eight independent loads, one 16-byte store.
+// Eight consecutive halves per thread -- every image and every range boundary is a multiple of
+// eight, and a group is one (n, k / 8) cell of a K-major image: the source of its eight values is
+// one base address and one stride (W for the forward images, 1 for the transposed ones), worked
+// out once; eight independent loads, one 16-byte store.
 __global__ void pack16_kernel(const float* __restrict__ P, Layout L, Packed16Layout pl,
                               __half* __restrict__ out, int64_t lo, int64_t hi, int64_t hole_lo,
                               int64_t hole_len) {
+  const int W = L.W;
+  const int64_t WW = (int64_t)W * W;
   const int64_t groups = (hi - lo - hole_len) >> 3;
   for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups;
        g += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t j = lo + (g << 3);
-    const int64_t i = j < hole_lo ? j : j + hole_len;
+    const int64_t j0 = lo + (g << 3);
+    const int64_t i = j0 < hole_lo ? j0 : j0 + hole_len;
     float v[8];
+    const float* src = nullptr;
+    int64_t stride = 0;
+    int valid = 8;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = pack16_value(P, L, pl, i + q);
+    for (int q = 0; q < 8; ++q) v[q] = 0.f;
+    if (i < pl.fwd) {                       // step-0 operand: B[n][k] = Wp[O + k][n]
+      const int64_t c = (i - pl.p0) >> 3;
+      const int n = (int)(c % W), k0 = (int)(c / W) * 8;
+      src = P + L.wp + (int64_t)(L.O + k0) * W + n;
+      stride = W;
+      valid = min(max(L.A - k0, 0), 8);
+    } else if (i < pl.rev) {                // forward layer m + bias slice of step m + 1
+      const int64_t e = i - pl.fwd;
+      const int64_t blk = WW + 16 * W;
+      const int m = (int)(e / blk);
+      const int64_t r = e - (int64_t)m * blk;
+      const int j = m >> 1;
+      if (r < WW) {
+        const int64_t c = r >> 3;
+        const int n = (int)(c % W), k0 = (int)(c / W) * 8;
+        src = P + ((m & 1) ? L.w2(j) : L.w1(j)) + (int64_t)k0 * W + n;
+        stride = W;
+      } else {                              // (hi, lo, 0 ...) of the bias, first K chunk only
+        const int64_t c = (r - WW) >> 3;
+        const int n = (int)(c % W), kc = (int)(c / W);
+        valid = 0;
+        if (kc == 0) {
+          const float bv = (m & 1) ? P[L.b2(j) + n] : P[L.b1(j) + n];
+          const float hi16 = __half2float(__float2half_rn(bv));
+          v[0] = hi16;
+          v[1] = bv - hi16;
+        }
+      }
+    } else if (i < pl.revp) {               // reverse layers: B[n = in][k = out] = W[in][out]
+      const int64_t e = i - pl.rev;
+      const int m = (int)(e / WW);          // 0: W2_{nb-1}, 1: W1_{nb-1}, 2: W2_{nb-2}, ...
+      const int64_t c = (e - (int64_t)m * WW) >> 3;
+      const int irow = (int)(c % W), o0 = (int)(c / W) * 8;
+      const int j = L.nb - 1 - (m >> 1);
+      src = P + ((m & 1) ? L.w1(j) : L.w2(j)) + (int64_t)irow * W + o0;
+      stride = 1;
+    } else {                                // dE/dact operand: B[n = a][k = w] = Wp[O + a][w]
+      const int64_t c = (i - pl.revp) >> 3;
+      const int a = (int)(c % pl.AP), w0 = (int)(c / pl.AP) * 8;
+      src = P + L.wp + (int64_t)(L.O + a) * W + w0;
+      stride = 1;
+      valid = a < L.A ? 8 : 0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (q < valid) v[q] = src[q * stride];
     __align__(16) __half2 h2[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) h2[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
