@@ -68,23 +68,38 @@ class PeerReducer:
     # [gradient, even steps | gradient, odd steps | flags (64 ints)]
     stride = (numel * 4 + 255) // 256 * 256
     self._bytes = 2 * stride + 256
+    # Every rank runs the SAME collectives whatever fails locally (one all_gather_object here, one
+    # all_reduce in `create`): a rank that cannot allocate or map still takes part, publishes
+    # None and raises afterwards, so that nobody is left waiting in a collective.
+    self._base, self._opened = None, []
     with torch.cuda.device(device):
       base = ctypes.c_void_p()
       handle = ctypes.create_string_buffer(64)
-      _lib.check(lib.ibc_peer_alloc(self._bytes, ctypes.byref(base), handle))
-      self._base = base.value
+      mine, failure = None, None
+      try:
+        _lib.check(lib.ibc_peer_alloc(self._bytes, ctypes.byref(base), handle))
+        self._base = base.value
+        mine = bytes(handle.raw)
+      except Exception as e:                    # noqa: BLE001
+        failure = e
       everyone = [None] * self.world
-      dist.all_gather_object(everyone, bytes(handle.raw))
-      self._opened = []
+      dist.all_gather_object(everyone, mine)
+      if failure is not None or any(hd is None for hd in everyone):
+        self._release()
+        raise failure or RuntimeError('a peer could not allocate its buffers')
       bases = []
-      for r, hd in enumerate(everyone):
-        if r == self.rank:
-          bases.append(self._base)
-          continue
-        q = ctypes.c_void_p()
-        _lib.check(lib.ibc_peer_open(ctypes.create_string_buffer(hd, 64), ctypes.byref(q)))
-        self._opened.append(q.value)
-        bases.append(q.value)
+      try:
+        for r, hd in enumerate(everyone):
+          if r == self.rank:
+            bases.append(self._base)
+            continue
+          q = ctypes.c_void_p()
+          _lib.check(lib.ibc_peer_open(ctypes.create_string_buffer(hd, 64), ctypes.byref(q)))
+          self._opened.append(q.value)
+          bases.append(q.value)
+      except Exception:
+        self._release()
+        raise
     self.bufs = [_device_view(self._base + k * stride, numel, torch.float32, device, self) for k in range(2)]
     arr = ctypes.c_void_p * 8
     pad = [None] * (8 - self.world)
@@ -94,7 +109,15 @@ class PeerReducer:
     self.status = torch.zeros(1, device=device, dtype=torch.int32)
     self.epoch = 0
     torch.cuda.synchronize(device)
-    dist.barrier()
+    # (no barrier here: `create` ends with an all_reduce on every rank, which is one)
+
+  def _release(self):
+    lib = self._lib.load()
+    for q in self._opened:
+      lib.ibc_peer_close(q, 0)
+    if self._base:
+      lib.ibc_peer_close(self._base, 1)
+    self._base, self._opened, self.bufs = None, [], []
 
   def close(self):
     """Unmaps the peers' buffers and frees this rank's (all ranks, after their last step)."""
@@ -102,10 +125,7 @@ class PeerReducer:
       lib = self._lib.load()
       torch.cuda.synchronize()
       dist.barrier()                 # no peer still reads this rank's buffers
-      for q in self._opened:
-        lib.ibc_peer_close(q, 0)
-      lib.ibc_peer_close(self._base, 1)
-      self._base, self._opened, self.bufs = None, [], []
+      self._release()
 
   @classmethod
   def create(cls, numel: int, device):
@@ -122,8 +142,12 @@ class PeerReducer:
       ok.zero_()
       import warnings
       warnings.warn('peer-memory all-reduce unavailable (%s): using NCCL' % (e,))
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN)    # all ranks take the same path
-    return red if float(ok) > 0 else None
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)    # all ranks take the same path (and a barrier)
+    if float(ok) > 0:
+      return red
+    if red is not None:                          # a peer failed: give the buffers back
+      red._release()
+    return None
 
   def buffer(self, step: int) -> torch.Tensor:
     """The gradient buffer of this step (its parity): what train_grads writes."""
