@@ -224,6 +224,8 @@ int info_nce(ibc_handle* h, const float* pred, int64_t B, int64_t n1, float temp
              unsigned int* dpred_absmax) {
   if (B <= 0 || n1 <= 0) IBC_FAIL(h, IBC_ERR_INVALID, "info_nce: bad shape");
   if (temperature <= 0.f) IBC_FAIL(h, IBC_ERR_INVALID, "info_nce: temperature must be > 0");
+  // (one warp per example with the row in registers was tried: 10 us against this kernel's 7 for
+  // 512 rows of 257 -- nine serial exp / IEEE divisions / log per lane cost more than the barriers)
   info_nce_kernel<<<(unsigned)B, 128, 0, s>>>(pred, (int)n1, temperature, grad_scale, loss, dpred,
                                               dpred_absmax);
   IBC_LAUNCH_CHECK(h);

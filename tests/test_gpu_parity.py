@@ -484,7 +484,9 @@ def test_langevin_f16_chain_tracks_the_tf32_chain(monkeypatch):
 
 # ------------------------------ losses -------------------------------------------
 @pytest.mark.parametrize('b,n1,temp,scale', [(512, 257, 1.0, 1.0), (16, 9, 0.5, 20.0),
-                                             (3, 2, 1.0, 50.0)])
+                                             (3, 2, 1.0, 50.0),
+                                             # long rows: several strides of the block
+                                             (7, 1000, 2.0, 5.0), (5, 2049, 1.0, 3.0)])
 def test_info_nce(b, n1, temp, scale):
   from ibc_b200 import engine as eng
   g = torch.Generator().manual_seed(b)
