@@ -395,19 +395,35 @@ __global__ void __launch_bounds__(kW) first_layer_grads_tiled_kernel(
   int64_t cur_b = r0 / n1;
   int64_t next_edge = (cur_b + 1) * n1;
   const float* sg = reinterpret_cast<const float*>(s_g) + (w >> 2) * (33 * 4) + (w & 3);
+  // the next 32 rows travel (L2 / HBM -> registers) while the current 32 are being summed: a
+  // block is a chain of four load -> barrier -> sum -> barrier rounds, and the whole grid is one
+  // resident wave, so the chain's latency is the kernel's duration
+  float4 pre[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = i * kW + w, c = idx >> 5, rr = idx & 31;
+    pre[i] = tile[c * 128 + rr];
+  }
   for (int64_t rb = r0; rb < r1; rb += 32) {
     const int nr = (int)min((int64_t)32, r1 - rb);
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int idx = i * kW + w, c = idx >> 5, rr = idx & 31;
-      s_g[c * 33 + rr] = tile[c * 128 + (int)(rb - r0) + rr];
+      s_g[c * 33 + rr] = pre[i];
     }
     for (int i = w; i < nr * AMAX; i += kW) {
       const int k = i / AMAX, a = i % AMAX;
       s_act[i] = (a < A) ? act[(rb + k) * A + a] : 0.f;
     }
     __syncthreads();
+    if (rb + 32 < r1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = i * kW + w, c = idx >> 5, rr = idx & 31;
+        pre[i] = tile[c * 128 + (int)(rb + 32 - r0) + rr];
+      }
+    }
     for (int k = 0; k < nr; ++k) {
       if (rb + k == next_edge) {
         atomicAdd(gsum + cur_b * kW + w, gs);
