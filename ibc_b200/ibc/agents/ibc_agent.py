@@ -243,10 +243,17 @@ class ImplicitBCAgent(BehavioralCloningAgent):
       # Keras MSE(NONE) -> [B, N]; aggregate_losses averages the extra axis then
       # sums / global batch (ibc_agent.py:182-189).  All groups have the same size,
       # so that is sum((c - a)^2) / (N * A * global_batch): two kernels instead of six.
-      losses_dict['mse_counter_examples'] = _scaled_sq_diff_sum(
-          counter_example_actions, expanded_actions,
-          1.0 / (float(global_batch) * counter_example_actions.shape[1]
-                 * counter_example_actions.shape[2]))
+      mse_scale = 1.0 / (float(global_batch) * counter_example_actions.shape[1]
+                         * counter_example_actions.shape[2])
+      if isinstance(total_loss, _EarlyScalar):
+        # a logged scalar of inputs that exist before the forward: on the loss stream, beside
+        # the backward, instead of four small launches between the backward and Adam
+        losses_dict['mse_counter_examples'] = self._side_scalar(
+            lambda: _scaled_sq_diff_sum(counter_example_actions, expanded_actions, mse_scale),
+            (counter_example_actions, expanded_actions))
+      else:
+        losses_dict['mse_counter_examples'] = _scaled_sq_diff_sum(
+            counter_example_actions, expanded_actions, mse_scale)
     self._chain_metrics(chain_data, losses_dict)
     self.last_losses_dict = losses_dict
     if training:
@@ -282,6 +289,25 @@ class ImplicitBCAgent(BehavioralCloningAgent):
     loss.record_stream(main)
     main.wait_stream(side)             # later uses of the device value on the main stream
     return _EarlyScalar(loss, ring, slot, gen, ev)
+
+  def _side_scalar(self, fn, inputs):
+    """fn() (a CUDA scalar of `inputs`) computed on the loss stream of this step -- which already
+    waits behind the step's loss kernel (_early_loss) -- with the same pinned read-out."""
+    from ibc_b200 import parallel
+    dev = inputs[0].device
+    side = parallel._side_stream(dev)
+    main = torch.cuda.current_stream(dev)
+    slot, gen = self._loss_ring.take()
+    with torch.cuda.stream(side):
+      val = fn()
+      self._loss_ring.host[slot:slot + 1].copy_(val.reshape(1), non_blocking=True)
+      ev = torch.cuda.Event()
+      ev.record(side)
+    for t in inputs:
+      t.record_stream(side)
+    val.record_stream(main)
+    main.wait_stream(side)             # later uses of the device value on the main stream
+    return _EarlyScalar(val, self._loss_ring, slot, gen, ev)
 
   @staticmethod
   def _chain_metrics(chain_data, losses_dict):
