@@ -465,46 +465,54 @@ class ImplicitBCAgent(BehavioralCloningAgent):
   # the caller reads it); 'sync' raises inside the offending step.
   check_numerics = 'deferred'
 
-  def _check_finite(self, loss):
+  def _check_finite(self, loss, extra_host=None):
+    """extra_host: a pinned one-element tensor a kernel of this step writes (the peer all-reduce's
+    reduced d/d be): looked at together with the loss, behind an event recorded now."""
     if self.check_numerics == 'sync':
       if not math.isfinite(float(loss)):
         raise FloatingPointError('Loss is inf or nan')
+      if extra_host is not None:
+        torch.cuda.current_stream().synchronize()
+        if not math.isfinite(float(extra_host[0])):
+          raise FloatingPointError('Loss is inf or nan')
       return
     # Deferred: the loss is copied to pinned host memory behind the step's kernels and
     # looked at (a plain host read, no CUDA call, no stream sync) once its event has
     # completed -- typically while the next step is being submitted.
     pending = getattr(self, '_pending_finite', None)
     if pending is not None:
-      host, ev = pending
+      hosts, ev = pending
       if not ev.query():
         return                        # still in flight: keep waiting on the older one
       self._pending_finite = None
-      if not math.isfinite(float(host[0])):
+      if not all(math.isfinite(float(h[0])) for h in hosts):
         raise FloatingPointError('Loss is inf or nan')
-    else:
-      host = None
     if isinstance(loss, _EarlyScalar) and loss._ring.gen[loss._slot] == loss._gen:
       # the early read-out already copies this loss to pinned memory: look at that copy
-      self._pending_finite = (loss._ring.host[loss._slot:loss._slot + 1], loss._ev)
+      hosts, ev = [loss._ring.host[loss._slot:loss._slot + 1]], loss._ev
+      if extra_host is not None:
+        hosts.append(extra_host)
+        ev = torch.cuda.Event()
+        ev.record()
+      self._pending_finite = (hosts, ev)
       return
+    host = getattr(self, '_finite_host', None)
     if host is None:
-      host = getattr(self, '_finite_host', None)
-      if host is None:
-        host = torch.empty(1, dtype=torch.float32, pin_memory=True)
-        self._finite_host = host
+      host = torch.empty(1, dtype=torch.float32, pin_memory=True)
+      self._finite_host = host
     host.copy_(loss.detach().reshape(1), non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
-    self._pending_finite = (host, ev)
+    self._pending_finite = ([host] + ([extra_host] if extra_host is not None else []), ev)
 
   def flush_checks(self):
     """Look at the last deferred finiteness check (call when training ends)."""
     pending = getattr(self, '_pending_finite', None)
     if pending is not None:
-      host, ev = pending
+      hosts, ev = pending
       ev.synchronize()
       self._pending_finite = None
-      if not math.isfinite(float(host[0])):
+      if not all(math.isfinite(float(h[0])) for h in hosts):
         raise FloatingPointError('Loss is inf or nan')
 
   def _peer_reducer(self):
@@ -527,9 +535,10 @@ class ImplicitBCAgent(BehavioralCloningAgent):
       self._grads = peer.buffer(step)
       loss_info, grads = self._loss(experience, weights=weights, training=True, draws=draws)
       self._optimizer.apply_gradients_peer(self.cloning_network, peer, step)
-      # d/d be summed over ALL replicas is non-finite as soon as any replica's loss is:
-      # every rank sees it (0 * (inf | nan) = nan)
-      self._check_finite(loss_info.loss + peer.tail[0] * 0.0)
+      # d/d be summed over ALL replicas is non-finite as soon as any replica's loss is: every
+      # rank sees it in the reduced last gradient entry, which the kernel writes to pinned host
+      # memory (no probe kernels between this step and the next)
+      self._check_finite(loss_info.loss, extra_host=peer.tail)
       self.train_step_counter += 1
       return loss_info
     loss_info, grads = self._loss(experience, weights=weights, training=True, draws=draws)

@@ -105,7 +105,9 @@ class PeerReducer:
     pad = [None] * (8 - self.world)
     self._g = [arr(*([x + k * stride for x in bases] + pad)) for k in range(2)]
     self._f = arr(*([x + 2 * stride for x in bases] + pad))
-    self.tail = torch.zeros(1, device=device, dtype=torch.float32)
+    # the reduced last gradient entry lands in pinned HOST memory (device-addressable): the
+    # caller's finiteness check reads it without a copy or a probe kernel
+    self.tail = torch.zeros(1, dtype=torch.float32, pin_memory=True)
     self.status = torch.zeros(1, device=device, dtype=torch.int32)
     self.epoch = 0
     torch.cuda.synchronize(device)

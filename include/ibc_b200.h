@@ -208,8 +208,8 @@ int ibc_uniform_actions(const float* u, int64_t rows, int32_t A,
  * gradient buffer of this step's parity and its flag array (>= world ints, zero at start) as
  * mapped into THIS process (CUDA IPC); epoch increases by one per call on every rank.  The kernel
  * publishes the epoch to every peer, waits (bounded: status 6001) for all peers, sums the
- * gradients in rank order and applies Adam to the local replica; tail_out (optional) receives
- * the reduced last entry.
+ * gradients in rank order and applies Adam to the local replica; tail_out (optional; device or
+ * pinned host memory) receives the reduced last entry.
  * ibc_peer_alloc makes one zeroed device allocation on the current device and writes its 64-byte
  * CUDA IPC handle to handle64; ibc_peer_open maps a peer process's handle into the current
  * device's address space (peer access over NVLink); ibc_peer_close unmaps (owned = 0) or frees
