@@ -103,7 +103,7 @@ class ClockSampler:
        'clocks_event_reasons.sw_power_cap')
 
   def __init__(self, index):
-    self.index, self.rows, self.proc = index, [], None
+    self.index, self.rows, self.proc, self.first = index, [], None, 0
 
   def start(self):
     try:
@@ -115,6 +115,10 @@ class ClockSampler:
       self.t.start()
     except Exception:
       self.proc = None
+
+  def mark(self):
+    """Rows printed so far (start-up, warm-up) are not part of the report."""
+    self.first = len(self.rows)
 
   def _read(self):
     for line in self.proc.stdout:
@@ -131,7 +135,7 @@ class ClockSampler:
       self.proc.kill()
     sm, mx, reasons = [], [], set()
     names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-    for r in self.rows:
+    for r in self.rows[self.first:]:
       try:
         sm.append(float(r[0])); mx.append(float(r[1]))
         for nm, v in zip(names, r[2:6]):
@@ -238,11 +242,22 @@ def run_b200(args):
   def step_dev(i):
     agent.train((dev_batches[i % nb], ()))
 
-  for i in range(args.warmup):
-    step_dev(i)
+  # W warm-up steps as asked, and never fewer than 300: the step's temporaries pass between two
+  # streams (record_stream), so the caching allocator keeps growing -- cudaMalloc, a device-wide
+  # stall, on whichever rank needs it, with every other rank waiting in the gradient sum -- for
+  # a few hundred steps (4 GPUs, 200 timed steps: 0.533 ms/step after 20 warm-up steps, 0.479
+  # after 400; `sustained` 0.477-0.484 either way)
+  warm_run = max(args.warmup, 300)
+  # nvidia-smi starts BEFORE the warm-up (its start-up -- NVML initialisation inside the driver --
+  # stalled the first launches of a 20-step timed region by 0.8 ms); only the rows it prints
+  # from the start of the timed region on are used
   sampler = ClockSampler(local)
   if rank == 0:
     sampler.start()
+  for i in range(warm_run):
+    step_dev(i)
+  torch.cuda.synchronize()
+  sampler.mark()
   _lib.reset_launch_count()
   t_dev = max_over_ranks(timed(step_dev, args.steps, barrier))
   launches = _lib.launch_count()
@@ -363,7 +378,8 @@ def run_b200(args):
     achieved = step_flops / (t_dev / args.steps) / 1e12
     result = {
         'metric': 'ebm_train_energy_evals_per_s', 'value': evals / t_dev, 'unit': 'energy evals/s',
-        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'warmup_steps_run': warm_run,
+        'ms_per_step': ms,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'tf32 (tcgen05 kind::tf32 operands, fp32 accumulate; first/last layer and loss in fp32)', 'data': 'synthetic',
         'config': workload_config(c),
