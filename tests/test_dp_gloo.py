@@ -45,6 +45,10 @@ def _worker(rank, world, port, out):
   parallel.allreduce_gradients(local)
   full = _grads(flat, spec, obs, act, n, b)
   err = float((local - full).abs().max() / full.abs().max())
+  # the peer-memory reducer is for NCCL ranks on CUDA devices: under gloo / on the CPU `create`
+  # answers None on every rank (no collective is left half entered) and the agent keeps
+  # allreduce_gradients + ibc_adam_step
+  assert parallel.PeerReducer.create(flat.numel(), torch.device('cpu')) is None
   if rank == 0:
     with open(out, 'w') as f:
       f.write(repr(err))
@@ -65,3 +69,4 @@ def test_parallel_helpers_single_process():
   t = torch.ones(3)
   assert parallel.allreduce_gradients(t) is t
   assert parallel.shard_observations(10) == (0, 10)
+  assert parallel.PeerReducer.create(100, torch.device('cpu')) is None      # single replica
