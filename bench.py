@@ -254,6 +254,13 @@ def run_b200(args):
   sampler = ClockSampler(local)
   if rank == 0:
     sampler.start()
+  # the interpreter's start-up heap (torch, numpy: ~10^6 objects) out of the cyclic collector's
+  # way: a full collection over it is a pause of tens of milliseconds on one rank, which every
+  # other rank of a data-parallel run then waits for.  The collector itself stays on.  (Before
+  # the warm-up, not after it: a host pause in front of the timed region idles the GPU.)
+  import gc
+  gc.collect()
+  gc.freeze()
   for i in range(warm_run):
     step_dev(i)
   torch.cuda.synchronize()
