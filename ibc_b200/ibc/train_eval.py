@@ -214,6 +214,11 @@ def train_eval(task='PARTICLE', root_dir=None, dataset_path=None, loss_type='ebm
   step = load_checkpoint(root_dir, agent, data)          # resume (get_learner.py:60-76)
   if step:
     log(json.dumps({'resumed_from_step': step}))
+  # the interpreter's start-up heap out of the cyclic collector's way: a full collection over it is
+  # a pause of tens of milliseconds, which in a data-parallel run every other rank waits for
+  import gc
+  gc.collect()
+  gc.freeze()
   t0 = time.perf_counter()
   info = None
   while step < num_iterations:

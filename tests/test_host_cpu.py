@@ -145,3 +145,22 @@ def test_specs_tile_and_flatten():
   assert flat.tolist() == [[10., 11., 0., 1.], [12., 13., 2., 3.]]     # sorted keys: a then b
   t = specs.tile_batch(torch.tensor([[0.], [1.]]), 3)
   assert t.reshape(-1).tolist() == [0., 0., 0., 1., 1., 1.]
+
+
+def test_clipped_cd_debug_scalars_match_oracle():
+  """The logged scalars of clipped_cd (ibc/losses/ebm_loss.py:138-147) are plain tensor ops in
+  the host mirror (ibc_b200/ibc/losses/ebm_loss.py::clipped_cd_debug): against the oracle."""
+  import torch
+  from ibc_b200.ibc.losses import ebm_loss
+  from oracle import losses as olosses
+  g = torch.Generator().manual_seed(3)
+  pred = torch.randn(6, 10, generator=g, dtype=torch.float64)
+  true = (torch.rand(6, 1, 2, generator=g, dtype=torch.float64) - 0.5).expand(6, 9, 2)
+  counter = true + (torch.rand(6, 9, 2, generator=g, dtype=torch.float64) - 0.5) * 1.2
+  for soft in (False, True):
+    _, want = olosses.clipped_cd(pred, counter, true, soft)
+    got = ebm_loss.clipped_cd_debug(pred, counter, true, soft)
+    assert set(got) == set(want)
+    for k in want:
+      assert abs(float(got[k]) - float(want[k])) < 1e-12, k
+  assert 0.0 < float(want['fraction_outside_threshold']) < 1.0
